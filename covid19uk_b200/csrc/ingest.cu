@@ -1,0 +1,200 @@
+// K1: state reconstruction (a1) and events-only caches.
+//
+//  * seir_state_kernel    -- gemlib.util.compute_state (call sites inference.py:500-510): one warp per
+//                            (chain, metapopulation) row, integer-exact warp-scan over time.
+//  * seir_ingest_kernel   -- events f64 [B,M,T,3] -> compact int32 day slabs [B][T][Mp] of the three
+//                            event counts and of S,E,I (exclusive cumsum over time), plus
+//                            every parameter-free piece of the log-pmf: sum of log binomial
+//                            coefficients, the E->I sufficient statistics and the per-day I->R
+//                            sufficient statistics (exact integer sums).
+#include "seir_internal.cuh"
+
+// ------------------------------------------------------------------------------------------------
+// compute_state: one warp per (b, m) row; lanes stride over days; 3 inclusive shuffle scans / 32 days
+// ------------------------------------------------------------------------------------------------
+__global__ void __launch_bounds__(256) seir_state_kernel(int M, int T, long long rows, const int* __restrict__ init, int initStride,
+                                                         const double* __restrict__ events, double* __restrict__ state) {
+  const int lane = threadIdx.x & 31;
+  const long long row = (long long)blockIdx.x * (blockDim.x >> 5) + (threadIdx.x >> 5);
+  if (row >= rows) return;
+  const int m = (int)(row % M);
+  const double* ev = events + row * (long long)T * 3;
+  double* st = state + row * (long long)T * 4;
+  long long c0 = 0, c1 = 0, c2 = 0;  // events before the current 32-day block
+  const long long S0 = init[m * initStride + 0], E0 = init[m * initStride + 1], I0 = init[m * initStride + 2],
+                  R0 = init[m * initStride + 3];
+  for (int t0 = 0; t0 < T; t0 += 32) {
+    const int t = t0 + lane;
+    long long y0 = 0, y1 = 0, y2 = 0;
+    if (t < T) {
+      y0 = __double2ll_rn(ev[t * 3 + 0]);
+      y1 = __double2ll_rn(ev[t * 3 + 1]);
+      y2 = __double2ll_rn(ev[t * 3 + 2]);
+    }
+    long long s0 = y0, s1 = y1, s2 = y2;
+#pragma unroll
+    for (int o = 1; o < 32; o <<= 1) {
+      const long long a0 = __shfl_up_sync(0xffffffffu, s0, o), a1 = __shfl_up_sync(0xffffffffu, s1, o),
+                      a2 = __shfl_up_sync(0xffffffffu, s2, o);
+      if (lane >= o) { s0 += a0; s1 += a1; s2 += a2; }
+    }
+    const long long e0 = c0 + s0 - y0, e1 = c1 + s1 - y1, e2 = c2 + s2 - y2;  // exclusive
+    if (t < T) {
+      double4 v;
+      v.x = (double)(S0 - e0);
+      v.y = (double)(E0 + e0 - e1);
+      v.z = (double)(I0 + e1 - e2);
+      v.w = (double)(R0 + e2);
+      *reinterpret_cast<double4*>(st + (long long)t * 4) = v;
+    }
+    c0 += __shfl_sync(0xffffffffu, s0, 31);
+    c1 += __shfl_sync(0xffffffffu, s1, 31);
+    c2 += __shfl_sync(0xffffffffu, s2, 31);
+  }
+}
+
+int seir_launch_state(const seir_model* m, int B, const double* d_events, double* d_state, cudaStream_t s) {
+  const long long rows = (long long)B * m->M;
+  const int wpb = 8;
+  const long long grid = (rows + wpb - 1) / wpb;
+  seir_state_kernel<<<(unsigned)grid, wpb * 32, 0, s>>>(m->M, m->T, rows, m->d_init, 4, d_events, d_state);
+  seir_count_launch(1);
+  return seir_cuda_check(cudaGetLastError(), "seir_state_kernel");
+}
+
+// ------------------------------------------------------------------------------------------------
+// ingest: CTA = (chain b, 32 metapopulations); 8 warps.  Per chunk of TC days:
+//   load  : warp-per-row coalesced f64 reads -> int32 tile in shared memory (row stride odd => the
+//           lane<->metapopulation reads below are bank-conflict free)
+//   scan  : lane <-> metapopulation; warp w owns days [w*seg, (w+1)*seg) of the chunk: segment sums,
+//           exchange through shared memory, then a serial pass that emits the day slabs -- every global
+//           store is a full 128-byte line (32 consecutive metapopulations of one day)
+// ------------------------------------------------------------------------------------------------
+template <int TC>
+__global__ void __launch_bounds__(256) seir_ingest_kernel(int M, int T, int Mp, const int* __restrict__ init,
+                                                          const double* __restrict__ lgtab, const double* __restrict__ events,
+                                                          int* __restrict__ yse, int* __restrict__ yei, int* __restrict__ yir,
+                                                          int* __restrict__ Sx, int* __restrict__ Ex, int* __restrict__ Ix,
+                                                          double* __restrict__ llc_part, long long* __restrict__ Yir,
+                                                          long long* __restrict__ Rir, long long* __restrict__ sumYei,
+                                                          long long* __restrict__ sumEres, int* __restrict__ flags) {
+  constexpr int STRIDE = TC * 3 + 1;
+  extern __shared__ int smem_i[];
+  int* ev = smem_i;                    // [32][STRIDE]
+  int* segsum = smem_i + 32 * STRIDE;  // [8][3][32]
+  __shared__ double red[32];
+
+  const int b = blockIdx.y, m0 = blockIdx.x * 32;
+  const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+  const int m = m0 + lane;
+  const bool live = m < M;
+  const int S0 = init[m * 4 + 0], E0 = init[m * 4 + 1], I0 = init[m * 4 + 2];
+  int carry0 = 0, carry1 = 0, carry2 = 0;
+  int bad = 0;
+  double acc = 0.0;
+  long long accYei = 0, accEres = 0;
+
+  for (int t0 = 0; t0 < T; t0 += TC) {
+    const int tc = min(TC, T - t0);
+    // ---- load ----
+    for (int r = warp; r < 32; r += 8) {
+      const int mm = m0 + r;
+      const double* src = events + (((size_t)b * M + mm) * T + t0) * 3;
+      for (int k = lane; k < tc * 3; k += 32) {
+        int iv = 0;
+        if (mm < M) {
+          const double v = __ldg(src + k);
+          iv = __double2int_rn(v);
+          if ((double)iv != v || iv < 0) bad |= 1;
+        }
+        ev[r * STRIDE + k] = iv;
+      }
+    }
+    __syncthreads();
+    // ---- segment sums ----
+    const int seg = (tc + 7) >> 3;
+    const int s0 = min(tc, warp * seg), s1 = min(tc, s0 + seg);
+    int a0 = 0, a1 = 0, a2 = 0;
+    for (int s = s0; s < s1; ++s) {
+      a0 += ev[lane * STRIDE + s * 3 + 0];
+      a1 += ev[lane * STRIDE + s * 3 + 1];
+      a2 += ev[lane * STRIDE + s * 3 + 2];
+    }
+    segsum[(warp * 3 + 0) * 32 + lane] = a0;
+    segsum[(warp * 3 + 1) * 32 + lane] = a1;
+    segsum[(warp * 3 + 2) * 32 + lane] = a2;
+    __syncthreads();
+    int c0 = carry0, c1 = carry1, c2 = carry2;
+    int tot0 = 0, tot1 = 0, tot2 = 0;
+#pragma unroll
+    for (int w = 0; w < 8; ++w) {
+      const int v0 = segsum[(w * 3 + 0) * 32 + lane], v1 = segsum[(w * 3 + 1) * 32 + lane], v2 = segsum[(w * 3 + 2) * 32 + lane];
+      if (w < warp) { c0 += v0; c1 += v1; c2 += v2; }
+      tot0 += v0; tot1 += v1; tot2 += v2;
+    }
+    // ---- emit ----
+    for (int s = s0; s < s1; ++s) {
+      const int y0 = ev[lane * STRIDE + s * 3 + 0], y1 = ev[lane * STRIDE + s * 3 + 1], y2 = ev[lane * STRIDE + s * 3 + 2];
+      const int S = S0 - c0, E = E0 + c0 - c1, I = I0 + c1 - c2;
+      const size_t o = ((size_t)b * T + (t0 + s)) * Mp + m;
+      yse[o] = y0; yei[o] = y1; yir[o] = y2;
+      Sx[o] = S; Ex[o] = E; Ix[o] = I;
+      const bool ok = (S >= 0) & (E >= 0) & (I >= 0) & (y0 <= S) & (y1 <= E) & (y2 <= I);
+      if (!ok) bad |= 2;
+      int ry = 0, rr = 0;
+      if (live && ok) {
+        acc += log_binom_coef(S, y0, lgtab) + log_binom_coef(E, y1, lgtab) + log_binom_coef(I, y2, lgtab);
+        accYei += y1;
+        accEres += E - y1;
+        ry = y2;
+        rr = I - y2;
+      }
+      ry = __reduce_add_sync(0xffffffffu, ry);
+      rr = __reduce_add_sync(0xffffffffu, rr);
+      if (lane == 0) {
+        atomicAdd(reinterpret_cast<unsigned long long*>(Yir + (size_t)b * T + t0 + s), (unsigned long long)ry);
+        atomicAdd(reinterpret_cast<unsigned long long*>(Rir + (size_t)b * T + t0 + s), (unsigned long long)rr);
+      }
+      c0 += y0; c1 += y1; c2 += y2;
+    }
+    carry0 += tot0; carry1 += tot1; carry2 += tot2;
+    __syncthreads();
+  }
+  // ---- per-CTA reductions ----
+  const double tot = block_sum(acc, red);
+  if (threadIdx.x == 0) llc_part[(size_t)b * gridDim.x + blockIdx.x] = tot;
+#pragma unroll
+  for (int o = 16; o > 0; o >>= 1) {
+    accYei += __shfl_xor_sync(0xffffffffu, accYei, o);
+    accEres += __shfl_xor_sync(0xffffffffu, accEres, o);
+  }
+  if (lane == 0) {
+    atomicAdd(reinterpret_cast<unsigned long long*>(sumYei + b), (unsigned long long)accYei);
+    atomicAdd(reinterpret_cast<unsigned long long*>(sumEres + b), (unsigned long long)accEres);
+  }
+  bad = __reduce_or_sync(0xffffffffu, bad);
+  if (lane == 0 && bad) atomicOr(flags + b, bad);
+}
+
+int seir_launch_ingest(seir_chains* c, const double* d_events, cudaStream_t s) {
+  const seir_model* m = c->model;
+  const int B = c->B, T = m->T;
+  SEIR_CUDA(cudaMemsetAsync(c->d_Yir, 0, sizeof(long long) * (size_t)B * T, s));
+  SEIR_CUDA(cudaMemsetAsync(c->d_Rir, 0, sizeof(long long) * (size_t)B * T, s));
+  SEIR_CUDA(cudaMemsetAsync(c->d_sumYei, 0, sizeof(long long) * (size_t)B, s));
+  SEIR_CUDA(cudaMemsetAsync(c->d_sumEres, 0, sizeof(long long) * (size_t)B, s));
+  SEIR_CUDA(cudaMemsetAsync(c->d_flags, 0, sizeof(int) * (size_t)B, s));
+  constexpr int TC = SEIR_INGEST_TC;
+  const size_t smem = sizeof(int) * (32 * (TC * 3 + 1) + 8 * 3 * 32);
+  static bool attr_set = false;
+  if (!attr_set) {
+    SEIR_CUDA(cudaFuncSetAttribute(seir_ingest_kernel<TC>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+    attr_set = true;
+  }
+  dim3 grid(c->nblk32, B);
+  seir_ingest_kernel<TC><<<grid, 256, smem, s>>>(m->M, T, m->Mp, m->d_init, m->d_lgtab, d_events, c->d_yse, c->d_yei, c->d_yir,
+                                                 c->d_S, c->d_E, c->d_I, c->d_llc_part, c->d_Yir, c->d_Rir, c->d_sumYei,
+                                                 c->d_sumEres, c->d_flags);
+  seir_count_launch(1);
+  return seir_cuda_check(cudaGetLastError(), "seir_ingest_kernel");
+}

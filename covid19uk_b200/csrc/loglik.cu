@@ -1,0 +1,327 @@
+// K3/K4: parameter-dependent half of the log-probability against the cached events.
+//
+//  seir_theta_prep_kernel  per chain: bijector (inference.py:525-535), the alpha_t random-walk path
+//                          (model_spec.py:242-256), per-day and per-metapopulation rate factors
+//                          (model_spec.py:257-274), the eight prior nodes (model_spec.py:140-198) and ILDJ.
+//  seir_loglik_kernel      fused S->E chain-binomial term over every (day, metapopulation) cell
+//                          (+ the pieces of its parameter gradient): HBM-bound streaming
+//                          kernel, thread <-> metapopulation, loop over days.
+//  seir_finalize_kernel    fixed-order reduction of the partials, E->I / I->R sufficient-statistic
+//                          terms, priors; assembles the gradient.
+#include "seir_internal.cuh"
+
+#define HALF_LOG_2PI 0.9189385332046727
+
+__device__ __forceinline__ double softplus_d(double x) { return fmax(x, 0.0) + log1p(exp(-fabs(x))); }
+__device__ __forceinline__ double sigmoid_d(double x) { return 1.0 / (1.0 + exp(-x)); }
+__device__ __forceinline__ double normal_lp(double x, double s) {
+  const double z = x / s;
+  return -0.5 * z * z - (HALF_LOG_2PI + log(s));
+}
+
+// ------------------------------------------------------------------------------------------------
+__global__ void __launch_bounds__(256) seir_theta_prep_kernel(
+    int M, int T, int Mp, int P, double dt, double car_log_det_scale, const double* __restrict__ theta, int kind, int parts,
+    const double* __restrict__ W, const double* __restrict__ wk, const int* __restrict__ aidx, const double* __restrict__ la,
+    const double* __restrict__ rN, const int* __restrict__ car_indptr, const int* __restrict__ car_indices,
+    const double* __restrict__ car_values, double* __restrict__ pa, double* __restrict__ psiW, double* __restrict__ gam,
+    double* __restrict__ logpir, double* __restrict__ pm, double* __restrict__ scal) {
+  extern __shared__ double cs[];  // [T] cumsum(alpha_t)
+  __shared__ double sc[SEIR_NSCAL];
+  __shared__ double red[32];
+  const int b = blockIdx.x, tid = threadIdx.x;
+  const double* th = theta + (size_t)b * P;
+  const double* alpha_t = th + 6;
+  const double* sp = th + 6 + (T - 1);
+  if (tid == 0) {
+    double psi = th[0], sigma = th[1], dpsi = 1.0, dsig = 1.0, ildj = 0.0, g0 = 0.0, g1 = 0.0;
+    if (kind == SEIR_THETA_UNCONSTRAINED) {
+      const double eps = 2.220446049250313e-16;  // tfb.Softplus(low=eps(float64)), inference.py:528
+      const double u0 = th[0], u1 = th[1];
+      psi = softplus_d(u0) + eps;
+      sigma = softplus_d(u1) + eps;
+      dpsi = sigmoid_d(u0);
+      dsig = sigmoid_d(u1);
+      if (parts & SEIR_PART_ILDJ) {
+        ildj = -softplus_d(-u0) - softplus_d(-u1);
+        g0 = 1.0 - dpsi;
+        g1 = 1.0 - dsig;
+      }
+    }
+    sc[SC_PSI] = psi; sc[SC_SIGMA] = sigma; sc[SC_BETA] = th[2]; sc[SC_GAMMA0] = th[3]; sc[SC_GAMMA1] = th[4];
+    sc[SC_ALPHA0] = th[5]; sc[SC_DPSI_DU] = dpsi; sc[SC_DSIGMA_DU] = dsig; sc[SC_ILDJ_G0] = g0; sc[SC_ILDJ_G1] = g1;
+    double prior = ildj;
+    if (parts & SEIR_PART_PRIORS) {
+      prior += normal_lp(th[5], 10.0);                                               // alpha_0  model_spec.py:140
+      prior += normal_lp(th[2], 1.0);                                                // beta_area :146
+      prior += 2.0 * log(psi) - 10.0 * psi - (0.6931471805599453 - 3.0 * 2.302585092994046);  // Gamma(3,10) :152
+      prior += (sigma < 0.0) ? -INFINITY                                             // HalfNormal(0.1) :167
+                             : (0.5 * log(2.0 / 3.141592653589793) - log(0.1) - 0.5 * (sigma / 0.1) * (sigma / 0.1));
+      prior += normal_lp(th[3], 100.0) + normal_lp(th[4], 100.0);                   // gamma0, gamma1 :188-198
+    }
+    sc[SC_PRIOR] = prior;
+    double run = 0.0;  // sequential, same order as a cumsum
+    for (int k = 0; k < T - 1; ++k) { run += alpha_t[k]; cs[k] = run; }
+  }
+  __syncthreads();
+  const double psi = sc[SC_PSI], sigma = sc[SC_SIGMA], beta = sc[SC_BETA], alpha0 = sc[SC_ALPHA0];
+  for (int t = tid; t < T; t += blockDim.x) {
+    const int k = aidx[t];
+    const double a = (k < 0) ? alpha0 : alpha0 + cs[k];
+    pa[(size_t)b * T + t] = exp(a);
+    psiW[(size_t)b * T + t] = psi * W[t];
+    const double g = exp(sc[SC_GAMMA0] + sc[SC_GAMMA1] * wk[t]);
+    gam[(size_t)b * T + t] = g;
+    logpir[(size_t)b * T + t] = log(-expm1(-g * dt));
+  }
+  for (int m = tid; m < Mp; m += blockDim.x)
+    pm[(size_t)b * Mp + m] = (m < M) ? exp(beta * la[m] + sigma * sp[m]) * rN[m] : 0.0;
+
+  if (parts & SEIR_PART_PRIORS) {
+    double acc = 0.0;
+    for (int k = tid; k < T - 1; k += blockDim.x) acc += normal_lp(alpha_t[k], 0.005);  // alpha_t :158-165
+    double q = 0.0;  // x' Q x with Q = Dw - rho W (CSR)   spatial_effect :171-181
+    for (int i = tid; i < M; i += blockDim.x) {
+      double r = 0.0;
+      for (int e = car_indptr[i]; e < car_indptr[i + 1]; ++e) r += car_values[e] * sp[car_indices[e]];
+      q += sp[i] * r;
+    }
+    const double tot = block_sum(acc - 0.5 * q, red);
+    if (tid == 0) sc[SC_PRIOR] += tot - (double)M * HALF_LOG_2PI - car_log_det_scale;
+  }
+  __syncthreads();
+  if (tid < SEIR_NSCAL) scal[(size_t)b * SEIR_NSCAL + tid] = sc[tid];
+}
+
+int seir_launch_theta_prep(seir_chains* c, const double* d_theta, int kind, int parts, cudaStream_t s) {
+  const seir_model* m = c->model;
+  seir_theta_prep_kernel<<<c->B, 256, sizeof(double) * m->T, s>>>(
+      m->M, m->T, m->Mp, m->P, m->dt, m->car_log_det_scale, d_theta, kind, parts, m->d_W, m->d_wk, m->d_aidx, m->d_la, m->d_rN,
+      m->d_car_indptr, m->d_car_indices, m->d_car_values, c->d_pa, c->d_psiW, c->d_gam, c->d_logpir, c->d_pm, c->d_scal);
+  seir_count_launch(1);
+  return seir_cuda_check(cudaGetLastError(), "seir_theta_prep_kernel");
+}
+
+// ------------------------------------------------------------------------------------------------
+// S->E term:  sum_{t,m} y log(1-exp(-lam dt)) - (S-y) lam dt,
+//   lam = exp(a_t + beta la_m + sigma s_m) (I + psi W_t Bc) / N_m + eps        (model_spec.py:257-266)
+// Day-slab caches => for a fixed day the 32 lanes of a warp read 32 consecutive metapopulations.
+// ------------------------------------------------------------------------------------------------
+template <bool GRAD>
+__global__ void __launch_bounds__(SEIR_LL_THREADS) seir_loglik_kernel(
+    int T, int Mp, double dt, double eps, const int* __restrict__ yse, const int* __restrict__ Sx, const int* __restrict__ Ix,
+    const double* __restrict__ Bc, const double* __restrict__ pa, const double* __restrict__ psiW, const double* __restrict__ W,
+    const double* __restrict__ pm, double* __restrict__ val_part, double* __restrict__ psi_part, double* __restrict__ col_part,
+    double* __restrict__ rowsum) {
+  extern __shared__ double sm[];
+  double* pa_s = sm;            // [T]
+  double* pw_s = sm + T;        // [T]
+  double* w_s = sm + 2 * T;     // [T]            (GRAD)
+  double* colw = sm + 3 * T;    // [nwarps][T]    (GRAD)
+  __shared__ double red[32];
+  const int b = blockIdx.y, tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
+  const int m = blockIdx.x * SEIR_LL_THREADS + tid;
+  const bool active = m < Mp;
+  for (int t = tid; t < T; t += SEIR_LL_THREADS) {
+    pa_s[t] = pa[(size_t)b * T + t];
+    pw_s[t] = psiW[(size_t)b * T + t];
+    if (GRAD) w_s[t] = W[t];
+  }
+  __syncthreads();
+  const double pm_m = active ? pm[(size_t)b * Mp + m] : 0.0;
+  const size_t base = (size_t)b * T * Mp + (active ? m : 0);
+  double val = 0.0, row = 0.0, psig = 0.0;
+#pragma unroll 4
+  for (int t = 0; t < T; ++t) {
+    const size_t o = base + (size_t)t * Mp;
+    int y = 0, S = 0, I = 0;
+    double bc = 0.0;
+    if (active) {
+      y = yse[o];
+      S = Sx[o];
+      I = Ix[o];
+      bc = Bc[o];
+    }
+    const double e = pa_s[t] * pm_m;
+    const double X = (double)I + pw_s[t] * bc;
+    const double lam = fma(e, X, eps);
+    const double ldt = lam * dt;
+    const double em = expm1(-ldt);  // -(1-exp(-lam dt)) = -p
+    const double yd = (double)y, rd = (double)(S - y);
+    double term = -rd * ldt;
+    if (y > 0) term += yd * log(-em);
+    val += term;
+    if (GRAD) {
+      double g = -rd;
+      if (y > 0) g += yd * (1.0 + em) / (-em);  // y / expm1(lam dt)
+      g *= dt;
+      const double h = g * (lam - eps);
+      row += h;
+      psig += g * e * w_s[t] * bc;
+      const double hs = warp_sum(h);
+      if (lane == 0) colw[warp * T + t] = hs;
+    }
+  }
+  const int nblk = gridDim.x;
+  const double v = block_sum(val, red);
+  if (tid == 0) val_part[(size_t)b * nblk + blockIdx.x] = v;
+  if (GRAD) {
+    const double pg = block_sum(psig, red);
+    if (tid == 0) psi_part[(size_t)b * nblk + blockIdx.x] = pg;
+    if (active) rowsum[(size_t)b * Mp + m] = row;
+    __syncthreads();
+    for (int t = tid; t < T; t += SEIR_LL_THREADS) {
+      double cta = 0.0;
+#pragma unroll
+      for (int w = 0; w < SEIR_LL_THREADS / 32; ++w) cta += colw[w * T + t];
+      col_part[((size_t)b * nblk + blockIdx.x) * T + t] = cta;
+    }
+  }
+}
+
+int seir_launch_loglik(seir_chains* c, bool grad, cudaStream_t s) {
+  const seir_model* m = c->model;
+  dim3 grid(c->nblkLL, c->B);
+  const size_t smem = sizeof(double) * (size_t)m->T * (grad ? 3 + SEIR_LL_THREADS / 32 : 2);
+  if (grad)
+    seir_loglik_kernel<true><<<grid, SEIR_LL_THREADS, smem, s>>>(m->T, m->Mp, m->dt, m->rate_eps, c->d_yse, c->d_S, c->d_I, c->d_Bc,
+                                                                 c->d_pa, c->d_psiW, m->d_W, c->d_pm, c->d_val_part, c->d_psi_part,
+                                                                 c->d_col_part, c->d_rowsum);
+  else
+    seir_loglik_kernel<false><<<grid, SEIR_LL_THREADS, smem, s>>>(m->T, m->Mp, m->dt, m->rate_eps, c->d_yse, c->d_S, c->d_I, c->d_Bc,
+                                                                  c->d_pa, c->d_psiW, m->d_W, c->d_pm, c->d_val_part, c->d_psi_part,
+                                                                  c->d_col_part, c->d_rowsum);
+  seir_count_launch(1);
+  return seir_cuda_check(cudaGetLastError(), "seir_loglik_kernel");
+}
+
+// ------------------------------------------------------------------------------------------------
+__global__ void __launch_bounds__(128) seir_finalize_kernel(
+    int M, int T, int Mp, int P, int nblkLL, int nblk32, double dt, double nu, double log_p_nu, int kind, int parts,
+    const double* __restrict__ theta, const double* __restrict__ scal, const double* __restrict__ val_part,
+    const double* __restrict__ llc_part, const long long* __restrict__ Yir, const long long* __restrict__ Rir,
+    const long long* __restrict__ sumYei, const long long* __restrict__ sumEres, const int* __restrict__ flags,
+    const double* __restrict__ gam, const double* __restrict__ logpir, const double* __restrict__ wk, const int* __restrict__ aidx,
+    const double* __restrict__ la, const double* __restrict__ psi_part, const double* __restrict__ col_part,
+    const double* __restrict__ rowsum, const int* __restrict__ car_indptr, const int* __restrict__ car_indices,
+    const double* __restrict__ car_values, double* __restrict__ out, double* __restrict__ grad) {
+  extern __shared__ double sm[];  // [T] column sums, [T] bucket
+  __shared__ double red[32];
+  const int b = blockIdx.x, tid = threadIdx.x;
+  const bool want_seir = parts & SEIR_PART_SEIR;
+  const bool want_prior = parts & SEIR_PART_PRIORS;
+  const double* sc = scal + (size_t)b * SEIR_NSCAL;
+
+  // ---- value ----
+  double ir = 0.0;
+  if (want_seir)
+    for (int t = tid; t < T; t += blockDim.x) {
+      const double yv = (double)Yir[(size_t)b * T + t], rv = (double)Rir[(size_t)b * T + t];
+      const double g = gam[(size_t)b * T + t];
+      double term = -rv * g * dt;
+      if (yv > 0.0) term += yv * logpir[(size_t)b * T + t];
+      ir += term;
+    }
+  const double ir_tot = block_sum(ir, red);
+  if (tid == 0) {
+    double v = sc[SC_PRIOR];
+    if (want_seir) {
+      double s = 0.0;
+      for (int k = 0; k < nblkLL; ++k) s += val_part[(size_t)b * nblkLL + k];
+      double l = 0.0;
+      for (int k = 0; k < nblk32; ++k) l += llc_part[(size_t)b * nblk32 + k];
+      const double yei = (double)sumYei[b], eres = (double)sumEres[b];
+      double ei = -eres * nu * dt;
+      if (yei > 0.0) ei += yei * log_p_nu;
+      v += s + l + ei + ir_tot;
+      if (flags[b] != 0) v = -INFINITY;
+    }
+    out[b] = v;
+  }
+  if (grad == nullptr) return;
+
+  // ---- gradient ----
+  double* g = grad + (size_t)b * P;
+  const double* th = theta + (size_t)b * P;
+  const double* sp = th + 6 + (T - 1);
+  double* col = sm;
+  double* bucket = sm + T;
+  const double sigma = sc[SC_SIGMA];
+  for (int t = tid; t < T; t += blockDim.x) {
+    double s = 0.0;
+    if (want_seir)
+      for (int k = 0; k < nblkLL; ++k) s += col_part[((size_t)b * nblkLL + k) * T + t];
+    col[t] = s;
+    bucket[t] = 0.0;
+  }
+  __syncthreads();
+  double gb = 0.0, gs = 0.0;
+  for (int m = tid; m < M; m += blockDim.x) {
+    const double r = want_seir ? rowsum[(size_t)b * Mp + m] : 0.0;
+    gb += r * la[m];
+    gs += r * sp[m];
+    double gm = sigma * r;
+    if (want_prior) {
+      double q = 0.0;
+      for (int e = car_indptr[m]; e < car_indptr[m + 1]; ++e) q += car_values[e] * sp[car_indices[e]];
+      gm -= q;
+    }
+    g[6 + (T - 1) + m] = gm;
+  }
+  const double gbeta = block_sum(gb, red);
+  const double gsigma = block_sum(gs, red);
+  double g0 = 0.0, g1 = 0.0;
+  if (want_seir)
+    for (int t = tid; t < T; t += blockDim.x) {
+      const double yv = (double)Yir[(size_t)b * T + t], rv = (double)Rir[(size_t)b * T + t];
+      const double gt = gam[(size_t)b * T + t];
+      double d = -rv;
+      if (yv > 0.0) d += yv / expm1(gt * dt);
+      d *= dt * gt;
+      g0 += d;
+      g1 += d * wk[t];
+    }
+  const double gg0 = block_sum(g0, red);
+  const double gg1 = block_sum(g1, red);
+  if (tid == 0) {
+    double a0 = 0.0;
+    for (int t = 0; t < T; ++t) {
+      a0 += col[t];
+      if (aidx[t] >= 0) bucket[aidx[t]] += col[t];
+    }
+    double run = 0.0;  // alpha_t[k] feeds every day whose cumsum index is >= k
+    for (int k = T - 2; k >= 0; --k) {
+      run += bucket[k];
+      g[6 + k] = run - (want_prior ? th[6 + k] / (0.005 * 0.005) : 0.0);
+    }
+    double gpsi = 0.0;
+    if (want_seir)
+      for (int k = 0; k < nblkLL; ++k) gpsi += psi_part[(size_t)b * nblkLL + k];
+    double gsg = gsigma, gbt = gbeta, gga0 = gg0, gga1 = gg1;
+    if (want_prior) {
+      gpsi += 2.0 / sc[SC_PSI] - 10.0;
+      gsg += -sigma / (0.1 * 0.1);
+      gbt += -th[2];
+      gga0 += -th[3] / (100.0 * 100.0);
+      gga1 += -th[4] / (100.0 * 100.0);
+      a0 += -th[5] / (10.0 * 10.0);
+    }
+    g[0] = gpsi * sc[SC_DPSI_DU] + sc[SC_ILDJ_G0];
+    g[1] = gsg * sc[SC_DSIGMA_DU] + sc[SC_ILDJ_G1];
+    g[2] = gbt;
+    g[3] = gga0;
+    g[4] = gga1;
+    g[5] = a0;
+  }
+}
+
+int seir_launch_finalize(seir_chains* c, const double* d_theta, int kind, int parts, double* d_out, double* d_grad,
+                         cudaStream_t s) {
+  const seir_model* m = c->model;
+  seir_finalize_kernel<<<c->B, 128, sizeof(double) * 2 * m->T, s>>>(
+      m->M, m->T, m->Mp, m->P, c->nblkLL, c->nblk32, m->dt, m->nu, m->log_p_nu, kind, parts, d_theta, c->d_scal, c->d_val_part,
+      c->d_llc_part, c->d_Yir, c->d_Rir, c->d_sumYei, c->d_sumEres, c->d_flags, c->d_gam, c->d_logpir, m->d_wk, m->d_aidx, m->d_la,
+      c->d_psi_part, c->d_col_part, c->d_rowsum, m->d_car_indptr, m->d_car_indices, m->d_car_values, d_out, d_grad);
+  seir_count_launch(1);
+  return seir_cuda_check(cudaGetLastError(), "seir_finalize_kernel");
+}

@@ -1,0 +1,311 @@
+// C-ABI layer: object lifetime, argument checking, error text, and the sequencing of the kernels
+// behind each entry point of include/seir_b200.h.
+#include <math.h>
+#include <stdarg.h>
+#include <stdio.h>
+#include <string.h>
+
+#include <atomic>
+#include <new>
+#include <vector>
+
+#include "seir_internal.cuh"
+
+static thread_local char g_err[512] = "";
+static std::atomic<long long> g_launches{0};
+
+int seir_set_error(int code, const char* fmt, ...) {
+  va_list ap;
+  va_start(ap, fmt);
+  vsnprintf(g_err, sizeof(g_err), fmt, ap);
+  va_end(ap);
+  return code;
+}
+
+int seir_cuda_check(cudaError_t e, const char* what) {
+  if (e == cudaSuccess) return SEIR_OK;
+  return seir_set_error(SEIR_ERR_CUDA, "CUDA error %d (%s) in %s", (int)e, cudaGetErrorString(e), what);
+}
+
+void seir_count_launch(int n) { g_launches.fetch_add(n, std::memory_order_relaxed); }
+
+static inline int round_up(int x, int m) { return (x + m - 1) / m * m; }
+
+template <typename T>
+static int dev_alloc(T** p, size_t n, int64_t* bytes = nullptr) {
+  *p = nullptr;
+  if (n == 0) n = 1;
+  SEIR_CUDA(cudaMalloc(reinterpret_cast<void**>(p), n * sizeof(T)));
+  if (bytes) *bytes += (int64_t)(n * sizeof(T));
+  return SEIR_OK;
+}
+
+template <typename T>
+static int dev_upload(T** p, const std::vector<T>& h) {
+  int rc = dev_alloc(p, h.size());
+  if (rc != SEIR_OK) return rc;
+  if (!h.empty()) SEIR_CUDA(cudaMemcpy(*p, h.data(), h.size() * sizeof(T), cudaMemcpyHostToDevice));
+  return SEIR_OK;
+}
+
+#define SEIR_TRY(expr)            \
+  do {                            \
+    int _rc = (expr);             \
+    if (_rc != SEIR_OK) return _rc; \
+  } while (0)
+
+extern "C" {
+
+int seir_abi_version(void) { return SEIR_B200_ABI_VERSION; }
+const char* seir_last_error(void) { return g_err; }
+int64_t seir_launch_count(void) { return g_launches.load(); }
+
+int seir_model_create(const seir_spec* spec, int device, seir_model** out) {
+  if (!spec || !out) return seir_set_error(SEIR_ERR_BAD_ARG, "seir_model_create: NULL argument");
+  *out = nullptr;
+  const int M = spec->num_meta, T = spec->num_steps;
+  if (M < 1 || T < 2) return seir_set_error(SEIR_ERR_SHAPE, "seir_model_create: need M >= 1 and T >= 2 (got %d, %d)", M, T);
+  if (T > 4096) return seir_set_error(SEIR_ERR_SHAPE, "seir_model_create: T=%d > 4096 unsupported", T);
+  if (!spec->cstar || !spec->population || !spec->commute_volume || !spec->weekday_c || !spec->log_area_c ||
+      !spec->initial_state || !spec->car_indptr || (spec->car_nnz > 0 && (!spec->car_indices || !spec->car_values)))
+    return seir_set_error(SEIR_ERR_BAD_ARG, "seir_model_create: NULL array in spec");
+  if (spec->n_commute_volume < 1 || spec->n_weekday < 1)
+    return seir_set_error(SEIR_ERR_SHAPE, "seir_model_create: empty commute_volume / weekday");
+  SEIR_CUDA(cudaSetDevice(device));
+
+  seir_model* m = new (std::nothrow) seir_model();
+  if (!m) return seir_set_error(SEIR_ERR_BAD_ARG, "out of host memory");
+  memset(m, 0, sizeof(*m));
+  m->device = device;
+  m->M = M;
+  m->T = T;
+  m->Mp = round_up(M, SEIR_PAD);
+  m->P = 6 + (T - 1) + M;
+  m->initial_step = spec->initial_step;
+  m->dt = spec->time_delta;
+  m->nu = spec->nu;
+  m->rate_eps = spec->rate_eps;
+  m->car_log_det_scale = spec->car_log_det_scale;
+  m->log_p_nu = log(-expm1(-spec->nu * spec->time_delta));
+  m->car_nnz = spec->car_nnz;
+  const int Mp = m->Mp;
+
+  std::vector<double> cstar((size_t)Mp * Mp, 0.0), rN(Mp, 0.0), la(Mp, 0.0), W(T), wk(T), lgtab(SEIR_LGTAB);
+  std::vector<int> init((size_t)Mp * 4, 0), aidx(T);
+  for (int i = 0; i < M; ++i) {
+    memcpy(&cstar[(size_t)i * Mp], &spec->cstar[(size_t)i * M], sizeof(double) * M);
+    rN[i] = 1.0 / spec->population[i];
+    la[i] = spec->log_area_c[i];
+    for (int s = 0; s < 4; ++s) {
+      const double v = spec->initial_state[i * 4 + s];
+      if (v < 0 || v > 2.0e9 || v != floor(v)) {
+        delete m;
+        return seir_set_error(SEIR_ERR_BAD_ARG, "seir_model_create: initial_state[%d,%d]=%g is not a non-negative int32", i, s, v);
+      }
+      init[(size_t)i * 4 + s] = (int)v;
+    }
+  }
+  for (int k = 0; k < T; ++k) {
+    // t = initial_step + k*time_delta cast to int64 inside the rate closure (model_spec.py:234,238,244)
+    const long long t = (long long)((double)spec->initial_step + (double)k * spec->time_delta);
+    long long wi = t < 0 ? 0 : t;
+    if (wi > spec->n_commute_volume - 1) wi = spec->n_commute_volume - 1;
+    W[k] = spec->commute_volume[wi];
+    long long di = t < 0 ? 0 : t;
+    if (di > spec->n_weekday - 1) di = spec->n_weekday - 1;
+    wk[k] = spec->weekday_c[di];
+    long long ai = t - 1;  // model_spec.py:245-255
+    if (ai < 0) ai = 0;
+    if (ai > T - 2) ai = T - 2;
+    aidx[k] = (t == 0) ? -1 : (int)ai;
+  }
+  for (int k = 0; k < SEIR_LGTAB; ++k) lgtab[k] = lgamma((double)k + 1.0);
+  std::vector<int> indptr(spec->car_indptr, spec->car_indptr + M + 1);
+  std::vector<int> indices(spec->car_indices, spec->car_indices + spec->car_nnz);
+  std::vector<double> values(spec->car_values, spec->car_values + spec->car_nnz);
+
+  int rc = SEIR_OK;
+  if ((rc = dev_upload(&m->d_cstar, cstar)) || (rc = dev_upload(&m->d_rN, rN)) || (rc = dev_upload(&m->d_W, W)) ||
+      (rc = dev_upload(&m->d_wk, wk)) || (rc = dev_upload(&m->d_aidx, aidx)) || (rc = dev_upload(&m->d_la, la)) ||
+      (rc = dev_upload(&m->d_init, init)) || (rc = dev_upload(&m->d_car_indptr, indptr)) ||
+      (rc = dev_upload(&m->d_car_indices, indices)) || (rc = dev_upload(&m->d_car_values, values)) ||
+      (rc = dev_upload(&m->d_lgtab, lgtab))) {
+    seir_model_destroy(m);
+    return rc;
+  }
+  *out = m;
+  return SEIR_OK;
+}
+
+void seir_model_destroy(seir_model* m) {
+  if (!m) return;
+  cudaSetDevice(m->device);
+  cudaFree(m->d_cstar); cudaFree(m->d_rN); cudaFree(m->d_W); cudaFree(m->d_wk); cudaFree(m->d_aidx); cudaFree(m->d_la);
+  cudaFree(m->d_init); cudaFree(m->d_car_indptr); cudaFree(m->d_car_indices); cudaFree(m->d_car_values); cudaFree(m->d_lgtab);
+  delete m;
+}
+
+int seir_model_dims(const seir_model* m, int32_t* M, int32_t* T, int32_t* P, int32_t* Mp) {
+  if (!m) return seir_set_error(SEIR_ERR_BAD_ARG, "seir_model_dims: NULL model");
+  if (M) *M = m->M;
+  if (T) *T = m->T;
+  if (P) *P = m->P;
+  if (Mp) *Mp = m->Mp;
+  return SEIR_OK;
+}
+
+int seir_chains_create(const seir_model* m, int B, seir_chains** out) {
+  if (!m || !out) return seir_set_error(SEIR_ERR_BAD_ARG, "seir_chains_create: NULL argument");
+  *out = nullptr;
+  if (B < 1 || B > 65535) return seir_set_error(SEIR_ERR_SHAPE, "seir_chains_create: need 1 <= num_chains <= 65535 (got %d)", B);
+  SEIR_CUDA(cudaSetDevice(m->device));
+  seir_chains* c = new (std::nothrow) seir_chains();
+  if (!c) return seir_set_error(SEIR_ERR_BAD_ARG, "out of host memory");
+  memset(c, 0, sizeof(*c));
+  c->model = m;
+  c->B = B;
+  c->nblk32 = m->Mp / 32;
+  c->nblkLL = (m->Mp + SEIR_LL_THREADS - 1) / SEIR_LL_THREADS;
+  const size_t cells = (size_t)B * m->T * m->Mp, BT = (size_t)B * m->T;
+  int rc = SEIR_OK;
+  if ((rc = dev_alloc(&c->d_yse, cells, &c->bytes)) || (rc = dev_alloc(&c->d_yei, cells, &c->bytes)) ||
+      (rc = dev_alloc(&c->d_yir, cells, &c->bytes)) || (rc = dev_alloc(&c->d_S, cells, &c->bytes)) ||
+      (rc = dev_alloc(&c->d_E, cells, &c->bytes)) || (rc = dev_alloc(&c->d_I, cells, &c->bytes)) ||
+      (rc = dev_alloc(&c->d_Bc, cells, &c->bytes)) || (rc = dev_alloc(&c->d_llc_part, (size_t)B * c->nblk32, &c->bytes)) ||
+      (rc = dev_alloc(&c->d_Yir, BT, &c->bytes)) || (rc = dev_alloc(&c->d_Rir, BT, &c->bytes)) ||
+      (rc = dev_alloc(&c->d_sumYei, (size_t)B, &c->bytes)) || (rc = dev_alloc(&c->d_sumEres, (size_t)B, &c->bytes)) ||
+      (rc = dev_alloc(&c->d_flags, (size_t)B, &c->bytes)) || (rc = dev_alloc(&c->d_pa, BT, &c->bytes)) ||
+      (rc = dev_alloc(&c->d_psiW, BT, &c->bytes)) || (rc = dev_alloc(&c->d_gam, BT, &c->bytes)) ||
+      (rc = dev_alloc(&c->d_logpir, BT, &c->bytes)) || (rc = dev_alloc(&c->d_pm, (size_t)B * m->Mp, &c->bytes)) ||
+      (rc = dev_alloc(&c->d_scal, (size_t)B * SEIR_NSCAL, &c->bytes)) ||
+      (rc = dev_alloc(&c->d_val_part, (size_t)B * c->nblkLL, &c->bytes)) ||
+      (rc = dev_alloc(&c->d_psi_part, (size_t)B * c->nblkLL, &c->bytes)) ||
+      (rc = dev_alloc(&c->d_col_part, (size_t)B * c->nblkLL * m->T, &c->bytes)) ||
+      (rc = dev_alloc(&c->d_rowsum, (size_t)B * m->Mp, &c->bytes))) {
+    seir_chains_destroy(c);
+    return rc;
+  }
+  *out = c;
+  return SEIR_OK;
+}
+
+void seir_chains_destroy(seir_chains* c) {
+  if (!c) return;
+  cudaSetDevice(c->model->device);
+  cudaFree(c->d_yse); cudaFree(c->d_yei); cudaFree(c->d_yir); cudaFree(c->d_S); cudaFree(c->d_E); cudaFree(c->d_I);
+  cudaFree(c->d_Bc); cudaFree(c->d_llc_part); cudaFree(c->d_Yir); cudaFree(c->d_Rir); cudaFree(c->d_sumYei);
+  cudaFree(c->d_sumEres); cudaFree(c->d_flags); cudaFree(c->d_pa); cudaFree(c->d_psiW); cudaFree(c->d_gam);
+  cudaFree(c->d_logpir); cudaFree(c->d_pm); cudaFree(c->d_scal); cudaFree(c->d_val_part); cudaFree(c->d_psi_part);
+  cudaFree(c->d_col_part); cudaFree(c->d_rowsum); cudaFree(c->d_stage_events); cudaFree(c->d_stage_theta);
+  cudaFree(c->d_stage_out);
+  delete c;
+}
+
+int64_t seir_chains_bytes(const seir_chains* c) { return c ? c->bytes : 0; }
+
+static int check_dev_ptr(const void* p, const char* name) {
+  if (!p) return seir_set_error(SEIR_ERR_BAD_ARG, "%s is NULL", name);
+  if ((uintptr_t)p & 15) return seir_set_error(SEIR_ERR_ALIGN, "%s is not 16-byte aligned", name);
+  return SEIR_OK;
+}
+
+static int check_parts(int kind, int parts) {
+  if (kind != SEIR_THETA_CONSTRAINED && kind != SEIR_THETA_UNCONSTRAINED)
+    return seir_set_error(SEIR_ERR_BAD_ARG, "theta_kind must be SEIR_THETA_CONSTRAINED or SEIR_THETA_UNCONSTRAINED");
+  if (parts <= 0 || (parts & ~SEIR_PART_JOINT)) return seir_set_error(SEIR_ERR_BAD_ARG, "invalid parts mask %d", parts);
+  if ((parts & SEIR_PART_ILDJ) && kind != SEIR_THETA_UNCONSTRAINED)
+    return seir_set_error(SEIR_ERR_BAD_ARG, "SEIR_PART_ILDJ needs SEIR_THETA_UNCONSTRAINED");
+  return SEIR_OK;
+}
+
+int seir_compute_state(const seir_model* m, int B, const double* d_events, double* d_state, void* stream) {
+  if (!m) return seir_set_error(SEIR_ERR_BAD_ARG, "seir_compute_state: NULL model");
+  if (B < 1) return seir_set_error(SEIR_ERR_SHAPE, "seir_compute_state: num_chains < 1");
+  SEIR_TRY(check_dev_ptr(d_events, "d_events"));
+  SEIR_TRY(check_dev_ptr(d_state, "d_state"));
+  return seir_launch_state(m, B, d_events, d_state, (cudaStream_t)stream);
+}
+
+int seir_ingest_events(seir_chains* c, const double* d_events, void* stream) {
+  if (!c) return seir_set_error(SEIR_ERR_BAD_ARG, "seir_ingest_events: NULL chains");
+  SEIR_TRY(check_dev_ptr(d_events, "d_events"));
+  SEIR_TRY(seir_launch_ingest(c, d_events, (cudaStream_t)stream));
+  return seir_launch_contract(c, (cudaStream_t)stream);
+}
+
+int seir_log_prob_cached(seir_chains* c, const double* d_theta, int kind, int parts, double* d_out, void* stream) {
+  if (!c) return seir_set_error(SEIR_ERR_BAD_ARG, "seir_log_prob_cached: NULL chains");
+  SEIR_TRY(check_parts(kind, parts));
+  SEIR_TRY(check_dev_ptr(d_theta, "d_theta"));
+  if (!d_out) return seir_set_error(SEIR_ERR_BAD_ARG, "d_out is NULL");
+  cudaStream_t s = (cudaStream_t)stream;
+  SEIR_TRY(seir_launch_theta_prep(c, d_theta, kind, parts, s));
+  if (parts & SEIR_PART_SEIR) SEIR_TRY(seir_launch_loglik(c, false, s));
+  return seir_launch_finalize(c, d_theta, kind, parts, d_out, nullptr, s);
+}
+
+int seir_log_prob_grad_cached(seir_chains* c, const double* d_theta, int kind, int parts, double* d_out, double* d_grad,
+                              void* stream) {
+  if (!c) return seir_set_error(SEIR_ERR_BAD_ARG, "seir_log_prob_grad_cached: NULL chains");
+  SEIR_TRY(check_parts(kind, parts));
+  SEIR_TRY(check_dev_ptr(d_theta, "d_theta"));
+  if (!d_out || !d_grad) return seir_set_error(SEIR_ERR_BAD_ARG, "d_out / d_grad is NULL");
+  cudaStream_t s = (cudaStream_t)stream;
+  SEIR_TRY(seir_launch_theta_prep(c, d_theta, kind, parts, s));
+  if (parts & SEIR_PART_SEIR) SEIR_TRY(seir_launch_loglik(c, true, s));
+  return seir_launch_finalize(c, d_theta, kind, parts, d_out, d_grad, s);
+}
+
+int seir_log_prob(seir_chains* c, const double* d_events, const double* d_theta, int kind, int parts, double* d_out,
+                  void* stream) {
+  if (!c) return seir_set_error(SEIR_ERR_BAD_ARG, "seir_log_prob: NULL chains");
+  SEIR_TRY(check_parts(kind, parts));
+  if (parts & SEIR_PART_SEIR) SEIR_TRY(seir_ingest_events(c, d_events, stream));
+  return seir_log_prob_cached(c, d_theta, kind, parts, d_out, stream);
+}
+
+int seir_log_prob_host(seir_chains* c, const double* h_events, const double* h_theta, int kind, int parts, double* h_out) {
+  if (!c || !h_events || !h_theta || !h_out) return seir_set_error(SEIR_ERR_BAD_ARG, "seir_log_prob_host: NULL argument");
+  const seir_model* m = c->model;
+  SEIR_CUDA(cudaSetDevice(m->device));
+  const size_t ne = (size_t)c->B * m->M * m->T * 3, nt = (size_t)c->B * m->P;
+  if (!c->d_stage_events) {
+    SEIR_TRY(dev_alloc(&c->d_stage_events, ne, &c->bytes));
+    SEIR_TRY(dev_alloc(&c->d_stage_theta, nt, &c->bytes));
+    SEIR_TRY(dev_alloc(&c->d_stage_out, (size_t)c->B, &c->bytes));
+  }
+  cudaStream_t s = cudaStreamPerThread;
+  SEIR_CUDA(cudaMemcpyAsync(c->d_stage_events, h_events, ne * sizeof(double), cudaMemcpyHostToDevice, s));
+  SEIR_CUDA(cudaMemcpyAsync(c->d_stage_theta, h_theta, nt * sizeof(double), cudaMemcpyHostToDevice, s));
+  SEIR_TRY(seir_log_prob(c, c->d_stage_events, c->d_stage_theta, kind, parts, c->d_stage_out, s));
+  SEIR_CUDA(cudaMemcpyAsync(h_out, c->d_stage_out, (size_t)c->B * sizeof(double), cudaMemcpyDeviceToHost, s));
+  SEIR_CUDA(cudaStreamSynchronize(s));
+  return SEIR_OK;
+}
+
+int seir_run_stage(seir_chains* c, int stage, const double* d_events, const double* d_theta, int kind, int parts, double* d_out,
+                   double* d_grad, void* stream) {
+  if (!c) return seir_set_error(SEIR_ERR_BAD_ARG, "seir_run_stage: NULL chains");
+  cudaStream_t s = (cudaStream_t)stream;
+  switch (stage) {
+    case 0: SEIR_TRY(check_dev_ptr(d_events, "d_events")); return seir_launch_ingest(c, d_events, s);
+    case 1: return seir_launch_contract(c, s);
+    case 2: SEIR_TRY(check_dev_ptr(d_theta, "d_theta")); return seir_launch_theta_prep(c, d_theta, kind, parts, s);
+    case 3: return seir_launch_loglik(c, false, s);
+    case 4: return seir_launch_loglik(c, true, s);
+    case 5: SEIR_TRY(check_dev_ptr(d_theta, "d_theta")); return seir_launch_finalize(c, d_theta, kind, parts, d_out, nullptr, s);
+    case 6:
+      SEIR_TRY(check_dev_ptr(d_theta, "d_theta"));
+      if (!d_grad) return seir_set_error(SEIR_ERR_BAD_ARG, "seir_run_stage: stage 6 needs d_grad");
+      return seir_launch_finalize(c, d_theta, kind, parts, d_out, d_grad, s);
+    default: return seir_set_error(SEIR_ERR_BAD_ARG, "seir_run_stage: unknown stage %d", stage);
+  }
+}
+
+int seir_chain_flags(const seir_chains* c, int32_t* d_flags_out, void* stream) {
+  if (!c || !d_flags_out) return seir_set_error(SEIR_ERR_BAD_ARG, "seir_chain_flags: NULL argument");
+  SEIR_CUDA(cudaMemcpyAsync(d_flags_out, c->d_flags, sizeof(int) * (size_t)c->B, cudaMemcpyDeviceToDevice, (cudaStream_t)stream));
+  return SEIR_OK;
+}
+
+}  // extern "C"

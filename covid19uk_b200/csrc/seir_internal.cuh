@@ -1,0 +1,146 @@
+// Internal definitions shared by the kernels and the C-ABI layer (not installed; the public
+// interface is include/seir_b200.h).
+#pragma once
+
+#include <cuda_runtime.h>
+#include <stdint.h>
+
+#include "../../include/seir_b200.h"
+
+#define SEIR_PAD 64          // metapopulation axis is padded to a multiple of this
+#define SEIR_LGTAB 1024      // lgamma(k+1) table entries, k < SEIR_LGTAB
+#define SEIR_INGEST_TC 128   // days per ingest chunk
+#define SEIR_LL_THREADS 128  // metapopulations per CTA in the log-likelihood kernel
+#define SEIR_NSCAL 16        // per-chain scalar slots
+
+// per-chain scalar slots (d_scal[b*SEIR_NSCAL + k])
+enum {
+  SC_PSI = 0, SC_SIGMA, SC_BETA, SC_GAMMA0, SC_GAMMA1, SC_ALPHA0,
+  SC_PRIOR,      // sum of selected prior terms (+ ILDJ)
+  SC_DPSI_DU,    // d psi / d u0  (sigmoid(u0)) or 1
+  SC_DSIGMA_DU,  // d sigma / d u1
+  SC_ILDJ_G0,    // d ILDJ / d u0
+  SC_ILDJ_G1
+};
+
+struct seir_model {
+  int device;
+  int M, T, Mp, P;
+  int initial_step;
+  double dt, nu, rate_eps, car_log_det_scale;
+  double log_p_nu;  // log(1 - exp(-nu*dt))
+  int car_nnz;
+  // device arrays
+  double* d_cstar;     // [Mp*Mp] zero padded, symmetric
+  double* d_rN;        // [Mp] 1/N, 0 in the padding
+  double* d_W;         // [T] commute volume resolved per step (model_spec.py:234-235)
+  double* d_wk;        // [T] centred weekday resolved per step (model_spec.py:237-240)
+  int* d_aidx;         // [T] index into cumsum(alpha_t) or -1 for alpha_0 alone (model_spec.py:242-256)
+  double* d_la;        // [Mp] centred log area
+  int* d_init;         // [Mp*4] initial state
+  int* d_car_indptr;   // [M+1]
+  int* d_car_indices;  // [nnz]
+  double* d_car_values;
+  double* d_lgtab;     // [SEIR_LGTAB]
+};
+
+struct seir_chains {
+  const seir_model* model;
+  int B;
+  int nblk32;   // Mp/32   (ingest CTAs per chain)
+  int nblkLL;   // ceil(Mp/SEIR_LL_THREADS)
+  int64_t bytes;
+  // events-only caches, day-slab layout [B][T][Mp]
+  int *d_yse, *d_yei, *d_yir, *d_S, *d_E, *d_I;
+  double* d_Bc;          // [B][T][Mp]  Cstar . (I/N)
+  double* d_llc_part;    // [B][nblk32] parameter-free log-pmf partials (log binomial coefficients)
+  long long* d_Yir;      // [B][T]  sum_m y_ir
+  long long* d_Rir;      // [B][T]  sum_m (I - y_ir)
+  long long* d_sumYei;   // [B]
+  long long* d_sumEres;  // [B]  sum (E - y_ei)
+  int* d_flags;          // [B]
+  // theta-derived
+  double *d_pa, *d_psiW, *d_gam, *d_logpir;  // [B][T]
+  double* d_pm;                              // [B][Mp]
+  double* d_scal;                            // [B][SEIR_NSCAL]
+  // reductions
+  double* d_val_part;  // [B][nblkLL]
+  double* d_psi_part;  // [B][nblkLL]
+  double* d_col_part;  // [B][nblkLL][T]
+  double* d_rowsum;    // [B][Mp]
+  // staging for the host-buffer entry points
+  double *d_stage_events, *d_stage_theta, *d_stage_out;
+};
+
+// error plumbing (seir_api.cu)
+int seir_set_error(int code, const char* fmt, ...);
+int seir_cuda_check(cudaError_t e, const char* what);
+void seir_count_launch(int n);
+
+#define SEIR_CUDA(call)                                   \
+  do {                                                    \
+    int _rc = seir_cuda_check((call), #call);             \
+    if (_rc != SEIR_OK) return _rc;                       \
+  } while (0)
+
+// kernel launchers (one per .cu file)
+int seir_launch_state(const seir_model* m, int B, const double* d_events, double* d_state, cudaStream_t s);
+int seir_launch_ingest(seir_chains* c, const double* d_events, cudaStream_t s);
+int seir_launch_contract(seir_chains* c, cudaStream_t s);
+int seir_launch_theta_prep(seir_chains* c, const double* d_theta, int kind, int parts, cudaStream_t s);
+int seir_launch_loglik(seir_chains* c, bool grad, cudaStream_t s);
+int seir_launch_finalize(seir_chains* c, const double* d_theta, int kind, int parts, double* d_out, double* d_grad,
+                         cudaStream_t s);
+
+// ---- device helpers ---------------------------------------------------------------------------
+#ifdef __CUDACC__
+
+__device__ __forceinline__ double warp_sum(double v) {
+#pragma unroll
+  for (int o = 16; o > 0; o >>= 1) v += __shfl_xor_sync(0xffffffffu, v, o);
+  return v;  // xor butterfly: every lane ends with the same, order-fixed sum
+}
+
+// Deterministic block sum (fixed tree); result valid in thread 0.  `red` holds >= 32 doubles.
+__device__ __forceinline__ double block_sum(double v, double* red) {
+  const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5, nw = (blockDim.x + 31) >> 5;
+  v = warp_sum(v);
+  __syncthreads();
+  if (lane == 0) red[warp] = v;
+  __syncthreads();
+  double r = 0.0;
+  if (threadIdx.x == 0)
+    for (int w = 0; w < nw; ++w) r += red[w];
+  return r;
+}
+
+// Stirling tail  1/(12x) - 1/(360x^3) + 1/(1260x^5) - 1/(1680x^7)   (x >= 256: next term < 1e-24)
+__device__ __forceinline__ double stirling_tail(double x) {
+  const double r = 1.0 / x, r2 = r * r;
+  return r * (0.08333333333333333 + r2 * (-0.002777777777777778 + r2 * (7.936507936507937e-4 + r2 * -5.952380952380953e-4)));
+}
+
+// lgamma(n+1) for integer n >= 0
+__device__ __forceinline__ double lgamma1p_int(int n, const double* __restrict__ lgtab) {
+  if (n < SEIR_LGTAB) return __ldg(lgtab + n);
+  const double x = (double)n + 1.0;
+  return (x - 0.5) * log(x) - x + 0.9189385332046727 + stirling_tail(x);
+}
+
+// log C(n, y) for integers 0 <= y <= n.  For large n-y the difference lgamma(n+1)-lgamma(n-y+1) is
+// formed analytically ((b-1/2) log1p(y/b) + y (log a - 1) + tails, a=n+1, b=n-y+1) so that it does not
+// suffer the catastrophic cancellation of two ~1e7-sized lgamma values.
+__device__ __forceinline__ double log_binom_coef(int n, int y, const double* __restrict__ lgtab) {
+  if (y == 0 || y == n) return 0.0;
+  const int r = n - y;
+  double d;
+  if (r >= SEIR_LGTAB) {
+    const double a = (double)n + 1.0, b = (double)r + 1.0, yd = (double)y;
+    d = (b - 0.5) * log1p(yd / b) + yd * (log(a) - 1.0) + (stirling_tail(a) - stirling_tail(b));
+  } else {
+    d = lgamma1p_int(n, lgtab) - lgamma1p_int(r, lgtab);
+  }
+  return d - lgamma1p_int(y, lgtab);
+}
+
+#endif  // __CUDACC__

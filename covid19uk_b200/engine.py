@@ -1,0 +1,186 @@
+"""Host-side owner of the native model / chain-set handles.
+
+PyTorch supplies device memory and streams only; all arithmetic of the hot path happens in
+``libseir_b200.so`` through the C ABI of ``include/seir_b200.h``.
+"""
+from __future__ import annotations
+
+import ctypes
+from ctypes import POINTER, byref, c_double, c_int32, c_void_p
+
+import numpy as np
+import torch
+
+from . import _native as nat
+
+STOICHIOMETRY = np.array([[-1, 1, 0, 0], [0, -1, 1, 0], [0, 0, -1, 1]])  # model_spec.py:24
+TIME_DELTA = 1.0  # model_spec.py:25
+NU = 0.28  # model_spec.py:26
+RATE_EPS = 0.000000001  # model_spec.py:266
+CAR_RHO = 0.25  # model_spec.py:174
+
+
+def _as_f64(a):
+    return np.ascontiguousarray(np.asarray(a, dtype=np.float64))
+
+
+def _dptr(a: np.ndarray):
+    return a.ctypes.data_as(POINTER(c_double))
+
+
+def _iptr(a: np.ndarray):
+    return a.ctypes.data_as(POINTER(c_int32))
+
+
+def prepare_constants(covariates) -> dict:
+    """One-off host preparation, identical in meaning to model_spec.py:212-230 and :171-181."""
+    C = np.array(covariates["C"], dtype=np.float64)
+    np.fill_diagonal(C, 0.0)
+    Cstar = C + C.T
+    np.fill_diagonal(Cstar, -C.sum(axis=-2))
+    W = np.atleast_1d(np.squeeze(_as_f64(covariates["W"])))
+    N = np.atleast_1d(np.squeeze(_as_f64(covariates["N"])))
+    weekday = _as_f64(covariates["weekday"])
+    weekday_c = weekday - weekday.mean(axis=-1)
+    log_area = np.log(_as_f64(covariates["area"]) / 100000000.0)
+    log_area_c = log_area - log_area.mean()
+    adj = _as_f64(covariates["adjacency"])
+    precision = np.diag(adj.sum(axis=-1)) - CAR_RHO * adj
+    scale = np.linalg.cholesky(np.linalg.inv(precision))
+    rows, cols = np.nonzero(precision)
+    order = np.lexsort((cols, rows))
+    rows, cols = rows[order], cols[order]
+    indptr = np.zeros(precision.shape[0] + 1, np.int32)
+    np.add.at(indptr, rows + 1, 1)
+    indptr = np.cumsum(indptr).astype(np.int32)
+    return dict(
+        Cstar=_as_f64(Cstar), W=W, N=N, weekday_c=_as_f64(weekday_c), log_area_c=_as_f64(log_area_c),
+        car_indptr=indptr, car_indices=cols.astype(np.int32), car_values=_as_f64(precision[rows, cols]),
+        car_log_det_scale=float(np.sum(np.log(np.diag(scale)))),
+    )
+
+
+class SeirEngine:
+    """One model on one CUDA device plus chain sets (caches) keyed by the number of chains."""
+
+    def __init__(self, covariates, initial_state, initial_step, num_steps, device=None):
+        if not torch.cuda.is_available():
+            raise nat.NativeError("covid19uk_b200 needs a CUDA device: there is no CPU fallback for the hot path")
+        self.lib = nat.load()
+        self.device = torch.device("cuda", torch.cuda.current_device() if device is None else torch.device(device).index or 0)
+        consts = prepare_constants(covariates)
+        init = _as_f64(initial_state)
+        self.M = int(init.shape[0])
+        self.T = int(num_steps)
+        self.P = 6 + (self.T - 1) + self.M
+        if consts["Cstar"].shape != (self.M, self.M):
+            raise ValueError(f"covariates['C'] must be [{self.M},{self.M}]")
+        self._keep = (consts, init)
+        spec = nat.SeirSpec(
+            num_meta=self.M, num_steps=self.T, initial_step=int(initial_step),
+            n_commute_volume=int(consts["W"].shape[0]), n_weekday=int(consts["weekday_c"].shape[0]),
+            car_nnz=int(consts["car_indices"].shape[0]), time_delta=TIME_DELTA, nu=NU, rate_eps=RATE_EPS,
+            car_log_det_scale=consts["car_log_det_scale"],
+            cstar=_dptr(consts["Cstar"]), population=_dptr(consts["N"]), commute_volume=_dptr(consts["W"]),
+            weekday_c=_dptr(consts["weekday_c"]), log_area_c=_dptr(consts["log_area_c"]), initial_state=_dptr(init),
+            car_indptr=_iptr(consts["car_indptr"]), car_indices=_iptr(consts["car_indices"]),
+            car_values=_dptr(consts["car_values"]),
+        )
+        handle = c_void_p()
+        nat.check(self.lib.seir_model_create(byref(spec), self.device.index, byref(handle)))
+        self._model = handle
+        self._chains: dict[int, c_void_p] = {}
+        self.initial_state = init
+
+    # ---- lifetime ----
+    def close(self):
+        for h in self._chains.values():
+            self.lib.seir_chains_destroy(h)
+        self._chains.clear()
+        if self._model is not None:
+            self.lib.seir_model_destroy(self._model)
+            self._model = None
+
+    def __del__(self):  # pragma: no cover
+        try:
+            self.close()
+        except Exception:
+            pass
+
+    def chains(self, B: int) -> c_void_p:
+        h = self._chains.get(B)
+        if h is None:
+            h = c_void_p()
+            nat.check(self.lib.seir_chains_create(self._model, int(B), byref(h)))
+            self._chains[B] = h
+        return h
+
+    def chains_bytes(self, B: int) -> int:
+        return int(self.lib.seir_chains_bytes(self.chains(B)))
+
+    # ---- helpers ----
+    def _stream(self):
+        return c_void_p(torch.cuda.current_stream(self.device).cuda_stream)
+
+    def to_device(self, a, shape_tail):
+        """numpy / torch -> contiguous float64 CUDA tensor with a leading chain axis."""
+        t = a if isinstance(a, torch.Tensor) else torch.from_numpy(np.asarray(a, dtype=np.float64))
+        t = t.to(device=self.device, dtype=torch.float64)
+        if t.dim() == len(shape_tail):
+            t = t.unsqueeze(0)
+        if tuple(t.shape[1:]) != tuple(shape_tail):
+            raise ValueError(f"expected trailing shape {tuple(shape_tail)}, got {tuple(t.shape)}")
+        return t.contiguous()
+
+    # ---- a1 ----
+    def compute_state(self, events: torch.Tensor) -> torch.Tensor:
+        ev = self.to_device(events, (self.M, self.T, 3))
+        out = torch.empty((ev.shape[0], self.M, self.T, 4), dtype=torch.float64, device=self.device)
+        nat.check(self.lib.seir_compute_state(self._model, ev.shape[0], c_void_p(ev.data_ptr()), c_void_p(out.data_ptr()), self._stream()))
+        return out
+
+    # ---- a4 / a5 ----
+    def ingest(self, events: torch.Tensor):
+        ev = self.to_device(events, (self.M, self.T, 3))
+        nat.check(self.lib.seir_ingest_events(self.chains(ev.shape[0]), c_void_p(ev.data_ptr()), self._stream()))
+        return ev.shape[0]
+
+    def log_prob_cached(self, theta, kind=nat.THETA_CONSTRAINED, parts=nat.PART_SEIR):
+        th = self.to_device(theta, (self.P,))
+        out = torch.empty((th.shape[0],), dtype=torch.float64, device=self.device)
+        nat.check(self.lib.seir_log_prob_cached(self.chains(th.shape[0]), c_void_p(th.data_ptr()), kind, parts, c_void_p(out.data_ptr()), self._stream()))
+        return out
+
+    def log_prob(self, events, theta, kind=nat.THETA_CONSTRAINED, parts=nat.PART_SEIR, out=None):
+        ev = self.to_device(events, (self.M, self.T, 3))
+        th = self.to_device(theta, (self.P,))
+        if th.shape[0] != ev.shape[0]:
+            raise ValueError("events and theta disagree on the number of chains")
+        if out is None:
+            out = torch.empty((th.shape[0],), dtype=torch.float64, device=self.device)
+        nat.check(self.lib.seir_log_prob(self.chains(ev.shape[0]), c_void_p(ev.data_ptr()), c_void_p(th.data_ptr()), kind, parts, c_void_p(out.data_ptr()), self._stream()))
+        return out
+
+    def value_and_grad_cached(self, theta, kind=nat.THETA_UNCONSTRAINED, parts=nat.PART_JOINT):
+        th = self.to_device(theta, (self.P,))
+        out = torch.empty((th.shape[0],), dtype=torch.float64, device=self.device)
+        grad = torch.empty_like(th)
+        nat.check(self.lib.seir_log_prob_grad_cached(self.chains(th.shape[0]), c_void_p(th.data_ptr()), kind, parts, c_void_p(out.data_ptr()), c_void_p(grad.data_ptr()), self._stream()))
+        return out, grad
+
+    def log_prob_host(self, h_events: torch.Tensor, h_theta: torch.Tensor, h_out: torch.Tensor, kind=nat.THETA_CONSTRAINED, parts=nat.PART_SEIR):
+        """Host-buffer entry point: (pinned) CPU tensors in, CPU tensor out, synchronous."""
+        B = h_events.shape[0]
+        assert h_events.dtype == torch.float64 and h_events.is_contiguous() and not h_events.is_cuda
+        nat.check(self.lib.seir_log_prob_host(self.chains(B), c_void_p(h_events.data_ptr()), c_void_p(h_theta.data_ptr()), kind, parts, c_void_p(h_out.data_ptr())))
+        return h_out
+
+    def run_stage(self, B, stage, events=None, theta=None, kind=nat.THETA_CONSTRAINED, parts=nat.PART_SEIR, out=None, grad=None):
+        """Enqueue one kernel of the pipeline (measurement hook, see seir_run_stage)."""
+        ptr = lambda t: c_void_p(t.data_ptr()) if t is not None else c_void_p(0)
+        nat.check(self.lib.seir_run_stage(self.chains(B), stage, ptr(events), ptr(theta), kind, parts, ptr(out), ptr(grad), self._stream()))
+
+    def chain_flags(self, B: int) -> torch.Tensor:
+        out = torch.empty((B,), dtype=torch.int32, device=self.device)
+        nat.check(self.lib.seir_chain_flags(self.chains(B), c_void_p(out.data_ptr()), self._stream()))
+        return out

@@ -1,0 +1,146 @@
+/*
+ * seir_b200.h -- C ABI of the B200-native covid19uk MCMC likelihood hot path.
+ *
+ * The reference (chrism0dwk/covid19uk) has no FFI layer: its boundary for this path is the Python
+ * API between `covid19uk` and gemlib / TensorFlow-Probability.  Each entry point below names the
+ * reference interface it stands behind (file:line under /root/reference).  The Python mirror of that
+ * interface lives in covid19uk_b200/ and binds these symbols with ctypes (INTEGRATION.md shows the
+ * stub a maintainer of the reference would add).
+ *
+ * Conventions
+ *   - plain pointers and sizes only; `d_` = device pointer, `h_` = host pointer;
+ *   - all device work is enqueued on the caller's stream (`stream` is a cudaStream_t passed as void*;
+ *     NULL = legacy default stream); no call synchronises unless it says so;
+ *   - every function returns 0 on success or a negative seir_status; seir_last_error() gives the text;
+ *   - dtype of the path is float64 (`DTYPE = np.float64`, model_spec.py:22); events are float64
+ *     integer-valued tensors laid out [B, M, T, X] (chains, metapopulations, days, transitions;
+ *     model_spec.py:118-126, inference.py:513); X = 3 (S->E, E->I, I->R), 4 states (S,E,I,R);
+ *   - parameter vectors are [B, P], P = 6 + (T-1) + M, in the order psi, sigma_space, beta_area,
+ *     gamma0, gamma1, alpha_0, alpha_t[T-1], spatial_effect[M] (inference.py:540-553).
+ */
+#ifndef SEIR_B200_H
+#define SEIR_B200_H
+
+#include <stdint.h>
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+#define SEIR_B200_ABI_VERSION 3
+
+typedef enum seir_status {
+  SEIR_OK = 0,
+  SEIR_ERR_BAD_ARG = -1,     /* NULL pointer, non-positive size */
+  SEIR_ERR_SHAPE = -2,       /* M/T/B outside what the kernels support */
+  SEIR_ERR_ALIGN = -3,       /* device pointer not 16-byte aligned */
+  SEIR_ERR_CUDA = -4,        /* a CUDA runtime call failed (text in seir_last_error) */
+  SEIR_ERR_UNSUPPORTED = -5  /* option not implemented */
+} seir_status;
+
+/* What `theta` holds (inference.py:525-557). */
+#define SEIR_THETA_CONSTRAINED 0   /* model parameters as passed to CovidUK(...).log_prob */
+#define SEIR_THETA_UNCONSTRAINED 1 /* the MCMC state: softplus(+eps) bijector applied to the first two */
+
+/* Which terms of the joint density are summed into the output (model_spec.py:287-299, inference.py:555-557). */
+#define SEIR_PART_SEIR 1   /* DiscreteTimeStateTransitionModel.log_prob(events)            */
+#define SEIR_PART_PRIORS 2 /* the eight prior nodes of the JointDistributionNamed           */
+#define SEIR_PART_ILDJ 4   /* + param_bij.inverse_log_det_jacobian (needs UNCONSTRAINED)     */
+#define SEIR_PART_JOINT (SEIR_PART_SEIR | SEIR_PART_PRIORS | SEIR_PART_ILDJ)
+
+/* Host-side description of one model: the data `CovidUK(covariates, initial_state, initial_step,
+ * num_steps)` closes over (model_spec.py:139-299) after the one-off host preparation of
+ * model_spec.py:212-230 (Cstar, centred weekday, centred log-area).  All pointers are HOST memory and
+ * are copied; the caller may free them after seir_model_create returns. */
+typedef struct seir_spec {
+  int32_t num_meta;               /* M                                                          */
+  int32_t num_steps;              /* T   (CovidUK num_steps)                                    */
+  int32_t initial_step;           /* CovidUK initial_step (0 in inference.py:521)               */
+  int32_t n_commute_volume;       /* length of commute_volume                                   */
+  int32_t n_weekday;              /* length of weekday_c                                        */
+  int32_t car_nnz;                /* non-zeros of the CAR precision in CSR                      */
+  double time_delta;              /* TIME_DELTA, model_spec.py:25                               */
+  double nu;                      /* NU, model_spec.py:26                                       */
+  double rate_eps;                /* the +1e-9 of model_spec.py:266                             */
+  double car_log_det_scale;       /* sum(log(diag(cholesky(inv(Dw - rho W))))), model_spec.py:171-181 */
+  const double* cstar;            /* [M*M] row-major, model_spec.py:216-219                     */
+  const double* population;       /* N [M]                                                      */
+  const double* commute_volume;   /* W [n_commute_volume]                                       */
+  const double* weekday_c;        /* centred weekday indicator [n_weekday], model_spec.py:224-225 */
+  const double* log_area_c;       /* centred log(area/1e8) [M], model_spec.py:228-230           */
+  const double* initial_state;    /* [M*4] integer-valued                                       */
+  const int32_t* car_indptr;      /* CSR of precision = Dw - rho W  [M+1]                       */
+  const int32_t* car_indices;     /* [car_nnz]                                                  */
+  const double* car_values;       /* [car_nnz]                                                  */
+} seir_spec;
+
+typedef struct seir_model seir_model;   /* immutable model data resident on one device          */
+typedef struct seir_chains seir_chains; /* per-chain caches + workspace for B chains of one model */
+
+int seir_abi_version(void);
+const char* seir_last_error(void);
+
+/* ---- model / chain-set lifetime -------------------------------------------------------------- */
+/* stands behind: model_spec.CovidUK(covariates, initial_state, initial_step, num_steps), model_spec.py:139 */
+int seir_model_create(const seir_spec* spec, int device, seir_model** out);
+void seir_model_destroy(seir_model* model);
+int seir_model_dims(const seir_model* model, int32_t* M, int32_t* T, int32_t* P, int32_t* M_padded);
+
+/* B independent chains (new leading dimension; the reference is single-chain, inference.py:563-576). */
+int seir_chains_create(const seir_model* model, int num_chains, seir_chains** out);
+void seir_chains_destroy(seir_chains* chains);
+/* bytes of device memory held by the chain set (caches + workspace) */
+int64_t seir_chains_bytes(const seir_chains* chains);
+
+/* ---- a1: gemlib.util.compute_state(initial_state, events, stoichiometry) ---------------------- */
+/* call sites inference.py:500-510, predict.py:32, reproduction_number.py:28, within_between.py:74.
+ * d_events [B,M,T,3] f64 -> d_state [B,M,T,4] f64 (state BEFORE the events of day t; exclusive cumsum). */
+int seir_compute_state(const seir_model* model, int num_chains, const double* d_events, double* d_state,
+                       void* stream);
+
+/* ---- a4/a5: log-probability ------------------------------------------------------------------- */
+/* Refresh every events-only cache of the chain set from d_events [B,M,T,3]: compact events, the
+ * integer-exact state, the commuting contraction Cstar.(I/N) (model_spec.py:262) and the
+ * parameter-free part of the log-pmf.  (This is the "cold" half of an evaluation.) */
+int seir_ingest_events(seir_chains* chains, const double* d_events, void* stream);
+
+/* Evaluate the selected parts at d_theta [B,P] against the cached events ("warm" half; this is what
+ * HMC calls 17x per sweep with events fixed, mcmc_kernel_factory.py:14-29).  d_out [B]. */
+int seir_log_prob_cached(seir_chains* chains, const double* d_theta, int theta_kind, int parts,
+                         double* d_out, void* stream);
+
+/* stands behind: DiscreteTimeStateTransitionModel.log_prob(events) (model_spec.py:278-285),
+ * CovidUK(...).log_prob(dict) (model_spec.py:287-299) and joint_log_prob(unconstrained_params, events)
+ * (inference.py:537-557) depending on `parts`.  = seir_ingest_events + seir_log_prob_cached. */
+int seir_log_prob(seir_chains* chains, const double* d_events, const double* d_theta, int theta_kind,
+                  int parts, double* d_out, void* stream);
+
+/* Same call with HOST buffers: copies events/theta in, evaluates, copies [B] results out and
+ * synchronises.  h_events [B,M,T,3], h_theta [B,P], h_out [B].  (bench.py's end-to-end figure.) */
+int seir_log_prob_host(seir_chains* chains, const double* h_events, const double* h_theta, int theta_kind,
+                       int parts, double* h_out);
+
+/* a5 + a9: value and gradient w.r.t. theta of the selected parts against the cached events
+ * (TF autodiff through joint_log_prob in the reference; HMC leapfrog, mcmc_kernel_factory.py:20-27).
+ * d_out [B], d_grad [B,P]. */
+int seir_log_prob_grad_cached(seir_chains* chains, const double* d_theta, int theta_kind, int parts,
+                              double* d_out, double* d_grad, void* stream);
+
+/* Per-chain status bits set by ingest / commits: bit0 = events not non-negative integers,
+ * bit1 = reconstructed state negative or events exceed the source compartment (log-prob = -inf). */
+int seir_chain_flags(const seir_chains* chains, int32_t* d_flags_out, void* stream);
+
+/* Measurement hook: enqueue exactly ONE kernel of the pipeline on `stream` (bench.py times each kernel
+ * with CUDA events for the roofline).  stage: 0 ingest (state + caches), 1 contraction, 2 theta prep,
+ * 3 S->E log-likelihood, 4 S->E log-likelihood + gradient pieces, 5 finalize (value),
+ * 6 finalize (value + gradient; d_grad required). */
+int seir_run_stage(seir_chains* chains, int stage, const double* d_events, const double* d_theta, int theta_kind,
+                   int parts, double* d_out, double* d_grad, void* stream);
+
+/* number of kernels launched by this library since load (bench.py's gpu_launches) */
+int64_t seir_launch_count(void);
+
+#ifdef __cplusplus
+}
+#endif
+#endif /* SEIR_B200_H */
