@@ -83,6 +83,8 @@ __global__ void __launch_bounds__(256) seir_ingest_kernel(int M, int T, int Mp, 
   int* ev = smem_i;                    // [32][STRIDE]
   int* segsum = smem_i + 32 * STRIDE;  // [8][3][32]
   __shared__ double red[32];
+  __shared__ double lgs[SEIR_LGTAB];   // lgamma(k+1) table staged in shared memory (per-lane gathers)
+  for (int k = threadIdx.x; k < SEIR_LGTAB; k += blockDim.x) lgs[k] = lgtab[k];
 
   const int b = blockIdx.y, m0 = blockIdx.x * 32;
   const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
@@ -143,7 +145,9 @@ __global__ void __launch_bounds__(256) seir_ingest_kernel(int M, int T, int Mp, 
       if (!ok) bad |= 2;
       int ry = 0, rr = 0;
       if (live && ok) {
-        acc += log_binom_coef(S, y0, lgtab) + log_binom_coef(E, y1, lgtab) + log_binom_coef(I, y2, lgtab);
+        // S only ever decreases, so sum_t [lgamma(S_t+1) - lgamma(S_t-y_t+1)] telescopes to
+        // lgamma(S_0+1) - lgamma(S_T+1) (added once per metapopulation below); per cell only -lgamma(y+1) remains.
+        acc += log_binom_coef(E, y1, lgs) + log_binom_coef(I, y2, lgs) - (y0 < SEIR_LGTAB ? lgs[y0] : lgamma1p_int(y0, lgs));
         accYei += y1;
         accEres += E - y1;
         ry = y2;
@@ -160,6 +164,8 @@ __global__ void __launch_bounds__(256) seir_ingest_kernel(int M, int T, int Mp, 
     carry0 += tot0; carry1 += tot1; carry2 += tot2;
     __syncthreads();
   }
+  // telescoped S->E coefficient term, once per metapopulation (carry0 = all S->E events of the row)
+  if (warp == 0 && live && carry0 >= 0 && carry0 <= S0) acc += lgamma_diff_exact(S0, carry0, lgs);
   // ---- per-CTA reductions ----
   const double tot = block_sum(acc, red);
   if (threadIdx.x == 0) llc_part[(size_t)b * gridDim.x + blockIdx.x] = tot;

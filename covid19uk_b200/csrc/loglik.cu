@@ -106,98 +106,141 @@ int seir_launch_theta_prep(seir_chains* c, const double* d_theta, int kind, int 
 // S->E term:  sum_{t,m} y log(1-exp(-lam dt)) - (S-y) lam dt,
 //   lam = exp(a_t + beta la_m + sigma s_m) (I + psi W_t Bc) / N_m + eps        (model_spec.py:257-266)
 // Day-slab caches => for a fixed day the 32 lanes of a warp read 32 consecutive metapopulations.
+// grid = (metapopulation blocks, chains, day splits); the day split is chosen at launch so that the grid
+// fills the resident-CTA slots of the 148 SMs once.
+//
+// For x = lam*dt < 0.05 (always, for realistic infection hazards) the two transcendentals expm1+log are
+// replaced by one log plus even-power series (truncation < 1e-17):
+//   log(1-e^-x) = log x - x/2 + x^2/24 - x^4/2880 + x^6/181440
+//   1/expm1(x)  = 1/x - 1/2 + x/12 - x^3/720 + x^5/30240
 // ------------------------------------------------------------------------------------------------
+#define LL_SMALL_X 0.05
+
 template <bool GRAD>
-__global__ void __launch_bounds__(SEIR_LL_THREADS) seir_loglik_kernel(
-    int T, int Mp, double dt, double eps, const int* __restrict__ yse, const int* __restrict__ Sx, const int* __restrict__ Ix,
-    const double* __restrict__ Bc, const double* __restrict__ pa, const double* __restrict__ psiW, const double* __restrict__ W,
-    const double* __restrict__ pm, double* __restrict__ val_part, double* __restrict__ psi_part, double* __restrict__ col_part,
-    double* __restrict__ rowsum) {
+__global__ void __launch_bounds__(SEIR_LL_THREADS, GRAD ? 10 : 16) seir_loglik_kernel(
+    int T, int Mp, int dps, double dt, double eps, const int* __restrict__ yse, const int* __restrict__ Sx,
+    const int* __restrict__ Ix, const double* __restrict__ Bc, const double* __restrict__ pa, const double* __restrict__ psiW,
+    const double* __restrict__ W, const double* __restrict__ pm, double* __restrict__ val_part, double* __restrict__ psi_part,
+    double* __restrict__ col_part, double* __restrict__ rowsum_part) {
   extern __shared__ double sm[];
-  double* pa_s = sm;            // [T]
-  double* pw_s = sm + T;        // [T]
-  double* w_s = sm + 2 * T;     // [T]            (GRAD)
-  double* colw = sm + 3 * T;    // [nwarps][T]    (GRAD)
+  double* pa_s = sm;             // [dps]
+  double* pw_s = sm + dps;       // [dps]
+  double* w_s = sm + 2 * dps;    // [dps]            (GRAD)
+  double* colw = sm + 3 * dps;   // [nwarps][dps]    (GRAD)
   __shared__ double red[32];
   const int b = blockIdx.y, tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
   const int m = blockIdx.x * SEIR_LL_THREADS + tid;
   const bool active = m < Mp;
-  for (int t = tid; t < T; t += SEIR_LL_THREADS) {
-    pa_s[t] = pa[(size_t)b * T + t];
-    pw_s[t] = psiW[(size_t)b * T + t];
-    if (GRAD) w_s[t] = W[t];
+  const int tb = blockIdx.z * dps, nt = min(dps, T - tb);
+  for (int t = tid; t < nt; t += SEIR_LL_THREADS) {
+    pa_s[t] = pa[(size_t)b * T + tb + t];
+    pw_s[t] = psiW[(size_t)b * T + tb + t];
+    if (GRAD) w_s[t] = W[tb + t];
   }
   __syncthreads();
   const double pm_m = active ? pm[(size_t)b * Mp + m] : 0.0;
-  const size_t base = (size_t)b * T * Mp + (active ? m : 0);
+  const size_t base = ((size_t)b * T + tb) * Mp + (active ? m : 0);
   double val = 0.0, row = 0.0, psig = 0.0;
 #pragma unroll 4
-  for (int t = 0; t < T; ++t) {
+  for (int t = 0; t < nt; ++t) {
     const size_t o = base + (size_t)t * Mp;
     int y = 0, S = 0, I = 0;
     double bc = 0.0;
     if (active) {
-      y = yse[o];
-      S = Sx[o];
-      I = Ix[o];
-      bc = Bc[o];
+      y = __ldg(yse + o);
+      S = __ldg(Sx + o);
+      I = __ldg(Ix + o);
+      bc = __ldg(Bc + o);
     }
     const double e = pa_s[t] * pm_m;
     const double X = (double)I + pw_s[t] * bc;
     const double lam = fma(e, X, eps);
-    const double ldt = lam * dt;
-    const double em = expm1(-ldt);  // -(1-exp(-lam dt)) = -p
+    const double x = lam * dt;
     const double yd = (double)y, rd = (double)(S - y);
-    double term = -rd * ldt;
-    if (y > 0) term += yd * log(-em);
+    double term = -rd * x;
+    double g = -rd;
+    if (x > 0.0 && x < LL_SMALL_X) {
+      const double x2 = x * x;
+      if (y > 0) term += yd * (log(x) + fma(x2, fma(x2, fma(x2, 5.511463844797178e-06, -3.472222222222222e-04), 0.041666666666666664), -0.5 * x));
+      if (GRAD && y > 0)
+        g += yd * (1.0 / x - 0.5 + x * fma(x2, fma(x2, 3.306878306878307e-05, -1.388888888888889e-03), 0.08333333333333333));
+    } else {
+      const double em = expm1(-x);  // -(1-exp(-x)) = -p ; NaN log for x < 0 like the reference
+      if (y > 0) term += yd * log(-em);
+      if (GRAD && y > 0) g += yd * (1.0 + em) / (-em);
+    }
     val += term;
     if (GRAD) {
-      double g = -rd;
-      if (y > 0) g += yd * (1.0 + em) / (-em);  // y / expm1(lam dt)
       g *= dt;
       const double h = g * (lam - eps);
       row += h;
       psig += g * e * w_s[t] * bc;
       const double hs = warp_sum(h);
-      if (lane == 0) colw[warp * T + t] = hs;
+      if (lane == 0) colw[warp * dps + t] = hs;
     }
   }
-  const int nblk = gridDim.x;
+  const int slot = blockIdx.z * gridDim.x + blockIdx.x, nslot = gridDim.x * gridDim.z;
   const double v = block_sum(val, red);
-  if (tid == 0) val_part[(size_t)b * nblk + blockIdx.x] = v;
+  if (tid == 0) val_part[(size_t)b * nslot + slot] = v;
   if (GRAD) {
     const double pg = block_sum(psig, red);
-    if (tid == 0) psi_part[(size_t)b * nblk + blockIdx.x] = pg;
-    if (active) rowsum[(size_t)b * Mp + m] = row;
+    if (tid == 0) psi_part[(size_t)b * nslot + slot] = pg;
+    if (active) rowsum_part[((size_t)b * gridDim.z + blockIdx.z) * Mp + m] = row;
     __syncthreads();
-    for (int t = tid; t < T; t += SEIR_LL_THREADS) {
+    for (int t = tid; t < nt; t += SEIR_LL_THREADS) {
       double cta = 0.0;
 #pragma unroll
-      for (int w = 0; w < SEIR_LL_THREADS / 32; ++w) cta += colw[w * T + t];
-      col_part[((size_t)b * nblk + blockIdx.x) * T + t] = cta;
+      for (int w = 0; w < SEIR_LL_THREADS / 32; ++w) cta += colw[w * dps + t];
+      col_part[((size_t)b * gridDim.x + blockIdx.x) * T + tb + t] = cta;
     }
   }
 }
 
+// day splits so that (metapopulation blocks x chains x splits) fills the resident CTA slots once
+static int choose_splits(const seir_chains* c, bool grad) {
+  static int slots[2] = {0, 0};
+  if (!slots[grad]) {
+    int dev = 0, sms = 148, per = 8;
+    cudaGetDevice(&dev);
+    cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev);
+    if (grad)
+      cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per, seir_loglik_kernel<true>, SEIR_LL_THREADS, 8 * 1024);
+    else
+      cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per, seir_loglik_kernel<false>, SEIR_LL_THREADS, 2 * 1024);
+    slots[grad] = sms * (per > 0 ? per : 1);
+  }
+  const int T = c->model->T;
+  long long base = (long long)c->nblkLL * c->B;
+  int ts = (int)(slots[grad] / base);
+  const int cap = (T + 3) / 4 < SEIR_MAX_SPLITS ? (T + 3) / 4 : SEIR_MAX_SPLITS;
+  if (ts > cap) ts = cap;
+  if (ts < 1) ts = 1;
+  return ts;
+}
+
 int seir_launch_loglik(seir_chains* c, bool grad, cudaStream_t s) {
   const seir_model* m = c->model;
-  dim3 grid(c->nblkLL, c->B);
-  const size_t smem = sizeof(double) * (size_t)m->T * (grad ? 3 + SEIR_LL_THREADS / 32 : 2);
+  const int ts = choose_splits(c, grad);
+  const int dps = (m->T + ts - 1) / ts;
+  const int nts = (m->T + dps - 1) / dps;
+  c->nts = nts;
+  dim3 grid(c->nblkLL, c->B, nts);
+  const size_t smem = sizeof(double) * (size_t)dps * (grad ? 3 + SEIR_LL_THREADS / 32 : 2);
   if (grad)
-    seir_loglik_kernel<true><<<grid, SEIR_LL_THREADS, smem, s>>>(m->T, m->Mp, m->dt, m->rate_eps, c->d_yse, c->d_S, c->d_I, c->d_Bc,
-                                                                 c->d_pa, c->d_psiW, m->d_W, c->d_pm, c->d_val_part, c->d_psi_part,
-                                                                 c->d_col_part, c->d_rowsum);
+    seir_loglik_kernel<true><<<grid, SEIR_LL_THREADS, smem, s>>>(m->T, m->Mp, dps, m->dt, m->rate_eps, c->d_yse, c->d_S, c->d_I,
+                                                                 c->d_Bc, c->d_pa, c->d_psiW, m->d_W, c->d_pm, c->d_val_part,
+                                                                 c->d_psi_part, c->d_col_part, c->d_rowsum);
   else
-    seir_loglik_kernel<false><<<grid, SEIR_LL_THREADS, smem, s>>>(m->T, m->Mp, m->dt, m->rate_eps, c->d_yse, c->d_S, c->d_I, c->d_Bc,
-                                                                  c->d_pa, c->d_psiW, m->d_W, c->d_pm, c->d_val_part, c->d_psi_part,
-                                                                  c->d_col_part, c->d_rowsum);
+    seir_loglik_kernel<false><<<grid, SEIR_LL_THREADS, smem, s>>>(m->T, m->Mp, dps, m->dt, m->rate_eps, c->d_yse, c->d_S, c->d_I,
+                                                                  c->d_Bc, c->d_pa, c->d_psiW, m->d_W, c->d_pm, c->d_val_part,
+                                                                  c->d_psi_part, c->d_col_part, c->d_rowsum);
   seir_count_launch(1);
   return seir_cuda_check(cudaGetLastError(), "seir_loglik_kernel");
 }
 
 // ------------------------------------------------------------------------------------------------
 __global__ void __launch_bounds__(128) seir_finalize_kernel(
-    int M, int T, int Mp, int P, int nblkLL, int nblk32, double dt, double nu, double log_p_nu, int kind, int parts,
+    int M, int T, int Mp, int P, int nblkLL, int nts, int nblk32, double dt, double nu, double log_p_nu, int kind, int parts,
     const double* __restrict__ theta, const double* __restrict__ scal, const double* __restrict__ val_part,
     const double* __restrict__ llc_part, const long long* __restrict__ Yir, const long long* __restrict__ Rir,
     const long long* __restrict__ sumYei, const long long* __restrict__ sumEres, const int* __restrict__ flags,
@@ -227,7 +270,7 @@ __global__ void __launch_bounds__(128) seir_finalize_kernel(
     double v = sc[SC_PRIOR];
     if (want_seir) {
       double s = 0.0;
-      for (int k = 0; k < nblkLL; ++k) s += val_part[(size_t)b * nblkLL + k];
+      for (int k = 0; k < nblkLL * nts; ++k) s += val_part[(size_t)b * nblkLL * nts + k];
       double l = 0.0;
       for (int k = 0; k < nblk32; ++k) l += llc_part[(size_t)b * nblk32 + k];
       const double yei = (double)sumYei[b], eres = (double)sumEres[b];
@@ -257,7 +300,9 @@ __global__ void __launch_bounds__(128) seir_finalize_kernel(
   __syncthreads();
   double gb = 0.0, gs = 0.0;
   for (int m = tid; m < M; m += blockDim.x) {
-    const double r = want_seir ? rowsum[(size_t)b * Mp + m] : 0.0;
+    double r = 0.0;
+    if (want_seir)
+      for (int z = 0; z < nts; ++z) r += rowsum[((size_t)b * nts + z) * Mp + m];
     gb += r * la[m];
     gs += r * sp[m];
     double gm = sigma * r;
@@ -296,7 +341,7 @@ __global__ void __launch_bounds__(128) seir_finalize_kernel(
     }
     double gpsi = 0.0;
     if (want_seir)
-      for (int k = 0; k < nblkLL; ++k) gpsi += psi_part[(size_t)b * nblkLL + k];
+      for (int k = 0; k < nblkLL * nts; ++k) gpsi += psi_part[(size_t)b * nblkLL * nts + k];
     double gsg = gsigma, gbt = gbeta, gga0 = gg0, gga1 = gg1;
     if (want_prior) {
       gpsi += 2.0 / sc[SC_PSI] - 10.0;
@@ -319,7 +364,7 @@ int seir_launch_finalize(seir_chains* c, const double* d_theta, int kind, int pa
                          cudaStream_t s) {
   const seir_model* m = c->model;
   seir_finalize_kernel<<<c->B, 128, sizeof(double) * 2 * m->T, s>>>(
-      m->M, m->T, m->Mp, m->P, c->nblkLL, c->nblk32, m->dt, m->nu, m->log_p_nu, kind, parts, d_theta, c->d_scal, c->d_val_part,
+      m->M, m->T, m->Mp, m->P, c->nblkLL, c->nts, c->nblk32, m->dt, m->nu, m->log_p_nu, kind, parts, d_theta, c->d_scal, c->d_val_part,
       c->d_llc_part, c->d_Yir, c->d_Rir, c->d_sumYei, c->d_sumEres, c->d_flags, c->d_gam, c->d_logpir, m->d_wk, m->d_aidx, m->d_la,
       c->d_psi_part, c->d_col_part, c->d_rowsum, m->d_car_indptr, m->d_car_indices, m->d_car_values, d_out, d_grad);
   seir_count_launch(1);

@@ -93,8 +93,8 @@ int seir_model_create(const seir_spec* spec, int device, seir_model** out) {
   std::vector<double> cstar((size_t)Mp * Mp, 0.0), rN(Mp, 0.0), la(Mp, 0.0), W(T), wk(T), lgtab(SEIR_LGTAB);
   std::vector<int> init((size_t)Mp * 4, 0), aidx(T);
   for (int i = 0; i < M; ++i) {
-    memcpy(&cstar[(size_t)i * Mp], &spec->cstar[(size_t)i * M], sizeof(double) * M);
     rN[i] = 1.0 / spec->population[i];
+    for (int j = 0; j < M; ++j) cstar[(size_t)i * Mp + j] = spec->cstar[(size_t)i * M + j] * rN[i];
     la[i] = spec->log_area_c[i];
     for (int s = 0; s < 4; ++s) {
       const double v = spec->initial_state[i * 4 + s];
@@ -125,7 +125,7 @@ int seir_model_create(const seir_spec* spec, int device, seir_model** out) {
   std::vector<double> values(spec->car_values, spec->car_values + spec->car_nnz);
 
   int rc = SEIR_OK;
-  if ((rc = dev_upload(&m->d_cstar, cstar)) || (rc = dev_upload(&m->d_rN, rN)) || (rc = dev_upload(&m->d_W, W)) ||
+  if ((rc = dev_upload(&m->d_cs, cstar)) || (rc = dev_upload(&m->d_rN, rN)) || (rc = dev_upload(&m->d_W, W)) ||
       (rc = dev_upload(&m->d_wk, wk)) || (rc = dev_upload(&m->d_aidx, aidx)) || (rc = dev_upload(&m->d_la, la)) ||
       (rc = dev_upload(&m->d_init, init)) || (rc = dev_upload(&m->d_car_indptr, indptr)) ||
       (rc = dev_upload(&m->d_car_indices, indices)) || (rc = dev_upload(&m->d_car_values, values)) ||
@@ -140,7 +140,7 @@ int seir_model_create(const seir_spec* spec, int device, seir_model** out) {
 void seir_model_destroy(seir_model* m) {
   if (!m) return;
   cudaSetDevice(m->device);
-  cudaFree(m->d_cstar); cudaFree(m->d_rN); cudaFree(m->d_W); cudaFree(m->d_wk); cudaFree(m->d_aidx); cudaFree(m->d_la);
+  cudaFree(m->d_cs); cudaFree(m->d_rN); cudaFree(m->d_W); cudaFree(m->d_wk); cudaFree(m->d_aidx); cudaFree(m->d_la);
   cudaFree(m->d_init); cudaFree(m->d_car_indptr); cudaFree(m->d_car_indices); cudaFree(m->d_car_values); cudaFree(m->d_lgtab);
   delete m;
 }
@@ -166,6 +166,7 @@ int seir_chains_create(const seir_model* m, int B, seir_chains** out) {
   c->B = B;
   c->nblk32 = m->Mp / 32;
   c->nblkLL = (m->Mp + SEIR_LL_THREADS - 1) / SEIR_LL_THREADS;
+  c->nts = 1;
   const size_t cells = (size_t)B * m->T * m->Mp, BT = (size_t)B * m->T;
   int rc = SEIR_OK;
   if ((rc = dev_alloc(&c->d_yse, cells, &c->bytes)) || (rc = dev_alloc(&c->d_yei, cells, &c->bytes)) ||
@@ -178,10 +179,10 @@ int seir_chains_create(const seir_model* m, int B, seir_chains** out) {
       (rc = dev_alloc(&c->d_psiW, BT, &c->bytes)) || (rc = dev_alloc(&c->d_gam, BT, &c->bytes)) ||
       (rc = dev_alloc(&c->d_logpir, BT, &c->bytes)) || (rc = dev_alloc(&c->d_pm, (size_t)B * m->Mp, &c->bytes)) ||
       (rc = dev_alloc(&c->d_scal, (size_t)B * SEIR_NSCAL, &c->bytes)) ||
-      (rc = dev_alloc(&c->d_val_part, (size_t)B * c->nblkLL, &c->bytes)) ||
-      (rc = dev_alloc(&c->d_psi_part, (size_t)B * c->nblkLL, &c->bytes)) ||
+      (rc = dev_alloc(&c->d_val_part, (size_t)B * c->nblkLL * SEIR_MAX_SPLITS, &c->bytes)) ||
+      (rc = dev_alloc(&c->d_psi_part, (size_t)B * c->nblkLL * SEIR_MAX_SPLITS, &c->bytes)) ||
       (rc = dev_alloc(&c->d_col_part, (size_t)B * c->nblkLL * m->T, &c->bytes)) ||
-      (rc = dev_alloc(&c->d_rowsum, (size_t)B * m->Mp, &c->bytes))) {
+      (rc = dev_alloc(&c->d_rowsum, (size_t)B * m->Mp * SEIR_MAX_SPLITS, &c->bytes))) {
     seir_chains_destroy(c);
     return rc;
   }

@@ -12,6 +12,7 @@
 #define SEIR_INGEST_TC 128   // days per ingest chunk
 #define SEIR_LL_THREADS 128  // metapopulations per CTA in the log-likelihood kernel
 #define SEIR_NSCAL 16        // per-chain scalar slots
+#define SEIR_MAX_SPLITS 16    // max day splits of the log-likelihood grid
 
 // per-chain scalar slots (d_scal[b*SEIR_NSCAL + k])
 enum {
@@ -31,7 +32,7 @@ struct seir_model {
   double log_p_nu;  // log(1 - exp(-nu*dt))
   int car_nnz;
   // device arrays
-  double* d_cstar;     // [Mp*Mp] zero padded, symmetric
+  double* d_cs;        // [Mp*Mp] zero padded: Cs[j][i] = Cstar[j][i] / N[j]  (Cstar symmetric, model_spec.py:216-219)
   double* d_rN;        // [Mp] 1/N, 0 in the padding
   double* d_W;         // [T] commute volume resolved per step (model_spec.py:234-235)
   double* d_wk;        // [T] centred weekday resolved per step (model_spec.py:237-240)
@@ -49,6 +50,7 @@ struct seir_chains {
   int B;
   int nblk32;   // Mp/32   (ingest CTAs per chain)
   int nblkLL;   // ceil(Mp/SEIR_LL_THREADS)
+  int nts;      // day splits used by the last log-likelihood launch
   int64_t bytes;
   // events-only caches, day-slab layout [B][T][Mp]
   int *d_yse, *d_yei, *d_yir, *d_S, *d_E, *d_I;
@@ -64,10 +66,10 @@ struct seir_chains {
   double* d_pm;                              // [B][Mp]
   double* d_scal;                            // [B][SEIR_NSCAL]
   // reductions
-  double* d_val_part;  // [B][nblkLL]
-  double* d_psi_part;  // [B][nblkLL]
+  double* d_val_part;  // [B][nts*nblkLL]
+  double* d_psi_part;  // [B][nts*nblkLL]
   double* d_col_part;  // [B][nblkLL][T]
-  double* d_rowsum;    // [B][Mp]
+  double* d_rowsum;    // [B][nts][Mp]  per-day-split partial row sums
   // staging for the host-buffer entry points
   double *d_stage_events, *d_stage_theta, *d_stage_out;
 };
@@ -122,25 +124,43 @@ __device__ __forceinline__ double stirling_tail(double x) {
 
 // lgamma(n+1) for integer n >= 0
 __device__ __forceinline__ double lgamma1p_int(int n, const double* __restrict__ lgtab) {
-  if (n < SEIR_LGTAB) return __ldg(lgtab + n);
+  if (n < SEIR_LGTAB) return lgtab[n];
   const double x = (double)n + 1.0;
   return (x - 0.5) * log(x) - x + 0.9189385332046727 + stirling_tail(x);
 }
 
-// log C(n, y) for integers 0 <= y <= n.  For large n-y the difference lgamma(n+1)-lgamma(n-y+1) is
-// formed analytically ((b-1/2) log1p(y/b) + y (log a - 1) + tails, a=n+1, b=n-y+1) so that it does not
-// suffer the catastrophic cancellation of two ~1e7-sized lgamma values.
-__device__ __forceinline__ double log_binom_coef(int n, int y, const double* __restrict__ lgtab) {
+// lgamma(n+1) - lgamma(n-y+1) for integers 0 <= y <= n, formed analytically when n-y is large:
+//   (b-1/2) log1p(y/b) + y (log a - 1) + tail(a) - tail(b),  a = n+1, b = n-y+1
+// (no catastrophic cancellation of two ~1e7-sized lgamma values).  Used once per metapopulation for the
+// telescoped S->E coefficient sum, so its cost does not matter.
+__device__ __forceinline__ double lgamma_diff_exact(int n, int y, const double* __restrict__ lgtab) {
+  if (y == 0) return 0.0;
+  const int r = n - y;
+  if (r >= SEIR_LGTAB) {
+    const double a = (double)n + 1.0, b = (double)r + 1.0, yd = (double)y;
+    return (b - 0.5) * log1p(yd / b) + yd * (log(a) - 1.0) + (stirling_tail(a) - stirling_tail(b));
+  }
+  return lgamma1p_int(n, lgtab) - lgamma1p_int(r, lgtab);
+}
+
+// log C(n, y) for integers 0 <= y <= n; `lgtab` may point to shared memory.
+// Large n-y: Stirling with two logs,  (a-1/2) log a - (b-1/2) log b - y + tail(a) - tail(b),
+// tail(a)-tail(b) = -y/(12ab) + y(a^2+ab+b^2)/(360 a^3 b^3) with 1/(ab) from an FP32 reciprocal
+// (the term is < 1e-4, so the 6e-8 relative error of the reciprocal is < 1e-11 absolute).
+__device__ __forceinline__ double log_binom_coef(int n, int y, const double* lgtab) {
   if (y == 0 || y == n) return 0.0;
   const int r = n - y;
   double d;
   if (r >= SEIR_LGTAB) {
     const double a = (double)n + 1.0, b = (double)r + 1.0, yd = (double)y;
-    d = (b - 0.5) * log1p(yd / b) + yd * (log(a) - 1.0) + (stirling_tail(a) - stirling_tail(b));
+    const double inv = (double)__frcp_rn((float)(a * b));
+    const double t1 = yd * inv;
+    d = (a - 0.5) * log(a) - (b - 0.5) * log(b) - yd;
+    d += t1 * (-0.08333333333333333 + (a * a + a * b + b * b) * inv * inv * 0.002777777777777778);
   } else {
-    d = lgamma1p_int(n, lgtab) - lgamma1p_int(r, lgtab);
+    d = (n < SEIR_LGTAB ? lgtab[n] : lgamma1p_int(n, lgtab)) - lgtab[r];
   }
-  return d - lgamma1p_int(y, lgtab);
+  return d - (y < SEIR_LGTAB ? lgtab[y] : lgamma1p_int(y, lgtab));
 }
 
 #endif  // __CUDACC__
