@@ -244,9 +244,10 @@ def run_native(args):
         hbm_peak, peak_src = _peaks()
         grad_d = torch.empty_like(theta_d)
         kw = dict(events=events_d, theta=theta_d, kind=kind, parts=parts, out=out_d, grad=grad_d)
-        names = {0: "seir_ingest_kernel", 1: "seir_contract_kernel", 2: "seir_theta_prep_kernel", 3: "seir_loglik_kernel<false>",
-                 5: "seir_finalize_kernel", 4: "seir_loglik_kernel<true>"}
-        stage_ms = {s: time_stage(eng, B, s, max(K, 10), **kw) for s in (0, 1, 2, 3, 5, 4)}
+        names = {0: "seir_ingest_kernel", 7: "seir_coef_kernel", 1: "seir_contract_kernel", 2: "seir_theta_prep_kernel",
+                 3: "seir_loglik_kernel<false>", 5: "seir_finalize_kernel", 4: "seir_loglik_kernel<true>"}
+        cold_stages = (0, 7, 1, 2, 3, 5)
+        stage_ms = {s: time_stage(eng, B, s, max(K, 10), **kw) for s in cold_stages + (4,)}
         Mp = (M_UK + 63) // 64 * 64
         P = 6 + T_UK - 1 + M_UK
         cells = B * T_UK * M_UK
@@ -270,7 +271,7 @@ def run_native(args):
             best = min(best, s.elapsed_time(e))
         fp64_peak = 2 * 4096**3 / (best * 1e-3) / 1e12
         kernels = []
-        for sidx in (0, 1, 2, 3, 5):
+        for sidx in cold_stages:
             ent = {"kernel": names[sidx], "ms": stage_ms[sidx]}
             if sidx == 1:
                 ach = flops_contract / (stage_ms[sidx] * 1e-3) / 1e12
@@ -279,7 +280,7 @@ def run_native(args):
                 ach = alg_bytes[sidx] / (stage_ms[sidx] * 1e-3) / 1e9
                 ent.update(bound="hbm", achieved=ach, peak=hbm_peak, unit="GB/s", frac=ach / hbm_peak)
             kernels.append(ent)
-        cold_sum = sum(stage_ms[s] for s in (0, 1, 2, 3, 5))
+        cold_sum = sum(stage_ms[s] for s in cold_stages)
         dom = max((k for k in kernels if "frac" in k), key=lambda k: k["ms"])
         roofline = {"kernel": dom["kernel"], "bound": dom["bound"], "achieved": dom["achieved"], "peak": dom["peak"],
                     "unit": dom["unit"], "frac": dom["frac"], "traffic": None, "share_of_step": dom["ms"] / cold_sum,

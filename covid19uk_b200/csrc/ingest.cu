@@ -63,37 +63,34 @@ int seir_launch_state(const seir_model* m, int B, const double* d_events, double
 }
 
 // ------------------------------------------------------------------------------------------------
-// ingest: CTA = (chain b, 32 metapopulations); 8 warps.  Per chunk of TC days:
+// ingest: CTA = (chain b, 32 metapopulations); 8 warps.  Pure data movement + integer statistics.
+// Per chunk of TC days:
 //   load  : warp-per-row coalesced f64 reads -> int32 tile in shared memory (row stride odd => the
 //           lane<->metapopulation reads below are bank-conflict free)
 //   scan  : lane <-> metapopulation; warp w owns days [w*seg, (w+1)*seg) of the chunk: segment sums,
 //           exchange through shared memory, then a serial pass that emits the day slabs -- every global
 //           store is a full 128-byte line (32 consecutive metapopulations of one day)
+// The FP64 work (log binomial coefficients) lives in seir_coef_kernel below: ncu on the fused version
+// showed 16/32 active lanes (table-vs-Stirling divergence) and 37 % occupancy (profiles/r01_v2_*).
 // ------------------------------------------------------------------------------------------------
 template <int TC>
 __global__ void __launch_bounds__(256) seir_ingest_kernel(int M, int T, int Mp, const int* __restrict__ init,
-                                                          const double* __restrict__ lgtab, const double* __restrict__ events,
-                                                          int* __restrict__ yse, int* __restrict__ yei, int* __restrict__ yir,
-                                                          int* __restrict__ Sx, int* __restrict__ Ex, int* __restrict__ Ix,
-                                                          double* __restrict__ llc_part, long long* __restrict__ Yir,
+                                                          const double* __restrict__ events, int* __restrict__ yse,
+                                                          int* __restrict__ yei, int* __restrict__ yir, int* __restrict__ Sx,
+                                                          int* __restrict__ Ex, int* __restrict__ Ix, long long* __restrict__ Yir,
                                                           long long* __restrict__ Rir, long long* __restrict__ sumYei,
                                                           long long* __restrict__ sumEres, int* __restrict__ flags) {
   constexpr int STRIDE = TC * 3 + 1;
   extern __shared__ int smem_i[];
   int* ev = smem_i;                    // [32][STRIDE]
   int* segsum = smem_i + 32 * STRIDE;  // [8][3][32]
-  __shared__ double red[32];
-  __shared__ double lgs[SEIR_LGTAB];   // lgamma(k+1) table staged in shared memory (per-lane gathers)
-  for (int k = threadIdx.x; k < SEIR_LGTAB; k += blockDim.x) lgs[k] = lgtab[k];
 
   const int b = blockIdx.y, m0 = blockIdx.x * 32;
   const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
   const int m = m0 + lane;
-  const bool live = m < M;
   const int S0 = init[m * 4 + 0], E0 = init[m * 4 + 1], I0 = init[m * 4 + 2];
   int carry0 = 0, carry1 = 0, carry2 = 0;
   int bad = 0;
-  double acc = 0.0;
   long long accYei = 0, accEres = 0;
 
   for (int t0 = 0; t0 < T; t0 += TC) {
@@ -135,6 +132,7 @@ __global__ void __launch_bounds__(256) seir_ingest_kernel(int M, int T, int Mp, 
       tot0 += v0; tot1 += v1; tot2 += v2;
     }
     // ---- emit ----
+#pragma unroll 2
     for (int s = s0; s < s1; ++s) {
       const int y0 = ev[lane * STRIDE + s * 3 + 0], y1 = ev[lane * STRIDE + s * 3 + 1], y2 = ev[lane * STRIDE + s * 3 + 2];
       const int S = S0 - c0, E = E0 + c0 - c1, I = I0 + c1 - c2;
@@ -143,32 +141,19 @@ __global__ void __launch_bounds__(256) seir_ingest_kernel(int M, int T, int Mp, 
       Sx[o] = S; Ex[o] = E; Ix[o] = I;
       const bool ok = (S >= 0) & (E >= 0) & (I >= 0) & (y0 <= S) & (y1 <= E) & (y2 <= I);
       if (!ok) bad |= 2;
-      int ry = 0, rr = 0;
-      if (live && ok) {
-        // S only ever decreases, so sum_t [lgamma(S_t+1) - lgamma(S_t-y_t+1)] telescopes to
-        // lgamma(S_0+1) - lgamma(S_T+1) (added once per metapopulation below); per cell only -lgamma(y+1) remains.
-        acc += log_binom_coef(E, y1, lgs) + log_binom_coef(I, y2, lgs) - (y0 < SEIR_LGTAB ? lgs[y0] : lgamma1p_int(y0, lgs));
-        accYei += y1;
-        accEres += E - y1;
-        ry = y2;
-        rr = I - y2;
-      }
-      ry = __reduce_add_sync(0xffffffffu, ry);
-      rr = __reduce_add_sync(0xffffffffu, rr);
+      accYei += y1;
+      accEres += E - y1;
+      const int ry = __reduce_add_sync(0xffffffffu, y2);      // padding lanes hold zeros
+      const int rr = __reduce_add_sync(0xffffffffu, I - y2);
       if (lane == 0) {
-        atomicAdd(reinterpret_cast<unsigned long long*>(Yir + (size_t)b * T + t0 + s), (unsigned long long)ry);
-        atomicAdd(reinterpret_cast<unsigned long long*>(Rir + (size_t)b * T + t0 + s), (unsigned long long)rr);
+        atomicAdd(reinterpret_cast<unsigned long long*>(Yir + (size_t)b * T + t0 + s), (unsigned long long)(long long)ry);
+        atomicAdd(reinterpret_cast<unsigned long long*>(Rir + (size_t)b * T + t0 + s), (unsigned long long)(long long)rr);
       }
       c0 += y0; c1 += y1; c2 += y2;
     }
     carry0 += tot0; carry1 += tot1; carry2 += tot2;
     __syncthreads();
   }
-  // telescoped S->E coefficient term, once per metapopulation (carry0 = all S->E events of the row)
-  if (warp == 0 && live && carry0 >= 0 && carry0 <= S0) acc += lgamma_diff_exact(S0, carry0, lgs);
-  // ---- per-CTA reductions ----
-  const double tot = block_sum(acc, red);
-  if (threadIdx.x == 0) llc_part[(size_t)b * gridDim.x + blockIdx.x] = tot;
 #pragma unroll
   for (int o = 16; o > 0; o >>= 1) {
     accYei += __shfl_xor_sync(0xffffffffu, accYei, o);
@@ -182,25 +167,97 @@ __global__ void __launch_bounds__(256) seir_ingest_kernel(int M, int T, int Mp, 
   if (lane == 0 && bad) atomicOr(flags + b, bad);
 }
 
-int seir_launch_ingest(seir_chains* c, const double* d_events, cudaStream_t s) {
+template <int TC>
+static int launch_ingest_tc(seir_chains* c, const double* d_events, cudaStream_t s) {
   const seir_model* m = c->model;
-  const int B = c->B, T = m->T;
-  SEIR_CUDA(cudaMemsetAsync(c->d_Yir, 0, sizeof(long long) * (size_t)B * T, s));
-  SEIR_CUDA(cudaMemsetAsync(c->d_Rir, 0, sizeof(long long) * (size_t)B * T, s));
-  SEIR_CUDA(cudaMemsetAsync(c->d_sumYei, 0, sizeof(long long) * (size_t)B, s));
-  SEIR_CUDA(cudaMemsetAsync(c->d_sumEres, 0, sizeof(long long) * (size_t)B, s));
-  SEIR_CUDA(cudaMemsetAsync(c->d_flags, 0, sizeof(int) * (size_t)B, s));
-  constexpr int TC = SEIR_INGEST_TC;
   const size_t smem = sizeof(int) * (32 * (TC * 3 + 1) + 8 * 3 * 32);
   static bool attr_set = false;
   if (!attr_set) {
     SEIR_CUDA(cudaFuncSetAttribute(seir_ingest_kernel<TC>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
     attr_set = true;
   }
-  dim3 grid(c->nblk32, B);
-  seir_ingest_kernel<TC><<<grid, 256, smem, s>>>(m->M, T, m->Mp, m->d_init, m->d_lgtab, d_events, c->d_yse, c->d_yei, c->d_yir,
-                                                 c->d_S, c->d_E, c->d_I, c->d_llc_part, c->d_Yir, c->d_Rir, c->d_sumYei,
-                                                 c->d_sumEres, c->d_flags);
+  dim3 grid(c->nblk32, c->B);
+  seir_ingest_kernel<TC><<<grid, 256, smem, s>>>(m->M, m->T, m->Mp, m->d_init, d_events, c->d_yse, c->d_yei, c->d_yir, c->d_S,
+                                                 c->d_E, c->d_I, c->d_Yir, c->d_Rir, c->d_sumYei, c->d_sumEres, c->d_flags);
   seir_count_launch(1);
   return seir_cuda_check(cudaGetLastError(), "seir_ingest_kernel");
+}
+
+int seir_launch_ingest(seir_chains* c, const double* d_events, cudaStream_t s) {
+  const int B = c->B, T = c->model->T;
+  // one memset over the contiguous integer-statistics block [Yir | Rir | sumYei | sumEres | flags]
+  SEIR_CUDA(cudaMemsetAsync(c->d_Yir, 0, c->stats_bytes, s));
+  (void)B;
+  return (T <= 96) ? launch_ingest_tc<96>(c, d_events, s) : launch_ingest_tc<128>(c, d_events, s);
+}
+
+// ------------------------------------------------------------------------------------------------
+// parameter-free part of the log-pmf: sum over cells of log C(n, y) for the three transitions.
+//   S->E : S only ever decreases, so sum_t [lgamma(S_t+1) - lgamma(S_t-y_t+1)] telescopes to
+//          lgamma(S_0+1) - lgamma(S_T+1): one term per metapopulation, per cell only -lgamma(y+1);
+//   E->I, I->R : lgamma(n+1) - lgamma(n-y+1) - lgamma(y+1) from a 16384-entry lgamma table held in
+//          SHARED memory (128 KB): three conflict-tolerant shared-memory gathers instead of four FP64
+//          logarithms per coefficient.  (The first version evaluated a two-log Stirling form per
+//          coefficient and ran at 0.21 ms -- FP64-pipe bound; counts beyond the table still take it.)
+// Persistent kernel: one 1024-thread CTA per SM loads the table once, then warps stride over the
+// B*T day slabs; lanes sweep the metapopulations of a slab with coalesced 128-byte loads.  One partial
+// per (chain, day) is written and reduced in fixed order by seir_finalize_kernel.
+// ------------------------------------------------------------------------------------------------
+__device__ __forceinline__ double log_binom_coef_tab(int n, int y, const double* tab) {
+  if (n < SEIR_LGTAB_BIG) return tab[n] - tab[n - y] - tab[y];
+  return log_binom_coef(n, y, tab);
+}
+
+__global__ void __launch_bounds__(1024, 1) seir_coef_kernel(int M, int T, int Mp, int slabs, const int* __restrict__ init,
+                                                            const double* __restrict__ lgtab, const int* __restrict__ yse,
+                                                            const int* __restrict__ yei, const int* __restrict__ yir,
+                                                            const int* __restrict__ Sx, const int* __restrict__ Ex,
+                                                            const int* __restrict__ Ix, double* __restrict__ llc_part) {
+  extern __shared__ double lgs[];  // [SEIR_LGTAB_BIG]
+  for (int k = threadIdx.x; k < SEIR_LGTAB_BIG; k += blockDim.x) lgs[k] = lgtab[k];
+  __syncthreads();
+  const int lane = threadIdx.x & 31, nwarp = blockDim.x >> 5;
+  const int wg = blockIdx.x * nwarp + (threadIdx.x >> 5), wstride = gridDim.x * nwarp;
+  for (int slab = wg; slab < slabs; slab += wstride) {
+    const int t = slab % T;
+    const size_t base = (size_t)slab * Mp;
+    double acc = 0.0;
+#pragma unroll 4
+    for (int m = lane; m < M; m += 32) {
+      const size_t o = base + m;
+      const int y0 = __ldg(yse + o), y1 = __ldg(yei + o), y2 = __ldg(yir + o), E = __ldg(Ex + o), I = __ldg(Ix + o);
+      const bool ok = (y0 >= 0) & (y1 >= 0) & (y2 >= 0) & (y1 <= E) & (y2 <= I);
+      if (ok)
+        acc += log_binom_coef_tab(E, y1, lgs) + log_binom_coef_tab(I, y2, lgs) -
+               (y0 < SEIR_LGTAB_BIG ? lgs[y0] : lgamma1p_int(y0, lgs));
+    }
+    if (t == T - 1) {  // last day of a chain: the telescoped S->E term, once per metapopulation
+      for (int m = lane; m < M; m += 32) {
+        const int S0 = init[m * 4 + 0], ST = __ldg(Sx + base + m) - __ldg(yse + base + m);
+        if (ST >= 0 && ST <= S0) acc += lgamma_diff_exact(S0, S0 - ST, lgs);
+      }
+    }
+    acc = warp_sum(acc);
+    if (lane == 0) llc_part[slab] = acc;
+  }
+}
+
+int seir_launch_coef(seir_chains* c, cudaStream_t s) {
+  const seir_model* m = c->model;
+  static int sms = 0;
+  const size_t smem = sizeof(double) * SEIR_LGTAB_BIG;
+  if (!sms) {
+    int dev = 0;
+    cudaGetDevice(&dev);
+    cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev);
+    SEIR_CUDA(cudaFuncSetAttribute(seir_coef_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+  }
+  const int slabs = c->B * m->T;
+  c->nllc = m->T;
+  int grid = (slabs + 31) / 32;
+  if (grid > sms) grid = sms;
+  seir_coef_kernel<<<grid, 1024, smem, s>>>(m->M, m->T, m->Mp, slabs, m->d_init, m->d_lgtab, c->d_yse, c->d_yei, c->d_yir, c->d_S,
+                                            c->d_E, c->d_I, c->d_llc_part);
+  seir_count_launch(1);
+  return seir_cuda_check(cudaGetLastError(), "seir_coef_kernel");
 }

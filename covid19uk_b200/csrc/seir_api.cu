@@ -90,7 +90,7 @@ int seir_model_create(const seir_spec* spec, int device, seir_model** out) {
   m->car_nnz = spec->car_nnz;
   const int Mp = m->Mp;
 
-  std::vector<double> cstar((size_t)Mp * Mp, 0.0), rN(Mp, 0.0), la(Mp, 0.0), W(T), wk(T), lgtab(SEIR_LGTAB);
+  std::vector<double> cstar((size_t)Mp * Mp, 0.0), rN(Mp, 0.0), la(Mp, 0.0), W(T), wk(T), lgtab(SEIR_LGTAB_BIG);
   std::vector<int> init((size_t)Mp * 4, 0), aidx(T);
   for (int i = 0; i < M; ++i) {
     rN[i] = 1.0 / spec->population[i];
@@ -119,7 +119,7 @@ int seir_model_create(const seir_spec* spec, int device, seir_model** out) {
     if (ai > T - 2) ai = T - 2;
     aidx[k] = (t == 0) ? -1 : (int)ai;
   }
-  for (int k = 0; k < SEIR_LGTAB; ++k) lgtab[k] = lgamma((double)k + 1.0);
+  for (int k = 0; k < SEIR_LGTAB_BIG; ++k) lgtab[k] = lgamma((double)k + 1.0);
   std::vector<int> indptr(spec->car_indptr, spec->car_indptr + M + 1);
   std::vector<int> indices(spec->car_indices, spec->car_indices + spec->car_nnz);
   std::vector<double> values(spec->car_values, spec->car_values + spec->car_nnz);
@@ -172,10 +172,8 @@ int seir_chains_create(const seir_model* m, int B, seir_chains** out) {
   if ((rc = dev_alloc(&c->d_yse, cells, &c->bytes)) || (rc = dev_alloc(&c->d_yei, cells, &c->bytes)) ||
       (rc = dev_alloc(&c->d_yir, cells, &c->bytes)) || (rc = dev_alloc(&c->d_S, cells, &c->bytes)) ||
       (rc = dev_alloc(&c->d_E, cells, &c->bytes)) || (rc = dev_alloc(&c->d_I, cells, &c->bytes)) ||
-      (rc = dev_alloc(&c->d_Bc, cells, &c->bytes)) || (rc = dev_alloc(&c->d_llc_part, (size_t)B * c->nblk32, &c->bytes)) ||
-      (rc = dev_alloc(&c->d_Yir, BT, &c->bytes)) || (rc = dev_alloc(&c->d_Rir, BT, &c->bytes)) ||
-      (rc = dev_alloc(&c->d_sumYei, (size_t)B, &c->bytes)) || (rc = dev_alloc(&c->d_sumEres, (size_t)B, &c->bytes)) ||
-      (rc = dev_alloc(&c->d_flags, (size_t)B, &c->bytes)) || (rc = dev_alloc(&c->d_pa, BT, &c->bytes)) ||
+      (rc = dev_alloc(&c->d_Bc, cells, &c->bytes)) || (rc = dev_alloc(&c->d_llc_part, BT, &c->bytes)) ||
+      (rc = dev_alloc(&c->d_Yir, 2 * BT + 2 * (size_t)B + ((size_t)B + 1) / 2, &c->bytes)) || (rc = dev_alloc(&c->d_pa, BT, &c->bytes)) ||
       (rc = dev_alloc(&c->d_psiW, BT, &c->bytes)) || (rc = dev_alloc(&c->d_gam, BT, &c->bytes)) ||
       (rc = dev_alloc(&c->d_logpir, BT, &c->bytes)) || (rc = dev_alloc(&c->d_pm, (size_t)B * m->Mp, &c->bytes)) ||
       (rc = dev_alloc(&c->d_scal, (size_t)B * SEIR_NSCAL, &c->bytes)) ||
@@ -186,6 +184,14 @@ int seir_chains_create(const seir_model* m, int B, seir_chains** out) {
     seir_chains_destroy(c);
     return rc;
   }
+  // one contiguous block of integer statistics: [Yir | Rir | sumYei | sumEres | flags]
+  c->d_Rir = c->d_Yir + BT;
+  c->d_sumYei = c->d_Rir + BT;
+  c->d_sumEres = c->d_sumYei + B;
+  c->d_flags = reinterpret_cast<int*>(c->d_sumEres + B);
+  c->stats_bytes = sizeof(long long) * (2 * BT + 2 * (size_t)B) + sizeof(int) * (size_t)B;
+  c->nllc = 0;
+  SEIR_CUDA(cudaMemset(c->d_Yir, 0, c->stats_bytes));
   *out = c;
   return SEIR_OK;
 }
@@ -194,8 +200,7 @@ void seir_chains_destroy(seir_chains* c) {
   if (!c) return;
   cudaSetDevice(c->model->device);
   cudaFree(c->d_yse); cudaFree(c->d_yei); cudaFree(c->d_yir); cudaFree(c->d_S); cudaFree(c->d_E); cudaFree(c->d_I);
-  cudaFree(c->d_Bc); cudaFree(c->d_llc_part); cudaFree(c->d_Yir); cudaFree(c->d_Rir); cudaFree(c->d_sumYei);
-  cudaFree(c->d_sumEres); cudaFree(c->d_flags); cudaFree(c->d_pa); cudaFree(c->d_psiW); cudaFree(c->d_gam);
+  cudaFree(c->d_Bc); cudaFree(c->d_llc_part); cudaFree(c->d_Yir); cudaFree(c->d_pa); cudaFree(c->d_psiW); cudaFree(c->d_gam);
   cudaFree(c->d_logpir); cudaFree(c->d_pm); cudaFree(c->d_scal); cudaFree(c->d_val_part); cudaFree(c->d_psi_part);
   cudaFree(c->d_col_part); cudaFree(c->d_rowsum); cudaFree(c->d_stage_events); cudaFree(c->d_stage_theta);
   cudaFree(c->d_stage_out);
@@ -231,6 +236,7 @@ int seir_ingest_events(seir_chains* c, const double* d_events, void* stream) {
   if (!c) return seir_set_error(SEIR_ERR_BAD_ARG, "seir_ingest_events: NULL chains");
   SEIR_TRY(check_dev_ptr(d_events, "d_events"));
   SEIR_TRY(seir_launch_ingest(c, d_events, (cudaStream_t)stream));
+  SEIR_TRY(seir_launch_coef(c, (cudaStream_t)stream));
   return seir_launch_contract(c, (cudaStream_t)stream);
 }
 
@@ -299,6 +305,7 @@ int seir_run_stage(seir_chains* c, int stage, const double* d_events, const doub
       SEIR_TRY(check_dev_ptr(d_theta, "d_theta"));
       if (!d_grad) return seir_set_error(SEIR_ERR_BAD_ARG, "seir_run_stage: stage 6 needs d_grad");
       return seir_launch_finalize(c, d_theta, kind, parts, d_out, d_grad, s);
+    case 7: return seir_launch_coef(c, s);
     default: return seir_set_error(SEIR_ERR_BAD_ARG, "seir_run_stage: unknown stage %d", stage);
   }
 }

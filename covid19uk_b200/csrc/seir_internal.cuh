@@ -8,7 +8,9 @@
 #include "../../include/seir_b200.h"
 
 #define SEIR_PAD 64          // metapopulation axis is padded to a multiple of this
-#define SEIR_LGTAB 1024      // lgamma(k+1) table entries, k < SEIR_LGTAB
+#define SEIR_LGTAB 1024      // lgamma(k+1) table entries used by per-cell helpers, k < SEIR_LGTAB
+#define SEIR_LGTAB_BIG 16384 // entries of the device table (the coefficient kernel stages all of it in shared memory)
+#define SEIR_STIRLING_MIN 64 // n-y at or above this uses the two-log Stirling form (uniform control flow across lanes)
 #define SEIR_INGEST_TC 128   // days per ingest chunk
 #define SEIR_LL_THREADS 128  // metapopulations per CTA in the log-likelihood kernel
 #define SEIR_NSCAL 16        // per-chain scalar slots
@@ -42,7 +44,7 @@ struct seir_model {
   int* d_car_indptr;   // [M+1]
   int* d_car_indices;  // [nnz]
   double* d_car_values;
-  double* d_lgtab;     // [SEIR_LGTAB]
+  double* d_lgtab;     // [SEIR_LGTAB_BIG]
 };
 
 struct seir_chains {
@@ -51,11 +53,13 @@ struct seir_chains {
   int nblk32;   // Mp/32   (ingest CTAs per chain)
   int nblkLL;   // ceil(Mp/SEIR_LL_THREADS)
   int nts;      // day splits used by the last log-likelihood launch
+  int nllc;     // number of llc partials per chain written by the last coefficient launch
+  size_t stats_bytes;  // bytes of the contiguous integer-statistics block starting at d_Yir
   int64_t bytes;
   // events-only caches, day-slab layout [B][T][Mp]
   int *d_yse, *d_yei, *d_yir, *d_S, *d_E, *d_I;
   double* d_Bc;          // [B][T][Mp]  Cstar . (I/N)
-  double* d_llc_part;    // [B][nblk32] parameter-free log-pmf partials (log binomial coefficients)
+  double* d_llc_part;    // [B][nllc] parameter-free log-pmf partials (log binomial coefficients)
   long long* d_Yir;      // [B][T]  sum_m y_ir
   long long* d_Rir;      // [B][T]  sum_m (I - y_ir)
   long long* d_sumYei;   // [B]
@@ -88,6 +92,7 @@ void seir_count_launch(int n);
 // kernel launchers (one per .cu file)
 int seir_launch_state(const seir_model* m, int B, const double* d_events, double* d_state, cudaStream_t s);
 int seir_launch_ingest(seir_chains* c, const double* d_events, cudaStream_t s);
+int seir_launch_coef(seir_chains* c, cudaStream_t s);
 int seir_launch_contract(seir_chains* c, cudaStream_t s);
 int seir_launch_theta_prep(seir_chains* c, const double* d_theta, int kind, int parts, cudaStream_t s);
 int seir_launch_loglik(seir_chains* c, bool grad, cudaStream_t s);
@@ -151,7 +156,7 @@ __device__ __forceinline__ double log_binom_coef(int n, int y, const double* lgt
   if (y == 0 || y == n) return 0.0;
   const int r = n - y;
   double d;
-  if (r >= SEIR_LGTAB) {
+  if (r >= SEIR_STIRLING_MIN) {
     const double a = (double)n + 1.0, b = (double)r + 1.0, yd = (double)y;
     const double inv = (double)__frcp_rn((float)(a * b));
     const double t1 = yd * inv;

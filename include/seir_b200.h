@@ -133,7 +133,7 @@ int seir_chain_flags(const seir_chains* chains, int32_t* d_flags_out, void* stre
 /* Measurement hook: enqueue exactly ONE kernel of the pipeline on `stream` (bench.py times each kernel
  * with CUDA events for the roofline).  stage: 0 ingest (state + caches), 1 contraction, 2 theta prep,
  * 3 S->E log-likelihood, 4 S->E log-likelihood + gradient pieces, 5 finalize (value),
- * 6 finalize (value + gradient; d_grad required). */
+ * 6 finalize (value + gradient; d_grad required), 7 log-binomial-coefficient sums. */
 int seir_run_stage(seir_chains* chains, int stage, const double* d_events, const double* d_theta, int theta_kind,
                    int parts, double* d_out, double* d_grad, void* stream);
 
