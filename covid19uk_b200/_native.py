@@ -44,6 +44,15 @@ class SeirSpec(ctypes.Structure):
     ]
 
 
+class SeirUpdateSpec(ctypes.Structure):
+    """include/seir_b200.h: struct seir_update_spec."""
+
+    _fields_ = [(n, c_int32) for n in ("kind", "target", "prev", "next", "mmax", "nmax", "dmax", "t0", "t1")]
+
+
+MMAX = 4  # columns of a proposal record [4][MMAX] (rows m, t, delta_t, x_star)
+
+
 class NativeError(RuntimeError):
     pass
 
@@ -67,6 +76,9 @@ SIGNATURES = {
     "seir_log_prob_host": (c_int, [c_void_p, c_void_p, c_void_p, c_int, c_int, c_void_p]),
     "seir_log_prob_grad_cached": (c_int, [c_void_p, c_void_p, c_int, c_int, c_void_p, c_void_p, c_void_p]),
     "seir_run_stage": (c_int, [c_void_p, c_int, c_void_p, c_void_p, c_int, c_int, c_void_p, c_void_p, c_void_p]),
+    "seir_prepare_theta": (c_int, [c_void_p, c_void_p, c_int, c_void_p]),
+    "seir_update_step": (c_int, [c_void_p, c_void_p, c_int, c_void_p, c_void_p, c_void_p, c_void_p, c_void_p, c_void_p, c_void_p]),
+    "seir_export_events": (c_int, [c_void_p, c_void_p, c_void_p]),
     "seir_chain_flags": (c_int, [c_void_p, c_void_p, c_void_p]),
     "seir_launch_count": (c_int64, []),
 }

@@ -1,0 +1,486 @@
+// K5: discrete Metropolis-within-Gibbs updates of the censored event tensor, batched over chains.
+//
+//   kind 0  MetropolisHastings(UncalibratedEventTimesUpdate)   call site mcmc_kernel_factory.py:63-86
+//   kind 1  MetropolisHastings(UncalibratedOccultUpdate)       call site mcmc_kernel_factory.py:89-113
+//
+// The reference evaluates the FULL joint log-density of the proposed events for every proposal
+// (20 per sweep).  Here a proposal is a list of "point changes" (metapopulation, day, dy) of
+// one transition, and only what depends on them is recomputed:
+//   * S->E (target 0): I is untouched => the force of infection is unchanged; only the S->E and E->I cells
+//     of the touched metapopulations change                                         (seir_update_prepare_kernel)
+//   * E->I (target 1): I of the touched metapopulations changes on a range of days => rank-1 update of
+//     the cached contraction Bc with a row of Cs and new S->E terms for EVERY metapopulation on those
+//     days                                                                          (seir_update_slab_kernel)
+// seir_update_commit_kernel takes the MH decision  log u < d(log pi) + log q_rev - log q_fwd  and applies
+// the accepted change to every cache in place (events, state rows, Bc slabs, sufficient statistics).
+//
+// Proposal conventions restated from gemlib ([recall], see oracle/seir_oracle.py move_max_events /
+// occult_delete_max and SURVEY Appendix B.1/B.3): parity unpinned.
+#include <limits.h>
+
+#include "seir_internal.cuh"
+
+#define UPD_THREADS 128
+#define SLAB_DAYS 8
+
+struct chain_view {
+  int M, T, Mp;
+  const int *yse, *yei, *yir, *S, *E, *I;  // already offset to the chain
+  const int* init;                         // [Mp][4]
+};
+
+__device__ __forceinline__ const int* yarr(const chain_view& v, int x) { return x == 0 ? v.yse : (x == 1 ? v.yei : v.yir); }
+__device__ __forceinline__ const int* xarr(const chain_view& v, int c) { return c == 0 ? v.S : (c == 1 ? v.E : v.I); }
+
+// state of compartment c (0..2) of metapopulation m AFTER the events of day s
+__device__ __forceinline__ int after_state(const chain_view& v, int c, int m, int s) {
+  const size_t o = (size_t)s * v.Mp + m;
+  int x = xarr(v, c)[o] - yarr(v, c)[o];
+  if (c > 0) x += yarr(v, c - 1)[o];
+  return x;
+}
+
+// net change of the cumulative target-event count of metapopulation m with day <= s under the proposal
+__device__ __forceinline__ int dcum_le(const int* pm, const int* pd, const int* pdy, int npts, int m, int s) {
+  int d = 0;
+  for (int p = 0; p < npts; ++p)
+    if (pm[p] == m && pd[p] <= s) d += pdy[p];
+  return d;
+}
+__device__ __forceinline__ int dy_at(const int* pm, const int* pd, const int* pdy, int npts, int m, int s) {
+  int d = 0;
+  for (int p = 0; p < npts; ++p)
+    if (pm[p] == m && pd[p] == s) d += pdy[p];
+  return d;
+}
+
+__device__ __forceinline__ int blk_reduce_min(int v, int* red) {
+  v = __reduce_min_sync(0xffffffffu, v);
+  __syncthreads();
+  if ((threadIdx.x & 31) == 0) red[threadIdx.x >> 5] = v;
+  __syncthreads();
+  int r = red[0];
+  for (int w = 1; w < UPD_THREADS / 32; ++w) r = min(r, red[w]);
+  return r;
+}
+__device__ __forceinline__ int blk_reduce_add(int v, int* red) {
+  v = __reduce_add_sync(0xffffffffu, v);
+  __syncthreads();
+  if ((threadIdx.x & 31) == 0) red[threadIdx.x >> 5] = v;
+  __syncthreads();
+  int r = 0;
+  for (int w = 0; w < UPD_THREADS / 32; ++w) r += red[w];
+  return r;
+}
+__device__ __forceinline__ double blk_reduce_addd(double v, double* red) {
+  v = warp_sum(v);
+  __syncthreads();
+  if ((threadIdx.x & 31) == 0) red[threadIdx.x >> 5] = v;
+  __syncthreads();
+  double r = 0.0;
+  for (int w = 0; w < UPD_THREADS / 32; ++w) r += red[w];
+  return r;
+}
+
+// min over days s in [lo, hi) of  init_c + |X_c(s+1) - init_c|   (gemlib _abscumdiff convention), on the
+// current (delta = 0) or proposed state; compartment c loses dcum for c == target and gains it for target+1.
+__device__ int bound_abs_min(const chain_view& v, int c, int m, int lo, int hi, bool proposed, int target, const int* pm,
+                             const int* pd, const int* pdy, int npts, int* red) {
+  const int init_c = v.init[m * 4 + c];
+  int best = INT_MAX;
+  for (int s = lo + (int)threadIdx.x; s < hi; s += UPD_THREADS) {
+    int x = after_state(v, c, m, s);
+    if (proposed) {
+      const int d = dcum_le(pm, pd, pdy, npts, m, s);
+      x += (c == target) ? -d : d;
+    }
+    const int dev = x - init_c;
+    best = min(best, init_c + (dev < 0 ? -dev : dev));
+  }
+  return blk_reduce_min(best, red);
+}
+
+// min over days s in [lo, hi) of X_c(s+1) (occult delete bound, no abs)
+__device__ int bound_level_min(const chain_view& v, int c, int m, int lo, int hi, bool proposed, int target, const int* pm,
+                               const int* pd, const int* pdy, int npts, int* red) {
+  int best = INT_MAX;
+  for (int s = lo + (int)threadIdx.x; s < hi; s += UPD_THREADS) {
+    int x = after_state(v, c, m, s);
+    if (proposed) {
+      const int d = dcum_le(pm, pd, pdy, npts, m, s);
+      x += (c == target) ? -d : d;
+    }
+    best = min(best, x);
+  }
+  return blk_reduce_min(best, red);
+}
+
+__device__ __forceinline__ int clampi(int x, int lo, int hi) { return x < lo ? lo : (x > hi ? hi : x); }
+
+// ------------------------------------------------------------------------------------------------
+// prepare: one CTA per chain.  Parses the proposal, evaluates log q_fwd / log q_rev and the delta
+// log-likelihood of the cells owned by the touched metapopulations.
+// ------------------------------------------------------------------------------------------------
+__global__ void __launch_bounds__(UPD_THREADS) seir_update_prepare_kernel(
+    int M, int T, int Mp, double dt, double nu, double log_p_nu, double eps, seir_update_cfg cfg, const int* __restrict__ prop,
+    const int* __restrict__ yse, const int* __restrict__ yei, const int* __restrict__ yir, const int* __restrict__ Sx,
+    const int* __restrict__ Ex, const int* __restrict__ Ix, const double* __restrict__ Bc, const int* __restrict__ init,
+    const double* __restrict__ lgtab, const double* __restrict__ pa, const double* __restrict__ psiW,
+    const double* __restrict__ pm_arr, const double* __restrict__ gam, seir_upd* __restrict__ upd) {
+  __shared__ int s_pm[4], s_pd[4], s_pdy[4], s_npts, s_valid;
+  __shared__ int redi[UPD_THREADS / 32];
+  __shared__ double redd[UPD_THREADS / 32];
+  const int b = blockIdx.x, tid = threadIdx.x;
+  const size_t cb = (size_t)b * T * Mp;
+  chain_view v{M, T, Mp, yse + cb, yei + cb, yir + cb, Sx + cb, Ex + cb, Ix + cb, init};
+  const int* pr = prop + (size_t)b * 4 * SEIR_MMAX;
+  const int target = cfg.target;
+  const int* yt = yarr(v, target);
+
+  if (tid == 0) {
+    int valid = 1, npts = 0;
+    if (cfg.kind == 0) {
+      for (int k = 0; k < cfg.mmax; ++k) {
+        const int m = pr[k], t = pr[SEIR_MMAX + k], d = pr[2 * SEIR_MMAX + k], x = pr[3 * SEIR_MMAX + k];
+        if (m < 0 || m >= M || t < 0 || t >= T || t + d < 0 || t + d >= T || d == 0 || x < 0) valid = 0;
+        for (int j = 0; j < k; ++j)
+          if (pr[j] == m) valid = 0;
+        if (valid && x > 0) {
+          s_pm[npts] = m; s_pd[npts] = t; s_pdy[npts] = -x; ++npts;
+          s_pm[npts] = m; s_pd[npts] = t + d; s_pdy[npts] = x; ++npts;
+        }
+      }
+    } else {
+      const int m = pr[0], t = pr[SEIR_MMAX], sg = pr[2 * SEIR_MMAX], x = pr[3 * SEIR_MMAX];
+      if (m < 0 || m >= M || t < cfg.t0 || t >= cfg.t1 || t >= T || x < 0 || x > cfg.nmax || (sg != 1 && sg != -1)) valid = 0;
+      if (valid && x > 0) { s_pm[0] = m; s_pd[0] = t; s_pdy[0] = sg * x; npts = 1; }
+    }
+    s_npts = npts;
+    s_valid = valid;
+  }
+  __syncthreads();
+  int valid = s_valid;
+  const int npts = s_npts;
+  double qf = 0.0, qr = 0.0;
+
+  if (valid && cfg.kind == 0) {
+    for (int k = 0; k < cfg.mmax; ++k) {
+      const int m = pr[k], t = pr[SEIR_MMAX + k], d = pr[2 * SEIR_MMAX + k], x = pr[3 * SEIR_MMAX + k];
+      int cnt = 0;
+      for (int s = tid; s < T; s += UPD_THREADS) cnt += yt[(size_t)s * Mp + m] > 0;
+      const int nnz = blk_reduce_add(cnt, redi);
+      const int ytt = yt[(size_t)t * Mp + m], ytd = yt[(size_t)(t + d) * Mp + m];
+      const int lo = d > 0 ? t : t + d, hi = d > 0 ? t + d : t;
+      const int hi_c = min(hi, lo + cfg.dmax);
+      // forward: later move depletes the destination compartment (bounded via `next`), earlier move the source (via `prev`)
+      const int cf = d > 0 ? target + 1 : target, cr = d > 0 ? target : target + 1;
+      const bool have_f = d > 0 ? cfg.next >= 0 : cfg.prev >= 0, have_r = d > 0 ? cfg.prev >= 0 : cfg.next >= 0;
+      const int bf = have_f ? bound_abs_min(v, cf, m, lo, hi_c, false, target, s_pm, s_pd, s_pdy, npts, redi) : INT_MAX;
+      const int br = have_r ? bound_abs_min(v, cr, m, lo, hi_c, true, target, s_pm, s_pd, s_pdy, npts, redi) : INT_MAX;
+      const int maxf = clampi(min(bf, ytt), 0, cfg.nmax);
+      const int maxr = clampi(min(br, ytd + x), 0, cfg.nmax);
+      if (ytt <= 0 || nnz <= 0 || x > maxf) valid = 0;  // outside the forward proposal's support
+      const int nnz2 = nnz - ((x > 0 && ytt == x) ? 1 : 0) + ((x > 0 && ytd == 0) ? 1 : 0);
+      qf += -log((double)nnz) - log((double)maxf + 1.0);
+      qr += (x > maxr || nnz2 <= 0) ? -INFINITY : (-log((double)nnz2) - log((double)maxr + 1.0));
+    }
+  } else if (valid) {
+    const int m = pr[0], t = pr[SEIR_MMAX], sg = pr[2 * SEIR_MMAX], x = pr[3 * SEIR_MMAX];
+    const int t1 = min(cfg.t1, T);
+    const double q_add = -log((double)M) - log((double)(cfg.t1 - cfg.t0)) - log((double)cfg.nmax + 1.0);
+    // hot metapopulations / hot days of the window, on the events the DELETE proposal is built on
+    // (current events for a delete, proposed events for the reverse of an add)
+    const int ymt = yt[(size_t)t * Mp + m];
+    const int ymt_del = sg > 0 ? ymt + x : ymt;
+    int hm = 0;
+    for (int mm = tid; mm < M; mm += UPD_THREADS) {
+      int any = 0;
+      for (int s = cfg.t0; s < t1; ++s) any |= yt[(size_t)s * Mp + mm] > 0;
+      if (mm == m && sg > 0 && x > 0) any = 1;
+      hm += any;
+    }
+    const int hotm = blk_reduce_add(hm, redi);
+    int hd = 0;
+    for (int s = cfg.t0 + tid; s < t1; s += UPD_THREADS) {
+      int y = yt[(size_t)s * Mp + m];
+      if (s == t && sg > 0) y += x;
+      hd += y > 0;
+    }
+    const int hotd = blk_reduce_add(hd, redi);
+    const int bound = cfg.next >= 0 ? bound_level_min(v, target + 1, m, t, T, sg > 0, target, s_pm, s_pd, s_pdy, npts, redi) : INT_MAX;
+    const int maxd = clampi(min(ymt_del, bound), 0, cfg.nmax);
+    const double q_del = (ymt_del <= 0 || hotm <= 0 || hotd <= 0 || x > maxd)
+                             ? -INFINITY
+                             : (-log((double)hotm) - log((double)hotd) - log((double)maxd + 1.0));
+    if (sg > 0) { qf = q_add; qr = q_del; } else { qf = q_del; qr = q_add; }
+    if (!(qf > -INFINITY)) valid = 0;
+  }
+
+  // ---- delta log-lik of the cells owned by the touched metapopulations ----
+  double dll = 0.0, dllc = 0.0;
+  int neg = 0;
+  if (valid && npts > 0) {
+    const int ngroups = cfg.kind == 0 ? npts / 2 : 1;
+    for (int gidx = 0; gidx < ngroups; ++gidx) {
+      const int m = s_pm[cfg.kind == 0 ? 2 * gidx : 0];
+      for (int s = tid; s < T; s += UPD_THREADS) {
+        const int dy = dy_at(s_pm, s_pd, s_pdy, npts, m, s);
+        const int dc = dcum_le(s_pm, s_pd, s_pdy, npts, m, s - 1);  // change of the exclusive cumulative count at day s
+        if (dy == 0 && dc == 0) continue;
+        const size_t o = (size_t)s * Mp + m;
+        const int y = yt[o], n = xarr(v, target)[o], n2 = xarr(v, target + 1)[o];
+        const int yn = y + dy, nn = n - dc, nn2 = n2 + dc;
+        const int y2 = yarr(v, target + 1)[o];  // events of the next transition (unchanged)
+        if (yn < 0 || nn < 0 || yn > nn || nn2 < 0 || y2 > nn2) { neg = 1; continue; }
+        // cell of the target transition: count and source compartment change
+        const double dcoef = log_binom_coef(nn, yn, lgtab) - log_binom_coef(n, y, lgtab) +
+                             log_binom_coef(nn2, y2, lgtab) - log_binom_coef(n2, y2, lgtab);
+        dllc += dcoef;
+        double term = dcoef;
+        const double dres = (double)((nn - yn) - (n - y));  // change of the survivors of the target transition
+        if (target == 0) {
+          const double e = pa[(size_t)b * T + s] * pm_arr[(size_t)b * Mp + m];
+          const double X = (double)v.I[o] + psiW[(size_t)b * T + s] * Bc[cb + o];
+          const double x = fma(e, X, eps) * dt;
+          if (dy != 0) term += (double)dy * log1mexp_neg(x);
+          term -= dres * x;
+          term -= (double)dc * nu * dt;  // E->I survivors change by +dc (y_ei fixed)
+        } else {
+          if (dy != 0) term += (double)dy * log_p_nu;
+          term -= dres * nu * dt;
+          term -= (double)dc * gam[(size_t)b * T + s] * dt;  // I->R survivors change by +dc (y_ir fixed)
+        }
+        dll += term;
+      }
+    }
+  }
+  dll = blk_reduce_addd(dll, redd);
+  dllc = blk_reduce_addd(dllc, redd);
+  neg = blk_reduce_add(neg, redi);
+  if (tid == 0) {
+    seir_upd u;
+    u.valid = valid; u.neg = neg > 0; u.npts = valid ? npts : 0; u.accept = 0;
+    for (int p = 0; p < 4; ++p) { u.pm[p] = p < npts ? s_pm[p] : 0; u.pd[p] = p < npts ? s_pd[p] : 0; u.pdy[p] = p < npts ? s_pdy[p] : 0; }
+    u.lac = valid ? qr - qf : 0.0;
+    u.dll_row = dll; u.dllc = dllc; u.dll = 0.0;
+    upd[b] = u;
+  }
+}
+
+// ------------------------------------------------------------------------------------------------
+// slab (target = E->I only): the infectious count of the touched metapopulations changes by dI on some
+// days => Bc'[i] = Bc[i] + sum_g Cs[m_g][i] dI_g and new S->E terms for every metapopulation i.
+// grid = (chains, day chunks); warp <-> day, lanes sweep metapopulations (coalesced day slabs).
+// ------------------------------------------------------------------------------------------------
+template <bool COMMIT>
+__global__ void __launch_bounds__(32 * SLAB_DAYS) seir_update_slab_kernel(
+    int M, int T, int Mp, double dt, double eps, int kind, const seir_upd* __restrict__ upd, const int* __restrict__ yse,
+    const int* __restrict__ Sx, const int* __restrict__ Ix, double* __restrict__ Bc, const double* __restrict__ cs,
+    const double* __restrict__ pa, const double* __restrict__ psiW, const double* __restrict__ pm_arr, double* __restrict__ part) {
+  __shared__ double red[SLAB_DAYS];
+  const int b = blockIdx.x, lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+  const seir_upd u = upd[b];
+  const int s = blockIdx.y * SLAB_DAYS + warp;
+  double acc = 0.0;
+  const bool go = COMMIT ? (u.accept != 0) : (u.valid && !u.neg);
+  if (go && u.npts > 0 && s < T) {
+    const int ngroups = kind == 0 ? u.npts / 2 : 1;
+    int gm[2];
+    double gd[2];
+    bool any = false;
+    for (int g = 0; g < 2; ++g) {
+      gm[g] = 0; gd[g] = 0.0;
+      if (g < ngroups) {
+        const int p0 = kind == 0 ? 2 * g : 0, np = kind == 0 ? 2 : 1;
+        int d = 0;
+        for (int p = p0; p < p0 + np; ++p)
+          if (u.pd[p] < s) d += u.pdy[p];
+        gm[g] = u.pm[p0];
+        gd[g] = (double)d;  // I is the destination compartment of E->I: +dcum
+        any |= d != 0;
+      }
+    }
+    if (any) {
+      const size_t base = ((size_t)b * T + s) * Mp;
+      const double pas = pa[(size_t)b * T + s], pws = psiW[(size_t)b * T + s];
+      for (int i = lane; i < Mp; i += 32) {
+        const double bc = Bc[base + i];
+        double bcn = bc;
+        double dIi = 0.0;
+#pragma unroll
+        for (int g = 0; g < 2; ++g) {
+          bcn = fma(cs[(size_t)gm[g] * Mp + i], gd[g], bcn);
+          if (i == gm[g]) dIi += gd[g];
+        }
+        if (COMMIT) {
+          Bc[base + i] = bcn;
+        } else if (i < M) {
+          const int y = yse[base + i], S = Sx[base + i];
+          const double I = (double)Ix[base + i];
+          const double e = pas * pm_arr[(size_t)b * Mp + i];
+          const double x0 = fma(e, I + pws * bc, eps) * dt;
+          const double x1 = fma(e, I + dIi + pws * bcn, eps) * dt;
+          double term = -(double)(S - y) * (x1 - x0);
+          if (y > 0) term += (double)y * (log1mexp_neg(x1) - log1mexp_neg(x0));
+          acc += term;
+        }
+      }
+    }
+  }
+  if (!COMMIT) {
+    acc = warp_sum(acc);
+    if (lane == 0) red[warp] = acc;
+    __syncthreads();
+    if (threadIdx.x == 0) {
+      double r = 0.0;
+      for (int w = 0; w < SLAB_DAYS; ++w) r += red[w];
+      part[(size_t)b * gridDim.y + blockIdx.y] = r;
+    }
+  }
+}
+
+// ------------------------------------------------------------------------------------------------
+// decide + commit rows: one CTA per chain.  accept iff log u < dll + lac  (tfp.mcmc.MetropolisHastings
+// [recall]); on accept apply the point changes to the event / state rows and the sufficient statistics.
+// ------------------------------------------------------------------------------------------------
+__global__ void __launch_bounds__(UPD_THREADS) seir_update_decide_kernel(
+    int M, int T, int Mp, seir_update_cfg cfg, int nchunk, seir_upd* __restrict__ upd, const double* __restrict__ part,
+    const double* __restrict__ log_u, const int* __restrict__ prop, int* __restrict__ yse, int* __restrict__ yei,
+    int* __restrict__ Sx, int* __restrict__ Ex, int* __restrict__ Ix, long long* __restrict__ Rir,
+    long long* __restrict__ sumYei, long long* __restrict__ sumEres, double* __restrict__ llc_adj, double* __restrict__ tlp,
+    int* __restrict__ accept_out, int* __restrict__ last_acc, int* __restrict__ trace, double* __restrict__ dbg) {
+  __shared__ int s_acc;
+  __shared__ long long redl[UPD_THREADS / 32];
+  const int b = blockIdx.x, tid = threadIdx.x;
+  seir_upd u = upd[b];
+  if (tid == 0) {
+    double dll = u.dll_row;
+    if (cfg.target == 1)
+      for (int k = 0; k < nchunk; ++k) dll += part[(size_t)b * nchunk + k];
+    double prop_tlp = tlp[b] + dll;
+    if (!u.valid || u.neg) { dll = -INFINITY; prop_tlp = -INFINITY; }
+    const double ratio = dll + u.lac;                      // NaN compares false => reject
+    const int acc = (u.valid && !u.neg && log_u[b] < ratio) ? 1 : 0;
+    if (acc) {
+      tlp[b] = prop_tlp;
+      llc_adj[b] += u.dllc;
+    }
+    upd[b].accept = acc;
+    upd[b].dll = dll;
+    accept_out[b] = acc;
+    if (dbg) {
+      dbg[(size_t)b * 4 + 0] = dll;
+      dbg[(size_t)b * 4 + 1] = u.lac;
+      dbg[(size_t)b * 4 + 2] = prop_tlp;
+      dbg[(size_t)b * 4 + 3] = ratio;
+    }
+    s_acc = acc;
+  }
+  __syncthreads();
+  const int acc = s_acc;
+  // MetropolisHastings.accepted_results: the last ACCEPTED proposal is what the reference traces
+  if (tid < 4 * SEIR_MMAX) {
+    int* la = last_acc + (size_t)b * 4 * SEIR_MMAX;
+    if (acc) la[tid] = prop[(size_t)b * 4 * SEIR_MMAX + tid];
+    if (trace) trace[(size_t)b * 4 * SEIR_MMAX + tid] = la[tid];
+  }
+  if (!acc || u.npts == 0) return;
+  const size_t cb = (size_t)b * T * Mp;
+  int* yt = (cfg.target == 0 ? yse : yei) + cb;
+  int* src = (cfg.target == 0 ? Sx : Ex) + cb;
+  int* dst = (cfg.target == 0 ? Ex : Ix) + cb;
+  const int ngroups = cfg.kind == 0 ? u.npts / 2 : 1;
+  long long dE = 0, dI = 0;
+  for (int g = 0; g < ngroups; ++g) {
+    const int m = u.pm[cfg.kind == 0 ? 2 * g : 0];
+    for (int s = tid; s < T; s += UPD_THREADS) {
+      const int dc = dcum_le(u.pm, u.pd, u.pdy, u.npts, m, s - 1);
+      const int dy = dy_at(u.pm, u.pd, u.pdy, u.npts, m, s);
+      const size_t o = (size_t)s * Mp + m;
+      if (dy) yt[o] += dy;
+      if (dc) {
+        src[o] -= dc;
+        dst[o] += dc;
+        if (cfg.target == 1) atomicAdd(reinterpret_cast<unsigned long long*>(Rir + (size_t)b * T + s), (unsigned long long)(long long)dc);
+      }
+      // sum (E - y_ei): target 0 moves E by +dc; target 1 moves E by -dc and y_ei by dy
+      if (cfg.target == 0) dE += dc; else { dE += -dc - dy; dI += dy; }
+    }
+  }
+  // block reduce the two integer statistics
+  for (int o = 16; o > 0; o >>= 1) { dE += __shfl_xor_sync(0xffffffffu, dE, o); dI += __shfl_xor_sync(0xffffffffu, dI, o); }
+  if ((tid & 31) == 0) redl[tid >> 5] = dE;
+  __syncthreads();
+  if (tid == 0) { long long r = 0; for (int w = 0; w < UPD_THREADS / 32; ++w) r += redl[w]; sumEres[b] += r; }
+  __syncthreads();
+  if ((tid & 31) == 0) redl[tid >> 5] = dI;
+  __syncthreads();
+  if (tid == 0) { long long r = 0; for (int w = 0; w < UPD_THREADS / 32; ++w) r += redl[w]; sumYei[b] += r; }
+}
+
+int seir_launch_update(seir_chains* c, const seir_update_cfg& cfg, int slot, const int* d_proposal, const double* d_log_u,
+                       double* d_tlp, int* d_accept, int* d_trace, double* d_dbg, cudaStream_t s) {
+  const seir_model* m = c->model;
+  const int B = c->B, T = m->T, Mp = m->Mp;
+  const int nchunk = (T + SLAB_DAYS - 1) / SLAB_DAYS;
+  seir_update_prepare_kernel<<<B, UPD_THREADS, 0, s>>>(m->M, T, Mp, m->dt, m->nu, m->log_p_nu, m->rate_eps, cfg, d_proposal, c->d_yse,
+                                                       c->d_yei, c->d_yir, c->d_S, c->d_E, c->d_I, c->d_Bc, m->d_init, m->d_lgtab,
+                                                       c->d_pa, c->d_psiW, c->d_pm, c->d_gam, c->d_upd);
+  int launches = 2;
+  if (cfg.target == 1) {
+    seir_update_slab_kernel<false><<<dim3(B, nchunk), 32 * SLAB_DAYS, 0, s>>>(m->M, T, Mp, m->dt, m->rate_eps, cfg.kind, c->d_upd, c->d_yse,
+                                                                             c->d_S, c->d_I, c->d_Bc, m->d_cs, c->d_pa, c->d_psiW,
+                                                                             c->d_pm, c->d_upd_part);
+    ++launches;
+  }
+  seir_update_decide_kernel<<<B, UPD_THREADS, 0, s>>>(m->M, T, Mp, cfg, nchunk, c->d_upd, c->d_upd_part, d_log_u, d_proposal, c->d_yse,
+                                                      c->d_yei, c->d_S, c->d_E, c->d_I, c->d_Rir, c->d_sumYei, c->d_sumEres,
+                                                      c->d_llc_adj, d_tlp, d_accept, c->d_last_acc + (size_t)slot * B * 4 * SEIR_MMAX,
+                                                      d_trace, d_dbg);
+  if (cfg.target == 1) {
+    seir_update_slab_kernel<true><<<dim3(B, nchunk), 32 * SLAB_DAYS, 0, s>>>(m->M, T, Mp, m->dt, m->rate_eps, cfg.kind, c->d_upd, c->d_yse,
+                                                                            c->d_S, c->d_I, c->d_Bc, m->d_cs, c->d_pa, c->d_psiW,
+                                                                            c->d_pm, c->d_upd_part);
+    ++launches;
+  }
+  seir_count_launch(launches);
+  return seir_cuda_check(cudaGetLastError(), "seir_update kernels");
+}
+
+// ------------------------------------------------------------------------------------------------
+// caches -> reference layout: events f64 [B, M, T, 3]  (the `seir` sample written to the posterior)
+// ------------------------------------------------------------------------------------------------
+__global__ void __launch_bounds__(256) seir_export_events_kernel(int M, int T, int Mp, const int* __restrict__ yse,
+                                                                 const int* __restrict__ yei, const int* __restrict__ yir,
+                                                                 double* __restrict__ events) {
+  __shared__ int tile[3][32][33];
+  const int b = blockIdx.z, m0 = blockIdx.x * 32, t0 = blockIdx.y * 32;
+  const int tx = threadIdx.x & 31, ty = threadIdx.x >> 5;  // 8 warps
+  for (int r = ty; r < 32; r += 8) {                        // r: day, tx: metapopulation (coalesced slab reads)
+    const int t = t0 + r, m = m0 + tx;
+    int a = 0, c = 0, d = 0;
+    if (t < T && m < Mp) {
+      const size_t o = ((size_t)b * T + t) * Mp + m;
+      a = yse[o]; c = yei[o]; d = yir[o];
+    }
+    tile[0][r][tx] = a; tile[1][r][tx] = c; tile[2][r][tx] = d;
+  }
+  __syncthreads();
+  for (int r = ty; r < 32; r += 8) {                        // r: metapopulation, lanes cover 32 days x 3 transitions
+    const int m = m0 + r;
+    if (m >= M) continue;
+    double* dst = events + (((size_t)b * M + m) * T + t0) * 3;
+    for (int k = tx; k < 96; k += 32) {
+      const int t = k / 3, x = k - 3 * t;
+      if (t0 + t < T) dst[k] = (double)tile[x][t][r];
+    }
+  }
+}
+
+int seir_launch_export_events(seir_chains* c, double* d_events, cudaStream_t s) {
+  const seir_model* m = c->model;
+  dim3 grid((m->M + 31) / 32, (m->T + 31) / 32, c->B);
+  seir_export_events_kernel<<<grid, 256, 0, s>>>(m->M, m->T, m->Mp, c->d_yse, c->d_yei, c->d_yir, d_events);
+  seir_count_launch(1);
+  return seir_cuda_check(cudaGetLastError(), "seir_export_events_kernel");
+}

@@ -187,6 +187,7 @@ int seir_launch_ingest(seir_chains* c, const double* d_events, cudaStream_t s) {
   const int B = c->B, T = c->model->T;
   // one memset over the contiguous integer-statistics block [Yir | Rir | sumYei | sumEres | flags]
   SEIR_CUDA(cudaMemsetAsync(c->d_Yir, 0, c->stats_bytes, s));
+  SEIR_CUDA(cudaMemsetAsync(c->d_llc_adj, 0, sizeof(double) * (size_t)B, s));
   (void)B;
   return (T <= 96) ? launch_ingest_tc<96>(c, d_events, s) : launch_ingest_tc<128>(c, d_events, s);
 }

@@ -242,7 +242,7 @@ int seir_launch_loglik(seir_chains* c, bool grad, cudaStream_t s) {
 __global__ void __launch_bounds__(128) seir_finalize_kernel(
     int M, int T, int Mp, int P, int nblkLL, int nts, int nllc, double dt, double nu, double log_p_nu, int kind, int parts,
     const double* __restrict__ theta, const double* __restrict__ scal, const double* __restrict__ val_part,
-    const double* __restrict__ llc_part, const long long* __restrict__ Yir, const long long* __restrict__ Rir,
+    const double* __restrict__ llc_part, const double* __restrict__ llc_adj, const long long* __restrict__ Yir, const long long* __restrict__ Rir,
     const long long* __restrict__ sumYei, const long long* __restrict__ sumEres, const int* __restrict__ flags,
     const double* __restrict__ gam, const double* __restrict__ logpir, const double* __restrict__ wk, const int* __restrict__ aidx,
     const double* __restrict__ la, const double* __restrict__ psi_part, const double* __restrict__ col_part,
@@ -273,6 +273,7 @@ __global__ void __launch_bounds__(128) seir_finalize_kernel(
       for (int k = 0; k < nblkLL * nts; ++k) s += val_part[(size_t)b * nblkLL * nts + k];
       double l = 0.0;
       for (int k = 0; k < nllc; ++k) l += llc_part[(size_t)b * nllc + k];
+      l += llc_adj[b];
       const double yei = (double)sumYei[b], eres = (double)sumEres[b];
       double ei = -eres * nu * dt;
       if (yei > 0.0) ei += yei * log_p_nu;
@@ -365,7 +366,7 @@ int seir_launch_finalize(seir_chains* c, const double* d_theta, int kind, int pa
   const seir_model* m = c->model;
   seir_finalize_kernel<<<c->B, 128, sizeof(double) * 2 * m->T, s>>>(
       m->M, m->T, m->Mp, m->P, c->nblkLL, c->nts, c->nllc, m->dt, m->nu, m->log_p_nu, kind, parts, d_theta, c->d_scal, c->d_val_part,
-      c->d_llc_part, c->d_Yir, c->d_Rir, c->d_sumYei, c->d_sumEres, c->d_flags, c->d_gam, c->d_logpir, m->d_wk, m->d_aidx, m->d_la,
+      c->d_llc_part, c->d_llc_adj, c->d_Yir, c->d_Rir, c->d_sumYei, c->d_sumEres, c->d_flags, c->d_gam, c->d_logpir, m->d_wk, m->d_aidx, m->d_la,
       c->d_psi_part, c->d_col_part, c->d_rowsum, m->d_car_indptr, m->d_car_indices, m->d_car_values, d_out, d_grad);
   seir_count_launch(1);
   return seir_cuda_check(cudaGetLastError(), "seir_finalize_kernel");

@@ -180,7 +180,11 @@ int seir_chains_create(const seir_model* m, int B, seir_chains** out) {
       (rc = dev_alloc(&c->d_val_part, (size_t)B * c->nblkLL * SEIR_MAX_SPLITS, &c->bytes)) ||
       (rc = dev_alloc(&c->d_psi_part, (size_t)B * c->nblkLL * SEIR_MAX_SPLITS, &c->bytes)) ||
       (rc = dev_alloc(&c->d_col_part, (size_t)B * c->nblkLL * m->T, &c->bytes)) ||
-      (rc = dev_alloc(&c->d_rowsum, (size_t)B * m->Mp * SEIR_MAX_SPLITS, &c->bytes))) {
+      (rc = dev_alloc(&c->d_rowsum, (size_t)B * m->Mp * SEIR_MAX_SPLITS, &c->bytes)) ||
+      (rc = dev_alloc(&c->d_upd, (size_t)B, &c->bytes)) ||
+      (rc = dev_alloc(&c->d_upd_part, (size_t)B * ((m->T + 7) / 8), &c->bytes)) ||
+      (rc = dev_alloc(&c->d_llc_adj, (size_t)B, &c->bytes)) || (rc = dev_alloc(&c->d_tlp, (size_t)B, &c->bytes)) ||
+      (rc = dev_alloc(&c->d_last_acc, (size_t)4 * B * 4 * SEIR_MMAX, &c->bytes))) {
     seir_chains_destroy(c);
     return rc;
   }
@@ -192,6 +196,8 @@ int seir_chains_create(const seir_model* m, int B, seir_chains** out) {
   c->stats_bytes = sizeof(long long) * (2 * BT + 2 * (size_t)B) + sizeof(int) * (size_t)B;
   c->nllc = 0;
   SEIR_CUDA(cudaMemset(c->d_Yir, 0, c->stats_bytes));
+  SEIR_CUDA(cudaMemset(c->d_llc_adj, 0, sizeof(double) * (size_t)B));
+  SEIR_CUDA(cudaMemset(c->d_last_acc, 0, sizeof(int) * (size_t)4 * B * 4 * SEIR_MMAX));
   *out = c;
   return SEIR_OK;
 }
@@ -202,7 +208,8 @@ void seir_chains_destroy(seir_chains* c) {
   cudaFree(c->d_yse); cudaFree(c->d_yei); cudaFree(c->d_yir); cudaFree(c->d_S); cudaFree(c->d_E); cudaFree(c->d_I);
   cudaFree(c->d_Bc); cudaFree(c->d_llc_part); cudaFree(c->d_Yir); cudaFree(c->d_pa); cudaFree(c->d_psiW); cudaFree(c->d_gam);
   cudaFree(c->d_logpir); cudaFree(c->d_pm); cudaFree(c->d_scal); cudaFree(c->d_val_part); cudaFree(c->d_psi_part);
-  cudaFree(c->d_col_part); cudaFree(c->d_rowsum); cudaFree(c->d_stage_events); cudaFree(c->d_stage_theta);
+  cudaFree(c->d_col_part); cudaFree(c->d_rowsum); cudaFree(c->d_upd); cudaFree(c->d_upd_part); cudaFree(c->d_llc_adj);
+  cudaFree(c->d_tlp); cudaFree(c->d_last_acc); cudaFree(c->d_stage_events); cudaFree(c->d_stage_theta);
   cudaFree(c->d_stage_out);
   delete c;
 }
@@ -308,6 +315,41 @@ int seir_run_stage(seir_chains* c, int stage, const double* d_events, const doub
     case 7: return seir_launch_coef(c, s);
     default: return seir_set_error(SEIR_ERR_BAD_ARG, "seir_run_stage: unknown stage %d", stage);
   }
+}
+
+int seir_prepare_theta(seir_chains* c, const double* d_theta, int kind, void* stream) {
+  if (!c) return seir_set_error(SEIR_ERR_BAD_ARG, "seir_prepare_theta: NULL chains");
+  SEIR_TRY(check_dev_ptr(d_theta, "d_theta"));
+  if (kind != SEIR_THETA_CONSTRAINED && kind != SEIR_THETA_UNCONSTRAINED)
+    return seir_set_error(SEIR_ERR_BAD_ARG, "seir_prepare_theta: bad theta_kind");
+  return seir_launch_theta_prep(c, d_theta, kind, SEIR_PART_SEIR, (cudaStream_t)stream);
+}
+
+int seir_update_step(seir_chains* c, const seir_update_spec* spec, int slot, const int32_t* d_proposal, const double* d_log_u,
+                     double* d_tlp, int32_t* d_accept, int32_t* d_trace, double* d_dbg, void* stream) {
+  if (!c || !spec || !d_proposal || !d_log_u || !d_tlp || !d_accept)
+    return seir_set_error(SEIR_ERR_BAD_ARG, "seir_update_step: NULL argument");
+  const seir_model* m = c->model;
+  if (slot < 0 || slot > 3) return seir_set_error(SEIR_ERR_BAD_ARG, "seir_update_step: slot must be 0..3");
+  if (spec->kind != 0 && spec->kind != 1) return seir_set_error(SEIR_ERR_BAD_ARG, "seir_update_step: kind must be 0 (move) or 1 (occult)");
+  if (spec->target != 0 && spec->target != 1)
+    return seir_set_error(SEIR_ERR_UNSUPPORTED, "seir_update_step: only the censored transitions S->E (0) and E->I (1) can be updated");
+  if (spec->kind == 0 && (spec->mmax < 1 || spec->mmax > 2))
+    return seir_set_error(SEIR_ERR_UNSUPPORTED, "seir_update_step: 1 <= mmax <= 2 supported (got %d)", spec->mmax);
+  if (spec->nmax < 0 || (spec->kind == 0 && spec->dmax < 1)) return seir_set_error(SEIR_ERR_BAD_ARG, "seir_update_step: bad nmax/dmax");
+  if (spec->kind == 1 && !(0 <= spec->t0 && spec->t0 < spec->t1 && spec->t1 <= m->T))
+    return seir_set_error(SEIR_ERR_BAD_ARG, "seir_update_step: occult window [%d,%d) outside [0,%d)", spec->t0, spec->t1, m->T);
+  if (spec->next != spec->target + 1 || (spec->prev != -1 && spec->prev != spec->target - 1))
+    return seir_set_error(SEIR_ERR_UNSUPPORTED, "seir_update_step: topology must be (target-1 | None, target, target+1)");
+  seir_update_cfg cfg{spec->kind, spec->target, spec->prev, spec->next, spec->kind == 0 ? spec->mmax : 1, spec->nmax, spec->dmax,
+                      spec->t0, spec->t1};
+  return seir_launch_update(c, cfg, slot, d_proposal, d_log_u, d_tlp, d_accept, d_trace, d_dbg, (cudaStream_t)stream);
+}
+
+int seir_export_events(seir_chains* c, double* d_events, void* stream) {
+  if (!c) return seir_set_error(SEIR_ERR_BAD_ARG, "seir_export_events: NULL chains");
+  SEIR_TRY(check_dev_ptr(d_events, "d_events"));
+  return seir_launch_export_events(c, d_events, (cudaStream_t)stream);
 }
 
 int seir_chain_flags(const seir_chains* c, int32_t* d_flags_out, void* stream) {

@@ -47,6 +47,30 @@ struct seir_model {
   double* d_lgtab;     // [SEIR_LGTAB_BIG]
 };
 
+// ---- discrete updates (delta.cu) -------------------------------------------------------------------
+#define SEIR_MMAX 4  // max metapopulations moved by one event-time proposal (config "m", example_config.yaml:28)
+
+struct seir_update_cfg {
+  int kind;    // 0 = event-time move (UncalibratedEventTimesUpdate), 1 = occult add/delete (UncalibratedOccultUpdate)
+  int target;  // transition whose events are updated: 0 S->E, 1 E->I
+  int prev;    // previous / next transition id in the topology, -1 = None (mcmc_kernel_factory.py:127-161)
+  int next;
+  int mmax, nmax, dmax;
+  int t0, t1;  // occult window [t0, t1)  (inference.py:336-339)
+};
+
+struct seir_upd {  // per-chain scratch of one discrete update
+  int valid;       // proposal inside its own support and inside [0,T)
+  int neg;         // proposed state invalid => target_log_prob = -inf
+  int npts;        // point changes (metapopulation, day, dy) of the target transition
+  int accept;
+  int pm[4], pd[4], pdy[4];
+  double lac;      // log_acceptance_correction = log q_rev - log q_fwd
+  double dll_row;  // delta log-lik of the cells owned by the touched metapopulations
+  double dllc;     // part of dll_row that is parameter free (log binomial coefficients)
+  double dll;      // total delta (filled by the commit kernel)
+};
+
 struct seir_chains {
   const seir_model* model;
   int B;
@@ -74,6 +98,12 @@ struct seir_chains {
   double* d_psi_part;  // [B][nts*nblkLL]
   double* d_col_part;  // [B][nblkLL][T]
   double* d_rowsum;    // [B][nts][Mp]  per-day-split partial row sums
+  // discrete updates
+  seir_upd* d_upd;        // [B]
+  double* d_upd_part;     // [B][nchunk] force-of-infection delta partials
+  double* d_llc_adj;      // [B] accumulated coefficient-sum changes since the last ingest
+  double* d_tlp;          // [B] running target log-prob maintained by the update kernels
+  int* d_last_acc;        // [4 kinds][B][4][SEIR_MMAX] last accepted proposal (MetropolisHastings accepted_results)
   // staging for the host-buffer entry points
   double *d_stage_events, *d_stage_theta, *d_stage_out;
 };
@@ -98,6 +128,9 @@ int seir_launch_theta_prep(seir_chains* c, const double* d_theta, int kind, int 
 int seir_launch_loglik(seir_chains* c, bool grad, cudaStream_t s);
 int seir_launch_finalize(seir_chains* c, const double* d_theta, int kind, int parts, double* d_out, double* d_grad,
                          cudaStream_t s);
+int seir_launch_export_events(seir_chains* c, double* d_events, cudaStream_t s);
+int seir_launch_update(seir_chains* c, const seir_update_cfg& cfg, int slot, const int* d_proposal, const double* d_log_u,
+                       double* d_tlp, int* d_accept, int* d_trace, double* d_dbg, cudaStream_t s);
 
 // ---- device helpers ---------------------------------------------------------------------------
 #ifdef __CUDACC__
@@ -166,6 +199,17 @@ __device__ __forceinline__ double log_binom_coef(int n, int y, const double* lgt
     d = (n < SEIR_LGTAB ? lgtab[n] : lgamma1p_int(n, lgtab)) - lgtab[r];
   }
   return d - (y < SEIR_LGTAB ? lgtab[y] : lgamma1p_int(y, lgtab));
+}
+
+// log(1 - exp(-x)), x > 0: one log plus an even-power series for small x (truncation < 1e-17 for
+// x < 0.05), expm1+log otherwise; NaN for x < 0 like the reference's log(1 - exp(-x)).
+#define SEIR_SMALL_X 0.05
+__device__ __forceinline__ double log1mexp_neg(double x) {
+  if (x > 0.0 && x < SEIR_SMALL_X) {
+    const double x2 = x * x;
+    return log(x) + fma(x2, fma(x2, fma(x2, 5.511463844797178e-06, -3.472222222222222e-04), 0.041666666666666664), -0.5 * x);
+  }
+  return log(-expm1(-x));
 }
 
 #endif  // __CUDACC__

@@ -180,6 +180,36 @@ class SeirEngine:
         ptr = lambda t: c_void_p(t.data_ptr()) if t is not None else c_void_p(0)
         nat.check(self.lib.seir_run_stage(self.chains(B), stage, ptr(events), ptr(theta), kind, parts, ptr(out), ptr(grad), self._stream()))
 
+    # ---- a6 / a7: discrete updates ----
+    def prepare_theta(self, theta, kind=nat.THETA_UNCONSTRAINED):
+        """Load the rate factors of `theta` [B,P] for the discrete updates (after any change of theta)."""
+        th = self.to_device(theta, (self.P,))
+        nat.check(self.lib.seir_prepare_theta(self.chains(th.shape[0]), c_void_p(th.data_ptr()), kind, self._stream()))
+        return th
+
+    def update_step(self, spec: "nat.SeirUpdateSpec", slot, proposal, log_u, tlp, want_debug=False):
+        """One MH step of a discrete kernel for every chain (explicit proposals, explicit log u).
+
+        proposal int32 [B,4,MMAX] (rows m, t, delta_t, x_star), log_u [B], tlp [B] (updated in place).
+        Returns (is_accepted [B] int32, trace [B,4,MMAX] int32, debug [B,4] or None)."""
+        B = tlp.shape[0]
+        prop = torch.as_tensor(proposal, dtype=torch.int32, device=self.device).contiguous()
+        lu = torch.as_tensor(log_u, dtype=torch.float64, device=self.device).contiguous()
+        assert tuple(prop.shape) == (B, 4, nat.MMAX) and tlp.is_cuda and tlp.dtype == torch.float64
+        acc = torch.empty((B,), dtype=torch.int32, device=self.device)
+        trace = torch.empty((B, 4, nat.MMAX), dtype=torch.int32, device=self.device)
+        dbg = torch.empty((B, 4), dtype=torch.float64, device=self.device) if want_debug else None
+        nat.check(self.lib.seir_update_step(
+            self.chains(B), byref(spec), int(slot), c_void_p(prop.data_ptr()), c_void_p(lu.data_ptr()), c_void_p(tlp.data_ptr()),
+            c_void_p(acc.data_ptr()), c_void_p(trace.data_ptr()), c_void_p(dbg.data_ptr()) if dbg is not None else c_void_p(0),
+            self._stream()))
+        return acc, trace, dbg
+
+    def export_events(self, B: int) -> torch.Tensor:
+        out = torch.empty((B, self.M, self.T, 3), dtype=torch.float64, device=self.device)
+        nat.check(self.lib.seir_export_events(self.chains(B), c_void_p(out.data_ptr()), self._stream()))
+        return out
+
     def chain_flags(self, B: int) -> torch.Tensor:
         out = torch.empty((B,), dtype=torch.int32, device=self.device)
         nat.check(self.lib.seir_chain_flags(self.chains(B), c_void_p(out.data_ptr()), self._stream()))

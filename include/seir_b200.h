@@ -126,6 +126,39 @@ int seir_log_prob_host(seir_chains* chains, const double* h_events, const double
 int seir_log_prob_grad_cached(seir_chains* chains, const double* d_theta, int theta_kind, int parts,
                               double* d_out, double* d_grad, void* stream);
 
+/* ---- a6/a7: discrete Metropolis-within-Gibbs updates of the censored events -------------------- */
+/* (prev, target, next) is gemlib's TransitionTopology (mcmc_kernel_factory.py:102-104); -1 = None. */
+typedef struct seir_update_spec {
+  int32_t kind;    /* 0: MetropolisHastings(UncalibratedEventTimesUpdate)  mcmc_kernel_factory.py:63-86   */
+                   /* 1: MetropolisHastings(UncalibratedOccultUpdate)      mcmc_kernel_factory.py:89-113  */
+  int32_t target;  /* transition whose events are updated: 0 S->E, 1 E->I                                */
+  int32_t prev;    /* -1 or target-1                                                                      */
+  int32_t next;    /* target+1                                                                            */
+  int32_t mmax;    /* config "m"   (example_config.yaml:28), 1..2                                         */
+  int32_t nmax;    /* config "nmax" / "occult_nmax" (example_config.yaml:27,29)                           */
+  int32_t dmax;    /* config "dmax" (example_config.yaml:26)                                              */
+  int32_t t0, t1;  /* occult window [t0, t1)  (t_range, inference.py:336-339)                             */
+} seir_update_spec;
+
+/* Load the parameter-dependent rate factors for the discrete updates (must follow any change of theta). */
+int seir_prepare_theta(seir_chains* chains, const double* d_theta, int theta_kind, void* stream);
+
+/* One MH step of the given kernel for every chain, RNG-free: explicit proposals and explicit log-uniforms.
+ *   d_proposal [B][4][4] int32: rows m, t, delta_t, x_star (columns = moved metapopulations; an occult
+ *              uses column 0 with delta_t = +1 add / -1 delete) -- the layout of the reference's traced
+ *              `proposed_delta` (inference.py:266-273);
+ *   d_log_u    [B] log of the uniform draw;   d_tlp [B] in/out running target log-prob;
+ *   d_accept   [B] out;   d_trace [B][4][4] out (may be NULL): accepted_results of MetropolisHastings;
+ *   d_dbg      [B][4] out (may be NULL): delta log-prob, log_acceptance_correction, proposed tlp, log accept ratio.
+ * Needs caches from seir_ingest_events and rate factors from seir_prepare_theta; accepted changes are
+ * applied to every cache in place.  slot 0..3 selects the accepted_results memory of the four kernels. */
+int seir_update_step(seir_chains* chains, const seir_update_spec* spec, int slot, const int32_t* d_proposal,
+                     const double* d_log_u, double* d_tlp, int32_t* d_accept, int32_t* d_trace, double* d_dbg,
+                     void* stream);
+
+/* Current events of every chain back in the reference layout: d_events [B,M,T,3] f64. */
+int seir_export_events(seir_chains* chains, double* d_events, void* stream);
+
 /* Per-chain status bits set by ingest / commits: bit0 = events not non-negative integers,
  * bit1 = reconstructed state negative or events exceed the source compartment (log-prob = -inf). */
 int seir_chain_flags(const seir_chains* chains, int32_t* d_flags_out, void* stream);

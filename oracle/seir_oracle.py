@@ -494,6 +494,10 @@ def event_time_update(target_log_prob_fn, events, current_tlp, initial_state, to
         return dict(is_accepted=False, events=events, target_log_prob=current_tlp, proposed_tlp=-np.inf,
                     log_acceptance_correction=0.0, log_accept_ratio=-np.inf)
     q_fwd = move_log_q(events, initial_state, topology, m, t, delta_t, x_star, dmax, nmax)
+    if not np.isfinite(q_fwd) or len(set(m.tolist())) != len(m) or np.any(delta_t == 0):
+        # outside the forward proposal's own support: an invalid (rejected) proposal
+        return dict(is_accepted=False, events=events, target_log_prob=current_tlp, proposed_tlp=-np.inf,
+                    log_acceptance_correction=0.0, log_accept_ratio=-np.inf)
     proposed = apply_move(events, topology.target, m, t, delta_t, x_star)
     q_rev = move_log_q(proposed, initial_state, topology, m, to_t, -delta_t, x_star, dmax, nmax)
     tlp = target_log_prob_fn(proposed)
