@@ -78,6 +78,7 @@ SIGNATURES = {
     "seir_run_stage": (c_int, [c_void_p, c_int, c_void_p, c_void_p, c_int, c_int, c_void_p, c_void_p, c_void_p]),
     "seir_prepare_theta": (c_int, [c_void_p, c_void_p, c_int, c_void_p]),
     "seir_update_step": (c_int, [c_void_p, c_void_p, c_int, c_void_p, c_void_p, c_void_p, c_void_p, c_void_p, c_void_p, c_void_p]),
+    "seir_hmc_step": (c_int, [c_void_p, c_void_p, c_void_p, c_void_p, c_void_p, c_void_p, c_int, c_void_p, c_void_p, c_void_p, c_void_p]),
     "seir_export_events": (c_int, [c_void_p, c_void_p, c_void_p]),
     "seir_chain_flags": (c_int, [c_void_p, c_void_p, c_void_p]),
     "seir_launch_count": (c_int64, []),

@@ -1,0 +1,196 @@
+// a9: preconditioned Hamiltonian Monte Carlo on the parameter block, batched over chains
+// (tfp.experimental.mcmc.PreconditionedHamiltonianMonteCarlo [recall]; call site
+// mcmc_kernel_factory.py:14-29, kwargs inference.py:324-329: step_size 0.1, 16 leapfrog steps).
+//
+// momentum p ~ N(0, diag(1/inv_mass)); velocity = inv_mass * p; leapfrog = half kick, L x (drift,
+// value+gradient, kick) with the last kick halved; accept iff log u < (tlp1 - K1) - (tlp0 - K0).
+// The 17 value-and-gradient evaluations run against the cached events (seir_log_prob_grad_cached path):
+// the state, the contraction Cstar.(I/N) and the log binomial coefficients are constant across them.
+//
+// Also here: the counter-based Philox4x32-10 generator used by the device-side samplers.
+#include "seir_internal.cuh"
+
+// ---- Philox4x32-10 (Salmon et al. 2011), counter-based: stream = (seed, chain id), position = counter ----
+__device__ __forceinline__ void philox_round(uint32_t (&c)[4], uint32_t k0, uint32_t k1) {
+  const uint64_t p0 = (uint64_t)0xD2511F53u * c[0], p1 = (uint64_t)0xCD9E8D57u * c[2];
+  const uint32_t h0 = (uint32_t)(p0 >> 32), l0 = (uint32_t)p0, h1 = (uint32_t)(p1 >> 32), l1 = (uint32_t)p1;
+  c[0] = h1 ^ c[1] ^ k0;
+  c[1] = l1;
+  c[2] = h0 ^ c[3] ^ k1;
+  c[3] = l0;
+}
+
+__device__ void seir_philox(uint64_t seed, uint32_t c0, uint32_t c1, uint32_t c2, uint32_t c3, uint32_t (&out)[4]) {
+  uint32_t c[4] = {c0, c1, c2, c3};
+  uint32_t k0 = (uint32_t)seed, k1 = (uint32_t)(seed >> 32);
+#pragma unroll
+  for (int r = 0; r < 10; ++r) {
+    philox_round(c, k0, k1);
+    k0 += 0x9E3779B9u;
+    k1 += 0xBB67AE85u;
+  }
+  out[0] = c[0]; out[1] = c[1]; out[2] = c[2]; out[3] = c[3];
+}
+
+// uniform in (0,1) with 53 random bits
+__device__ __forceinline__ double u01_from_bits(uint32_t hi, uint32_t lo) {
+  const uint64_t x = (((uint64_t)hi << 32) | lo) >> 11;
+  return ((double)x + 0.5) * (1.0 / 9007199254740992.0);
+}
+
+// ---- momentum ~ N(0, diag(1/inv_mass)) from Philox (Box-Muller), [B][P] ----
+__global__ void __launch_bounds__(256) seir_hmc_momentum_kernel(int B, int P, uint64_t seed, uint32_t chain0, uint32_t sweep,
+                                                                const double* __restrict__ inv_mass, double* __restrict__ p) {
+  const int b = blockIdx.y;
+  for (int j2 = blockIdx.x * blockDim.x + threadIdx.x; 2 * j2 < P; j2 += gridDim.x * blockDim.x) {
+    uint32_t r[4];
+    seir_philox(seed, chain0 + (uint32_t)b, sweep, 0x484D43u /* 'HMC' */, (uint32_t)j2, r);
+    const double u1 = u01_from_bits(r[0], r[1]), u2 = u01_from_bits(r[2], r[3]);
+    const double rad = sqrt(-2.0 * log(u1));
+    double s, c;
+    sincospi(2.0 * u2, &s, &c);
+    const int j = 2 * j2;
+    const double im0 = inv_mass ? inv_mass[(size_t)b * P + j] : 1.0;
+    p[(size_t)b * P + j] = rad * c / sqrt(im0);
+    if (j + 1 < P) {
+      const double im1 = inv_mass ? inv_mass[(size_t)b * P + j + 1] : 1.0;
+      p[(size_t)b * P + j + 1] = rad * s / sqrt(im1);
+    }
+  }
+}
+
+// ---- begin: K0, save u0/tlp0, half kick ----
+__global__ void __launch_bounds__(256) seir_hmc_begin_kernel(int P, const double* __restrict__ step, const double* __restrict__ inv_mass,
+                                                             const double* __restrict__ u, const double* __restrict__ grad,
+                                                             const double* __restrict__ val, double* __restrict__ u0,
+                                                             double* __restrict__ p, double* __restrict__ k0,
+                                                             double* __restrict__ val0) {
+  __shared__ double red[32];
+  const int b = blockIdx.x;
+  const double eps = step[b];
+  double k = 0.0;
+  for (int j = threadIdx.x; j < P; j += blockDim.x) {
+    const size_t o = (size_t)b * P + j;
+    const double im = inv_mass ? inv_mass[o] : 1.0, pj = p[o];
+    k += im * pj * pj;
+    u0[o] = u[o];
+    p[o] = pj + 0.5 * eps * grad[o];
+  }
+  const double tot = block_sum(k, red);
+  if (threadIdx.x == 0) {
+    k0[b] = 0.5 * tot;
+    val0[b] = val[b];
+  }
+}
+
+// ---- drift: u += eps * inv_mass * p ----
+__global__ void __launch_bounds__(256) seir_hmc_drift_kernel(int P, const double* __restrict__ step, const double* __restrict__ inv_mass,
+                                                             const double* __restrict__ p, double* __restrict__ u) {
+  const int b = blockIdx.y;
+  const double eps = step[b];
+  for (int j = blockIdx.x * blockDim.x + threadIdx.x; j < P; j += gridDim.x * blockDim.x) {
+    const size_t o = (size_t)b * P + j;
+    u[o] = u[o] + eps * ((inv_mass ? inv_mass[o] : 1.0) * p[o]);
+  }
+}
+
+// ---- kick: p += scale * eps * grad ----
+__global__ void __launch_bounds__(256) seir_hmc_kick_kernel(int P, double scale, const double* __restrict__ step,
+                                                            const double* __restrict__ grad, double* __restrict__ p) {
+  const int b = blockIdx.y;
+  const double eps = scale * step[b];
+  for (int j = blockIdx.x * blockDim.x + threadIdx.x; j < P; j += gridDim.x * blockDim.x) {
+    const size_t o = (size_t)b * P + j;
+    p[o] = p[o] + eps * grad[o];
+  }
+}
+
+// ---- end: K1, MH decision on the energy, restore rejected chains ----
+__global__ void __launch_bounds__(256) seir_hmc_end_kernel(int P, const double* __restrict__ inv_mass, const double* __restrict__ p,
+                                                           const double* __restrict__ u0, const double* __restrict__ k0,
+                                                           const double* __restrict__ val0, const double* __restrict__ val,
+                                                           const double* __restrict__ log_u, double* __restrict__ u,
+                                                           double* __restrict__ tlp, int* __restrict__ accept,
+                                                           double* __restrict__ dbg) {
+  __shared__ double red[32];
+  __shared__ int s_acc;
+  const int b = blockIdx.x;
+  double k = 0.0;
+  for (int j = threadIdx.x; j < P; j += blockDim.x) {
+    const size_t o = (size_t)b * P + j;
+    const double pj = p[o];
+    k += (inv_mass ? inv_mass[o] : 1.0) * pj * pj;
+  }
+  const double tot = block_sum(k, red);
+  if (threadIdx.x == 0) {
+    const double k1 = 0.5 * tot;
+    const double ratio = (val[b] - k1) - (val0[b] - k0[b]);
+    const bool fin = isfinite(val[b]) && isfinite(k1);
+    const int acc = (fin && log_u[b] < ratio) ? 1 : 0;  // non-finite proposed energy rejects; NaN compares false
+    s_acc = acc;
+    accept[b] = acc;
+    tlp[b] = acc ? val[b] : val0[b];
+    if (dbg) {
+      dbg[(size_t)b * 4 + 0] = ratio;
+      dbg[(size_t)b * 4 + 1] = val[b];
+      dbg[(size_t)b * 4 + 2] = k0[b];
+      dbg[(size_t)b * 4 + 3] = k1;
+    }
+  }
+  __syncthreads();
+  if (!s_acc)
+    for (int j = threadIdx.x; j < P; j += blockDim.x) u[(size_t)b * P + j] = u0[(size_t)b * P + j];
+}
+
+static int hmc_alloc(seir_chains* c) {
+  if (c->d_hmc_u0) return SEIR_OK;
+  const size_t n = (size_t)c->B * c->model->P;
+  SEIR_CUDA(cudaMalloc(&c->d_hmc_u0, sizeof(double) * n));
+  SEIR_CUDA(cudaMalloc(&c->d_hmc_p, sizeof(double) * n));
+  SEIR_CUDA(cudaMalloc(&c->d_hmc_grad, sizeof(double) * n));
+  SEIR_CUDA(cudaMalloc(&c->d_hmc_val, sizeof(double) * 3 * (size_t)c->B));
+  c->bytes += (int64_t)(sizeof(double) * (3 * n + 3 * (size_t)c->B));
+  return SEIR_OK;
+}
+
+static int value_and_grad(seir_chains* c, const double* d_u, double* d_val, double* d_grad, cudaStream_t s) {
+  int rc;
+  if ((rc = seir_launch_theta_prep(c, d_u, SEIR_THETA_UNCONSTRAINED, SEIR_PART_JOINT, s)) != SEIR_OK) return rc;
+  if ((rc = seir_launch_loglik(c, true, s)) != SEIR_OK) return rc;
+  return seir_launch_finalize(c, d_u, SEIR_THETA_UNCONSTRAINED, SEIR_PART_JOINT, d_val, d_grad, s);
+}
+
+int seir_launch_hmc_momentum(seir_chains* c, unsigned long long seed, unsigned chain0, unsigned sweep, const double* d_inv_mass,
+                             double* d_p, cudaStream_t s) {
+  const int P = c->model->P;
+  dim3 grid((P / 2 + 255) / 256 > 0 ? (P / 2 + 255) / 256 : 1, c->B);
+  seir_hmc_momentum_kernel<<<grid, 256, 0, s>>>(c->B, P, seed, chain0, sweep, d_inv_mass, d_p);
+  seir_count_launch(1);
+  return seir_cuda_check(cudaGetLastError(), "seir_hmc_momentum_kernel");
+}
+
+// One HMC transition; d_momentum == NULL means "already in c->d_hmc_p".
+int seir_launch_hmc(seir_chains* c, double* d_u, const double* d_momentum, const double* d_log_u, const double* d_step,
+                    const double* d_inv_mass, int num_leapfrog, double* d_tlp, int* d_accept, double* d_dbg, cudaStream_t s) {
+  int rc = hmc_alloc(c);
+  if (rc != SEIR_OK) return rc;
+  const seir_model* m = c->model;
+  const int B = c->B, P = m->P;
+  double *val = c->d_hmc_val, *val0 = c->d_hmc_val + B, *k0 = c->d_hmc_val + 2 * B;
+  if (d_momentum)
+    SEIR_CUDA(cudaMemcpyAsync(c->d_hmc_p, d_momentum, sizeof(double) * (size_t)B * P, cudaMemcpyDeviceToDevice, s));
+  // GibbsKernel re-bootstraps gradient-based kernels: one fresh value+gradient at the current point
+  if ((rc = value_and_grad(c, d_u, val, c->d_hmc_grad, s)) != SEIR_OK) return rc;
+  seir_hmc_begin_kernel<<<B, 256, 0, s>>>(P, d_step, d_inv_mass, d_u, c->d_hmc_grad, val, c->d_hmc_u0, c->d_hmc_p, k0, val0);
+  const dim3 eg((P + 255) / 256, B);
+  for (int i = 0; i < num_leapfrog; ++i) {
+    seir_hmc_drift_kernel<<<eg, 256, 0, s>>>(P, d_step, d_inv_mass, c->d_hmc_p, d_u);
+    if ((rc = value_and_grad(c, d_u, val, c->d_hmc_grad, s)) != SEIR_OK) return rc;
+    seir_hmc_kick_kernel<<<eg, 256, 0, s>>>(P, i + 1 < num_leapfrog ? 1.0 : 0.5, d_step, c->d_hmc_grad, c->d_hmc_p);
+  }
+  seir_hmc_end_kernel<<<B, 256, 0, s>>>(P, d_inv_mass, c->d_hmc_p, c->d_hmc_u0, k0, val0, val, d_log_u, d_u, d_tlp, d_accept, d_dbg);
+  seir_count_launch(2 + 2 * num_leapfrog);
+  if ((rc = seir_cuda_check(cudaGetLastError(), "seir_hmc kernels")) != SEIR_OK) return rc;
+  // rate factors of the CURRENT theta for the discrete updates that follow (rejected chains moved back)
+  return seir_launch_theta_prep(c, d_u, SEIR_THETA_UNCONSTRAINED, SEIR_PART_SEIR, s);
+}

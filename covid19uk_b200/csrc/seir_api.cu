@@ -209,7 +209,8 @@ void seir_chains_destroy(seir_chains* c) {
   cudaFree(c->d_Bc); cudaFree(c->d_llc_part); cudaFree(c->d_Yir); cudaFree(c->d_pa); cudaFree(c->d_psiW); cudaFree(c->d_gam);
   cudaFree(c->d_logpir); cudaFree(c->d_pm); cudaFree(c->d_scal); cudaFree(c->d_val_part); cudaFree(c->d_psi_part);
   cudaFree(c->d_col_part); cudaFree(c->d_rowsum); cudaFree(c->d_upd); cudaFree(c->d_upd_part); cudaFree(c->d_llc_adj);
-  cudaFree(c->d_tlp); cudaFree(c->d_last_acc); cudaFree(c->d_stage_events); cudaFree(c->d_stage_theta);
+  cudaFree(c->d_tlp); cudaFree(c->d_last_acc); cudaFree(c->d_hmc_u0); cudaFree(c->d_hmc_p); cudaFree(c->d_hmc_grad);
+  cudaFree(c->d_hmc_val); cudaFree(c->d_stage_events); cudaFree(c->d_stage_theta);
   cudaFree(c->d_stage_out);
   delete c;
 }
@@ -344,6 +345,17 @@ int seir_update_step(seir_chains* c, const seir_update_spec* spec, int slot, con
   seir_update_cfg cfg{spec->kind, spec->target, spec->prev, spec->next, spec->kind == 0 ? spec->mmax : 1, spec->nmax, spec->dmax,
                       spec->t0, spec->t1};
   return seir_launch_update(c, cfg, slot, d_proposal, d_log_u, d_tlp, d_accept, d_trace, d_dbg, (cudaStream_t)stream);
+}
+
+int seir_hmc_step(seir_chains* c, double* d_u, const double* d_momentum, const double* d_log_u, const double* d_step_size,
+                  const double* d_inv_mass, int num_leapfrog_steps, double* d_tlp, int32_t* d_accept, double* d_dbg, void* stream) {
+  if (!c || !d_momentum || !d_log_u || !d_step_size || !d_tlp || !d_accept)
+    return seir_set_error(SEIR_ERR_BAD_ARG, "seir_hmc_step: NULL argument");
+  SEIR_TRY(check_dev_ptr(d_u, "d_u"));
+  if (num_leapfrog_steps < 1 || num_leapfrog_steps > 4096)
+    return seir_set_error(SEIR_ERR_BAD_ARG, "seir_hmc_step: num_leapfrog_steps out of range");
+  return seir_launch_hmc(c, d_u, d_momentum, d_log_u, d_step_size, d_inv_mass, num_leapfrog_steps, d_tlp, d_accept, d_dbg,
+                         (cudaStream_t)stream);
 }
 
 int seir_export_events(seir_chains* c, double* d_events, void* stream) {

@@ -104,6 +104,8 @@ struct seir_chains {
   double* d_llc_adj;      // [B] accumulated coefficient-sum changes since the last ingest
   double* d_tlp;          // [B] running target log-prob maintained by the update kernels
   int* d_last_acc;        // [4 kinds][B][4][SEIR_MMAX] last accepted proposal (MetropolisHastings accepted_results)
+  // HMC workspace (allocated on first use)
+  double *d_hmc_u0, *d_hmc_p, *d_hmc_grad, *d_hmc_val;
   // staging for the host-buffer entry points
   double *d_stage_events, *d_stage_theta, *d_stage_out;
 };
@@ -128,6 +130,10 @@ int seir_launch_theta_prep(seir_chains* c, const double* d_theta, int kind, int 
 int seir_launch_loglik(seir_chains* c, bool grad, cudaStream_t s);
 int seir_launch_finalize(seir_chains* c, const double* d_theta, int kind, int parts, double* d_out, double* d_grad,
                          cudaStream_t s);
+int seir_launch_hmc_momentum(seir_chains* c, unsigned long long seed, unsigned chain0, unsigned sweep, const double* d_inv_mass,
+                             double* d_p, cudaStream_t s);
+int seir_launch_hmc(seir_chains* c, double* d_u, const double* d_momentum, const double* d_log_u, const double* d_step,
+                    const double* d_inv_mass, int num_leapfrog, double* d_tlp, int* d_accept, double* d_dbg, cudaStream_t s);
 int seir_launch_export_events(seir_chains* c, double* d_events, cudaStream_t s);
 int seir_launch_update(seir_chains* c, const seir_update_cfg& cfg, int slot, const int* d_proposal, const double* d_log_u,
                        double* d_tlp, int* d_accept, int* d_trace, double* d_dbg, cudaStream_t s);

@@ -205,6 +205,25 @@ class SeirEngine:
             self._stream()))
         return acc, trace, dbg
 
+    # ---- a9: HMC ----
+    def hmc_step(self, u, momentum, log_u, step_size, inv_mass=None, num_leapfrog_steps=16, want_debug=False):
+        """One PreconditionedHMC transition per chain (explicit momentum and log u).  `u` [B,P] is a CUDA
+        float64 tensor updated in place.  Returns (tlp [B], is_accepted [B] int32, debug [B,4] or None)."""
+        assert u.is_cuda and u.dtype == torch.float64 and u.is_contiguous() and u.dim() == 2 and u.shape[1] == self.P
+        B = u.shape[0]
+        dev = lambda a: torch.as_tensor(a, dtype=torch.float64, device=self.device).contiguous()
+        mom, lu = dev(momentum), dev(log_u)
+        st = dev(step_size).expand(B).contiguous() if dev(step_size).dim() == 0 else dev(step_size)
+        im = dev(inv_mass).expand(B, self.P).contiguous() if inv_mass is not None else None
+        tlp = torch.empty((B,), dtype=torch.float64, device=self.device)
+        acc = torch.empty((B,), dtype=torch.int32, device=self.device)
+        dbg = torch.empty((B, 4), dtype=torch.float64, device=self.device) if want_debug else None
+        nat.check(self.lib.seir_hmc_step(
+            self.chains(B), c_void_p(u.data_ptr()), c_void_p(mom.data_ptr()), c_void_p(lu.data_ptr()), c_void_p(st.data_ptr()),
+            c_void_p(im.data_ptr()) if im is not None else c_void_p(0), int(num_leapfrog_steps), c_void_p(tlp.data_ptr()),
+            c_void_p(acc.data_ptr()), c_void_p(dbg.data_ptr()) if dbg is not None else c_void_p(0), self._stream()))
+        return tlp, acc, dbg
+
     def export_events(self, B: int) -> torch.Tensor:
         out = torch.empty((B, self.M, self.T, 3), dtype=torch.float64, device=self.device)
         nat.check(self.lib.seir_export_events(self.chains(B), c_void_p(out.data_ptr()), self._stream()))

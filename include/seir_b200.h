@@ -126,6 +126,19 @@ int seir_log_prob_host(seir_chains* chains, const double* h_events, const double
 int seir_log_prob_grad_cached(seir_chains* chains, const double* d_theta, int theta_kind, int parts,
                               double* d_out, double* d_grad, void* stream);
 
+/* ---- a9: PreconditionedHamiltonianMonteCarlo on the parameter block ----------------------------- */
+/* One HMC transition for every chain (mcmc_kernel_factory.py:14-29; step_size / num_leapfrog_steps
+ * inference.py:324-329), RNG-free: explicit momentum draw and explicit log-uniform.
+ *   d_u [B,P] in/out unconstrained parameters;  d_momentum [B,P] ~ N(0, diag(1/inv_mass));
+ *   d_step_size [B];  d_inv_mass [B,P] or NULL (identity) -- the running variance of
+ *   DiagonalMassMatrixAdaptation (inference.py:36-47,184-186);  d_tlp [B] out (accepted state's joint
+ *   log-prob);  d_accept [B] out;  d_dbg [B][4] out or NULL: log accept ratio, proposed tlp, K0, K1.
+ * Runs 1 + num_leapfrog_steps value-and-gradient evaluations against the cached events and leaves the
+ * rate factors of the resulting theta loaded (as seir_prepare_theta would). */
+int seir_hmc_step(seir_chains* chains, double* d_u, const double* d_momentum, const double* d_log_u,
+                  const double* d_step_size, const double* d_inv_mass, int num_leapfrog_steps, double* d_tlp,
+                  int32_t* d_accept, double* d_dbg, void* stream);
+
 /* ---- a6/a7: discrete Metropolis-within-Gibbs updates of the censored events -------------------- */
 /* (prev, target, next) is gemlib's TransitionTopology (mcmc_kernel_factory.py:102-104); -1 = None. */
 typedef struct seir_update_spec {

@@ -248,7 +248,7 @@ def car_constants(adjacency):
 def mvn_tril_log_prob(x, scale_tril):
     from scipy.linalg import solve_triangular
 
-    z = solve_triangular(scale_tril, np.asarray(x, DTYPE), lower=True)
+    z = solve_triangular(scale_tril, np.asarray(x, DTYPE), lower=True, check_finite=False)
     M = x.shape[-1]
     return float(-0.5 * np.sum(z * z) - M * _HALF_LOG_2PI - np.sum(np.log(np.diag(scale_tril))))
 
@@ -404,8 +404,8 @@ class OracleModel:
         from scipy.linalg import solve_triangular
 
         L = self.car["scale_tril"]
-        z = solve_triangular(L, params["spatial_effect"], lower=True)
-        grad_theta[6 + T - 1 :] += -solve_triangular(L.T, z, lower=False)
+        z = solve_triangular(L, params["spatial_effect"], lower=True, check_finite=False)
+        grad_theta[6 + T - 1 :] += -solve_triangular(L.T, z, lower=False, check_finite=False)
         # chain rule to the unconstrained space + ILDJ
         grad_u = grad_theta.copy()
         sig = 1.0 / (1.0 + np.exp(-u[:2]))
