@@ -50,6 +50,13 @@ class SeirUpdateSpec(ctypes.Structure):
     _fields_ = [(n, c_int32) for n in ("kind", "target", "prev", "next", "mmax", "nmax", "dmax", "t0", "t1")]
 
 
+class SeirSweepSpec(ctypes.Structure):
+    """include/seir_b200.h: struct seir_sweep_spec."""
+
+    _fields_ = [(n, c_int32) for n in ("num_leapfrog_steps", "num_event_time_updates", "dmax", "nmax", "mmax", "occult_nmax", "t0", "t1")] + [
+        ("chain_offset", ctypes.c_uint32), ("reserved", ctypes.c_uint32), ("seed", ctypes.c_uint64)]
+
+
 MMAX = 4  # columns of a proposal record [4][MMAX] (rows m, t, delta_t, x_star)
 
 
@@ -79,6 +86,8 @@ SIGNATURES = {
     "seir_prepare_theta": (c_int, [c_void_p, c_void_p, c_int, c_void_p]),
     "seir_update_step": (c_int, [c_void_p, c_void_p, c_int, c_void_p, c_void_p, c_void_p, c_void_p, c_void_p, c_void_p, c_void_p]),
     "seir_hmc_step": (c_int, [c_void_p, c_void_p, c_void_p, c_void_p, c_void_p, c_void_p, c_int, c_void_p, c_void_p, c_void_p, c_void_p]),
+    "seir_propose": (c_int, [c_void_p, c_void_p, ctypes.c_uint64, ctypes.c_uint32, ctypes.c_uint32, c_void_p, c_void_p, c_void_p]),
+    "seir_mcmc_sweep": (c_int, [c_void_p, c_void_p, ctypes.c_uint32] + [c_void_p] * 10),
     "seir_export_events": (c_int, [c_void_p, c_void_p, c_void_p]),
     "seir_chain_flags": (c_int, [c_void_p, c_void_p, c_void_p]),
     "seir_launch_count": (c_int64, []),

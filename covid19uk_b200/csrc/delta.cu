@@ -16,106 +16,7 @@
 //
 // Proposal conventions restated from gemlib ([recall], see oracle/seir_oracle.py move_max_events /
 // occult_delete_max and SURVEY Appendix B.1/B.3): parity unpinned.
-#include <limits.h>
-
-#include "seir_internal.cuh"
-
-#define UPD_THREADS 128
-#define SLAB_DAYS 8
-
-struct chain_view {
-  int M, T, Mp;
-  const int *yse, *yei, *yir, *S, *E, *I;  // already offset to the chain
-  const int* init;                         // [Mp][4]
-};
-
-__device__ __forceinline__ const int* yarr(const chain_view& v, int x) { return x == 0 ? v.yse : (x == 1 ? v.yei : v.yir); }
-__device__ __forceinline__ const int* xarr(const chain_view& v, int c) { return c == 0 ? v.S : (c == 1 ? v.E : v.I); }
-
-// state of compartment c (0..2) of metapopulation m AFTER the events of day s
-__device__ __forceinline__ int after_state(const chain_view& v, int c, int m, int s) {
-  const size_t o = (size_t)s * v.Mp + m;
-  int x = xarr(v, c)[o] - yarr(v, c)[o];
-  if (c > 0) x += yarr(v, c - 1)[o];
-  return x;
-}
-
-// net change of the cumulative target-event count of metapopulation m with day <= s under the proposal
-__device__ __forceinline__ int dcum_le(const int* pm, const int* pd, const int* pdy, int npts, int m, int s) {
-  int d = 0;
-  for (int p = 0; p < npts; ++p)
-    if (pm[p] == m && pd[p] <= s) d += pdy[p];
-  return d;
-}
-__device__ __forceinline__ int dy_at(const int* pm, const int* pd, const int* pdy, int npts, int m, int s) {
-  int d = 0;
-  for (int p = 0; p < npts; ++p)
-    if (pm[p] == m && pd[p] == s) d += pdy[p];
-  return d;
-}
-
-__device__ __forceinline__ int blk_reduce_min(int v, int* red) {
-  v = __reduce_min_sync(0xffffffffu, v);
-  __syncthreads();
-  if ((threadIdx.x & 31) == 0) red[threadIdx.x >> 5] = v;
-  __syncthreads();
-  int r = red[0];
-  for (int w = 1; w < UPD_THREADS / 32; ++w) r = min(r, red[w]);
-  return r;
-}
-__device__ __forceinline__ int blk_reduce_add(int v, int* red) {
-  v = __reduce_add_sync(0xffffffffu, v);
-  __syncthreads();
-  if ((threadIdx.x & 31) == 0) red[threadIdx.x >> 5] = v;
-  __syncthreads();
-  int r = 0;
-  for (int w = 0; w < UPD_THREADS / 32; ++w) r += red[w];
-  return r;
-}
-__device__ __forceinline__ double blk_reduce_addd(double v, double* red) {
-  v = warp_sum(v);
-  __syncthreads();
-  if ((threadIdx.x & 31) == 0) red[threadIdx.x >> 5] = v;
-  __syncthreads();
-  double r = 0.0;
-  for (int w = 0; w < UPD_THREADS / 32; ++w) r += red[w];
-  return r;
-}
-
-// min over days s in [lo, hi) of  init_c + |X_c(s+1) - init_c|   (gemlib _abscumdiff convention), on the
-// current (delta = 0) or proposed state; compartment c loses dcum for c == target and gains it for target+1.
-__device__ int bound_abs_min(const chain_view& v, int c, int m, int lo, int hi, bool proposed, int target, const int* pm,
-                             const int* pd, const int* pdy, int npts, int* red) {
-  const int init_c = v.init[m * 4 + c];
-  int best = INT_MAX;
-  for (int s = lo + (int)threadIdx.x; s < hi; s += UPD_THREADS) {
-    int x = after_state(v, c, m, s);
-    if (proposed) {
-      const int d = dcum_le(pm, pd, pdy, npts, m, s);
-      x += (c == target) ? -d : d;
-    }
-    const int dev = x - init_c;
-    best = min(best, init_c + (dev < 0 ? -dev : dev));
-  }
-  return blk_reduce_min(best, red);
-}
-
-// min over days s in [lo, hi) of X_c(s+1) (occult delete bound, no abs)
-__device__ int bound_level_min(const chain_view& v, int c, int m, int lo, int hi, bool proposed, int target, const int* pm,
-                               const int* pd, const int* pdy, int npts, int* red) {
-  int best = INT_MAX;
-  for (int s = lo + (int)threadIdx.x; s < hi; s += UPD_THREADS) {
-    int x = after_state(v, c, m, s);
-    if (proposed) {
-      const int d = dcum_le(pm, pd, pdy, npts, m, s);
-      x += (c == target) ? -d : d;
-    }
-    best = min(best, x);
-  }
-  return blk_reduce_min(best, red);
-}
-
-__device__ __forceinline__ int clampi(int x, int lo, int hi) { return x < lo ? lo : (x > hi ? hi : x); }
+#include "delta_common.cuh"
 
 // ------------------------------------------------------------------------------------------------
 // prepare: one CTA per chain.  Parses the proposal, evaluates log q_fwd / log q_rev and the delta

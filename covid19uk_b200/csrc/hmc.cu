@@ -8,34 +8,23 @@
 // the state, the contraction Cstar.(I/N) and the log binomial coefficients are constant across them.
 //
 // Also here: the counter-based Philox4x32-10 generator used by the device-side samplers.
+#include "philox.cuh"
 #include "seir_internal.cuh"
 
-// ---- Philox4x32-10 (Salmon et al. 2011), counter-based: stream = (seed, chain id), position = counter ----
-__device__ __forceinline__ void philox_round(uint32_t (&c)[4], uint32_t k0, uint32_t k1) {
-  const uint64_t p0 = (uint64_t)0xD2511F53u * c[0], p1 = (uint64_t)0xCD9E8D57u * c[2];
-  const uint32_t h0 = (uint32_t)(p0 >> 32), l0 = (uint32_t)p0, h1 = (uint32_t)(p1 >> 32), l1 = (uint32_t)p1;
-  c[0] = h1 ^ c[1] ^ k0;
-  c[1] = l1;
-  c[2] = h0 ^ c[3] ^ k1;
-  c[3] = l0;
+// ---- log u = log(U(0,1)) for the MH decisions, [B] ----
+__global__ void seir_log_uniform_kernel(int B, uint64_t seed, uint32_t chain0, uint32_t sweep, uint32_t purpose, double* __restrict__ out) {
+  const int b = blockIdx.x * blockDim.x + threadIdx.x;
+  if (b >= B) return;
+  uint32_t r[4];
+  seir_philox(seed, chain0 + (uint32_t)b, sweep, purpose, 0u, r);
+  out[b] = log(u01_from_bits(r[0], r[1]));
 }
 
-__device__ void seir_philox(uint64_t seed, uint32_t c0, uint32_t c1, uint32_t c2, uint32_t c3, uint32_t (&out)[4]) {
-  uint32_t c[4] = {c0, c1, c2, c3};
-  uint32_t k0 = (uint32_t)seed, k1 = (uint32_t)(seed >> 32);
-#pragma unroll
-  for (int r = 0; r < 10; ++r) {
-    philox_round(c, k0, k1);
-    k0 += 0x9E3779B9u;
-    k1 += 0xBB67AE85u;
-  }
-  out[0] = c[0]; out[1] = c[1]; out[2] = c[2]; out[3] = c[3];
-}
-
-// uniform in (0,1) with 53 random bits
-__device__ __forceinline__ double u01_from_bits(uint32_t hi, uint32_t lo) {
-  const uint64_t x = (((uint64_t)hi << 32) | lo) >> 11;
-  return ((double)x + 0.5) * (1.0 / 9007199254740992.0);
+int seir_launch_log_uniform(int B, unsigned long long seed, unsigned chain0, unsigned sweep, unsigned purpose, double* d_out,
+                            cudaStream_t s) {
+  seir_log_uniform_kernel<<<(B + 127) / 128, 128, 0, s>>>(B, seed, chain0, sweep, purpose, d_out);
+  seir_count_launch(1);
+  return seir_cuda_check(cudaGetLastError(), "seir_log_uniform_kernel");
 }
 
 // ---- momentum ~ N(0, diag(1/inv_mass)) from Philox (Box-Muller), [B][P] ----
@@ -152,6 +141,8 @@ static int hmc_alloc(seir_chains* c) {
   c->bytes += (int64_t)(sizeof(double) * (3 * n + 3 * (size_t)c->B));
   return SEIR_OK;
 }
+
+int seir_hmc_workspace(seir_chains* c) { return hmc_alloc(c); }
 
 static int value_and_grad(seir_chains* c, const double* d_u, double* d_val, double* d_grad, cudaStream_t s) {
   int rc;

@@ -210,7 +210,7 @@ void seir_chains_destroy(seir_chains* c) {
   cudaFree(c->d_logpir); cudaFree(c->d_pm); cudaFree(c->d_scal); cudaFree(c->d_val_part); cudaFree(c->d_psi_part);
   cudaFree(c->d_col_part); cudaFree(c->d_rowsum); cudaFree(c->d_upd); cudaFree(c->d_upd_part); cudaFree(c->d_llc_adj);
   cudaFree(c->d_tlp); cudaFree(c->d_last_acc); cudaFree(c->d_hmc_u0); cudaFree(c->d_hmc_p); cudaFree(c->d_hmc_grad);
-  cudaFree(c->d_hmc_val); cudaFree(c->d_stage_events); cudaFree(c->d_stage_theta);
+  cudaFree(c->d_hmc_val); cudaFree(c->d_prop); cudaFree(c->d_logu); cudaFree(c->d_stage_events); cudaFree(c->d_stage_theta);
   cudaFree(c->d_stage_out);
   delete c;
 }
@@ -356,6 +356,34 @@ int seir_hmc_step(seir_chains* c, double* d_u, const double* d_momentum, const d
     return seir_set_error(SEIR_ERR_BAD_ARG, "seir_hmc_step: num_leapfrog_steps out of range");
   return seir_launch_hmc(c, d_u, d_momentum, d_log_u, d_step_size, d_inv_mass, num_leapfrog_steps, d_tlp, d_accept, d_dbg,
                          (cudaStream_t)stream);
+}
+
+int seir_propose(seir_chains* c, const seir_update_spec* spec, uint64_t seed, uint32_t chain_offset, uint32_t counter,
+                 int32_t* d_proposal, double* d_log_u, void* stream) {
+  if (!c || !spec || !d_proposal || !d_log_u) return seir_set_error(SEIR_ERR_BAD_ARG, "seir_propose: NULL argument");
+  if ((spec->kind != 0 && spec->kind != 1) || (spec->target != 0 && spec->target != 1))
+    return seir_set_error(SEIR_ERR_BAD_ARG, "seir_propose: bad kind/target");
+  if (spec->kind == 0 && (spec->mmax < 1 || spec->mmax > 2 || spec->dmax < 1))
+    return seir_set_error(SEIR_ERR_UNSUPPORTED, "seir_propose: need 1 <= mmax <= 2 and dmax >= 1");
+  if (spec->kind == 1 && !(0 <= spec->t0 && spec->t0 < spec->t1 && spec->t1 <= c->model->T))
+    return seir_set_error(SEIR_ERR_BAD_ARG, "seir_propose: bad occult window");
+  seir_update_cfg cfg{spec->kind, spec->target, spec->prev, spec->next, spec->kind == 0 ? spec->mmax : 1, spec->nmax, spec->dmax,
+                      spec->t0, spec->t1};
+  return seir_launch_propose(c, cfg, seed, chain_offset, counter, d_proposal, d_log_u, (cudaStream_t)stream);
+}
+
+int seir_mcmc_sweep(seir_chains* c, const seir_sweep_spec* sp, uint32_t sweep_index, double* d_u, const double* d_step_size,
+                    const double* d_inv_mass, double* d_tlp, int32_t* d_hmc_accept, double* d_hmc_dbg, int32_t* d_upd_accept,
+                    double* d_upd_tlp, int32_t* d_upd_trace, void* stream) {
+  if (!c || !sp || !d_step_size || !d_tlp || !d_hmc_accept || !d_upd_accept)
+    return seir_set_error(SEIR_ERR_BAD_ARG, "seir_mcmc_sweep: NULL argument");
+  SEIR_TRY(check_dev_ptr(d_u, "d_u"));
+  const int T = c->model->T;
+  if (sp->num_leapfrog_steps < 1 || sp->num_event_time_updates < 0 || sp->mmax < 1 || sp->mmax > 2 || sp->dmax < 1 || sp->nmax < 0 ||
+      sp->occult_nmax < 0 || !(0 <= sp->t0 && sp->t0 < sp->t1 && sp->t1 <= T) || sp->num_event_time_updates > 16)
+    return seir_set_error(SEIR_ERR_BAD_ARG, "seir_mcmc_sweep: invalid sweep spec");
+  return seir_launch_sweep(c, sp, sweep_index, d_u, d_step_size, d_inv_mass, d_tlp, d_hmc_accept, d_hmc_dbg, d_upd_accept, d_upd_tlp,
+                           d_upd_trace, (cudaStream_t)stream);
 }
 
 int seir_export_events(seir_chains* c, double* d_events, void* stream) {

@@ -106,6 +106,9 @@ struct seir_chains {
   int* d_last_acc;        // [4 kinds][B][4][SEIR_MMAX] last accepted proposal (MetropolisHastings accepted_results)
   // HMC workspace (allocated on first use)
   double *d_hmc_u0, *d_hmc_p, *d_hmc_grad, *d_hmc_val;
+  // sweep scratch: sampled proposals and log-uniforms
+  int* d_prop;
+  double* d_logu;
   // staging for the host-buffer entry points
   double *d_stage_events, *d_stage_theta, *d_stage_out;
 };
@@ -134,6 +137,14 @@ int seir_launch_hmc_momentum(seir_chains* c, unsigned long long seed, unsigned c
                              double* d_p, cudaStream_t s);
 int seir_launch_hmc(seir_chains* c, double* d_u, const double* d_momentum, const double* d_log_u, const double* d_step,
                     const double* d_inv_mass, int num_leapfrog, double* d_tlp, int* d_accept, double* d_dbg, cudaStream_t s);
+int seir_hmc_workspace(seir_chains* c);
+int seir_launch_log_uniform(int B, unsigned long long seed, unsigned chain0, unsigned sweep, unsigned purpose, double* d_out,
+                            cudaStream_t s);
+int seir_launch_propose(seir_chains* c, const seir_update_cfg& cfg, unsigned long long seed, unsigned chain0, unsigned ctr,
+                        int* d_proposal, double* d_log_u, cudaStream_t s);
+int seir_launch_sweep(seir_chains* c, const seir_sweep_spec* sp, unsigned sweep_index, double* d_u, const double* d_step,
+                      const double* d_inv_mass, double* d_tlp, int* d_hmc_accept, double* d_hmc_dbg, int* d_upd_accept,
+                      double* d_upd_tlp, int* d_upd_trace, cudaStream_t s);
 int seir_launch_export_events(seir_chains* c, double* d_events, cudaStream_t s);
 int seir_launch_update(seir_chains* c, const seir_update_cfg& cfg, int slot, const int* d_proposal, const double* d_log_u,
                        double* d_tlp, int* d_accept, int* d_trace, double* d_dbg, cudaStream_t s);

@@ -224,6 +224,23 @@ class SeirEngine:
             c_void_p(acc.data_ptr()), c_void_p(dbg.data_ptr()) if dbg is not None else c_void_p(0), self._stream()))
         return tlp, acc, dbg
 
+    # ---- device-side proposals and the fused sweep (a8) ----
+    def propose(self, spec: "nat.SeirUpdateSpec", B, seed, chain_offset, counter):
+        """Draw one proposal per chain on the device -> (proposal int32 [B,4,MMAX], log_u [B])."""
+        prop = torch.empty((B, 4, nat.MMAX), dtype=torch.int32, device=self.device)
+        lu = torch.empty((B,), dtype=torch.float64, device=self.device)
+        nat.check(self.lib.seir_propose(self.chains(B), byref(spec), int(seed), int(chain_offset), int(counter),
+                                        c_void_p(prop.data_ptr()), c_void_p(lu.data_ptr()), self._stream()))
+        return prop, lu
+
+    def mcmc_sweep(self, spec: "nat.SeirSweepSpec", sweep_index, u, step_size, inv_mass, tlp, hmc_accept, upd_accept,
+                   hmc_dbg=None, upd_tlp=None, upd_trace=None):
+        """One Metropolis-within-Gibbs sweep for every chain; all tensors are caller-owned CUDA tensors."""
+        B = u.shape[0]
+        p = lambda t: c_void_p(t.data_ptr()) if t is not None else c_void_p(0)
+        nat.check(self.lib.seir_mcmc_sweep(self.chains(B), byref(spec), int(sweep_index), p(u), p(step_size), p(inv_mass), p(tlp),
+                                           p(hmc_accept), p(hmc_dbg), p(upd_accept), p(upd_tlp), p(upd_trace), self._stream()))
+
     def export_events(self, B: int) -> torch.Tensor:
         out = torch.empty((B, self.M, self.T, 3), dtype=torch.float64, device=self.device)
         nat.check(self.lib.seir_export_events(self.chains(B), c_void_p(out.data_ptr()), self._stream()))

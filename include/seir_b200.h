@@ -169,6 +169,37 @@ int seir_update_step(seir_chains* chains, const seir_update_spec* spec, int slot
                      const double* d_log_u, double* d_tlp, int32_t* d_accept, int32_t* d_trace, double* d_dbg,
                      void* stream);
 
+/* Draw one proposal per chain for the given kernel on the device (Philox stream keyed by
+ * chain_offset + chain index; `counter` selects the position in the stream).  Writes d_proposal [B][4][4]
+ * and d_log_u [B] in the layout seir_update_step consumes.  The reference never seeds its RNG
+ * (inference.py:68,134,205), so only the proposal distributions are reproduced, not a stream. */
+int seir_propose(seir_chains* chains, const seir_update_spec* spec, uint64_t seed, uint32_t chain_offset,
+                 uint32_t counter, int32_t* d_proposal, double* d_log_u, void* stream);
+
+/* ---- a8: one full Metropolis-within-Gibbs sweep (GibbsKernel + MultiScanKernel) ------------------ */
+typedef struct seir_sweep_spec {
+  int32_t num_leapfrog_steps;     /* inference.py:326 (16)                                              */
+  int32_t num_event_time_updates; /* config, example_config.yaml:30 (5)                                 */
+  int32_t dmax, nmax, mmax;       /* example_config.yaml:26-28                                          */
+  int32_t occult_nmax;            /* example_config.yaml:29                                             */
+  int32_t t0, t1;                 /* occult t_range = [T-21, T), inference.py:336-339                   */
+  uint32_t chain_offset;          /* global id of this rank's first chain (RNG streams are rank independent) */
+  uint32_t reserved;
+  uint64_t seed;
+} seir_sweep_spec;
+
+/* HMC on theta, then num_event_time_updates x [S->E move, E->I move, S->E occult, E->I occult], for every
+ * chain, all on `stream` without host synchronisation (inference.py:219-228, mcmc_kernel_factory.py:116-168).
+ *   d_u [B,P] in/out;  d_step_size [B];  d_inv_mass [B,P] or NULL;  d_tlp [B] in/out;
+ *   d_hmc_accept [B];  d_hmc_dbg [B][4] or NULL;
+ *   d_upd_accept [4][B], d_upd_tlp [5][B] (or NULL), d_upd_trace [4][B][4][4] (or NULL): results of the LAST
+ *   repetition of each of the four discrete kernels (what MultiScanKernel returns and inference.py:262-280 traces);
+ *   row 4 of d_upd_tlp is the target log-prob right after the HMC step (results/hmc/target_log_prob).
+ * Needs caches from seir_ingest_events. */
+int seir_mcmc_sweep(seir_chains* chains, const seir_sweep_spec* spec, uint32_t sweep_index, double* d_u,
+                    const double* d_step_size, const double* d_inv_mass, double* d_tlp, int32_t* d_hmc_accept,
+                    double* d_hmc_dbg, int32_t* d_upd_accept, double* d_upd_tlp, int32_t* d_upd_trace, void* stream);
+
 /* Current events of every chain back in the reference layout: d_events [B,M,T,3] f64. */
 int seir_export_events(seir_chains* chains, double* d_events, void* stream);
 

@@ -1,0 +1,105 @@
+"""GPU tests of the device-side proposal samplers and the fused Metropolis-within-Gibbs sweep (a8):
+proposals lie in the support the oracle computes, the in-place caches stay consistent with a fresh
+evaluation, and results do not depend on how chains are partitioned (RNG streams keyed by global chain id)."""
+import numpy as np
+import pytest
+
+pytestmark = pytest.mark.gpu
+
+CFG = dict(dmax=84, nmax=25, m=2, occult_nmax=15, num_event_time_updates=5)  # example_config.yaml:26-30
+
+
+def _setup(M, T, B, seed=0):
+    from covid19uk_b200 import synthetic as syn
+    from covid19uk_b200.engine import SeirEngine
+    from oracle import seir_oracle as so
+
+    pb = syn.make_problem(M, T, chains=B, seed=seed)
+    eng = SeirEngine(pb["covariates"], pb["initial_state"], 0, T)
+    om = so.OracleModel(pb["covariates"], pb["initial_state"], 0, T)
+    return pb, eng, om, so.unconstrain(pb["theta"])
+
+
+def test_device_proposals_are_in_support():
+    from covid19uk_b200 import _native as nat
+    from oracle import seir_oracle as so
+
+    M, T, B = 40, 60, 16
+    pb, eng, om, u = _setup(M, T, B)
+    eng.ingest(pb["events"])
+    eng.prepare_theta(u)
+    init = pb["initial_state"]
+    t_range = [T - 21, T]
+    S = nat.SeirUpdateSpec
+    specs = [S(kind=0, target=0, prev=-1, next=1, mmax=2, nmax=25, dmax=30, t0=0, t1=0),
+             S(kind=0, target=1, prev=0, next=2, mmax=2, nmax=25, dmax=30, t0=0, t1=0),
+             S(kind=1, target=0, prev=-1, next=1, mmax=1, nmax=15, dmax=0, t0=t_range[0], t1=t_range[1]),
+             S(kind=1, target=1, prev=0, next=2, mmax=1, nmax=15, dmax=0, t0=t_range[0], t1=t_range[1])]
+    topo = {0: so.TransitionTopology(None, 0, 1), 1: so.TransitionTopology(0, 1, 2)}
+    seen_add = seen_del = 0
+    xs = []
+    for ctr in range(12):
+        for spec in specs:
+            prop, log_u = eng.propose(spec, B, seed=123, chain_offset=0, counter=ctr * 4 + spec.kind * 2 + spec.target)
+            prop, log_u = prop.cpu().numpy(), log_u.cpu().numpy()
+            assert np.all(log_u < 0)
+            for b in range(B):
+                ev = pb["events"][b]
+                tp = topo[spec.target]
+                if spec.kind == 0:
+                    m, t, d, x = (prop[b, r, :2].astype(np.int64) for r in range(4))
+                    assert m[0] != m[1] and np.all(np.abs(d) >= 1) and np.all(np.abs(d) <= 30)
+                    assert np.all(ev[m, t, spec.target] > 0)
+                    inside = np.all((t + d >= 0) & (t + d < T))
+                    if inside:
+                        assert np.isfinite(so.move_log_q(ev, init, tp, m, t, d, x, 30, 25))
+                    else:  # a destination outside [0,T) rejects the whole proposal; its own x* stays 0
+                        outside = (t + d < 0) | (t + d >= T)
+                        assert np.all(x[outside] == 0)
+                    xs.extend(x.tolist())
+                else:
+                    m, t, sg, x = (int(prop[b, r, 0]) for r in range(4))
+                    assert t_range[0] <= t < t_range[1] and 0 <= m < M and sg in (1, -1)
+                    if sg > 0:
+                        seen_add += 1
+                        assert 0 <= x <= 15
+                    else:
+                        seen_del += 1
+                        assert np.isfinite(so.occult_log_q_del(ev, init, tp, t_range, 15, m, t, x))
+    assert seen_add > 0 and seen_del > 0
+    assert max(xs) > 0
+    eng.close()
+
+
+def test_sweeps_keep_caches_consistent_and_are_partition_independent():
+    import torch
+    from covid19uk_b200 import _native as nat
+    from covid19uk_b200.inference.sampler import ChainSet
+
+    M, T, B = 60, 84, 6
+    pb, eng, om, u = _setup(M, T, B, seed=4)
+    t_range = [T - 21, T]
+    cs = ChainSet(eng, pb["events"], u, CFG, t_range, seed=99, chain_offset=0)
+    draws, trace = cs.sample(12, step_size=1e-3)
+    ev = cs.events().cpu().numpy()
+    assert ev.min() >= 0 and np.array_equal(ev, np.round(ev))
+    assert not np.array_equal(ev, pb["events"])  # some discrete update was accepted
+    for k in ("move/S->E", "move/E->I", "occult/S->E", "occult/E->I"):
+        assert trace[k]["is_accepted"].shape == (12, B)
+    # running target log-prob == joint log-prob recomputed from scratch on the exported events
+    fresh = eng.log_prob(ev, cs.u, nat.THETA_UNCONSTRAINED, nat.PART_JOINT).cpu().numpy()
+    np.testing.assert_allclose(cs.tlp.cpu().numpy(), fresh, rtol=1e-10)
+    for b in range(2):
+        ref = om.joint_log_prob(cs.u[b].cpu().numpy(), ev[b])
+        assert abs(fresh[b] - ref) <= 1e-10 * abs(ref)
+    assert int(eng.chain_flags(B).abs().sum()) == 0
+    last = trace["occult/E->I"]["target_log_prob"][-1].cpu().numpy()
+    np.testing.assert_allclose(last, cs.tlp.cpu().numpy(), rtol=1e-13)
+    u_all, ev_all = cs.u.cpu().numpy().copy(), ev.copy()
+
+    # the same global chains 4,5 run alone (another "rank") give bit-identical results
+    cs2 = ChainSet(eng, pb["events"][4:6], u[4:6], CFG, t_range, seed=99, chain_offset=4)
+    cs2.sample(12, step_size=1e-3)
+    assert np.array_equal(cs2.u.cpu().numpy(), u_all[4:6])
+    assert np.array_equal(cs2.events().cpu().numpy(), ev_all[4:6])
+    eng.close()
