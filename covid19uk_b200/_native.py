@@ -17,7 +17,7 @@ PART_SEIR = 1
 PART_PRIORS = 2
 PART_ILDJ = 4
 PART_JOINT = 7
-ABI_VERSION = 3
+ABI_VERSION = 4
 
 
 class SeirSpec(ctypes.Structure):
@@ -86,6 +86,7 @@ SIGNATURES = {
     "seir_prepare_theta": (c_int, [c_void_p, c_void_p, c_int, c_void_p]),
     "seir_update_step": (c_int, [c_void_p, c_void_p, c_int, c_void_p, c_void_p, c_void_p, c_void_p, c_void_p, c_void_p, c_void_p]),
     "seir_hmc_step": (c_int, [c_void_p, c_void_p, c_void_p, c_void_p, c_void_p, c_void_p, c_int, c_void_p, c_void_p, c_void_p, c_void_p]),
+    "seir_hmc_draw": (c_int, [c_void_p, ctypes.c_uint64, ctypes.c_uint32, ctypes.c_uint32, c_void_p, c_void_p, c_void_p, c_void_p]),
     "seir_propose": (c_int, [c_void_p, c_void_p, ctypes.c_uint64, ctypes.c_uint32, ctypes.c_uint32, c_void_p, c_void_p, c_void_p]),
     "seir_mcmc_sweep": (c_int, [c_void_p, c_void_p, ctypes.c_uint32] + [c_void_p] * 10),
     "seir_export_events": (c_int, [c_void_p, c_void_p, c_void_p]),

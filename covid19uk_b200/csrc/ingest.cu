@@ -188,7 +188,8 @@ int seir_launch_ingest(seir_chains* c, const double* d_events, cudaStream_t s) {
   // one memset over the contiguous integer-statistics block [Yir | Rir | sumYei | sumEres | flags]
   SEIR_CUDA(cudaMemsetAsync(c->d_Yir, 0, c->stats_bytes, s));
   SEIR_CUDA(cudaMemsetAsync(c->d_llc_adj, 0, sizeof(double) * (size_t)B, s));
-  (void)B;
+  // new events = freshly bootstrapped kernels: no proposal has been accepted yet (MetropolisHastings accepted_results)
+  SEIR_CUDA(cudaMemsetAsync(c->d_last_acc, 0, sizeof(int) * (size_t)4 * B * 4 * SEIR_MMAX, s));
   return (T <= 96) ? launch_ingest_tc<96>(c, d_events, s) : launch_ingest_tc<128>(c, d_events, s);
 }
 

@@ -358,6 +358,13 @@ int seir_hmc_step(seir_chains* c, double* d_u, const double* d_momentum, const d
                          (cudaStream_t)stream);
 }
 
+int seir_hmc_draw(seir_chains* c, uint64_t seed, uint32_t chain_offset, uint32_t sweep_index, const double* d_inv_mass,
+                  double* d_momentum, double* d_log_u, void* stream) {
+  if (!c || !d_momentum || !d_log_u) return seir_set_error(SEIR_ERR_BAD_ARG, "seir_hmc_draw: NULL argument");
+  SEIR_TRY(seir_launch_hmc_momentum(c, seed, chain_offset, sweep_index, d_inv_mass, d_momentum, (cudaStream_t)stream));
+  return seir_launch_log_uniform(c->B, seed, chain_offset, sweep_index, 0x48u, d_log_u, (cudaStream_t)stream);
+}
+
 int seir_propose(seir_chains* c, const seir_update_spec* spec, uint64_t seed, uint32_t chain_offset, uint32_t counter,
                  int32_t* d_proposal, double* d_log_u, void* stream) {
   if (!c || !spec || !d_proposal || !d_log_u) return seir_set_error(SEIR_ERR_BAD_ARG, "seir_propose: NULL argument");

@@ -91,6 +91,7 @@ class SeirEngine:
         self._model = handle
         self._chains: dict[int, c_void_p] = {}
         self.initial_state = init
+        self.chain_offset = 0  # global id of this rank's first chain (multi-GPU: set by the launcher)
 
     # ---- lifetime ----
     def close(self):
@@ -223,6 +224,18 @@ class SeirEngine:
             c_void_p(im.data_ptr()) if im is not None else c_void_p(0), int(num_leapfrog_steps), c_void_p(tlp.data_ptr()),
             c_void_p(acc.data_ptr()), c_void_p(dbg.data_ptr()) if dbg is not None else c_void_p(0), self._stream()))
         return tlp, acc, dbg
+
+    def hmc_draw(self, B, seed, chain_offset, sweep_index, inv_mass=None):
+        """Momentum [B,P] ~ N(0, diag(1/inv_mass)) and log u [B] from the Philox streams of the fused sweep."""
+        mom = torch.empty((B, self.P), dtype=torch.float64, device=self.device)
+        lu = torch.empty((B,), dtype=torch.float64, device=self.device)
+        im = None
+        if inv_mass is not None:
+            im = torch.as_tensor(inv_mass, dtype=torch.float64, device=self.device).expand(B, self.P).contiguous()
+        nat.check(self.lib.seir_hmc_draw(self.chains(B), int(seed), int(chain_offset), int(sweep_index),
+                                         c_void_p(im.data_ptr()) if im is not None else c_void_p(0),
+                                         c_void_p(mom.data_ptr()), c_void_p(lu.data_ptr()), self._stream()))
+        return mom, lu
 
     # ---- device-side proposals and the fused sweep (a8) ----
     def propose(self, spec: "nat.SeirUpdateSpec", B, seed, chain_offset, counter):

@@ -1,0 +1,265 @@
+"""MCMC driver with the structure of ``covid19uk/inference/inference.py``: windowed adaptation
+(fast 200, slow 25*2^k for k<6, fast 50), then bursts of fixed-kernel sampling streamed to the posterior file.
+
+    python -m covid19uk_b200.inference.inference -c config.yaml -o posterior.h5 data.npz [--chains B]
+
+Differences from the reference that a user must know about:
+  * a leading chain axis: B independent chains run in lock-step on the device (B = 1 reproduces the reference
+    shapes with one extra axis of length 1 after the draw axis);
+  * the data file is an ``.npz`` with the arrays of the reference's NetCDF groups (``C, W, N, adjacency, weekday,
+    area, cases`` [+ ``time``]); NetCDF is read when ``xarray`` is importable (it is not in this image);
+  * seeds name positions in counter-based Philox streams (the reference is unseeded, inference.py:68,134,205).
+"""
+from __future__ import annotations
+
+import sys
+
+import numpy as np
+import torch
+
+from .. import model_spec
+from .. import tfp_mcmc as tm
+from ..gemlib.mcmc import GibbsKernel, Posterior
+from ..gemlib.util import compute_state
+from .mcmc_kernel_factory import (make_event_multiscan_gibbs_step, make_hmc_base_kernel, make_hmc_fast_adapt_kernel,
+                                  make_hmc_slow_adapt_kernel)
+from .sampler import constrain, unconstrain
+
+DTYPE = model_spec.DTYPE
+get_weighted_running_variance = tm.get_weighted_running_variance  # inference.py:36-47
+
+
+def _get_window_sizes(num_adaptation_steps):
+    """inference.py:50-56 (unused by the reference's run_mcmc, kept for API parity)."""
+    slow = num_adaptation_steps // 21
+    first = 3 * slow
+    return first, slow, num_adaptation_steps - 15 * slow - first
+
+
+class ParamBijector:
+    """``tfb.Invert(tfb.Blockwise([Softplus(low=eps), Identity, ...]))`` of inference.py:525-535: ``forward``
+    unconstrains, ``inverse`` constrains (softplus + eps on psi and sigma_space)."""
+
+    @staticmethod
+    def inverse(u):
+        return constrain(u)
+
+    @staticmethod
+    def forward(theta):
+        return unconstrain(theta)
+
+    @staticmethod
+    def inverse_log_det_jacobian(u, event_ndims=1):
+        return torch.nn.functional.logsigmoid(u[..., :2]).sum(dim=-1)
+
+
+def _window(kernel_list, name, num_draws, joint_log_prob_fn, initial_position, trace_fn, seed):
+    kernel = GibbsKernel(target_log_prob_fn=joint_log_prob_fn, kernel_list=kernel_list, name=name)
+    state = kernel.normalise_state(initial_position)
+    pkr = kernel.bootstrap_results(state)
+    return tm.sample_chain(num_draws, current_state=state, kernel=kernel, previous_kernel_results=pkr,
+                           return_final_kernel_results=True, trace_fn=trace_fn, seed=seed)
+
+
+def _fast_adapt_window(num_draws, joint_log_prob_fn, initial_position, hmc_kernel_kwargs, dual_averaging_kwargs,
+                       event_kernel_kwargs, trace_fn=None, seed=None):
+    """inference.py:59-121: dual-averaging step-size adaptation around HMC + the event scans.
+    Returns draws, trace, the adapted step size and the variance accumulator of the window."""
+    kernel_list = [(0, make_hmc_fast_adapt_kernel(hmc_kernel_kwargs=hmc_kernel_kwargs, dual_averaging_kwargs=dual_averaging_kwargs)),
+                   (1, make_event_multiscan_gibbs_step(**event_kernel_kwargs))]
+    draws, trace, fkr = _window(kernel_list, "fast_adapt", num_draws, joint_log_prob_fn, initial_position, trace_fn, seed)
+    step_size = tm.unnest.get_outermost(fkr.inner_results[0], "step_size")
+    return draws, trace, step_size, get_weighted_running_variance(draws[0])
+
+
+def _slow_adapt_window(num_draws, joint_log_prob_fn, initial_position, initial_running_variance, hmc_kernel_kwargs,
+                       dual_averaging_kwargs, event_kernel_kwargs, trace_fn=None, seed=None):
+    """inference.py:124-196: step size and diagonal mass matrix adapted together."""
+    kernel_list = [(0, make_hmc_slow_adapt_kernel(initial_running_variance, hmc_kernel_kwargs, dual_averaging_kwargs)),
+                   (1, make_event_multiscan_gibbs_step(**event_kernel_kwargs))]
+    draws, trace, fkr = _window(kernel_list, "slow_adapt", num_draws, joint_log_prob_fn, initial_position, trace_fn, seed)
+    step_size = tm.unnest.get_outermost(fkr.inner_results[0], "step_size")
+    momentum_distribution = tm.unnest.get_outermost(fkr.inner_results[0], "momentum_distribution")
+    return draws, trace, step_size, get_weighted_running_variance(draws[0]), momentum_distribution
+
+
+def make_fixed_window_sampler(num_draws, joint_log_prob_fn, hmc_kernel_kwargs, event_kernel_kwargs, trace_fn=None, seed=None,
+                              jit_compile=False):
+    """inference.py:199-242: fixed step size and mass matrix.  Returns ``(sample_fn, kernel)``."""
+    kernel_list = [(0, make_hmc_base_kernel(**hmc_kernel_kwargs)), (1, make_event_multiscan_gibbs_step(**event_kernel_kwargs))]
+    kernel = GibbsKernel(target_log_prob_fn=joint_log_prob_fn, kernel_list=kernel_list, name="fixed")
+
+    def sample_fn(current_state, previous_kernel_results=None):
+        return tm.sample_chain(num_draws, current_state=current_state, kernel=kernel, return_final_kernel_results=True,
+                               previous_kernel_results=previous_kernel_results, trace_fn=trace_fn, seed=seed)
+
+    return sample_fn, kernel
+
+
+def trace_results_fn(_, results):
+    """inference.py:245-282: the dictionary written under ``results/`` (chain axis leading every entry)."""
+    root = results.inner_results
+    out = {"hmc": {"is_accepted": tm.unnest.get_innermost(root[0], "is_accepted"),
+                   "target_log_prob": tm.unnest.get_innermost(root[0], "target_log_prob"),
+                   "step_size": tm.unnest.get_outermost(root[0], "step_size")}}
+
+    def move_results(r):
+        a = r.accepted_results
+        return {"is_accepted": r.is_accepted, "target_log_prob": a.target_log_prob,
+                "proposed_delta": torch.stack([a.m, a.t, a.delta_t, a.x_star], dim=-2)}
+
+    scans = root[1].inner_results
+    for key, r in zip(("move/S->E", "move/E->I", "occult/S->E", "occult/E->I"), scans):
+        out[key] = move_results(r)
+    return out
+
+
+def draws_to_dict(draws):
+    """inference.py:285-301 with the chain axis: draws[0] [n,B,P], draws[1] [n,B,M,T,3]."""
+    theta, events = draws
+    M, T = events.shape[-3], events.shape[-2]
+    a = 6 + T - 1
+    return {"psi": theta[..., 0], "sigma_space": theta[..., 1], "beta_area": theta[..., 2], "gamma0": theta[..., 3],
+            "gamma1": theta[..., 4], "alpha_0": theta[..., 5], "alpha_t": theta[..., 6:a], "spatial_effect": theta[..., a:a + M],
+            "seir": events}
+
+
+def run_mcmc(joint_log_prob_fn, current_state, param_bijector, initial_conditions, config, output_file):
+    """inference.py:304-470.  Window sizes are the reference's (200 / 25 x 6 doublings / 50) unless the config
+    overrides them (``first_window_size``, ``slow_window_size``, ``num_slow_windows``, ``last_window_size``)."""
+    first_window_size = int(config.get("first_window_size", 200))
+    last_window_size = int(config.get("last_window_size", 50))
+    slow_window_size = int(config.get("slow_window_size", 25))
+    num_slow_windows = int(config.get("num_slow_windows", 6))
+    warmup_size = first_window_size + slow_window_size * (2 ** num_slow_windows - 1) + last_window_size
+    seed_base = int(config.get("seed", 0))
+
+    hmc_kernel_kwargs = {"step_size": float(config.get("initial_step_size", 0.1)), "num_leapfrog_steps": 16,
+                         "momentum_distribution": None, "store_parameters_in_results": True}
+    dual_averaging_kwargs = {"target_accept_prob": 0.75}
+    T = current_state[1].shape[-2]
+    event_kernel_kwargs = {"initial_state": initial_conditions, "t_range": [T - 21, T], "config": config}
+
+    def write(posterior, draws, trace, offset):
+        draws = [param_bijector.inverse(draws[0]), draws[1]]
+        posterior.write_samples(draws_to_dict(draws), first_dim_offset=offset)
+        posterior.write_results(trace, first_dim_offset=offset)
+
+    print("Initialising output...", end="", flush=True, file=sys.stderr)
+    probe, _ = make_fixed_window_sampler(1, joint_log_prob_fn, hmc_kernel_kwargs, event_kernel_kwargs, trace_fn=trace_results_fn,
+                                         seed=tm.SeedPath(seed_base, 0))
+    draws, trace, _ = probe(current_state)
+    posterior = Posterior(output_file, sample_dict=draws_to_dict(draws), results_dict=trace,
+                          num_samples=warmup_size + config["num_burst_samples"] * config["num_bursts"])
+    offset = 0
+    print("Done", flush=True, file=sys.stderr)  # (like the reference, the probe sweep does not advance the chain)
+
+    print(f"Fast window {first_window_size}", file=sys.stderr, flush=True)
+    dual_averaging_kwargs["num_adaptation_steps"] = first_window_size
+    draws, trace, step_size, running_variance = _fast_adapt_window(
+        first_window_size, joint_log_prob_fn, current_state, hmc_kernel_kwargs, dual_averaging_kwargs, event_kernel_kwargs,
+        trace_fn=trace_results_fn, seed=tm.SeedPath(seed_base, 1 + offset))
+    current_state = [s[-1] for s in draws]
+    write(posterior, draws, trace, offset)
+    offset += first_window_size
+
+    hmc_kernel_kwargs["step_size"] = step_size
+    for k in range(num_slow_windows):
+        n = slow_window_size * 2 ** k
+        dual_averaging_kwargs["num_adaptation_steps"] = n
+        print(f"Slow window {n}", file=sys.stderr, flush=True)
+        draws, trace, step_size, running_variance, momentum_distribution = _slow_adapt_window(
+            n, joint_log_prob_fn, current_state, running_variance, hmc_kernel_kwargs, dual_averaging_kwargs, event_kernel_kwargs,
+            trace_fn=trace_results_fn, seed=tm.SeedPath(seed_base, 1 + offset))
+        hmc_kernel_kwargs["step_size"] = step_size
+        hmc_kernel_kwargs["momentum_distribution"] = momentum_distribution
+        current_state = [s[-1] for s in draws]
+        write(posterior, draws, trace, offset)
+        offset += n
+
+    print(f"Fast window {last_window_size}", file=sys.stderr, flush=True)
+    dual_averaging_kwargs["num_adaptation_steps"] = last_window_size
+    draws, trace, step_size, _ = _fast_adapt_window(
+        last_window_size, joint_log_prob_fn, current_state, hmc_kernel_kwargs, dual_averaging_kwargs, event_kernel_kwargs,
+        trace_fn=trace_results_fn, seed=tm.SeedPath(seed_base, 1 + offset))
+    current_state = [s[-1] for s in draws]
+    write(posterior, draws, trace, offset)
+    offset += last_window_size
+
+    print("Sampling...", file=sys.stderr, flush=True)
+    # per chain: mean step size over the last half of the final adaptation window (inference.py:437-439)
+    hmc_kernel_kwargs["step_size"] = trace["hmc"]["step_size"][-(last_window_size // 2):].mean(dim=0)
+    fixed_sample, kernel = make_fixed_window_sampler(
+        config["num_burst_samples"], joint_log_prob_fn, hmc_kernel_kwargs, event_kernel_kwargs, trace_fn=trace_results_fn,
+        seed=tm.SeedPath(seed_base, 1 + offset), jit_compile=True)
+    pkr = kernel.bootstrap_results(kernel.normalise_state(current_state))
+    for _ in range(config["num_bursts"]):
+        draws, trace, pkr = fixed_sample(current_state, pkr)
+        current_state = [s[-1] for s in draws]
+        write(posterior, draws, trace, offset)
+        offset += config["num_burst_samples"]
+    return posterior
+
+
+# ---- data ---------------------------------------------------------------------------------------------
+def load_data(data_file):
+    """The reference reads NetCDF groups ``constant_data`` / ``observations`` with xarray (inference.py:481-485)."""
+    if str(data_file).endswith(".npz"):
+        z = np.load(data_file, allow_pickle=False)
+        data = {k: z[k] for k in ("C", "W", "N", "adjacency", "weekday", "area")}
+        time = z["time"] if "time" in z.files else np.arange(z["cases"].shape[1]).astype(str)
+        return data, z["cases"].astype(DTYPE), time
+    import xarray  # not in this image; kept for drop-in use where it exists
+
+    data = xarray.open_dataset(data_file, group="constant_data")
+    cases = xarray.open_dataset(data_file, group="observations")["cases"].astype(DTYPE)
+    return {k: np.asarray(data[k]) for k in ("C", "W", "N", "adjacency", "weekday", "area")}, np.asarray(cases), np.asarray(cases.coords["time"])
+
+
+def mcmc(data_file, output_file, config, use_autograph=False, use_xla=True, num_chains=1, device=None):
+    """inference.py:473-609: impute the censored events, fix the initial state, build the model and run."""
+    data, cases, dates = load_data(data_file)
+    # the last week of data repeated three more times gives a better occult initialisation (inference.py:487-491)
+    cases = np.concatenate([cases, np.tile(cases[:, -7:], (1, 3))], axis=-1)
+    events = model_spec.impute_censored_events(cases, seed=int(config.get("seed", 0)))
+    padded_init = np.concatenate([np.asarray(data["N"], DTYPE)[:, None], np.zeros_like(events[:, 0, :])], axis=-1)
+    state = compute_state(initial_state=padded_init, events=events, stoichiometry=model_spec.STOICHIOMETRY).cpu().numpy()
+    start_time = state.shape[1] - cases.shape[1]
+    initial_state = state[:, start_time, :]
+    events = events[:, start_time:-21, :]  # clip off the "extra" events
+    M, T = events.shape[0], events.shape[1]
+
+    model = model_spec.CovidUK(covariates=data, initial_state=initial_state, initial_step=0, num_steps=T, device=device)
+    joint_log_prob = model.joint_log_prob  # bijector + model.log_prob + ILDJ (inference.py:537-557), evaluated on the device
+
+    B = int(num_chains)
+    u0 = np.zeros((B, 5 + T + M), DTYPE)  # inference.py:563-574
+    events_b = np.broadcast_to(events, (B,) + events.shape).copy()
+    current_chain_state = [u0, events_b]
+    print("Initial logpi:", joint_log_prob(*current_chain_state).cpu().numpy(), flush=True)
+
+    posterior = run_mcmc(joint_log_prob_fn=joint_log_prob, current_state=current_chain_state, param_bijector=ParamBijector(),
+                         initial_conditions=initial_state, config=config, output_file=output_file)
+    posterior._file.create_dataset("initial_state", data=initial_state)
+    posterior._file.create_dataset("time", data=np.array(dates).astype(str).astype("S"))
+    for label, key in (("theta", "hmc"), ("move S->E", "move/S->E"), ("move E->I", "move/E->I"),
+                       ("occult S->E", "occult/S->E"), ("occult E->I", "occult/E->I")):
+        print(f"Acceptance {label}: {posterior[f'results/{key}/is_accepted'][:].mean()}")
+    posterior.close()
+    return output_file
+
+
+if __name__ == "__main__":
+    from argparse import ArgumentParser
+
+    import yaml
+
+    parser = ArgumentParser(description="Run MCMC inference algorithm")
+    parser.add_argument("-c", "--config", type=str, help="Config file", required=True)
+    parser.add_argument("-o", "--output", type=str, help="Output file", required=True)
+    parser.add_argument("--chains", type=int, default=1, help="independent chains run in lock-step on the device")
+    parser.add_argument("data_file", type=str, help="Data file (.npz; NetCDF where xarray exists)")
+    args = parser.parse_args()
+    with open(args.config, "r") as f:
+        config = yaml.load(f, Loader=yaml.FullLoader)
+    mcmc(args.data_file, args.output, config["Mcmc"], num_chains=args.chains)

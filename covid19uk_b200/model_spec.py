@@ -76,8 +76,24 @@ class CovidUKModel:
 
     def joint_log_prob(self, unconstrained_params, events):
         """The hot closure of inference.py:537-557 (bijector + model.log_prob + ILDJ)."""
+        if hasattr(events, "num_chains"):  # gemlib.mcmc.DeviceEvents: the events already live in the caches
+            return self.engine.log_prob_cached(unconstrained_params, nat.THETA_UNCONSTRAINED, nat.PART_JOINT)
         out = self.engine.log_prob(events, unconstrained_params, nat.THETA_UNCONSTRAINED, nat.PART_JOINT)
         return self._squeeze(out, events)
+
+
+def impute_censored_events(cases, seed=0):
+    """model_spec.py:108-126: impute censored S->E and E->I events from the I->R case matrix ``cases`` [M, T] by two
+    rounds of geometric back-distribution (rates 0.25 and 0.5, the reference's hard-coded lags).  Returns [M, T', 3]."""
+    from .util import impute_previous_cases
+
+    rng = np.random.default_rng(seed)
+    cases = np.asarray(cases, DTYPE)
+    ei_events, lag_ei = impute_previous_cases(cases, 0.25, rng=rng)
+    se_events, lag_se = impute_previous_cases(ei_events, 0.5, rng=rng)
+    ir_events = np.pad(cases, ((0, 0), (lag_ei + lag_se - 2, 0)))
+    ei_events = np.pad(ei_events, ((0, 0), (lag_se - 1, 0)))
+    return np.stack([se_events, ei_events, ir_events], axis=-1)
 
 
 def CovidUK(covariates, initial_state, initial_step, num_steps, device=None):

@@ -27,7 +27,7 @@
 extern "C" {
 #endif
 
-#define SEIR_B200_ABI_VERSION 3
+#define SEIR_B200_ABI_VERSION 4
 
 typedef enum seir_status {
   SEIR_OK = 0,
@@ -138,6 +138,12 @@ int seir_log_prob_grad_cached(seir_chains* chains, const double* d_theta, int th
 int seir_hmc_step(seir_chains* chains, double* d_u, const double* d_momentum, const double* d_log_u,
                   const double* d_step_size, const double* d_inv_mass, int num_leapfrog_steps, double* d_tlp,
                   int32_t* d_accept, double* d_dbg, void* stream);
+
+/* Draw what one HMC transition consumes, on the device, from the same Philox streams seir_mcmc_sweep uses
+ * (stream = seed + global chain id, position = sweep_index): d_momentum [B,P] ~ N(0, diag(1/inv_mass)) and
+ * d_log_u [B] = log U(0,1).  seir_hmc_draw + seir_hmc_step reproduces the HMC part of seir_mcmc_sweep bit for bit. */
+int seir_hmc_draw(seir_chains* chains, uint64_t seed, uint32_t chain_offset, uint32_t sweep_index,
+                  const double* d_inv_mass, double* d_momentum, double* d_log_u, void* stream);
 
 /* ---- a6/a7: discrete Metropolis-within-Gibbs updates of the censored events -------------------- */
 /* (prev, target, next) is gemlib's TransitionTopology (mcmc_kernel_factory.py:102-104); -1 = None. */
