@@ -29,8 +29,10 @@ __global__ void __launch_bounds__(UPD_THREADS) seir_update_prepare_kernel(
     const double* __restrict__ lgtab, const double* __restrict__ pa, const double* __restrict__ psiW,
     const double* __restrict__ pm_arr, const double* __restrict__ gam, seir_upd* __restrict__ upd) {
   __shared__ int s_pm[4], s_pd[4], s_pdy[4], s_npts, s_valid;
-  __shared__ int redi[UPD_THREADS / 32];
-  __shared__ double redd[UPD_THREADS / 32];
+  __shared__ int s_colvalid[SEIR_MMAX], s_r3[UPD_THREADS / 32][3];
+  __shared__ double s_qf[SEIR_MMAX], s_qr[SEIR_MMAX];
+  __shared__ double redd[UPD_THREADS / 32][2];
+  __shared__ int redn[UPD_THREADS / 32];
   const int b = blockIdx.x, tid = threadIdx.x;
   const size_t cb = (size_t)b * T * Mp;
   chain_view v{M, T, Mp, yse + cb, yei + cb, yir + cb, Sx + cb, Ex + cb, Ix + cb, init};
@@ -63,28 +65,40 @@ __global__ void __launch_bounds__(UPD_THREADS) seir_update_prepare_kernel(
   int valid = s_valid;
   const int npts = s_npts;
   double qf = 0.0, qr = 0.0;
+  const int lane = tid & 31, warp = tid >> 5;
 
-  if (valid && cfg.kind == 0) {
-    for (int k = 0; k < cfg.mmax; ++k) {
+  if (cfg.kind == 0) {
+    // warp k evaluates column k of the proposal on its own (warp-level reductions, no block barrier)
+    if (valid && warp < cfg.mmax) {
+      const int k = warp;
       const int m = pr[k], t = pr[SEIR_MMAX + k], d = pr[2 * SEIR_MMAX + k], x = pr[3 * SEIR_MMAX + k];
       int cnt = 0;
-      for (int s = tid; s < T; s += UPD_THREADS) cnt += yt[(size_t)s * Mp + m] > 0;
-      const int nnz = blk_reduce_add(cnt, redi);
+      for (int s = lane; s < T; s += 32) cnt += yt[(size_t)s * Mp + m] > 0;
+      const int nnz = __reduce_add_sync(0xffffffffu, cnt);
       const int ytt = yt[(size_t)t * Mp + m], ytd = yt[(size_t)(t + d) * Mp + m];
       const int lo = d > 0 ? t : t + d, hi = d > 0 ? t + d : t;
       const int hi_c = min(hi, lo + cfg.dmax);
       // forward: later move depletes the destination compartment (bounded via `next`), earlier move the source (via `prev`)
       const int cf = d > 0 ? target + 1 : target, cr = d > 0 ? target : target + 1;
       const bool have_f = d > 0 ? cfg.next >= 0 : cfg.prev >= 0, have_r = d > 0 ? cfg.prev >= 0 : cfg.next >= 0;
-      const int bf = have_f ? bound_abs_min(v, cf, m, lo, hi_c, false, target, s_pm, s_pd, s_pdy, npts, redi) : INT_MAX;
-      const int br = have_r ? bound_abs_min(v, cr, m, lo, hi_c, true, target, s_pm, s_pd, s_pdy, npts, redi) : INT_MAX;
-      const int maxf = clampi(min(bf, ytt), 0, cfg.nmax);
-      const int maxr = clampi(min(br, ytd + x), 0, cfg.nmax);
-      if (ytt <= 0 || nnz <= 0 || x > maxf) valid = 0;  // outside the forward proposal's support
-      const int nnz2 = nnz - ((x > 0 && ytt == x) ? 1 : 0) + ((x > 0 && ytd == 0) ? 1 : 0);
-      qf += -log((double)nnz) - log((double)maxf + 1.0);
-      qr += (x > maxr || nnz2 <= 0) ? -INFINITY : (-log((double)nnz2) - log((double)maxr + 1.0));
+      const int bf = have_f ? warp_bound_abs_min(v, cf, m, lo, hi_c, false, target, s_pm, s_pd, s_pdy, npts) : INT_MAX;
+      const int br = have_r ? warp_bound_abs_min(v, cr, m, lo, hi_c, true, target, s_pm, s_pd, s_pdy, npts) : INT_MAX;
+      if (lane == 0) {
+        const int maxf = clampi(min(bf, ytt), 0, cfg.nmax);
+        const int maxr = clampi(min(br, ytd + x), 0, cfg.nmax);
+        s_colvalid[k] = !(ytt <= 0 || nnz <= 0 || x > maxf);  // inside the forward proposal's support
+        const int nnz2 = nnz - ((x > 0 && ytt == x) ? 1 : 0) + ((x > 0 && ytd == 0) ? 1 : 0);
+        s_qf[k] = -log((double)max(nnz, 1)) - log((double)maxf + 1.0);
+        s_qr[k] = (x > maxr || nnz2 <= 0) ? -INFINITY : (-log((double)nnz2) - log((double)maxr + 1.0));
+      }
     }
+    __syncthreads();
+    if (valid)
+      for (int k = 0; k < cfg.mmax; ++k) {  // fixed order: the sums are bitwise reproducible
+        if (!s_colvalid[k]) valid = 0;
+        qf += s_qf[k];
+        qr += s_qr[k];
+      }
   } else if (valid) {
     const int m = pr[0], t = pr[SEIR_MMAX], sg = pr[2 * SEIR_MMAX], x = pr[3 * SEIR_MMAX];
     const int t1 = min(cfg.t1, T);
@@ -100,15 +114,27 @@ __global__ void __launch_bounds__(UPD_THREADS) seir_update_prepare_kernel(
       if (mm == m && sg > 0 && x > 0) any = 1;
       hm += any;
     }
-    const int hotm = blk_reduce_add(hm, redi);
     int hd = 0;
     for (int s = cfg.t0 + tid; s < t1; s += UPD_THREADS) {
       int y = yt[(size_t)s * Mp + m];
       if (s == t && sg > 0) y += x;
       hd += y > 0;
     }
-    const int hotd = blk_reduce_add(hd, redi);
-    const int bound = cfg.next >= 0 ? bound_level_min(v, target + 1, m, t, T, sg > 0, target, s_pm, s_pd, s_pdy, npts, redi) : INT_MAX;
+    int bnd = INT_MAX;
+    if (cfg.next >= 0)
+      for (int s = t + tid; s < T; s += UPD_THREADS) {
+        int xs = after_state(v, target + 1, m, s);
+        if (sg > 0) xs += dcum_le(s_pm, s_pd, s_pdy, npts, m, s);
+        bnd = min(bnd, xs);
+      }
+    // one combined block reduction of (hot metapopulations, hot days, bound)
+    hm = __reduce_add_sync(0xffffffffu, hm);
+    hd = __reduce_add_sync(0xffffffffu, hd);
+    bnd = __reduce_min_sync(0xffffffffu, bnd);
+    if (lane == 0) { s_r3[warp][0] = hm; s_r3[warp][1] = hd; s_r3[warp][2] = bnd; }
+    __syncthreads();
+    int hotm = 0, hotd = 0, bound = INT_MAX;
+    for (int w = 0; w < UPD_THREADS / 32; ++w) { hotm += s_r3[w][0]; hotd += s_r3[w][1]; bound = min(bound, s_r3[w][2]); }
     const int maxd = clampi(min(ymt_del, bound), 0, cfg.nmax);
     const double q_del = (ymt_del <= 0 || hotm <= 0 || hotd <= 0 || x > maxd)
                              ? -INFINITY
@@ -155,9 +181,14 @@ __global__ void __launch_bounds__(UPD_THREADS) seir_update_prepare_kernel(
       }
     }
   }
-  dll = blk_reduce_addd(dll, redd);
-  dllc = blk_reduce_addd(dllc, redd);
-  neg = blk_reduce_add(neg, redi);
+  // one combined block reduction of (dll, dllc, neg), fixed order
+  dll = warp_sum(dll);
+  dllc = warp_sum(dllc);
+  neg = __reduce_or_sync(0xffffffffu, neg);
+  if (lane == 0) { redd[warp][0] = dll; redd[warp][1] = dllc; redn[warp] = neg; }
+  __syncthreads();
+  dll = 0.0; dllc = 0.0; neg = 0;
+  for (int w = 0; w < UPD_THREADS / 32; ++w) { dll += redd[w][0]; dllc += redd[w][1]; neg |= redn[w]; }
   if (tid == 0) {
     seir_upd u;
     u.valid = valid; u.neg = neg > 0; u.npts = valid ? npts : 0; u.accept = 0;

@@ -100,4 +100,50 @@ __device__ __forceinline__ int bound_level_min(const chain_view& v, int c, int m
   return blk_reduce_min(best, red);
 }
 
+// ---- single-warp variants (all 32 lanes of ONE warp call these; no block barrier) ----
+__device__ __forceinline__ int warp_bound_abs_min(const chain_view& v, int c, int m, int lo, int hi, bool proposed, int target,
+                                                  const int* pm, const int* pd, const int* pdy, int npts) {
+  const int init_c = v.init[m * 4 + c];
+  int best = INT_MAX;
+  for (int s = lo + (int)(threadIdx.x & 31); s < hi; s += 32) {
+    int x = after_state(v, c, m, s);
+    if (proposed) {
+      const int d = dcum_le(pm, pd, pdy, npts, m, s);
+      x += (c == target) ? -d : d;
+    }
+    const int dev = x - init_c;
+    best = min(best, init_c + (dev < 0 ? -dev : dev));
+  }
+  return __reduce_min_sync(0xffffffffu, best);
+}
+
+__device__ __forceinline__ int warp_bound_level_min(const chain_view& v, int c, int m, int lo, int hi, bool proposed, int target,
+                                                    const int* pm, const int* pd, const int* pdy, int npts) {
+  int best = INT_MAX;
+  for (int s = lo + (int)(threadIdx.x & 31); s < hi; s += 32) {
+    int x = after_state(v, c, m, s);
+    if (proposed) {
+      const int d = dcum_le(pm, pd, pdy, npts, m, s);
+      x += (c == target) ? -d : d;
+    }
+    best = min(best, x);
+  }
+  return __reduce_min_sync(0xffffffffu, best);
+}
+
+// index of the rank-th (0-based) element with pred true among i in [lo, hi), scanned 32 at a time by one warp;
+// -1 when there are not that many.  `pred(i)` is evaluated by lane (i - lo) % 32.
+template <typename Pred>
+__device__ __forceinline__ int warp_select_nth(int lo, int hi, int rank, Pred pred) {
+  const int lane = threadIdx.x & 31;
+  for (int base = lo; base < hi; base += 32) {
+    const int i = base + lane;
+    const unsigned bal = __ballot_sync(0xffffffffu, i < hi && pred(i));
+    const int c = __popc(bal);
+    if (rank < c) return base + (int)__fns(bal, 0, rank + 1);
+    rank -= c;
+  }
+  return -1;
+}
+
 __device__ __forceinline__ int clampi(int x, int lo, int hi) { return x < lo ? lo : (x > hi ? hi : x); }

@@ -239,111 +239,137 @@ int seir_launch_loglik(seir_chains* c, bool grad, cudaStream_t s) {
 }
 
 // ------------------------------------------------------------------------------------------------
-__global__ void __launch_bounds__(128) seir_finalize_kernel(
+// finalize: one CTA per chain.  Every sum is a thread-strided partial followed by ONE fixed-tree block reduction
+// of all partials at once (bitwise reproducible; no serial single-thread loops).  The alpha_t gradient is a suffix
+// sum over days: d/d alpha_t[k] = sum_{t : aidx[t] >= k} col[t] = suffix(col)[tfirst[k]] (aidx is non-decreasing).
+// ------------------------------------------------------------------------------------------------
+#define FIN_THREADS 128
+#define FIN_NACC 8
+
+__device__ __forceinline__ void block_sum_multi(double (&v)[FIN_NACC], int n, double (*red)[FIN_NACC]) {
+  const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+#pragma unroll
+  for (int i = 0; i < FIN_NACC; ++i)
+    if (i < n) v[i] = warp_sum(v[i]);
+  __syncthreads();
+  if (lane == 0)
+#pragma unroll
+    for (int i = 0; i < FIN_NACC; ++i) red[warp][i] = v[i];
+  __syncthreads();
+#pragma unroll
+  for (int i = 0; i < FIN_NACC; ++i) {
+    double r = 0.0;
+    if (i < n)
+      for (int w = 0; w < FIN_THREADS / 32; ++w) r += red[w][i];
+    v[i] = r;
+  }
+}
+
+__global__ void __launch_bounds__(FIN_THREADS) seir_finalize_kernel(
     int M, int T, int Mp, int P, int nblkLL, int nts, int nllc, double dt, double nu, double log_p_nu, int kind, int parts,
     const double* __restrict__ theta, const double* __restrict__ scal, const double* __restrict__ val_part,
     const double* __restrict__ llc_part, const double* __restrict__ llc_adj, const long long* __restrict__ Yir, const long long* __restrict__ Rir,
     const long long* __restrict__ sumYei, const long long* __restrict__ sumEres, const int* __restrict__ flags,
-    const double* __restrict__ gam, const double* __restrict__ logpir, const double* __restrict__ wk, const int* __restrict__ aidx,
+    const double* __restrict__ gam, const double* __restrict__ logpir, const double* __restrict__ wk, const int* __restrict__ tfirst,
     const double* __restrict__ la, const double* __restrict__ psi_part, const double* __restrict__ col_part,
     const double* __restrict__ rowsum, const int* __restrict__ car_indptr, const int* __restrict__ car_indices,
     const double* __restrict__ car_values, double* __restrict__ out, double* __restrict__ grad) {
-  extern __shared__ double sm[];  // [T] column sums, [T] bucket
-  __shared__ double red[32];
+  extern __shared__ double sm[];  // [T] column sums -> their suffix sums
+  __shared__ double red[FIN_THREADS / 32][FIN_NACC];
+  __shared__ double chunk_sum[FIN_THREADS];
   const int b = blockIdx.x, tid = threadIdx.x;
   const bool want_seir = parts & SEIR_PART_SEIR;
   const bool want_prior = parts & SEIR_PART_PRIORS;
+  const bool want_grad = grad != nullptr;
   const double* sc = scal + (size_t)b * SEIR_NSCAL;
+  const double* th = theta + (size_t)b * P;
+  const double* sp = th + 6 + (T - 1);
+  const double sigma = sc[SC_SIGMA];
+  double* g = want_grad ? grad + (size_t)b * P : nullptr;
+  const int nslot = nblkLL * nts;
 
-  // ---- value ----
-  double ir = 0.0;
-  if (want_seir)
-    for (int t = tid; t < T; t += blockDim.x) {
+  // acc: 0 I->R value, 1 S->E value partials, 2 coefficient partials, 3 psi partials, 4 beta, 5 sigma, 6 gamma0, 7 gamma1
+  double acc[FIN_NACC];
+#pragma unroll
+  for (int i = 0; i < FIN_NACC; ++i) acc[i] = 0.0;
+  if (want_seir) {
+    for (int t = tid; t < T; t += FIN_THREADS) {
       const double yv = (double)Yir[(size_t)b * T + t], rv = (double)Rir[(size_t)b * T + t];
-      const double g = gam[(size_t)b * T + t];
-      double term = -rv * g * dt;
+      const double gt = gam[(size_t)b * T + t];
+      double term = -rv * gt * dt;
       if (yv > 0.0) term += yv * logpir[(size_t)b * T + t];
-      ir += term;
+      acc[0] += term;
+      if (want_grad) {
+        double d = -rv;
+        if (yv > 0.0) d += yv / expm1(gt * dt);
+        d *= dt * gt;
+        acc[6] += d;
+        acc[7] += d * wk[t];
+      }
     }
-  const double ir_tot = block_sum(ir, red);
+    for (int k = tid; k < nslot; k += FIN_THREADS) {
+      acc[1] += val_part[(size_t)b * nslot + k];
+      if (want_grad) acc[3] += psi_part[(size_t)b * nslot + k];
+    }
+    for (int k = tid; k < nllc; k += FIN_THREADS) acc[2] += llc_part[(size_t)b * nllc + k];
+  }
+  if (want_grad) {
+    for (int m = tid; m < M; m += FIN_THREADS) {
+      double r = 0.0;
+      if (want_seir)
+        for (int z = 0; z < nts; ++z) r += rowsum[((size_t)b * nts + z) * Mp + m];
+      acc[4] += r * la[m];
+      acc[5] += r * sp[m];
+      double gm = sigma * r;
+      if (want_prior) {
+        double q = 0.0;
+        for (int e = car_indptr[m]; e < car_indptr[m + 1]; ++e) q += car_values[e] * sp[car_indices[e]];
+        gm -= q;
+      }
+      g[6 + (T - 1) + m] = gm;
+    }
+    for (int t = tid; t < T; t += FIN_THREADS) {
+      double s = 0.0;
+      if (want_seir)
+        for (int k = 0; k < nblkLL; ++k) s += col_part[((size_t)b * nblkLL + k) * T + t];
+      sm[t] = s;
+    }
+  }
+  block_sum_multi(acc, want_grad ? 8 : 3, red);  // (its barriers also publish sm[])
+
   if (tid == 0) {
     double v = sc[SC_PRIOR];
     if (want_seir) {
-      double s = 0.0;
-      for (int k = 0; k < nblkLL * nts; ++k) s += val_part[(size_t)b * nblkLL * nts + k];
-      double l = 0.0;
-      for (int k = 0; k < nllc; ++k) l += llc_part[(size_t)b * nllc + k];
-      l += llc_adj[b];
       const double yei = (double)sumYei[b], eres = (double)sumEres[b];
       double ei = -eres * nu * dt;
       if (yei > 0.0) ei += yei * log_p_nu;
-      v += s + l + ei + ir_tot;
+      v += acc[1] + (acc[2] + llc_adj[b]) + ei + acc[0];
       if (flags[b] != 0) v = -INFINITY;
     }
     out[b] = v;
   }
-  if (grad == nullptr) return;
+  if (!want_grad) return;
 
-  // ---- gradient ----
-  double* g = grad + (size_t)b * P;
-  const double* th = theta + (size_t)b * P;
-  const double* sp = th + 6 + (T - 1);
-  double* col = sm;
-  double* bucket = sm + T;
-  const double sigma = sc[SC_SIGMA];
-  for (int t = tid; t < T; t += blockDim.x) {
-    double s = 0.0;
-    if (want_seir)
-      for (int k = 0; k < nblkLL; ++k) s += col_part[((size_t)b * nblkLL + k) * T + t];
-    col[t] = s;
-    bucket[t] = 0.0;
+  // ---- suffix sums of the per-day column sums: each thread owns a contiguous chunk of days ----
+  const int chunk = (T + FIN_THREADS - 1) / FIN_THREADS;
+  const int c0 = min(T, tid * chunk), c1 = min(T, c0 + chunk);
+  double cs = 0.0;
+  for (int t = c1 - 1; t >= c0; --t) cs += sm[t];
+  chunk_sum[tid] = cs;
+  __syncthreads();
+  double tail = 0.0;  // sum of the chunks after mine, highest first
+  for (int j = FIN_THREADS - 1; j > tid; --j) tail += chunk_sum[j];
+  for (int t = c1 - 1; t >= c0; --t) {
+    tail += sm[t];
+    sm[t] = tail;
   }
   __syncthreads();
-  double gb = 0.0, gs = 0.0;
-  for (int m = tid; m < M; m += blockDim.x) {
-    double r = 0.0;
-    if (want_seir)
-      for (int z = 0; z < nts; ++z) r += rowsum[((size_t)b * nts + z) * Mp + m];
-    gb += r * la[m];
-    gs += r * sp[m];
-    double gm = sigma * r;
-    if (want_prior) {
-      double q = 0.0;
-      for (int e = car_indptr[m]; e < car_indptr[m + 1]; ++e) q += car_values[e] * sp[car_indices[e]];
-      gm -= q;
-    }
-    g[6 + (T - 1) + m] = gm;
+  for (int k = tid; k < T - 1; k += FIN_THREADS) {
+    const int tf = tfirst[k];
+    g[6 + k] = (tf < T ? sm[tf] : 0.0) - (want_prior ? th[6 + k] / (0.005 * 0.005) : 0.0);
   }
-  const double gbeta = block_sum(gb, red);
-  const double gsigma = block_sum(gs, red);
-  double g0 = 0.0, g1 = 0.0;
-  if (want_seir)
-    for (int t = tid; t < T; t += blockDim.x) {
-      const double yv = (double)Yir[(size_t)b * T + t], rv = (double)Rir[(size_t)b * T + t];
-      const double gt = gam[(size_t)b * T + t];
-      double d = -rv;
-      if (yv > 0.0) d += yv / expm1(gt * dt);
-      d *= dt * gt;
-      g0 += d;
-      g1 += d * wk[t];
-    }
-  const double gg0 = block_sum(g0, red);
-  const double gg1 = block_sum(g1, red);
   if (tid == 0) {
-    double a0 = 0.0;
-    for (int t = 0; t < T; ++t) {
-      a0 += col[t];
-      if (aidx[t] >= 0) bucket[aidx[t]] += col[t];
-    }
-    double run = 0.0;  // alpha_t[k] feeds every day whose cumsum index is >= k
-    for (int k = T - 2; k >= 0; --k) {
-      run += bucket[k];
-      g[6 + k] = run - (want_prior ? th[6 + k] / (0.005 * 0.005) : 0.0);
-    }
-    double gpsi = 0.0;
-    if (want_seir)
-      for (int k = 0; k < nblkLL * nts; ++k) gpsi += psi_part[(size_t)b * nblkLL * nts + k];
-    double gsg = gsigma, gbt = gbeta, gga0 = gg0, gga1 = gg1;
+    double gpsi = acc[3], gsg = acc[5], gbt = acc[4], gga0 = acc[6], gga1 = acc[7], a0 = sm[0];
     if (want_prior) {
       gpsi += 2.0 / sc[SC_PSI] - 10.0;
       gsg += -sigma / (0.1 * 0.1);
@@ -364,9 +390,9 @@ __global__ void __launch_bounds__(128) seir_finalize_kernel(
 int seir_launch_finalize(seir_chains* c, const double* d_theta, int kind, int parts, double* d_out, double* d_grad,
                          cudaStream_t s) {
   const seir_model* m = c->model;
-  seir_finalize_kernel<<<c->B, 128, sizeof(double) * 2 * m->T, s>>>(
+  seir_finalize_kernel<<<c->B, FIN_THREADS, sizeof(double) * m->T, s>>>(
       m->M, m->T, m->Mp, m->P, c->nblkLL, c->nts, c->nllc, m->dt, m->nu, m->log_p_nu, kind, parts, d_theta, c->d_scal, c->d_val_part,
-      c->d_llc_part, c->d_llc_adj, c->d_Yir, c->d_Rir, c->d_sumYei, c->d_sumEres, c->d_flags, c->d_gam, c->d_logpir, m->d_wk, m->d_aidx, m->d_la,
+      c->d_llc_part, c->d_llc_adj, c->d_Yir, c->d_Rir, c->d_sumYei, c->d_sumEres, c->d_flags, c->d_gam, c->d_logpir, m->d_wk, m->d_tfirst, m->d_la,
       c->d_psi_part, c->d_col_part, c->d_rowsum, m->d_car_indptr, m->d_car_indices, m->d_car_values, d_out, d_grad);
   seir_count_launch(1);
   return seir_cuda_check(cudaGetLastError(), "seir_finalize_kernel");

@@ -23,7 +23,6 @@ __global__ void __launch_bounds__(UPD_THREADS) seir_propose_kernel(int M, int T,
                                                                    int* __restrict__ prop, double* __restrict__ log_u) {
   extern __shared__ int cnt[];  // [Mp] days with target events per metapopulation (whole series or window)
   __shared__ int redi[UPD_THREADS / 32];
-  __shared__ int s_m[2], s_t[2], s_d[2], s_x[2], s_mode;
   const int b = blockIdx.x, tid = threadIdx.x;
   const size_t cb = (size_t)b * T * Mp;
   chain_view v{M, T, Mp, yse + cb, yei + cb, yir + cb, Sx + cb, Ex + cb, Ix + cb, init};
@@ -43,102 +42,74 @@ __global__ void __launch_bounds__(UPD_THREADS) seir_propose_kernel(int M, int T,
     hot += c > 0;
   }
   const int H = blk_reduce_add(hot, redi);  // (barriers inside also publish cnt[])
+  if (tid >= 32) return;                    // the rest is one warp: ballot-based rank selection, warp-level bounds
+  const int lane = tid;
+  auto pick_hot = [&](int rank, int skip) { return warp_select_nth(0, M, rank, [&](int m) { return cnt[m] > 0 && m != skip; }); };
+  auto pick_day = [&](int m, int rank) { return warp_select_nth(w0, w1, rank, [&](int s) { return yt[(size_t)s * Mp + m] > 0; }); };
 
-  auto pick_hot = [&](int rank, int skip) {  // rank-th metapopulation with cnt > 0, skipping `skip`
-    for (int m = 0; m < M; ++m)
-      if (cnt[m] > 0 && m != skip) {
-        if (rank == 0) return m;
-        --rank;
-      }
-    return -1;
-  };
-  auto pick_day = [&](int m, int rank) {  // rank-th day of the window with events in m
-    for (int s = w0; s < w1; ++s)
-      if (yt[(size_t)s * Mp + m] > 0) {
-        if (rank == 0) return s;
-        --rank;
-      }
-    return -1;
-  };
-
-  if (tid == 0) {
-    uint32_t r[4];
-    seir_philox(seed, chain, ctr, 0x55u, 0u, r);
-    log_u[b] = log(u01_from_bits(r[0], r[1]));
-    if (cfg.kind == 0) {
-      s_mode = (H >= cfg.mmax) ? 1 : 0;
-      int prev = -1;
-      for (int k = 0; k < cfg.mmax && s_mode; ++k) {
-        uint32_t q[4], q2[4];
-        seir_philox(seed, chain, ctr, 0x4Du, (uint32_t)k, q);
-        seir_philox(seed, chain, ctr, 0x54u, (uint32_t)k, q2);
-        const int m = pick_hot((int)rand_below(q[0], q[1], (uint32_t)(H - k)), prev);
-        const int t = pick_day(m, (int)rand_below(q[2], q[3], (uint32_t)cnt[m]));
-        const int mag = 1 + (int)rand_below(q2[0], q2[1], (uint32_t)cfg.dmax);
-        s_m[k] = m; s_t[k] = t; s_d[k] = (q2[2] & 1u) ? mag : -mag; s_x[k] = 0;
-        prev = m;
-      }
-    } else {
-      const bool coin = (r[2] & 1u) != 0;
-      uint32_t q[4];
-      seir_philox(seed, chain, ctr, 0x4Fu, 0u, q);
-      if (coin && H > 0) {
-        s_mode = 2;  // delete
-        const int m = pick_hot((int)rand_below(q[0], q[1], (uint32_t)H), -1);
-        s_m[0] = m; s_t[0] = pick_day(m, (int)rand_below(q[2], q[3], (uint32_t)cnt[m])); s_d[0] = -1; s_x[0] = 0;
-      } else {
-        s_mode = 3;  // add
-        uint32_t q2[4];
-        seir_philox(seed, chain, ctr, 0x41u, 0u, q2);
-        s_m[0] = (int)rand_below(q[0], q[1], (uint32_t)M);
-        s_t[0] = cfg.t0 + (int)rand_below(q[2], q[3], (uint32_t)(cfg.t1 - cfg.t0));
-        s_d[0] = 1;
-        s_x[0] = (int)rand_below(q2[0], q2[1], (uint32_t)cfg.nmax + 1u);
-      }
+  uint32_t r[4];
+  seir_philox(seed, chain, ctr, 0x55u, 0u, r);  // every lane computes the same stream position
+  if (lane == 0) log_u[b] = log(u01_from_bits(r[0], r[1]));
+  int pm_[2] = {0, 0}, pt_[2] = {0, 0}, pd_[2] = {0, 0}, px_[2] = {0, 0};
+  int cols = 0;
+  if (cfg.kind == 0) {
+    if (H < cfg.mmax) {  // fewer hot metapopulations than mmax: emit an invalid record (rejected by the update step)
+      if (lane == 0) pr[0] = -1;
+      return;
     }
-  }
-  __syncthreads();
-  const int mode = s_mode;
-  if (mode == 0) {  // fewer hot metapopulations than mmax: emit an invalid record (rejected by the update step)
-    if (tid == 0) pr[0] = -1;
-    return;
-  }
-  // x* needs the forward bound: a block-wide min over the affected days of the current state
-  if (mode == 1) {
+    int prev = -1;
     for (int k = 0; k < cfg.mmax; ++k) {
-      const int m = s_m[k], t = s_t[k], d = s_d[k];
+      uint32_t q[4], q2[4], q3[4];
+      seir_philox(seed, chain, ctr, 0x4Du, (uint32_t)k, q);
+      seir_philox(seed, chain, ctr, 0x54u, (uint32_t)k, q2);
+      seir_philox(seed, chain, ctr, 0x58u, (uint32_t)k, q3);
+      const int m = pick_hot((int)rand_below(q[0], q[1], (uint32_t)(H - k)), prev);
+      const int t = pick_day(m, (int)rand_below(q[2], q[3], (uint32_t)cnt[m]));
+      const int mag = 1 + (int)rand_below(q2[0], q2[1], (uint32_t)cfg.dmax);
+      const int d = (q2[2] & 1u) ? mag : -mag;
+      // x* needs the forward bound: a min over the affected days of the current state
       int maxf = 0;
       if (t + d >= 0 && t + d < T) {  // otherwise the whole proposal is rejected; keep x* = 0
         const int lo = d > 0 ? t : t + d, hi = d > 0 ? t + d : t, hi_c = min(hi, lo + cfg.dmax);
         const int cf = d > 0 ? target + 1 : target;
         const bool have = d > 0 ? cfg.next >= 0 : cfg.prev >= 0;
-        const int bf = have ? bound_abs_min(v, cf, m, lo, hi_c, false, target, nullptr, nullptr, nullptr, 0, redi) : INT_MAX;
+        const int bf = have ? warp_bound_abs_min(v, cf, m, lo, hi_c, false, target, nullptr, nullptr, nullptr, 0) : INT_MAX;
         maxf = clampi(min(bf, yt[(size_t)t * Mp + m]), 0, cfg.nmax);
       }
-      if (tid == 0) {
-        uint32_t q[4];
-        seir_philox(seed, chain, ctr, 0x58u, (uint32_t)k, q);
-        s_x[k] = (int)rand_below(q[0], q[1], (uint32_t)maxf + 1u);
-      }
+      pm_[k] = m; pt_[k] = t; pd_[k] = d; px_[k] = (int)rand_below(q3[0], q3[1], (uint32_t)maxf + 1u);
+      prev = m;
     }
-  } else if (mode == 2) {
-    const int m = s_m[0], t = s_t[0];
-    const int bound = cfg.next >= 0 ? bound_level_min(v, target + 1, m, t, T, false, target, nullptr, nullptr, nullptr, 0, redi) : INT_MAX;
-    const int maxd = clampi(min(yt[(size_t)t * Mp + m], bound), 0, cfg.nmax);
-    if (tid == 0) {
-      uint32_t q[4];
-      seir_philox(seed, chain, ctr, 0x58u, 0u, q);
-      s_x[0] = (int)rand_below(q[0], q[1], (uint32_t)maxd + 1u);
+    cols = cfg.mmax;
+  } else {
+    const bool coin = (r[2] & 1u) != 0;
+    uint32_t q[4];
+    seir_philox(seed, chain, ctr, 0x4Fu, 0u, q);
+    if (coin && H > 0) {  // delete
+      uint32_t q3[4];
+      seir_philox(seed, chain, ctr, 0x58u, 0u, q3);
+      const int m = pick_hot((int)rand_below(q[0], q[1], (uint32_t)H), -1);
+      const int t = pick_day(m, (int)rand_below(q[2], q[3], (uint32_t)cnt[m]));
+      const int bound = cfg.next >= 0 ? warp_bound_level_min(v, target + 1, m, t, T, false, target, nullptr, nullptr, nullptr, 0) : INT_MAX;
+      const int maxd = clampi(min(yt[(size_t)t * Mp + m], bound), 0, cfg.nmax);
+      pm_[0] = m; pt_[0] = t; pd_[0] = -1; px_[0] = (int)rand_below(q3[0], q3[1], (uint32_t)maxd + 1u);
+    } else {  // add
+      uint32_t q2[4];
+      seir_philox(seed, chain, ctr, 0x41u, 0u, q2);
+      pm_[0] = (int)rand_below(q[0], q[1], (uint32_t)M);
+      pt_[0] = cfg.t0 + (int)rand_below(q[2], q[3], (uint32_t)(cfg.t1 - cfg.t0));
+      pd_[0] = 1;
+      px_[0] = (int)rand_below(q2[0], q2[1], (uint32_t)cfg.nmax + 1u);
     }
+    cols = 1;
   }
-  __syncthreads();
-  const int cols = cfg.kind == 0 ? cfg.mmax : 1;
-  if (tid < cols) {
-    pr[tid] = s_m[tid];
-    pr[SEIR_MMAX + tid] = s_t[tid];
-    pr[2 * SEIR_MMAX + tid] = s_d[tid];
-    pr[3 * SEIR_MMAX + tid] = s_x[tid];
-  }
+  __syncwarp();  // the zero fill of pr[] by lanes 0..15 above precedes these stores
+  if (lane == 0)
+    for (int k = 0; k < cols; ++k) {
+      pr[k] = pm_[k];
+      pr[SEIR_MMAX + k] = pt_[k];
+      pr[2 * SEIR_MMAX + k] = pd_[k];
+      pr[3 * SEIR_MMAX + k] = px_[k];
+    }
 }
 
 int seir_launch_propose(seir_chains* c, const seir_update_cfg& cfg, unsigned long long seed, unsigned chain0, unsigned ctr,

@@ -119,6 +119,15 @@ int seir_model_create(const seir_spec* spec, int device, seir_model** out) {
     if (ai > T - 2) ai = T - 2;
     aidx[k] = (t == 0) ? -1 : (int)ai;
   }
+  std::vector<int> tfirst(T > 1 ? T - 1 : 1, T);
+  for (int k = 0; k < T - 1; ++k)
+    for (int t = 0; t < T; ++t)
+      if (aidx[t] >= k) { tfirst[k] = t; break; }
+  for (int t = 1; t < T; ++t)
+    if (aidx[t] < aidx[t - 1]) {
+      delete m;
+      return seir_set_error(SEIR_ERR_UNSUPPORTED, "seir_model_create: alpha_t index path must be non-decreasing in time");
+    }
   for (int k = 0; k < SEIR_LGTAB_BIG; ++k) lgtab[k] = lgamma((double)k + 1.0);
   std::vector<int> indptr(spec->car_indptr, spec->car_indptr + M + 1);
   std::vector<int> indices(spec->car_indices, spec->car_indices + spec->car_nnz);
@@ -126,7 +135,7 @@ int seir_model_create(const seir_spec* spec, int device, seir_model** out) {
 
   int rc = SEIR_OK;
   if ((rc = dev_upload(&m->d_cs, cstar)) || (rc = dev_upload(&m->d_rN, rN)) || (rc = dev_upload(&m->d_W, W)) ||
-      (rc = dev_upload(&m->d_wk, wk)) || (rc = dev_upload(&m->d_aidx, aidx)) || (rc = dev_upload(&m->d_la, la)) ||
+      (rc = dev_upload(&m->d_wk, wk)) || (rc = dev_upload(&m->d_aidx, aidx)) || (rc = dev_upload(&m->d_tfirst, tfirst)) || (rc = dev_upload(&m->d_la, la)) ||
       (rc = dev_upload(&m->d_init, init)) || (rc = dev_upload(&m->d_car_indptr, indptr)) ||
       (rc = dev_upload(&m->d_car_indices, indices)) || (rc = dev_upload(&m->d_car_values, values)) ||
       (rc = dev_upload(&m->d_lgtab, lgtab))) {
@@ -140,7 +149,7 @@ int seir_model_create(const seir_spec* spec, int device, seir_model** out) {
 void seir_model_destroy(seir_model* m) {
   if (!m) return;
   cudaSetDevice(m->device);
-  cudaFree(m->d_cs); cudaFree(m->d_rN); cudaFree(m->d_W); cudaFree(m->d_wk); cudaFree(m->d_aidx); cudaFree(m->d_la);
+  cudaFree(m->d_cs); cudaFree(m->d_rN); cudaFree(m->d_W); cudaFree(m->d_wk); cudaFree(m->d_aidx); cudaFree(m->d_tfirst); cudaFree(m->d_la);
   cudaFree(m->d_init); cudaFree(m->d_car_indptr); cudaFree(m->d_car_indices); cudaFree(m->d_car_values); cudaFree(m->d_lgtab);
   delete m;
 }

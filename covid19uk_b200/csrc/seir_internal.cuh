@@ -39,6 +39,7 @@ struct seir_model {
   double* d_W;         // [T] commute volume resolved per step (model_spec.py:234-235)
   double* d_wk;        // [T] centred weekday resolved per step (model_spec.py:237-240)
   int* d_aidx;         // [T] index into cumsum(alpha_t) or -1 for alpha_0 alone (model_spec.py:242-256)
+  int* d_tfirst;       // [T-1] first day whose cumsum index is >= k (aidx is non-decreasing), T if none
   double* d_la;        // [Mp] centred log area
   int* d_init;         // [Mp*4] initial state
   int* d_car_indptr;   // [M+1]

@@ -25,7 +25,7 @@ def main():
     ap.add_argument("--warmup", type=int, default=2)
     ap.add_argument("--M", type=int, default=382)
     ap.add_argument("--T", type=int, default=84)
-    ap.add_argument("--step-size", type=float, default=2e-4)
+    ap.add_argument("--step-size", type=float, default=2e-5)
     a = ap.parse_args()
     import torch
 
