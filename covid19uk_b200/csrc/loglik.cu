@@ -8,6 +8,8 @@
 //                          kernel, thread <-> metapopulation, loop over days.
 //  seir_finalize_kernel    fixed-order reduction of the partials, E->I / I->R sufficient-statistic
 //                          terms, priors; assembles the gradient.
+#include <stdlib.h>
+
 #include "seir_internal.cuh"
 
 #define HALF_LOG_2PI 0.9189385332046727
@@ -107,76 +109,156 @@ int seir_launch_theta_prep(seir_chains* c, const double* d_theta, int kind, int 
 //   lam = exp(a_t + beta la_m + sigma s_m) (I + psi W_t Bc) / N_m + eps        (model_spec.py:257-266)
 // Day-slab caches => for a fixed day the 32 lanes of a warp read 32 consecutive metapopulations.
 // grid = (metapopulation blocks, chains, day splits); the day split is chosen at launch so that the grid
-// fills the resident-CTA slots of the 148 SMs once.
+// fills the resident-CTA slots of the 148 SMs once.  A thread owns MPT metapopulations (m, m+128, ...):
+// MPT independent dependency chains per day, and the per-day column sums of the gradient are formed over
+// the thread's own cells before any shuffle.
 //
-// For x = lam*dt < 0.05 (always, for realistic infection hazards) the two transcendentals expm1+log are
-// replaced by one log plus even-power series (truncation < 1e-17):
-//   log(1-e^-x) = log x - x/2 + x^2/24 - x^4/2880 + x^6/181440
-//   1/expm1(x)  = 1/x - 1/2 + x/12 - x^3/720 + x^5/30240
+// The kernel is FP64-instruction bound, not HBM bound (ncu r01_v2: issue 64 %, DRAM 32 %), so the work per
+// cell is cut rather than the traffic:
+//   * for x = lam*dt < 0.05 (always, for realistic infection hazards) expm1+log become one log plus even-power
+//     series (truncation < 1e-17):  log(1-e^-x) = log x - x/2 + x^2/24 - x^4/2880 + x^6/181440
+//                                   1/expm1(x)  = 1/x - 1/2 + x/12 - x^3/720 + x^5/30240
+//   * log x and 1/x share one table-driven range reduction (128 entries in shared memory):
+//     x = 2^e m, c_i = centre of the mantissa bucket, r = m/c_i - 1 (|r| <= 2^-8, exact through an FMA with the
+//     rounded 1/c_i whose own log is tabulated), log x = e ln2 - log(1/c_i) + log1p(r) [degree 7],
+//     1/x = 2^-e (1/c_i) (1-r)(1+r^2)(1+r^4) [error r^8 = 2^-64]  -- ~17 FP64 operations instead of ~50;
+//   * the per-day column sums of 4 consecutive days are reduced across the warp together by a transposing
+//     butterfly (6 shuffles for 4 days instead of 20).
 // ------------------------------------------------------------------------------------------------
 #define LL_SMALL_X 0.05
+#define LL_UNROLL 4
 
-template <bool GRAD>
-__global__ void __launch_bounds__(SEIR_LL_THREADS, GRAD ? 10 : 16) seir_loglik_kernel(
+__device__ __forceinline__ double int_to_double_magic(int k) {  // exact int32 -> double with one FP64 add
+  return __hiloint2double(0x43300000, k ^ 0x80000000) - 4503601774854144.0;  // 2^52 + 2^31
+}
+
+// log(x) and (optionally) 1/x for a positive normal double; false => caller takes the library path
+template <bool RCP>
+__device__ __forceinline__ bool fast_log_rcp(double x, const double2* __restrict__ tab, double& lg, double& rc) {
+  const int hi = __double2hiint(x), lo = __double2loint(x);
+  if (hi < 0x00100000 || hi >= 0x7ff00000) return false;
+  const int e = (hi >> 20) - 1023;
+  const double m = __hiloint2double((hi & 0x000fffff) | 0x3ff00000, lo);
+  const double2 tc = tab[(hi >> 13) & 127];  // {1/c rounded, -log(1/c rounded)}
+  const double r = fma(m, tc.x, -1.0);
+  const double r2 = r * r;
+  double p = fma(r, 0.14285714285714285, -0.16666666666666666);
+  p = fma(r, p, 0.2);
+  p = fma(r, p, -0.25);
+  p = fma(r, p, 0.3333333333333333);
+  p = fma(r, p, -0.5);
+  lg = fma(int_to_double_magic(e), 0.6931471805599453, tc.y) + fma(r2, p, r);
+  if (RCP) {
+    const double r4 = r2 * r2;
+    const double q = ((1.0 - r) * (1.0 + r2)) * ((1.0 + r4) * tc.x);
+    rc = __hiloint2double(__double2hiint(q) - (e << 20), __double2loint(q));
+  }
+  return true;
+}
+
+// transposing butterfly: lanes hold a[0..3] (4 days); afterwards lane 8*j holds the warp total of a[j]
+__device__ __forceinline__ double warp_sum4_transposed(const double (&a)[4]) {
+  const int lane = threadIdx.x & 31;
+  const bool up16 = lane & 16, up8 = lane & 8;
+  double k0 = up16 ? a[2] : a[0], k1 = up16 ? a[3] : a[1];
+  const double s0 = up16 ? a[0] : a[2], s1 = up16 ? a[1] : a[3];
+  k0 += __shfl_xor_sync(0xffffffffu, s0, 16);
+  k1 += __shfl_xor_sync(0xffffffffu, s1, 16);
+  double c = up8 ? k1 : k0;
+  c += __shfl_xor_sync(0xffffffffu, up8 ? k0 : k1, 8);
+  c += __shfl_xor_sync(0xffffffffu, c, 4);
+  c += __shfl_xor_sync(0xffffffffu, c, 2);
+  c += __shfl_xor_sync(0xffffffffu, c, 1);
+  return c;  // day index of this lane's total: ((lane >> 4) & 1) * 2 + ((lane >> 3) & 1)
+}
+
+template <bool GRAD, int MPT>
+__global__ void __launch_bounds__(SEIR_LL_THREADS, GRAD ? 6 : 10) seir_loglik_kernel(
     int T, int Mp, int dps, double dt, double eps, const int* __restrict__ yse, const int* __restrict__ Sx,
     const int* __restrict__ Ix, const double* __restrict__ Bc, const double* __restrict__ pa, const double* __restrict__ psiW,
-    const double* __restrict__ W, const double* __restrict__ pm, double* __restrict__ val_part, double* __restrict__ psi_part,
-    double* __restrict__ col_part, double* __restrict__ rowsum_part) {
+    const double* __restrict__ W, const double* __restrict__ pm, const double2* __restrict__ logtab, double* __restrict__ val_part,
+    double* __restrict__ psi_part, double* __restrict__ col_part, double* __restrict__ rowsum_part) {
   extern __shared__ double sm[];
+  __shared__ double2 tab[128];
   double* pa_s = sm;             // [dps]
   double* pw_s = sm + dps;       // [dps]
   double* w_s = sm + 2 * dps;    // [dps]            (GRAD)
-  double* colw = sm + 3 * dps;   // [nwarps][dps]    (GRAD)
+  double* colw = sm + 3 * dps;   // [nwarps][dps+4]  (GRAD)
   __shared__ double red[32];
   const int b = blockIdx.y, tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
-  const int m = blockIdx.x * SEIR_LL_THREADS + tid;
-  const bool active = m < Mp;
+  const int m0 = blockIdx.x * (SEIR_LL_THREADS * MPT) + tid;
   const int tb = blockIdx.z * dps, nt = min(dps, T - tb);
+  const int cstride = dps + LL_UNROLL;
+  tab[tid] = logtab[tid];  // SEIR_LL_THREADS == 128 entries
   for (int t = tid; t < nt; t += SEIR_LL_THREADS) {
     pa_s[t] = pa[(size_t)b * T + tb + t];
     pw_s[t] = psiW[(size_t)b * T + tb + t];
     if (GRAD) w_s[t] = W[tb + t];
   }
   __syncthreads();
-  const double pm_m = active ? pm[(size_t)b * Mp + m] : 0.0;
-  const size_t base = ((size_t)b * T + tb) * Mp + (active ? m : 0);
-  double val = 0.0, row = 0.0, psig = 0.0;
-#pragma unroll 4
-  for (int t = 0; t < nt; ++t) {
-    const size_t o = base + (size_t)t * Mp;
-    int y = 0, S = 0, I = 0;
-    double bc = 0.0;
-    if (active) {
-      y = __ldg(yse + o);
-      S = __ldg(Sx + o);
-      I = __ldg(Ix + o);
-      bc = __ldg(Bc + o);
+  double pm_m[MPT], row[MPT];
+  bool act[MPT];
+#pragma unroll
+  for (int q = 0; q < MPT; ++q) {
+    const int m = m0 + q * SEIR_LL_THREADS;
+    act[q] = m < Mp;
+    pm_m[q] = act[q] ? pm[(size_t)b * Mp + m] : 0.0;
+    row[q] = 0.0;
+  }
+  const size_t base = ((size_t)b * T + tb) * Mp + m0;
+  double val = 0.0, psig = 0.0;
+  for (int t0 = 0; t0 < nt; t0 += LL_UNROLL) {
+    double colv[LL_UNROLL];
+#pragma unroll
+    for (int j = 0; j < LL_UNROLL; ++j) {
+      const int t = t0 + j;
+      colv[j] = 0.0;
+      if (t < nt) {
+        const double pat = pa_s[t], pwt = pw_s[t];
+#pragma unroll
+        for (int q = 0; q < MPT; ++q) {
+          const size_t o = base + (size_t)t * Mp + q * SEIR_LL_THREADS;
+          int y = 0, S = 0, I = 0;
+          double bc = 0.0;
+          if (act[q]) {
+            y = __ldg(yse + o);
+            S = __ldg(Sx + o);
+            I = __ldg(Ix + o);
+            bc = __ldg(Bc + o);
+          }
+          const double e = pat * pm_m[q];
+          const double X = (double)I + pwt * bc;
+          const double lam = fma(e, X, eps);
+          const double x = lam * dt;
+          const double yd = (double)y, rd = (double)(S - y);
+          double term = -rd * x;
+          double g = -rd;
+          double lg, rc;
+          if (x < LL_SMALL_X && fast_log_rcp<GRAD>(x, tab, lg, rc)) {
+            const double x2 = x * x;
+            if (y > 0) {
+              term += yd * (lg + fma(x2, fma(x2, fma(x2, 5.511463844797178e-06, -3.472222222222222e-04), 0.041666666666666664), -0.5 * x));
+              if (GRAD) g += yd * (rc - 0.5 + x * fma(x2, fma(x2, 3.306878306878307e-05, -1.388888888888889e-03), 0.08333333333333333));
+            }
+          } else {
+            const double em = expm1(-x);  // -(1-exp(-x)) = -p ; NaN log for x < 0 like the reference
+            if (y > 0) term += yd * log(-em);
+            if (GRAD && y > 0) g += yd * (1.0 + em) / (-em);
+          }
+          val += term;
+          if (GRAD) {
+            g *= dt;
+            const double h = g * (lam - eps);
+            row[q] += h;
+            psig += g * e * w_s[t] * bc;
+            colv[j] += h;
+          }
+        }
+      }
     }
-    const double e = pa_s[t] * pm_m;
-    const double X = (double)I + pw_s[t] * bc;
-    const double lam = fma(e, X, eps);
-    const double x = lam * dt;
-    const double yd = (double)y, rd = (double)(S - y);
-    double term = -rd * x;
-    double g = -rd;
-    if (x > 0.0 && x < LL_SMALL_X) {
-      const double x2 = x * x;
-      if (y > 0) term += yd * (log(x) + fma(x2, fma(x2, fma(x2, 5.511463844797178e-06, -3.472222222222222e-04), 0.041666666666666664), -0.5 * x));
-      if (GRAD && y > 0)
-        g += yd * (1.0 / x - 0.5 + x * fma(x2, fma(x2, 3.306878306878307e-05, -1.388888888888889e-03), 0.08333333333333333));
-    } else {
-      const double em = expm1(-x);  // -(1-exp(-x)) = -p ; NaN log for x < 0 like the reference
-      if (y > 0) term += yd * log(-em);
-      if (GRAD && y > 0) g += yd * (1.0 + em) / (-em);
-    }
-    val += term;
     if (GRAD) {
-      g *= dt;
-      const double h = g * (lam - eps);
-      row += h;
-      psig += g * e * w_s[t] * bc;
-      const double hs = warp_sum(h);
-      if (lane == 0) colw[warp * dps + t] = hs;
+      const double tot = warp_sum4_transposed(colv);
+      if ((lane & 7) == 0) colw[warp * cstride + t0 + ((lane >> 4) & 1) * 2 + ((lane >> 3) & 1)] = tot;
     }
   }
   const int slot = blockIdx.z * gridDim.x + blockIdx.x, nslot = gridDim.x * gridDim.z;
@@ -185,55 +267,301 @@ __global__ void __launch_bounds__(SEIR_LL_THREADS, GRAD ? 10 : 16) seir_loglik_k
   if (GRAD) {
     const double pg = block_sum(psig, red);
     if (tid == 0) psi_part[(size_t)b * nslot + slot] = pg;
-    if (active) rowsum_part[((size_t)b * gridDim.z + blockIdx.z) * Mp + m] = row;
+#pragma unroll
+    for (int q = 0; q < MPT; ++q)
+      if (act[q]) rowsum_part[((size_t)b * gridDim.z + blockIdx.z) * Mp + m0 + q * SEIR_LL_THREADS] = row[q];
     __syncthreads();
     for (int t = tid; t < nt; t += SEIR_LL_THREADS) {
       double cta = 0.0;
 #pragma unroll
-      for (int w = 0; w < SEIR_LL_THREADS / 32; ++w) cta += colw[w * dps + t];
+      for (int w = 0; w < SEIR_LL_THREADS / 32; ++w) cta += colw[w * cstride + t];
       col_part[((size_t)b * gridDim.x + blockIdx.x) * T + tb + t] = cta;
     }
   }
 }
 
-// day splits so that (metapopulation blocks x chains x splits) fills the resident CTA slots once
-static int choose_splits(const seir_chains* c, bool grad) {
-  static int slots[2] = {0, 0};
-  if (!slots[grad]) {
-    int dev = 0, sms = 148, per = 8;
-    cudaGetDevice(&dev);
-    cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev);
-    if (grad)
-      cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per, seir_loglik_kernel<true>, SEIR_LL_THREADS, 8 * 1024);
-    else
-      cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per, seir_loglik_kernel<false>, SEIR_LL_THREADS, 2 * 1024);
-    slots[grad] = sms * (per > 0 ? per : 1);
+// ------------------------------------------------------------------------------------------------
+// TMA-staged variant (used when the padded metapopulation count is a multiple of 128).
+// ncu on the direct-load kernel above (profiles/r01_v5_*): 64 % of the stall samples are long-scoreboard --
+// the 12 dependent global loads of a day are not far enough ahead of their use at 24 warps / SM.  Here one
+// elected thread streams whole day-slab segments (yse | S | I | Bc of MB metapopulations, MB*20 bytes per day)
+// into a shared-memory ring with 1-D bulk copies (cp.async.bulk -> SASS UBLKCP) that complete on an mbarrier;
+// a stage holds the 4 days of one column-sum butterfly group.  Bytes in flight no longer depend on occupancy or
+// registers, all shared-memory reads are lane-consecutive (conflict free), and the zero padding of the slabs makes
+// every cell valid (no per-cell predicates).
+// ------------------------------------------------------------------------------------------------
+#define LL_STAGE_DAYS LL_UNROLL
+
+__device__ __forceinline__ unsigned smem_u32(const void* p) { return (unsigned)__cvta_generic_to_shared(p); }
+__device__ __forceinline__ void mbar_init(uint64_t* bar, unsigned count) {
+  asm volatile("mbarrier.init.shared::cta.b64 [%0], %1;" ::"r"(smem_u32(bar)), "r"(count) : "memory");
+}
+__device__ __forceinline__ void mbar_expect_tx(uint64_t* bar, unsigned bytes) {
+  asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"(smem_u32(bar)), "r"(bytes) : "memory");
+}
+__device__ __forceinline__ void bulk_load_1d(void* dst, const void* src, unsigned bytes, uint64_t* bar) {
+  asm volatile("cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1], %2, [%3];" ::"r"(smem_u32(dst)),
+               "l"(src), "r"(bytes), "r"(smem_u32(bar))
+               : "memory");
+}
+__device__ __forceinline__ void mbar_wait(uint64_t* bar, unsigned parity) {
+  unsigned done = 0;
+  for (unsigned spins = 0; !done; ++spins) {
+    asm volatile(
+        "{\n\t.reg .pred p;\n\tmbarrier.try_wait.parity.shared::cta.b64 p, [%1], %2;\n\tselp.u32 %0, 1, 0, p;\n\t}"
+        : "=r"(done)
+        : "r"(smem_u32(bar)), "r"(parity)
+        : "memory");
+    if (spins > (1u << 24)) __trap();  // a copy that never lands must fail loudly, not hang the device
   }
+}
+
+template <bool GRAD, int MPT, int NSTAGE, int NTHR>
+__global__ void __launch_bounds__(NTHR, NTHR >= 384 ? (GRAD ? 2 : 3) : 1) seir_loglik_tma_kernel(
+    int T, int Mp, int dps, double dt, double eps, const int* __restrict__ yse, const int* __restrict__ Sx,
+    const int* __restrict__ Ix, const double* __restrict__ Bc, const double* __restrict__ pa, const double* __restrict__ psiW,
+    const double* __restrict__ W, const double* __restrict__ pm, const double2* __restrict__ logtab, double* __restrict__ val_part,
+    double* __restrict__ psi_part, double* __restrict__ col_part, double* __restrict__ rowsum_part) {
+  constexpr int MB = NTHR * MPT;  // metapopulations per CTA
+  constexpr int DAY_BYTES = MB * 20;         // yse | S | I (int32) | Bc (f64)
+  constexpr int STAGE_BYTES = DAY_BYTES * LL_STAGE_DAYS;
+  extern __shared__ __align__(128) unsigned char smraw[];
+  __shared__ uint64_t full[NSTAGE];
+  __shared__ double2 tab[128];
+  __shared__ double red[32];
+  double* sm = reinterpret_cast<double*>(smraw + (size_t)NSTAGE * STAGE_BYTES);
+  double* pa_s = sm;             // [dps]
+  double* pw_s = sm + dps;       // [dps]
+  double* w_s = sm + 2 * dps;    // [dps]            (GRAD)
+  double* colw = sm + 3 * dps;   // [nwarps][dps+4]  (GRAD)
+  const int b = blockIdx.y, tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
+  const int mb0 = blockIdx.x * MB;
+  const int tb = blockIdx.z * dps, nt = min(dps, T - tb);
+  const int ngroups = (nt + LL_STAGE_DAYS - 1) / LL_STAGE_DAYS;
+  const int cstride = dps + LL_UNROLL;
+
+  auto issue = [&](int g, int st) {  // elected thread: arm the barrier, then 4 bulk copies per day of the group
+    const int days = min(LL_STAGE_DAYS, nt - g * LL_STAGE_DAYS);
+    mbar_expect_tx(&full[st], (unsigned)(days * DAY_BYTES));
+    for (int d = 0; d < days; ++d) {
+      const size_t o = ((size_t)b * T + tb + g * LL_STAGE_DAYS + d) * Mp + mb0;
+      unsigned char* dst = smraw + (size_t)st * STAGE_BYTES + (size_t)d * DAY_BYTES;
+      bulk_load_1d(dst, yse + o, MB * 4, &full[st]);
+      bulk_load_1d(dst + MB * 4, Sx + o, MB * 4, &full[st]);
+      bulk_load_1d(dst + MB * 8, Ix + o, MB * 4, &full[st]);
+      bulk_load_1d(dst + MB * 12, Bc + o, MB * 8, &full[st]);
+    }
+  };
+  if (tid == 0) {
+    for (int st = 0; st < NSTAGE; ++st) mbar_init(&full[st], 1);
+    asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+    for (int g = 0; g < NSTAGE && g < ngroups; ++g) issue(g, g);
+  }
+  if (tid < 128) tab[tid] = logtab[tid];
+  for (int t = tid; t < nt; t += NTHR) {
+    pa_s[t] = pa[(size_t)b * T + tb + t];
+    pw_s[t] = psiW[(size_t)b * T + tb + t];
+    if (GRAD) w_s[t] = W[tb + t];
+  }
+  double pm_m[MPT], row[MPT];
+#pragma unroll
+  for (int q = 0; q < MPT; ++q) {
+    pm_m[q] = pm[(size_t)b * Mp + mb0 + tid + q * NTHR];
+    row[q] = 0.0;
+  }
+  __syncthreads();  // barriers initialised, tables staged
+
+  double val = 0.0, psig = 0.0;
+  for (int g = 0; g < ngroups; ++g) {
+    const int st = g % NSTAGE;
+    mbar_wait(&full[st], (unsigned)((g / NSTAGE) & 1));
+    const unsigned char* stage = smraw + (size_t)st * STAGE_BYTES;
+    double colv[LL_UNROLL];
+#pragma unroll
+    for (int j = 0; j < LL_UNROLL; ++j) {
+      const int t = g * LL_STAGE_DAYS + j;
+      colv[j] = 0.0;
+      if (t < nt) {
+        const int* sy = reinterpret_cast<const int*>(stage + (size_t)j * DAY_BYTES);
+        const int* sS = sy + MB;
+        const int* sI = sy + 2 * MB;
+        const double* sB = reinterpret_cast<const double*>(sy + 3 * MB);
+        const double pat = pa_s[t], pwt = pw_s[t];
+#pragma unroll
+        for (int q = 0; q < MPT; ++q) {
+          const int k = tid + q * NTHR;
+          const int y = sy[k], S = sS[k], I = sI[k];
+          const double bc = sB[k];
+          const double e = pat * pm_m[q];
+          const double X = (double)I + pwt * bc;
+          const double lam = fma(e, X, eps);
+          const double x = lam * dt;
+          const double yd = (double)y, rd = (double)(S - y);
+          double term = -rd * x;
+          double gg = -rd;
+          double lg, rc;
+          if (x < LL_SMALL_X && fast_log_rcp<GRAD>(x, tab, lg, rc)) {
+            const double x2 = x * x;
+            if (y > 0) {
+              term += yd * (lg + fma(x2, fma(x2, fma(x2, 5.511463844797178e-06, -3.472222222222222e-04), 0.041666666666666664), -0.5 * x));
+              if (GRAD) gg += yd * (rc - 0.5 + x * fma(x2, fma(x2, 3.306878306878307e-05, -1.388888888888889e-03), 0.08333333333333333));
+            }
+          } else {
+            const double em = expm1(-x);
+            if (y > 0) term += yd * log(-em);
+            if (GRAD && y > 0) gg += yd * (1.0 + em) / (-em);
+          }
+          val += term;
+          if (GRAD) {
+            gg *= dt;
+            const double h = gg * (lam - eps);
+            row[q] += h;
+            psig += gg * e * w_s[t] * bc;
+            colv[j] += h;
+          }
+        }
+      }
+    }
+    if (GRAD) {
+      const double tot = warp_sum4_transposed(colv);
+      if ((lane & 7) == 0) colw[warp * cstride + g * LL_STAGE_DAYS + ((lane >> 4) & 1) * 2 + ((lane >> 3) & 1)] = tot;
+    }
+    __syncthreads();  // every thread is done reading this stage: it may be refilled
+    if (tid == 0 && g + NSTAGE < ngroups) issue(g + NSTAGE, st);
+  }
+  const int slot = blockIdx.z * gridDim.x + blockIdx.x, nslot = gridDim.x * gridDim.z;
+  const double v = block_sum(val, red);
+  if (tid == 0) val_part[(size_t)b * nslot + slot] = v;
+  if (GRAD) {
+    const double pg = block_sum(psig, red);
+    if (tid == 0) psi_part[(size_t)b * nslot + slot] = pg;
+#pragma unroll
+    for (int q = 0; q < MPT; ++q) rowsum_part[((size_t)b * gridDim.z + blockIdx.z) * Mp + mb0 + tid + q * NTHR] = row[q];
+    __syncthreads();
+    for (int t = tid; t < nt; t += NTHR) {
+      double cta = 0.0;
+#pragma unroll
+      for (int w = 0; w < NTHR / 32; ++w) cta += colw[w * cstride + t];
+      col_part[((size_t)b * gridDim.x + blockIdx.x) * T + tb + t] = cta;
+    }
+  }
+}
+
+#define LL_TMA_STAGES 2
+
+typedef void (*loglik_fn)(int, int, int, double, double, const int*, const int*, const int*, const double*, const double*,
+                          const double*, const double*, const double*, const double2*, double*, double*, double*, double*);
+
+struct loglik_cfg {
+  bool tma;
+  int threads, mpt, nblk;  // CTA = threads x mpt metapopulations; nblk CTAs cover Mp
+  int stages;              // shared-memory ring depth of the TMA kernel
+};
+
+// Kernel shape for a padded metapopulation count.  TMA kernel: one thread per metapopulation, up to 512 threads
+// (12 warps at the UK's Mp = 384: thread-level parallelism hides the FP64 dependency chains while the bulk copies
+// hide HBM latency); direct-load kernel for sizes that are not a multiple of 128.
+static loglik_cfg loglik_config(const seir_chains* c) {
+  const int Mp = c->model->Mp;
+  static int variant = -1;
+  if (variant < 0) {
+    const char* e = getenv("SEIR_LL_VARIANT");  // experiments: 0 direct loads, 1 TMA 128 threads x mpt, 2 TMA wide CTA (default)
+    variant = e ? atoi(e) : 2;
+  }
+  loglik_cfg k;
+  k.mpt = c->mpt;
+  k.stages = LL_TMA_STAGES;
+  k.threads = SEIR_LL_THREADS;
+  k.nblk = c->nblkLL;
+  k.tma = variant != 0 && Mp % (SEIR_LL_THREADS * c->mpt) == 0;
+  if (k.tma && variant == 2) {
+    const int thr = Mp % 512 == 0 ? 512 : (Mp % 384 == 0 ? 384 : (Mp % 256 == 0 ? 256 : 128));
+    if (Mp / thr <= c->nblkLL) {  // partial arrays are sized for nblkLL column blocks
+      k.threads = thr;
+      k.mpt = 1;
+      k.nblk = Mp / thr;
+      const char* e = getenv("SEIR_LL_STAGES");
+      if (e && atoi(e) == 3) k.stages = 3;
+    }
+  }
+  return k;
+}
+
+template <bool GRAD>
+static loglik_fn loglik_kernel_for(const loglik_cfg& k) {
+  if (k.tma) {
+    if (k.mpt == 1) {
+      if (k.stages == 3) {
+        switch (k.threads) {
+          case 512: return seir_loglik_tma_kernel<GRAD, 1, 3, 512>;
+          case 384: return seir_loglik_tma_kernel<GRAD, 1, 3, 384>;
+          case 256: return seir_loglik_tma_kernel<GRAD, 1, 3, 256>;
+          default: return seir_loglik_tma_kernel<GRAD, 1, 3, 128>;
+        }
+      }
+      switch (k.threads) {
+        case 512: return seir_loglik_tma_kernel<GRAD, 1, LL_TMA_STAGES, 512>;
+        case 384: return seir_loglik_tma_kernel<GRAD, 1, LL_TMA_STAGES, 384>;
+        case 256: return seir_loglik_tma_kernel<GRAD, 1, LL_TMA_STAGES, 256>;
+        default: return seir_loglik_tma_kernel<GRAD, 1, LL_TMA_STAGES, 128>;
+      }
+    }
+    switch (k.mpt) {
+      case 2: return seir_loglik_tma_kernel<GRAD, 2, LL_TMA_STAGES, 128>;
+      case 3: return seir_loglik_tma_kernel<GRAD, 3, LL_TMA_STAGES, 128>;
+      default: return seir_loglik_tma_kernel<GRAD, 4, LL_TMA_STAGES, 128>;
+    }
+  }
+  switch (k.mpt) {
+    case 1: return seir_loglik_kernel<GRAD, 1>;
+    case 2: return seir_loglik_kernel<GRAD, 2>;
+    case 3: return seir_loglik_kernel<GRAD, 3>;
+    default: return seir_loglik_kernel<GRAD, 4>;
+  }
+}
+
+static size_t loglik_smem(bool grad, int dps, const loglik_cfg& k) {
+  size_t bytes = sizeof(double) * (grad ? (size_t)3 * dps + (k.threads / 32) * (dps + LL_UNROLL) : (size_t)2 * dps);
+  if (k.tma) bytes += (size_t)k.stages * LL_STAGE_DAYS * k.threads * k.mpt * 20;
+  return bytes;
+}
+
+// Day splits.  Direct-load kernel: (metapopulation blocks x chains x splits) fills the resident CTA slots once.
+// TMA kernel: few CTA slots per SM (shared-memory bound), so aim at ~4 waves of short CTAs (whole butterfly groups
+// of 4 days) that the hardware scheduler balances dynamically.
+static int choose_dps(const seir_chains* c, bool grad, const loglik_cfg& k, loglik_fn fn) {
+  int dev = 0, sms = 148, per = 8;
+  cudaGetDevice(&dev);
+  cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev);
   const int T = c->model->T;
-  long long base = (long long)c->nblkLL * c->B;
-  int ts = (int)(slots[grad] / base);
+  const size_t smem = loglik_smem(grad, k.tma ? 16 : (grad ? 32 : 16), k);
+  if (smem > 48 * 1024) cudaFuncSetAttribute(fn, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
+  cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per, fn, k.threads, smem);
+  const long long slots = (long long)sms * (per > 0 ? per : 1);
+  const long long base = (long long)k.nblk * c->B;
   const int cap = (T + 3) / 4 < SEIR_MAX_SPLITS ? (T + 3) / 4 : SEIR_MAX_SPLITS;
-  if (ts > cap) ts = cap;
+  long long want = k.tma ? (4 * slots + base - 1) / base : slots / base;
+  int ts = (int)(want > cap ? cap : want);
   if (ts < 1) ts = 1;
-  return ts;
+  int dps = (T + ts - 1) / ts;
+  if (k.tma) dps = (dps + LL_STAGE_DAYS - 1) / LL_STAGE_DAYS * LL_STAGE_DAYS;
+  return dps;
 }
 
 int seir_launch_loglik(seir_chains* c, bool grad, cudaStream_t s) {
   const seir_model* m = c->model;
-  const int ts = choose_splits(c, grad);
-  const int dps = (m->T + ts - 1) / ts;
+  const loglik_cfg k = loglik_config(c);
+  loglik_fn fn = grad ? loglik_kernel_for<true>(k) : loglik_kernel_for<false>(k);
+  if (!c->ll_dps[grad]) c->ll_dps[grad] = choose_dps(c, grad, k, fn);
+  const int dps = c->ll_dps[grad];
   const int nts = (m->T + dps - 1) / dps;
   c->nts = nts;
-  dim3 grid(c->nblkLL, c->B, nts);
-  const size_t smem = sizeof(double) * (size_t)dps * (grad ? 3 + SEIR_LL_THREADS / 32 : 2);
-  if (grad)
-    seir_loglik_kernel<true><<<grid, SEIR_LL_THREADS, smem, s>>>(m->T, m->Mp, dps, m->dt, m->rate_eps, c->d_yse, c->d_S, c->d_I,
-                                                                 c->d_Bc, c->d_pa, c->d_psiW, m->d_W, c->d_pm, c->d_val_part,
-                                                                 c->d_psi_part, c->d_col_part, c->d_rowsum);
-  else
-    seir_loglik_kernel<false><<<grid, SEIR_LL_THREADS, smem, s>>>(m->T, m->Mp, dps, m->dt, m->rate_eps, c->d_yse, c->d_S, c->d_I,
-                                                                  c->d_Bc, c->d_pa, c->d_psiW, m->d_W, c->d_pm, c->d_val_part,
-                                                                  c->d_psi_part, c->d_col_part, c->d_rowsum);
+  c->nblk_last = k.nblk;
+  dim3 grid(k.nblk, c->B, nts);
+  const size_t smem = loglik_smem(grad, dps, k);
+  if (smem > 48 * 1024) SEIR_CUDA(cudaFuncSetAttribute(fn, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+  fn<<<grid, k.threads, smem, s>>>(m->T, m->Mp, dps, m->dt, m->rate_eps, c->d_yse, c->d_S, c->d_I, c->d_Bc, c->d_pa, c->d_psiW,
+                                   m->d_W, c->d_pm, m->d_logtab, c->d_val_part, c->d_psi_part, c->d_col_part, c->d_rowsum);
   seir_count_launch(1);
   return seir_cuda_check(cudaGetLastError(), "seir_loglik_kernel");
 }
@@ -391,7 +719,7 @@ int seir_launch_finalize(seir_chains* c, const double* d_theta, int kind, int pa
                          cudaStream_t s) {
   const seir_model* m = c->model;
   seir_finalize_kernel<<<c->B, FIN_THREADS, sizeof(double) * m->T, s>>>(
-      m->M, m->T, m->Mp, m->P, c->nblkLL, c->nts, c->nllc, m->dt, m->nu, m->log_p_nu, kind, parts, d_theta, c->d_scal, c->d_val_part,
+      m->M, m->T, m->Mp, m->P, c->nblk_last ? c->nblk_last : c->nblkLL, c->nts, c->nllc, m->dt, m->nu, m->log_p_nu, kind, parts, d_theta, c->d_scal, c->d_val_part,
       c->d_llc_part, c->d_llc_adj, c->d_Yir, c->d_Rir, c->d_sumYei, c->d_sumEres, c->d_flags, c->d_gam, c->d_logpir, m->d_wk, m->d_tfirst, m->d_la,
       c->d_psi_part, c->d_col_part, c->d_rowsum, m->d_car_indptr, m->d_car_indices, m->d_car_values, d_out, d_grad);
   seir_count_launch(1);

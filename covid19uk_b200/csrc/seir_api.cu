@@ -129,6 +129,12 @@ int seir_model_create(const seir_spec* spec, int device, seir_model** out) {
       return seir_set_error(SEIR_ERR_UNSUPPORTED, "seir_model_create: alpha_t index path must be non-decreasing in time");
     }
   for (int k = 0; k < SEIR_LGTAB_BIG; ++k) lgtab[k] = lgamma((double)k + 1.0);
+  std::vector<double2> logtab(128);
+  for (int i = 0; i < 128; ++i) {
+    const double inv_c = 1.0 / (1.0 + ((double)i + 0.5) / 128.0);
+    logtab[i].x = inv_c;
+    logtab[i].y = (double)(-logl((long double)inv_c));
+  }
   std::vector<int> indptr(spec->car_indptr, spec->car_indptr + M + 1);
   std::vector<int> indices(spec->car_indices, spec->car_indices + spec->car_nnz);
   std::vector<double> values(spec->car_values, spec->car_values + spec->car_nnz);
@@ -138,7 +144,7 @@ int seir_model_create(const seir_spec* spec, int device, seir_model** out) {
       (rc = dev_upload(&m->d_wk, wk)) || (rc = dev_upload(&m->d_aidx, aidx)) || (rc = dev_upload(&m->d_tfirst, tfirst)) || (rc = dev_upload(&m->d_la, la)) ||
       (rc = dev_upload(&m->d_init, init)) || (rc = dev_upload(&m->d_car_indptr, indptr)) ||
       (rc = dev_upload(&m->d_car_indices, indices)) || (rc = dev_upload(&m->d_car_values, values)) ||
-      (rc = dev_upload(&m->d_lgtab, lgtab))) {
+      (rc = dev_upload(&m->d_lgtab, lgtab)) || (rc = dev_upload(&m->d_logtab, logtab))) {
     seir_model_destroy(m);
     return rc;
   }
@@ -150,7 +156,7 @@ void seir_model_destroy(seir_model* m) {
   if (!m) return;
   cudaSetDevice(m->device);
   cudaFree(m->d_cs); cudaFree(m->d_rN); cudaFree(m->d_W); cudaFree(m->d_wk); cudaFree(m->d_aidx); cudaFree(m->d_tfirst); cudaFree(m->d_la);
-  cudaFree(m->d_init); cudaFree(m->d_car_indptr); cudaFree(m->d_car_indices); cudaFree(m->d_car_values); cudaFree(m->d_lgtab);
+  cudaFree(m->d_init); cudaFree(m->d_car_indptr); cudaFree(m->d_car_indices); cudaFree(m->d_car_values); cudaFree(m->d_lgtab); cudaFree(m->d_logtab);
   delete m;
 }
 
@@ -174,7 +180,9 @@ int seir_chains_create(const seir_model* m, int B, seir_chains** out) {
   c->model = m;
   c->B = B;
   c->nblk32 = m->Mp / 32;
-  c->nblkLL = (m->Mp + SEIR_LL_THREADS - 1) / SEIR_LL_THREADS;
+  c->mpt = (m->Mp + SEIR_LL_THREADS - 1) / SEIR_LL_THREADS;
+  if (c->mpt > 4) c->mpt = 4;
+  c->nblkLL = (m->Mp + SEIR_LL_THREADS * c->mpt - 1) / (SEIR_LL_THREADS * c->mpt);
   c->nts = 1;
   const size_t cells = (size_t)B * m->T * m->Mp, BT = (size_t)B * m->T;
   int rc = SEIR_OK;

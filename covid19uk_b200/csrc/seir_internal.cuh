@@ -46,6 +46,7 @@ struct seir_model {
   int* d_car_indices;  // [nnz]
   double* d_car_values;
   double* d_lgtab;     // [SEIR_LGTAB_BIG]
+  double2* d_logtab;   // [128] {1/c_i rounded, -log(1/c_i)}: range reduction of log / reciprocal in the log-likelihood kernel
 };
 
 // ---- discrete updates (delta.cu) -------------------------------------------------------------------
@@ -76,8 +77,11 @@ struct seir_chains {
   const seir_model* model;
   int B;
   int nblk32;   // Mp/32   (ingest CTAs per chain)
-  int nblkLL;   // ceil(Mp/SEIR_LL_THREADS)
+  int mpt;      // metapopulations per thread of the log-likelihood kernel (1..4)
+  int nblkLL;   // ceil(Mp/(SEIR_LL_THREADS*mpt))
   int nts;      // day splits used by the last log-likelihood launch
+  int nblk_last;  // metapopulation column blocks used by the last log-likelihood launch
+  int ll_dps[2];  // days per CTA of the log-likelihood kernel (value / value+gradient), chosen on first launch
   int nllc;     // number of llc partials per chain written by the last coefficient launch
   size_t stats_bytes;  // bytes of the contiguous integer-statistics block starting at d_Yir
   int64_t bytes;
