@@ -32,6 +32,7 @@ ROOT = os.path.dirname(os.path.abspath(__file__))
 sys.path.insert(0, ROOT)
 
 M_UK, T_UK = 382, 84
+SWEEP_CFG = dict(dmax=84, nmax=25, m=2, occult_nmax=15, num_event_time_updates=5)  # example_config.yaml:26-30
 METRIC = "log-prob evals/sec (joint log-density, 382 LAD x 84 d)"
 UNIT = "evals/s"
 
@@ -235,9 +236,33 @@ def run_native(args):
     if world > 1:
         dist.all_reduce(e2e_s, op=dist.ReduceOp.MAX)
     e2e_value = world * B * K / float(e2e_s.item())
-    clocks = sampler.stop() if rank == 0 else None
     assert torch.allclose(out_h.cuda(), out_d, rtol=1e-13), "host and device entry points disagree"
     assert bool(torch.isfinite(out_d).all()), "non-finite log-prob in the benchmark workload"
+
+    # ---- MCMC sweeps/s (BASELINE.json configs[2]/[3]): HMC (16 leapfrogs) + 5 x 4 discrete updates per chain,
+    #      through the public sampler (ChainSet.sample -> seir_mcmc_sweep), trace read back to the host ----
+    from covid19uk_b200.inference.sampler import ChainSet
+
+    cs = ChainSet(eng, events_d, theta_d, SWEEP_CFG, [T_UK - 21, T_UK], seed=1, chain_offset=rank * B)
+    cs.sample(2, step_size=args.sweep_step_size, collect_draws=False)
+    sync_all()
+    launches_s0 = nat.launch_count()
+    start.record()
+    _, trace = cs.sample(args.sweeps, step_size=args.sweep_step_size, collect_draws=False)
+    acc = {k: float(v["is_accepted"].double().mean().cpu()) for k, v in trace.items()}
+    end.record()
+    sync_all()
+    sweep_launches = (nat.launch_count() - launches_s0) / max(args.sweeps, 1)
+    ms_s = torch.tensor([start.elapsed_time(end)], dtype=torch.float64, device="cuda")
+    if world > 1:
+        dist.all_reduce(ms_s, op=dist.ReduceOp.MAX)
+    sweep_ms = float(ms_s.item()) / max(args.sweeps, 1)
+    sweeps_info = {"chain_sweeps_per_s": world * B / (sweep_ms * 1e-3), "ms_per_sweep": sweep_ms, "chains_per_gpu": B,
+                   "sweeps_timed": args.sweeps, "launches_per_sweep": sweep_launches, "acceptance_rank0": acc,
+                   "tlp_finite": bool(torch.isfinite(cs.tlp).all()),
+                   "config": "1 HMC transition (16 leapfrogs, 17 value+gradient) + 5 x [S->E move, E->I move, S->E occult, E->I occult]; "
+                             "dmax 84, nmax 25, m 2, occult_nmax 15 (example_config.yaml:26-30); reference-equivalent = 37 full log-prob evaluations"}
+    clocks = sampler.stop() if rank == 0 else None
 
     if rank == 0:
         # ---- per-kernel timing (CUDA events on the launch stream) for the roofline ----
@@ -305,6 +330,7 @@ def run_native(args):
             "roofline_kernels": kernels + [warm_grad],
             "warm": {"evals_per_s": B / (warm_ms * 1e-3), "ms_per_step": warm_ms,
                      "note": "events unchanged since ingest (the HMC case): theta_prep + loglik + finalize"},
+            "sweeps": sweeps_info,
             "cpu_baseline": cpu,
             "fp64_peak_tflops_measured": fp64_peak,
         }
@@ -322,6 +348,8 @@ def main():
     ap.add_argument("--warmup", type=int, default=3)
     ap.add_argument("--impl", default="native", choices=["native", "reference"])
     ap.add_argument("--chains", type=int, default=256, help="chains per GPU")
+    ap.add_argument("--sweeps", type=int, default=10, help="MCMC sweeps timed for the sweeps/s figure")
+    ap.add_argument("--sweep-step-size", type=float, default=2e-5)
     args = ap.parse_args()
     if args.impl == "reference":
         run_reference(args)

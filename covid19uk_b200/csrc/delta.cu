@@ -17,14 +17,22 @@
 // Proposal conventions restated from gemlib ([recall], see oracle/seir_oracle.py move_max_events /
 // occult_delete_max and SURVEY Appendix B.1/B.3): parity unpinned.
 #include "delta_common.cuh"
+#include "propose.cuh"
 
 // ------------------------------------------------------------------------------------------------
-// prepare: one CTA per chain.  Parses the proposal, evaluates log q_fwd / log q_rev and the delta
-// log-likelihood of the cells owned by the touched metapopulations.
+// prepare: one CTA per chain.  Optionally DRAWS the proposal first (fused sweep: Philox stream position
+// (seed, chain0 + b, ctr), same draws as seir_propose_kernel), then parses it, evaluates log q_fwd / log q_rev
+// and the delta log-likelihood of the cells owned by the touched metapopulations.
 // ------------------------------------------------------------------------------------------------
+struct seir_draw_args {
+  int enabled;
+  uint64_t seed;
+  uint32_t chain0, ctr;
+};
+
 __global__ void __launch_bounds__(UPD_THREADS) seir_update_prepare_kernel(
-    int M, int T, int Mp, double dt, double nu, double log_p_nu, double eps, seir_update_cfg cfg, const int* __restrict__ prop,
-    const int* __restrict__ yse, const int* __restrict__ yei, const int* __restrict__ yir, const int* __restrict__ Sx,
+    int M, int T, int Mp, double dt, double nu, double log_p_nu, double eps, seir_update_cfg cfg, seir_draw_args draw, int* prop,
+    double* log_u, const int* __restrict__ nzd_all, const int* __restrict__ yse, const int* __restrict__ yei, const int* __restrict__ yir, const int* __restrict__ Sx,
     const int* __restrict__ Ex, const int* __restrict__ Ix, const double* __restrict__ Bc, const int* __restrict__ init,
     const double* __restrict__ lgtab, const double* __restrict__ pa, const double* __restrict__ psiW,
     const double* __restrict__ pm_arr, const double* __restrict__ gam, seir_upd* __restrict__ upd) {
@@ -33,12 +41,18 @@ __global__ void __launch_bounds__(UPD_THREADS) seir_update_prepare_kernel(
   __shared__ double s_qf[SEIR_MMAX], s_qr[SEIR_MMAX];
   __shared__ double redd[UPD_THREADS / 32][2];
   __shared__ int redn[UPD_THREADS / 32];
+  extern __shared__ int s_cnt[];  // [Mp], only when drawing
   const int b = blockIdx.x, tid = threadIdx.x;
   const size_t cb = (size_t)b * T * Mp;
   chain_view v{M, T, Mp, yse + cb, yei + cb, yir + cb, Sx + cb, Ex + cb, Ix + cb, init};
-  const int* pr = prop + (size_t)b * 4 * SEIR_MMAX;
+  int* pr = prop + (size_t)b * 4 * SEIR_MMAX;
   const int target = cfg.target;
   const int* yt = yarr(v, target);
+  const int* nzd = nzd_all + ((size_t)b * 2 + target) * Mp;
+  if (draw.enabled) {
+    seir_sample_proposal(v, cfg, draw.seed, draw.chain0 + (uint32_t)b, draw.ctr, nzd, s_cnt, redn, pr, log_u + b);
+    __syncthreads();  // warp 0's global stores of the record are visible to the whole CTA
+  }
 
   if (tid == 0) {
     int valid = 1, npts = 0;
@@ -72,9 +86,7 @@ __global__ void __launch_bounds__(UPD_THREADS) seir_update_prepare_kernel(
     if (valid && warp < cfg.mmax) {
       const int k = warp;
       const int m = pr[k], t = pr[SEIR_MMAX + k], d = pr[2 * SEIR_MMAX + k], x = pr[3 * SEIR_MMAX + k];
-      int cnt = 0;
-      for (int s = lane; s < T; s += 32) cnt += yt[(size_t)s * Mp + m] > 0;
-      const int nnz = __reduce_add_sync(0xffffffffu, cnt);
+      const int nnz = nzd[m];  // days of m with target events (maintained by ingest / commit)
       const int ytt = yt[(size_t)t * Mp + m], ytd = yt[(size_t)(t + d) * Mp + m];
       const int lo = d > 0 ? t : t + d, hi = d > 0 ? t + d : t;
       const int hi_c = min(hi, lo + cfg.dmax);
@@ -280,7 +292,8 @@ __global__ void __launch_bounds__(UPD_THREADS) seir_update_decide_kernel(
     const double* __restrict__ log_u, const int* __restrict__ prop, int* __restrict__ yse, int* __restrict__ yei,
     int* __restrict__ Sx, int* __restrict__ Ex, int* __restrict__ Ix, long long* __restrict__ Rir,
     long long* __restrict__ sumYei, long long* __restrict__ sumEres, double* __restrict__ llc_adj, double* __restrict__ tlp,
-    int* __restrict__ accept_out, int* __restrict__ last_acc, int* __restrict__ trace, double* __restrict__ dbg) {
+    int* __restrict__ accept_out, int* __restrict__ last_acc, int* __restrict__ trace, double* __restrict__ dbg,
+    int* __restrict__ nzd_all) {
   __shared__ int s_acc;
   __shared__ long long redl[UPD_THREADS / 32];
   const int b = blockIdx.x, tid = threadIdx.x;
@@ -329,7 +342,11 @@ __global__ void __launch_bounds__(UPD_THREADS) seir_update_decide_kernel(
       const int dc = dcum_le(u.pm, u.pd, u.pdy, u.npts, m, s - 1);
       const int dy = dy_at(u.pm, u.pd, u.pdy, u.npts, m, s);
       const size_t o = (size_t)s * Mp + m;
-      if (dy) yt[o] += dy;
+      if (dy) {  // the point changes of a proposal are distinct cells: one thread owns each
+        const int y_old = yt[o], y_new = y_old + dy;
+        yt[o] = y_new;
+        if ((y_old > 0) != (y_new > 0)) atomicAdd(nzd_all + ((size_t)b * 2 + cfg.target) * Mp + m, y_new > 0 ? 1 : -1);
+      }
       if (dc) {
         src[o] -= dc;
         dst[o] += dc;
@@ -350,14 +367,14 @@ __global__ void __launch_bounds__(UPD_THREADS) seir_update_decide_kernel(
   if (tid == 0) { long long r = 0; for (int w = 0; w < UPD_THREADS / 32; ++w) r += redl[w]; sumYei[b] += r; }
 }
 
-int seir_launch_update(seir_chains* c, const seir_update_cfg& cfg, int slot, const int* d_proposal, const double* d_log_u,
-                       double* d_tlp, int* d_accept, int* d_trace, double* d_dbg, cudaStream_t s) {
+static int launch_update(seir_chains* c, const seir_update_cfg& cfg, int slot, const seir_draw_args& draw, int* d_proposal,
+                         double* d_log_u, double* d_tlp, int* d_accept, int* d_trace, double* d_dbg, cudaStream_t s) {
   const seir_model* m = c->model;
   const int B = c->B, T = m->T, Mp = m->Mp;
   const int nchunk = (T + SLAB_DAYS - 1) / SLAB_DAYS;
-  seir_update_prepare_kernel<<<B, UPD_THREADS, 0, s>>>(m->M, T, Mp, m->dt, m->nu, m->log_p_nu, m->rate_eps, cfg, d_proposal, c->d_yse,
-                                                       c->d_yei, c->d_yir, c->d_S, c->d_E, c->d_I, c->d_Bc, m->d_init, m->d_lgtab,
-                                                       c->d_pa, c->d_psiW, c->d_pm, c->d_gam, c->d_upd);
+  seir_update_prepare_kernel<<<B, UPD_THREADS, draw.enabled ? sizeof(int) * Mp : 0, s>>>(
+      m->M, T, Mp, m->dt, m->nu, m->log_p_nu, m->rate_eps, cfg, draw, d_proposal, d_log_u, c->d_nzd, c->d_yse, c->d_yei, c->d_yir, c->d_S,
+      c->d_E, c->d_I, c->d_Bc, m->d_init, m->d_lgtab, c->d_pa, c->d_psiW, c->d_pm, c->d_gam, c->d_upd);
   int launches = 2;
   if (cfg.target == 1) {
     seir_update_slab_kernel<false><<<dim3(B, nchunk), 32 * SLAB_DAYS, 0, s>>>(m->M, T, Mp, m->dt, m->rate_eps, cfg.kind, c->d_upd, c->d_yse,
@@ -368,7 +385,7 @@ int seir_launch_update(seir_chains* c, const seir_update_cfg& cfg, int slot, con
   seir_update_decide_kernel<<<B, UPD_THREADS, 0, s>>>(m->M, T, Mp, cfg, nchunk, c->d_upd, c->d_upd_part, d_log_u, d_proposal, c->d_yse,
                                                       c->d_yei, c->d_S, c->d_E, c->d_I, c->d_Rir, c->d_sumYei, c->d_sumEres,
                                                       c->d_llc_adj, d_tlp, d_accept, c->d_last_acc + (size_t)slot * B * 4 * SEIR_MMAX,
-                                                      d_trace, d_dbg);
+                                                      d_trace, d_dbg, c->d_nzd);
   if (cfg.target == 1) {
     seir_update_slab_kernel<true><<<dim3(B, nchunk), 32 * SLAB_DAYS, 0, s>>>(m->M, T, Mp, m->dt, m->rate_eps, cfg.kind, c->d_upd, c->d_yse,
                                                                             c->d_S, c->d_I, c->d_Bc, m->d_cs, c->d_pa, c->d_psiW,
@@ -377,6 +394,21 @@ int seir_launch_update(seir_chains* c, const seir_update_cfg& cfg, int slot, con
   }
   seir_count_launch(launches);
   return seir_cuda_check(cudaGetLastError(), "seir_update kernels");
+}
+
+// explicit proposal + log u (the RNG-free path the parity tests pin)
+int seir_launch_update(seir_chains* c, const seir_update_cfg& cfg, int slot, const int* d_proposal, const double* d_log_u,
+                       double* d_tlp, int* d_accept, int* d_trace, double* d_dbg, cudaStream_t s) {
+  const seir_draw_args none{0, 0ull, 0u, 0u};
+  return launch_update(c, cfg, slot, none, const_cast<int*>(d_proposal), const_cast<double*>(d_log_u), d_tlp, d_accept, d_trace, d_dbg, s);
+}
+
+// proposal and log u drawn inside the prepare kernel (fused sweep); the record is left in d_proposal / d_log_u
+int seir_launch_update_drawn(seir_chains* c, const seir_update_cfg& cfg, int slot, unsigned long long seed, unsigned chain0,
+                             unsigned ctr, int* d_proposal, double* d_log_u, double* d_tlp, int* d_accept, int* d_trace,
+                             cudaStream_t s) {
+  const seir_draw_args draw{1, seed, chain0, ctr};
+  return launch_update(c, cfg, slot, draw, d_proposal, d_log_u, d_tlp, d_accept, d_trace, nullptr, s);
 }
 
 // ------------------------------------------------------------------------------------------------

@@ -79,7 +79,8 @@ __global__ void __launch_bounds__(256) seir_ingest_kernel(int M, int T, int Mp, 
                                                           int* __restrict__ yei, int* __restrict__ yir, int* __restrict__ Sx,
                                                           int* __restrict__ Ex, int* __restrict__ Ix, long long* __restrict__ Yir,
                                                           long long* __restrict__ Rir, long long* __restrict__ sumYei,
-                                                          long long* __restrict__ sumEres, int* __restrict__ flags) {
+                                                          long long* __restrict__ sumEres, int* __restrict__ flags,
+                                                          int* __restrict__ nzd) {
   constexpr int STRIDE = TC * 3 + 1;
   extern __shared__ int smem_i[];
   int* ev = smem_i;                    // [32][STRIDE]
@@ -92,6 +93,7 @@ __global__ void __launch_bounds__(256) seir_ingest_kernel(int M, int T, int Mp, 
   int carry0 = 0, carry1 = 0, carry2 = 0;
   int bad = 0;
   long long accYei = 0, accEres = 0;
+  int nz0 = 0, nz1 = 0;  // days with S->E / E->I events of this lane's metapopulation, within this warp's segments
 
   for (int t0 = 0; t0 < T; t0 += TC) {
     const int tc = min(TC, T - t0);
@@ -143,6 +145,8 @@ __global__ void __launch_bounds__(256) seir_ingest_kernel(int M, int T, int Mp, 
       if (!ok) bad |= 2;
       accYei += y1;
       accEres += E - y1;
+      nz0 += y0 > 0;
+      nz1 += y1 > 0;
       const int ry = __reduce_add_sync(0xffffffffu, y2);      // padding lanes hold zeros
       const int rr = __reduce_add_sync(0xffffffffu, I - y2);
       if (lane == 0) {
@@ -163,6 +167,8 @@ __global__ void __launch_bounds__(256) seir_ingest_kernel(int M, int T, int Mp, 
     atomicAdd(reinterpret_cast<unsigned long long*>(sumYei + b), (unsigned long long)accYei);
     atomicAdd(reinterpret_cast<unsigned long long*>(sumEres + b), (unsigned long long)accEres);
   }
+  if (nz0) atomicAdd(nzd + ((size_t)b * 2 + 0) * Mp + m, nz0);
+  if (nz1) atomicAdd(nzd + ((size_t)b * 2 + 1) * Mp + m, nz1);
   bad = __reduce_or_sync(0xffffffffu, bad);
   if (lane == 0 && bad) atomicOr(flags + b, bad);
 }
@@ -178,7 +184,7 @@ static int launch_ingest_tc(seir_chains* c, const double* d_events, cudaStream_t
   }
   dim3 grid(c->nblk32, c->B);
   seir_ingest_kernel<TC><<<grid, 256, smem, s>>>(m->M, m->T, m->Mp, m->d_init, d_events, c->d_yse, c->d_yei, c->d_yir, c->d_S,
-                                                 c->d_E, c->d_I, c->d_Yir, c->d_Rir, c->d_sumYei, c->d_sumEres, c->d_flags);
+                                                 c->d_E, c->d_I, c->d_Yir, c->d_Rir, c->d_sumYei, c->d_sumEres, c->d_flags, c->d_nzd);
   seir_count_launch(1);
   return seir_cuda_check(cudaGetLastError(), "seir_ingest_kernel");
 }
@@ -188,6 +194,7 @@ int seir_launch_ingest(seir_chains* c, const double* d_events, cudaStream_t s) {
   // one memset over the contiguous integer-statistics block [Yir | Rir | sumYei | sumEres | flags]
   SEIR_CUDA(cudaMemsetAsync(c->d_Yir, 0, c->stats_bytes, s));
   SEIR_CUDA(cudaMemsetAsync(c->d_llc_adj, 0, sizeof(double) * (size_t)B, s));
+  SEIR_CUDA(cudaMemsetAsync(c->d_nzd, 0, sizeof(int) * (size_t)B * 2 * c->model->Mp, s));
   // new events = freshly bootstrapped kernels: no proposal has been accepted yet (MetropolisHastings accepted_results)
   SEIR_CUDA(cudaMemsetAsync(c->d_last_acc, 0, sizeof(int) * (size_t)4 * B * 4 * SEIR_MMAX, s));
   return (T <= 96) ? launch_ingest_tc<96>(c, d_events, s) : launch_ingest_tc<128>(c, d_events, s);

@@ -201,7 +201,8 @@ int seir_chains_create(const seir_model* m, int B, seir_chains** out) {
       (rc = dev_alloc(&c->d_upd, (size_t)B, &c->bytes)) ||
       (rc = dev_alloc(&c->d_upd_part, (size_t)B * ((m->T + 7) / 8), &c->bytes)) ||
       (rc = dev_alloc(&c->d_llc_adj, (size_t)B, &c->bytes)) || (rc = dev_alloc(&c->d_tlp, (size_t)B, &c->bytes)) ||
-      (rc = dev_alloc(&c->d_last_acc, (size_t)4 * B * 4 * SEIR_MMAX, &c->bytes))) {
+      (rc = dev_alloc(&c->d_last_acc, (size_t)4 * B * 4 * SEIR_MMAX, &c->bytes)) ||
+      (rc = dev_alloc(&c->d_nzd, (size_t)B * 2 * m->Mp, &c->bytes))) {
     seir_chains_destroy(c);
     return rc;
   }
@@ -215,6 +216,7 @@ int seir_chains_create(const seir_model* m, int B, seir_chains** out) {
   SEIR_CUDA(cudaMemset(c->d_Yir, 0, c->stats_bytes));
   SEIR_CUDA(cudaMemset(c->d_llc_adj, 0, sizeof(double) * (size_t)B));
   SEIR_CUDA(cudaMemset(c->d_last_acc, 0, sizeof(int) * (size_t)4 * B * 4 * SEIR_MMAX));
+  SEIR_CUDA(cudaMemset(c->d_nzd, 0, sizeof(int) * (size_t)B * 2 * m->Mp));
   *out = c;
   return SEIR_OK;
 }
@@ -226,7 +228,7 @@ void seir_chains_destroy(seir_chains* c) {
   cudaFree(c->d_Bc); cudaFree(c->d_llc_part); cudaFree(c->d_Yir); cudaFree(c->d_pa); cudaFree(c->d_psiW); cudaFree(c->d_gam);
   cudaFree(c->d_logpir); cudaFree(c->d_pm); cudaFree(c->d_scal); cudaFree(c->d_val_part); cudaFree(c->d_psi_part);
   cudaFree(c->d_col_part); cudaFree(c->d_rowsum); cudaFree(c->d_upd); cudaFree(c->d_upd_part); cudaFree(c->d_llc_adj);
-  cudaFree(c->d_tlp); cudaFree(c->d_last_acc); cudaFree(c->d_hmc_u0); cudaFree(c->d_hmc_p); cudaFree(c->d_hmc_grad);
+  cudaFree(c->d_tlp); cudaFree(c->d_last_acc); cudaFree(c->d_nzd); cudaFree(c->d_hmc_u0); cudaFree(c->d_hmc_p); cudaFree(c->d_hmc_grad);
   cudaFree(c->d_hmc_val); cudaFree(c->d_prop); cudaFree(c->d_logu); cudaFree(c->d_stage_events); cudaFree(c->d_stage_theta);
   cudaFree(c->d_stage_out);
   delete c;

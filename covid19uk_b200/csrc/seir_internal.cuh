@@ -94,6 +94,7 @@ struct seir_chains {
   long long* d_sumYei;   // [B]
   long long* d_sumEres;  // [B]  sum (E - y_ei)
   int* d_flags;          // [B]
+  int* d_nzd;            // [B][2][Mp] days with >= 1 event per metapopulation, for S->E and E->I (proposal normalisers)
   // theta-derived
   double *d_pa, *d_psiW, *d_gam, *d_logpir;  // [B][T]
   double* d_pm;                              // [B][Mp]
@@ -153,6 +154,10 @@ int seir_launch_sweep(seir_chains* c, const seir_sweep_spec* sp, unsigned sweep_
 int seir_launch_export_events(seir_chains* c, double* d_events, cudaStream_t s);
 int seir_launch_update(seir_chains* c, const seir_update_cfg& cfg, int slot, const int* d_proposal, const double* d_log_u,
                        double* d_tlp, int* d_accept, int* d_trace, double* d_dbg, cudaStream_t s);
+
+int seir_launch_update_drawn(seir_chains* c, const seir_update_cfg& cfg, int slot, unsigned long long seed, unsigned chain0,
+                             unsigned ctr, int* d_proposal, double* d_log_u, double* d_tlp, int* d_accept, int* d_trace,
+                             cudaStream_t s);
 
 // ---- device helpers ---------------------------------------------------------------------------
 #ifdef __CUDACC__

@@ -50,10 +50,9 @@ int seir_launch_sweep(seir_chains* c, const seir_sweep_spec* sp, unsigned sweep_
       seir_update_cfg cfg;
       slot_cfg(sp, slot, &cfg);
       const unsigned ctr = sweep_index * 64u + (unsigned)(rep * 4 + slot);
-      if ((rc = seir_launch_propose(c, cfg, sp->seed, sp->chain_offset, ctr, c->d_prop, c->d_logu, s)) != SEIR_OK) return rc;
-      if ((rc = seir_launch_update(c, cfg, slot, c->d_prop, c->d_logu, d_tlp, d_upd_accept + (size_t)slot * B,
-                                   (last && d_upd_trace) ? d_upd_trace + (size_t)slot * B * 4 * SEIR_MMAX : nullptr, nullptr, s)) !=
-          SEIR_OK)
+      if ((rc = seir_launch_update_drawn(c, cfg, slot, sp->seed, sp->chain_offset, ctr, c->d_prop, c->d_logu, d_tlp,
+                                         d_upd_accept + (size_t)slot * B,
+                                         (last && d_upd_trace) ? d_upd_trace + (size_t)slot * B * 4 * SEIR_MMAX : nullptr, s)) != SEIR_OK)
         return rc;
       if (last && d_upd_tlp)
         SEIR_CUDA(cudaMemcpyAsync(d_upd_tlp + (size_t)slot * B, d_tlp, sizeof(double) * (size_t)B, cudaMemcpyDeviceToDevice, s));
