@@ -10,6 +10,7 @@
 // Also here: the counter-based Philox4x32-10 generator used by the device-side samplers.
 #include "philox.cuh"
 #include "seir_internal.cuh"
+#include "theta_fin.cuh"
 
 // ---- log u = log(U(0,1)) for the MH decisions, [B] ----
 __global__ void seir_log_uniform_kernel(int B, uint64_t seed, uint32_t chain0, uint32_t sweep, uint32_t purpose, double* __restrict__ out) {
@@ -48,87 +49,77 @@ __global__ void __launch_bounds__(256) seir_hmc_momentum_kernel(int B, int P, ui
   }
 }
 
-// ---- begin: K0, save u0/tlp0, half kick ----
-__global__ void __launch_bounds__(256) seir_hmc_begin_kernel(int P, const double* __restrict__ step, const double* __restrict__ inv_mass,
-                                                             const double* __restrict__ u, const double* __restrict__ grad,
-                                                             const double* __restrict__ val, double* __restrict__ u0,
-                                                             double* __restrict__ p, double* __restrict__ k0,
-                                                             double* __restrict__ val0) {
-  __shared__ double red[32];
-  const int b = blockIdx.x;
-  const double eps = step[b];
-  double k = 0.0;
-  for (int j = threadIdx.x; j < P; j += blockDim.x) {
-    const size_t o = (size_t)b * P + j;
-    const double im = inv_mass ? inv_mass[o] : 1.0, pj = p[o];
-    k += im * pj * pj;
-    u0[o] = u[o];
-    p[o] = pj + 0.5 * eps * grad[o];
-  }
-  const double tot = block_sum(k, red);
-  if (threadIdx.x == 0) {
-    k0[b] = 0.5 * tot;
-    val0[b] = val[b];
-  }
-}
+// ---- fused leapfrog kernel: one CTA per chain, ONE launch between two log-likelihood launches ----
+//   finalize (value + gradient at the current u from the log-likelihood partials)
+//   BEGIN: K0 = p' M^-1 p / 2, save u0 / value0, half kick, drift, theta prep at the new u
+//   MID  : full kick, drift, theta prep at the new u
+//   END  : half kick, K1, MH decision on the energy, rejected chains move back, theta prep (rate factors only)
+//          of the state the chain is left in -- what the discrete updates that follow need
+// (The separate begin/drift/kick/end kernels of the first version cost 5 launches per leapfrog step, each a
+// latency-bound O(P) pass; profiles/r01_v5_*.)
+enum { HMC_BEGIN = 0, HMC_MID = 1, HMC_END = 2 };
 
-// ---- drift: u += eps * inv_mass * p ----
-__global__ void __launch_bounds__(256) seir_hmc_drift_kernel(int P, const double* __restrict__ step, const double* __restrict__ inv_mass,
-                                                             const double* __restrict__ p, double* __restrict__ u) {
-  const int b = blockIdx.y;
-  const double eps = step[b];
-  for (int j = blockIdx.x * blockDim.x + threadIdx.x; j < P; j += gridDim.x * blockDim.x) {
-    const size_t o = (size_t)b * P + j;
-    u[o] = u[o] + eps * ((inv_mass ? inv_mass[o] : 1.0) * p[o]);
-  }
-}
-
-// ---- kick: p += scale * eps * grad ----
-__global__ void __launch_bounds__(256) seir_hmc_kick_kernel(int P, double scale, const double* __restrict__ step,
-                                                            const double* __restrict__ grad, double* __restrict__ p) {
-  const int b = blockIdx.y;
-  const double eps = scale * step[b];
-  for (int j = blockIdx.x * blockDim.x + threadIdx.x; j < P; j += gridDim.x * blockDim.x) {
-    const size_t o = (size_t)b * P + j;
-    p[o] = p[o] + eps * grad[o];
-  }
-}
-
-// ---- end: K1, MH decision on the energy, restore rejected chains ----
-__global__ void __launch_bounds__(256) seir_hmc_end_kernel(int P, const double* __restrict__ inv_mass, const double* __restrict__ p,
-                                                           const double* __restrict__ u0, const double* __restrict__ k0,
-                                                           const double* __restrict__ val0, const double* __restrict__ val,
-                                                           const double* __restrict__ log_u, double* __restrict__ u,
-                                                           double* __restrict__ tlp, int* __restrict__ accept,
-                                                           double* __restrict__ dbg) {
+template <int MODE>
+__global__ void __launch_bounds__(TF_THREADS) seir_hmc_leap_kernel(tf_model md, tf_chains ch, const double* __restrict__ step,
+                                                                  const double* __restrict__ inv_mass, const double* __restrict__ log_u,
+                                                                  double* u, double* __restrict__ p, double* grad,
+                                                                  double* __restrict__ u0, double* __restrict__ val0, double* __restrict__ k0,
+                                                                  double* __restrict__ tlp, int* __restrict__ accept, double* __restrict__ dbg) {
+  extern __shared__ double dyn[];
+  __shared__ tf_shared sh;
   __shared__ double red[32];
   __shared__ int s_acc;
-  const int b = blockIdx.x;
+  const int b = blockIdx.x, P = md.P;
+  double* ub = u + (size_t)b * P;
+  double* gb = grad + (size_t)b * P;
+  const double val = tf_finalize(md, ch, b, ub, SEIR_PART_JOINT, gb, dyn, sh);
+  const double eps = step[b];
   double k = 0.0;
-  for (int j = threadIdx.x; j < P; j += blockDim.x) {
+  for (int j = threadIdx.x; j < P; j += TF_THREADS) {
     const size_t o = (size_t)b * P + j;
-    const double pj = p[o];
-    k += (inv_mass ? inv_mass[o] : 1.0) * pj * pj;
+    const double im = inv_mass ? inv_mass[o] : 1.0;
+    double pj = p[o];
+    if (MODE == HMC_BEGIN) {
+      k += im * pj * pj;
+      u0[o] = ub[j];
+      pj = pj + 0.5 * eps * gb[j];
+    } else if (MODE == HMC_MID) {
+      pj = pj + (1.0 * eps) * gb[j];
+    } else {
+      pj = pj + (0.5 * eps) * gb[j];
+      k += im * pj * pj;
+    }
+    p[o] = pj;
+    if (MODE != HMC_END) ub[j] = ub[j] + eps * (im * pj);
   }
-  const double tot = block_sum(k, red);
-  if (threadIdx.x == 0) {
-    const double k1 = 0.5 * tot;
-    const double ratio = (val[b] - k1) - (val0[b] - k0[b]);
-    const bool fin = isfinite(val[b]) && isfinite(k1);
-    const int acc = (fin && log_u[b] < ratio) ? 1 : 0;  // non-finite proposed energy rejects; NaN compares false
-    s_acc = acc;
-    accept[b] = acc;
-    tlp[b] = acc ? val[b] : val0[b];
-    if (dbg) {
-      dbg[(size_t)b * 4 + 0] = ratio;
-      dbg[(size_t)b * 4 + 1] = val[b];
-      dbg[(size_t)b * 4 + 2] = k0[b];
-      dbg[(size_t)b * 4 + 3] = k1;
+  if (MODE != HMC_MID) {
+    const double tot = block_sum(k, red);
+    if (threadIdx.x == 0) {
+      if (MODE == HMC_BEGIN) {
+        k0[b] = 0.5 * tot;
+        val0[b] = val;
+      } else {
+        const double k1 = 0.5 * tot;
+        const double ratio = (val - k1) - (val0[b] - k0[b]);
+        const bool fin = isfinite(val) && isfinite(k1);
+        const int acc = (fin && log_u[b] < ratio) ? 1 : 0;  // non-finite proposed energy rejects; NaN compares false
+        s_acc = acc;
+        accept[b] = acc;
+        tlp[b] = acc ? val : val0[b];
+        if (dbg) {
+          dbg[(size_t)b * 4 + 0] = ratio;
+          dbg[(size_t)b * 4 + 1] = val;
+          dbg[(size_t)b * 4 + 2] = k0[b];
+          dbg[(size_t)b * 4 + 3] = k1;
+        }
+      }
     }
   }
   __syncthreads();
-  if (!s_acc)
-    for (int j = threadIdx.x; j < P; j += blockDim.x) u[(size_t)b * P + j] = u0[(size_t)b * P + j];
+  if (MODE == HMC_END && !s_acc)
+    for (int j = threadIdx.x; j < P; j += TF_THREADS) ub[j] = u0[(size_t)b * P + j];
+  __syncthreads();  // u of this chain is final: stage it for the next log-likelihood launch
+  tf_theta_prep(md, ch, b, ub, SEIR_THETA_UNCONSTRAINED, MODE == HMC_END ? SEIR_PART_SEIR : SEIR_PART_JOINT, dyn, sh);
 }
 
 static int hmc_alloc(seir_chains* c) {
@@ -144,13 +135,6 @@ static int hmc_alloc(seir_chains* c) {
 
 int seir_hmc_workspace(seir_chains* c) { return hmc_alloc(c); }
 
-static int value_and_grad(seir_chains* c, const double* d_u, double* d_val, double* d_grad, cudaStream_t s) {
-  int rc;
-  if ((rc = seir_launch_theta_prep(c, d_u, SEIR_THETA_UNCONSTRAINED, SEIR_PART_JOINT, s)) != SEIR_OK) return rc;
-  if ((rc = seir_launch_loglik(c, true, s)) != SEIR_OK) return rc;
-  return seir_launch_finalize(c, d_u, SEIR_THETA_UNCONSTRAINED, SEIR_PART_JOINT, d_val, d_grad, s);
-}
-
 int seir_launch_hmc_momentum(seir_chains* c, unsigned long long seed, unsigned chain0, unsigned sweep, const double* d_inv_mass,
                              double* d_p, cudaStream_t s) {
   const int P = c->model->P;
@@ -161,27 +145,38 @@ int seir_launch_hmc_momentum(seir_chains* c, unsigned long long seed, unsigned c
 }
 
 // One HMC transition; d_momentum == NULL means "already in c->d_hmc_p".
+// Launch sequence for L leapfrog steps: theta prep, [log-lik, leap kernel] x (L + 1)  -- the GibbsKernel re-bootstraps
+// gradient-based kernels, i.e. one fresh value+gradient at the current point, then L more.
 int seir_launch_hmc(seir_chains* c, double* d_u, const double* d_momentum, const double* d_log_u, const double* d_step,
                     const double* d_inv_mass, int num_leapfrog, double* d_tlp, int* d_accept, double* d_dbg, cudaStream_t s) {
   int rc = hmc_alloc(c);
   if (rc != SEIR_OK) return rc;
   const seir_model* m = c->model;
   const int B = c->B, P = m->P;
-  double *val = c->d_hmc_val, *val0 = c->d_hmc_val + B, *k0 = c->d_hmc_val + 2 * B;
+  double *val0 = c->d_hmc_val + B, *k0 = c->d_hmc_val + 2 * B;
   if (d_momentum)
     SEIR_CUDA(cudaMemcpyAsync(c->d_hmc_p, d_momentum, sizeof(double) * (size_t)B * P, cudaMemcpyDeviceToDevice, s));
-  // GibbsKernel re-bootstraps gradient-based kernels: one fresh value+gradient at the current point
-  if ((rc = value_and_grad(c, d_u, val, c->d_hmc_grad, s)) != SEIR_OK) return rc;
-  seir_hmc_begin_kernel<<<B, 256, 0, s>>>(P, d_step, d_inv_mass, d_u, c->d_hmc_grad, val, c->d_hmc_u0, c->d_hmc_p, k0, val0);
-  const dim3 eg((P + 255) / 256, B);
-  for (int i = 0; i < num_leapfrog; ++i) {
-    seir_hmc_drift_kernel<<<eg, 256, 0, s>>>(P, d_step, d_inv_mass, c->d_hmc_p, d_u);
-    if ((rc = value_and_grad(c, d_u, val, c->d_hmc_grad, s)) != SEIR_OK) return rc;
-    seir_hmc_kick_kernel<<<eg, 256, 0, s>>>(P, i + 1 < num_leapfrog ? 1.0 : 0.5, d_step, c->d_hmc_grad, c->d_hmc_p);
+  const size_t smem = seir_tf_smem(m);
+  if (smem > 48 * 1024) {
+    SEIR_CUDA(cudaFuncSetAttribute(seir_hmc_leap_kernel<HMC_BEGIN>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+    SEIR_CUDA(cudaFuncSetAttribute(seir_hmc_leap_kernel<HMC_MID>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+    SEIR_CUDA(cudaFuncSetAttribute(seir_hmc_leap_kernel<HMC_END>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
   }
-  seir_hmc_end_kernel<<<B, 256, 0, s>>>(P, d_inv_mass, c->d_hmc_p, c->d_hmc_u0, k0, val0, val, d_log_u, d_u, d_tlp, d_accept, d_dbg);
-  seir_count_launch(2 + 2 * num_leapfrog);
-  if ((rc = seir_cuda_check(cudaGetLastError(), "seir_hmc kernels")) != SEIR_OK) return rc;
-  // rate factors of the CURRENT theta for the discrete updates that follow (rejected chains moved back)
-  return seir_launch_theta_prep(c, d_u, SEIR_THETA_UNCONSTRAINED, SEIR_PART_SEIR, s);
+  const tf_model md = seir_tf_model(m);
+  if ((rc = seir_launch_theta_prep(c, d_u, SEIR_THETA_UNCONSTRAINED, SEIR_PART_JOINT, s)) != SEIR_OK) return rc;
+  for (int i = 0; i <= num_leapfrog; ++i) {
+    if ((rc = seir_launch_loglik(c, true, s)) != SEIR_OK) return rc;
+    const tf_chains ch = seir_tf_chains(c);  // (after the log-lik launch: it fixes the partial-array shapes)
+    if (i == 0)
+      seir_hmc_leap_kernel<HMC_BEGIN><<<B, TF_THREADS, smem, s>>>(md, ch, d_step, d_inv_mass, d_log_u, d_u, c->d_hmc_p, c->d_hmc_grad,
+                                                                  c->d_hmc_u0, val0, k0, d_tlp, d_accept, d_dbg);
+    else if (i < num_leapfrog)
+      seir_hmc_leap_kernel<HMC_MID><<<B, TF_THREADS, smem, s>>>(md, ch, d_step, d_inv_mass, d_log_u, d_u, c->d_hmc_p, c->d_hmc_grad,
+                                                                c->d_hmc_u0, val0, k0, d_tlp, d_accept, d_dbg);
+    else
+      seir_hmc_leap_kernel<HMC_END><<<B, TF_THREADS, smem, s>>>(md, ch, d_step, d_inv_mass, d_log_u, d_u, c->d_hmc_p, c->d_hmc_grad,
+                                                                c->d_hmc_u0, val0, k0, d_tlp, d_accept, d_dbg);
+  }
+  seir_count_launch(num_leapfrog + 1);
+  return seir_cuda_check(cudaGetLastError(), "seir_hmc kernels");
 }

@@ -193,7 +193,7 @@ int seir_chains_create(const seir_model* m, int B, seir_chains** out) {
       (rc = dev_alloc(&c->d_Yir, 2 * BT + 2 * (size_t)B + ((size_t)B + 1) / 2, &c->bytes)) || (rc = dev_alloc(&c->d_pa, BT, &c->bytes)) ||
       (rc = dev_alloc(&c->d_psiW, BT, &c->bytes)) || (rc = dev_alloc(&c->d_gam, BT, &c->bytes)) ||
       (rc = dev_alloc(&c->d_logpir, BT, &c->bytes)) || (rc = dev_alloc(&c->d_pm, (size_t)B * m->Mp, &c->bytes)) ||
-      (rc = dev_alloc(&c->d_scal, (size_t)B * SEIR_NSCAL, &c->bytes)) ||
+      (rc = dev_alloc(&c->d_scal, (size_t)B * SEIR_NSCAL, &c->bytes)) || (rc = dev_alloc(&c->d_carq, (size_t)B * m->Mp, &c->bytes)) ||
       (rc = dev_alloc(&c->d_val_part, (size_t)B * c->nblkLL * SEIR_MAX_SPLITS, &c->bytes)) ||
       (rc = dev_alloc(&c->d_psi_part, (size_t)B * c->nblkLL * SEIR_MAX_SPLITS, &c->bytes)) ||
       (rc = dev_alloc(&c->d_col_part, (size_t)B * c->nblkLL * m->T, &c->bytes)) ||
@@ -226,7 +226,7 @@ void seir_chains_destroy(seir_chains* c) {
   cudaSetDevice(c->model->device);
   cudaFree(c->d_yse); cudaFree(c->d_yei); cudaFree(c->d_yir); cudaFree(c->d_S); cudaFree(c->d_E); cudaFree(c->d_I);
   cudaFree(c->d_Bc); cudaFree(c->d_llc_part); cudaFree(c->d_Yir); cudaFree(c->d_pa); cudaFree(c->d_psiW); cudaFree(c->d_gam);
-  cudaFree(c->d_logpir); cudaFree(c->d_pm); cudaFree(c->d_scal); cudaFree(c->d_val_part); cudaFree(c->d_psi_part);
+  cudaFree(c->d_logpir); cudaFree(c->d_pm); cudaFree(c->d_scal); cudaFree(c->d_carq); cudaFree(c->d_val_part); cudaFree(c->d_psi_part);
   cudaFree(c->d_col_part); cudaFree(c->d_rowsum); cudaFree(c->d_upd); cudaFree(c->d_upd_part); cudaFree(c->d_llc_adj);
   cudaFree(c->d_tlp); cudaFree(c->d_last_acc); cudaFree(c->d_nzd); cudaFree(c->d_hmc_u0); cudaFree(c->d_hmc_p); cudaFree(c->d_hmc_grad);
   cudaFree(c->d_hmc_val); cudaFree(c->d_prop); cudaFree(c->d_logu); cudaFree(c->d_stage_events); cudaFree(c->d_stage_theta);

@@ -99,6 +99,7 @@ struct seir_chains {
   double *d_pa, *d_psiW, *d_gam, *d_logpir;  // [B][T]
   double* d_pm;                              // [B][Mp]
   double* d_scal;                            // [B][SEIR_NSCAL]
+  double* d_carq;                            // [B][Mp]  (Q . spatial_effect) of the CAR prior, reused by the gradient
   // reductions
   double* d_val_part;  // [B][nts*nblkLL]
   double* d_psi_part;  // [B][nts*nblkLL]
