@@ -79,28 +79,73 @@ __device__ __forceinline__ double int_to_double_magic(int k) {  // exact int32 -
   return __hiloint2double(0x43300000, k ^ 0x80000000) - 4503601774854144.0;  // 2^52 + 2^31
 }
 
-// log(x) and (optionally) 1/x for a positive normal double; false => caller takes the library path
-template <bool RCP>
-__device__ __forceinline__ bool fast_log_rcp(double x, const double2* __restrict__ tab, double& lg, double& rc) {
+// Polynomial / series coefficients travel as a by-value kernel parameter: they sit in constant bank 0 and FP64
+// instructions take them directly as c[0x0][offset] operands.  (As literals the compiler rebuilt each 64-bit immediate
+// with two UMOVs per use -- 14 % of the instructions of the v5 kernel, profiles/r01_v5_ncu_full_summary.md; a
+// __constant__ array costs an LDC per use.)
+struct ll_coefs {
+  double k[13];
+};
+static const ll_coefs LL_COEFS = {{
+    0.14285714285714285, -0.16666666666666666, 0.2, -0.25, 0.3333333333333333, -0.5,  // log1p(r) = r + r^2 (c5 + r (c4 + ...))
+    0.6931471805599453,                                                                // ln 2
+    5.511463844797178e-06, -3.472222222222222e-04, 0.041666666666666664,             // log(1-e^-x) - log x + x/2, even powers
+    3.306878306878307e-05, -1.388888888888889e-03, 0.08333333333333333}};            // 1/expm1(x) - 1/x + 1/2, odd powers
+
+// One (day, metapopulation) cell of the S->E term.  Fast path for a positive normal x = lam*dt < 0.05 (always, for
+// realistic infection hazards), evaluated branch-free:
+//   log x   table-driven range reduction: x = 2^e m, c_i = centre of the mantissa bucket (128 buckets in shared memory),
+//           r = m/c_i - 1 (|r| <= 2^-8, exact through an FMA with the rounded 1/c_i whose own log is tabulated),
+//           log x = e ln2 - log(1/c_i) + log1p(r) [degree 7]
+//   1/x     (gradient only; tolerance 1e-8) FP32 reciprocal + one FP64 Newton step: relative error 2^-46
+//   log(1-e^-x) = log x - x/2 + x^2/24 - x^4/2880 + x^6/181440        (truncation < 1e-17)
+//   1/expm1(x)  = 1/x - 1/2 + x/12 - x^3/720 + x^5/30240
+// Anything else (x >= 0.05, x <= 0, subnormal, NaN) takes the library path: NaN log for x < 0 like the reference.
+// Outputs: val += term;  GRAD: ge = d term / d lam * e  (so that h = ge * X is the cell's d/d log-rate).
+template <bool GRAD>
+__device__ __forceinline__ void ll_cell(int y, int S, int I, double bc, double e, double pwt, double dt, double eps,
+                                        const double2* __restrict__ tab, const ll_coefs& LLK_, double& val, double& h, double& gebc) {
+  const double* LLK = LLK_.k;
+  const double X = (double)I + pwt * bc;
+  const double eX = e * X;
+  const double x = (eX + eps) * dt;
+  const double yd = (double)y, rd = (double)(S - y);
   const int hi = __double2hiint(x), lo = __double2loint(x);
-  if (hi < 0x00100000 || hi >= 0x7ff00000) return false;
-  const int e = (hi >> 20) - 1023;
+  const int ex = (hi >> 20) - 1023;
   const double m = __hiloint2double((hi & 0x000fffff) | 0x3ff00000, lo);
   const double2 tc = tab[(hi >> 13) & 127];  // {1/c rounded, -log(1/c rounded)}
   const double r = fma(m, tc.x, -1.0);
   const double r2 = r * r;
-  double p = fma(r, 0.14285714285714285, -0.16666666666666666);
-  p = fma(r, p, 0.2);
-  p = fma(r, p, -0.25);
-  p = fma(r, p, 0.3333333333333333);
-  p = fma(r, p, -0.5);
-  lg = fma(int_to_double_magic(e), 0.6931471805599453, tc.y) + fma(r2, p, r);
-  if (RCP) {
-    const double r4 = r2 * r2;
-    const double q = ((1.0 - r) * (1.0 + r2)) * ((1.0 + r4) * tc.x);
-    rc = __hiloint2double(__double2hiint(q) - (e << 20), __double2loint(q));
+  double p = fma(r, LLK[0], LLK[1]);
+  p = fma(r, p, LLK[2]);
+  p = fma(r, p, LLK[3]);
+  p = fma(r, p, LLK[4]);
+  p = fma(r, p, LLK[5]);
+  const double lg = fma(int_to_double_magic(ex), LLK[6], tc.y) + fma(r2, p, r);
+  const double x2 = x * x;
+  double term = fma(yd, lg + fma(x2, fma(x2, fma(x2, LLK[7], LLK[8]), LLK[9]), -0.5 * x), -rd * x);
+  double gg = 0.0;
+  if (GRAD) {
+    double rc = (double)__frcp_rn((float)x);
+    rc = fma(rc, fma(-x, rc, 1.0), rc);
+    gg = fma(yd, (rc - 0.5) + x * fma(x2, fma(x2, LLK[10], LLK[11]), LLK[12]), -rd);
   }
-  return true;
+  const bool fast = (hi >= 0x00100000) & (x < LL_SMALL_X);
+  if (__builtin_expect(!fast, 0)) {
+    const double em = expm1(-x);  // -(1-exp(-x)) = -p
+    term = -rd * x;
+    gg = -rd;
+    if (y > 0) {
+      term += yd * log(-em);
+      if (GRAD) gg += yd * (1.0 + em) / (-em);
+    }
+  }
+  val += term;
+  if (GRAD) {
+    const double ge = (gg * dt) * e;
+    h = ge * X;
+    gebc = ge * bc;
+  }
 }
 
 // transposing butterfly: lanes hold a[0..3] (4 days); afterwards lane 8*j holds the warp total of a[j]
@@ -124,7 +169,7 @@ __global__ void __launch_bounds__(SEIR_LL_THREADS, GRAD ? 6 : 10) seir_loglik_ke
     int T, int Mp, int dps, double dt, double eps, const int* __restrict__ yse, const int* __restrict__ Sx,
     const int* __restrict__ Ix, const double* __restrict__ Bc, const double* __restrict__ pa, const double* __restrict__ psiW,
     const double* __restrict__ W, const double* __restrict__ pm, const double2* __restrict__ logtab, double* __restrict__ val_part,
-    double* __restrict__ psi_part, double* __restrict__ col_part, double* __restrict__ rowsum_part) {
+    double* __restrict__ psi_part, double* __restrict__ col_part, double* __restrict__ rowsum_part, const ll_coefs K) {
   extern __shared__ double sm[];
   __shared__ double2 tab[128];
   double* pa_s = sm;             // [dps]
@@ -173,31 +218,11 @@ __global__ void __launch_bounds__(SEIR_LL_THREADS, GRAD ? 6 : 10) seir_loglik_ke
             I = __ldg(Ix + o);
             bc = __ldg(Bc + o);
           }
-          const double e = pat * pm_m[q];
-          const double X = (double)I + pwt * bc;
-          const double lam = fma(e, X, eps);
-          const double x = lam * dt;
-          const double yd = (double)y, rd = (double)(S - y);
-          double term = -rd * x;
-          double g = -rd;
-          double lg, rc;
-          if (x < LL_SMALL_X && fast_log_rcp<GRAD>(x, tab, lg, rc)) {
-            const double x2 = x * x;
-            if (y > 0) {
-              term += yd * (lg + fma(x2, fma(x2, fma(x2, 5.511463844797178e-06, -3.472222222222222e-04), 0.041666666666666664), -0.5 * x));
-              if (GRAD) g += yd * (rc - 0.5 + x * fma(x2, fma(x2, 3.306878306878307e-05, -1.388888888888889e-03), 0.08333333333333333));
-            }
-          } else {
-            const double em = expm1(-x);  // -(1-exp(-x)) = -p ; NaN log for x < 0 like the reference
-            if (y > 0) term += yd * log(-em);
-            if (GRAD && y > 0) g += yd * (1.0 + em) / (-em);
-          }
-          val += term;
+          double h = 0.0, gebc = 0.0;
+          ll_cell<GRAD>(y, S, I, bc, pat * pm_m[q], pwt, dt, eps, tab, K, val, h, gebc);
           if (GRAD) {
-            g *= dt;
-            const double h = g * (lam - eps);
             row[q] += h;
-            psig += g * e * w_s[t] * bc;
+            psig = fma(w_s[t], gebc, psig);
             colv[j] += h;
           }
         }
@@ -263,17 +288,26 @@ __device__ __forceinline__ void mbar_wait(uint64_t* bar, unsigned parity) {
   }
 }
 
+__device__ __forceinline__ void mbar_arrive(uint64_t* bar) {
+  asm volatile("mbarrier.arrive.shared::cta.b64 _, [%0];" ::"r"(smem_u32(bar)) : "memory");
+}
+
+// NTHR consumer threads (thread <-> metapopulation, MPT of them each) + ONE producer warp.  The producer's elected lane
+// refills a stage as soon as every consumer WARP has released it (empty[] mbarrier, one arrival per warp), so warps
+// drift apart by up to NSTAGE-1 stages instead of meeting at a CTA barrier after every 4 days (v5: barrier stalls were
+// 3.2 of 10 stall cycles per issue, profiles/r01_v5_ncu_full_summary.md).
 template <bool GRAD, int MPT, int NSTAGE, int NTHR>
-__global__ void __launch_bounds__(NTHR, NTHR >= 384 ? (GRAD ? 2 : 3) : 1) seir_loglik_tma_kernel(
+__global__ void __launch_bounds__(NTHR + 32, NTHR >= 384 ? (GRAD ? 2 : 3) : 1) seir_loglik_tma_kernel(
     int T, int Mp, int dps, double dt, double eps, const int* __restrict__ yse, const int* __restrict__ Sx,
     const int* __restrict__ Ix, const double* __restrict__ Bc, const double* __restrict__ pa, const double* __restrict__ psiW,
     const double* __restrict__ W, const double* __restrict__ pm, const double2* __restrict__ logtab, double* __restrict__ val_part,
-    double* __restrict__ psi_part, double* __restrict__ col_part, double* __restrict__ rowsum_part) {
+    double* __restrict__ psi_part, double* __restrict__ col_part, double* __restrict__ rowsum_part, const ll_coefs K) {
   constexpr int MB = NTHR * MPT;  // metapopulations per CTA
   constexpr int DAY_BYTES = MB * 20;         // yse | S | I (int32) | Bc (f64)
   constexpr int STAGE_BYTES = DAY_BYTES * LL_STAGE_DAYS;
+  constexpr int NCW = NTHR / 32;             // consumer warps
   extern __shared__ __align__(128) unsigned char smraw[];
-  __shared__ uint64_t full[NSTAGE];
+  __shared__ uint64_t full[NSTAGE], empty[NSTAGE];
   __shared__ double2 tab[128];
   __shared__ double red[32];
   double* sm = reinterpret_cast<double*>(smraw + (size_t)NSTAGE * STAGE_BYTES);
@@ -286,95 +320,83 @@ __global__ void __launch_bounds__(NTHR, NTHR >= 384 ? (GRAD ? 2 : 3) : 1) seir_l
   const int tb = blockIdx.z * dps, nt = min(dps, T - tb);
   const int ngroups = (nt + LL_STAGE_DAYS - 1) / LL_STAGE_DAYS;
   const int cstride = dps + LL_UNROLL;
+  const bool producer = warp == NCW;
 
-  auto issue = [&](int g, int st) {  // elected thread: arm the barrier, then 4 bulk copies per day of the group
-    const int days = min(LL_STAGE_DAYS, nt - g * LL_STAGE_DAYS);
-    mbar_expect_tx(&full[st], (unsigned)(days * DAY_BYTES));
-    for (int d = 0; d < days; ++d) {
-      const size_t o = ((size_t)b * T + tb + g * LL_STAGE_DAYS + d) * Mp + mb0;
-      unsigned char* dst = smraw + (size_t)st * STAGE_BYTES + (size_t)d * DAY_BYTES;
-      bulk_load_1d(dst, yse + o, MB * 4, &full[st]);
-      bulk_load_1d(dst + MB * 4, Sx + o, MB * 4, &full[st]);
-      bulk_load_1d(dst + MB * 8, Ix + o, MB * 4, &full[st]);
-      bulk_load_1d(dst + MB * 12, Bc + o, MB * 8, &full[st]);
-    }
-  };
   if (tid == 0) {
-    for (int st = 0; st < NSTAGE; ++st) mbar_init(&full[st], 1);
+    for (int st = 0; st < NSTAGE; ++st) {
+      mbar_init(&full[st], 1);
+      mbar_init(&empty[st], NCW);
+    }
     asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
-    for (int g = 0; g < NSTAGE && g < ngroups; ++g) issue(g, g);
   }
   if (tid < 128) tab[tid] = logtab[tid];
-  for (int t = tid; t < nt; t += NTHR) {
+  for (int t = tid; t < nt; t += NTHR + 32) {
     pa_s[t] = pa[(size_t)b * T + tb + t];
     pw_s[t] = psiW[(size_t)b * T + tb + t];
     if (GRAD) w_s[t] = W[tb + t];
   }
-  double pm_m[MPT], row[MPT];
-#pragma unroll
-  for (int q = 0; q < MPT; ++q) {
-    pm_m[q] = pm[(size_t)b * Mp + mb0 + tid + q * NTHR];
-    row[q] = 0.0;
-  }
   __syncthreads();  // barriers initialised, tables staged
 
   double val = 0.0, psig = 0.0;
-  for (int g = 0; g < ngroups; ++g) {
-    const int st = g % NSTAGE;
-    mbar_wait(&full[st], (unsigned)((g / NSTAGE) & 1));
-    const unsigned char* stage = smraw + (size_t)st * STAGE_BYTES;
-    double colv[LL_UNROLL];
+  double row[MPT];
 #pragma unroll
-    for (int j = 0; j < LL_UNROLL; ++j) {
-      const int t = g * LL_STAGE_DAYS + j;
-      colv[j] = 0.0;
-      if (t < nt) {
-        const int* sy = reinterpret_cast<const int*>(stage + (size_t)j * DAY_BYTES);
-        const int* sS = sy + MB;
-        const int* sI = sy + 2 * MB;
-        const double* sB = reinterpret_cast<const double*>(sy + 3 * MB);
-        const double pat = pa_s[t], pwt = pw_s[t];
-#pragma unroll
-        for (int q = 0; q < MPT; ++q) {
-          const int k = tid + q * NTHR;
-          const int y = sy[k], S = sS[k], I = sI[k];
-          const double bc = sB[k];
-          const double e = pat * pm_m[q];
-          const double X = (double)I + pwt * bc;
-          const double lam = fma(e, X, eps);
-          const double x = lam * dt;
-          const double yd = (double)y, rd = (double)(S - y);
-          double term = -rd * x;
-          double gg = -rd;
-          double lg, rc;
-          if (x < LL_SMALL_X && fast_log_rcp<GRAD>(x, tab, lg, rc)) {
-            const double x2 = x * x;
-            if (y > 0) {
-              term += yd * (lg + fma(x2, fma(x2, fma(x2, 5.511463844797178e-06, -3.472222222222222e-04), 0.041666666666666664), -0.5 * x));
-              if (GRAD) gg += yd * (rc - 0.5 + x * fma(x2, fma(x2, 3.306878306878307e-05, -1.388888888888889e-03), 0.08333333333333333));
-            }
-          } else {
-            const double em = expm1(-x);
-            if (y > 0) term += yd * log(-em);
-            if (GRAD && y > 0) gg += yd * (1.0 + em) / (-em);
-          }
-          val += term;
-          if (GRAD) {
-            gg *= dt;
-            const double h = gg * (lam - eps);
-            row[q] += h;
-            psig += gg * e * w_s[t] * bc;
-            colv[j] += h;
-          }
+  for (int q = 0; q < MPT; ++q) row[q] = 0.0;
+  if (producer) {
+    if (lane == 0) {
+      for (int g = 0; g < ngroups; ++g) {
+        const int st = g % NSTAGE;
+        if (g >= NSTAGE) mbar_wait(&empty[st], (unsigned)((g / NSTAGE - 1) & 1));
+        const int days = min(LL_STAGE_DAYS, nt - g * LL_STAGE_DAYS);
+        mbar_expect_tx(&full[st], (unsigned)(days * DAY_BYTES));
+        for (int d = 0; d < days; ++d) {  // 4 bulk copies per day of the group
+          const size_t o = ((size_t)b * T + tb + g * LL_STAGE_DAYS + d) * Mp + mb0;
+          unsigned char* dst = smraw + (size_t)st * STAGE_BYTES + (size_t)d * DAY_BYTES;
+          bulk_load_1d(dst, yse + o, MB * 4, &full[st]);
+          bulk_load_1d(dst + MB * 4, Sx + o, MB * 4, &full[st]);
+          bulk_load_1d(dst + MB * 8, Ix + o, MB * 4, &full[st]);
+          bulk_load_1d(dst + MB * 12, Bc + o, MB * 8, &full[st]);
         }
       }
     }
-    if (GRAD) {
-      const double tot = warp_sum4_transposed(colv);
-      if ((lane & 7) == 0) colw[warp * cstride + g * LL_STAGE_DAYS + ((lane >> 4) & 1) * 2 + ((lane >> 3) & 1)] = tot;
+  } else {
+    double pm_m[MPT];
+#pragma unroll
+    for (int q = 0; q < MPT; ++q) pm_m[q] = pm[(size_t)b * Mp + mb0 + tid + q * NTHR];
+    for (int g = 0; g < ngroups; ++g) {
+      const int st = g % NSTAGE;
+      mbar_wait(&full[st], (unsigned)((g / NSTAGE) & 1));
+      const unsigned char* stage = smraw + (size_t)st * STAGE_BYTES;
+      double colv[LL_UNROLL];
+#pragma unroll
+      for (int j = 0; j < LL_UNROLL; ++j) {
+        const int t = g * LL_STAGE_DAYS + j;
+        colv[j] = 0.0;
+        if (t < nt) {
+          const int* sy = reinterpret_cast<const int*>(stage + (size_t)j * DAY_BYTES);
+          const int* sS = sy + MB;
+          const int* sI = sy + 2 * MB;
+          const double* sB = reinterpret_cast<const double*>(sy + 3 * MB);
+          const double pat = pa_s[t], pwt = pw_s[t];
+#pragma unroll
+          for (int q = 0; q < MPT; ++q) {
+            const int k = tid + q * NTHR;
+            double h = 0.0, gebc = 0.0;
+            ll_cell<GRAD>(sy[k], sS[k], sI[k], sB[k], pat * pm_m[q], pwt, dt, eps, tab, K, val, h, gebc);
+            if (GRAD) {
+              row[q] += h;
+              psig = fma(w_s[t], gebc, psig);
+              colv[j] += h;
+            }
+          }
+        }
+      }
+      __syncwarp();
+      if (lane == 0) mbar_arrive(&empty[st]);  // this warp is done reading the stage
+      if (GRAD) {
+        const double tot = warp_sum4_transposed(colv);
+        if ((lane & 7) == 0) colw[warp * cstride + g * LL_STAGE_DAYS + ((lane >> 4) & 1) * 2 + ((lane >> 3) & 1)] = tot;
+      }
     }
-    __syncthreads();  // every thread is done reading this stage: it may be refilled
-    if (tid == 0 && g + NSTAGE < ngroups) issue(g + NSTAGE, st);
   }
   const int slot = blockIdx.z * gridDim.x + blockIdx.x, nslot = gridDim.x * gridDim.z;
   const double v = block_sum(val, red);
@@ -382,13 +404,15 @@ __global__ void __launch_bounds__(NTHR, NTHR >= 384 ? (GRAD ? 2 : 3) : 1) seir_l
   if (GRAD) {
     const double pg = block_sum(psig, red);
     if (tid == 0) psi_part[(size_t)b * nslot + slot] = pg;
+    if (!producer) {
 #pragma unroll
-    for (int q = 0; q < MPT; ++q) rowsum_part[((size_t)b * gridDim.z + blockIdx.z) * Mp + mb0 + tid + q * NTHR] = row[q];
+      for (int q = 0; q < MPT; ++q) rowsum_part[((size_t)b * gridDim.z + blockIdx.z) * Mp + mb0 + tid + q * NTHR] = row[q];
+    }
     __syncthreads();
-    for (int t = tid; t < nt; t += NTHR) {
+    for (int t = tid; t < nt; t += NTHR + 32) {
       double cta = 0.0;
 #pragma unroll
-      for (int w = 0; w < NTHR / 32; ++w) cta += colw[w * cstride + t];
+      for (int w = 0; w < NCW; ++w) cta += colw[w * cstride + t];
       col_part[((size_t)b * gridDim.x + blockIdx.x) * T + tb + t] = cta;
     }
   }
@@ -397,7 +421,7 @@ __global__ void __launch_bounds__(NTHR, NTHR >= 384 ? (GRAD ? 2 : 3) : 1) seir_l
 #define LL_TMA_STAGES 2
 
 typedef void (*loglik_fn)(int, int, int, double, double, const int*, const int*, const int*, const double*, const double*,
-                          const double*, const double*, const double*, const double2*, double*, double*, double*, double*);
+                          const double*, const double*, const double*, const double2*, double*, double*, double*, double*, const ll_coefs);
 
 struct loglik_cfg {
   bool tma;
@@ -483,7 +507,7 @@ static int choose_dps(const seir_chains* c, bool grad, const loglik_cfg& k, logl
   const int T = c->model->T;
   const size_t smem = loglik_smem(grad, k.tma ? 16 : (grad ? 32 : 16), k);
   if (smem > 48 * 1024) cudaFuncSetAttribute(fn, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
-  cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per, fn, k.threads, smem);
+  cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per, fn, k.tma ? k.threads + 32 : k.threads, smem);
   const long long slots = (long long)sms * (per > 0 ? per : 1);
   const long long base = (long long)k.nblk * c->B;
   const int cap = (T + 3) / 4 < SEIR_MAX_SPLITS ? (T + 3) / 4 : SEIR_MAX_SPLITS;
@@ -507,8 +531,8 @@ int seir_launch_loglik(seir_chains* c, bool grad, cudaStream_t s) {
   dim3 grid(k.nblk, c->B, nts);
   const size_t smem = loglik_smem(grad, dps, k);
   if (smem > 48 * 1024) SEIR_CUDA(cudaFuncSetAttribute(fn, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
-  fn<<<grid, k.threads, smem, s>>>(m->T, m->Mp, dps, m->dt, m->rate_eps, c->d_yse, c->d_S, c->d_I, c->d_Bc, c->d_pa, c->d_psiW,
-                                   m->d_W, c->d_pm, m->d_logtab, c->d_val_part, c->d_psi_part, c->d_col_part, c->d_rowsum);
+  fn<<<grid, k.tma ? k.threads + 32 : k.threads, smem, s>>>(m->T, m->Mp, dps, m->dt, m->rate_eps, c->d_yse, c->d_S, c->d_I, c->d_Bc, c->d_pa, c->d_psiW,
+                                   m->d_W, c->d_pm, m->d_logtab, c->d_val_part, c->d_psi_part, c->d_col_part, c->d_rowsum, LL_COEFS);
   seir_count_launch(1);
   return seir_cuda_check(cudaGetLastError(), "seir_loglik_kernel");
 }
