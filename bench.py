@@ -322,8 +322,12 @@ def run_native(args):
             "config": {"workload": f"uk_{M_UK}x{T_UK}_b{B}", "chains_per_gpu": B, "M": M_UK, "T": T_UK, "transitions": 3,
                        "eval": "cold joint log-prob (nothing cached)", "l2": "inputs larger than L2 (events 197 MB + caches 264 MB per step at B=256)",
                        "parallelism": f"chains x{world}"},
-            "e2e": {"value": e2e_value, "unit": UNIT, "h2d_bytes_per_step": int(events_h.numel() * 8 + theta_h.numel() * 8),
-                    "d2h_bytes_per_step": int(out_h.numel() * 8)},
+            "e2e": {"value": e2e_value, "unit": UNIT, "h2d_bytes_per_step": int(eng.last_h2d_bytes(B)),
+                    "d2h_bytes_per_step": int(out_h.numel() * 8),
+                    "host_input_bytes_per_step": int(events_h.numel() * 8 + theta_h.numel() * 8),
+                    "note": "float64 host events [B,M,T,3] in, log-prob [B] out, through seir_log_prob_host: the host pool narrows chunks "
+                            "to uint16 (exact) from the front while float64 chunks travel from the back; h2d_bytes_per_step = bytes "
+                            "actually shipped in the last timed call (the split is dynamic)"},
             "gpu_launches": int(launches),
             "clocks": clocks,
             "roofline": roofline,

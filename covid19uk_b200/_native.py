@@ -81,6 +81,7 @@ SIGNATURES = {
     "seir_log_prob_cached": (c_int, [c_void_p, c_void_p, c_int, c_int, c_void_p, c_void_p]),
     "seir_log_prob": (c_int, [c_void_p, c_void_p, c_void_p, c_int, c_int, c_void_p, c_void_p]),
     "seir_log_prob_host": (c_int, [c_void_p, c_void_p, c_void_p, c_int, c_int, c_void_p]),
+    "seir_last_h2d_bytes": (c_int64, [c_void_p]),
     "seir_log_prob_grad_cached": (c_int, [c_void_p, c_void_p, c_int, c_int, c_void_p, c_void_p, c_void_p]),
     "seir_run_stage": (c_int, [c_void_p, c_int, c_void_p, c_void_p, c_int, c_int, c_void_p, c_void_p, c_void_p]),
     "seir_prepare_theta": (c_int, [c_void_p, c_void_p, c_int, c_void_p]),

@@ -18,7 +18,8 @@ HERE = os.path.dirname(os.path.abspath(__file__))
 CSRC = os.path.join(HERE, "csrc")
 LIBDIR = os.path.join(HERE, "lib")
 LIBNAME = "libseir_b200.so"
-SOURCES = ["seir_api.cu", "ingest.cu", "contract.cu", "loglik.cu", "delta.cu", "hmc.cu", "propose.cu", "sweep.cu"]
+SOURCES = ["seir_api.cu", "ingest.cu", "contract.cu", "loglik.cu", "delta.cu", "hmc.cu", "propose.cu", "sweep.cu", "host_pack.cpp"]
+CXX_FLAGS = ["-O3", "-std=c++17", "-fPIC", "-pthread"]
 NVCC_FLAGS = [
     "-O3",
     "-std=c++17",
@@ -64,11 +65,14 @@ def build(force: bool = False, verbose: bool = False) -> str:
     srcs = _sources()
 
     def compile_one(src):
-        obj = os.path.join(objdir, src.replace(".cu", ".o"))
+        obj = os.path.join(objdir, os.path.splitext(src)[0] + ".o")
         path = os.path.join(CSRC, src)
         if not force and not _stale(obj, [path] + headers):
             return obj, ""
-        cmd = [nvcc] + NVCC_FLAGS + ["-c", path, "-o", obj]
+        if src.endswith(".cpp"):  # plain host code: g++ directly (function multiversioning attributes are not nvcc-friendly)
+            cmd = [os.environ.get("CXX", "g++")] + CXX_FLAGS + ["-c", path, "-o", obj]
+        else:
+            cmd = [nvcc] + NVCC_FLAGS + ["-c", path, "-o", obj]
         res = subprocess.run(cmd, capture_output=True, text=True)
         if res.returncode != 0:
             raise RuntimeError(f"nvcc failed for {src}:\n{res.stdout}\n{res.stderr}")
@@ -84,7 +88,7 @@ def build(force: bool = False, verbose: bool = False) -> str:
         print(log, file=sys.stderr)
     target = lib_path()
     if force or _stale(target, objs):
-        cmd = [nvcc, "-shared", "-gencode", "arch=compute_100a,code=sm_100a", "-o", target] + objs
+        cmd = [nvcc, "-shared", "-gencode", "arch=compute_100a,code=sm_100a", "-Xcompiler", "-pthread", "-o", target] + objs
         res = subprocess.run(cmd, capture_output=True, text=True)
         if res.returncode != 0:
             raise RuntimeError(f"link failed:\n{res.stdout}\n{res.stderr}")

@@ -1,0 +1,187 @@
+// Host side of seir_log_prob_host (seir_api.cu): a small persistent thread pool that narrows the caller's float64
+// event tensor (integer-valued counts, model_spec.py:118-126) to uint16 in pinned staging memory, so that the PCIe
+// transfer carries 2 bytes per count instead of 8.  The narrowing is exact or refused: a block holding any value that
+// is not an integer in [0, 65535] is reported and the caller ships that block as float64 instead (the device-side
+// ingest then flags invalid events exactly as it does for device-resident input).
+//
+// Plain C++ (g++), no CUDA: compiled separately and linked into libseir_b200.so.
+#include <stdint.h>
+#include <stddef.h>
+
+#include <atomic>
+#include <condition_variable>
+#include <mutex>
+#include <thread>
+#include <vector>
+
+namespace {
+
+// exact double -> uint16 narrowing of n values; returns false if any value is not representable
+__attribute__((target_clones("avx512f", "avx2", "default"))) bool pack_block(const double* __restrict__ src, uint16_t* __restrict__ dst, size_t n) {
+  int bad = 0;
+  for (size_t i = 0; i < n; ++i) {
+    const double v = src[i];
+    const int32_t k = (int32_t)v;  // (vectorises: cvttpd2dq; out-of-range / NaN give INT_MIN => caught below)
+    bad |= (k < 0) | (k > 65535) | ((double)k != v);
+    dst[i] = (uint16_t)k;
+  }
+  return bad == 0;
+}
+
+struct Pool {
+  std::vector<std::thread> workers;
+  std::mutex mu;
+  std::condition_variable cv;
+  uint64_t generation = 0;
+  bool stop = false;
+  // current batch
+  const double* src = nullptr;
+  uint16_t* dst = nullptr;
+  size_t chunk_elems = 0, job_elems = 0, total_elems = 0;
+  int njobs = 0, jobs_per_chunk = 1;
+  std::atomic<int> next{0};
+  std::atomic<int> active{0};  // workers inside run_jobs (a new batch waits for stragglers of the previous one)
+  std::atomic<int>* chunk_done = nullptr;  // finished jobs per chunk
+  std::atomic<int>* chunk_bad = nullptr;
+  std::atomic<int>* chunk_owner = nullptr;  // 0 free, 1 pool (being narrowed), 2 caller (shipped as float64)
+
+  void run_jobs() {
+    for (;;) {
+      const int j = next.fetch_add(1, std::memory_order_relaxed);
+      if (j >= njobs) return;
+      const int ch = j / jobs_per_chunk;
+      int own = chunk_owner[ch].load(std::memory_order_acquire);
+      if (own == 0) {
+        int expect = 0;
+        own = chunk_owner[ch].compare_exchange_strong(expect, 1, std::memory_order_acq_rel) ? 1 : expect;
+      }
+      if (own == 2) return;  // the caller claims chunks from the back: this one and all later ones go as float64
+      const size_t within = (size_t)(j - ch * jobs_per_chunk) * job_elems;  // jobs never straddle chunks
+      size_t n = within + job_elems <= chunk_elems ? job_elems : chunk_elems - within;
+      const size_t o = (size_t)ch * chunk_elems + within;
+      if (o >= total_elems) n = 0;
+      else if (o + n > total_elems) n = total_elems - o;  // the last chunk may be short
+      const bool ok = pack_block(src + o, dst + o, n);
+      if (!ok) chunk_bad[ch].store(1, std::memory_order_relaxed);
+      chunk_done[ch].fetch_add(1, std::memory_order_release);
+    }
+  }
+
+  void worker() {
+    uint64_t seen = 0;
+    for (;;) {
+      {
+        std::unique_lock<std::mutex> lk(mu);
+        cv.wait(lk, [&] { return stop || generation != seen; });
+        if (stop) return;
+        seen = generation;
+        active.fetch_add(1, std::memory_order_acq_rel);
+      }
+      run_jobs();
+      active.fetch_sub(1, std::memory_order_acq_rel);
+    }
+  }
+
+  explicit Pool(int n) {
+    for (int i = 0; i < n; ++i) workers.emplace_back([this] { worker(); });
+  }
+  ~Pool() {
+    {
+      std::lock_guard<std::mutex> lk(mu);
+      stop = true;
+    }
+    cv.notify_all();
+    for (auto& t : workers) t.join();
+  }
+};
+
+Pool* g_pool = nullptr;
+std::vector<std::atomic<int>>* g_done = nullptr;
+std::vector<std::atomic<int>>* g_bad = nullptr;
+std::vector<std::atomic<int>>* g_owner = nullptr;
+
+}  // namespace
+
+extern "C" {
+
+int seir_pack_threads(void) {
+  unsigned hc = std::thread::hardware_concurrency();
+  if (hc == 0) hc = 4;
+  int n = (int)hc - 1;  // the calling thread drives the copies
+  if (n < 1) n = 1;
+  if (n > 32) n = 32;
+  return n;
+}
+
+// Start narrowing `nchunks` chunks of `chunk_elems` values each (the last one may be short: `total_elems` in all),
+// src -> dst at the same element offsets, front to back.  Returns at once with the number of jobs per chunk.
+//   seir_pack_poll(chunk, jpc)   -1 not finished, 1 narrowed exactly, 0 holds a value outside uint16
+//   seir_pack_wait(chunk, jpc)   blocking form of poll
+//   seir_pack_claim_raw(chunk)   1: the caller now owns the chunk (ships it as float64 itself, the pool will not touch
+//                                it nor any later chunk); 0: the pool got there first
+// One batch at a time (the chain-set handle is not thread-safe anyway).
+int seir_pack_begin(const double* src, uint16_t* dst, size_t chunk_elems, size_t total_elems, int nchunks) {
+  if (!g_pool) g_pool = new Pool(seir_pack_threads());
+  if (!g_done || (int)g_done->size() < nchunks) {
+    delete g_done;
+    delete g_bad;
+    delete g_owner;
+    g_done = new std::vector<std::atomic<int>>(nchunks);
+    g_bad = new std::vector<std::atomic<int>>(nchunks);
+    g_owner = new std::vector<std::atomic<int>>(nchunks);
+  }
+  Pool& p = *g_pool;
+  while (p.active.load(std::memory_order_acquire) != 0) std::this_thread::yield();  // stragglers of the previous batch
+  const int nthreads = (int)p.workers.size();
+  int jpc = (2 * nthreads + nchunks - 1) / nchunks;  // every thread gets work on the EARLIEST chunk first
+  if (jpc < 1) jpc = 1;
+  size_t job = (chunk_elems + jpc - 1) / jpc;
+  job = (job + 63) / 64 * 64;
+  jpc = (int)((chunk_elems + job - 1) / job);
+  // jobs must not straddle chunks: lay them out per chunk
+  for (int c = 0; c < nchunks; ++c) {
+    (*g_done)[c].store(0, std::memory_order_relaxed);
+    (*g_bad)[c].store(0, std::memory_order_relaxed);
+    (*g_owner)[c].store(0, std::memory_order_relaxed);
+  }
+  {
+    std::lock_guard<std::mutex> lk(p.mu);
+    p.src = src;
+    p.dst = dst;
+    p.chunk_elems = chunk_elems;
+    p.total_elems = total_elems;
+    p.chunk_owner = g_owner->data();
+    p.job_elems = job;
+    p.jobs_per_chunk = jpc;
+    p.njobs = jpc * nchunks;
+    p.chunk_done = g_done->data();
+    p.chunk_bad = g_bad->data();
+    p.next.store(0, std::memory_order_relaxed);
+    ++p.generation;
+  }
+  p.cv.notify_all();
+  return jpc;
+}
+
+int seir_pack_poll(int chunk, int jobs_per_chunk) {
+  if ((*g_done)[chunk].load(std::memory_order_acquire) < jobs_per_chunk) return -1;
+  return (*g_bad)[chunk].load(std::memory_order_relaxed) ? 0 : 1;
+}
+
+int seir_pack_claim_raw(int chunk) {
+  int expect = 0;
+  return (*g_owner)[chunk].compare_exchange_strong(expect, 2, std::memory_order_acq_rel) ? 1 : 0;
+}
+
+int seir_pack_owner(int chunk) { return (*g_owner)[chunk].load(std::memory_order_acquire); }
+
+int seir_pack_wait(int chunk, int jobs_per_chunk) {
+  std::atomic<int>& d = (*g_done)[chunk];
+  unsigned spins = 0;
+  while (d.load(std::memory_order_acquire) < jobs_per_chunk) {
+    if (++spins > 64) std::this_thread::yield();
+  }
+  return (*g_bad)[chunk].load(std::memory_order_relaxed) ? 0 : 1;
+}
+
+}  // extern "C"

@@ -73,9 +73,9 @@ int seir_launch_state(const seir_model* m, int B, const double* d_events, double
 // The FP64 work (log binomial coefficients) lives in seir_coef_kernel below: ncu on the fused version
 // showed 16/32 active lanes (table-vs-Stirling divergence) and 37 % occupancy (profiles/r01_v2_*).
 // ------------------------------------------------------------------------------------------------
-template <int TC>
-__global__ void __launch_bounds__(256) seir_ingest_kernel(int M, int T, int Mp, const int* __restrict__ init,
-                                                          const double* __restrict__ events, int* __restrict__ yse,
+template <int TC, typename EV>
+__global__ void __launch_bounds__(256) seir_ingest_kernel(int M, int T, int Mp, int b0, const int* __restrict__ init,
+                                                          const EV* __restrict__ events, int* __restrict__ yse,
                                                           int* __restrict__ yei, int* __restrict__ yir, int* __restrict__ Sx,
                                                           int* __restrict__ Ex, int* __restrict__ Ix, long long* __restrict__ Yir,
                                                           long long* __restrict__ Rir, long long* __restrict__ sumYei,
@@ -86,7 +86,7 @@ __global__ void __launch_bounds__(256) seir_ingest_kernel(int M, int T, int Mp, 
   int* ev = smem_i;                    // [32][STRIDE]
   int* segsum = smem_i + 32 * STRIDE;  // [8][3][32]
 
-  const int b = blockIdx.y, m0 = blockIdx.x * 32;
+  const int b = b0 + blockIdx.y, m0 = blockIdx.x * 32;
   const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
   const int m = m0 + lane;
   const int S0 = init[m * 4 + 0], E0 = init[m * 4 + 1], I0 = init[m * 4 + 2];
@@ -100,13 +100,17 @@ __global__ void __launch_bounds__(256) seir_ingest_kernel(int M, int T, int Mp, 
     // ---- load ----
     for (int r = warp; r < 32; r += 8) {
       const int mm = m0 + r;
-      const double* src = events + (((size_t)b * M + mm) * T + t0) * 3;
+      const EV* src = events + (((size_t)b * M + mm) * T + t0) * 3;
       for (int k = lane; k < tc * 3; k += 32) {
         int iv = 0;
         if (mm < M) {
-          const double v = __ldg(src + k);
-          iv = __double2int_rn(v);
-          if ((double)iv != v || iv < 0) bad |= 1;
+          if (sizeof(EV) == sizeof(double)) {
+            const double v = (double)__ldg(src + k);
+            iv = __double2int_rn(v);
+            if ((double)iv != v || iv < 0) bad |= 1;
+          } else {
+            iv = (int)__ldg(src + k);  // uint16 counts narrowed (exactly) by the host packer
+          }
         }
         ev[r * STRIDE + k] = iv;
       }
@@ -173,31 +177,48 @@ __global__ void __launch_bounds__(256) seir_ingest_kernel(int M, int T, int Mp, 
   if (lane == 0 && bad) atomicOr(flags + b, bad);
 }
 
-template <int TC>
-static int launch_ingest_tc(seir_chains* c, const double* d_events, cudaStream_t s) {
+template <int TC, typename EV>
+static int launch_ingest_tc(seir_chains* c, const EV* d_events, int b0, int nb, cudaStream_t s) {
   const seir_model* m = c->model;
   const size_t smem = sizeof(int) * (32 * (TC * 3 + 1) + 8 * 3 * 32);
   static bool attr_set = false;
   if (!attr_set) {
-    SEIR_CUDA(cudaFuncSetAttribute(seir_ingest_kernel<TC>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+    SEIR_CUDA(cudaFuncSetAttribute(seir_ingest_kernel<TC, EV>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
     attr_set = true;
   }
-  dim3 grid(c->nblk32, c->B);
-  seir_ingest_kernel<TC><<<grid, 256, smem, s>>>(m->M, m->T, m->Mp, m->d_init, d_events, c->d_yse, c->d_yei, c->d_yir, c->d_S,
-                                                 c->d_E, c->d_I, c->d_Yir, c->d_Rir, c->d_sumYei, c->d_sumEres, c->d_flags, c->d_nzd);
+  dim3 grid(c->nblk32, nb);
+  seir_ingest_kernel<TC, EV><<<grid, 256, smem, s>>>(m->M, m->T, m->Mp, b0, m->d_init, d_events, c->d_yse, c->d_yei, c->d_yir, c->d_S,
+                                                     c->d_E, c->d_I, c->d_Yir, c->d_Rir, c->d_sumYei, c->d_sumEres, c->d_flags, c->d_nzd);
   seir_count_launch(1);
   return seir_cuda_check(cudaGetLastError(), "seir_ingest_kernel");
 }
 
-int seir_launch_ingest(seir_chains* c, const double* d_events, cudaStream_t s) {
-  const int B = c->B, T = c->model->T;
+// zero every accumulator the ingest kernels add into (before the first chain range of a new event tensor)
+int seir_ingest_reset(seir_chains* c, cudaStream_t s) {
+  const int B = c->B;
   // one memset over the contiguous integer-statistics block [Yir | Rir | sumYei | sumEres | flags]
   SEIR_CUDA(cudaMemsetAsync(c->d_Yir, 0, c->stats_bytes, s));
   SEIR_CUDA(cudaMemsetAsync(c->d_llc_adj, 0, sizeof(double) * (size_t)B, s));
   SEIR_CUDA(cudaMemsetAsync(c->d_nzd, 0, sizeof(int) * (size_t)B * 2 * c->model->Mp, s));
   // new events = freshly bootstrapped kernels: no proposal has been accepted yet (MetropolisHastings accepted_results)
   SEIR_CUDA(cudaMemsetAsync(c->d_last_acc, 0, sizeof(int) * (size_t)4 * B * 4 * SEIR_MMAX, s));
-  return (T <= 96) ? launch_ingest_tc<96>(c, d_events, s) : launch_ingest_tc<128>(c, d_events, s);
+  return SEIR_OK;
+}
+
+// chains [b0, b0 + nb) of an event tensor whose chain 0 is at d_events (float64) / d_events_u16 (exactly one non-NULL)
+int seir_launch_ingest_range(seir_chains* c, const double* d_events, const unsigned short* d_events_u16, int b0, int nb,
+                             cudaStream_t s) {
+  const int T = c->model->T;
+  if (d_events_u16)
+    return (T <= 96) ? launch_ingest_tc<96, unsigned short>(c, d_events_u16, b0, nb, s)
+                     : launch_ingest_tc<128, unsigned short>(c, d_events_u16, b0, nb, s);
+  return (T <= 96) ? launch_ingest_tc<96, double>(c, d_events, b0, nb, s) : launch_ingest_tc<128, double>(c, d_events, b0, nb, s);
+}
+
+int seir_launch_ingest(seir_chains* c, const double* d_events, cudaStream_t s) {
+  int rc = seir_ingest_reset(c, s);
+  if (rc != SEIR_OK) return rc;
+  return seir_launch_ingest_range(c, d_events, nullptr, 0, c->B, s);
 }
 
 // ------------------------------------------------------------------------------------------------

@@ -230,7 +230,13 @@ void seir_chains_destroy(seir_chains* c) {
   cudaFree(c->d_col_part); cudaFree(c->d_rowsum); cudaFree(c->d_upd); cudaFree(c->d_upd_part); cudaFree(c->d_llc_adj);
   cudaFree(c->d_tlp); cudaFree(c->d_last_acc); cudaFree(c->d_nzd); cudaFree(c->d_hmc_u0); cudaFree(c->d_hmc_p); cudaFree(c->d_hmc_grad);
   cudaFree(c->d_hmc_val); cudaFree(c->d_prop); cudaFree(c->d_logu); cudaFree(c->d_stage_events); cudaFree(c->d_stage_theta);
-  cudaFree(c->d_stage_out);
+  cudaFree(c->d_stage_out); cudaFree(c->d_stage_u16);
+  if (c->h_stage_u16) cudaFreeHost(c->h_stage_u16);
+  if (c->copy_stream) cudaStreamDestroy(c->copy_stream);
+  if (c->stage_ev) {
+    for (int k = 0; k < c->stage_nchunks; ++k) cudaEventDestroy(c->stage_ev[k]);
+    delete[] c->stage_ev;
+  }
   delete c;
 }
 
@@ -298,24 +304,101 @@ int seir_log_prob(seir_chains* c, const double* d_events, const double* d_theta,
   return seir_log_prob_cached(c, d_theta, kind, parts, d_out, stream);
 }
 
+// host packer (host_pack.cpp)
+int seir_pack_begin(const double* src, unsigned short* dst, size_t chunk_elems, size_t total_elems, int nchunks);
+int seir_pack_poll(int chunk, int jobs_per_chunk);
+int seir_pack_claim_raw(int chunk);
+int seir_pack_owner(int chunk);
+
+#define SEIR_HOST_CHUNKS 16
+
+// Host-buffer entry point.  The event tensor is the whole transfer (8 B per count, 198 MB at the UK size with 256
+// chains, vs 1.2 ms of device work), so the chains are cut into chunks that travel two ways at once:
+//   * from the FRONT the host thread pool narrows chunks to uint16 (exact, or the chunk is refused) into pinned staging;
+//     a narrowed chunk is a quarter of the bytes on the link;
+//   * from the BACK the calling thread ships chunks as they are (float64), at most two in flight, so the link is busy
+//     while the cores narrow.
+// Each chunk's ingest kernel runs as soon as its copy lands (event-ordered on the compute stream); the events-wide
+// kernels (coefficients, contraction) and the theta-dependent half follow once every chunk is in.
 int seir_log_prob_host(seir_chains* c, const double* h_events, const double* h_theta, int kind, int parts, double* h_out) {
   if (!c || !h_events || !h_theta || !h_out) return seir_set_error(SEIR_ERR_BAD_ARG, "seir_log_prob_host: NULL argument");
+  SEIR_TRY(check_parts(kind, parts));
   const seir_model* m = c->model;
   SEIR_CUDA(cudaSetDevice(m->device));
-  const size_t ne = (size_t)c->B * m->M * m->T * 3, nt = (size_t)c->B * m->P;
+  const int B = c->B;
+  const size_t per_chain = (size_t)m->M * m->T * 3, ne = (size_t)B * per_chain, nt = (size_t)B * m->P;
   if (!c->d_stage_events) {
     SEIR_TRY(dev_alloc(&c->d_stage_events, ne, &c->bytes));
     SEIR_TRY(dev_alloc(&c->d_stage_theta, nt, &c->bytes));
-    SEIR_TRY(dev_alloc(&c->d_stage_out, (size_t)c->B, &c->bytes));
+    SEIR_TRY(dev_alloc(&c->d_stage_out, (size_t)B, &c->bytes));
+    SEIR_TRY(dev_alloc(&c->d_stage_u16, ne, &c->bytes));
+    SEIR_CUDA(cudaHostAlloc(reinterpret_cast<void**>(&c->h_stage_u16), ne * sizeof(unsigned short), cudaHostAllocDefault));
+    SEIR_CUDA(cudaStreamCreateWithFlags(&c->copy_stream, cudaStreamNonBlocking));
+    c->stage_nchunks = B < SEIR_HOST_CHUNKS ? B : SEIR_HOST_CHUNKS;
+    c->stage_ev = new cudaEvent_t[c->stage_nchunks];
+    for (int k = 0; k < c->stage_nchunks; ++k) SEIR_CUDA(cudaEventCreateWithFlags(&c->stage_ev[k], cudaEventDisableTiming));
   }
-  cudaStream_t s = cudaStreamPerThread;
-  SEIR_CUDA(cudaMemcpyAsync(c->d_stage_events, h_events, ne * sizeof(double), cudaMemcpyHostToDevice, s));
+  cudaStream_t s = cudaStreamPerThread, cs = c->copy_stream;
   SEIR_CUDA(cudaMemcpyAsync(c->d_stage_theta, h_theta, nt * sizeof(double), cudaMemcpyHostToDevice, s));
-  SEIR_TRY(seir_log_prob(c, c->d_stage_events, c->d_stage_theta, kind, parts, c->d_stage_out, s));
-  SEIR_CUDA(cudaMemcpyAsync(h_out, c->d_stage_out, (size_t)c->B * sizeof(double), cudaMemcpyDeviceToHost, s));
+  c->last_h2d_bytes = (int64_t)(nt * sizeof(double));
+  if (parts & SEIR_PART_SEIR) {
+    const int nch = c->stage_nchunks, cb = (B + nch - 1) / nch;  // chains per chunk (the last chunk may be short)
+    const int jpc = seir_pack_begin(h_events, c->h_stage_u16, (size_t)cb * per_chain, ne, nch);
+    SEIR_TRY(seir_ingest_reset(c, s));
+    int front = 0, back = nch - 1;       // next chunk expected from the pool / next chunk the caller may claim
+    int raw_pending[2] = {-1, -1};       // chunks whose float64 copy is in flight
+    auto ship = [&](int k, bool narrowed) -> int {
+      const int b0 = k * cb, nb = (b0 + cb <= B ? cb : B - b0);
+      if (nb <= 0) return SEIR_OK;
+      const size_t off = (size_t)b0 * per_chain, n = (size_t)nb * per_chain;
+      c->last_h2d_bytes += (int64_t)(n * (narrowed ? sizeof(unsigned short) : sizeof(double)));
+      if (narrowed)
+        SEIR_CUDA(cudaMemcpyAsync(c->d_stage_u16 + off, c->h_stage_u16 + off, n * sizeof(unsigned short), cudaMemcpyHostToDevice, cs));
+      else
+        SEIR_CUDA(cudaMemcpyAsync(c->d_stage_events + off, h_events + off, n * sizeof(double), cudaMemcpyHostToDevice, cs));
+      SEIR_CUDA(cudaEventRecord(c->stage_ev[k], cs));
+      SEIR_CUDA(cudaStreamWaitEvent(s, c->stage_ev[k], 0));
+      return seir_launch_ingest_range(c, narrowed ? nullptr : c->d_stage_events, narrowed ? c->d_stage_u16 : nullptr, b0, nb, s);
+    };
+    bool pool_done = false, claim_done = false;
+    while (!(pool_done && claim_done)) {
+      bool progressed = false;
+      // narrowed chunks, in order
+      while (!pool_done) {
+        if (front > back || seir_pack_owner(front) == 2) { pool_done = true; break; }
+        if (seir_pack_owner(front) != 1) break;  // not started yet
+        const int st = seir_pack_poll(front, jpc);
+        if (st < 0) break;
+        SEIR_TRY(ship(front, st == 1));  // a refused chunk travels as float64; the device-side ingest flags what is wrong with it
+        ++front;
+        progressed = true;
+      }
+      // float64 chunks from the back, at most two copies in flight
+      for (int q = 0; q < 2; ++q)
+        if (raw_pending[q] >= 0 && cudaEventQuery(c->stage_ev[raw_pending[q]]) == cudaSuccess) raw_pending[q] = -1;
+      while (!claim_done && (raw_pending[0] < 0 || raw_pending[1] < 0)) {
+        if (back < front || !seir_pack_claim_raw(back)) { claim_done = true; break; }
+        SEIR_TRY(ship(back, false));
+        raw_pending[raw_pending[0] < 0 ? 0 : 1] = back;
+        --back;
+        progressed = true;
+      }
+      if (!progressed) {
+#if defined(__x86_64__)
+        __builtin_ia32_pause();
+#endif
+      }
+    }
+    SEIR_TRY(seir_launch_coef(c, s));
+    SEIR_TRY(seir_launch_contract(c, s));
+  }
+  SEIR_TRY(seir_log_prob_cached(c, c->d_stage_theta, kind, parts, c->d_stage_out, s));
+  SEIR_CUDA(cudaMemcpyAsync(h_out, c->d_stage_out, (size_t)B * sizeof(double), cudaMemcpyDeviceToHost, s));
   SEIR_CUDA(cudaStreamSynchronize(s));
   return SEIR_OK;
 }
+
+int64_t seir_last_h2d_bytes(const seir_chains* c) { return c ? c->last_h2d_bytes : 0; }
 
 int seir_run_stage(seir_chains* c, int stage, const double* d_events, const double* d_theta, int kind, int parts, double* d_out,
                    double* d_grad, void* stream) {

@@ -118,6 +118,11 @@ struct seir_chains {
   double* d_logu;
   // staging for the host-buffer entry points
   double *d_stage_events, *d_stage_theta, *d_stage_out;
+  unsigned short *d_stage_u16, *h_stage_u16;  // narrowed events: device copy and pinned host staging
+  cudaStream_t copy_stream;
+  cudaEvent_t* stage_ev;                       // one per chain chunk of the host entry point
+  int stage_nchunks;
+  int64_t last_h2d_bytes;
 };
 
 // error plumbing (seir_api.cu)
@@ -134,6 +139,9 @@ void seir_count_launch(int n);
 // kernel launchers (one per .cu file)
 int seir_launch_state(const seir_model* m, int B, const double* d_events, double* d_state, cudaStream_t s);
 int seir_launch_ingest(seir_chains* c, const double* d_events, cudaStream_t s);
+int seir_ingest_reset(seir_chains* c, cudaStream_t s);
+int seir_launch_ingest_range(seir_chains* c, const double* d_events, const unsigned short* d_events_u16, int b0, int nb,
+                             cudaStream_t s);
 int seir_launch_coef(seir_chains* c, cudaStream_t s);
 int seir_launch_contract(seir_chains* c, cudaStream_t s);
 int seir_launch_theta_prep(seir_chains* c, const double* d_theta, int kind, int parts, cudaStream_t s);

@@ -176,6 +176,10 @@ class SeirEngine:
         nat.check(self.lib.seir_log_prob_host(self.chains(B), c_void_p(h_events.data_ptr()), c_void_p(h_theta.data_ptr()), kind, parts, c_void_p(h_out.data_ptr())))
         return h_out
 
+    def last_h2d_bytes(self, B: int) -> int:
+        """Bytes the last log_prob_host call moved host->device (events as shipped + theta)."""
+        return int(self.lib.seir_last_h2d_bytes(self.chains(B)))
+
     def run_stage(self, B, stage, events=None, theta=None, kind=nat.THETA_CONSTRAINED, parts=nat.PART_SEIR, out=None, grad=None):
         """Enqueue one kernel of the pipeline (measurement hook, see seir_run_stage)."""
         ptr = lambda t: c_void_p(t.data_ptr()) if t is not None else c_void_p(0)

@@ -116,9 +116,17 @@ int seir_log_prob(seir_chains* chains, const double* d_events, const double* d_t
                   int parts, double* d_out, void* stream);
 
 /* Same call with HOST buffers: copies events/theta in, evaluates, copies [B] results out and
- * synchronises.  h_events [B,M,T,3], h_theta [B,P], h_out [B].  (bench.py's end-to-end figure.) */
+ * synchronises.  h_events [B,M,T,3], h_theta [B,P], h_out [B].  (bench.py's end-to-end figure.)
+ * The chains travel in chunks, pipelined with their ingest kernels: from the front a host thread pool narrows
+ * integer-valued counts to uint16 (exactly, or the chunk is refused and goes as float64), from the back the
+ * calling thread ships float64 chunks, so PCIe and the host cores work at the same time.  Results are
+ * bit-identical to seir_log_prob on the same data. */
 int seir_log_prob_host(seir_chains* chains, const double* h_events, const double* h_theta, int theta_kind,
                        int parts, double* h_out);
+
+/* Bytes the last seir_log_prob_host call moved host->device (events as shipped -- uint16 where the host pool
+ * narrowed a chunk exactly, float64 otherwise -- plus theta).  Measurement accessor for bench.py's e2e figure. */
+int64_t seir_last_h2d_bytes(const seir_chains* chains);
 
 /* a5 + a9: value and gradient w.r.t. theta of the selected parts against the cached events
  * (TF autodiff through joint_log_prob in the reference; HMC leapfrog, mcmc_kernel_factory.py:20-27).

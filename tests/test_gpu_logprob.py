@@ -129,3 +129,38 @@ def test_model_spec_api(uk_problem):
     st = compute_state(pb["initial_state"], pb["events"][0], model_spec.STOICHIOMETRY)
     assert tuple(st.shape) == (M, T, 4)
     assert np.array_equal(st.cpu().numpy(), so.compute_state(pb["initial_state"], pb["events"][0]))
+
+
+@pytest.mark.parametrize("B", [1, 5, 37])
+def test_host_entry_point_equals_device_path(B):
+    """seir_log_prob_host (chunks narrowed to uint16 by the host pool from the front, float64 chunks from the back) gives
+    bit-identical results to the device-resident path, including chunks the packer must refuse (a count beyond uint16,
+    a non-integer count) and ragged chunking (37 chains over 16 chunks)."""
+    import torch
+    from covid19uk_b200 import _native as nat
+    from covid19uk_b200 import synthetic as syn
+
+    M, T = 48, 40
+    pb = syn.make_problem(M, T, chains=B, seed=5, distinct=min(B, 4))
+    eng = _engine(pb["covariates"], pb["initial_state"], T)
+    ev = pb["events"].copy()
+    if B >= 5:
+        ev[1, int(np.argmax(pb["covariates"]["N"])), 2, 0] = 70000.0   # beyond uint16: the chunk is shipped as float64
+        ev[3, 7, 5, 1] += 0.5      # not an integer: refused by the packer, flagged by the device ingest => -inf
+    th = pb["theta"]
+    kind, parts = nat.THETA_CONSTRAINED, nat.PART_SEIR | nat.PART_PRIORS
+    want = eng.log_prob(ev, th, kind, parts).cpu().numpy()
+    ev_h = torch.from_numpy(np.ascontiguousarray(ev)).pin_memory()
+    th_h = torch.from_numpy(np.ascontiguousarray(th)).pin_memory()
+    out_h = torch.empty(B, dtype=torch.float64).pin_memory()
+    for _ in range(3):  # repeated calls reuse the staging buffers and the pool
+        out_h.fill_(0.0)
+        eng.log_prob_host(ev_h, th_h, out_h, kind, parts)
+        assert np.array_equal(out_h.numpy(), want)
+    if B >= 5:
+        assert want[3] == -np.inf and np.isfinite(want[0]) and np.isfinite(want[2])
+    # pageable (unpinned) host memory works too
+    out2 = torch.empty(B, dtype=torch.float64)
+    eng.log_prob_host(torch.from_numpy(np.ascontiguousarray(ev)), torch.from_numpy(np.ascontiguousarray(th)), out2, kind, parts)
+    assert np.array_equal(out2.numpy(), want)
+    eng.close()
