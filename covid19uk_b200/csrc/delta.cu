@@ -11,13 +11,109 @@
 //   * E->I (target 1): I of the touched metapopulations changes on a range of days => rank-1 update of
 //     the cached contraction Bc with a row of Cs and new S->E terms for EVERY metapopulation on those
 //     days                                                                          (seir_update_slab_kernel)
-// seir_update_commit_kernel takes the MH decision  log u < d(log pi) + log q_rev - log q_fwd  and applies
-// the accepted change to every cache in place (events, state rows, Bc slabs, sufficient statistics).
+// The MH decision  log u < d(log pi) + log q_rev - log q_fwd  and the in-place commit of an accepted change to every
+// cache (events, state rows, Bc slabs, sufficient statistics, event-day counts) happen at the end of the prepare kernel
+// for S->E updates (ONE launch per update) and in seir_update_commit_kernel for E->I updates (three launches).
 //
 // Proposal conventions restated from gemlib ([recall], see oracle/seir_oracle.py move_max_events /
 // occult_delete_max and SURVEY Appendix B.1/B.3): parity unpinned.
 #include "delta_common.cuh"
 #include "propose.cuh"
+
+// ------------------------------------------------------------------------------------------------
+// decide + commit.  accept iff log u < dll + lac  (tfp.mcmc.MetropolisHastings [recall]); on accept the point changes
+// are applied to the event / state rows, the sufficient statistics and the event-day counts.
+//   upd_decide        the MH decision from a prepared record (+ the force-of-infection partials for E->I); pure, so
+//                     every CTA of the fused commit kernel can take it on its own and arrive at the same answer
+//   upd_commit_rows   one CTA per chain (NT threads): outputs + row commit
+//   upd_commit_slabs  E->I only: Bc'[i] = Bc[i] + sum_g Cs[m_g][i] dI_g on the affected day slabs
+// ------------------------------------------------------------------------------------------------
+struct upd_outputs {
+  double* tlp;
+  int* accept;
+  int* last_acc;
+  int* trace;
+  double* dbg;
+};
+
+__device__ __forceinline__ int upd_decide(const seir_upd& u, int target, int nchunk, const double* part_b, double log_u, double* dll_out) {
+  double dll = u.dll_row;
+  if (target == 1)
+    for (int k = 0; k < nchunk; ++k) dll += part_b[k];  // fixed order
+  if (!u.valid || u.neg) dll = -INFINITY;
+  *dll_out = dll;
+  const double ratio = dll + u.lac;  // NaN compares false => reject
+  return (u.valid && !u.neg && log_u < ratio) ? 1 : 0;
+}
+
+template <int NT>
+__device__ __forceinline__ void upd_commit_rows(int b, int T, int Mp, const seir_update_cfg& cfg, const seir_upd& u, int acc, double dll,
+                                                double log_u, seir_upd* upd, const int* prop, int* yse, int* yei, int* Sx, int* Ex,
+                                                int* Ix, long long* Rir, long long* sumYei, long long* sumEres, double* llc_adj,
+                                                int* nzd_all, const upd_outputs& o, long long* redl) {
+  const int tid = threadIdx.x;
+  if (tid == 0) {
+    double prop_tlp = o.tlp[b] + dll;
+    if (!u.valid || u.neg) prop_tlp = -INFINITY;
+    if (acc) {
+      o.tlp[b] = prop_tlp;
+      llc_adj[b] += u.dllc;
+    }
+    upd[b].accept = acc;
+    upd[b].dll = dll;
+    o.accept[b] = acc;
+    if (o.dbg) {
+      o.dbg[(size_t)b * 4 + 0] = dll;
+      o.dbg[(size_t)b * 4 + 1] = u.lac;
+      o.dbg[(size_t)b * 4 + 2] = prop_tlp;
+      o.dbg[(size_t)b * 4 + 3] = dll + u.lac;
+    }
+  }
+  // MetropolisHastings.accepted_results: the last ACCEPTED proposal is what the reference traces
+  if (tid < 4 * SEIR_MMAX) {
+    int* la = o.last_acc + (size_t)b * 4 * SEIR_MMAX;
+    if (acc) la[tid] = prop[(size_t)b * 4 * SEIR_MMAX + tid];
+    if (o.trace) o.trace[(size_t)b * 4 * SEIR_MMAX + tid] = la[tid];
+  }
+  if (!acc || u.npts == 0) return;  // (uniform over the CTA)
+  const size_t cb = (size_t)b * T * Mp;
+  int* yt = (cfg.target == 0 ? yse : yei) + cb;
+  int* src = (cfg.target == 0 ? Sx : Ex) + cb;
+  int* dst = (cfg.target == 0 ? Ex : Ix) + cb;
+  const int ngroups = cfg.kind == 0 ? u.npts / 2 : 1;
+  long long dE = 0, dI = 0;
+  for (int g = 0; g < ngroups; ++g) {
+    const int m = u.pm[cfg.kind == 0 ? 2 * g : 0];
+    for (int s = tid; s < T; s += NT) {
+      const int dc = dcum_le(u.pm, u.pd, u.pdy, u.npts, m, s - 1);
+      const int dy = dy_at(u.pm, u.pd, u.pdy, u.npts, m, s);
+      const size_t o2 = (size_t)s * Mp + m;
+      if (dy) {  // the point changes of a proposal are distinct cells: one thread owns each
+        const int y_old = yt[o2], y_new = y_old + dy;
+        yt[o2] = y_new;
+        if ((y_old > 0) != (y_new > 0)) atomicAdd(nzd_all + ((size_t)b * 2 + cfg.target) * Mp + m, y_new > 0 ? 1 : -1);
+      }
+      if (dc) {
+        src[o2] -= dc;
+        dst[o2] += dc;
+        if (cfg.target == 1) atomicAdd(reinterpret_cast<unsigned long long*>(Rir + (size_t)b * T + s), (unsigned long long)(long long)dc);
+      }
+      // sum (E - y_ei): target 0 moves E by +dc; target 1 moves E by -dc and y_ei by dy
+      if (cfg.target == 0) dE += dc; else { dE += -dc - dy; dI += dy; }
+    }
+  }
+  // block reduce the two integer statistics
+  for (int o2 = 16; o2 > 0; o2 >>= 1) { dE += __shfl_xor_sync(0xffffffffu, dE, o2); dI += __shfl_xor_sync(0xffffffffu, dI, o2); }
+  __syncthreads();
+  if ((tid & 31) == 0) { redl[tid >> 5] = dE; redl[NT / 32 + (tid >> 5)] = dI; }
+  __syncthreads();
+  if (tid == 0) {
+    long long rE = 0, rI = 0;
+    for (int w = 0; w < NT / 32; ++w) { rE += redl[w]; rI += redl[NT / 32 + w]; }
+    sumEres[b] += rE;
+    sumYei[b] += rI;
+  }
+}
 
 // ------------------------------------------------------------------------------------------------
 // prepare: one CTA per chain.  Optionally DRAWS the proposal first (fused sweep: Philox stream position
@@ -32,10 +128,12 @@ struct seir_draw_args {
 
 __global__ void __launch_bounds__(UPD_THREADS) seir_update_prepare_kernel(
     int M, int T, int Mp, double dt, double nu, double log_p_nu, double eps, seir_update_cfg cfg, seir_draw_args draw, int* prop,
-    double* log_u, const int* __restrict__ nzd_all, const int* __restrict__ yse, const int* __restrict__ yei, const int* __restrict__ yir, const int* __restrict__ Sx,
-    const int* __restrict__ Ex, const int* __restrict__ Ix, const double* __restrict__ Bc, const int* __restrict__ init,
-    const double* __restrict__ lgtab, const double* __restrict__ pa, const double* __restrict__ psiW,
-    const double* __restrict__ pm_arr, const double* __restrict__ gam, seir_upd* __restrict__ upd) {
+    double* log_u, int* nzd_all, int* yse, int* yei, const int* __restrict__ yir, int* Sx, int* Ex, int* Ix,
+    const double* __restrict__ Bc, const int* __restrict__ init, const double* __restrict__ lgtab, const double* __restrict__ pa,
+    const double* __restrict__ psiW, const double* __restrict__ pm_arr, const double* __restrict__ gam, seir_upd* upd,
+    long long* Rir, long long* sumYei, long long* sumEres, double* llc_adj, upd_outputs outs) {
+  __shared__ long long s_redl[2 * (UPD_THREADS / 32)];
+  __shared__ seir_upd s_u;
   __shared__ int s_pm[4], s_pd[4], s_pdy[4], s_npts, s_valid;
   __shared__ int s_colvalid[SEIR_MMAX], s_r3[UPD_THREADS / 32][3];
   __shared__ double s_qf[SEIR_MMAX], s_qr[SEIR_MMAX];
@@ -208,7 +306,16 @@ __global__ void __launch_bounds__(UPD_THREADS) seir_update_prepare_kernel(
     u.lac = valid ? qr - qf : 0.0;
     u.dll_row = dll; u.dllc = dllc; u.dll = 0.0;
     upd[b] = u;
+    s_u = u;
   }
+  if (target == 1) return;  // E->I: the force of infection changes too -> slab kernel, then seir_update_commit_kernel
+  // S->E: everything the decision needs is here: decide and commit in place (one launch per update)
+  __syncthreads();  // s_u published; every read of the caches above is complete
+  const seir_upd u = s_u;
+  double dll_tot;
+  const int acc = upd_decide(u, 0, 0, nullptr, log_u[b], &dll_tot);
+  upd_commit_rows<UPD_THREADS>(b, T, Mp, cfg, u, acc, dll_tot, log_u[b], upd, prop, yse, yei, Sx, Ex, Ix, Rir, sumYei, sumEres, llc_adj,
+                               nzd_all, outs, s_redl);
 }
 
 // ------------------------------------------------------------------------------------------------
@@ -216,17 +323,16 @@ __global__ void __launch_bounds__(UPD_THREADS) seir_update_prepare_kernel(
 // days => Bc'[i] = Bc[i] + sum_g Cs[m_g][i] dI_g and new S->E terms for every metapopulation i.
 // grid = (chains, day chunks); warp <-> day, lanes sweep metapopulations (coalesced day slabs).
 // ------------------------------------------------------------------------------------------------
-template <bool COMMIT>
 __global__ void __launch_bounds__(32 * SLAB_DAYS) seir_update_slab_kernel(
     int M, int T, int Mp, double dt, double eps, int kind, const seir_upd* __restrict__ upd, const int* __restrict__ yse,
-    const int* __restrict__ Sx, const int* __restrict__ Ix, double* __restrict__ Bc, const double* __restrict__ cs,
+    const int* __restrict__ Sx, const int* __restrict__ Ix, const double* __restrict__ Bc, const double* __restrict__ cs,
     const double* __restrict__ pa, const double* __restrict__ psiW, const double* __restrict__ pm_arr, double* __restrict__ part) {
   __shared__ double red[SLAB_DAYS];
   const int b = blockIdx.x, lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
   const seir_upd u = upd[b];
   const int s = blockIdx.y * SLAB_DAYS + warp;
   double acc = 0.0;
-  const bool go = COMMIT ? (u.accept != 0) : (u.valid && !u.neg);
+  const bool go = u.valid && !u.neg;
   if (go && u.npts > 0 && s < T) {
     const int ngroups = kind == 0 ? u.npts / 2 : 1;
     int gm[2];
@@ -256,9 +362,7 @@ __global__ void __launch_bounds__(32 * SLAB_DAYS) seir_update_slab_kernel(
           bcn = fma(cs[(size_t)gm[g] * Mp + i], gd[g], bcn);
           if (i == gm[g]) dIi += gd[g];
         }
-        if (COMMIT) {
-          Bc[base + i] = bcn;
-        } else if (i < M) {
+        if (i < M) {
           const int y = yse[base + i], S = Sx[base + i];
           const double I = (double)Ix[base + i];
           const double e = pas * pm_arr[(size_t)b * Mp + i];
@@ -271,100 +375,60 @@ __global__ void __launch_bounds__(32 * SLAB_DAYS) seir_update_slab_kernel(
       }
     }
   }
-  if (!COMMIT) {
-    acc = warp_sum(acc);
-    if (lane == 0) red[warp] = acc;
-    __syncthreads();
-    if (threadIdx.x == 0) {
-      double r = 0.0;
-      for (int w = 0; w < SLAB_DAYS; ++w) r += red[w];
-      part[(size_t)b * gridDim.y + blockIdx.y] = r;
-    }
+  acc = warp_sum(acc);
+  if (lane == 0) red[warp] = acc;
+  __syncthreads();
+  if (threadIdx.x == 0) {
+    double r = 0.0;
+    for (int w = 0; w < SLAB_DAYS; ++w) r += red[w];
+    part[(size_t)b * gridDim.y + blockIdx.y] = r;
   }
 }
 
-// ------------------------------------------------------------------------------------------------
-// decide + commit rows: one CTA per chain.  accept iff log u < dll + lac  (tfp.mcmc.MetropolisHastings
-// [recall]); on accept apply the point changes to the event / state rows and the sufficient statistics.
-// ------------------------------------------------------------------------------------------------
-__global__ void __launch_bounds__(UPD_THREADS) seir_update_decide_kernel(
-    int M, int T, int Mp, seir_update_cfg cfg, int nchunk, seir_upd* __restrict__ upd, const double* __restrict__ part,
-    const double* __restrict__ log_u, const int* __restrict__ prop, int* __restrict__ yse, int* __restrict__ yei,
-    int* __restrict__ Sx, int* __restrict__ Ex, int* __restrict__ Ix, long long* __restrict__ Rir,
-    long long* __restrict__ sumYei, long long* __restrict__ sumEres, double* __restrict__ llc_adj, double* __restrict__ tlp,
-    int* __restrict__ accept_out, int* __restrict__ last_acc, int* __restrict__ trace, double* __restrict__ dbg,
-    int* __restrict__ nzd_all) {
-  __shared__ int s_acc;
-  __shared__ long long redl[UPD_THREADS / 32];
-  const int b = blockIdx.x, tid = threadIdx.x;
-  seir_upd u = upd[b];
-  if (tid == 0) {
-    double dll = u.dll_row;
-    if (cfg.target == 1)
-      for (int k = 0; k < nchunk; ++k) dll += part[(size_t)b * nchunk + k];
-    double prop_tlp = tlp[b] + dll;
-    if (!u.valid || u.neg) { dll = -INFINITY; prop_tlp = -INFINITY; }
-    const double ratio = dll + u.lac;                      // NaN compares false => reject
-    const int acc = (u.valid && !u.neg && log_u[b] < ratio) ? 1 : 0;
-    if (acc) {
-      tlp[b] = prop_tlp;
-      llc_adj[b] += u.dllc;
-    }
-    upd[b].accept = acc;
-    upd[b].dll = dll;
-    accept_out[b] = acc;
-    if (dbg) {
-      dbg[(size_t)b * 4 + 0] = dll;
-      dbg[(size_t)b * 4 + 1] = u.lac;
-      dbg[(size_t)b * 4 + 2] = prop_tlp;
-      dbg[(size_t)b * 4 + 3] = ratio;
-    }
-    s_acc = acc;
-  }
-  __syncthreads();
-  const int acc = s_acc;
-  // MetropolisHastings.accepted_results: the last ACCEPTED proposal is what the reference traces
-  if (tid < 4 * SEIR_MMAX) {
-    int* la = last_acc + (size_t)b * 4 * SEIR_MMAX;
-    if (acc) la[tid] = prop[(size_t)b * 4 * SEIR_MMAX + tid];
-    if (trace) trace[(size_t)b * 4 * SEIR_MMAX + tid] = la[tid];
+// E->I commit in ONE launch: grid (chains, 1 + day chunks), 32*SLAB_DAYS threads.  Every CTA takes the MH decision
+// itself (same inputs, same order => same answer); CTA y = 0 commits the rows, CTA y >= 1 the Bc slabs of its chunk.
+__global__ void __launch_bounds__(32 * SLAB_DAYS) seir_update_commit_kernel(
+    int M, int T, int Mp, seir_update_cfg cfg, int nchunk, seir_upd* upd, const double* __restrict__ part,
+    const double* __restrict__ log_u, const int* __restrict__ prop, int* yse, int* yei, int* Sx, int* Ex, int* Ix, double* Bc,
+    const double* __restrict__ cs, long long* Rir, long long* sumYei, long long* sumEres, double* llc_adj, int* nzd_all, upd_outputs o) {
+  __shared__ long long redl[2 * SLAB_DAYS];
+  const int b = blockIdx.x;
+  const seir_upd u = upd[b];
+  double dll;
+  const int acc = upd_decide(u, cfg.target, nchunk, part + (size_t)b * nchunk, log_u[b], &dll);
+  if (blockIdx.y == 0) {
+    upd_commit_rows<32 * SLAB_DAYS>(b, T, Mp, cfg, u, acc, dll, log_u[b], upd, prop, yse, yei, Sx, Ex, Ix, Rir, sumYei, sumEres, llc_adj,
+                                    nzd_all, o, redl);
+    return;
   }
   if (!acc || u.npts == 0) return;
-  const size_t cb = (size_t)b * T * Mp;
-  int* yt = (cfg.target == 0 ? yse : yei) + cb;
-  int* src = (cfg.target == 0 ? Sx : Ex) + cb;
-  int* dst = (cfg.target == 0 ? Ex : Ix) + cb;
+  const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+  const int s = (blockIdx.y - 1) * SLAB_DAYS + warp;
+  if (s >= T) return;
   const int ngroups = cfg.kind == 0 ? u.npts / 2 : 1;
-  long long dE = 0, dI = 0;
-  for (int g = 0; g < ngroups; ++g) {
-    const int m = u.pm[cfg.kind == 0 ? 2 * g : 0];
-    for (int s = tid; s < T; s += UPD_THREADS) {
-      const int dc = dcum_le(u.pm, u.pd, u.pdy, u.npts, m, s - 1);
-      const int dy = dy_at(u.pm, u.pd, u.pdy, u.npts, m, s);
-      const size_t o = (size_t)s * Mp + m;
-      if (dy) {  // the point changes of a proposal are distinct cells: one thread owns each
-        const int y_old = yt[o], y_new = y_old + dy;
-        yt[o] = y_new;
-        if ((y_old > 0) != (y_new > 0)) atomicAdd(nzd_all + ((size_t)b * 2 + cfg.target) * Mp + m, y_new > 0 ? 1 : -1);
-      }
-      if (dc) {
-        src[o] -= dc;
-        dst[o] += dc;
-        if (cfg.target == 1) atomicAdd(reinterpret_cast<unsigned long long*>(Rir + (size_t)b * T + s), (unsigned long long)(long long)dc);
-      }
-      // sum (E - y_ei): target 0 moves E by +dc; target 1 moves E by -dc and y_ei by dy
-      if (cfg.target == 0) dE += dc; else { dE += -dc - dy; dI += dy; }
+  int gm[2];
+  double gd[2];
+  bool any = false;
+  for (int g = 0; g < 2; ++g) {
+    gm[g] = 0; gd[g] = 0.0;
+    if (g < ngroups) {
+      const int p0 = cfg.kind == 0 ? 2 * g : 0, np = cfg.kind == 0 ? 2 : 1;
+      int d = 0;
+      for (int p = p0; p < p0 + np; ++p)
+        if (u.pd[p] < s) d += u.pdy[p];
+      gm[g] = u.pm[p0];
+      gd[g] = (double)d;  // I is the destination compartment of E->I: +dcum
+      any |= d != 0;
     }
   }
-  // block reduce the two integer statistics
-  for (int o = 16; o > 0; o >>= 1) { dE += __shfl_xor_sync(0xffffffffu, dE, o); dI += __shfl_xor_sync(0xffffffffu, dI, o); }
-  if ((tid & 31) == 0) redl[tid >> 5] = dE;
-  __syncthreads();
-  if (tid == 0) { long long r = 0; for (int w = 0; w < UPD_THREADS / 32; ++w) r += redl[w]; sumEres[b] += r; }
-  __syncthreads();
-  if ((tid & 31) == 0) redl[tid >> 5] = dI;
-  __syncthreads();
-  if (tid == 0) { long long r = 0; for (int w = 0; w < UPD_THREADS / 32; ++w) r += redl[w]; sumYei[b] += r; }
+  if (!any) return;
+  const size_t base = ((size_t)b * T + s) * Mp;
+  for (int i = lane; i < Mp; i += 32) {
+    double bcn = Bc[base + i];
+#pragma unroll
+    for (int g = 0; g < 2; ++g) bcn = fma(cs[(size_t)gm[g] * Mp + i], gd[g], bcn);
+    Bc[base + i] = bcn;
+  }
 }
 
 static int launch_update(seir_chains* c, const seir_update_cfg& cfg, int slot, const seir_draw_args& draw, int* d_proposal,
@@ -372,25 +436,20 @@ static int launch_update(seir_chains* c, const seir_update_cfg& cfg, int slot, c
   const seir_model* m = c->model;
   const int B = c->B, T = m->T, Mp = m->Mp;
   const int nchunk = (T + SLAB_DAYS - 1) / SLAB_DAYS;
+  const upd_outputs outs{d_tlp, d_accept, c->d_last_acc + (size_t)slot * B * 4 * SEIR_MMAX, d_trace, d_dbg};
   seir_update_prepare_kernel<<<B, UPD_THREADS, draw.enabled ? sizeof(int) * Mp : 0, s>>>(
       m->M, T, Mp, m->dt, m->nu, m->log_p_nu, m->rate_eps, cfg, draw, d_proposal, d_log_u, c->d_nzd, c->d_yse, c->d_yei, c->d_yir, c->d_S,
-      c->d_E, c->d_I, c->d_Bc, m->d_init, m->d_lgtab, c->d_pa, c->d_psiW, c->d_pm, c->d_gam, c->d_upd);
-  int launches = 2;
+      c->d_E, c->d_I, c->d_Bc, m->d_init, m->d_lgtab, c->d_pa, c->d_psiW, c->d_pm, c->d_gam, c->d_upd, c->d_Rir, c->d_sumYei,
+      c->d_sumEres, c->d_llc_adj, outs);
+  int launches = 1;
   if (cfg.target == 1) {
-    seir_update_slab_kernel<false><<<dim3(B, nchunk), 32 * SLAB_DAYS, 0, s>>>(m->M, T, Mp, m->dt, m->rate_eps, cfg.kind, c->d_upd, c->d_yse,
-                                                                             c->d_S, c->d_I, c->d_Bc, m->d_cs, c->d_pa, c->d_psiW,
-                                                                             c->d_pm, c->d_upd_part);
-    ++launches;
-  }
-  seir_update_decide_kernel<<<B, UPD_THREADS, 0, s>>>(m->M, T, Mp, cfg, nchunk, c->d_upd, c->d_upd_part, d_log_u, d_proposal, c->d_yse,
-                                                      c->d_yei, c->d_S, c->d_E, c->d_I, c->d_Rir, c->d_sumYei, c->d_sumEres,
-                                                      c->d_llc_adj, d_tlp, d_accept, c->d_last_acc + (size_t)slot * B * 4 * SEIR_MMAX,
-                                                      d_trace, d_dbg, c->d_nzd);
-  if (cfg.target == 1) {
-    seir_update_slab_kernel<true><<<dim3(B, nchunk), 32 * SLAB_DAYS, 0, s>>>(m->M, T, Mp, m->dt, m->rate_eps, cfg.kind, c->d_upd, c->d_yse,
-                                                                            c->d_S, c->d_I, c->d_Bc, m->d_cs, c->d_pa, c->d_psiW,
-                                                                            c->d_pm, c->d_upd_part);
-    ++launches;
+    seir_update_slab_kernel<<<dim3(B, nchunk), 32 * SLAB_DAYS, 0, s>>>(m->M, T, Mp, m->dt, m->rate_eps, cfg.kind, c->d_upd, c->d_yse, c->d_S,
+                                                                      c->d_I, c->d_Bc, m->d_cs, c->d_pa, c->d_psiW, c->d_pm, c->d_upd_part);
+    seir_update_commit_kernel<<<dim3(B, 1 + nchunk), 32 * SLAB_DAYS, 0, s>>>(m->M, T, Mp, cfg, nchunk, c->d_upd, c->d_upd_part, d_log_u,
+                                                                            d_proposal, c->d_yse, c->d_yei, c->d_S, c->d_E, c->d_I, c->d_Bc,
+                                                                            m->d_cs, c->d_Rir, c->d_sumYei, c->d_sumEres, c->d_llc_adj,
+                                                                            c->d_nzd, outs);
+    launches += 2;
   }
   seir_count_launch(launches);
   return seir_cuda_check(cudaGetLastError(), "seir_update kernels");

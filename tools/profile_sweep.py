@@ -42,13 +42,16 @@ def main():
     torch.cuda.synchronize()
     l0 = nat.launch_count()
     s, e = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    import time
     s.record()
+    t0 = time.perf_counter()
     _, trace = cs.sample(a.sweeps, step_size=a.step_size, collect_draws=False)
+    cpu_ms = 1e3 * (time.perf_counter() - t0)
     e.record()
     torch.cuda.synchronize()
     ms = s.elapsed_time(e)
     acc = {k: float(v["is_accepted"].double().mean()) for k, v in trace.items()}
-    print(json.dumps({"chains": a.chains, "M": a.M, "T": a.T, "sweeps": a.sweeps, "ms_per_sweep": ms / a.sweeps,
+    print(json.dumps({"chains": a.chains, "M": a.M, "T": a.T, "sweeps": a.sweeps, "ms_per_sweep": ms / a.sweeps, "cpu_enqueue_ms_per_sweep": cpu_ms / a.sweeps,
                       "chain_sweeps_per_s": a.chains * a.sweeps / (ms * 1e-3), "launches_per_sweep": (nat.launch_count() - l0) / a.sweeps,
                       "acceptance": acc, "tlp_finite": bool(torch.isfinite(cs.tlp).all())}))
     eng.close()
