@@ -127,7 +127,7 @@ struct seir_draw_args {
 };
 
 __global__ void __launch_bounds__(UPD_THREADS) seir_update_prepare_kernel(
-    int M, int T, int Mp, double dt, double nu, double log_p_nu, double eps, seir_update_cfg cfg, seir_draw_args draw, int* prop,
+    int M, int T, int Mp, int b0, double dt, double nu, double log_p_nu, double eps, seir_update_cfg cfg, seir_draw_args draw, int* prop,
     double* log_u, int* nzd_all, int* yse, int* yei, const int* __restrict__ yir, int* Sx, int* Ex, int* Ix,
     const double* __restrict__ Bc, const int* __restrict__ init, const double* __restrict__ lgtab, const double* __restrict__ pa,
     const double* __restrict__ psiW, const double* __restrict__ pm_arr, const double* __restrict__ gam, seir_upd* upd,
@@ -140,7 +140,7 @@ __global__ void __launch_bounds__(UPD_THREADS) seir_update_prepare_kernel(
   __shared__ double redd[UPD_THREADS / 32][2];
   __shared__ int redn[UPD_THREADS / 32];
   extern __shared__ int s_cnt[];  // [Mp], only when drawing
-  const int b = blockIdx.x, tid = threadIdx.x;
+  const int b = b0 + blockIdx.x, tid = threadIdx.x;
   const size_t cb = (size_t)b * T * Mp;
   chain_view v{M, T, Mp, yse + cb, yei + cb, yir + cb, Sx + cb, Ex + cb, Ix + cb, init};
   int* pr = prop + (size_t)b * 4 * SEIR_MMAX;
@@ -324,11 +324,11 @@ __global__ void __launch_bounds__(UPD_THREADS) seir_update_prepare_kernel(
 // grid = (chains, day chunks); warp <-> day, lanes sweep metapopulations (coalesced day slabs).
 // ------------------------------------------------------------------------------------------------
 __global__ void __launch_bounds__(32 * SLAB_DAYS) seir_update_slab_kernel(
-    int M, int T, int Mp, double dt, double eps, int kind, const seir_upd* __restrict__ upd, const int* __restrict__ yse,
+    int M, int T, int Mp, int b0, double dt, double eps, int kind, const seir_upd* __restrict__ upd, const int* __restrict__ yse,
     const int* __restrict__ Sx, const int* __restrict__ Ix, const double* __restrict__ Bc, const double* __restrict__ cs,
     const double* __restrict__ pa, const double* __restrict__ psiW, const double* __restrict__ pm_arr, double* __restrict__ part) {
   __shared__ double red[SLAB_DAYS];
-  const int b = blockIdx.x, lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+  const int b = b0 + blockIdx.x, lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
   const seir_upd u = upd[b];
   const int s = blockIdx.y * SLAB_DAYS + warp;
   double acc = 0.0;
@@ -388,11 +388,11 @@ __global__ void __launch_bounds__(32 * SLAB_DAYS) seir_update_slab_kernel(
 // E->I commit in ONE launch: grid (chains, 1 + day chunks), 32*SLAB_DAYS threads.  Every CTA takes the MH decision
 // itself (same inputs, same order => same answer); CTA y = 0 commits the rows, CTA y >= 1 the Bc slabs of its chunk.
 __global__ void __launch_bounds__(32 * SLAB_DAYS) seir_update_commit_kernel(
-    int M, int T, int Mp, seir_update_cfg cfg, int nchunk, seir_upd* upd, const double* __restrict__ part,
+    int M, int T, int Mp, int b0, seir_update_cfg cfg, int nchunk, seir_upd* upd, const double* __restrict__ part,
     const double* __restrict__ log_u, const int* __restrict__ prop, int* yse, int* yei, int* Sx, int* Ex, int* Ix, double* Bc,
     const double* __restrict__ cs, long long* Rir, long long* sumYei, long long* sumEres, double* llc_adj, int* nzd_all, upd_outputs o) {
   __shared__ long long redl[2 * SLAB_DAYS];
-  const int b = blockIdx.x;
+  const int b = b0 + blockIdx.x;
   const seir_upd u = upd[b];
   double dll;
   const int acc = upd_decide(u, cfg.target, nchunk, part + (size_t)b * nchunk, log_u[b], &dll);
@@ -432,20 +432,20 @@ __global__ void __launch_bounds__(32 * SLAB_DAYS) seir_update_commit_kernel(
 }
 
 static int launch_update(seir_chains* c, const seir_update_cfg& cfg, int slot, const seir_draw_args& draw, int* d_proposal,
-                         double* d_log_u, double* d_tlp, int* d_accept, int* d_trace, double* d_dbg, cudaStream_t s) {
+                         double* d_log_u, double* d_tlp, int* d_accept, int* d_trace, double* d_dbg, cudaStream_t s, seir_range r) {
   const seir_model* m = c->model;
   const int B = c->B, T = m->T, Mp = m->Mp;
   const int nchunk = (T + SLAB_DAYS - 1) / SLAB_DAYS;
   const upd_outputs outs{d_tlp, d_accept, c->d_last_acc + (size_t)slot * B * 4 * SEIR_MMAX, d_trace, d_dbg};
-  seir_update_prepare_kernel<<<B, UPD_THREADS, draw.enabled ? sizeof(int) * Mp : 0, s>>>(
-      m->M, T, Mp, m->dt, m->nu, m->log_p_nu, m->rate_eps, cfg, draw, d_proposal, d_log_u, c->d_nzd, c->d_yse, c->d_yei, c->d_yir, c->d_S,
+  seir_update_prepare_kernel<<<r.nb, UPD_THREADS, draw.enabled ? sizeof(int) * Mp : 0, s>>>(
+      m->M, T, Mp, r.b0, m->dt, m->nu, m->log_p_nu, m->rate_eps, cfg, draw, d_proposal, d_log_u, c->d_nzd, c->d_yse, c->d_yei, c->d_yir, c->d_S,
       c->d_E, c->d_I, c->d_Bc, m->d_init, m->d_lgtab, c->d_pa, c->d_psiW, c->d_pm, c->d_gam, c->d_upd, c->d_Rir, c->d_sumYei,
       c->d_sumEres, c->d_llc_adj, outs);
   int launches = 1;
   if (cfg.target == 1) {
-    seir_update_slab_kernel<<<dim3(B, nchunk), 32 * SLAB_DAYS, 0, s>>>(m->M, T, Mp, m->dt, m->rate_eps, cfg.kind, c->d_upd, c->d_yse, c->d_S,
+    seir_update_slab_kernel<<<dim3(r.nb, nchunk), 32 * SLAB_DAYS, 0, s>>>(m->M, T, Mp, r.b0, m->dt, m->rate_eps, cfg.kind, c->d_upd, c->d_yse, c->d_S,
                                                                       c->d_I, c->d_Bc, m->d_cs, c->d_pa, c->d_psiW, c->d_pm, c->d_upd_part);
-    seir_update_commit_kernel<<<dim3(B, 1 + nchunk), 32 * SLAB_DAYS, 0, s>>>(m->M, T, Mp, cfg, nchunk, c->d_upd, c->d_upd_part, d_log_u,
+    seir_update_commit_kernel<<<dim3(r.nb, 1 + nchunk), 32 * SLAB_DAYS, 0, s>>>(m->M, T, Mp, r.b0, cfg, nchunk, c->d_upd, c->d_upd_part, d_log_u,
                                                                             d_proposal, c->d_yse, c->d_yei, c->d_S, c->d_E, c->d_I, c->d_Bc,
                                                                             m->d_cs, c->d_Rir, c->d_sumYei, c->d_sumEres, c->d_llc_adj,
                                                                             c->d_nzd, outs);
@@ -459,15 +459,16 @@ static int launch_update(seir_chains* c, const seir_update_cfg& cfg, int slot, c
 int seir_launch_update(seir_chains* c, const seir_update_cfg& cfg, int slot, const int* d_proposal, const double* d_log_u,
                        double* d_tlp, int* d_accept, int* d_trace, double* d_dbg, cudaStream_t s) {
   const seir_draw_args none{0, 0ull, 0u, 0u};
-  return launch_update(c, cfg, slot, none, const_cast<int*>(d_proposal), const_cast<double*>(d_log_u), d_tlp, d_accept, d_trace, d_dbg, s);
+  return launch_update(c, cfg, slot, none, const_cast<int*>(d_proposal), const_cast<double*>(d_log_u), d_tlp, d_accept, d_trace, d_dbg, s,
+                       seir_all(c));
 }
 
 // proposal and log u drawn inside the prepare kernel (fused sweep); the record is left in d_proposal / d_log_u
 int seir_launch_update_drawn(seir_chains* c, const seir_update_cfg& cfg, int slot, unsigned long long seed, unsigned chain0,
                              unsigned ctr, int* d_proposal, double* d_log_u, double* d_tlp, int* d_accept, int* d_trace,
-                             cudaStream_t s) {
+                             cudaStream_t s, seir_range r) {
   const seir_draw_args draw{1, seed, chain0, ctr};
-  return launch_update(c, cfg, slot, draw, d_proposal, d_log_u, d_tlp, d_accept, d_trace, nullptr, s);
+  return launch_update(c, cfg, slot, draw, d_proposal, d_log_u, d_tlp, d_accept, d_trace, nullptr, s, r);
 }
 
 // ------------------------------------------------------------------------------------------------

@@ -13,25 +13,27 @@
 #include "theta_fin.cuh"
 
 // ---- log u = log(U(0,1)) for the MH decisions, [B] ----
-__global__ void seir_log_uniform_kernel(int B, uint64_t seed, uint32_t chain0, uint32_t sweep, uint32_t purpose, double* __restrict__ out) {
-  const int b = blockIdx.x * blockDim.x + threadIdx.x;
-  if (b >= B) return;
+__global__ void seir_log_uniform_kernel(int b0, int nb, uint64_t seed, uint32_t chain0, uint32_t sweep, uint32_t purpose,
+                                        double* __restrict__ out) {
+  const int i = blockIdx.x * blockDim.x + threadIdx.x;
+  if (i >= nb) return;
+  const int b = b0 + i;
   uint32_t r[4];
   seir_philox(seed, chain0 + (uint32_t)b, sweep, purpose, 0u, r);
   out[b] = log(u01_from_bits(r[0], r[1]));
 }
 
-int seir_launch_log_uniform(int B, unsigned long long seed, unsigned chain0, unsigned sweep, unsigned purpose, double* d_out,
+int seir_launch_log_uniform(seir_range r, unsigned long long seed, unsigned chain0, unsigned sweep, unsigned purpose, double* d_out,
                             cudaStream_t s) {
-  seir_log_uniform_kernel<<<(B + 127) / 128, 128, 0, s>>>(B, seed, chain0, sweep, purpose, d_out);
+  seir_log_uniform_kernel<<<(r.nb + 127) / 128, 128, 0, s>>>(r.b0, r.nb, seed, chain0, sweep, purpose, d_out);
   seir_count_launch(1);
   return seir_cuda_check(cudaGetLastError(), "seir_log_uniform_kernel");
 }
 
 // ---- momentum ~ N(0, diag(1/inv_mass)) from Philox (Box-Muller), [B][P] ----
-__global__ void __launch_bounds__(256) seir_hmc_momentum_kernel(int B, int P, uint64_t seed, uint32_t chain0, uint32_t sweep,
+__global__ void __launch_bounds__(256) seir_hmc_momentum_kernel(int b0, int P, uint64_t seed, uint32_t chain0, uint32_t sweep,
                                                                 const double* __restrict__ inv_mass, double* __restrict__ p) {
-  const int b = blockIdx.y;
+  const int b = b0 + blockIdx.y;
   for (int j2 = blockIdx.x * blockDim.x + threadIdx.x; 2 * j2 < P; j2 += gridDim.x * blockDim.x) {
     uint32_t r[4];
     seir_philox(seed, chain0 + (uint32_t)b, sweep, 0x484D43u /* 'HMC' */, (uint32_t)j2, r);
@@ -60,7 +62,7 @@ __global__ void __launch_bounds__(256) seir_hmc_momentum_kernel(int B, int P, ui
 enum { HMC_BEGIN = 0, HMC_MID = 1, HMC_END = 2 };
 
 template <int MODE>
-__global__ void __launch_bounds__(TF_THREADS) seir_hmc_leap_kernel(tf_model md, tf_chains ch, const double* __restrict__ step,
+__global__ void __launch_bounds__(TF_THREADS) seir_hmc_leap_kernel(tf_model md, tf_chains ch, int b0, const double* __restrict__ step,
                                                                   const double* __restrict__ inv_mass, const double* __restrict__ log_u,
                                                                   double* u, double* __restrict__ p, double* grad,
                                                                   double* __restrict__ u0, double* __restrict__ val0, double* __restrict__ k0,
@@ -69,7 +71,7 @@ __global__ void __launch_bounds__(TF_THREADS) seir_hmc_leap_kernel(tf_model md, 
   __shared__ tf_shared sh;
   __shared__ double red[32];
   __shared__ int s_acc;
-  const int b = blockIdx.x, P = md.P;
+  const int b = b0 + blockIdx.x, P = md.P;
   double* ub = u + (size_t)b * P;
   double* gb = grad + (size_t)b * P;
   const double val = tf_finalize(md, ch, b, ub, SEIR_PART_JOINT, gb, dyn, sh);
@@ -136,47 +138,62 @@ static int hmc_alloc(seir_chains* c) {
 int seir_hmc_workspace(seir_chains* c) { return hmc_alloc(c); }
 
 int seir_launch_hmc_momentum(seir_chains* c, unsigned long long seed, unsigned chain0, unsigned sweep, const double* d_inv_mass,
-                             double* d_p, cudaStream_t s) {
+                             double* d_p, cudaStream_t s, seir_range r) {
   const int P = c->model->P;
-  dim3 grid((P / 2 + 255) / 256 > 0 ? (P / 2 + 255) / 256 : 1, c->B);
-  seir_hmc_momentum_kernel<<<grid, 256, 0, s>>>(c->B, P, seed, chain0, sweep, d_inv_mass, d_p);
+  dim3 grid((P / 2 + 255) / 256 > 0 ? (P / 2 + 255) / 256 : 1, r.nb);
+  seir_hmc_momentum_kernel<<<grid, 256, 0, s>>>(r.b0, P, seed, chain0, sweep, d_inv_mass, d_p);
   seir_count_launch(1);
   return seir_cuda_check(cudaGetLastError(), "seir_hmc_momentum_kernel");
 }
 
-// One HMC transition; d_momentum == NULL means "already in c->d_hmc_p".
-// Launch sequence for L leapfrog steps: theta prep, [log-lik, leap kernel] x (L + 1)  -- the GibbsKernel re-bootstraps
-// gradient-based kernels, i.e. one fresh value+gradient at the current point, then L more.
+// Launch sequence of one HMC transition with L leapfrog steps: theta prep (begin), then [log-lik, leap kernel] x (L + 1)
+// -- the GibbsKernel re-bootstraps gradient-based kernels, i.e. one fresh value+gradient at the current point
+// (SURVEY 3.2), then L more.  The momentum must already be in c->d_hmc_p.
+int seir_hmc_step_begin(seir_chains* c, const double* d_u, cudaStream_t s, seir_range r) {
+  return seir_launch_theta_prep(c, d_u, SEIR_THETA_UNCONSTRAINED, SEIR_PART_JOINT, s, r);
+}
+
+int seir_hmc_step_leap(seir_chains* c, int i, int num_leapfrog, double* d_u, const double* d_log_u, const double* d_step,
+                       const double* d_inv_mass, double* d_tlp, int* d_accept, double* d_dbg, cudaStream_t s, seir_range r) {
+  const seir_model* m = c->model;
+  const int B = c->B;
+  double *val0 = c->d_hmc_val + B, *k0 = c->d_hmc_val + 2 * B;
+  const size_t smem = seir_tf_smem(m);
+  static size_t attr_smem = 0;
+  if (smem > 48 * 1024 && attr_smem != smem) {
+    SEIR_CUDA(cudaFuncSetAttribute(seir_hmc_leap_kernel<HMC_BEGIN>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+    SEIR_CUDA(cudaFuncSetAttribute(seir_hmc_leap_kernel<HMC_MID>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+    SEIR_CUDA(cudaFuncSetAttribute(seir_hmc_leap_kernel<HMC_END>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+    attr_smem = smem;
+  }
+  int rc;
+  if ((rc = seir_launch_loglik(c, true, s, r)) != SEIR_OK) return rc;
+  const tf_model md = seir_tf_model(m);
+  const tf_chains ch = seir_tf_chains(c);  // (after the log-lik launch: it fixes the partial-array shapes)
+  if (i == 0)
+    seir_hmc_leap_kernel<HMC_BEGIN><<<r.nb, TF_THREADS, smem, s>>>(md, ch, r.b0, d_step, d_inv_mass, d_log_u, d_u, c->d_hmc_p, c->d_hmc_grad,
+                                                                   c->d_hmc_u0, val0, k0, d_tlp, d_accept, d_dbg);
+  else if (i < num_leapfrog)
+    seir_hmc_leap_kernel<HMC_MID><<<r.nb, TF_THREADS, smem, s>>>(md, ch, r.b0, d_step, d_inv_mass, d_log_u, d_u, c->d_hmc_p, c->d_hmc_grad,
+                                                                 c->d_hmc_u0, val0, k0, d_tlp, d_accept, d_dbg);
+  else
+    seir_hmc_leap_kernel<HMC_END><<<r.nb, TF_THREADS, smem, s>>>(md, ch, r.b0, d_step, d_inv_mass, d_log_u, d_u, c->d_hmc_p, c->d_hmc_grad,
+                                                                 c->d_hmc_u0, val0, k0, d_tlp, d_accept, d_dbg);
+  seir_count_launch(1);
+  return seir_cuda_check(cudaGetLastError(), "seir_hmc_leap_kernel");
+}
+
+// One HMC transition over every chain; d_momentum == NULL means "already in c->d_hmc_p".
 int seir_launch_hmc(seir_chains* c, double* d_u, const double* d_momentum, const double* d_log_u, const double* d_step,
                     const double* d_inv_mass, int num_leapfrog, double* d_tlp, int* d_accept, double* d_dbg, cudaStream_t s) {
   int rc = hmc_alloc(c);
   if (rc != SEIR_OK) return rc;
-  const seir_model* m = c->model;
-  const int B = c->B, P = m->P;
-  double *val0 = c->d_hmc_val + B, *k0 = c->d_hmc_val + 2 * B;
+  const int B = c->B, P = c->model->P;
   if (d_momentum)
     SEIR_CUDA(cudaMemcpyAsync(c->d_hmc_p, d_momentum, sizeof(double) * (size_t)B * P, cudaMemcpyDeviceToDevice, s));
-  const size_t smem = seir_tf_smem(m);
-  if (smem > 48 * 1024) {
-    SEIR_CUDA(cudaFuncSetAttribute(seir_hmc_leap_kernel<HMC_BEGIN>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
-    SEIR_CUDA(cudaFuncSetAttribute(seir_hmc_leap_kernel<HMC_MID>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
-    SEIR_CUDA(cudaFuncSetAttribute(seir_hmc_leap_kernel<HMC_END>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
-  }
-  const tf_model md = seir_tf_model(m);
-  if ((rc = seir_launch_theta_prep(c, d_u, SEIR_THETA_UNCONSTRAINED, SEIR_PART_JOINT, s)) != SEIR_OK) return rc;
-  for (int i = 0; i <= num_leapfrog; ++i) {
-    if ((rc = seir_launch_loglik(c, true, s)) != SEIR_OK) return rc;
-    const tf_chains ch = seir_tf_chains(c);  // (after the log-lik launch: it fixes the partial-array shapes)
-    if (i == 0)
-      seir_hmc_leap_kernel<HMC_BEGIN><<<B, TF_THREADS, smem, s>>>(md, ch, d_step, d_inv_mass, d_log_u, d_u, c->d_hmc_p, c->d_hmc_grad,
-                                                                  c->d_hmc_u0, val0, k0, d_tlp, d_accept, d_dbg);
-    else if (i < num_leapfrog)
-      seir_hmc_leap_kernel<HMC_MID><<<B, TF_THREADS, smem, s>>>(md, ch, d_step, d_inv_mass, d_log_u, d_u, c->d_hmc_p, c->d_hmc_grad,
-                                                                c->d_hmc_u0, val0, k0, d_tlp, d_accept, d_dbg);
-    else
-      seir_hmc_leap_kernel<HMC_END><<<B, TF_THREADS, smem, s>>>(md, ch, d_step, d_inv_mass, d_log_u, d_u, c->d_hmc_p, c->d_hmc_grad,
-                                                                c->d_hmc_u0, val0, k0, d_tlp, d_accept, d_dbg);
-  }
-  seir_count_launch(num_leapfrog + 1);
-  return seir_cuda_check(cudaGetLastError(), "seir_hmc kernels");
+  const seir_range all = seir_all(c);
+  if ((rc = seir_hmc_step_begin(c, d_u, s, all)) != SEIR_OK) return rc;
+  for (int i = 0; i <= num_leapfrog; ++i)
+    if ((rc = seir_hmc_step_leap(c, i, num_leapfrog, d_u, d_log_u, d_step, d_inv_mass, d_tlp, d_accept, d_dbg, s, all)) != SEIR_OK) return rc;
+  return SEIR_OK;
 }

@@ -35,18 +35,19 @@ tf_chains seir_tf_chains(const seir_chains* c) {
 
 size_t seir_tf_smem(const seir_model* m) { return sizeof(double) * ((size_t)m->P + m->T); }
 
-__global__ void __launch_bounds__(TF_THREADS) seir_theta_prep_kernel(tf_model md, tf_chains ch, const double* __restrict__ theta, int kind,
-                                                                     int parts) {
+__global__ void __launch_bounds__(TF_THREADS) seir_theta_prep_kernel(tf_model md, tf_chains ch, int b0, const double* __restrict__ theta,
+                                                                     int kind, int parts) {
   extern __shared__ double dyn[];
   __shared__ tf_shared sh;
-  tf_theta_prep(md, ch, blockIdx.x, theta + (size_t)blockIdx.x * md.P, kind, parts, dyn, sh);
+  const int b = b0 + blockIdx.x;
+  tf_theta_prep(md, ch, b, theta + (size_t)b * md.P, kind, parts, dyn, sh);
 }
 
-int seir_launch_theta_prep(seir_chains* c, const double* d_theta, int kind, int parts, cudaStream_t s) {
+int seir_launch_theta_prep(seir_chains* c, const double* d_theta, int kind, int parts, cudaStream_t s, seir_range r) {
   const seir_model* m = c->model;
   const size_t smem = seir_tf_smem(m);
   if (smem > 48 * 1024) SEIR_CUDA(cudaFuncSetAttribute(seir_theta_prep_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
-  seir_theta_prep_kernel<<<c->B, TF_THREADS, smem, s>>>(seir_tf_model(m), seir_tf_chains(c), d_theta, kind, parts);
+  seir_theta_prep_kernel<<<r.nb, TF_THREADS, smem, s>>>(seir_tf_model(m), seir_tf_chains(c), r.b0, d_theta, kind, parts);
   seir_count_launch(1);
   return seir_cuda_check(cudaGetLastError(), "seir_theta_prep_kernel");
 }
@@ -166,7 +167,7 @@ __device__ __forceinline__ double warp_sum4_transposed(const double (&a)[4]) {
 
 template <bool GRAD, int MPT>
 __global__ void __launch_bounds__(SEIR_LL_THREADS, GRAD ? 6 : 10) seir_loglik_kernel(
-    int T, int Mp, int dps, double dt, double eps, const int* __restrict__ yse, const int* __restrict__ Sx,
+    int T, int Mp, int dps, int b0, double dt, double eps, const int* __restrict__ yse, const int* __restrict__ Sx,
     const int* __restrict__ Ix, const double* __restrict__ Bc, const double* __restrict__ pa, const double* __restrict__ psiW,
     const double* __restrict__ W, const double* __restrict__ pm, const double2* __restrict__ logtab, double* __restrict__ val_part,
     double* __restrict__ psi_part, double* __restrict__ col_part, double* __restrict__ rowsum_part, const ll_coefs K) {
@@ -177,7 +178,7 @@ __global__ void __launch_bounds__(SEIR_LL_THREADS, GRAD ? 6 : 10) seir_loglik_ke
   double* w_s = sm + 2 * dps;    // [dps]            (GRAD)
   double* colw = sm + 3 * dps;   // [nwarps][dps+4]  (GRAD)
   __shared__ double red[32];
-  const int b = blockIdx.y, tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
+  const int b = b0 + blockIdx.y, tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
   const int m0 = blockIdx.x * (SEIR_LL_THREADS * MPT) + tid;
   const int tb = blockIdx.z * dps, nt = min(dps, T - tb);
   const int cstride = dps + LL_UNROLL;
@@ -298,7 +299,7 @@ __device__ __forceinline__ void mbar_arrive(uint64_t* bar) {
 // 3.2 of 10 stall cycles per issue, profiles/r01_v5_ncu_full_summary.md).
 template <bool GRAD, int MPT, int NSTAGE, int NTHR>
 __global__ void __launch_bounds__(NTHR + 32, NTHR >= 384 ? (GRAD ? 2 : 3) : 1) seir_loglik_tma_kernel(
-    int T, int Mp, int dps, double dt, double eps, const int* __restrict__ yse, const int* __restrict__ Sx,
+    int T, int Mp, int dps, int b0, double dt, double eps, const int* __restrict__ yse, const int* __restrict__ Sx,
     const int* __restrict__ Ix, const double* __restrict__ Bc, const double* __restrict__ pa, const double* __restrict__ psiW,
     const double* __restrict__ W, const double* __restrict__ pm, const double2* __restrict__ logtab, double* __restrict__ val_part,
     double* __restrict__ psi_part, double* __restrict__ col_part, double* __restrict__ rowsum_part, const ll_coefs K) {
@@ -315,7 +316,7 @@ __global__ void __launch_bounds__(NTHR + 32, NTHR >= 384 ? (GRAD ? 2 : 3) : 1) s
   double* pw_s = sm + dps;       // [dps]
   double* w_s = sm + 2 * dps;    // [dps]            (GRAD)
   double* colw = sm + 3 * dps;   // [nwarps][dps+4]  (GRAD)
-  const int b = blockIdx.y, tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
+  const int b = b0 + blockIdx.y, tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
   const int mb0 = blockIdx.x * MB;
   const int tb = blockIdx.z * dps, nt = min(dps, T - tb);
   const int ngroups = (nt + LL_STAGE_DAYS - 1) / LL_STAGE_DAYS;
@@ -420,7 +421,7 @@ __global__ void __launch_bounds__(NTHR + 32, NTHR >= 384 ? (GRAD ? 2 : 3) : 1) s
 
 #define LL_TMA_STAGES 2
 
-typedef void (*loglik_fn)(int, int, int, double, double, const int*, const int*, const int*, const double*, const double*,
+typedef void (*loglik_fn)(int, int, int, int, double, double, const int*, const int*, const int*, const double*, const double*,
                           const double*, const double*, const double*, const double2*, double*, double*, double*, double*, const ll_coefs);
 
 struct loglik_cfg {
@@ -497,29 +498,22 @@ static size_t loglik_smem(bool grad, int dps, const loglik_cfg& k) {
   return bytes;
 }
 
-// Day splits.  Direct-load kernel: (metapopulation blocks x chains x splits) fills the resident CTA slots once.
-// TMA kernel: few CTA slots per SM (shared-memory bound), so aim at ~4 waves of short CTAs (whole butterfly groups
-// of 4 days) that the hardware scheduler balances dynamically.
+// Day splits: CTAs of about 12 (value) / 20 (value + gradient) days, in whole butterfly groups of 4 -- the shape the
+// UK workload at 256 chains per GPU measured best with (about 4 waves of short CTAs that the hardware scheduler
+// balances).  The split depends on T only, never on the number of chains: the order of every floating-point sum, and
+// with it every bit of the result, is the same however the chains are partitioned over ranks and chain groups.
 static int choose_dps(const seir_chains* c, bool grad, const loglik_cfg& k, loglik_fn fn) {
-  int dev = 0, sms = 148, per = 8;
-  cudaGetDevice(&dev);
-  cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev);
-  const int T = c->model->T;
-  const size_t smem = loglik_smem(grad, k.tma ? 16 : (grad ? 32 : 16), k);
-  if (smem > 48 * 1024) cudaFuncSetAttribute(fn, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
-  cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per, fn, k.tma ? k.threads + 32 : k.threads, smem);
-  const long long slots = (long long)sms * (per > 0 ? per : 1);
-  const long long base = (long long)k.nblk * c->B;
-  const int cap = (T + 3) / 4 < SEIR_MAX_SPLITS ? (T + 3) / 4 : SEIR_MAX_SPLITS;
-  long long want = k.tma ? (4 * slots + base - 1) / base : slots / base;
-  int ts = (int)(want > cap ? cap : want);
+  (void)k; (void)fn;
+  const int T = c->model->T, target = grad ? 20 : 12;
+  int ts = (T + target - 1) / target;
+  if (ts > SEIR_MAX_SPLITS) ts = SEIR_MAX_SPLITS;
   if (ts < 1) ts = 1;
   int dps = (T + ts - 1) / ts;
-  if (k.tma) dps = (dps + LL_STAGE_DAYS - 1) / LL_STAGE_DAYS * LL_STAGE_DAYS;
+  dps = (dps + LL_STAGE_DAYS - 1) / LL_STAGE_DAYS * LL_STAGE_DAYS;
   return dps;
 }
 
-int seir_launch_loglik(seir_chains* c, bool grad, cudaStream_t s) {
+int seir_launch_loglik(seir_chains* c, bool grad, cudaStream_t s, seir_range r) {
   const seir_model* m = c->model;
   const loglik_cfg k = loglik_config(c);
   loglik_fn fn = grad ? loglik_kernel_for<true>(k) : loglik_kernel_for<false>(k);
@@ -528,10 +522,13 @@ int seir_launch_loglik(seir_chains* c, bool grad, cudaStream_t s) {
   const int nts = (m->T + dps - 1) / dps;
   c->nts = nts;
   c->nblk_last = k.nblk;
-  dim3 grid(k.nblk, c->B, nts);
+  dim3 grid(k.nblk, r.nb, nts);
   const size_t smem = loglik_smem(grad, dps, k);
-  if (smem > 48 * 1024) SEIR_CUDA(cudaFuncSetAttribute(fn, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
-  fn<<<grid, k.tma ? k.threads + 32 : k.threads, smem, s>>>(m->T, m->Mp, dps, m->dt, m->rate_eps, c->d_yse, c->d_S, c->d_I, c->d_Bc, c->d_pa, c->d_psiW,
+  if (smem > 48 * 1024 && c->ll_attr_smem[grad] != smem) {  // (once per shape, not per launch)
+    SEIR_CUDA(cudaFuncSetAttribute(fn, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+    c->ll_attr_smem[grad] = smem;
+  }
+  fn<<<grid, k.tma ? k.threads + 32 : k.threads, smem, s>>>(m->T, m->Mp, dps, r.b0, m->dt, m->rate_eps, c->d_yse, c->d_S, c->d_I, c->d_Bc, c->d_pa, c->d_psiW,
                                    m->d_W, c->d_pm, m->d_logtab, c->d_val_part, c->d_psi_part, c->d_col_part, c->d_rowsum, LL_COEFS);
   seir_count_launch(1);
   return seir_cuda_check(cudaGetLastError(), "seir_loglik_kernel");

@@ -229,7 +229,12 @@ void seir_chains_destroy(seir_chains* c) {
   cudaFree(c->d_logpir); cudaFree(c->d_pm); cudaFree(c->d_scal); cudaFree(c->d_carq); cudaFree(c->d_val_part); cudaFree(c->d_psi_part);
   cudaFree(c->d_col_part); cudaFree(c->d_rowsum); cudaFree(c->d_upd); cudaFree(c->d_upd_part); cudaFree(c->d_llc_adj);
   cudaFree(c->d_tlp); cudaFree(c->d_last_acc); cudaFree(c->d_nzd); cudaFree(c->d_hmc_u0); cudaFree(c->d_hmc_p); cudaFree(c->d_hmc_grad);
-  cudaFree(c->d_hmc_val); cudaFree(c->d_prop); cudaFree(c->d_logu); cudaFree(c->d_stage_events); cudaFree(c->d_stage_theta);
+  cudaFree(c->d_hmc_val);
+  if (c->grp_ready) {
+    for (int g = 0; g < 4; ++g) { cudaStreamDestroy(c->grp_stream[g]); cudaEventDestroy(c->grp_join[g]); }
+    cudaEventDestroy(c->grp_fork);
+  }
+  cudaFree(c->d_prop); cudaFree(c->d_logu); cudaFree(c->d_stage_events); cudaFree(c->d_stage_theta);
   cudaFree(c->d_stage_out); cudaFree(c->d_stage_u16);
   if (c->h_stage_u16) cudaFreeHost(c->h_stage_u16);
   if (c->copy_stream) cudaStreamDestroy(c->copy_stream);
@@ -279,8 +284,8 @@ int seir_log_prob_cached(seir_chains* c, const double* d_theta, int kind, int pa
   SEIR_TRY(check_dev_ptr(d_theta, "d_theta"));
   if (!d_out) return seir_set_error(SEIR_ERR_BAD_ARG, "d_out is NULL");
   cudaStream_t s = (cudaStream_t)stream;
-  SEIR_TRY(seir_launch_theta_prep(c, d_theta, kind, parts, s));
-  if (parts & SEIR_PART_SEIR) SEIR_TRY(seir_launch_loglik(c, false, s));
+  SEIR_TRY(seir_launch_theta_prep(c, d_theta, kind, parts, s, seir_all(c)));
+  if (parts & SEIR_PART_SEIR) SEIR_TRY(seir_launch_loglik(c, false, s, seir_all(c)));
   return seir_launch_finalize(c, d_theta, kind, parts, d_out, nullptr, s);
 }
 
@@ -291,8 +296,8 @@ int seir_log_prob_grad_cached(seir_chains* c, const double* d_theta, int kind, i
   SEIR_TRY(check_dev_ptr(d_theta, "d_theta"));
   if (!d_out || !d_grad) return seir_set_error(SEIR_ERR_BAD_ARG, "d_out / d_grad is NULL");
   cudaStream_t s = (cudaStream_t)stream;
-  SEIR_TRY(seir_launch_theta_prep(c, d_theta, kind, parts, s));
-  if (parts & SEIR_PART_SEIR) SEIR_TRY(seir_launch_loglik(c, true, s));
+  SEIR_TRY(seir_launch_theta_prep(c, d_theta, kind, parts, s, seir_all(c)));
+  if (parts & SEIR_PART_SEIR) SEIR_TRY(seir_launch_loglik(c, true, s, seir_all(c)));
   return seir_launch_finalize(c, d_theta, kind, parts, d_out, d_grad, s);
 }
 
@@ -407,9 +412,9 @@ int seir_run_stage(seir_chains* c, int stage, const double* d_events, const doub
   switch (stage) {
     case 0: SEIR_TRY(check_dev_ptr(d_events, "d_events")); return seir_launch_ingest(c, d_events, s);
     case 1: return seir_launch_contract(c, s);
-    case 2: SEIR_TRY(check_dev_ptr(d_theta, "d_theta")); return seir_launch_theta_prep(c, d_theta, kind, parts, s);
-    case 3: return seir_launch_loglik(c, false, s);
-    case 4: return seir_launch_loglik(c, true, s);
+    case 2: SEIR_TRY(check_dev_ptr(d_theta, "d_theta")); return seir_launch_theta_prep(c, d_theta, kind, parts, s, seir_all(c));
+    case 3: return seir_launch_loglik(c, false, s, seir_all(c));
+    case 4: return seir_launch_loglik(c, true, s, seir_all(c));
     case 5: SEIR_TRY(check_dev_ptr(d_theta, "d_theta")); return seir_launch_finalize(c, d_theta, kind, parts, d_out, nullptr, s);
     case 6:
       SEIR_TRY(check_dev_ptr(d_theta, "d_theta"));
@@ -425,7 +430,7 @@ int seir_prepare_theta(seir_chains* c, const double* d_theta, int kind, void* st
   SEIR_TRY(check_dev_ptr(d_theta, "d_theta"));
   if (kind != SEIR_THETA_CONSTRAINED && kind != SEIR_THETA_UNCONSTRAINED)
     return seir_set_error(SEIR_ERR_BAD_ARG, "seir_prepare_theta: bad theta_kind");
-  return seir_launch_theta_prep(c, d_theta, kind, SEIR_PART_SEIR, (cudaStream_t)stream);
+  return seir_launch_theta_prep(c, d_theta, kind, SEIR_PART_SEIR, (cudaStream_t)stream, seir_all(c));
 }
 
 int seir_update_step(seir_chains* c, const seir_update_spec* spec, int slot, const int32_t* d_proposal, const double* d_log_u,
@@ -463,8 +468,8 @@ int seir_hmc_step(seir_chains* c, double* d_u, const double* d_momentum, const d
 int seir_hmc_draw(seir_chains* c, uint64_t seed, uint32_t chain_offset, uint32_t sweep_index, const double* d_inv_mass,
                   double* d_momentum, double* d_log_u, void* stream) {
   if (!c || !d_momentum || !d_log_u) return seir_set_error(SEIR_ERR_BAD_ARG, "seir_hmc_draw: NULL argument");
-  SEIR_TRY(seir_launch_hmc_momentum(c, seed, chain_offset, sweep_index, d_inv_mass, d_momentum, (cudaStream_t)stream));
-  return seir_launch_log_uniform(c->B, seed, chain_offset, sweep_index, 0x48u, d_log_u, (cudaStream_t)stream);
+  SEIR_TRY(seir_launch_hmc_momentum(c, seed, chain_offset, sweep_index, d_inv_mass, d_momentum, (cudaStream_t)stream, seir_all(c)));
+  return seir_launch_log_uniform(seir_all(c), seed, chain_offset, sweep_index, 0x48u, d_log_u, (cudaStream_t)stream);
 }
 
 int seir_propose(seir_chains* c, const seir_update_spec* spec, uint64_t seed, uint32_t chain_offset, uint32_t counter,

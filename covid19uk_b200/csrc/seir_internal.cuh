@@ -81,6 +81,7 @@ struct seir_chains {
   int nblkLL;   // ceil(Mp/(SEIR_LL_THREADS*mpt))
   int nts;      // day splits used by the last log-likelihood launch
   int nblk_last;  // metapopulation column blocks used by the last log-likelihood launch
+  size_t ll_attr_smem[2];  // dynamic shared memory the log-likelihood kernels were last configured for
   int ll_dps[2];  // days per CTA of the log-likelihood kernel (value / value+gradient), chosen on first launch
   int nllc;     // number of llc partials per chain written by the last coefficient launch
   size_t stats_bytes;  // bytes of the contiguous integer-statistics block starting at d_Yir
@@ -116,6 +117,10 @@ struct seir_chains {
   // sweep scratch: sampled proposals and log-uniforms
   int* d_prop;
   double* d_logu;
+  // sweep chain groups: internal streams forked from / joined to the caller's stream
+  cudaStream_t grp_stream[4];
+  cudaEvent_t grp_fork, grp_join[4];
+  int grp_ready;
   // staging for the host-buffer entry points
   double *d_stage_events, *d_stage_theta, *d_stage_out;
   unsigned short *d_stage_u16, *h_stage_u16;  // narrowed events: device copy and pinned host staging
@@ -136,6 +141,12 @@ void seir_count_launch(int n);
     if (_rc != SEIR_OK) return _rc;                       \
   } while (0)
 
+// contiguous range of chains a launch covers (the sweep runs chain groups on separate streams)
+struct seir_range {
+  int b0, nb;
+};
+static inline seir_range seir_all(const seir_chains* c) { return seir_range{0, c->B}; }
+
 // kernel launchers (one per .cu file)
 int seir_launch_state(const seir_model* m, int B, const double* d_events, double* d_state, cudaStream_t s);
 int seir_launch_ingest(seir_chains* c, const double* d_events, cudaStream_t s);
@@ -144,16 +155,20 @@ int seir_launch_ingest_range(seir_chains* c, const double* d_events, const unsig
                              cudaStream_t s);
 int seir_launch_coef(seir_chains* c, cudaStream_t s);
 int seir_launch_contract(seir_chains* c, cudaStream_t s);
-int seir_launch_theta_prep(seir_chains* c, const double* d_theta, int kind, int parts, cudaStream_t s);
-int seir_launch_loglik(seir_chains* c, bool grad, cudaStream_t s);
+int seir_launch_theta_prep(seir_chains* c, const double* d_theta, int kind, int parts, cudaStream_t s, seir_range r);
+int seir_launch_loglik(seir_chains* c, bool grad, cudaStream_t s, seir_range r);
 int seir_launch_finalize(seir_chains* c, const double* d_theta, int kind, int parts, double* d_out, double* d_grad,
                          cudaStream_t s);
 int seir_launch_hmc_momentum(seir_chains* c, unsigned long long seed, unsigned chain0, unsigned sweep, const double* d_inv_mass,
-                             double* d_p, cudaStream_t s);
+                             double* d_p, cudaStream_t s, seir_range r);
+// the steps of one HMC transition (seir_launch_hmc = all of them over every chain)
+int seir_hmc_step_begin(seir_chains* c, const double* d_u, cudaStream_t s, seir_range r);
+int seir_hmc_step_leap(seir_chains* c, int i, int num_leapfrog, double* d_u, const double* d_log_u, const double* d_step,
+                       const double* d_inv_mass, double* d_tlp, int* d_accept, double* d_dbg, cudaStream_t s, seir_range r);
 int seir_launch_hmc(seir_chains* c, double* d_u, const double* d_momentum, const double* d_log_u, const double* d_step,
                     const double* d_inv_mass, int num_leapfrog, double* d_tlp, int* d_accept, double* d_dbg, cudaStream_t s);
 int seir_hmc_workspace(seir_chains* c);
-int seir_launch_log_uniform(int B, unsigned long long seed, unsigned chain0, unsigned sweep, unsigned purpose, double* d_out,
+int seir_launch_log_uniform(seir_range r, unsigned long long seed, unsigned chain0, unsigned sweep, unsigned purpose, double* d_out,
                             cudaStream_t s);
 int seir_launch_propose(seir_chains* c, const seir_update_cfg& cfg, unsigned long long seed, unsigned chain0, unsigned ctr,
                         int* d_proposal, double* d_log_u, cudaStream_t s);
@@ -166,7 +181,7 @@ int seir_launch_update(seir_chains* c, const seir_update_cfg& cfg, int slot, con
 
 int seir_launch_update_drawn(seir_chains* c, const seir_update_cfg& cfg, int slot, unsigned long long seed, unsigned chain0,
                              unsigned ctr, int* d_proposal, double* d_log_u, double* d_tlp, int* d_accept, int* d_trace,
-                             cudaStream_t s);
+                             cudaStream_t s, seir_range r);
 
 // ---- device helpers ---------------------------------------------------------------------------
 #ifdef __CUDACC__

@@ -103,3 +103,30 @@ def test_sweeps_keep_caches_consistent_and_are_partition_independent():
     assert np.array_equal(cs2.u.cpu().numpy(), u_all[4:6])
     assert np.array_equal(cs2.events().cpu().numpy(), ev_all[4:6])
     eng.close()
+
+
+def test_chain_groups_on_internal_streams_match_single_stream():
+    """B = 200 chains run as 4 chain groups on the library's internal streams (seir_launch_sweep); global chains
+    190..199 run alone as one group on the caller's stream must give bit-identical parameters, events and traces."""
+    import torch
+    from covid19uk_b200.inference.sampler import ChainSet
+
+    M, T, B = 24, 40, 200
+    pb, eng, om, u = _setup(M, T, B, seed=8)
+    cfg = dict(CFG, dmax=min(CFG["dmax"], T - 1))
+    t_range = [T - 21, T]
+    cs = ChainSet(eng, pb["events"], u, cfg, t_range, seed=5, chain_offset=0)
+    _, trace = cs.sample(6, step_size=1e-3)
+    ev = cs.events().cpu().numpy()
+    fresh = eng.log_prob(ev, cs.u, __import__("covid19uk_b200")._native.THETA_UNCONSTRAINED,
+                         __import__("covid19uk_b200")._native.PART_JOINT).cpu().numpy()
+    np.testing.assert_allclose(cs.tlp.cpu().numpy(), fresh, rtol=1e-10)
+    u_all = cs.u.cpu().numpy().copy()
+    acc_all = {k: v["is_accepted"].cpu().numpy().copy() for k, v in trace.items()}
+    cs2 = ChainSet(eng, pb["events"][190:200], u[190:200], cfg, t_range, seed=5, chain_offset=190)
+    _, trace2 = cs2.sample(6, step_size=1e-3)
+    assert np.array_equal(cs2.u.cpu().numpy(), u_all[190:200])
+    assert np.array_equal(cs2.events().cpu().numpy(), ev[190:200])
+    for k in acc_all:
+        assert np.array_equal(trace2[k]["is_accepted"].cpu().numpy(), acc_all[k][:, 190:200])
+    eng.close()
