@@ -17,7 +17,7 @@ PART_SEIR = 1
 PART_PRIORS = 2
 PART_ILDJ = 4
 PART_JOINT = 7
-ABI_VERSION = 4
+ABI_VERSION = 5
 
 
 class SeirSpec(ctypes.Structure):

@@ -27,7 +27,7 @@
 extern "C" {
 #endif
 
-#define SEIR_B200_ABI_VERSION 4
+#define SEIR_B200_ABI_VERSION 5
 
 typedef enum seir_status {
   SEIR_OK = 0,
