@@ -37,6 +37,20 @@ METRIC = "log-prob evals/sec (joint log-density, 382 LAD x 84 d)"
 UNIT = "evals/s"
 
 
+def _traffic(kernel_name):
+    """dram bytes per launch of a kernel from the committed ncu --set full capture (profiles/r01_traffic.json), or None."""
+    path = os.path.join(ROOT, "profiles", "r01_traffic.json")
+    if not os.path.exists(path):
+        return None
+    with open(path) as f:
+        ks = json.load(f)["kernels"]
+    base = kernel_name.split("<")[0]
+    for k, v in ks.items():
+        if k.split("<")[0] == base:
+            return v["dram_bytes_per_launch"]
+    return None
+
+
 def _peaks():
     path = os.path.join(ROOT, "MEASURED_PEAKS.json")
     if os.path.exists(path):
@@ -308,7 +322,8 @@ def run_native(args):
         cold_sum = sum(stage_ms[s] for s in cold_stages)
         dom = max((k for k in kernels if "frac" in k), key=lambda k: k["ms"])
         roofline = {"kernel": dom["kernel"], "bound": dom["bound"], "achieved": dom["achieved"], "peak": dom["peak"],
-                    "unit": dom["unit"], "frac": dom["frac"], "traffic": None, "share_of_step": dom["ms"] / cold_sum,
+                    "unit": dom["unit"], "frac": dom["frac"], "traffic": _traffic(dom["kernel"]),
+                    "traffic_unit": "dram bytes per launch (ncu --set full, profiles/r01_traffic.json)", "share_of_step": dom["ms"] / cold_sum,
                     "peak_source": (peak_src if dom["bound"] == "hbm" else "cuBLAS DGEMM 4096^3 measured in this run (FP64 is not in MEASURED_PEAKS.json)")}
         ach4 = alg_bytes[4] / (stage_ms[4] * 1e-3) / 1e9
         warm_grad = {"kernel": names[4], "ms": stage_ms[4], "bound": "hbm", "achieved": ach4, "peak": hbm_peak, "unit": "GB/s",
