@@ -7,7 +7,10 @@
 //                            every parameter-free piece of the log-pmf: sum of log binomial
 //                            coefficients, the E->I sufficient statistics and the per-day I->R
 //                            sufficient statistics (exact integer sums).
+#include <stdlib.h>
+
 #include "seir_internal.cuh"
+#include "tma.cuh"
 
 // ------------------------------------------------------------------------------------------------
 // compute_state: one warp per (b, m) row; lanes stride over days; 3 inclusive shuffle scans / 32 days
@@ -233,6 +236,11 @@ int seir_launch_ingest(seir_chains* c, const double* d_events, cudaStream_t s) {
 // B*T day slabs; lanes sweep the metapopulations of a slab with coalesced 128-byte loads.  One partial
 // per (chain, day) is written and reduced in fixed order by seir_finalize_kernel.
 // ------------------------------------------------------------------------------------------------
+__device__ __forceinline__ double log_binom_coef_n(int n, int y, const double* tab, int tabn) {  // table of tabn >= SEIR_LGTAB entries
+  if (n < tabn) return tab[n] - tab[n - y] - tab[y];
+  return log_binom_coef(n, y, tab);
+}
+
 __device__ __forceinline__ double log_binom_coef_tab(int n, int y, const double* tab) {
   if (n < SEIR_LGTAB_BIG) return tab[n] - tab[n - y] - tab[y];
   return log_binom_coef(n, y, tab);
@@ -272,22 +280,172 @@ __global__ void __launch_bounds__(1024, 1) seir_coef_kernel(int M, int T, int Mp
   }
 }
 
+// ------------------------------------------------------------------------------------------------
+// TMA-staged variant (default).  ncu on the kernel above (profiles/r01_v5_ncu_full_summary.md): 14 of 28 stall cycles
+// per issue are long-scoreboard -- the five global loads of a cell are not far enough ahead of the shared-memory
+// gathers that depend on them.  Here a producer warp streams batches of NB consecutive day slabs (yse | yei | yir | E | I,
+// NB*Mp*20 bytes; consecutive slabs are contiguous in every [B][T][Mp] array, across chain boundaries too) into a ring
+// beside the table with 1-D bulk copies; 24 consumer warps take 32 consecutive cells at a time (one slab, one
+// 32-metapopulation segment) and write ONE partial per (slab, segment) -- no block reduction.  seir_coef_reduce_kernel
+// then folds the partials of a chain in fixed order, once, so finalize reads a single number per chain.
+// ------------------------------------------------------------------------------------------------
+#define COEF_STAGES 3
+
+template <int COEF_CT, int MINB>
+__global__ void __launch_bounds__(COEF_CT + 32, MINB) seir_coef_tma_kernel(int M, int T, int Mp, int slabs, int NB, int nst, int tabn,
+                                                                        const int* __restrict__ init, const double* __restrict__ lgtab,
+                                                                        const int* __restrict__ yse, const int* __restrict__ yei,
+                                                                        const int* __restrict__ yir, const int* __restrict__ Sx,
+                                                                        const int* __restrict__ Ex, const int* __restrict__ Ix,
+                                                                        double* __restrict__ llc_part) {
+  extern __shared__ __align__(128) unsigned char coef_smem[];
+  __shared__ uint64_t full[COEF_STAGES], empty[COEF_STAGES];
+  double* lgs = reinterpret_cast<double*>(coef_smem);                           // [tabn]
+  unsigned char* ring = coef_smem + sizeof(double) * tabn;                     // [nst][5][NB*Mp] int
+  const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
+  const int arr = NB * Mp;                      // ints per array per stage
+  const size_t stage_bytes = (size_t)5 * arr * sizeof(int);
+  const int nbatch = (slabs + NB - 1) / NB;
+  const int nseg = Mp / 32;
+  if (tid == 0) {
+    for (int st = 0; st < nst; ++st) {
+      mbar_init(&full[st], 1);
+      mbar_init(&empty[st], COEF_CT / 32);
+    }
+    asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+  }
+  for (int k = tid; k < tabn; k += COEF_CT + 32) lgs[k] = lgtab[k];
+  __syncthreads();
+  if (warp == COEF_CT / 32) {  // producer
+    if (lane == 0) {
+      int j = 0;
+      for (int k = blockIdx.x; k < nbatch; k += gridDim.x, ++j) {
+        const int st = j % nst;
+        if (j >= nst) mbar_wait(&empty[st], (unsigned)((j / nst - 1) & 1));
+        const int n = min(NB, slabs - k * NB);
+        const unsigned bytes = (unsigned)((size_t)n * Mp * sizeof(int));
+        const size_t o = (size_t)k * NB * Mp;
+        int* dst = reinterpret_cast<int*>(ring + (size_t)st * stage_bytes);
+        mbar_expect_tx(&full[st], 5u * bytes);
+        bulk_load_1d(dst, yse + o, bytes, &full[st]);
+        bulk_load_1d(dst + arr, yei + o, bytes, &full[st]);
+        bulk_load_1d(dst + 2 * arr, yir + o, bytes, &full[st]);
+        bulk_load_1d(dst + 3 * arr, Ex + o, bytes, &full[st]);
+        bulk_load_1d(dst + 4 * arr, Ix + o, bytes, &full[st]);
+      }
+    }
+    return;
+  }
+  // Index arithmetic without per-cell divisions: a warp's 32 cells advance by COEF_CT per pass, (slab in batch, offset in
+  // slab) follow by subtraction; the day of a batch's first slab advances by a fixed stride per batch.
+  const int tstride = (int)(((long long)gridDim.x * NB) % T);
+  int t_first = (int)(((long long)blockIdx.x * NB) % T);  // day of the first slab of the current batch
+  int j = 0, st = 0;
+  unsigned phase = 0;
+  for (int k = blockIdx.x; k < nbatch; k += gridDim.x, ++j) {
+    mbar_wait(&full[st], phase);
+    const int* sy0 = reinterpret_cast<const int*>(ring + (size_t)st * stage_bytes);
+    const int n = min(NB, slabs - k * NB);
+    int s_in = 0, off = warp * 32;
+    while (off >= Mp) { off -= Mp; ++s_in; }
+    for (int c0 = warp * 32; c0 < n * Mp; c0 += COEF_CT) {  // 32 consecutive cells: one slab, one segment
+      const int m = off + lane, cell = c0 + lane;
+      const int slab = k * NB + s_in;
+      int t = t_first + s_in;
+      if (t >= T) t -= T;
+      double acc = 0.0;
+      const int y0 = sy0[cell], y1 = sy0[arr + cell], y2 = sy0[2 * arr + cell], E = sy0[3 * arr + cell], I = sy0[4 * arr + cell];
+      const bool ok = (m < M) & (y0 >= 0) & (y1 >= 0) & (y2 >= 0) & (y1 <= E) & (y2 <= I);
+      const bool small = (E < tabn) & (I < tabn) & (y0 < tabn);
+      if (__all_sync(0xffffffffu, small | !ok)) {  // (warp-uniform) every count inside the table: seven gathers, no branches
+        const int e = ok ? E : 0, i = ok ? I : 0, a = ok ? y1 : 0, b2 = ok ? y2 : 0, c = ok ? y0 : 0;
+        acc = ((lgs[e] - lgs[e - a]) - lgs[a]) + ((lgs[i] - lgs[i - b2]) - lgs[b2]) - lgs[c];  // all-zero indices give exactly 0
+      } else if (ok) {
+        acc = log_binom_coef_n(E, y1, lgs, tabn) + log_binom_coef_n(I, y2, lgs, tabn) - (y0 < tabn ? lgs[y0] : lgamma1p_int(y0, lgs));
+      }
+      if (t == T - 1 && m < M) {  // last day of a chain: the telescoped S->E term, once per metapopulation
+        const int S0 = init[m * 4 + 0], ST = __ldg(Sx + (size_t)slab * Mp + m) - y0;
+        if (ST >= 0 && ST <= S0) acc += lgamma_diff_exact(S0, S0 - ST, lgs);
+      }
+      acc = warp_sum(acc);
+      if (lane == 0) llc_part[(size_t)slab * nseg + (off >> 5)] = acc;
+      off += COEF_CT;
+      while (off >= Mp) { off -= Mp; ++s_in; }
+    }
+    __syncwarp();
+    if (lane == 0) mbar_arrive(&empty[st]);
+    if (++st == nst) { st = 0; phase ^= 1u; }
+    t_first += tstride;
+    if (t_first >= T) t_first -= T;
+  }
+}
+
+// fold the partials of each chain in fixed order: llc_sum[b] = sum_k llc_part[b*nper + k]
+__global__ void __launch_bounds__(256) seir_coef_reduce_kernel(int nper, const double* __restrict__ llc_part, double* __restrict__ llc_sum) {
+  __shared__ double red[32];
+  const int b = blockIdx.x;
+  double acc = 0.0;
+  for (int k = threadIdx.x; k < nper; k += 256) acc += llc_part[(size_t)b * nper + k];
+  const double tot = block_sum(acc, red);
+  if (threadIdx.x == 0) llc_sum[b] = tot;
+}
+
+template <int CT, int MINB>
+static int launch_coef_tma(seir_chains* c, int tabn, cudaStream_t s, int sms) {
+  const seir_model* m = c->model;
+  const int slabs = c->B * m->T;
+  const size_t table = sizeof(double) * tabn, budget = (size_t)(227 * 1024) / MINB - 1024 - table;
+  int nst = COEF_STAGES;
+  int NB = (int)(budget / nst / ((size_t)m->Mp * 20));
+  if (NB < 1) {  // wide models: two stages of one day slab
+    nst = 2;
+    NB = (int)(budget / nst / ((size_t)m->Mp * 20));
+  }
+  if (NB < 1) return 1;  // does not fit: caller falls back
+  if (NB > 4) NB = 4;
+  const size_t smem = table + (size_t)nst * NB * m->Mp * 20;
+  static size_t attr = 0;
+  if (attr != smem) {
+    SEIR_CUDA(cudaFuncSetAttribute(seir_coef_tma_kernel<CT, MINB>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+    attr = smem;
+  }
+  const int nbatch = (slabs + NB - 1) / NB, grid = sms * MINB;
+  seir_coef_tma_kernel<CT, MINB><<<nbatch < grid ? nbatch : grid, CT + 32, smem, s>>>(m->M, m->T, m->Mp, slabs, NB, nst, tabn, m->d_init,
+                                                                                     m->d_lgtab, c->d_yse, c->d_yei, c->d_yir, c->d_S,
+                                                                                     c->d_E, c->d_I, c->d_llc_part);
+  return 0;
+}
+
 int seir_launch_coef(seir_chains* c, cudaStream_t s) {
   const seir_model* m = c->model;
-  static int sms = 0;
-  const size_t smem = sizeof(double) * SEIR_LGTAB_BIG;
+  static int sms = 0, variant = -1;
   if (!sms) {
     int dev = 0;
     cudaGetDevice(&dev);
     cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev);
-    SEIR_CUDA(cudaFuncSetAttribute(seir_coef_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+    SEIR_CUDA(cudaFuncSetAttribute(seir_coef_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)(sizeof(double) * SEIR_LGTAB_BIG)));
+    // experiments: 0 direct loads; 1 TMA ring, one 800-thread CTA per SM, 16384-entry table; 2 TMA ring, one 1024-thread CTA;
+    // 3 TMA ring, two 640-thread CTAs per SM with an 8192-entry table each (counts beyond the table take the Stirling path)
+    // Measured at the UK size, B = 256 (CUDA events): 0: 88 us, 1: 87 us, 2: 80 us, 3: 81 us -- the kernel is bound by the
+    // conflicting 8-byte shared-memory gathers (7 per cell, ~14 M wavefronts), not by global-load latency or occupancy.
+    const char* e = getenv("SEIR_COEF_VARIANT");
+    variant = e ? atoi(e) : 2;
   }
   const int slabs = c->B * m->T;
-  c->nllc = m->T;
-  int grid = (slabs + 31) / 32;
-  if (grid > sms) grid = sms;
-  seir_coef_kernel<<<grid, 1024, smem, s>>>(m->M, m->T, m->Mp, slabs, m->d_init, m->d_lgtab, c->d_yse, c->d_yei, c->d_yir, c->d_S,
-                                            c->d_E, c->d_I, c->d_llc_part);
-  seir_count_launch(1);
+  int nper = m->T * (m->Mp / 32), rc = 1;
+  if (variant == 1) rc = launch_coef_tma<768, 1>(c, SEIR_LGTAB_BIG, s, sms);
+  if (variant == 2) rc = launch_coef_tma<992, 1>(c, SEIR_LGTAB_BIG, s, sms);
+  if (variant == 3) rc = launch_coef_tma<608, 2>(c, SEIR_LGTAB_BIG / 2, s, sms);
+  if (rc < 0) return rc;
+  if (rc != 0) {
+    int grid = (slabs + 31) / 32;
+    if (grid > sms) grid = sms;
+    nper = m->T;
+    seir_coef_kernel<<<grid, 1024, sizeof(double) * SEIR_LGTAB_BIG, s>>>(m->M, m->T, m->Mp, slabs, m->d_init, m->d_lgtab, c->d_yse, c->d_yei,
+                                                                         c->d_yir, c->d_S, c->d_E, c->d_I, c->d_llc_part);
+  }
+  seir_coef_reduce_kernel<<<c->B, 256, 0, s>>>(nper, c->d_llc_part, c->d_llc_sum);
+  c->nllc = 1;
+  seir_count_launch(2);
   return seir_cuda_check(cudaGetLastError(), "seir_coef_kernel");
 }

@@ -12,6 +12,7 @@
 
 #include "seir_internal.cuh"
 #include "theta_fin.cuh"
+#include "tma.cuh"
 
 // ------------------------------------------------------------------------------------------------
 tf_model seir_tf_model(const seir_model* m) {
@@ -27,7 +28,7 @@ tf_chains seir_tf_chains(const seir_chains* c) {
   tf_chains v;
   v.pa = c->d_pa; v.psiW = c->d_psiW; v.gam = c->d_gam; v.logpir = c->d_logpir; v.pm = c->d_pm; v.scal = c->d_scal; v.carq = c->d_carq;
   v.val_part = c->d_val_part; v.psi_part = c->d_psi_part; v.col_part = c->d_col_part; v.rowsum = c->d_rowsum;
-  v.llc_part = c->d_llc_part; v.llc_adj = c->d_llc_adj;
+  v.llc_part = c->d_llc_sum; v.llc_adj = c->d_llc_adj;
   v.Yir = c->d_Yir; v.Rir = c->d_Rir; v.sumYei = c->d_sumYei; v.sumEres = c->d_sumEres; v.flags = c->d_flags;
   v.nblkLL = c->nblk_last ? c->nblk_last : c->nblkLL; v.nts = c->nts; v.nllc = c->nllc;
   return v;
@@ -264,34 +265,6 @@ __global__ void __launch_bounds__(SEIR_LL_THREADS, GRAD ? 6 : 10) seir_loglik_ke
 // every cell valid (no per-cell predicates).
 // ------------------------------------------------------------------------------------------------
 #define LL_STAGE_DAYS LL_UNROLL
-
-__device__ __forceinline__ unsigned smem_u32(const void* p) { return (unsigned)__cvta_generic_to_shared(p); }
-__device__ __forceinline__ void mbar_init(uint64_t* bar, unsigned count) {
-  asm volatile("mbarrier.init.shared::cta.b64 [%0], %1;" ::"r"(smem_u32(bar)), "r"(count) : "memory");
-}
-__device__ __forceinline__ void mbar_expect_tx(uint64_t* bar, unsigned bytes) {
-  asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"(smem_u32(bar)), "r"(bytes) : "memory");
-}
-__device__ __forceinline__ void bulk_load_1d(void* dst, const void* src, unsigned bytes, uint64_t* bar) {
-  asm volatile("cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1], %2, [%3];" ::"r"(smem_u32(dst)),
-               "l"(src), "r"(bytes), "r"(smem_u32(bar))
-               : "memory");
-}
-__device__ __forceinline__ void mbar_wait(uint64_t* bar, unsigned parity) {
-  unsigned done = 0;
-  for (unsigned spins = 0; !done; ++spins) {
-    asm volatile(
-        "{\n\t.reg .pred p;\n\tmbarrier.try_wait.parity.shared::cta.b64 p, [%1], %2;\n\tselp.u32 %0, 1, 0, p;\n\t}"
-        : "=r"(done)
-        : "r"(smem_u32(bar)), "r"(parity)
-        : "memory");
-    if (spins > (1u << 24)) __trap();  // a copy that never lands must fail loudly, not hang the device
-  }
-}
-
-__device__ __forceinline__ void mbar_arrive(uint64_t* bar) {
-  asm volatile("mbarrier.arrive.shared::cta.b64 _, [%0];" ::"r"(smem_u32(bar)) : "memory");
-}
 
 // NTHR consumer threads (thread <-> metapopulation, MPT of them each) + ONE producer warp.  The producer's elected lane
 // refills a stage as soon as every consumer WARP has released it (empty[] mbarrier, one arrival per warp), so warps

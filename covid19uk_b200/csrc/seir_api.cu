@@ -189,7 +189,7 @@ int seir_chains_create(const seir_model* m, int B, seir_chains** out) {
   if ((rc = dev_alloc(&c->d_yse, cells, &c->bytes)) || (rc = dev_alloc(&c->d_yei, cells, &c->bytes)) ||
       (rc = dev_alloc(&c->d_yir, cells, &c->bytes)) || (rc = dev_alloc(&c->d_S, cells, &c->bytes)) ||
       (rc = dev_alloc(&c->d_E, cells, &c->bytes)) || (rc = dev_alloc(&c->d_I, cells, &c->bytes)) ||
-      (rc = dev_alloc(&c->d_Bc, cells, &c->bytes)) || (rc = dev_alloc(&c->d_llc_part, BT, &c->bytes)) ||
+      (rc = dev_alloc(&c->d_Bc, cells, &c->bytes)) || (rc = dev_alloc(&c->d_llc_part, BT * (m->Mp / 32), &c->bytes)) || (rc = dev_alloc(&c->d_llc_sum, (size_t)B, &c->bytes)) ||
       (rc = dev_alloc(&c->d_Yir, 2 * BT + 2 * (size_t)B + ((size_t)B + 1) / 2, &c->bytes)) || (rc = dev_alloc(&c->d_pa, BT, &c->bytes)) ||
       (rc = dev_alloc(&c->d_psiW, BT, &c->bytes)) || (rc = dev_alloc(&c->d_gam, BT, &c->bytes)) ||
       (rc = dev_alloc(&c->d_logpir, BT, &c->bytes)) || (rc = dev_alloc(&c->d_pm, (size_t)B * m->Mp, &c->bytes)) ||
@@ -225,7 +225,7 @@ void seir_chains_destroy(seir_chains* c) {
   if (!c) return;
   cudaSetDevice(c->model->device);
   cudaFree(c->d_yse); cudaFree(c->d_yei); cudaFree(c->d_yir); cudaFree(c->d_S); cudaFree(c->d_E); cudaFree(c->d_I);
-  cudaFree(c->d_Bc); cudaFree(c->d_llc_part); cudaFree(c->d_Yir); cudaFree(c->d_pa); cudaFree(c->d_psiW); cudaFree(c->d_gam);
+  cudaFree(c->d_Bc); cudaFree(c->d_llc_part); cudaFree(c->d_llc_sum); cudaFree(c->d_Yir); cudaFree(c->d_pa); cudaFree(c->d_psiW); cudaFree(c->d_gam);
   cudaFree(c->d_logpir); cudaFree(c->d_pm); cudaFree(c->d_scal); cudaFree(c->d_carq); cudaFree(c->d_val_part); cudaFree(c->d_psi_part);
   cudaFree(c->d_col_part); cudaFree(c->d_rowsum); cudaFree(c->d_upd); cudaFree(c->d_upd_part); cudaFree(c->d_llc_adj);
   cudaFree(c->d_tlp); cudaFree(c->d_last_acc); cudaFree(c->d_nzd); cudaFree(c->d_hmc_u0); cudaFree(c->d_hmc_p); cudaFree(c->d_hmc_grad);

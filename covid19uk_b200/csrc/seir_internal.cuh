@@ -83,13 +83,14 @@ struct seir_chains {
   int nblk_last;  // metapopulation column blocks used by the last log-likelihood launch
   size_t ll_attr_smem[2];  // dynamic shared memory the log-likelihood kernels were last configured for
   int ll_dps[2];  // days per CTA of the log-likelihood kernel (value / value+gradient), chosen on first launch
-  int nllc;     // number of llc partials per chain written by the last coefficient launch
+  int nllc;     // entries of d_llc_sum per chain (1 once the coefficient kernels have run)
   size_t stats_bytes;  // bytes of the contiguous integer-statistics block starting at d_Yir
   int64_t bytes;
   // events-only caches, day-slab layout [B][T][Mp]
   int *d_yse, *d_yei, *d_yir, *d_S, *d_E, *d_I;
   double* d_Bc;          // [B][T][Mp]  Cstar . (I/N)
-  double* d_llc_part;    // [B][nllc] parameter-free log-pmf partials (log binomial coefficients)
+  double* d_llc_part;    // [B][T][Mp/32] parameter-free log-pmf partials (log binomial coefficients), scratch of the coefficient kernel
+  double* d_llc_sum;     // [B] their per-chain sum (what finalize reads)
   long long* d_Yir;      // [B][T]  sum_m y_ir
   long long* d_Rir;      // [B][T]  sum_m (I - y_ir)
   long long* d_sumYei;   // [B]
