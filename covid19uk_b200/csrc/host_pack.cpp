@@ -7,6 +7,7 @@
 // Plain C++ (g++), no CUDA: compiled separately and linked into libseir_b200.so.
 #include <stdint.h>
 #include <stddef.h>
+#include <stdlib.h>
 
 #include <atomic>
 #include <condition_variable>
@@ -107,6 +108,15 @@ extern "C" {
 int seir_pack_threads(void) {
   unsigned hc = std::thread::hardware_concurrency();
   if (hc == 0) hc = 4;
+  if (const char* e = getenv("SEIR_PACK_THREADS")) {
+    const int n = atoi(e);
+    if (n >= 1) return n > 64 ? 64 : n;
+  }
+  // one process per GPU: the ranks of a node share its cores (torchrun exports LOCAL_WORLD_SIZE)
+  if (const char* e = getenv("LOCAL_WORLD_SIZE")) {
+    const int lw = atoi(e);
+    if (lw > 1) hc = hc / (unsigned)lw > 2 ? hc / (unsigned)lw : 2;
+  }
   int n = (int)hc - 1;  // the calling thread drives the copies
   if (n < 1) n = 1;
   if (n > 32) n = 32;
