@@ -39,6 +39,7 @@ def _make_tf():
     tf.where = np.where
     tf.broadcast_to = lambda x, shape: np.broadcast_to(np.asarray(x), shape)
     tf.stack = lambda values, axis=0: np.stack(values, axis=axis)
+    tf.eye = lambda n, dtype=np.float64: np.eye(n, dtype=dtype)
     tf.concat = lambda values, axis=0: np.concatenate(values, axis=axis)
     tf.name_scope = lambda name: contextlib.nullcontext()
     tf.function = lambda *a, **k: (a[0] if a and callable(a[0]) else (lambda f: f))
