@@ -17,7 +17,7 @@ PART_SEIR = 1
 PART_PRIORS = 2
 PART_ILDJ = 4
 PART_JOINT = 7
-ABI_VERSION = 5
+ABI_VERSION = 6
 
 
 class SeirSpec(ctypes.Structure):
@@ -91,6 +91,8 @@ SIGNATURES = {
     "seir_propose": (c_int, [c_void_p, c_void_p, ctypes.c_uint64, ctypes.c_uint32, ctypes.c_uint32, c_void_p, c_void_p, c_void_p]),
     "seir_mcmc_sweep": (c_int, [c_void_p, c_void_p, ctypes.c_uint32] + [c_void_p] * 10),
     "seir_export_events": (c_int, [c_void_p, c_void_p, c_void_p]),
+    "seir_reproduction_number": (c_int, [c_void_p, c_void_p, c_void_p, c_void_p]),
+    "seir_pressure_components": (c_int, [c_void_p, c_void_p, c_void_p, c_void_p, c_void_p]),
     "seir_chain_flags": (c_int, [c_void_p, c_void_p, c_void_p]),
     "seir_launch_count": (c_int64, []),
 }

@@ -91,10 +91,12 @@ int seir_model_create(const seir_spec* spec, int device, seir_model** out) {
   const int Mp = m->Mp;
 
   std::vector<double> cstar((size_t)Mp * Mp, 0.0), rN(Mp, 0.0), la(Mp, 0.0), W(T), wk(T), lgtab(SEIR_LGTAB_BIG);
+  std::vector<double> cst((size_t)Mp * Mp, 0.0);
   std::vector<int> init((size_t)Mp * 4, 0), aidx(T);
   for (int i = 0; i < M; ++i) {
     rN[i] = 1.0 / spec->population[i];
     for (int j = 0; j < M; ++j) cstar[(size_t)i * Mp + j] = spec->cstar[(size_t)i * M + j] * rN[i];
+    for (int j = 0; j < M; ++j) cst[(size_t)j * Mp + i] = cstar[(size_t)i * Mp + j];
     la[i] = spec->log_area_c[i];
     for (int s = 0; s < 4; ++s) {
       const double v = spec->initial_state[i * 4 + s];
@@ -140,7 +142,8 @@ int seir_model_create(const seir_spec* spec, int device, seir_model** out) {
   std::vector<double> values(spec->car_values, spec->car_values + spec->car_nnz);
 
   int rc = SEIR_OK;
-  if ((rc = dev_upload(&m->d_cs, cstar)) || (rc = dev_upload(&m->d_rN, rN)) || (rc = dev_upload(&m->d_W, W)) ||
+  m->w_last = spec->commute_volume[spec->n_commute_volume - 1];
+  if ((rc = dev_upload(&m->d_cs, cstar)) || (rc = dev_upload(&m->d_cst, cst)) || (rc = dev_upload(&m->d_rN, rN)) || (rc = dev_upload(&m->d_W, W)) ||
       (rc = dev_upload(&m->d_wk, wk)) || (rc = dev_upload(&m->d_aidx, aidx)) || (rc = dev_upload(&m->d_tfirst, tfirst)) || (rc = dev_upload(&m->d_la, la)) ||
       (rc = dev_upload(&m->d_init, init)) || (rc = dev_upload(&m->d_car_indptr, indptr)) ||
       (rc = dev_upload(&m->d_car_indices, indices)) || (rc = dev_upload(&m->d_car_values, values)) ||
@@ -155,7 +158,7 @@ int seir_model_create(const seir_spec* spec, int device, seir_model** out) {
 void seir_model_destroy(seir_model* m) {
   if (!m) return;
   cudaSetDevice(m->device);
-  cudaFree(m->d_cs); cudaFree(m->d_rN); cudaFree(m->d_W); cudaFree(m->d_wk); cudaFree(m->d_aidx); cudaFree(m->d_tfirst); cudaFree(m->d_la);
+  cudaFree(m->d_cs); cudaFree(m->d_cst); cudaFree(m->d_rN); cudaFree(m->d_W); cudaFree(m->d_wk); cudaFree(m->d_aidx); cudaFree(m->d_tfirst); cudaFree(m->d_la);
   cudaFree(m->d_init); cudaFree(m->d_car_indptr); cudaFree(m->d_car_indices); cudaFree(m->d_car_values); cudaFree(m->d_lgtab); cudaFree(m->d_logtab);
   delete m;
 }
@@ -504,6 +507,20 @@ int seir_export_events(seir_chains* c, double* d_events, void* stream) {
   if (!c) return seir_set_error(SEIR_ERR_BAD_ARG, "seir_export_events: NULL chains");
   SEIR_TRY(check_dev_ptr(d_events, "d_events"));
   return seir_launch_export_events(c, d_events, (cudaStream_t)stream);
+}
+
+int seir_reproduction_number(seir_chains* c, const double* d_theta, double* d_rit, void* stream) {
+  if (!c || !d_rit) return seir_set_error(SEIR_ERR_BAD_ARG, "seir_reproduction_number: NULL argument");
+  SEIR_TRY(check_dev_ptr(d_theta, "d_theta"));
+  if (c->model->initial_step != 0)
+    return seir_set_error(SEIR_ERR_UNSUPPORTED, "seir_reproduction_number: the reference evaluates the NGM at t = 0..T-1 of the inference window (initial_step 0)");
+  return seir_launch_rit(c, d_theta, d_rit, (cudaStream_t)stream);
+}
+
+int seir_pressure_components(seir_chains* c, const double* d_theta, double* d_within, double* d_between, void* stream) {
+  if (!c || !d_within || !d_between) return seir_set_error(SEIR_ERR_BAD_ARG, "seir_pressure_components: NULL argument");
+  SEIR_TRY(check_dev_ptr(d_theta, "d_theta"));
+  return seir_launch_pressure(c, d_theta, d_within, d_between, (cudaStream_t)stream);
 }
 
 int seir_chain_flags(const seir_chains* c, int32_t* d_flags_out, void* stream) {

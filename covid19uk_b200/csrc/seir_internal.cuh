@@ -35,6 +35,8 @@ struct seir_model {
   int car_nnz;
   // device arrays
   double* d_cs;        // [Mp*Mp] zero padded: Cs[j][i] = Cstar[j][i] / N[j]  (Cstar symmetric, model_spec.py:216-219)
+  double* d_cst;       // [Mp*Mp] its transpose: Cst[i][j] = Cstar[i][j] / N[j]  (next-generation matrix, analytics.cu)
+  double w_last;       // last entry of the commute-volume series (within_between.py evaluates its rates at t = len(W))
   double* d_rN;        // [Mp] 1/N, 0 in the padding
   double* d_W;         // [T] commute volume resolved per step (model_spec.py:234-235)
   double* d_wk;        // [T] centred weekday resolved per step (model_spec.py:237-240)
@@ -177,6 +179,8 @@ int seir_launch_sweep(seir_chains* c, const seir_sweep_spec* sp, unsigned sweep_
                       const double* d_inv_mass, double* d_tlp, int* d_hmc_accept, double* d_hmc_dbg, int* d_upd_accept,
                       double* d_upd_tlp, int* d_upd_trace, cudaStream_t s);
 int seir_launch_export_events(seir_chains* c, double* d_events, cudaStream_t s);
+int seir_launch_rit(seir_chains* c, const double* d_theta, double* d_out, cudaStream_t s);
+int seir_launch_pressure(seir_chains* c, const double* d_theta, double* d_within, double* d_between, cudaStream_t s);
 int seir_launch_update(seir_chains* c, const seir_update_cfg& cfg, int slot, const int* d_proposal, const double* d_log_u,
                        double* d_tlp, int* d_accept, int* d_trace, double* d_dbg, cudaStream_t s);
 

@@ -263,6 +263,25 @@ class SeirEngine:
         nat.check(self.lib.seir_export_events(self.chains(B), c_void_p(out.data_ptr()), self._stream()))
         return out
 
+    # ---- f4: posterior analytics on the cached state of the ingested events ----
+    def reproduction_number(self, theta) -> torch.Tensor:
+        """R_it [B,T,M] (posterior/reproduction_number.py:13-45); `theta` [B,P] CONSTRAINED; events ingested before."""
+        th = self.to_device(theta, (self.P,))
+        B = th.shape[0]
+        out = torch.empty((B, self.T, self.M), dtype=torch.float64, device=self.device)
+        nat.check(self.lib.seir_reproduction_number(self.chains(B), c_void_p(th.data_ptr()), c_void_p(out.data_ptr()), self._stream()))
+        return out
+
+    def pressure_components(self, theta):
+        """(within, between) [B,M] infection pressure at the final state (posterior/within_between.py:13-56)."""
+        th = self.to_device(theta, (self.P,))
+        B = th.shape[0]
+        within = torch.empty((B, self.M), dtype=torch.float64, device=self.device)
+        between = torch.empty_like(within)
+        nat.check(self.lib.seir_pressure_components(self.chains(B), c_void_p(th.data_ptr()), c_void_p(within.data_ptr()),
+                                                    c_void_p(between.data_ptr()), self._stream()))
+        return within, between
+
     def chain_flags(self, B: int) -> torch.Tensor:
         out = torch.empty((B,), dtype=torch.int32, device=self.device)
         nat.check(self.lib.seir_chain_flags(self.chains(B), c_void_p(out.data_ptr()), self._stream()))

@@ -10,7 +10,7 @@ from __future__ import annotations
 
 import numpy as np
 
-from . import hdf5_min
+from .. import hdf5_min
 
 
 def _to_numpy(x):

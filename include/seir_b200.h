@@ -27,7 +27,7 @@
 extern "C" {
 #endif
 
-#define SEIR_B200_ABI_VERSION 5
+#define SEIR_B200_ABI_VERSION 6
 
 typedef enum seir_status {
   SEIR_OK = 0,
@@ -216,6 +216,17 @@ int seir_mcmc_sweep(seir_chains* chains, const seir_sweep_spec* spec, uint32_t s
 
 /* Current events of every chain back in the reference layout: d_events [B,M,T,3] f64. */
 int seir_export_events(seir_chains* chains, double* d_events, void* stream);
+
+/* f4: posterior/reproduction_number.py:13-45 (calc_posterior_rit) over the chain axis as the posterior-sample axis:
+ * R[b,t,j] = sum_i NGM_t[i,j] with the next-generation matrix of model_spec.py:300-367, from the cached state of the
+ * ingested events.  d_theta [B,P] CONSTRAINED parameters, d_rit [B,T,M].  (initial_step must be 0, as in the
+ * reference's inference window.) */
+int seir_reproduction_number(seir_chains* chains, const double* d_theta, double* d_rit, void* stream);
+
+/* f4: posterior/within_between.py:13-56 (make_within_rate_fns at the final state, t = len(W)):
+ * d_within / d_between [B,M] infection pressure from inside / outside each metapopulation. */
+int seir_pressure_components(seir_chains* chains, const double* d_theta, double* d_within, double* d_between,
+                             void* stream);
 
 /* Per-chain status bits set by ingest / commits: bit0 = events not non-negative integers,
  * bit1 = reconstructed state negative or events exceed the source compartment (log-prob = -inf). */

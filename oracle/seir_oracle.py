@@ -636,3 +636,52 @@ def hmc_transition(value_and_grad_fn, u0, momentum, log_u, step_size, num_leapfr
         accept = True
     return dict(is_accepted=accept, state=u if accept else u0, target_log_prob=tlp if accept else tlp0,
                 proposed_state=u, proposed_tlp=tlp, log_accept_ratio=ratio)
+
+
+# --------------------------------------------------------------------------------------------
+# f4  posterior analytics: next-generation matrix / R_it and within/between pressure
+#     Fully specified in-tree => pinned by tests/golden/ref_ngm_*.npz (the reference's own functions run
+#     under the numpy shim, tests/golden/make_golden_ngm.py).
+# --------------------------------------------------------------------------------------------
+def next_generation_matrix(covariates, params, t, state):
+    """``next_generation_matrix_fn(covar_data, param)(t, state)`` (model_spec.py:300-367) -> [M, M].
+
+    Reference quirks kept: ``eta`` is ``[M,1] + [M]`` (:344-348), i.e. the area effect varies along the ROW and
+    the spatial effect along the COLUMN; the alpha_t path is indexed with ``t`` (:332-342), not ``t-1`` as in
+    ``transition_rate_fn``; ``1 - exp(-x)`` is formed literally (:358)."""
+    consts = rate_constants(covariates)  # same C / Cstar / N / centred log-area construction (:316-327)
+    Cstar, W, N, log_area = consts["Cstar"], consts["W"], consts["N"], consts["log_area_c"]
+    t = int(t)
+    commute_volume = W[min(max(t, 0), W.shape[0] - 1)]  # :329-330
+    alpha_t = np.asarray(params["alpha_t"], DTYPE)
+    b_t = params["alpha_0"] + np.cumsum(alpha_t)  # :331
+    a = params["alpha_0"] if t == 0 else b_t[min(max(t, 0), alpha_t.shape[-1] - 1)]  # :332-342
+    eta = a + params["beta_area"] * log_area[:, None] + params["sigma_space"] * np.asarray(params["spatial_effect"], DTYPE)  # :344-348
+    M = Cstar.shape[0]
+    infec_rate = np.exp(eta) * (np.eye(M) + params["psi"] * commute_volume * Cstar / N[None, :]) / N[:, None]  # :349-357
+    infec_prob = 1.0 - np.exp(-infec_rate)  # :358
+    expected_new_infec = infec_prob * np.asarray(state, DTYPE)[..., 0][..., None]  # :360
+    expected_infec_period = 1.0 / (1.0 - np.exp(-np.exp(params["gamma0"])))  # :361-363
+    return expected_new_infec * expected_infec_period  # :364
+
+
+def posterior_rit(covariates, params, initial_state, events, times=None):
+    """One sample of ``calc_posterior_rit`` (posterior/reproduction_number.py:13-45): R[t, j] = sum_i ngm_t[i, j]."""
+    state = compute_state(initial_state, events)
+    times = np.arange(events.shape[-2]) if times is None else np.asarray(times)
+    return np.stack([next_generation_matrix(covariates, params, t, state[:, t, :]).sum(axis=-2) for t in times])
+
+
+def pressure_components(covariates, psi, state):
+    """``make_within_rate_fns`` + ``calc_pressure_components`` for one sample (posterior/within_between.py:13-56):
+    state [M, 4] -> (within / total, between / total, within, between); t = W.shape[0] (clipped to the last W)."""
+    C = np.array(covariates["C"], DTYPE)
+    np.fill_diagonal(C, 0.0)  # :16
+    W = np.atleast_1d(np.squeeze(np.asarray(covariates["W"], DTYPE)))  # :18-20
+    N = np.atleast_1d(np.squeeze(np.asarray(covariates["N"], DTYPE)))  # :21-23
+    commute_volume = W[W.shape[0] - 1]  # :26-27, :35-36 with t = W.shape[0]
+    infected = np.asarray(state, DTYPE)[..., 2]
+    within = infected - psi * infected / N * commute_volume * np.sum(C, axis=-2)  # :28-30
+    between = psi * commute_volume * ((C + C.T) @ (infected / N))  # :37-41
+    total = within + between
+    return within / total, between / total, within, between

@@ -1,6 +1,7 @@
 """Pin the oracle against fixtures produced by executing the reference's own model_spec.py /
 joint_log_prob closure (tests/golden/make_golden.py).  CPU only."""
 import numpy as np
+import pytest
 
 from oracle import seir_oracle as so
 
@@ -49,3 +50,25 @@ def test_joint_log_prob_and_bijector(golden):
         got = model.joint_log_prob(u, golden["events"])
         ref = float(golden[key])
         assert abs(got - ref) <= 1e-12 * abs(ref), (key, got, ref)
+
+
+NGM_CASES = ["ref_ngm_M11_T32_s0", "ref_ngm_M23_T17_s2", "ref_ngm_M60_T40_s3"]
+
+
+@pytest.mark.parametrize("case", NGM_CASES)
+def test_next_generation_matrix_and_pressure_match_reference(case):
+    """Oracle vs the reference's own next_generation_matrix_fn / make_within_rate_fns (run under the numpy shim)."""
+    import os
+
+    g = np.load(os.path.join(os.path.dirname(__file__), "golden", case + ".npz"))
+    M, T = int(g["M"]), int(g["T"])
+    cov = {k: g[k] for k in ("C", "W", "N", "adjacency", "weekday", "area")}
+    params = so.unpack_params(g["theta"], M, T)
+    events = g["events"].astype(np.float64)
+    state = so.compute_state(g["initial_state"], events)
+    np.testing.assert_allclose(so.next_generation_matrix(cov, params, 0, state[:, 0]), g["ngm_t0"], rtol=1e-13, atol=0)
+    np.testing.assert_allclose(so.next_generation_matrix(cov, params, T - 1, state[:, T - 1]), g["ngm_tlast"], rtol=1e-13, atol=0)
+    np.testing.assert_allclose(so.posterior_rit(cov, params, g["initial_state"], events), g["r_it"], rtol=1e-12)
+    _, _, within, between = so.pressure_components(cov, params["psi"], state[:, -1])
+    np.testing.assert_allclose(within, g["within"], rtol=1e-13)
+    np.testing.assert_allclose(between, g["between"], rtol=1e-13)
