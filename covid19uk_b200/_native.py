@@ -91,6 +91,7 @@ SIGNATURES = {
     "seir_propose": (c_int, [c_void_p, c_void_p, ctypes.c_uint64, ctypes.c_uint32, ctypes.c_uint32, c_void_p, c_void_p, c_void_p]),
     "seir_mcmc_sweep": (c_int, [c_void_p, c_void_p, ctypes.c_uint32] + [c_void_p] * 10),
     "seir_export_events": (c_int, [c_void_p, c_void_p, c_void_p]),
+    "seir_simulate": (c_int, [c_void_p, c_int, ctypes.c_uint64, ctypes.c_uint32, c_void_p, c_void_p, c_void_p, c_void_p, c_void_p, c_void_p]),
     "seir_reproduction_number": (c_int, [c_void_p, c_void_p, c_void_p, c_void_p]),
     "seir_pressure_components": (c_int, [c_void_p, c_void_p, c_void_p, c_void_p, c_void_p]),
     "seir_chain_flags": (c_int, [c_void_p, c_void_p, c_void_p]),

@@ -509,6 +509,16 @@ int seir_export_events(seir_chains* c, double* d_events, void* stream) {
   return seir_launch_export_events(c, d_events, (cudaStream_t)stream);
 }
 
+int seir_simulate(const seir_model* m, int B, uint64_t seed, uint32_t chain_offset, const double* d_alpha_path, const double* d_scalars,
+                  const double* d_spatial_effect, const double* d_initial_state, double* d_events, void* stream) {
+  if (!m || !d_alpha_path || !d_scalars || !d_spatial_effect || !d_initial_state)
+    return seir_set_error(SEIR_ERR_BAD_ARG, "seir_simulate: NULL argument");
+  if (B < 1 || B > 65535) return seir_set_error(SEIR_ERR_SHAPE, "seir_simulate: need 1 <= num_samples <= 65535");
+  SEIR_TRY(check_dev_ptr(d_events, "d_events"));
+  return seir_launch_simulate(m, B, seed, chain_offset, d_alpha_path, d_scalars, d_spatial_effect, d_initial_state, d_events,
+                              (cudaStream_t)stream);
+}
+
 int seir_reproduction_number(seir_chains* c, const double* d_theta, double* d_rit, void* stream) {
   if (!c || !d_rit) return seir_set_error(SEIR_ERR_BAD_ARG, "seir_reproduction_number: NULL argument");
   SEIR_TRY(check_dev_ptr(d_theta, "d_theta"));

@@ -179,6 +179,8 @@ int seir_launch_sweep(seir_chains* c, const seir_sweep_spec* sp, unsigned sweep_
                       const double* d_inv_mass, double* d_tlp, int* d_hmc_accept, double* d_hmc_dbg, int* d_upd_accept,
                       double* d_upd_tlp, int* d_upd_trace, cudaStream_t s);
 int seir_launch_export_events(seir_chains* c, double* d_events, cudaStream_t s);
+int seir_launch_simulate(const seir_model* m, int B, unsigned long long seed, unsigned chain0, const double* d_alpha_path,
+                         const double* d_scal, const double* d_spatial, const double* d_init_state, double* d_events, cudaStream_t s);
 int seir_launch_rit(seir_chains* c, const double* d_theta, double* d_out, cudaStream_t s);
 int seir_launch_pressure(seir_chains* c, const double* d_theta, double* d_within, double* d_between, cudaStream_t s);
 int seir_launch_update(seir_chains* c, const seir_update_cfg& cfg, int slot, const int* d_proposal, const double* d_log_u,

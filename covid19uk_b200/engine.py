@@ -263,6 +263,22 @@ class SeirEngine:
         nat.check(self.lib.seir_export_events(self.chains(B), c_void_p(out.data_ptr()), self._stream()))
         return out
 
+    # ---- f4: forward simulation (model.sample) ----
+    def simulate(self, alpha_path, scalars, spatial_effect, initial_state, seed=0, chain_offset=0) -> torch.Tensor:
+        """Chain-binomial simulation of B samples over this model's steps -> events [B,M,T,3] (CUDA float64).
+        alpha_path [B,T] resolved per-step log-rate offsets, scalars [B,5] (psi, sigma_space, beta_area, gamma0, gamma1),
+        spatial_effect [B,M], initial_state [B,M,4]."""
+        dev = lambda a: (a if isinstance(a, torch.Tensor) else torch.as_tensor(np.asarray(a, dtype=np.float64))).to(
+            device=self.device, dtype=torch.float64).contiguous()
+        ap, sc, sp, st = dev(alpha_path), dev(scalars), dev(spatial_effect), dev(initial_state)
+        B = ap.shape[0]
+        assert tuple(ap.shape) == (B, self.T) and tuple(sc.shape) == (B, 5) and tuple(sp.shape) == (B, self.M)
+        assert tuple(st.shape) == (B, self.M, 4)
+        out = torch.empty((B, self.M, self.T, 3), dtype=torch.float64, device=self.device)
+        nat.check(self.lib.seir_simulate(self._model, B, int(seed), int(chain_offset), c_void_p(ap.data_ptr()), c_void_p(sc.data_ptr()),
+                                         c_void_p(sp.data_ptr()), c_void_p(st.data_ptr()), c_void_p(out.data_ptr()), self._stream()))
+        return out
+
     # ---- f4: posterior analytics on the cached state of the ingested events ----
     def reproduction_number(self, theta) -> torch.Tensor:
         """R_it [B,T,M] (posterior/reproduction_number.py:13-45); `theta` [B,P] CONSTRAINED; events ingested before."""

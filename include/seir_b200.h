@@ -217,6 +217,17 @@ int seir_mcmc_sweep(seir_chains* chains, const seir_sweep_spec* spec, uint32_t s
 /* Current events of every chain back in the reference layout: d_events [B,M,T,3] f64. */
 int seir_export_events(seir_chains* chains, double* d_events, void* stream);
 
+/* f4: CovidUK(...).sample(**par)["seir"] as used by predicted_incidence (posterior/predict.py:14-72; pinned to the CPU in
+ * the reference, predict.py:112): chain-binomial forward simulation of `B` posterior samples over the model's num_steps
+ * days from per-sample initial states.  d_alpha_path [B,T]: the log-rate offset a_k of every step, already resolved
+ * (alpha_0 at t == 0, else (alpha_0 + cumsum(alpha_t))[clip(t-1)], model_spec.py:242-256 -- the posterior's alpha_t may
+ * be longer than the prediction window); d_scalars [B,5] = psi, sigma_space, beta_area, gamma0, gamma1;
+ * d_spatial_effect [B,M]; d_initial_state [B,M,4] float64 integer-valued; d_events [B,M,T,3] out.  Philox streams keyed
+ * by (seed, chain_offset + b). */
+int seir_simulate(const seir_model* model, int num_samples, uint64_t seed, uint32_t chain_offset, const double* d_alpha_path,
+                  const double* d_scalars, const double* d_spatial_effect, const double* d_initial_state, double* d_events,
+                  void* stream);
+
 /* f4: posterior/reproduction_number.py:13-45 (calc_posterior_rit) over the chain axis as the posterior-sample axis:
  * R[b,t,j] = sum_i NGM_t[i,j] with the next-generation matrix of model_spec.py:300-367, from the cached state of the
  * ingested events.  d_theta [B,P] CONSTRAINED parameters, d_rit [B,T,M].  (initial_step must be 0, as in the
