@@ -20,6 +20,7 @@
 #include "delta_common.cuh"
 #include "propose.cuh"
 
+
 // ------------------------------------------------------------------------------------------------
 // decide + commit.  accept iff log u < dll + lac  (tfp.mcmc.MetropolisHastings [recall]); on accept the point changes
 // are applied to the event / state rows, the sufficient statistics and the event-day counts.
@@ -139,16 +140,43 @@ __global__ void __launch_bounds__(UPD_THREADS) seir_update_prepare_kernel(
   __shared__ double s_qf[SEIR_MMAX], s_qr[SEIR_MMAX];
   __shared__ double redd[UPD_THREADS / 32][2];
   __shared__ int redn[UPD_THREADS / 32];
-  extern __shared__ int s_cnt[];  // [Mp], only when drawing
+  extern __shared__ __align__(16) unsigned char dynraw[];
+  __shared__ int s_sel[3];
   const int b = b0 + blockIdx.x, tid = threadIdx.x;
   const size_t cb = (size_t)b * T * Mp;
-  chain_view v{M, T, Mp, yse + cb, yei + cb, yir + cb, Sx + cb, Ex + cb, Ix + cb, init};
+  const chain_view g{M, T, Mp, yse + cb, yei + cb, yir + cb, Sx + cb, Ex + cb, Ix + cb, init, 0};
+  const upd_smem sm = upd_smem_carve(dynraw, T, Mp);
   int* pr = prop + (size_t)b * 4 * SEIR_MMAX;
   const int target = cfg.target;
-  const int* yt = yarr(v, target);
   const int* nzd = nzd_all + ((size_t)b * 2 + target) * Mp;
+  // ---- stage: rate factors of the chain, hot-day counts, then the (at most two) metapopulation columns the proposal
+  //      touches.  Everything below reads shared memory; HBM is paid in three round trips (counts, columns, lgamma table).
+  for (int t = tid; t < T; t += UPD_THREADS) {
+    sm.pa[t] = pa[(size_t)b * T + t];
+    sm.pw[t] = psiW[(size_t)b * T + t];
+    sm.gam[t] = gam[(size_t)b * T + t];
+  }
+  const int H = sample_hot_counts(g, cfg, nzd, sm.cnt, redn);
   if (draw.enabled) {
-    seir_sample_proposal(v, cfg, draw.seed, draw.chain0 + (uint32_t)b, draw.ctr, nzd, s_cnt, redn, pr, log_u + b);
+    if (tid < 32) sample_metapops(g, cfg, draw.seed, draw.chain0 + (uint32_t)b, draw.ctr, sm.cnt, H, pr, log_u + b, s_sel);
+  } else if (tid == 0) {  // explicit record (the RNG-free path the parity tests pin)
+    const int m0 = pr[0], m1 = (cfg.kind == 0 && cfg.mmax > 1) ? pr[1] : -1;
+    s_sel[0] = (m0 >= 0 && m0 < M) ? m0 : -1;
+    s_sel[1] = (m1 >= 0 && m1 < M) ? m1 : -1;
+    s_sel[2] = 0;
+  }
+  __syncthreads();
+  chain_view col[2] = {g, g};
+  const double* colbc[2] = {Bc + cb, Bc + cb};
+  stage_columns(g, Bc + cb, s_sel, sm.col, UPD_THREADS);
+  for (int k = 0; k < 2; ++k)
+    if (s_sel[k] >= 0) {
+      col[k] = column_view(g, sm.col[k], s_sel[k]);
+      colbc[k] = sm.col[k].bc;
+    }
+  __syncthreads();
+  if (draw.enabled) {
+    if (tid < 32) sample_finish(col, cfg, draw.seed, draw.chain0 + (uint32_t)b, draw.ctr, sm.cnt, s_sel, pr);
     __syncthreads();  // warp 0's global stores of the record are visible to the whole CTA
   }
 
@@ -184,8 +212,10 @@ __global__ void __launch_bounds__(UPD_THREADS) seir_update_prepare_kernel(
     if (valid && warp < cfg.mmax) {
       const int k = warp;
       const int m = pr[k], t = pr[SEIR_MMAX + k], d = pr[2 * SEIR_MMAX + k], x = pr[3 * SEIR_MMAX + k];
-      const int nnz = nzd[m];  // days of m with target events (maintained by ingest / commit)
-      const int ytt = yt[(size_t)t * Mp + m], ytd = yt[(size_t)(t + d) * Mp + m];
+      const chain_view& v = col[k];  // (valid => column k is staged)
+      const int* yt = yarr(v, target);
+      const int nnz = sm.cnt[m];  // days of m with target events (maintained by ingest / commit)
+      const int ytt = yt[cell(v, t, m)], ytd = yt[cell(v, t + d, m)];
       const int lo = d > 0 ? t : t + d, hi = d > 0 ? t + d : t;
       const int hi_c = min(hi, lo + cfg.dmax);
       // forward: later move depletes the destination compartment (bounded via `next`), earlier move the source (via `prev`)
@@ -215,21 +245,13 @@ __global__ void __launch_bounds__(UPD_THREADS) seir_update_prepare_kernel(
     const double q_add = -log((double)M) - log((double)(cfg.t1 - cfg.t0)) - log((double)cfg.nmax + 1.0);
     // hot metapopulations / hot days of the window, on the events the DELETE proposal is built on
     // (current events for a delete, proposed events for the reverse of an add)
-    const int ymt = yt[(size_t)t * Mp + m];
+    const chain_view& v = col[0];  // (valid => the column is staged)
+    const int ymt = yarr(v, target)[cell(v, t, m)];
     const int ymt_del = sg > 0 ? ymt + x : ymt;
-    int hm = 0;
-    for (int mm = tid; mm < M; mm += UPD_THREADS) {
-      int any = 0;
-      for (int s = cfg.t0; s < t1; ++s) any |= yt[(size_t)s * Mp + mm] > 0;
-      if (mm == m && sg > 0 && x > 0) any = 1;
-      hm += any;
-    }
-    int hd = 0;
-    for (int s = cfg.t0 + tid; s < t1; s += UPD_THREADS) {
-      int y = yt[(size_t)s * Mp + m];
-      if (s == t && sg > 0) y += x;
-      hd += y > 0;
-    }
+    (void)t1;
+    int hm = 0;  // metapopulations / days of m with events in the window: from the staged counts
+    for (int mm = tid; mm < M; mm += UPD_THREADS) hm += (sm.cnt[mm] > 0) || (mm == m && sg > 0 && x > 0);
+    int hd = (tid == 0) ? sm.cnt[m] + ((sg > 0 && x > 0 && ymt == 0) ? 1 : 0) : 0;
     int bnd = INT_MAX;
     if (cfg.next >= 0)
       for (int s = t + tid; s < T; s += UPD_THREADS) {
@@ -252,7 +274,6 @@ __global__ void __launch_bounds__(UPD_THREADS) seir_update_prepare_kernel(
     if (sg > 0) { qf = q_add; qr = q_del; } else { qf = q_del; qr = q_add; }
     if (!(qf > -INFINITY)) valid = 0;
   }
-
   // ---- delta log-lik of the cells owned by the touched metapopulations ----
   double dll = 0.0, dllc = 0.0;
   int neg = 0;
@@ -260,11 +281,16 @@ __global__ void __launch_bounds__(UPD_THREADS) seir_update_prepare_kernel(
     const int ngroups = cfg.kind == 0 ? npts / 2 : 1;
     for (int gidx = 0; gidx < ngroups; ++gidx) {
       const int m = s_pm[cfg.kind == 0 ? 2 * gidx : 0];
+      const int kc = (m == s_sel[0]) ? 0 : 1;  // staged column of this group
+      const chain_view& v = col[kc];
+      const double* bcol = colbc[kc];
+      const int* yt = yarr(v, target);
+      const double pm_m = target == 0 ? pm_arr[(size_t)b * Mp + m] : 0.0;
       for (int s = tid; s < T; s += UPD_THREADS) {
         const int dy = dy_at(s_pm, s_pd, s_pdy, npts, m, s);
         const int dc = dcum_le(s_pm, s_pd, s_pdy, npts, m, s - 1);  // change of the exclusive cumulative count at day s
         if (dy == 0 && dc == 0) continue;
-        const size_t o = (size_t)s * Mp + m;
+        const size_t o = cell(v, s, m);
         const int y = yt[o], n = xarr(v, target)[o], n2 = xarr(v, target + 1)[o];
         const int yn = y + dy, nn = n - dc, nn2 = n2 + dc;
         const int y2 = yarr(v, target + 1)[o];  // events of the next transition (unchanged)
@@ -276,8 +302,8 @@ __global__ void __launch_bounds__(UPD_THREADS) seir_update_prepare_kernel(
         double term = dcoef;
         const double dres = (double)((nn - yn) - (n - y));  // change of the survivors of the target transition
         if (target == 0) {
-          const double e = pa[(size_t)b * T + s] * pm_arr[(size_t)b * Mp + m];
-          const double X = (double)v.I[o] + psiW[(size_t)b * T + s] * Bc[cb + o];
+          const double e = sm.pa[s] * pm_m;
+          const double X = (double)v.I[o] + sm.pw[s] * bcol[o];
           const double x = fma(e, X, eps) * dt;
           if (dy != 0) term += (double)dy * log1mexp_neg(x);
           term -= dres * x;
@@ -285,7 +311,7 @@ __global__ void __launch_bounds__(UPD_THREADS) seir_update_prepare_kernel(
         } else {
           if (dy != 0) term += (double)dy * log_p_nu;
           term -= dres * nu * dt;
-          term -= (double)dc * gam[(size_t)b * T + s] * dt;  // I->R survivors change by +dc (y_ir fixed)
+          term -= (double)dc * sm.gam[s] * dt;  // I->R survivors change by +dc (y_ir fixed)
         }
         dll += term;
       }
@@ -437,7 +463,13 @@ static int launch_update(seir_chains* c, const seir_update_cfg& cfg, int slot, c
   const int B = c->B, T = m->T, Mp = m->Mp;
   const int nchunk = (T + SLAB_DAYS - 1) / SLAB_DAYS;
   const upd_outputs outs{d_tlp, d_accept, c->d_last_acc + (size_t)slot * B * 4 * SEIR_MMAX, d_trace, d_dbg};
-  seir_update_prepare_kernel<<<r.nb, UPD_THREADS, draw.enabled ? sizeof(int) * Mp : 0, s>>>(
+  const size_t smem = upd_smem_bytes(T, Mp);
+  static size_t attr = 0;
+  if (smem > 48 * 1024 && attr != smem) {
+    SEIR_CUDA(cudaFuncSetAttribute(seir_update_prepare_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+    attr = smem;
+  }
+  seir_update_prepare_kernel<<<r.nb, UPD_THREADS, smem, s>>>(
       m->M, T, Mp, r.b0, m->dt, m->nu, m->log_p_nu, m->rate_eps, cfg, draw, d_proposal, d_log_u, c->d_nzd, c->d_yse, c->d_yei, c->d_yir, c->d_S,
       c->d_E, c->d_I, c->d_Bc, m->d_init, m->d_lgtab, c->d_pa, c->d_psiW, c->d_pm, c->d_gam, c->d_upd, c->d_Rir, c->d_sumYei,
       c->d_sumEres, c->d_llc_adj, outs);

@@ -8,18 +8,66 @@
 #define UPD_THREADS 128
 #define SLAB_DAYS 8
 
+// A chain's day-slab caches, or ONE metapopulation column of them staged in shared memory: element (s, m) lives at
+// s * Mp + (m - m0).  Global view: Mp = padded width, m0 = 0.  Column view: Mp = 1, m0 = the staged metapopulation, the
+// arrays are [T] copies in shared memory and `init` points at that metapopulation's 4 initial-state entries.
 struct chain_view {
   int M, T, Mp;
   const int *yse, *yei, *yir, *S, *E, *I;  // already offset to the chain
-  const int* init;                         // [Mp][4]
+  const int* init;                         // [.][4], indexed (m - m0) * 4 + c
+  int m0;
 };
+__device__ __forceinline__ size_t cell(const chain_view& v, int s, int m) { return (size_t)s * v.Mp + (m - v.m0); }
+
+// Shared-memory staging of one metapopulation column: the 6 integer rows, the contraction row and the initial state.
+// Every discrete update touches at most two metapopulations; all their later reads (proposal bounds, q terms, delta
+// log-lik) are served from here, so the kernel pays ONE round trip to HBM for them instead of a chain of dependent ones
+// (the caches of 256 chains, 264 MB, do not fit the L2: each dependent strided read is a ~1 us HBM miss).
+struct col_stage {
+  int* rows;    // [6][T]: yse, yei, yir, S, E, I
+  double* bc;   // [T]
+  int* init4;   // [4]
+};
+// Both columns at once: thread <-> day; the 14 strided loads of a thread (2 columns x (6 integer rows + the contraction
+// row)) are issued back to back BEFORE any of them is consumed -- one round trip to HBM.  (A copy loop that stores each
+// value as it arrives keeps a single load in flight per thread: measured 9.4 us for two columns, profiles/r01_v7_*.)
+__device__ __forceinline__ void stage_columns(const chain_view& g, const double* __restrict__ Bc_chain, const int* sel, const col_stage* c,
+                                              int nthr) {
+  const int T = g.T, tid = threadIdx.x;
+  const bool has[2] = {sel[0] >= 0, sel[1] >= 0};
+  for (int s0 = 0; s0 < T; s0 += nthr) {
+    const int s = s0 + tid;
+    int vi[2][6];
+    double vb[2];
+#pragma unroll
+    for (int k = 0; k < 2; ++k)
+      if (has[k] && s < T) {
+        const size_t o = (size_t)s * g.Mp + sel[k];
+        vi[k][0] = g.yse[o]; vi[k][1] = g.yei[o]; vi[k][2] = g.yir[o];
+        vi[k][3] = g.S[o]; vi[k][4] = g.E[o]; vi[k][5] = g.I[o];
+        vb[k] = Bc_chain[o];
+      }
+#pragma unroll
+    for (int k = 0; k < 2; ++k)
+      if (has[k] && s < T) {
+#pragma unroll
+        for (int a = 0; a < 6; ++a) c[k].rows[a * T + s] = vi[k][a];
+        c[k].bc[s] = vb[k];
+      }
+  }
+  if (tid < 8 && has[tid >> 2]) c[tid >> 2].init4[tid & 3] = g.init[sel[tid >> 2] * 4 + (tid & 3)];
+}
+__device__ __forceinline__ chain_view column_view(const chain_view& g, const col_stage& c, int m) {
+  const int T = g.T;
+  return chain_view{g.M, T, 1, c.rows, c.rows + T, c.rows + 2 * T, c.rows + 3 * T, c.rows + 4 * T, c.rows + 5 * T, c.init4, m};
+}
 
 __device__ __forceinline__ const int* yarr(const chain_view& v, int x) { return x == 0 ? v.yse : (x == 1 ? v.yei : v.yir); }
 __device__ __forceinline__ const int* xarr(const chain_view& v, int c) { return c == 0 ? v.S : (c == 1 ? v.E : v.I); }
 
 // state of compartment c (0..2) of metapopulation m AFTER the events of day s
 __device__ __forceinline__ int after_state(const chain_view& v, int c, int m, int s) {
-  const size_t o = (size_t)s * v.Mp + m;
+  const size_t o = cell(v, s, m);
   int x = xarr(v, c)[o] - yarr(v, c)[o];
   if (c > 0) x += yarr(v, c - 1)[o];
   return x;
@@ -71,7 +119,7 @@ __device__ __forceinline__ double blk_reduce_addd(double v, double* red) {
 // current (delta = 0) or proposed state; compartment c loses dcum for c == target and gains it for target+1.
 __device__ __forceinline__ int bound_abs_min(const chain_view& v, int c, int m, int lo, int hi, bool proposed, int target,
                                              const int* pm, const int* pd, const int* pdy, int npts, int* red) {
-  const int init_c = v.init[m * 4 + c];
+  const int init_c = v.init[(m - v.m0) * 4 + c];
   int best = INT_MAX;
   for (int s = lo + (int)threadIdx.x; s < hi; s += UPD_THREADS) {
     int x = after_state(v, c, m, s);
@@ -103,7 +151,7 @@ __device__ __forceinline__ int bound_level_min(const chain_view& v, int c, int m
 // ---- single-warp variants (all 32 lanes of ONE warp call these; no block barrier) ----
 __device__ __forceinline__ int warp_bound_abs_min(const chain_view& v, int c, int m, int lo, int hi, bool proposed, int target,
                                                   const int* pm, const int* pd, const int* pdy, int npts) {
-  const int init_c = v.init[m * 4 + c];
+  const int init_c = v.init[(m - v.m0) * 4 + c];
   int best = INT_MAX;
   for (int s = lo + (int)(threadIdx.x & 31); s < hi; s += 32) {
     int x = after_state(v, c, m, s);
