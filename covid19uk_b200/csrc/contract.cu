@@ -9,6 +9,10 @@
 // HBM (DRAM 1 %), was the limit, which is the case the north star names for DMMA.
 //   CTA tile 64 x 64, 4 warps, warp tile 32 x 32 (4 x 4 MMA tiles, 32 accumulator doubles / thread),
 //   BK = 16, two shared-memory stages, next tile's global loads issued before the current tile's MMAs.
+// Measured 31.4 TFLOP/s = 89 % of cuBLAS DGEMM 4096^3 on the same GPU.  Tried and measured equal (197-209 us at the UK
+// size, B = 256): row tiles of 40..80 rows chosen per launch against wave quantisation (2016 CTAs on 592 slots), warp
+// strips of full tile height, and mma.sync.m16n8k16.f64 -- which ptxas lowers to eight DMMA.8x8x4 on sm_100a, the only
+// FP64 tensor shape in the SASS.  The kernel sits at the DMMA issue rate, not at a tiling or scheduling loss.
 #include "seir_internal.cuh"
 
 #define CT_BM 64
