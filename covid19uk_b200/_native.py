@@ -17,7 +17,7 @@ PART_SEIR = 1
 PART_PRIORS = 2
 PART_ILDJ = 4
 PART_JOINT = 7
-ABI_VERSION = 6
+ABI_VERSION = 7
 
 
 class SeirSpec(ctypes.Structure):
@@ -94,6 +94,7 @@ SIGNATURES = {
     "seir_simulate": (c_int, [c_void_p, c_int, ctypes.c_uint64, ctypes.c_uint32, c_void_p, c_void_p, c_void_p, c_void_p, c_void_p, c_void_p]),
     "seir_reproduction_number": (c_int, [c_void_p, c_void_p, c_void_p, c_void_p]),
     "seir_pressure_components": (c_int, [c_void_p, c_void_p, c_void_p, c_void_p, c_void_p]),
+    "seir_export_contraction": (c_int, [c_void_p, c_void_p, c_void_p]),
     "seir_chain_flags": (c_int, [c_void_p, c_void_p, c_void_p]),
     "seir_launch_count": (c_int64, []),
 }

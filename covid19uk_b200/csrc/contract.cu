@@ -13,6 +13,8 @@
 // size, B = 256): row tiles of 40..80 rows chosen per launch against wave quantisation (2016 CTAs on 592 slots), warp
 // strips of full tile height, and mma.sync.m16n8k16.f64 -- which ptxas lowers to eight DMMA.8x8x4 on sm_100a, the only
 // FP64 tensor shape in the SASS.  The kernel sits at the DMMA issue rate, not at a tiling or scheduling loss.
+#include <stdlib.h>
+
 #include "seir_internal.cuh"
 
 #define CT_BM 64
@@ -103,6 +105,17 @@ __global__ void __launch_bounds__(128) seir_contract_kernel(long long R, int Mp,
 }
 
 int seir_launch_contract(seir_chains* c, cudaStream_t s) {
+  const seir_model* m = c->model;
+  static int use_i8 = -1;
+  if (use_i8 < 0) {
+    const char* e = getenv("SEIR_CONTRACT_I8");  // 0: always the FP64 DMMA kernel below
+    use_i8 = e ? atoi(e) : 0;
+  }
+  if (use_i8 && m->i8_na > 0) return seir_launch_contract_i8(c, s);
+  return seir_launch_contract_f64(c, s);
+}
+
+int seir_launch_contract_f64(seir_chains* c, cudaStream_t s) {
   const seir_model* m = c->model;
   const long long R = (long long)c->B * m->T;
   dim3 grid(m->Mp / CT_BN, (unsigned)((R + CT_BM - 1) / CT_BM));

@@ -151,6 +151,15 @@ int seir_model_create(const seir_spec* spec, int device, seir_model** out) {
     seir_model_destroy(m);
     return rc;
   }
+  {
+    double max_pop = 0.0;
+    for (int i = 0; i < M; ++i) max_pop = fmax(max_pop, spec->population[i]);
+    rc = seir_contract_i8_setup(m, cstar.data(), max_pop);
+    if (rc < 0) {
+      seir_model_destroy(m);
+      return rc;
+    }
+  }
   *out = m;
   return SEIR_OK;
 }
@@ -158,7 +167,7 @@ int seir_model_create(const seir_spec* spec, int device, seir_model** out) {
 void seir_model_destroy(seir_model* m) {
   if (!m) return;
   cudaSetDevice(m->device);
-  cudaFree(m->d_cs); cudaFree(m->d_cst); cudaFree(m->d_rN); cudaFree(m->d_W); cudaFree(m->d_wk); cudaFree(m->d_aidx); cudaFree(m->d_tfirst); cudaFree(m->d_la);
+  cudaFree(m->d_cs); cudaFree(m->d_cst); cudaFree(m->d_cs_i8); cudaFree(m->d_cs_scale); cudaFree(m->d_rN); cudaFree(m->d_W); cudaFree(m->d_wk); cudaFree(m->d_aidx); cudaFree(m->d_tfirst); cudaFree(m->d_la);
   cudaFree(m->d_init); cudaFree(m->d_car_indptr); cudaFree(m->d_car_indices); cudaFree(m->d_car_values); cudaFree(m->d_lgtab); cudaFree(m->d_logtab);
   delete m;
 }
@@ -424,6 +433,10 @@ int seir_run_stage(seir_chains* c, int stage, const double* d_events, const doub
       if (!d_grad) return seir_set_error(SEIR_ERR_BAD_ARG, "seir_run_stage: stage 6 needs d_grad");
       return seir_launch_finalize(c, d_theta, kind, parts, d_out, d_grad, s);
     case 7: return seir_launch_coef(c, s);
+    case 8:
+      if (c->model->i8_na <= 0) return seir_set_error(SEIR_ERR_UNSUPPORTED, "seir_run_stage: the int8 tensor-core contraction does not apply to this model");
+      return seir_launch_contract_i8(c, s);
+    case 9: return seir_launch_contract_f64(c, s);
     default: return seir_set_error(SEIR_ERR_BAD_ARG, "seir_run_stage: unknown stage %d", stage);
   }
 }
@@ -531,6 +544,15 @@ int seir_pressure_components(seir_chains* c, const double* d_theta, double* d_wi
   if (!c || !d_within || !d_between) return seir_set_error(SEIR_ERR_BAD_ARG, "seir_pressure_components: NULL argument");
   SEIR_TRY(check_dev_ptr(d_theta, "d_theta"));
   return seir_launch_pressure(c, d_theta, d_within, d_between, (cudaStream_t)stream);
+}
+
+int seir_export_contraction(seir_chains* c, double* d_bc, void* stream) {
+  if (!c) return seir_set_error(SEIR_ERR_BAD_ARG, "seir_export_contraction: NULL chains");
+  SEIR_TRY(check_dev_ptr(d_bc, "d_bc"));
+  const seir_model* m = c->model;
+  SEIR_CUDA(cudaMemcpy2DAsync(d_bc, sizeof(double) * m->M, c->d_Bc, sizeof(double) * m->Mp, sizeof(double) * m->M, (size_t)c->B * m->T,
+                              cudaMemcpyDeviceToDevice, (cudaStream_t)stream));
+  return SEIR_OK;
 }
 
 int seir_chain_flags(const seir_chains* c, int32_t* d_flags_out, void* stream) {

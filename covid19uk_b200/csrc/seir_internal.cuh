@@ -37,6 +37,9 @@ struct seir_model {
   double* d_cs;        // [Mp*Mp] zero padded: Cs[j][i] = Cstar[j][i] / N[j]  (Cstar symmetric, model_spec.py:216-219)
   double* d_cst;       // [Mp*Mp] its transpose: Cst[i][j] = Cstar[i][j] / N[j]  (next-generation matrix, analytics.cu)
   double w_last;       // last entry of the commute-volume series (within_between.py evaluates its rates at t = len(W))
+  signed char* d_cs_i8;  // [7][Mp/128][2][128 x Mp/2] int8 digit planes of Cs in UMMA core-matrix layout (contract_i8.cu), or NULL
+  double* d_cs_scale;    // [Mp] per-column power-of-two scale of those digits
+  int i8_na;             // int8 digit planes of the infectious counts (0: integer path not applicable)
   double* d_rN;        // [Mp] 1/N, 0 in the padding
   double* d_W;         // [T] commute volume resolved per step (model_spec.py:234-235)
   double* d_wk;        // [T] centred weekday resolved per step (model_spec.py:237-240)
@@ -158,6 +161,9 @@ int seir_launch_ingest_range(seir_chains* c, const double* d_events, const unsig
                              cudaStream_t s);
 int seir_launch_coef(seir_chains* c, cudaStream_t s);
 int seir_launch_contract(seir_chains* c, cudaStream_t s);
+int seir_launch_contract_i8(seir_chains* c, cudaStream_t s);
+int seir_launch_contract_f64(seir_chains* c, cudaStream_t s);
+int seir_contract_i8_setup(seir_model* m, const double* h_cs, double max_population);
 int seir_launch_theta_prep(seir_chains* c, const double* d_theta, int kind, int parts, cudaStream_t s, seir_range r);
 int seir_launch_loglik(seir_chains* c, bool grad, cudaStream_t s, seir_range r);
 int seir_launch_finalize(seir_chains* c, const double* d_theta, int kind, int parts, double* d_out, double* d_grad,

@@ -298,6 +298,12 @@ class SeirEngine:
                                                     c_void_p(between.data_ptr()), self._stream()))
         return within, between
 
+    def export_contraction(self, B: int) -> torch.Tensor:
+        """The cached contraction Cstar (I/N) of the ingested events, [B,T,M]."""
+        out = torch.empty((B, self.T, self.M), dtype=torch.float64, device=self.device)
+        nat.check(self.lib.seir_export_contraction(self.chains(B), c_void_p(out.data_ptr()), self._stream()))
+        return out
+
     def chain_flags(self, B: int) -> torch.Tensor:
         out = torch.empty((B,), dtype=torch.int32, device=self.device)
         nat.check(self.lib.seir_chain_flags(self.chains(B), c_void_p(out.data_ptr()), self._stream()))

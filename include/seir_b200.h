@@ -27,7 +27,7 @@
 extern "C" {
 #endif
 
-#define SEIR_B200_ABI_VERSION 6
+#define SEIR_B200_ABI_VERSION 7
 
 typedef enum seir_status {
   SEIR_OK = 0,
@@ -238,6 +238,10 @@ int seir_reproduction_number(seir_chains* chains, const double* d_theta, double*
  * d_within / d_between [B,M] infection pressure from inside / outside each metapopulation. */
 int seir_pressure_components(seir_chains* chains, const double* d_theta, double* d_within, double* d_between,
                              void* stream);
+
+/* The cached commuting contraction Bc[b,t,i] = sum_j Cstar[i,j] I[b,t,j] / N[j] (model_spec.py:262) of the ingested
+ * events, d_bc [B,T,M] (diagnostics; tests/test_gpu_contract.py compares the FP64 and the int8 tensor-core kernels). */
+int seir_export_contraction(seir_chains* chains, double* d_bc, void* stream);
 
 /* Per-chain status bits set by ingest / commits: bit0 = events not non-negative integers,
  * bit1 = reconstructed state negative or events exceed the source compartment (log-prob = -inf). */
