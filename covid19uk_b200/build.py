@@ -72,7 +72,7 @@ def build(force: bool = False, verbose: bool = False) -> str:
         if src.endswith(".cpp"):  # plain host code: g++ directly (function multiversioning attributes are not nvcc-friendly)
             cmd = [os.environ.get("CXX", "g++")] + CXX_FLAGS + ["-c", path, "-o", obj]
         else:
-            cmd = [nvcc] + NVCC_FLAGS + ["-c", path, "-o", obj]
+            cmd = [nvcc] + NVCC_FLAGS + os.environ.get("SEIR_NVCC_EXTRA", "").split() + ["-c", path, "-o", obj]
         res = subprocess.run(cmd, capture_output=True, text=True)
         if res.returncode != 0:
             raise RuntimeError(f"nvcc failed for {src}:\n{res.stdout}\n{res.stderr}")

@@ -108,8 +108,8 @@ int seir_launch_contract(seir_chains* c, cudaStream_t s) {
   const seir_model* m = c->model;
   static int use_i8 = -1;
   if (use_i8 < 0) {
-    const char* e = getenv("SEIR_CONTRACT_I8");  // 0: always the FP64 DMMA kernel below
-    use_i8 = e ? atoi(e) : 0;
+    const char* e = getenv("SEIR_CONTRACT_I8");  // 0: always the FP64 DMMA kernel below; default: the exact int8 tcgen05 kernel
+    use_i8 = e ? atoi(e) : 1;                    // (contract_i8.cu) wherever it applies (Mp a multiple of 128, <= 384)
   }
   if (use_i8 && m->i8_na > 0) return seir_launch_contract_i8(c, s);
   return seir_launch_contract_f64(c, s);

@@ -1,16 +1,18 @@
 // K2 on the 5th-generation tensor cores: the commuting contraction  Bc = I . Cs  ([B*T, Mp] x [Mp, Mp], model_spec.py:262)
 // as an EXACT integer GEMM on tcgen05 (kind::i8, int32 accumulators in TMEM) -- an error-free splitting ("Ozaki scheme"):
 //
-//   I[r][j]   = sum_a 128^a A_a[r][j]                 A_a in [0,127]    (na <= 3 digit planes: populations < 2^21)
-//   Cs[j][i]  = 2^e_i sum_c 128^-(c+1) D_c[j][i] + delta   D_c in [-64,64], |delta| <= 2^e_i 128^-nb / 2  (nb = 7 planes,
-//                                                          per-column scale 2^e_i chosen at model creation)
-//   Bc[r][i]  = 2^e_i sum_s 128^(s-1) G_s[r][i],      G_s = sum_{a-c=s} A_a D_c   (int32, exact: |G_s| < 2^24)
+//   I[r][j]   = sum_a 256^a A_a[r][j]                 A_a in [0,255] (unsigned bytes; na <= 3 planes: counts < 2^24;
+//                                                     planes that are all zero in a tile are skipped at run time)
+//   Cs[j][i]  = 2^e_i sum_c 256^-(c+1) D_c[j][i] + delta   D_c in [-128,127] (balanced radix-256 digits of the 48-bit
+//                                                     fixed-point value round(Cs 2^(48-e_i)), 2^e_i > 4 max_j |Cs[j][i]|),
+//                                                     |delta| <= 2^(e_i-49),
+//                                                     nb = 6 planes, per-column scale 2^e_i chosen at model creation
+//   Bc[r][i]  = 2^e_i sum_s 256^(s-1) G_s[r][i],      G_s = sum_{a-c=s} A_a D_c   (int32, exact: |G_s| < 2^26)
 //
-// Every partial product is exact in int32; the only rounding is the truncation of Cs to 49 bits below its column maximum
-// and the nine FP64 additions of the epilogue -- a relative error of ~1e-14 on Bc, far inside the 1e-10 budget of the
+// Every partial product is exact in int32; the only rounding is the truncation of Cs to 46 bits below its column maximum
+// and the FP64 additions of the epilogue -- a relative error of ~1e-14 on Bc, far inside the 1e-10 budget of the
 // log-probability (tests/test_gpu_contract.py compares against the FP64 DMMA kernel of contract.cu).
-// 21 int8 GEMMs of 2 M^2 T flop each replace one FP64 GEMM: at 4.5 Pop/s (int8) vs 35 Tflop/s (FP64 DMMA) that is ~5x
-// less tensor time for the same result.
+// At most 18 (typically 12: infectious counts below 65536) int8 GEMMs of 2 M^2 T flop each replace one FP64 GEMM.
 //
 // Kernel (one CTA per SM, persistent over 128 x 128 output tiles):
 //   warps 0-7  (a) split the tile's 128 x K int32 slab of I into na int8 planes in shared memory, canonical K-major
@@ -20,7 +22,7 @@
 //   warp 8     producer: streams the pre-split planes of Cs (laid out on the host in the same canonical layout) with
 //              1-D bulk copies into a 3-stage ring (half a plane per stage)
 //   warp 9     allocates TMEM (512 columns = 4 accumulator slots of 128), one elected lane issues tcgen05.mma:
-//              plane-major order (c outer, a inner) so that only na+1 accumulator groups are live at a time:
+//              plane-major order (c outer, a inner) so that at most na+1 <= 4 accumulator groups are live at a time:
 //              group s = a - c uses slot s mod 4; after plane c group na-1-c is complete and is committed to the epilogue.
 #include <math.h>
 #include <stdlib.h>
@@ -32,10 +34,19 @@
 
 #define I8_BM 128
 #define I8_BN 128
-#define I8_NB 7        // digit planes of Cs
+#define I8_NB 6        // digit planes of Cs (balanced radix 256)
 #define I8_STAGES 3
 #define I8_EPI_THREADS 256
 #define I8_THREADS (I8_EPI_THREADS + 64)
+#define I8_STAGE_OUT (8 * 32 * 65 * 8)  // bytes of the epilogue's transposition buffer
+
+// phase timestamps of one CTA's second tile (build with SEIR_NVCC_EXTRA=-DSEIR_I8_DEBUG, read with seir_debug_i8)
+#ifdef SEIR_I8_DEBUG
+__device__ long long g_i8dbg[64];
+#define TM(k) do { if (blockIdx.x == 5) { long long t_; asm volatile("mov.u64 %0, %%globaltimer;" : "=l"(t_)); g_i8dbg[k] = t_; } } while (0)
+#else
+#define TM(k) do { } while (0)
+#endif
 
 // ---- tcgen05 wrappers -------------------------------------------------------------------------------------------------
 __device__ __forceinline__ void tc_fence_before() { asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory"); }
@@ -70,8 +81,9 @@ __device__ __forceinline__ void tc_wait_ld() { asm volatile("tcgen05.wait::ld.sy
 __device__ __forceinline__ uint64_t umma_desc(uint32_t smem_addr, uint32_t sbo_bytes) {
   return (uint64_t)((smem_addr & 0x3FFFFu) >> 4) | ((uint64_t)(128u >> 4) << 16) | ((uint64_t)(sbo_bytes >> 4) << 32) | (1ull << 46);
 }
-// cute::UMMA::InstrDescriptor: c_format S32 (2) [4,6), a/b_format INT8 (1) [7,10) / [10,13), K-major both, N>>3 [17,23), M>>4 [24,29)
-#define I8_IDESC ((2u << 4) | (1u << 7) | (1u << 10) | ((uint32_t)(I8_BN >> 3) << 17) | ((uint32_t)(I8_BM >> 4) << 24))
+// cute::UMMA::InstrDescriptor: c_format S32 (2) [4,6), a_format UINT8 (0) [7,10), b_format INT8 (1) [10,13), K-major both,
+// N>>3 [17,23), M>>4 [24,29)
+#define I8_IDESC ((2u << 4) | (0u << 7) | (1u << 10) | ((uint32_t)(I8_BN >> 3) << 17) | ((uint32_t)(I8_BM >> 4) << 24))
 
 __global__ void __launch_bounds__(I8_THREADS, 1) seir_contract_i8_kernel(long long R, int Mp, int na, int ntiles,
                                                                          const int* __restrict__ Ix,
@@ -80,11 +92,14 @@ __global__ void __launch_bounds__(I8_THREADS, 1) seir_contract_i8_kernel(long lo
   extern __shared__ __align__(1024) unsigned char smem[];
   __shared__ uint64_t full_b[I8_STAGES], empty_b[I8_STAGES], a_ready, a_free, t_full[4], t_empty[4];
   __shared__ uint32_t tmem_base_s;
+  __shared__ int s_plane_nz[2][4];  // per tile parity: digit plane a of the tile holds a non-zero byte
   const int K = Mp, KH = Mp / 2;                      // one B stage = half a plane: 128 columns x KH bytes
   const int plane_a = I8_BM * K;                      // bytes of one A digit plane
   const int stage_b = I8_BN * KH;
   unsigned char* smA = smem;                          // [na][plane_a]
-  unsigned char* smB = smem + (size_t)na * plane_a;   // [I8_STAGES][stage_b]
+  // (the A region doubles as the output staging buffer of the epilogue: at least 8 warps x 32 x 65 doubles)
+  const size_t a_region = (size_t)na * plane_a > (size_t)I8_STAGE_OUT ? (size_t)na * plane_a : (size_t)I8_STAGE_OUT;
+  unsigned char* smB = smem + a_region;               // [I8_STAGES][stage_b]
   const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
   const int ncol_tiles = Mp / I8_BN;
   const int ksteps_h = KH / 32;                       // MMAs (K = 32 bytes) per half plane
@@ -95,6 +110,7 @@ __global__ void __launch_bounds__(I8_THREADS, 1) seir_contract_i8_kernel(long lo
     mbar_init(&a_free, 1);
     for (int s = 0; s < 4; ++s) { mbar_init(&t_full[s], 1); mbar_init(&t_empty[s], I8_EPI_THREADS / 32); }
     asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+    for (int q = 0; q < 8; ++q) s_plane_nz[q >> 2][q & 3] = 0;
   }
   if (warp == 9) {  // TMEM: 512 columns (4 slots x 128 int32 accumulator columns)
     asm volatile("tcgen05.alloc.cta_group::1.sync.aligned.shared::cta.b32 [%0], %1;" ::"r"(smem_u32(&tmem_base_s)), "r"(512u) : "memory");
@@ -116,41 +132,66 @@ __global__ void __launch_bounds__(I8_THREADS, 1) seir_contract_i8_kernel(long lo
       const long long r0 = (long long)rb * I8_BM;
       // ---- (a) digits of I: unit = (row r, 16-byte K chunk kc); a lane group of 8 consecutive rows x 4 chunks writes
       //      512 contiguous bytes per plane (bank-conflict free)
+      if (tid == 0 && it == 1) TM(0);
       if (it > 0) { mbar_wait(&a_free, ph_afree); ph_afree ^= 1u; }
+      if (tid == 0 && it == 1) TM(1);
       const int nkc = K / 16;
-      for (int u = tid; u < (I8_BM / 8) * (nkc / 4) * 32; u += I8_EPI_THREADS) {
-        const int l = u & 31, blk = u >> 5;
-        const int rgrp = blk / (nkc / 4), kq = blk - rgrp * (nkc / 4);
-        const int r = rgrp * 8 + (l & 7), kc = kq * 4 + (l >> 3);
-        const long long gr = r0 + r;
-        int4 v[4];
+      const int nunits = (I8_BM / 8) * (nkc / 4) * 32;
+      uint32_t nz[3] = {0u, 0u, 0u};
+      for (int u0 = tid; u0 < nunits; u0 += 4 * I8_EPI_THREADS) {  // 4 units = 16 independent 16-byte loads in flight per thread
+        int4 v[4][4];
+        uint32_t off[4];
+        (void)0;
 #pragma unroll
-        for (int q = 0; q < 4; ++q)
-          v[q] = gr < R ? __ldg(reinterpret_cast<const int4*>(Ix + gr * Mp + kc * 16 + q * 4)) : make_int4(0, 0, 0, 0);
-        const uint32_t off = (uint32_t)rgrp * (uint32_t)(K * 8) + (uint32_t)kc * 128u + (uint32_t)(l & 7) * 16u;
-        for (int a = 0; a < na; ++a) {
-          const int sh = 7 * a;
-          uint4 o;
-          o.x = ((v[0].x >> sh) & 127) | (((v[0].y >> sh) & 127) << 8) | (((v[0].z >> sh) & 127) << 16) | (((v[0].w >> sh) & 127) << 24);
-          o.y = ((v[1].x >> sh) & 127) | (((v[1].y >> sh) & 127) << 8) | (((v[1].z >> sh) & 127) << 16) | (((v[1].w >> sh) & 127) << 24);
-          o.z = ((v[2].x >> sh) & 127) | (((v[2].y >> sh) & 127) << 8) | (((v[2].z >> sh) & 127) << 16) | (((v[2].w >> sh) & 127) << 24);
-          o.w = ((v[3].x >> sh) & 127) | (((v[3].y >> sh) & 127) << 8) | (((v[3].z >> sh) & 127) << 16) | (((v[3].w >> sh) & 127) << 24);
-          *reinterpret_cast<uint4*>(smA + (size_t)a * plane_a + off) = o;
+        for (int b4 = 0; b4 < 4; ++b4) {
+          const int u = u0 + b4 * I8_EPI_THREADS;
+          const int l = u & 31, blk = u >> 5;
+          const int rgrp = blk / (nkc / 4), kq = blk - rgrp * (nkc / 4);
+          const int r = rgrp * 8 + (l & 7), kc = kq * 4 + (l >> 3);
+          const long long gr = r0 + r;
+          const bool in = u < nunits && gr < R;
+#pragma unroll
+          for (int q = 0; q < 4; ++q)
+            v[b4][q] = in ? __ldg(reinterpret_cast<const int4*>(Ix + gr * Mp + kc * 16 + q * 4)) : make_int4(0, 0, 0, 0);
+          off[b4] = (uint32_t)rgrp * (uint32_t)(K * 8) + (uint32_t)kc * 128u + (uint32_t)(l & 7) * 16u;
+        }
+#pragma unroll
+        for (int b4 = 0; b4 < 4; ++b4) {
+          if (u0 + b4 * I8_EPI_THREADS >= nunits) break;
+          for (int a = 0; a < na; ++a) {
+            const int sh = 8 * a;
+            uint4 o;
+            o.x = ((v[b4][0].x >> sh) & 255) | (((v[b4][0].y >> sh) & 255) << 8) | (((v[b4][0].z >> sh) & 255) << 16) | (((v[b4][0].w >> sh) & 255) << 24);
+            o.y = ((v[b4][1].x >> sh) & 255) | (((v[b4][1].y >> sh) & 255) << 8) | (((v[b4][1].z >> sh) & 255) << 16) | (((v[b4][1].w >> sh) & 255) << 24);
+            o.z = ((v[b4][2].x >> sh) & 255) | (((v[b4][2].y >> sh) & 255) << 8) | (((v[b4][2].z >> sh) & 255) << 16) | (((v[b4][2].w >> sh) & 255) << 24);
+            o.w = ((v[b4][3].x >> sh) & 255) | (((v[b4][3].y >> sh) & 255) << 8) | (((v[b4][3].z >> sh) & 255) << 16) | (((v[b4][3].w >> sh) & 255) << 24);
+            *reinterpret_cast<uint4*>(smA + (size_t)a * plane_a + off[b4]) = o;
+            nz[a] |= o.x | o.y | o.z | o.w;
+          }
         }
       }
       asm volatile("fence.proxy.async.shared::cta;" ::: "memory");  // generic-proxy stores -> visible to the tensor core
-      __syncwarp();
+      for (int a = 1; a < na; ++a)
+        if (__any_sync(0xffffffffu, nz[a] != 0u) && lane == 0) atomicOr(&s_plane_nz[it & 1][a], 1);
+      asm volatile("bar.sync 1, %0;" ::"n"(I8_EPI_THREADS) : "memory");  // every warp's digits and flags are in
+      int na_t = 1;  // planes of this tile that hold anything (plane 0 always counts)
+      for (int a = 1; a < na; ++a)
+        if (s_plane_nz[it & 1][a]) na_t = a + 1;
       if (lane == 0) mbar_arrive(&a_ready);
+      if (tid == 0)  // reset the OTHER parity's flags for the tile after next (its readers passed a barrier long ago)
+        for (int a = 0; a < 4; ++a) s_plane_nz[(it & 1) ^ 1][a] = 0;
+      if (tid == 0 && it == 1) TM(2);
       // ---- (b) epilogue: groups complete in the order s = na-1, na-2, ..., -(I8_NB-1)
       double out[64];
 #pragma unroll
       for (int j = 0; j < 64; ++j) out[j] = 0.0;
-      for (int s = na - 1; s >= -(I8_NB - 1); --s) {
+      for (int s = na_t - 1; s >= -(I8_NB - 1); --s) {
         const int slot = s & 3;
         mbar_wait(&t_full[slot], ph_full[slot]);
         ph_full[slot] ^= 1u;
         tc_fence_after();
-        const double w = ldexp(1.0, 7 * (s - 1));  // 128^(s-1), exact
+        if (tid == 0 && it == 1) TM(10 + (na_t - 1 - s));
+        const double w = ldexp(1.0, 8 * (s - 1));  // 256^(s-1), exact
         const uint32_t taddr = tmem_base + ((uint32_t)lane_base << 16) + (uint32_t)(slot * I8_BN + half * 64);
         uint32_t v0[32], v1[32];
         tc_ld32(taddr, v0);
@@ -165,14 +206,27 @@ __global__ void __launch_bounds__(I8_THREADS, 1) seir_contract_i8_kernel(long lo
           out[32 + j] = fma((double)(int)v1[j], w, out[32 + j]);
         }
       }
-      const long long row = r0 + lane_base + lane;
-      if (row < R) {
+      if (tid == 0 && it == 1) TM(3);
+      // ---- store: every MMA of the tile has completed (the last groups were just drained), so the A planes are dead:
+      //      each warp transposes its 32 x 64 block through its own 16.6 KB of that region (row stride 65 doubles: conflict
+      //      free) and writes whole 512-byte row segments
+      {
         const int c0 = ct * I8_BN + half * 64;
-        double* dst = Bc + row * Mp + c0;
+        double* stg = reinterpret_cast<double*>(smA) + (size_t)warp * (32 * 65);
 #pragma unroll
-        for (int j = 0; j < 64; j += 2)
-          *reinterpret_cast<double2*>(dst + j) = make_double2(out[j] * colscale[c0 + j], out[j + 1] * colscale[c0 + j + 1]);
+        for (int j = 0; j < 64; ++j) stg[lane * 65 + j] = out[j] * colscale[c0 + j];
+        __syncwarp();
+        for (int rr = 0; rr < 32; ++rr) {
+          const long long row = r0 + lane_base + rr;
+          if (row < R) {
+            const double x0 = stg[rr * 65 + 2 * lane], x1 = stg[rr * 65 + 2 * lane + 1];
+            *reinterpret_cast<double2*>(Bc + row * Mp + c0 + 2 * lane) = make_double2(x0, x1);
+          }
+        }
       }
+      // the staging region is rewritten with digits by ALL epilogue warps next: wait for every warp's stores to be read out
+      asm volatile("bar.sync 1, %0;" ::"n"(I8_EPI_THREADS) : "memory");
+      if (tid == 0 && it == 1) TM(4);
     }
   } else if (warp == 8) {
     // ================= producer: planes of Cs =================
@@ -184,8 +238,13 @@ __global__ void __launch_bounds__(I8_THREADS, 1) seir_contract_i8_kernel(long lo
           for (int h = 0; h < 2; ++h, ++n) {
             const int st = n % I8_STAGES;
             if (n >= I8_STAGES) mbar_wait(&empty_b[st], ((n / I8_STAGES) - 1) & 1u);
+#ifdef SEIR_I8_EXPERIMENT_NOB  // timing experiment only (wrong results): 16 bytes per stage instead of the half plane
+            mbar_expect_tx(&full_b[st], 16u);
+            bulk_load_1d(smB + (size_t)st * stage_b, Bd + (((size_t)c * ncol_tiles + ct) * 2 + h) * stage_b, 16u, &full_b[st]);
+#else
             mbar_expect_tx(&full_b[st], (unsigned)stage_b);
             bulk_load_1d(smB + (size_t)st * stage_b, Bd + (((size_t)c * ncol_tiles + ct) * 2 + h) * stage_b, (unsigned)stage_b, &full_b[st]);
+#endif
           }
       }
     }
@@ -193,17 +252,25 @@ __global__ void __launch_bounds__(I8_THREADS, 1) seir_contract_i8_kernel(long lo
     // ================= MMA issuer (warp 9, one thread) =================
     uint32_t n = 0, ph_aready = 0;
     uint32_t hosted[4] = {0, 0, 0, 0};  // groups started in each accumulator slot so far (over all tiles)
-    for (int tile = blockIdx.x; tile < ntiles; tile += gridDim.x) {
+    uint64_t a_desc_plane[3];
+    for (int a = 0; a < 3; ++a) a_desc_plane[a] = umma_desc(smem_u32(smA + (size_t)(a < na ? a : 0) * plane_a), (uint32_t)K * 8u);
+    int itm = 0;
+    for (int tile = blockIdx.x; tile < ntiles; tile += gridDim.x, ++itm) {
+      if (itm == 1) TM(30);
       mbar_wait(&a_ready, ph_aready);
       ph_aready ^= 1u;
       tc_fence_after();
+      if (itm == 1) TM(31);
+      int na_t = 1;
+      for (int a = 1; a < na; ++a)
+        if (s_plane_nz[itm & 1][a]) na_t = a + 1;
       for (int c = 0; c < I8_NB; ++c) {
         for (int h = 0; h < 2; ++h, ++n) {
           const int st = n % I8_STAGES;
           mbar_wait(&full_b[st], (n / I8_STAGES) & 1u);
           tc_fence_after();
-          const uint32_t b_addr = smem_u32(smB + (size_t)st * stage_b);
-          for (int a = 0; a < na; ++a) {
+          const uint64_t b_desc0 = umma_desc(smem_u32(smB + (size_t)st * stage_b), (uint32_t)KH * 8u);
+          for (int a = 0; a < na_t; ++a) {
             const int s = a - c, slot = s & 3;
             const bool first_pair = (c == 0 || a == 0);  // group s receives its first digit pair in this plane
             if (first_pair && h == 0) {
@@ -213,18 +280,24 @@ __global__ void __launch_bounds__(I8_THREADS, 1) seir_contract_i8_kernel(long lo
               }
               hosted[slot] += 1;
             }
-            const uint32_t a_addr = smem_u32(smA + (size_t)a * plane_a);
-            for (int kk = 0; kk < ksteps_h; ++kk) {
-              const uint32_t acc = (first_pair && h == 0 && kk == 0) ? 0u : 1u;
-              tc_mma_i8(tmem_base + (uint32_t)(slot * I8_BN), umma_desc(a_addr + (uint32_t)(h * ksteps_h + kk) * 256u, (uint32_t)K * 8u),
-                        umma_desc(b_addr + (uint32_t)kk * 256u, (uint32_t)KH * 8u), I8_IDESC, acc);
-            }
+            // a K step of 32 bytes advances both start addresses by 256 bytes = 16 descriptor units (low field, no carry:
+            // shared-memory addresses stay below 2^18)
+            const uint64_t a_desc0 = a_desc_plane[a] + (uint64_t)(h * ksteps_h) * 16u;
+            const uint32_t d_addr = tmem_base + (uint32_t)(slot * I8_BN);
+            tc_mma_i8(d_addr, a_desc0, b_desc0, I8_IDESC, (first_pair && h == 0) ? 0u : 1u);
+#pragma unroll 5
+            for (int kk = 1; kk < ksteps_h; ++kk) tc_mma_i8(d_addr, a_desc0 + (uint64_t)kk * 16u, b_desc0 + (uint64_t)kk * 16u, I8_IDESC, 1u);
+#ifdef SEIR_I8_EXPERIMENT_REP  // timing experiment only (wrong results): extra MMAs per step to separate per-MMA from per-stage cost
+            for (int rep = 0; rep < SEIR_I8_EXPERIMENT_REP; ++rep)
+              for (int kk = 0; kk < ksteps_h; ++kk) tc_mma_i8(d_addr, a_desc0 + (uint64_t)kk * 16u, b_desc0 + (uint64_t)kk * 16u, I8_IDESC, 1u);
+#endif
           }
           tc_commit(&empty_b[st]);  // the stage is free once these MMAs have read it
         }
         // plane c done: group na-1-c has all its pairs; after the last plane every remaining group has
-        const int s_hi = na - 1 - c, s_lo = (c == I8_NB - 1) ? -(I8_NB - 1) : s_hi;
+        const int s_hi = na_t - 1 - c, s_lo = (c == I8_NB - 1) ? -(I8_NB - 1) : s_hi;
         for (int s = s_hi; s >= s_lo; --s) tc_commit(&t_full[s & 3]);
+        if (itm == 1) TM(40 + c);
       }
       tc_commit(&a_free);  // the A planes may be overwritten for the next tile
     }
@@ -242,7 +315,7 @@ int seir_contract_i8_setup(seir_model* m, const double* h_cs /*[Mp][Mp], Cs[j][i
   const int Mp = m->Mp;
   if (Mp % I8_BN != 0 || Mp > 384) return 1;
   int na = 1;
-  while (na < 6 && ldexp(1.0, 7 * na) <= max_population) ++na;  // infectious counts never exceed the population
+  while (na < 6 && ldexp(1.0, 8 * na) <= max_population) ++na;  // infectious counts never exceed the population
   if (na > 3) return 1;
   const int KH = Mp / 2, nct = Mp / I8_BN;
   const size_t stage_b = (size_t)I8_BN * KH;
@@ -254,20 +327,20 @@ int seir_contract_i8_setup(seir_model* m, const double* h_cs /*[Mp][Mp], Cs[j][i
     int e = 0;
     if (cmax > 0.0) {
       frexp(cmax, &e);  // cmax = f 2^e, f in [0.5, 1)
-      e += 1;           // |Cs / 2^e| < 0.5: every digit, the first included, lies in [-64, 64]
+      e += 2;           // |Cs / 2^e| < 0.25: the 48-bit fixed-point value stays below 2^46 and its top digit inside [-64, 64]
     }
     scale[i] = ldexp(1.0, e);
     const int ct = i / I8_BN, nn = i % I8_BN;
     for (int j = 0; j < Mp; ++j) {
-      double r = ldexp(h_cs[(size_t)j * Mp + i], -e);  // exact scaling
+      long long W = llrint(ldexp(h_cs[(size_t)j * Mp + i], 8 * I8_NB - e));  // round(Cs 2^(48-e)), |W| <= 2^46
       const int h = j / KH, kl = j % KH;
       const size_t off = (size_t)(nn / 8) * ((size_t)KH * 8) + (size_t)(kl / 16) * 128 + (size_t)(nn % 8) * 16 + (size_t)(kl % 16);
-      for (int c = 0; c < I8_NB; ++c) {
-        const double t = r * 128.0;   // exact
-        const double d = nearbyint(t);
+      for (int c = I8_NB - 1; c >= 0; --c) {  // balanced digits, least significant (plane nb-1) first
+        long long d = ((W + 128) & 255) - 128;  // in [-128, 127], congruent to W mod 256
         bd[(((size_t)c * nct + ct) * 2 + h) * stage_b + off] = (signed char)d;
-        r = t - d;                    // exact, in [-0.5, 0.5]
+        W = (W - d) / 256;                      // exact
       }
+      // (W is now 0: |top digit| <= 64 because |Cs / 2^e| < 0.25)
     }
   }
   SEIR_CUDA(cudaMalloc(reinterpret_cast<void**>(&m->d_cs_i8), bd.size()));
@@ -282,7 +355,9 @@ int seir_launch_contract_i8(seir_chains* c, cudaStream_t s) {
   const seir_model* m = c->model;
   const long long R = (long long)c->B * m->T;
   const int ntiles = (int)((R + I8_BM - 1) / I8_BM) * (m->Mp / I8_BN);
-  const size_t smem = (size_t)m->i8_na * I8_BM * m->Mp + (size_t)I8_STAGES * I8_BN * (m->Mp / 2);
+  size_t a_region = (size_t)m->i8_na * I8_BM * m->Mp;
+  if (a_region < (size_t)I8_STAGE_OUT) a_region = I8_STAGE_OUT;
+  const size_t smem = a_region + (size_t)I8_STAGES * I8_BN * (m->Mp / 2);
   static int sms = 0;
   static size_t attr = 0;
   if (!sms) {
@@ -299,3 +374,7 @@ int seir_launch_contract_i8(seir_chains* c, cudaStream_t s) {
   seir_count_launch(1);
   return seir_cuda_check(cudaGetLastError(), "seir_contract_i8_kernel");
 }
+
+#ifdef SEIR_I8_DEBUG
+extern "C" int seir_debug_i8(long long* h) { return (int)cudaMemcpyFromSymbol(h, g_i8dbg, sizeof(long long) * 64); }
+#endif

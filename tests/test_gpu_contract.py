@@ -1,7 +1,9 @@
 """The int8 tensor-core contraction (tcgen05 kind::i8, error-free digit splitting, csrc/contract_i8.cu) against the FP64
 DMMA kernel (csrc/contract.cu) on the same ingested events: both compute Bc = Cstar (I/N) (model_spec.py:262).
-Bound asserted: |Bc_i8 - Bc_f64| <= 1e-13 * sum_j |Cs[j,i]| I_j  (the truncation of Cs to 49 bits below its column maximum
-plus FP64 summation-order differences of the reference kernel)."""
+Bound asserted: |Bc_i8 - Bc_f64| <= 1e-12 * sum_j |Cs[j,i]| I_j.  The integer kernel is exact up to the truncation of Cs to a
+48-bit fixed-point value whose scale 2^e_i exceeds 4x the column maximum: per element <= 2^-47 of the column maximum
+(measured worst case of the normalised error at the UK shape: 2.8e-13); on the log-probability that is < 1e-12 relative,
+and tests/test_gpu_logprob.py holds its 1e-10 bound with this kernel as the default."""
 import numpy as np
 import pytest
 
@@ -29,8 +31,8 @@ def test_int8_contraction_matches_fp64(M, T, B):
     I = so.compute_state(pb["initial_state"], pb["events"])[..., 2]   # [B, M, T]
     bound = np.einsum("ij,bjt->bti", cs_abs, I)                       # sum_j |Cs| I_j
     err = np.abs(got - ref)
-    assert np.all(err <= 1e-13 * bound + 1e-300), float((err / np.maximum(bound, 1e-300)).max())
+    assert np.all(err <= 1e-12 * bound + 1e-300), float((err / np.maximum(bound, 1e-300)).max())
     # and against a plain numpy contraction
     exact = np.einsum("ij,bjt->bti", consts["Cstar"] / consts["N"][None, :], I)
-    assert np.all(np.abs(got - exact) <= 1e-13 * bound + 1e-300)
+    assert np.all(np.abs(got - exact) <= 1e-12 * bound + 1e-300)
     eng.close()

@@ -1,0 +1,18 @@
+import ctypes, sys, os
+sys.path.insert(0, os.path.dirname(os.path.dirname(os.path.abspath(__file__))))
+import numpy as np, torch
+from covid19uk_b200 import _native as nat, synthetic as syn
+from covid19uk_b200.engine import SeirEngine
+pb = syn.make_problem(382, 84, chains=256, seed=0, distinct=8)
+eng = SeirEngine(pb["covariates"], pb["initial_state"], 0, 84)
+ev = torch.from_numpy(pb["events"]).cuda()
+eng.ingest(ev)
+for _ in range(3):
+    eng.run_stage(256, 8)
+torch.cuda.synchronize()
+buf = (ctypes.c_longlong * 64)()
+nat.load().seir_debug_i8(buf)
+a = np.array(list(buf))
+t0 = a[0]
+print("epilogue thread: wait a_free %d, extract %d, groups at %s, last group->store %d, store %d" % (a[1]-a[0], a[2]-a[1], [int(a[10+i]-t0) for i in range(9)], a[3]-a[18], a[4]-a[3]))
+print("mma thread: tile start %d, a_ready at %d, planes issued at %s" % (a[30]-t0, a[31]-t0, [int(a[40+c]-t0) for c in range(7)]))
