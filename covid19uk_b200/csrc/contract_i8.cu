@@ -85,14 +85,67 @@ __device__ __forceinline__ uint64_t umma_desc(uint32_t smem_addr, uint32_t sbo_b
 // N>>3 [17,23), M>>4 [24,29)
 #define I8_IDESC ((2u << 4) | (0u << 7) | (1u << 10) | ((uint32_t)(I8_BN >> 3) << 17) | ((uint32_t)(I8_BM >> 4) << 24))
 
+// ---- digit planes of the infectious counts: one pass over I (33 MB at the UK size, 256 chains) ---------------------
+// CTA <-> 128-row tile; unit = (row r, 16-byte K chunk kc); a lane group of 8 consecutive rows x 4 chunks writes 512
+// contiguous bytes per plane.  Planes are stored per row tile in the canonical UMMA layout, so the contraction kernel
+// brings a plane into shared memory with ONE bulk copy; flags[rt][a] says whether plane a of the tile holds anything.
+__global__ void __launch_bounds__(I8_EPI_THREADS) seir_i8_split_kernel(long long R, int Mp, int na, const int* __restrict__ Ix,
+                                                                       unsigned char* __restrict__ planes, int* __restrict__ flags) {
+  __shared__ int s_nz[4];
+  const int tid = threadIdx.x, lane = tid & 31, rt = blockIdx.x, K = Mp;
+  const long long r0 = (long long)rt * I8_BM;
+  const size_t plane_a = (size_t)I8_BM * K;
+  unsigned char* dst = planes + (size_t)rt * na * plane_a;
+  if (tid < 4) s_nz[tid] = 0;
+  __syncthreads();
+  const int nkc = K / 16;
+  const int nunits = (I8_BM / 8) * (nkc / 4) * 32;
+  uint32_t nz[3] = {0u, 0u, 0u};
+  for (int u0 = tid; u0 < nunits; u0 += 4 * I8_EPI_THREADS) {  // 4 units = 16 independent 16-byte loads in flight per thread
+    int4 v[4][4];
+    uint32_t off[4];
+#pragma unroll
+    for (int b4 = 0; b4 < 4; ++b4) {
+      const int u = u0 + b4 * I8_EPI_THREADS;
+      const int l = u & 31, blk = u >> 5;
+      const int rgrp = blk / (nkc / 4), kq = blk - rgrp * (nkc / 4);
+      const int r = rgrp * 8 + (l & 7), kc = kq * 4 + (l >> 3);
+      const long long gr = r0 + r;
+      const bool in = u < nunits && gr < R;
+#pragma unroll
+      for (int q = 0; q < 4; ++q)
+        v[b4][q] = in ? __ldg(reinterpret_cast<const int4*>(Ix + gr * Mp + kc * 16 + q * 4)) : make_int4(0, 0, 0, 0);
+      off[b4] = (uint32_t)rgrp * (uint32_t)(K * 8) + (uint32_t)kc * 128u + (uint32_t)(l & 7) * 16u;
+    }
+#pragma unroll
+    for (int b4 = 0; b4 < 4; ++b4) {
+      if (u0 + b4 * I8_EPI_THREADS >= nunits) break;
+      for (int a = 0; a < na; ++a) {
+        const int sh = 8 * a;
+        uint4 o;
+        o.x = ((v[b4][0].x >> sh) & 255) | (((v[b4][0].y >> sh) & 255) << 8) | (((v[b4][0].z >> sh) & 255) << 16) | (((v[b4][0].w >> sh) & 255) << 24);
+        o.y = ((v[b4][1].x >> sh) & 255) | (((v[b4][1].y >> sh) & 255) << 8) | (((v[b4][1].z >> sh) & 255) << 16) | (((v[b4][1].w >> sh) & 255) << 24);
+        o.z = ((v[b4][2].x >> sh) & 255) | (((v[b4][2].y >> sh) & 255) << 8) | (((v[b4][2].z >> sh) & 255) << 16) | (((v[b4][2].w >> sh) & 255) << 24);
+        o.w = ((v[b4][3].x >> sh) & 255) | (((v[b4][3].y >> sh) & 255) << 8) | (((v[b4][3].z >> sh) & 255) << 16) | (((v[b4][3].w >> sh) & 255) << 24);
+        *reinterpret_cast<uint4*>(dst + (size_t)a * plane_a + off[b4]) = o;
+        nz[a] |= o.x | o.y | o.z | o.w;
+      }
+    }
+  }
+  for (int a = 1; a < na; ++a)
+    if (__any_sync(0xffffffffu, nz[a] != 0u) && lane == 0) atomicOr(&s_nz[a], 1);
+  __syncthreads();
+  if (tid < 4) flags[rt * 4 + tid] = tid == 0 ? 1 : s_nz[tid];
+}
+
 __global__ void __launch_bounds__(I8_THREADS, 1) seir_contract_i8_kernel(long long R, int Mp, int na, int ntiles,
-                                                                         const int* __restrict__ Ix,
+                                                                         const unsigned char* __restrict__ planes,
+                                                                         const int* __restrict__ flags,
                                                                          const signed char* __restrict__ Bd,
                                                                          const double* __restrict__ colscale, double* __restrict__ Bc) {
   extern __shared__ __align__(1024) unsigned char smem[];
-  __shared__ uint64_t full_b[I8_STAGES], empty_b[I8_STAGES], a_ready, a_free, t_full[4], t_empty[4];
+  __shared__ uint64_t full_b[I8_STAGES], empty_b[I8_STAGES], a_ready, a_region_free, t_full[4], t_empty[4];
   __shared__ uint32_t tmem_base_s;
-  __shared__ int s_plane_nz[2][4];  // per tile parity: digit plane a of the tile holds a non-zero byte
   const int K = Mp, KH = Mp / 2;                      // one B stage = half a plane: 128 columns x KH bytes
   const int plane_a = I8_BM * K;                      // bytes of one A digit plane
   const int stage_b = I8_BN * KH;
@@ -106,11 +159,10 @@ __global__ void __launch_bounds__(I8_THREADS, 1) seir_contract_i8_kernel(long lo
 
   if (tid == 0) {
     for (int s = 0; s < I8_STAGES; ++s) { mbar_init(&full_b[s], 1); mbar_init(&empty_b[s], 1); }
-    mbar_init(&a_ready, I8_EPI_THREADS / 32);
-    mbar_init(&a_free, 1);
+    mbar_init(&a_ready, 1);
+    mbar_init(&a_region_free, I8_EPI_THREADS / 32);
     for (int s = 0; s < 4; ++s) { mbar_init(&t_full[s], 1); mbar_init(&t_empty[s], I8_EPI_THREADS / 32); }
     asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
-    for (int q = 0; q < 8; ++q) s_plane_nz[q >> 2][q & 3] = 0;
   }
   if (warp == 9) {  // TMEM: 512 columns (4 slots x 128 int32 accumulator columns)
     asm volatile("tcgen05.alloc.cta_group::1.sync.aligned.shared::cta.b32 [%0], %1;" ::"r"(smem_u32(&tmem_base_s)), "r"(512u) : "memory");
@@ -122,65 +174,18 @@ __global__ void __launch_bounds__(I8_THREADS, 1) seir_contract_i8_kernel(long lo
   const uint32_t tmem_base = tmem_base_s;
 
   if (warp < 8) {
-    // ================= A-digit extraction + epilogue (256 threads) =================
+    // ================= epilogue (256 threads) =================
     const int half = warp >> 2;             // which 64 of the tile's 128 columns this warp drains
     const int lane_base = (warp & 3) * 32;  // TMEM lanes (= tile rows) this warp may access
-    uint32_t ph_afree = 0, ph_full[4] = {0, 0, 0, 0};
+    uint32_t ph_full[4] = {0, 0, 0, 0};
     int it = 0;
     for (int tile = blockIdx.x; tile < ntiles; tile += gridDim.x, ++it) {
       const int rb = tile / ncol_tiles, ct = tile - rb * ncol_tiles;
       const long long r0 = (long long)rb * I8_BM;
-      // ---- (a) digits of I: unit = (row r, 16-byte K chunk kc); a lane group of 8 consecutive rows x 4 chunks writes
-      //      512 contiguous bytes per plane (bank-conflict free)
+      int na_t = 1;  // planes of this row tile that hold anything (seir_i8_split_kernel)
+      for (int a = 1; a < na; ++a)
+        if (__ldg(flags + rb * 4 + a)) na_t = a + 1;
       if (tid == 0 && it == 1) TM(0);
-      if (it > 0) { mbar_wait(&a_free, ph_afree); ph_afree ^= 1u; }
-      if (tid == 0 && it == 1) TM(1);
-      const int nkc = K / 16;
-      const int nunits = (I8_BM / 8) * (nkc / 4) * 32;
-      uint32_t nz[3] = {0u, 0u, 0u};
-      for (int u0 = tid; u0 < nunits; u0 += 4 * I8_EPI_THREADS) {  // 4 units = 16 independent 16-byte loads in flight per thread
-        int4 v[4][4];
-        uint32_t off[4];
-        (void)0;
-#pragma unroll
-        for (int b4 = 0; b4 < 4; ++b4) {
-          const int u = u0 + b4 * I8_EPI_THREADS;
-          const int l = u & 31, blk = u >> 5;
-          const int rgrp = blk / (nkc / 4), kq = blk - rgrp * (nkc / 4);
-          const int r = rgrp * 8 + (l & 7), kc = kq * 4 + (l >> 3);
-          const long long gr = r0 + r;
-          const bool in = u < nunits && gr < R;
-#pragma unroll
-          for (int q = 0; q < 4; ++q)
-            v[b4][q] = in ? __ldg(reinterpret_cast<const int4*>(Ix + gr * Mp + kc * 16 + q * 4)) : make_int4(0, 0, 0, 0);
-          off[b4] = (uint32_t)rgrp * (uint32_t)(K * 8) + (uint32_t)kc * 128u + (uint32_t)(l & 7) * 16u;
-        }
-#pragma unroll
-        for (int b4 = 0; b4 < 4; ++b4) {
-          if (u0 + b4 * I8_EPI_THREADS >= nunits) break;
-          for (int a = 0; a < na; ++a) {
-            const int sh = 8 * a;
-            uint4 o;
-            o.x = ((v[b4][0].x >> sh) & 255) | (((v[b4][0].y >> sh) & 255) << 8) | (((v[b4][0].z >> sh) & 255) << 16) | (((v[b4][0].w >> sh) & 255) << 24);
-            o.y = ((v[b4][1].x >> sh) & 255) | (((v[b4][1].y >> sh) & 255) << 8) | (((v[b4][1].z >> sh) & 255) << 16) | (((v[b4][1].w >> sh) & 255) << 24);
-            o.z = ((v[b4][2].x >> sh) & 255) | (((v[b4][2].y >> sh) & 255) << 8) | (((v[b4][2].z >> sh) & 255) << 16) | (((v[b4][2].w >> sh) & 255) << 24);
-            o.w = ((v[b4][3].x >> sh) & 255) | (((v[b4][3].y >> sh) & 255) << 8) | (((v[b4][3].z >> sh) & 255) << 16) | (((v[b4][3].w >> sh) & 255) << 24);
-            *reinterpret_cast<uint4*>(smA + (size_t)a * plane_a + off[b4]) = o;
-            nz[a] |= o.x | o.y | o.z | o.w;
-          }
-        }
-      }
-      asm volatile("fence.proxy.async.shared::cta;" ::: "memory");  // generic-proxy stores -> visible to the tensor core
-      for (int a = 1; a < na; ++a)
-        if (__any_sync(0xffffffffu, nz[a] != 0u) && lane == 0) atomicOr(&s_plane_nz[it & 1][a], 1);
-      asm volatile("bar.sync 1, %0;" ::"n"(I8_EPI_THREADS) : "memory");  // every warp's digits and flags are in
-      int na_t = 1;  // planes of this tile that hold anything (plane 0 always counts)
-      for (int a = 1; a < na; ++a)
-        if (s_plane_nz[it & 1][a]) na_t = a + 1;
-      if (lane == 0) mbar_arrive(&a_ready);
-      if (tid == 0)  // reset the OTHER parity's flags for the tile after next (its readers passed a barrier long ago)
-        for (int a = 0; a < 4; ++a) s_plane_nz[(it & 1) ^ 1][a] = 0;
-      if (tid == 0 && it == 1) TM(2);
       // ---- (b) epilogue: groups complete in the order s = na-1, na-2, ..., -(I8_NB-1)
       double out[64];
 #pragma unroll
@@ -224,16 +229,26 @@ __global__ void __launch_bounds__(I8_THREADS, 1) seir_contract_i8_kernel(long lo
           }
         }
       }
-      // the staging region is rewritten with digits by ALL epilogue warps next: wait for every warp's stores to be read out
-      asm volatile("bar.sync 1, %0;" ::"n"(I8_EPI_THREADS) : "memory");
+      // the staging region is refilled with the next tile's planes by the producer's bulk copies (async proxy)
+      asm volatile("fence.proxy.async.shared::cta;" ::: "memory");
+      __syncwarp();
+      if (lane == 0) mbar_arrive(&a_region_free);
       if (tid == 0 && it == 1) TM(4);
     }
   } else if (warp == 8) {
     // ================= producer: planes of Cs =================
     if (lane == 0) {
-      uint32_t n = 0;
-      for (int tile = blockIdx.x; tile < ntiles; tile += gridDim.x) {
-        const int ct = tile % ncol_tiles;
+      uint32_t n = 0, itp = 0;
+      for (int tile = blockIdx.x; tile < ntiles; tile += gridDim.x, ++itp) {
+        const int rb = tile / ncol_tiles, ct = tile - rb * ncol_tiles;
+        // digit planes of the row tile: the A region is free once every epilogue warp has read its output out of it
+        if (itp > 0) mbar_wait(&a_region_free, (itp - 1) & 1u);
+        int na_t = 1;
+        for (int a = 1; a < na; ++a)
+          if (__ldg(flags + rb * 4 + a)) na_t = a + 1;
+        mbar_expect_tx(&a_ready, (unsigned)(na_t * plane_a));
+        for (int a = 0; a < na_t; ++a)
+          bulk_load_1d(smA + (size_t)a * plane_a, planes + ((size_t)rb * na + a) * plane_a, (unsigned)plane_a, &a_ready);
         for (int c = 0; c < I8_NB; ++c)
           for (int h = 0; h < 2; ++h, ++n) {
             const int st = n % I8_STAGES;
@@ -263,7 +278,7 @@ __global__ void __launch_bounds__(I8_THREADS, 1) seir_contract_i8_kernel(long lo
       if (itm == 1) TM(31);
       int na_t = 1;
       for (int a = 1; a < na; ++a)
-        if (s_plane_nz[itm & 1][a]) na_t = a + 1;
+        if (__ldg(flags + (tile / ncol_tiles) * 4 + a)) na_t = a + 1;
       for (int c = 0; c < I8_NB; ++c) {
         for (int h = 0; h < 2; ++h, ++n) {
           const int st = n % I8_STAGES;
@@ -299,7 +314,6 @@ __global__ void __launch_bounds__(I8_THREADS, 1) seir_contract_i8_kernel(long lo
         for (int s = s_hi; s >= s_lo; --s) tc_commit(&t_full[s & 3]);
         if (itm == 1) TM(40 + c);
       }
-      tc_commit(&a_free);  // the A planes may be overwritten for the next tile
     }
   }
   tc_fence_before();
@@ -369,9 +383,16 @@ int seir_launch_contract_i8(seir_chains* c, cudaStream_t s) {
     SEIR_CUDA(cudaFuncSetAttribute(seir_contract_i8_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
     attr = smem;
   }
-  seir_contract_i8_kernel<<<ntiles < sms ? ntiles : sms, I8_THREADS, smem, s>>>(R, m->Mp, m->i8_na, ntiles, c->d_I, m->d_cs_i8,
-                                                                                m->d_cs_scale, c->d_Bc);
-  seir_count_launch(1);
+  const int nrt = (int)((R + I8_BM - 1) / I8_BM);
+  if (!c->d_i8_planes) {
+    SEIR_CUDA(cudaMalloc(reinterpret_cast<void**>(&c->d_i8_planes), (size_t)nrt * m->i8_na * I8_BM * m->Mp));
+    SEIR_CUDA(cudaMalloc(reinterpret_cast<void**>(&c->d_i8_flags), sizeof(int) * 4 * (size_t)nrt));
+    c->bytes += (int64_t)((size_t)nrt * m->i8_na * I8_BM * m->Mp + sizeof(int) * 4 * (size_t)nrt);
+  }
+  seir_i8_split_kernel<<<nrt, I8_EPI_THREADS, 0, s>>>(R, m->Mp, m->i8_na, c->d_I, c->d_i8_planes, c->d_i8_flags);
+  seir_contract_i8_kernel<<<ntiles < sms ? ntiles : sms, I8_THREADS, smem, s>>>(R, m->Mp, m->i8_na, ntiles, c->d_i8_planes, c->d_i8_flags,
+                                                                                m->d_cs_i8, m->d_cs_scale, c->d_Bc);
+  seir_count_launch(2);
   return seir_cuda_check(cudaGetLastError(), "seir_contract_i8_kernel");
 }
 

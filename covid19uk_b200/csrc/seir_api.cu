@@ -240,7 +240,7 @@ void seir_chains_destroy(seir_chains* c) {
   cudaFree(c->d_Bc); cudaFree(c->d_llc_part); cudaFree(c->d_llc_sum); cudaFree(c->d_Yir); cudaFree(c->d_pa); cudaFree(c->d_psiW); cudaFree(c->d_gam);
   cudaFree(c->d_logpir); cudaFree(c->d_pm); cudaFree(c->d_scal); cudaFree(c->d_carq); cudaFree(c->d_val_part); cudaFree(c->d_psi_part);
   cudaFree(c->d_col_part); cudaFree(c->d_rowsum); cudaFree(c->d_upd); cudaFree(c->d_upd_part); cudaFree(c->d_llc_adj);
-  cudaFree(c->d_tlp); cudaFree(c->d_last_acc); cudaFree(c->d_nzd); cudaFree(c->d_hmc_u0); cudaFree(c->d_hmc_p); cudaFree(c->d_hmc_grad);
+  cudaFree(c->d_tlp); cudaFree(c->d_last_acc); cudaFree(c->d_nzd); cudaFree(c->d_i8_planes); cudaFree(c->d_i8_flags); cudaFree(c->d_hmc_u0); cudaFree(c->d_hmc_p); cudaFree(c->d_hmc_grad);
   cudaFree(c->d_hmc_val);
   if (c->grp_ready) {
     for (int g = 0; g < 4; ++g) { cudaStreamDestroy(c->grp_stream[g]); cudaEventDestroy(c->grp_join[g]); }

@@ -101,6 +101,8 @@ struct seir_chains {
   long long* d_sumYei;   // [B]
   long long* d_sumEres;  // [B]  sum (E - y_ei)
   int* d_flags;          // [B]
+  unsigned char* d_i8_planes;  // [B*T/128][na][128 x Mp] digit planes of I for the int8 contraction (allocated on first use)
+  int* d_i8_flags;             // [B*T/128][4] plane a of the row tile holds a non-zero byte
   int* d_nzd;            // [B][2][Mp] days with >= 1 event per metapopulation, for S->E and E->I (proposal normalisers)
   // theta-derived
   double *d_pa, *d_psiW, *d_gam, *d_logpir;  // [B][T]
