@@ -14,16 +14,21 @@
 // log-probability (tests/test_gpu_contract.py compares against the FP64 DMMA kernel of contract.cu).
 // At most 18 (typically 12: infectious counts below 65536) int8 GEMMs of 2 M^2 T flop each replace one FP64 GEMM.
 //
-// Kernel (one CTA per SM, persistent over 128 x 128 output tiles):
-//   warps 0-7  (a) split the tile's 128 x K int32 slab of I into na int8 planes in shared memory, canonical K-major
-//                  no-swizzle UMMA layout (8 x 16 B core matrices), fence.proxy.async, arrive
-//              (b) epilogue: tcgen05.ld finished accumulator groups, FMA them into 64 FP64 registers per thread with
-//                  weight 128^(s-1), scale by 2^e_i, store the tile
-//   warp 8     producer: streams the pre-split planes of Cs (laid out on the host in the same canonical layout) with
-//              1-D bulk copies into a 3-stage ring (half a plane per stage)
-//   warp 9     allocates TMEM (512 columns = 4 accumulator slots of 128), one elected lane issues tcgen05.mma:
-//              plane-major order (c outer, a inner) so that at most na+1 <= 4 accumulator groups are live at a time:
-//              group s = a - c uses slot s mod 4; after plane c group na-1-c is complete and is committed to the epilogue.
+// Two kernels:
+//   seir_i8_split_kernel     one pass over I: unsigned byte planes per 128-row tile in the canonical K-major no-swizzle
+//                            UMMA layout (8 x 16 B core matrices) + per-tile "plane holds anything" flags
+//   seir_contract_i8_kernel  one CTA per SM, persistent over 128 x 128 output tiles:
+//     warps 0-7  epilogue: tcgen05.ld finished accumulator groups, FMA them into 64 FP64 registers per thread with weight
+//                256^(s-1), release the A region, scale by 2^e_i, store the rows with 32-byte stores
+//     warp 8     producer: 1-D bulk copies of the tile's digit planes of I (one copy per plane) and of the pre-split planes
+//                of Cs (laid out on the host in the same canonical layout; 3-stage ring, half a plane per stage)
+//     warp 9     allocates TMEM (512 columns = 4 accumulator slots of 128), one thread issues tcgen05.mma (kind::i8,
+//                M = N = 128, K = 32) in plane-major order (c outer, a inner) so that at most na+1 <= 4 accumulator groups
+//                are live: group s = a - c uses slot s mod 4; after plane c group na_t-1-c is complete and is committed
+//                to the epilogue.
+// Measured (UK size, 256 chains, B200): 104 us for both kernels vs 200 us for the FP64 DMMA kernel.  Per 128 x 128 tile:
+// 144 MMAs in ~13 us (~110 cycles per MMA: operands from shared memory, 8 KB per MMA, plus ~0.8 us per plane of
+// barrier/commit turnaround), ~4 us of output stores; 504 tiles on 148 SMs = 4 rounds.
 #include <math.h>
 #include <stdlib.h>
 
@@ -38,7 +43,7 @@
 #define I8_STAGES 3
 #define I8_EPI_THREADS 256
 #define I8_THREADS (I8_EPI_THREADS + 64)
-#define I8_STAGE_OUT (8 * 32 * 65 * 8)  // bytes of the epilogue's transposition buffer
+#define I8_STAGE_OUT 0
 
 // phase timestamps of one CTA's second tile (build with SEIR_NVCC_EXTRA=-DSEIR_I8_DEBUG, read with seir_debug_i8)
 #ifdef SEIR_I8_DEBUG
@@ -150,7 +155,6 @@ __global__ void __launch_bounds__(I8_THREADS, 1) seir_contract_i8_kernel(long lo
   const int plane_a = I8_BM * K;                      // bytes of one A digit plane
   const int stage_b = I8_BN * KH;
   unsigned char* smA = smem;                          // [na][plane_a]
-  // (the A region doubles as the output staging buffer of the epilogue: at least 8 warps x 32 x 65 doubles)
   const size_t a_region = (size_t)na * plane_a > (size_t)I8_STAGE_OUT ? (size_t)na * plane_a : (size_t)I8_STAGE_OUT;
   unsigned char* smB = smem + a_region;               // [I8_STAGES][stage_b]
   const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
@@ -212,27 +216,26 @@ __global__ void __launch_bounds__(I8_THREADS, 1) seir_contract_i8_kernel(long lo
         }
       }
       if (tid == 0 && it == 1) TM(3);
-      // ---- store: every MMA of the tile has completed (the last groups were just drained), so the A planes are dead:
-      //      each warp transposes its 32 x 64 block through its own 16.6 KB of that region (row stride 65 doubles: conflict
-      //      free) and writes whole 512-byte row segments
+      // every MMA of the tile has completed (its last group was just drained): the A planes are dead, the producer may
+      // refill them while this tile is being stored
+      __syncwarp();
+      if (lane == 0) mbar_arrive(&a_region_free);
+      // ---- store: thread <-> row, 64 consecutive columns as sixteen 32-byte stores (st.global.v4.f64: every store fills
+      //      a whole 32-byte sector; a 16-byte store pattern took 8.4 us per tile, a shared-memory transposition 3.5 us but
+      //      held the A region until the end)
       {
         const int c0 = ct * I8_BN + half * 64;
-        double* stg = reinterpret_cast<double*>(smA) + (size_t)warp * (32 * 65);
+        const long long row = r0 + lane_base + lane;
+        if (row < R) {
+          double* dst = Bc + row * Mp + c0;
 #pragma unroll
-        for (int j = 0; j < 64; ++j) stg[lane * 65 + j] = out[j] * colscale[c0 + j];
-        __syncwarp();
-        for (int rr = 0; rr < 32; ++rr) {
-          const long long row = r0 + lane_base + rr;
-          if (row < R) {
-            const double x0 = stg[rr * 65 + 2 * lane], x1 = stg[rr * 65 + 2 * lane + 1];
-            *reinterpret_cast<double2*>(Bc + row * Mp + c0 + 2 * lane) = make_double2(x0, x1);
+          for (int j = 0; j < 64; j += 4) {
+            const double x0 = out[j] * colscale[c0 + j], x1 = out[j + 1] * colscale[c0 + j + 1], x2 = out[j + 2] * colscale[c0 + j + 2],
+                         x3 = out[j + 3] * colscale[c0 + j + 3];
+            asm volatile("st.global.v4.f64 [%0], {%1, %2, %3, %4};" ::"l"(dst + j), "d"(x0), "d"(x1), "d"(x2), "d"(x3) : "memory");
           }
         }
       }
-      // the staging region is refilled with the next tile's planes by the producer's bulk copies (async proxy)
-      asm volatile("fence.proxy.async.shared::cta;" ::: "memory");
-      __syncwarp();
-      if (lane == 0) mbar_arrive(&a_region_free);
       if (tid == 0 && it == 1) TM(4);
     }
   } else if (warp == 8) {
@@ -241,16 +244,20 @@ __global__ void __launch_bounds__(I8_THREADS, 1) seir_contract_i8_kernel(long lo
       uint32_t n = 0, itp = 0;
       for (int tile = blockIdx.x; tile < ntiles; tile += gridDim.x, ++itp) {
         const int rb = tile / ncol_tiles, ct = tile - rb * ncol_tiles;
-        // digit planes of the row tile: the A region is free once every epilogue warp has read its output out of it
-        if (itp > 0) mbar_wait(&a_region_free, (itp - 1) & 1u);
-        int na_t = 1;
-        for (int a = 1; a < na; ++a)
-          if (__ldg(flags + rb * 4 + a)) na_t = a + 1;
-        mbar_expect_tx(&a_ready, (unsigned)(na_t * plane_a));
-        for (int a = 0; a < na_t; ++a)
-          bulk_load_1d(smA + (size_t)a * plane_a, planes + ((size_t)rb * na + a) * plane_a, (unsigned)plane_a, &a_ready);
+        int issued = 0;
         for (int c = 0; c < I8_NB; ++c)
           for (int h = 0; h < 2; ++h, ++n) {
+            if (issued++ == I8_STAGES) {
+              // (the first ring-full of Cs stages of this tile is already on its way: it does not depend on the A region)
+              // digit planes of the row tile: the A region is free once every epilogue warp has drained the previous tile
+              if (itp > 0) mbar_wait(&a_region_free, (itp - 1) & 1u);
+              int na_t = 1;
+              for (int a = 1; a < na; ++a)
+                if (__ldg(flags + rb * 4 + a)) na_t = a + 1;
+              mbar_expect_tx(&a_ready, (unsigned)(na_t * plane_a));
+              for (int a = 0; a < na_t; ++a)
+                bulk_load_1d(smA + (size_t)a * plane_a, planes + ((size_t)rb * na + a) * plane_a, (unsigned)plane_a, &a_ready);
+            }
             const int st = n % I8_STAGES;
             if (n >= I8_STAGES) mbar_wait(&empty_b[st], ((n / I8_STAGES) - 1) & 1u);
 #ifdef SEIR_I8_EXPERIMENT_NOB  // timing experiment only (wrong results): 16 bytes per stage instead of the half plane

@@ -14,5 +14,5 @@ buf = (ctypes.c_longlong * 64)()
 nat.load().seir_debug_i8(buf)
 a = np.array(list(buf))
 t0 = a[0]
-print("epilogue thread: wait a_free %d, extract %d, groups at %s, last group->store %d, store %d" % (a[1]-a[0], a[2]-a[1], [int(a[10+i]-t0) for i in range(9)], a[3]-a[18], a[4]-a[3]))
-print("mma thread: tile start %d, a_ready at %d, planes issued at %s" % (a[30]-t0, a[31]-t0, [int(a[40+c]-t0) for c in range(7)]))
+print("epilogue thread: groups at", [int(a[10+i]-t0) for i in range(9) if a[10+i] > 0], "drain done", int(a[3]-t0), "store done", int(a[4]-t0))
+print("mma thread: tile start %d, a_ready at %d, planes issued at %s" % (a[30]-t0, a[31]-t0, [int(a[40+c]-t0) for c in range(6)]))
