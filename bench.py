@@ -292,10 +292,10 @@ def run_native(args):
         hbm_peak, peak_src = _peaks()
         grad_d = torch.empty_like(theta_d)
         kw = dict(events=events_d, theta=theta_d, kind=kind, parts=parts, out=out_d, grad=grad_d)
-        names = {0: "seir_ingest_kernel", 7: "seir_coef_kernel", 1: "seir_contract_kernel", 2: "seir_theta_prep_kernel",
+        names = {0: "seir_ingest_kernel", 7: "seir_coef_kernel", 1: "seir_contract_i8_kernel (+ seir_i8_split_kernel)", 2: "seir_theta_prep_kernel",
                  3: "seir_loglik_kernel<false>", 5: "seir_finalize_kernel", 4: "seir_loglik_kernel<true>"}
         cold_stages = (0, 7, 1, 2, 3, 5)
-        stage_ms = {s: time_stage(eng, B, s, max(K, 10), **kw) for s in cold_stages + (4,)}
+        stage_ms = {s: time_stage(eng, B, s, max(K, 10), **kw) for s in cold_stages + (4, 9)}  # 9: the FP64 DMMA contraction, for comparison
         Mp = (M_UK + 63) // 64 * 64
         P = 6 + T_UK - 1 + M_UK
         cells = B * T_UK * M_UK
@@ -322,8 +322,19 @@ def run_native(args):
         for sidx in cold_stages:
             ent = {"kernel": names[sidx], "ms": stage_ms[sidx]}
             if sidx == 1:
-                ach = flops_contract / (stage_ms[sidx] * 1e-3) / 1e12
-                ent.update(bound="tensor", achieved=ach, peak=fp64_peak, unit="TFLOP/s", frac=ach / fp64_peak)
+                # exact int8 splitting on tcgen05: executed work = (byte planes of I actually non-zero) x 6 planes of Cs GEMMs of
+                # 2 Mp^2 (B T) int8 op each.  Peak: nominal dense fp8/int8 tensor rate of B200_PROFILING.md (int8 is not in
+                # MEASURED_PEAKS.json, which holds HBM and dense bf16 only).
+                state_i = np.cumsum(pb["events"][..., 1] - pb["events"][..., 2], axis=-1) + pb["initial_state"][None, :, 2:3]
+                planes_i = max(1, int(np.ceil(np.log2(float(state_i.max()) + 1.0) / 8.0)))
+                ops = planes_i * 6 * 2.0 * Mp * Mp * T_UK * B
+                ach = ops / (stage_ms[sidx] * 1e-3) / 1e12
+                ent.update(bound="tensor", achieved=ach, peak=4500.0, unit="TOP/s (int8)", frac=ach / 4500.0,
+                           int8_gemms=planes_i * 6,
+                           fp64_equivalent_tflops=flops_contract / (stage_ms[sidx] * 1e-3) / 1e12,
+                           fp64_dmma_kernel_ms=stage_ms[9], fp64_dmma_tflops=flops_contract / (stage_ms[9] * 1e-3) / 1e12,
+                           fp64_dmma_frac_of_dgemm=flops_contract / (stage_ms[9] * 1e-3) / 1e12 / fp64_peak,
+                           peak_source="nominal dense fp8/int8 tensor rate (B200_PROFILING.md); int8 is not in MEASURED_PEAKS.json")
             elif alg_bytes.get(sidx):
                 ach = alg_bytes[sidx] / (stage_ms[sidx] * 1e-3) / 1e9
                 ent.update(bound="hbm", achieved=ach, peak=hbm_peak, unit="GB/s", frac=ach / hbm_peak)
@@ -333,7 +344,7 @@ def run_native(args):
         roofline = {"kernel": dom["kernel"], "bound": dom["bound"], "achieved": dom["achieved"], "peak": dom["peak"],
                     "unit": dom["unit"], "frac": dom["frac"], "traffic": _traffic(dom["kernel"]),
                     "traffic_unit": "dram bytes per launch (ncu --set full, profiles/r01_traffic.json)", "share_of_step": dom["ms"] / cold_sum,
-                    "peak_source": (peak_src if dom["bound"] == "hbm" else "cuBLAS DGEMM 4096^3 measured in this run (FP64 is not in MEASURED_PEAKS.json)")}
+                    "peak_source": (peak_src if dom["bound"] == "hbm" else dom.get("peak_source", ""))}
         ach4 = alg_bytes[4] / (stage_ms[4] * 1e-3) / 1e9
         warm_grad = {"kernel": names[4], "ms": stage_ms[4], "bound": "hbm", "achieved": ach4, "peak": hbm_peak, "unit": "GB/s",
                      "frac": ach4 / hbm_peak}
