@@ -91,7 +91,7 @@ __device__ __forceinline__ uint64_t umma_desc(uint32_t smem_addr, uint32_t sbo_b
 #define I8_IDESC ((2u << 4) | (0u << 7) | (1u << 10) | ((uint32_t)(I8_BN >> 3) << 17) | ((uint32_t)(I8_BM >> 4) << 24))
 
 // ---- digit planes of the infectious counts: one pass over I (33 MB at the UK size, 256 chains) ---------------------
-// CTA <-> 128-row tile; unit = (row r, 16-byte K chunk kc); a lane group of 8 consecutive rows x 4 chunks writes 512
+// grid (row tiles, 4): a CTA splits a quarter of a 128-row tile; unit = (row r, 16-byte K chunk kc); a lane group of 8 consecutive rows x 4 chunks writes 512
 // contiguous bytes per plane.  Planes are stored per row tile in the canonical UMMA layout, so the contraction kernel
 // brings a plane into shared memory with ONE bulk copy; flags[rt][a] says whether plane a of the tile holds anything.
 __global__ void __launch_bounds__(I8_EPI_THREADS) seir_i8_split_kernel(long long R, int Mp, int na, const int* __restrict__ Ix,
@@ -106,7 +106,8 @@ __global__ void __launch_bounds__(I8_EPI_THREADS) seir_i8_split_kernel(long long
   const int nkc = K / 16;
   const int nunits = (I8_BM / 8) * (nkc / 4) * 32;
   uint32_t nz[3] = {0u, 0u, 0u};
-  for (int u0 = tid; u0 < nunits; u0 += 4 * I8_EPI_THREADS) {  // 4 units = 16 independent 16-byte loads in flight per thread
+  const int uq = nunits / 4, ulo = blockIdx.y * uq, uhi = blockIdx.y == 3 ? nunits : ulo + uq;  // (nunits is a multiple of 128)
+  for (int u0 = ulo + tid; u0 < uhi; u0 += 4 * I8_EPI_THREADS) {  // 4 units = 16 independent 16-byte loads in flight per thread
     int4 v[4][4];
     uint32_t off[4];
 #pragma unroll
@@ -116,7 +117,7 @@ __global__ void __launch_bounds__(I8_EPI_THREADS) seir_i8_split_kernel(long long
       const int rgrp = blk / (nkc / 4), kq = blk - rgrp * (nkc / 4);
       const int r = rgrp * 8 + (l & 7), kc = kq * 4 + (l >> 3);
       const long long gr = r0 + r;
-      const bool in = u < nunits && gr < R;
+      const bool in = u < uhi && gr < R;
 #pragma unroll
       for (int q = 0; q < 4; ++q)
         v[b4][q] = in ? __ldg(reinterpret_cast<const int4*>(Ix + gr * Mp + kc * 16 + q * 4)) : make_int4(0, 0, 0, 0);
@@ -124,7 +125,7 @@ __global__ void __launch_bounds__(I8_EPI_THREADS) seir_i8_split_kernel(long long
     }
 #pragma unroll
     for (int b4 = 0; b4 < 4; ++b4) {
-      if (u0 + b4 * I8_EPI_THREADS >= nunits) break;
+      if (u0 + b4 * I8_EPI_THREADS >= uhi) break;
       for (int a = 0; a < na; ++a) {
         const int sh = 8 * a;
         uint4 o;
@@ -140,7 +141,7 @@ __global__ void __launch_bounds__(I8_EPI_THREADS) seir_i8_split_kernel(long long
   for (int a = 1; a < na; ++a)
     if (__any_sync(0xffffffffu, nz[a] != 0u) && lane == 0) atomicOr(&s_nz[a], 1);
   __syncthreads();
-  if (tid < 4) flags[rt * 4 + tid] = tid == 0 ? 1 : s_nz[tid];
+  if (tid < 4 && (tid == 0 || s_nz[tid])) atomicOr(flags + rt * 4 + tid, 1);  // (flags zeroed by the launcher)
 }
 
 __global__ void __launch_bounds__(I8_THREADS, 1) seir_contract_i8_kernel(long long R, int Mp, int na, int ntiles,
@@ -396,7 +397,8 @@ int seir_launch_contract_i8(seir_chains* c, cudaStream_t s) {
     SEIR_CUDA(cudaMalloc(reinterpret_cast<void**>(&c->d_i8_flags), sizeof(int) * 4 * (size_t)nrt));
     c->bytes += (int64_t)((size_t)nrt * m->i8_na * I8_BM * m->Mp + sizeof(int) * 4 * (size_t)nrt);
   }
-  seir_i8_split_kernel<<<nrt, I8_EPI_THREADS, 0, s>>>(R, m->Mp, m->i8_na, c->d_I, c->d_i8_planes, c->d_i8_flags);
+  SEIR_CUDA(cudaMemsetAsync(c->d_i8_flags, 0, sizeof(int) * 4 * (size_t)nrt, s));
+  seir_i8_split_kernel<<<dim3(nrt, 4), I8_EPI_THREADS, 0, s>>>(R, m->Mp, m->i8_na, c->d_I, c->d_i8_planes, c->d_i8_flags);
   seir_contract_i8_kernel<<<ntiles < sms ? ntiles : sms, I8_THREADS, smem, s>>>(R, m->Mp, m->i8_na, ntiles, c->d_i8_planes, c->d_i8_flags,
                                                                                 m->d_cs_i8, m->d_cs_scale, c->d_Bc);
   seir_count_launch(2);

@@ -11,11 +11,11 @@ tail -c 600 $out/${tag}_bench.err
 python bench.py --impl reference --steps 5 --warmup 1 > $out/${tag}_bench_ref.json 2>> $out/${tag}_bench.err
 python tools/profile_sweep.py --sweeps 5 > $out/${tag}_sweep.json 2> $out/${tag}_sweep.err; cat $out/${tag}_sweep.json
 if [ "$2" != "noncu" ]; then
-python tools/profile_once.py > $out/${tag}_once_plain.log 2>&1 &&
+SEIR_SWEEP_GROUPS=1 python tools/profile_once.py > $out/${tag}_once_plain.log 2>&1 &&
 ncu --metrics gpu__time_duration.sum --clock-control none --profile-from-start off --csv --log-file $out/${tag}_launches.csv \
-    python tools/profile_once.py > $out/${tag}_ncu_list.log 2>&1
-python tools/profile_once.py > $out/${tag}_once_plain2.log 2>&1 &&
+    env SEIR_SWEEP_GROUPS=1 python tools/profile_once.py > $out/${tag}_ncu_list.log 2>&1
+SEIR_SWEEP_GROUPS=1 python tools/profile_once.py > $out/${tag}_once_plain2.log 2>&1 &&
 ncu --set full --clock-control none --import-source on --profile-from-start off -k regex:seir_ -o $out/${tag}_full \
-    python tools/profile_once.py > $out/${tag}_ncu_full.log 2>&1
+    env SEIR_SWEEP_GROUPS=1 python tools/profile_once.py > $out/${tag}_ncu_full.log 2>&1
 tail -2 $out/${tag}_ncu_full.log
 fi
