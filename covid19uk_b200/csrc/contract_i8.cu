@@ -290,8 +290,10 @@ __global__ void __launch_bounds__(I8_THREADS, 1) seir_contract_i8_kernel(long lo
       for (int c = 0; c < I8_NB; ++c) {
         for (int h = 0; h < 2; ++h, ++n) {
           const int st = n % I8_STAGES;
+          if (itm == 1 && c == 2) TM(50 + 3 * h);
           mbar_wait(&full_b[st], (n / I8_STAGES) & 1u);
           tc_fence_after();
+          if (itm == 1 && c == 2) TM(51 + 3 * h);
           const uint64_t b_desc0 = umma_desc(smem_u32(smB + (size_t)st * stage_b), (uint32_t)KH * 8u);
           for (int a = 0; a < na_t; ++a) {
             const int s = a - c, slot = s & 3;
@@ -315,6 +317,7 @@ __global__ void __launch_bounds__(I8_THREADS, 1) seir_contract_i8_kernel(long lo
               for (int kk = 0; kk < ksteps_h; ++kk) tc_mma_i8(d_addr, a_desc0 + (uint64_t)kk * 16u, b_desc0 + (uint64_t)kk * 16u, I8_IDESC, 1u);
 #endif
           }
+          if (itm == 1 && c == 2) TM(52 + 3 * h);
           tc_commit(&empty_b[st]);  // the stage is free once these MMAs have read it
         }
         // plane c done: group na-1-c has all its pairs; after the last plane every remaining group has

@@ -198,13 +198,10 @@ static int launch_ingest_tc(seir_chains* c, const EV* d_events, int b0, int nb, 
 
 // zero every accumulator the ingest kernels add into (before the first chain range of a new event tensor)
 int seir_ingest_reset(seir_chains* c, cudaStream_t s) {
-  const int B = c->B;
-  // one memset over the contiguous integer-statistics block [Yir | Rir | sumYei | sumEres | flags]
+  // one memset over the contiguous block [Yir | Rir | sumYei | sumEres | flags | llc_adj | last_acc | nzd] (seir_chains_create):
+  // the integer statistics and event-day counts the ingest kernels add into, the coefficient adjustments of the discrete
+  // updates, and the last accepted proposals (new events = freshly bootstrapped kernels, MetropolisHastings accepted_results)
   SEIR_CUDA(cudaMemsetAsync(c->d_Yir, 0, c->stats_bytes, s));
-  SEIR_CUDA(cudaMemsetAsync(c->d_llc_adj, 0, sizeof(double) * (size_t)B, s));
-  SEIR_CUDA(cudaMemsetAsync(c->d_nzd, 0, sizeof(int) * (size_t)B * 2 * c->model->Mp, s));
-  // new events = freshly bootstrapped kernels: no proposal has been accepted yet (MetropolisHastings accepted_results)
-  SEIR_CUDA(cudaMemsetAsync(c->d_last_acc, 0, sizeof(int) * (size_t)4 * B * 4 * SEIR_MMAX, s));
   return SEIR_OK;
 }
 

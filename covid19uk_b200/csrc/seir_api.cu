@@ -202,7 +202,7 @@ int seir_chains_create(const seir_model* m, int B, seir_chains** out) {
       (rc = dev_alloc(&c->d_yir, cells, &c->bytes)) || (rc = dev_alloc(&c->d_S, cells, &c->bytes)) ||
       (rc = dev_alloc(&c->d_E, cells, &c->bytes)) || (rc = dev_alloc(&c->d_I, cells, &c->bytes)) ||
       (rc = dev_alloc(&c->d_Bc, cells, &c->bytes)) || (rc = dev_alloc(&c->d_llc_part, BT * (m->Mp / 32), &c->bytes)) || (rc = dev_alloc(&c->d_llc_sum, (size_t)B, &c->bytes)) ||
-      (rc = dev_alloc(&c->d_Yir, 2 * BT + 2 * (size_t)B + ((size_t)B + 1) / 2, &c->bytes)) || (rc = dev_alloc(&c->d_pa, BT, &c->bytes)) ||
+      (rc = dev_alloc(&c->d_Yir, 2 * BT + 2 * (size_t)B + ((size_t)B + 1) / 2 + (size_t)B + 32 * (size_t)B + (size_t)B * m->Mp, &c->bytes)) || (rc = dev_alloc(&c->d_pa, BT, &c->bytes)) ||
       (rc = dev_alloc(&c->d_psiW, BT, &c->bytes)) || (rc = dev_alloc(&c->d_gam, BT, &c->bytes)) ||
       (rc = dev_alloc(&c->d_logpir, BT, &c->bytes)) || (rc = dev_alloc(&c->d_pm, (size_t)B * m->Mp, &c->bytes)) ||
       (rc = dev_alloc(&c->d_scal, (size_t)B * SEIR_NSCAL, &c->bytes)) || (rc = dev_alloc(&c->d_carq, (size_t)B * m->Mp, &c->bytes)) ||
@@ -212,9 +212,7 @@ int seir_chains_create(const seir_model* m, int B, seir_chains** out) {
       (rc = dev_alloc(&c->d_rowsum, (size_t)B * m->Mp * SEIR_MAX_SPLITS, &c->bytes)) ||
       (rc = dev_alloc(&c->d_upd, (size_t)B, &c->bytes)) ||
       (rc = dev_alloc(&c->d_upd_part, (size_t)B * ((m->T + 7) / 8), &c->bytes)) ||
-      (rc = dev_alloc(&c->d_llc_adj, (size_t)B, &c->bytes)) || (rc = dev_alloc(&c->d_tlp, (size_t)B, &c->bytes)) ||
-      (rc = dev_alloc(&c->d_last_acc, (size_t)4 * B * 4 * SEIR_MMAX, &c->bytes)) ||
-      (rc = dev_alloc(&c->d_nzd, (size_t)B * 2 * m->Mp, &c->bytes))) {
+      (rc = dev_alloc(&c->d_tlp, (size_t)B, &c->bytes))) {
     seir_chains_destroy(c);
     return rc;
   }
@@ -223,12 +221,16 @@ int seir_chains_create(const seir_model* m, int B, seir_chains** out) {
   c->d_sumYei = c->d_Rir + BT;
   c->d_sumEres = c->d_sumYei + B;
   c->d_flags = reinterpret_cast<int*>(c->d_sumEres + B);
-  c->stats_bytes = sizeof(long long) * (2 * BT + 2 * (size_t)B) + sizeof(int) * (size_t)B;
+  // ... followed (8-byte units) by [llc_adj B | last_acc 4 x B x 4 x SEIR_MMAX ints | nzd B x 2 x Mp ints]: everything a new
+  // event tensor resets sits in ONE block, cleared by one memset
+  long long* after_flags = c->d_sumEres + B + ((size_t)B + 1) / 2;
+  c->d_llc_adj = reinterpret_cast<double*>(after_flags);
+  c->d_last_acc = reinterpret_cast<int*>(after_flags + B);
+  c->d_nzd = reinterpret_cast<int*>(after_flags + B + 32 * (size_t)B);
+  static_assert(4 * 4 * SEIR_MMAX * sizeof(int) == 32 * sizeof(long long), "last_acc block size");
+  c->stats_bytes = sizeof(long long) * (2 * BT + 2 * (size_t)B + ((size_t)B + 1) / 2 + (size_t)B + 32 * (size_t)B + (size_t)B * m->Mp);
   c->nllc = 0;
   SEIR_CUDA(cudaMemset(c->d_Yir, 0, c->stats_bytes));
-  SEIR_CUDA(cudaMemset(c->d_llc_adj, 0, sizeof(double) * (size_t)B));
-  SEIR_CUDA(cudaMemset(c->d_last_acc, 0, sizeof(int) * (size_t)4 * B * 4 * SEIR_MMAX));
-  SEIR_CUDA(cudaMemset(c->d_nzd, 0, sizeof(int) * (size_t)B * 2 * m->Mp));
   *out = c;
   return SEIR_OK;
 }
@@ -239,8 +241,8 @@ void seir_chains_destroy(seir_chains* c) {
   cudaFree(c->d_yse); cudaFree(c->d_yei); cudaFree(c->d_yir); cudaFree(c->d_S); cudaFree(c->d_E); cudaFree(c->d_I);
   cudaFree(c->d_Bc); cudaFree(c->d_llc_part); cudaFree(c->d_llc_sum); cudaFree(c->d_Yir); cudaFree(c->d_pa); cudaFree(c->d_psiW); cudaFree(c->d_gam);
   cudaFree(c->d_logpir); cudaFree(c->d_pm); cudaFree(c->d_scal); cudaFree(c->d_carq); cudaFree(c->d_val_part); cudaFree(c->d_psi_part);
-  cudaFree(c->d_col_part); cudaFree(c->d_rowsum); cudaFree(c->d_upd); cudaFree(c->d_upd_part); cudaFree(c->d_llc_adj);
-  cudaFree(c->d_tlp); cudaFree(c->d_last_acc); cudaFree(c->d_nzd); cudaFree(c->d_i8_planes); cudaFree(c->d_i8_flags); cudaFree(c->d_hmc_u0); cudaFree(c->d_hmc_p); cudaFree(c->d_hmc_grad);
+  cudaFree(c->d_col_part); cudaFree(c->d_rowsum); cudaFree(c->d_upd); cudaFree(c->d_upd_part);
+  cudaFree(c->d_tlp); cudaFree(c->d_i8_planes); cudaFree(c->d_i8_flags); cudaFree(c->d_hmc_u0); cudaFree(c->d_hmc_p); cudaFree(c->d_hmc_grad);
   cudaFree(c->d_hmc_val);
   if (c->grp_ready) {
     for (int g = 0; g < 4; ++g) { cudaStreamDestroy(c->grp_stream[g]); cudaEventDestroy(c->grp_join[g]); }

@@ -16,3 +16,4 @@ a = np.array(list(buf))
 t0 = a[0]
 print("epilogue thread: groups at", [int(a[10+i]-t0) for i in range(9) if a[10+i] > 0], "drain done", int(a[3]-t0), "store done", int(a[4]-t0))
 print("mma thread: tile start %d, a_ready at %d, planes issued at %s" % (a[30]-t0, a[31]-t0, [int(a[40+c]-t0) for c in range(6)]))
+print("plane 2 of the MMA thread: [before wait, after wait, after issue] x 2 halves:", [int(a[50+i]-a[41]) for i in range(6)], "plane done", int(a[42]-a[41]))
