@@ -15,20 +15,21 @@
 // At most 18 (typically 12: infectious counts below 65536) int8 GEMMs of 2 M^2 T flop each replace one FP64 GEMM.
 //
 // Two kernels:
-//   seir_i8_split_kernel     one pass over I: unsigned byte planes per 128-row tile in the canonical K-major no-swizzle
-//                            UMMA layout (8 x 16 B core matrices) + per-tile "plane holds anything" flags
+//   seir_i8_split_kernel     one pass over I: unsigned byte planes per 128-row tile in the K-major 128-byte-swizzled UMMA
+//                            layout ([K/128] blocks of [128 rows x 128 B]) + per-tile "plane holds anything" flags
 //   seir_contract_i8_kernel  one CTA per SM, persistent over 128 x 128 output tiles:
 //     warps 0-7  epilogue: tcgen05.ld finished accumulator groups, FMA them into 64 FP64 registers per thread with weight
 //                256^(s-1), release the A region, scale by 2^e_i, store the rows with 32-byte stores
 //     warp 8     producer: 1-D bulk copies of the tile's digit planes of I (one copy per plane) and of the pre-split planes
-//                of Cs (laid out on the host in the same canonical layout; 3-stage ring, half a plane per stage)
+//                of Cs (laid out on the host in the same layout; 4-stage ring, one 16 KB block per stage)
 //     warp 9     allocates TMEM (512 columns = 4 accumulator slots of 128), one thread issues tcgen05.mma (kind::i8,
 //                M = N = 128, K = 32) in plane-major order (c outer, a inner) so that at most na+1 <= 4 accumulator groups
 //                are live: group s = a - c uses slot s mod 4; after plane c group na_t-1-c is complete and is committed
 //                to the epilogue.
 // Measured (UK size, 256 chains, B200): 104 us for both kernels vs 200 us for the FP64 DMMA kernel.  Per 128 x 128 tile:
-// 144 MMAs in ~13 us (~110 cycles per MMA: operands from shared memory, 8 KB per MMA, plus ~0.8 us per plane of
-// barrier/commit turnaround), ~4 us of output stores; 504 tiles on 148 SMs = 4 rounds.
+// 144 MMAs in ~13 us (~150 cycles per MMA with both operands in shared memory -- the same with the no-swizzle core-matrix
+// layout and with 128-byte swizzle: the rate of the instruction, not the layout), ~4 us of output stores; 504 tiles on
+// 148 SMs = 4 rounds.
 #include <math.h>
 #include <stdlib.h>
 
@@ -40,7 +41,9 @@
 #define I8_BM 128
 #define I8_BN 128
 #define I8_NB 6        // digit planes of Cs (balanced radix 256)
-#define I8_STAGES 3
+#define I8_STAGES 4
+#define I8_KB 128        // bytes of K per swizzled row (one 128-byte swizzle span = 4 MMAs of K = 32)
+#define I8_KBLOCK (I8_BM * I8_KB)  // bytes of one [128 rows x 128 B] operand block
 #define I8_EPI_THREADS 256
 #define I8_THREADS (I8_EPI_THREADS + 64)
 #define I8_STAGE_OUT 0
@@ -81,10 +84,17 @@ __device__ __forceinline__ void tc_ld32(uint32_t taddr, uint32_t (&v)[32]) {
 }
 __device__ __forceinline__ void tc_wait_ld() { asm volatile("tcgen05.wait::ld.sync.aligned;" ::: "memory"); }
 
-// K-major, no swizzle: core matrix = 8 rows x 16 bytes (128 contiguous bytes); LBO = byte distance between the two
-// K-adjacent core matrices of one MMA (128), SBO = distance between 8-row groups.  (cute::UMMA::SmemDescriptor bit layout.)
-__device__ __forceinline__ uint64_t umma_desc(uint32_t smem_addr, uint32_t sbo_bytes) {
-  return (uint64_t)((smem_addr & 0x3FFFFu) >> 4) | ((uint64_t)(128u >> 4) << 16) | ((uint64_t)(sbo_bytes >> 4) << 32) | (1ull << 46);
+// K-major, 128-byte swizzle (cute::UMMA::SmemDescriptor bit layout; layout type SWIZZLE_128B = 2): an operand block is
+// [rows][128 bytes of K]; 8-row atoms of 1024 bytes (SBO), inside an atom the 16-byte chunk c of row r sits at chunk c ^ r
+// (Swizzle<3,4,3>).  An MMA consumes K = 32 bytes: its start address is the block base + 32 * (k step inside the block);
+// LBO is not used by swizzled K-major operands (set to 1 as CUTLASS does).  Blocks must be 1024-byte aligned.
+__device__ __forceinline__ uint64_t umma_desc(uint32_t smem_addr) {
+  return (uint64_t)((smem_addr & 0x3FFFFu) >> 4) | (1ull << 16) | ((uint64_t)(1024u >> 4) << 32) | (1ull << 46) | (2ull << 61);
+}
+// byte offset of (row r, K byte k) inside an operand made of [K / 128] consecutive blocks of [nrows x 128 B]
+__host__ __device__ __forceinline__ size_t sw128_offset(int r, int k, int nrows) {
+  return (size_t)(k >> 7) * ((size_t)nrows * 128) + (size_t)(r >> 3) * 1024 + (size_t)(r & 7) * 128 +
+         (size_t)((((k & 127) >> 4) ^ (r & 7)) << 4) + (size_t)(k & 15);
 }
 // cute::UMMA::InstrDescriptor: c_format S32 (2) [4,6), a_format UINT8 (0) [7,10), b_format INT8 (1) [10,13), K-major both,
 // N>>3 [17,23), M>>4 [24,29)
@@ -92,7 +102,7 @@ __device__ __forceinline__ uint64_t umma_desc(uint32_t smem_addr, uint32_t sbo_b
 
 // ---- digit planes of the infectious counts: one pass over I (33 MB at the UK size, 256 chains) ---------------------
 // grid (row tiles, 4): a CTA splits a quarter of a 128-row tile; unit = (row r, 16-byte K chunk kc); a lane group of 8 consecutive rows x 4 chunks writes 512
-// contiguous bytes per plane.  Planes are stored per row tile in the canonical UMMA layout, so the contraction kernel
+// bytes per plane.  Planes are stored per row tile in the 128-byte-swizzled K-major UMMA layout, so the contraction kernel
 // brings a plane into shared memory with ONE bulk copy; flags[rt][a] says whether plane a of the tile holds anything.
 __global__ void __launch_bounds__(I8_EPI_THREADS) seir_i8_split_kernel(long long R, int Mp, int na, const int* __restrict__ Ix,
                                                                        unsigned char* __restrict__ planes, int* __restrict__ flags) {
@@ -121,7 +131,7 @@ __global__ void __launch_bounds__(I8_EPI_THREADS) seir_i8_split_kernel(long long
 #pragma unroll
       for (int q = 0; q < 4; ++q)
         v[b4][q] = in ? __ldg(reinterpret_cast<const int4*>(Ix + gr * Mp + kc * 16 + q * 4)) : make_int4(0, 0, 0, 0);
-      off[b4] = (uint32_t)rgrp * (uint32_t)(K * 8) + (uint32_t)kc * 128u + (uint32_t)(l & 7) * 16u;
+      off[b4] = (uint32_t)sw128_offset(r, kc * 16, I8_BM);
     }
 #pragma unroll
     for (int b4 = 0; b4 < 4; ++b4) {
@@ -152,15 +162,14 @@ __global__ void __launch_bounds__(I8_THREADS, 1) seir_contract_i8_kernel(long lo
   extern __shared__ __align__(1024) unsigned char smem[];
   __shared__ uint64_t full_b[I8_STAGES], empty_b[I8_STAGES], a_ready, a_region_free, t_full[4], t_empty[4];
   __shared__ uint32_t tmem_base_s;
-  const int K = Mp, KH = Mp / 2;                      // one B stage = half a plane: 128 columns x KH bytes
+  const int K = Mp, nkb = Mp / I8_KB;                 // one B stage = one [128 columns x 128 B] block of a plane
   const int plane_a = I8_BM * K;                      // bytes of one A digit plane
-  const int stage_b = I8_BN * KH;
+  const int stage_b = I8_KBLOCK;
   unsigned char* smA = smem;                          // [na][plane_a]
   const size_t a_region = (size_t)na * plane_a > (size_t)I8_STAGE_OUT ? (size_t)na * plane_a : (size_t)I8_STAGE_OUT;
   unsigned char* smB = smem + a_region;               // [I8_STAGES][stage_b]
   const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
   const int ncol_tiles = Mp / I8_BN;
-  const int ksteps_h = KH / 32;                       // MMAs (K = 32 bytes) per half plane
 
   if (tid == 0) {
     for (int s = 0; s < I8_STAGES; ++s) { mbar_init(&full_b[s], 1); mbar_init(&empty_b[s], 1); }
@@ -247,7 +256,7 @@ __global__ void __launch_bounds__(I8_THREADS, 1) seir_contract_i8_kernel(long lo
         const int rb = tile / ncol_tiles, ct = tile - rb * ncol_tiles;
         int issued = 0;
         for (int c = 0; c < I8_NB; ++c)
-          for (int h = 0; h < 2; ++h, ++n) {
+          for (int h = 0; h < nkb; ++h, ++n) {
             if (issued++ == I8_STAGES) {
               // (the first ring-full of Cs stages of this tile is already on its way: it does not depend on the A region)
               // digit planes of the row tile: the A region is free once every epilogue warp has drained the previous tile
@@ -263,10 +272,10 @@ __global__ void __launch_bounds__(I8_THREADS, 1) seir_contract_i8_kernel(long lo
             if (n >= I8_STAGES) mbar_wait(&empty_b[st], ((n / I8_STAGES) - 1) & 1u);
 #ifdef SEIR_I8_EXPERIMENT_NOB  // timing experiment only (wrong results): 16 bytes per stage instead of the half plane
             mbar_expect_tx(&full_b[st], 16u);
-            bulk_load_1d(smB + (size_t)st * stage_b, Bd + (((size_t)c * ncol_tiles + ct) * 2 + h) * stage_b, 16u, &full_b[st]);
+            bulk_load_1d(smB + (size_t)st * stage_b, Bd + (((size_t)c * ncol_tiles + ct) * nkb + h) * stage_b, 16u, &full_b[st]);
 #else
             mbar_expect_tx(&full_b[st], (unsigned)stage_b);
-            bulk_load_1d(smB + (size_t)st * stage_b, Bd + (((size_t)c * ncol_tiles + ct) * 2 + h) * stage_b, (unsigned)stage_b, &full_b[st]);
+            bulk_load_1d(smB + (size_t)st * stage_b, Bd + (((size_t)c * ncol_tiles + ct) * nkb + h) * stage_b, (unsigned)stage_b, &full_b[st]);
 #endif
           }
       }
@@ -276,7 +285,7 @@ __global__ void __launch_bounds__(I8_THREADS, 1) seir_contract_i8_kernel(long lo
     uint32_t n = 0, ph_aready = 0;
     uint32_t hosted[4] = {0, 0, 0, 0};  // groups started in each accumulator slot so far (over all tiles)
     uint64_t a_desc_plane[3];
-    for (int a = 0; a < 3; ++a) a_desc_plane[a] = umma_desc(smem_u32(smA + (size_t)(a < na ? a : 0) * plane_a), (uint32_t)K * 8u);
+    for (int a = 0; a < 3; ++a) a_desc_plane[a] = umma_desc(smem_u32(smA + (size_t)(a < na ? a : 0) * plane_a));
     int itm = 0;
     for (int tile = blockIdx.x; tile < ntiles; tile += gridDim.x, ++itm) {
       if (itm == 1) TM(30);
@@ -288,13 +297,13 @@ __global__ void __launch_bounds__(I8_THREADS, 1) seir_contract_i8_kernel(long lo
       for (int a = 1; a < na; ++a)
         if (__ldg(flags + (tile / ncol_tiles) * 4 + a)) na_t = a + 1;
       for (int c = 0; c < I8_NB; ++c) {
-        for (int h = 0; h < 2; ++h, ++n) {
+        for (int h = 0; h < nkb; ++h, ++n) {
           const int st = n % I8_STAGES;
-          if (itm == 1 && c == 2) TM(50 + 3 * h);
+          if (itm == 1 && c == 2 && h < 2) TM(50 + 3 * h);
           mbar_wait(&full_b[st], (n / I8_STAGES) & 1u);
           tc_fence_after();
-          if (itm == 1 && c == 2) TM(51 + 3 * h);
-          const uint64_t b_desc0 = umma_desc(smem_u32(smB + (size_t)st * stage_b), (uint32_t)KH * 8u);
+          if (itm == 1 && c == 2 && h < 2) TM(51 + 3 * h);
+          const uint64_t b_desc0 = umma_desc(smem_u32(smB + (size_t)st * stage_b));
           for (int a = 0; a < na_t; ++a) {
             const int s = a - c, slot = s & 3;
             const bool first_pair = (c == 0 || a == 0);  // group s receives its first digit pair in this plane
@@ -305,19 +314,19 @@ __global__ void __launch_bounds__(I8_THREADS, 1) seir_contract_i8_kernel(long lo
               }
               hosted[slot] += 1;
             }
-            // a K step of 32 bytes advances both start addresses by 256 bytes = 16 descriptor units (low field, no carry:
-            // shared-memory addresses stay below 2^18)
-            const uint64_t a_desc0 = a_desc_plane[a] + (uint64_t)(h * ksteps_h) * 16u;
+            // K block h of plane a; a K step of 32 bytes advances both start addresses by 2 descriptor units (low field, no
+            // carry: shared-memory addresses stay below 2^18)
+            const uint64_t a_desc0 = a_desc_plane[a] + (uint64_t)h * (I8_KBLOCK >> 4);
             const uint32_t d_addr = tmem_base + (uint32_t)(slot * I8_BN);
             tc_mma_i8(d_addr, a_desc0, b_desc0, I8_IDESC, (first_pair && h == 0) ? 0u : 1u);
-#pragma unroll 5
-            for (int kk = 1; kk < ksteps_h; ++kk) tc_mma_i8(d_addr, a_desc0 + (uint64_t)kk * 16u, b_desc0 + (uint64_t)kk * 16u, I8_IDESC, 1u);
+#pragma unroll
+            for (int kk = 1; kk < I8_KB / 32; ++kk) tc_mma_i8(d_addr, a_desc0 + (uint64_t)kk * 2u, b_desc0 + (uint64_t)kk * 2u, I8_IDESC, 1u);
 #ifdef SEIR_I8_EXPERIMENT_REP  // timing experiment only (wrong results): extra MMAs per step to separate per-MMA from per-stage cost
             for (int rep = 0; rep < SEIR_I8_EXPERIMENT_REP; ++rep)
-              for (int kk = 0; kk < ksteps_h; ++kk) tc_mma_i8(d_addr, a_desc0 + (uint64_t)kk * 16u, b_desc0 + (uint64_t)kk * 16u, I8_IDESC, 1u);
+              for (int kk = 0; kk < I8_KB / 32; ++kk) tc_mma_i8(d_addr, a_desc0 + (uint64_t)kk * 2u, b_desc0 + (uint64_t)kk * 2u, I8_IDESC, 1u);
 #endif
           }
-          if (itm == 1 && c == 2) TM(52 + 3 * h);
+          if (itm == 1 && c == 2 && h < 2) TM(52 + 3 * h);
           tc_commit(&empty_b[st]);  // the stage is free once these MMAs have read it
         }
         // plane c done: group na-1-c has all its pairs; after the last plane every remaining group has
@@ -342,9 +351,9 @@ int seir_contract_i8_setup(seir_model* m, const double* h_cs /*[Mp][Mp], Cs[j][i
   int na = 1;
   while (na < 6 && ldexp(1.0, 8 * na) <= max_population) ++na;  // infectious counts never exceed the population
   if (na > 3) return 1;
-  const int KH = Mp / 2, nct = Mp / I8_BN;
-  const size_t stage_b = (size_t)I8_BN * KH;
-  std::vector<signed char> bd((size_t)I8_NB * nct * 2 * stage_b, 0);
+  const int nct = Mp / I8_BN;
+  const size_t plane_b = (size_t)I8_BN * Mp;  // one plane of one column tile: [Mp / 128] blocks of [128 columns x 128 B]
+  std::vector<signed char> bd((size_t)I8_NB * nct * plane_b, 0);
   std::vector<double> scale(Mp, 1.0);
   for (int i = 0; i < Mp; ++i) {
     double cmax = 0.0;
@@ -358,11 +367,10 @@ int seir_contract_i8_setup(seir_model* m, const double* h_cs /*[Mp][Mp], Cs[j][i
     const int ct = i / I8_BN, nn = i % I8_BN;
     for (int j = 0; j < Mp; ++j) {
       long long W = llrint(ldexp(h_cs[(size_t)j * Mp + i], 8 * I8_NB - e));  // round(Cs 2^(48-e)), |W| <= 2^46
-      const int h = j / KH, kl = j % KH;
-      const size_t off = (size_t)(nn / 8) * ((size_t)KH * 8) + (size_t)(kl / 16) * 128 + (size_t)(nn % 8) * 16 + (size_t)(kl % 16);
+      const size_t off = sw128_offset(nn, j, I8_BN);
       for (int c = I8_NB - 1; c >= 0; --c) {  // balanced digits, least significant (plane nb-1) first
         long long d = ((W + 128) & 255) - 128;  // in [-128, 127], congruent to W mod 256
-        bd[(((size_t)c * nct + ct) * 2 + h) * stage_b + off] = (signed char)d;
+        bd[((size_t)c * nct + ct) * plane_b + off] = (signed char)d;
         W = (W - d) / 256;                      // exact
       }
       // (W is now 0: |top digit| <= 64 because |Cs / 2^e| < 0.25)
@@ -382,7 +390,7 @@ int seir_launch_contract_i8(seir_chains* c, cudaStream_t s) {
   const int ntiles = (int)((R + I8_BM - 1) / I8_BM) * (m->Mp / I8_BN);
   size_t a_region = (size_t)m->i8_na * I8_BM * m->Mp;
   if (a_region < (size_t)I8_STAGE_OUT) a_region = I8_STAGE_OUT;
-  const size_t smem = a_region + (size_t)I8_STAGES * I8_BN * (m->Mp / 2);
+  const size_t smem = a_region + (size_t)I8_STAGES * I8_KBLOCK + 1024;  // (+ slack to align the dynamic base to 1024 bytes)
   static int sms = 0;
   static size_t attr = 0;
   if (!sms) {
