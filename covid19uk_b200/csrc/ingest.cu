@@ -88,6 +88,8 @@ __global__ void __launch_bounds__(256) seir_ingest_kernel(int M, int T, int Mp, 
   extern __shared__ int smem_i[];
   int* ev = smem_i;                    // [32][STRIDE]
   int* segsum = smem_i + 32 * STRIDE;  // [8][3][32]
+  int* dayY = segsum + 8 * 3 * 32;     // [TC] per-day sums over the CTA's 32 metapopulations: y_ir
+  int* dayR = dayY + TC;               // [TC]                                            : I - y_ir
 
   const int b = b0 + blockIdx.y, m0 = blockIdx.x * 32;
   const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
@@ -97,6 +99,8 @@ __global__ void __launch_bounds__(256) seir_ingest_kernel(int M, int T, int Mp, 
   int bad = 0;
   long long accYei = 0, accEres = 0;
   int nz0 = 0, nz1 = 0;  // days with S->E / E->I events of this lane's metapopulation, within this warp's segments
+  // 16-byte loads need even row lengths and an aligned base (chunk starts t0 are multiples of TC, which is even)
+  const bool vec2 = ((T * 3) % 2 == 0) && ((reinterpret_cast<uintptr_t>(events) & 15) == 0);
 
   for (int t0 = 0; t0 < T; t0 += TC) {
     const int tc = min(TC, T - t0);
@@ -104,6 +108,20 @@ __global__ void __launch_bounds__(256) seir_ingest_kernel(int M, int T, int Mp, 
     for (int r = warp; r < 32; r += 8) {
       const int mm = m0 + r;
       const EV* src = events + (((size_t)b * M + mm) * T + t0) * 3;
+      if (sizeof(EV) == sizeof(double) && vec2) {  // two counts per 16-byte load (row starts are 16-byte aligned: T even)
+        for (int k2 = lane; 2 * k2 < tc * 3; k2 += 32) {
+          int i0 = 0, i1 = 0;
+          if (mm < M) {
+            const double2 v = __ldg(reinterpret_cast<const double2*>(src) + k2);
+            i0 = __double2int_rn(v.x);
+            i1 = __double2int_rn(v.y);
+            if ((double)i0 != v.x || (double)i1 != v.y || (i0 | i1) < 0) bad |= 1;
+          }
+          ev[r * STRIDE + 2 * k2] = i0;
+          ev[r * STRIDE + 2 * k2 + 1] = i1;
+        }
+        continue;
+      }
       for (int k = lane; k < tc * 3; k += 32) {
         int iv = 0;
         if (mm < M) {
@@ -156,14 +174,16 @@ __global__ void __launch_bounds__(256) seir_ingest_kernel(int M, int T, int Mp, 
       nz1 += y1 > 0;
       const int ry = __reduce_add_sync(0xffffffffu, y2);      // padding lanes hold zeros
       const int rr = __reduce_add_sync(0xffffffffu, I - y2);
-      if (lane == 0) {
-        atomicAdd(reinterpret_cast<unsigned long long*>(Yir + (size_t)b * T + t0 + s), (unsigned long long)(long long)ry);
-        atomicAdd(reinterpret_cast<unsigned long long*>(Rir + (size_t)b * T + t0 + s), (unsigned long long)(long long)rr);
-      }
+      if (lane == 0) { dayY[s] = ry; dayR[s] = rr; }  // (a day belongs to exactly one warp of the CTA)
       c0 += y0; c1 += y1; c2 += y2;
     }
     carry0 += tot0; carry1 += tot1; carry2 += tot2;
     __syncthreads();
+    // the CTA's contribution to the per-day I->R statistics: one pair of atomics per day, issued in parallel
+    for (int s = threadIdx.x; s < tc; s += 256) {
+      atomicAdd(reinterpret_cast<unsigned long long*>(Yir + (size_t)b * T + t0 + s), (unsigned long long)(long long)dayY[s]);
+      atomicAdd(reinterpret_cast<unsigned long long*>(Rir + (size_t)b * T + t0 + s), (unsigned long long)(long long)dayR[s]);
+    }
   }
 #pragma unroll
   for (int o = 16; o > 0; o >>= 1) {
@@ -183,7 +203,7 @@ __global__ void __launch_bounds__(256) seir_ingest_kernel(int M, int T, int Mp, 
 template <int TC, typename EV>
 static int launch_ingest_tc(seir_chains* c, const EV* d_events, int b0, int nb, cudaStream_t s) {
   const seir_model* m = c->model;
-  const size_t smem = sizeof(int) * (32 * (TC * 3 + 1) + 8 * 3 * 32);
+  const size_t smem = sizeof(int) * (32 * (TC * 3 + 1) + 8 * 3 * 32 + 2 * TC);
   static bool attr_set = false;
   if (!attr_set) {
     SEIR_CUDA(cudaFuncSetAttribute(seir_ingest_kernel<TC, EV>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
