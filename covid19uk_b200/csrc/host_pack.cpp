@@ -8,6 +8,9 @@
 #include <stdint.h>
 #include <stddef.h>
 #include <stdlib.h>
+#if defined(__x86_64__)
+#include <immintrin.h>
+#endif
 
 #include <atomic>
 #include <condition_variable>
@@ -18,15 +21,45 @@
 namespace {
 
 // exact double -> uint16 narrowing of n values; returns false if any value is not representable
-__attribute__((target_clones("avx512f", "avx2", "default"))) bool pack_block(const double* __restrict__ src, uint16_t* __restrict__ dst, size_t n) {
+bool pack_block_scalar(const double* __restrict__ src, uint16_t* __restrict__ dst, size_t n) {
   int bad = 0;
   for (size_t i = 0; i < n; ++i) {
     const double v = src[i];
-    const int32_t k = (int32_t)v;  // (vectorises: cvttpd2dq; out-of-range / NaN give INT_MIN => caught below)
+    const int32_t k = (int32_t)v;  // out-of-range / NaN give INT_MIN => caught below
     bad |= (k < 0) | (k > 65535) | ((double)k != v);
     dst[i] = (uint16_t)k;
   }
   return bad == 0;
+}
+
+#if defined(__x86_64__)
+// AVX2: 8 counts per iteration -- truncate to int32, convert back and compare (exactness), check the 16-bit range, pack with
+// unsigned saturation.  (The auto-vectorised scalar loop ran at ~4.5 GB/s per thread; this one is bound by the memory read.)
+__attribute__((target("avx2"))) bool pack_block_avx2(const double* __restrict__ src, uint16_t* __restrict__ dst, size_t n) {
+  __m256d okacc = _mm256_castsi256_pd(_mm256_set1_epi64x(-1));
+  __m128i hiacc = _mm_setzero_si128();
+  size_t i = 0;
+  for (; i + 8 <= n; i += 8) {
+    _mm_prefetch(reinterpret_cast<const char*>(src + i + 128), _MM_HINT_NTA);
+    const __m256d a = _mm256_loadu_pd(src + i), b = _mm256_loadu_pd(src + i + 4);
+    const __m128i ia = _mm256_cvttpd_epi32(a), ib = _mm256_cvttpd_epi32(b);
+    okacc = _mm256_and_pd(okacc, _mm256_and_pd(_mm256_cmp_pd(_mm256_cvtepi32_pd(ia), a, _CMP_EQ_OQ),
+                                               _mm256_cmp_pd(_mm256_cvtepi32_pd(ib), b, _CMP_EQ_OQ)));
+    hiacc = _mm_or_si128(hiacc, _mm_or_si128(_mm_srli_epi32(ia, 16), _mm_srli_epi32(ib, 16)));  // negative or > 65535 => non-zero
+    _mm_storeu_si128(reinterpret_cast<__m128i*>(dst + i), _mm_packus_epi32(ia, ib));
+  }
+  bool ok = _mm256_movemask_pd(okacc) == 0xF && _mm_testz_si128(hiacc, hiacc);
+  if (i < n) ok = pack_block_scalar(src + i, dst + i, n - i) && ok;
+  return ok;
+}
+#endif
+
+bool pack_block(const double* __restrict__ src, uint16_t* __restrict__ dst, size_t n) {
+#if defined(__x86_64__)
+  static const bool have_avx2 = __builtin_cpu_supports("avx2");
+  if (have_avx2) return pack_block_avx2(src, dst, n);
+#endif
+  return pack_block_scalar(src, dst, n);
 }
 
 struct Pool {
