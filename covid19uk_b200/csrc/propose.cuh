@@ -8,7 +8,7 @@
 //           t   ~ uniform over the days of m with >= 1 target event
 //           d   ~ uniform on +-{1..dmax}
 //           x*  ~ UniformInteger[0, max_events(m, t, d)]
-//   occult: with prob 1/2 (and only if the window holds target events) DELETE:
+//   occult: with prob 1/2 DELETE (the null proposal if the window holds no target event):
 //               m ~ uniform over metapopulations with events in the window, t ~ uniform over such days of m,
 //               x* ~ UniformInteger[0, min(nmax, events[m,t], bound)]
 //           else ADD: m ~ U{0..M-1}, t ~ U{t0..t1-1}, x* ~ U{0..nmax}
@@ -93,9 +93,15 @@ __device__ __forceinline__ void sample_metapops(const chain_view& g, const seir_
     const bool coin = (r[2] & 1u) != 0;
     uint32_t q[4];
     seir_philox(seed, chain, ctr, 0x4Fu, 0u, q);
-    if (coin && H > 0) {
-      m0 = pick_hot((int)rand_below(q[0], q[1], (uint32_t)H), -1);
-      sg = -1;
+    if (coin) {  // delete; with no target event in the window this is the null proposal (the coin stays fair: an add
+                 // fallback would be chosen with probability 1 while the acceptance ratio assumes 1/2 on both sides)
+      if (H > 0) {
+        m0 = pick_hot((int)rand_below(q[0], q[1], (uint32_t)H), -1);
+        sg = -1;
+      } else {
+        __syncwarp();
+        if (lane == 0) pr[0] = -1;  // invalid record: rejected by the update step
+      }
     } else {
       m0 = (int)rand_below(q[0], q[1], (uint32_t)M);
       sg = 1;

@@ -594,9 +594,15 @@ def sample_move_proposal(rng, events, initial_state, topology, dmax, mmax, nmax)
 
 
 def sample_occult_proposal(rng, events, offset, topology, t_range, nmax):
+    """(is_add, m, t, x_star).  The add / delete coin is ALWAYS fair: a delete drawn while the window holds no target event is
+    the null proposal (x_star = 0; its q_del is -inf, so the update rejects it).  Falling back to an add instead would make
+    the add probability 1 in such states while the acceptance ratio assumes 1/2 on both sides -- the stationarity test on an
+    enumerable model (tests/test_gpu_stationarity.py) shows the resulting bias against event-free states."""
     window = events[:, t_range[0] : t_range[1], topology.target] > 0
-    do_delete = (rng.random() < 0.5) and window.any()
+    do_delete = rng.random() < 0.5
     M = events.shape[0]
+    if do_delete and not window.any():
+        return (False, 0, int(t_range[0]), 0)
     if not do_delete:
         return (True, int(rng.integers(0, M)), int(rng.integers(t_range[0], t_range[1])), int(rng.integers(0, nmax + 1)))
     hot = np.flatnonzero(np.any(window, axis=1))
