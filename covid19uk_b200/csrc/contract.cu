@@ -104,22 +104,35 @@ __global__ void __launch_bounds__(128) seir_contract_kernel(long long R, int Mp,
   }
 }
 
-int seir_launch_contract(seir_chains* c, cudaStream_t s) {
-  const seir_model* m = c->model;
+static bool contract_uses_i8(const seir_model* m) {
   static int use_i8 = -1;
   if (use_i8 < 0) {
     const char* e = getenv("SEIR_CONTRACT_I8");  // 0: always the FP64 DMMA kernel below; default: the exact int8 tcgen05 kernel
     use_i8 = e ? atoi(e) : 1;                    // (contract_i8.cu) wherever it applies (Mp a multiple of 128, <= 384)
   }
-  if (use_i8 && m->i8_na > 0) return seir_launch_contract_i8(c, s);
-  return seir_launch_contract_f64(c, s);
+  return use_i8 && m->i8_na > 0;
 }
 
-int seir_launch_contract_f64(seir_chains* c, cudaStream_t s) {
+int seir_launch_contract(seir_chains* c, cudaStream_t s) { return seir_launch_contract_range(c, s, seir_all(c)); }
+
+// can the contraction run on the rows of chains [b0, ...) alone?  (the int8 kernel works on 128-row tiles)
+bool seir_contract_range_ok(const seir_chains* c, int b0) {
+  return !contract_uses_i8(c->model) || ((long long)b0 * c->model->T) % 128 == 0;
+}
+
+int seir_launch_contract_range(seir_chains* c, cudaStream_t s, seir_range r) {
+  if (contract_uses_i8(c->model)) return seir_launch_contract_i8_range(c, s, r);
+  return seir_launch_contract_f64_range(c, s, r);
+}
+
+int seir_launch_contract_f64(seir_chains* c, cudaStream_t s) { return seir_launch_contract_f64_range(c, s, seir_all(c)); }
+
+int seir_launch_contract_f64_range(seir_chains* c, cudaStream_t s, seir_range r) {
   const seir_model* m = c->model;
-  const long long R = (long long)c->B * m->T;
+  const long long R = (long long)r.nb * m->T;
+  const size_t cell0 = (size_t)r.b0 * m->T * m->Mp;
   dim3 grid(m->Mp / CT_BN, (unsigned)((R + CT_BM - 1) / CT_BM));
-  seir_contract_kernel<<<grid, 128, 0, s>>>(R, m->Mp, c->d_I, m->d_cs, c->d_Bc);
+  seir_contract_kernel<<<grid, 128, 0, s>>>(R, m->Mp, c->d_I + cell0, m->d_cs, c->d_Bc + cell0);
   seir_count_launch(1);
   return seir_cuda_check(cudaGetLastError(), "seir_contract_kernel");
 }

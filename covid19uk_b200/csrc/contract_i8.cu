@@ -384,9 +384,13 @@ int seir_contract_i8_setup(seir_model* m, const double* h_cs /*[Mp][Mp], Cs[j][i
   return 0;
 }
 
-int seir_launch_contract_i8(seir_chains* c, cudaStream_t s) {
+int seir_launch_contract_i8(seir_chains* c, cudaStream_t s) { return seir_launch_contract_i8_range(c, s, seir_all(c)); }
+
+// rows of chains [r.b0, r.b0 + r.nb): the first row must start a 128-row tile (callers check seir_contract_range_ok)
+int seir_launch_contract_i8_range(seir_chains* c, cudaStream_t s, seir_range r) {
   const seir_model* m = c->model;
-  const long long R = (long long)c->B * m->T;
+  const long long Rall = (long long)c->B * m->T, R = (long long)r.nb * m->T, row0 = (long long)r.b0 * m->T;
+  if (row0 % I8_BM != 0) return seir_set_error(SEIR_ERR_BAD_ARG, "seir_launch_contract_i8_range: chain range does not start a row tile");
   const int ntiles = (int)((R + I8_BM - 1) / I8_BM) * (m->Mp / I8_BN);
   size_t a_region = (size_t)m->i8_na * I8_BM * m->Mp;
   if (a_region < (size_t)I8_STAGE_OUT) a_region = I8_STAGE_OUT;
@@ -402,16 +406,19 @@ int seir_launch_contract_i8(seir_chains* c, cudaStream_t s) {
     SEIR_CUDA(cudaFuncSetAttribute(seir_contract_i8_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
     attr = smem;
   }
-  const int nrt = (int)((R + I8_BM - 1) / I8_BM);
+  const int nrt_all = (int)((Rall + I8_BM - 1) / I8_BM), nrt = (int)((R + I8_BM - 1) / I8_BM), rt0 = (int)(row0 / I8_BM);
   if (!c->d_i8_planes) {
-    SEIR_CUDA(cudaMalloc(reinterpret_cast<void**>(&c->d_i8_planes), (size_t)nrt * m->i8_na * I8_BM * m->Mp));
-    SEIR_CUDA(cudaMalloc(reinterpret_cast<void**>(&c->d_i8_flags), sizeof(int) * 4 * (size_t)nrt));
-    c->bytes += (int64_t)((size_t)nrt * m->i8_na * I8_BM * m->Mp + sizeof(int) * 4 * (size_t)nrt);
+    SEIR_CUDA(cudaMalloc(reinterpret_cast<void**>(&c->d_i8_planes), (size_t)nrt_all * m->i8_na * I8_BM * m->Mp));
+    SEIR_CUDA(cudaMalloc(reinterpret_cast<void**>(&c->d_i8_flags), sizeof(int) * 4 * (size_t)nrt_all));
+    c->bytes += (int64_t)((size_t)nrt_all * m->i8_na * I8_BM * m->Mp + sizeof(int) * 4 * (size_t)nrt_all);
   }
-  SEIR_CUDA(cudaMemsetAsync(c->d_i8_flags, 0, sizeof(int) * 4 * (size_t)nrt, s));
-  seir_i8_split_kernel<<<dim3(nrt, 4), I8_EPI_THREADS, 0, s>>>(R, m->Mp, m->i8_na, c->d_I, c->d_i8_planes, c->d_i8_flags);
-  seir_contract_i8_kernel<<<ntiles < sms ? ntiles : sms, I8_THREADS, smem, s>>>(R, m->Mp, m->i8_na, ntiles, c->d_i8_planes, c->d_i8_flags,
-                                                                                m->d_cs_i8, m->d_cs_scale, c->d_Bc);
+  unsigned char* planes = c->d_i8_planes + (size_t)rt0 * m->i8_na * I8_BM * m->Mp;
+  int* flags = c->d_i8_flags + 4 * (size_t)rt0;
+  const size_t cell0 = (size_t)row0 * m->Mp;
+  SEIR_CUDA(cudaMemsetAsync(flags, 0, sizeof(int) * 4 * (size_t)nrt, s));
+  seir_i8_split_kernel<<<dim3(nrt, 4), I8_EPI_THREADS, 0, s>>>(R, m->Mp, m->i8_na, c->d_I + cell0, planes, flags);
+  seir_contract_i8_kernel<<<ntiles < sms ? ntiles : sms, I8_THREADS, smem, s>>>(R, m->Mp, m->i8_na, ntiles, planes, flags, m->d_cs_i8,
+                                                                                m->d_cs_scale, c->d_Bc + cell0);
   seir_count_launch(2);
   return seir_cuda_check(cudaGetLastError(), "seir_contract_i8_kernel");
 }

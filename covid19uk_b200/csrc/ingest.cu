@@ -408,9 +408,10 @@ __global__ void __launch_bounds__(256) seir_coef_reduce_kernel(int nper, const d
 }
 
 template <int CT, int MINB>
-static int launch_coef_tma(seir_chains* c, int tabn, cudaStream_t s, int sms) {
+static int launch_coef_tma(seir_chains* c, int tabn, cudaStream_t s, int sms, seir_range r) {
   const seir_model* m = c->model;
-  const int slabs = c->B * m->T;
+  const int slabs = r.nb * m->T;
+  const size_t cell0 = (size_t)r.b0 * m->T * m->Mp;  // (a chain range starts on day 0: the kernel's slab -> day map holds)
   const size_t table = sizeof(double) * tabn, budget = (size_t)(227 * 1024) / MINB - 1024 - table;
   int nst = COEF_STAGES;
   int NB = (int)(budget / nst / ((size_t)m->Mp * 20));
@@ -427,13 +428,15 @@ static int launch_coef_tma(seir_chains* c, int tabn, cudaStream_t s, int sms) {
     attr = smem;
   }
   const int nbatch = (slabs + NB - 1) / NB, grid = sms * MINB;
-  seir_coef_tma_kernel<CT, MINB><<<nbatch < grid ? nbatch : grid, CT + 32, smem, s>>>(m->M, m->T, m->Mp, slabs, NB, nst, tabn, m->d_init,
-                                                                                     m->d_lgtab, c->d_yse, c->d_yei, c->d_yir, c->d_S,
-                                                                                     c->d_E, c->d_I, c->d_llc_part);
+  seir_coef_tma_kernel<CT, MINB><<<nbatch < grid ? nbatch : grid, CT + 32, smem, s>>>(
+      m->M, m->T, m->Mp, slabs, NB, nst, tabn, m->d_init, m->d_lgtab, c->d_yse + cell0, c->d_yei + cell0, c->d_yir + cell0, c->d_S + cell0,
+      c->d_E + cell0, c->d_I + cell0, c->d_llc_part + (size_t)r.b0 * m->T * (m->Mp / 32));
   return 0;
 }
 
-int seir_launch_coef(seir_chains* c, cudaStream_t s) {
+int seir_launch_coef(seir_chains* c, cudaStream_t s) { return seir_launch_coef_range(c, s, seir_all(c)); }
+
+int seir_launch_coef_range(seir_chains* c, cudaStream_t s, seir_range r) {
   const seir_model* m = c->model;
   static int sms = 0, variant = -1;
   if (!sms) {
@@ -448,20 +451,22 @@ int seir_launch_coef(seir_chains* c, cudaStream_t s) {
     const char* e = getenv("SEIR_COEF_VARIANT");
     variant = e ? atoi(e) : 2;
   }
-  const int slabs = c->B * m->T;
+  const int slabs = r.nb * m->T;
   int nper = m->T * (m->Mp / 32), rc = 1;
-  if (variant == 1) rc = launch_coef_tma<768, 1>(c, SEIR_LGTAB_BIG, s, sms);
-  if (variant == 2) rc = launch_coef_tma<992, 1>(c, SEIR_LGTAB_BIG, s, sms);
-  if (variant == 3) rc = launch_coef_tma<608, 2>(c, SEIR_LGTAB_BIG / 2, s, sms);
+  if (variant == 1) rc = launch_coef_tma<768, 1>(c, SEIR_LGTAB_BIG, s, sms, r);
+  if (variant == 2) rc = launch_coef_tma<992, 1>(c, SEIR_LGTAB_BIG, s, sms, r);
+  if (variant == 3) rc = launch_coef_tma<608, 2>(c, SEIR_LGTAB_BIG / 2, s, sms, r);
   if (rc < 0) return rc;
   if (rc != 0) {
     int grid = (slabs + 31) / 32;
     if (grid > sms) grid = sms;
     nper = m->T;
-    seir_coef_kernel<<<grid, 1024, sizeof(double) * SEIR_LGTAB_BIG, s>>>(m->M, m->T, m->Mp, slabs, m->d_init, m->d_lgtab, c->d_yse, c->d_yei,
-                                                                         c->d_yir, c->d_S, c->d_E, c->d_I, c->d_llc_part);
+    const size_t cell0 = (size_t)r.b0 * m->T * m->Mp;
+    seir_coef_kernel<<<grid, 1024, sizeof(double) * SEIR_LGTAB_BIG, s>>>(m->M, m->T, m->Mp, slabs, m->d_init, m->d_lgtab, c->d_yse + cell0,
+                                                                         c->d_yei + cell0, c->d_yir + cell0, c->d_S + cell0, c->d_E + cell0,
+                                                                         c->d_I + cell0, c->d_llc_part + (size_t)r.b0 * nper);
   }
-  seir_coef_reduce_kernel<<<c->B, 256, 0, s>>>(nper, c->d_llc_part, c->d_llc_sum);
+  seir_coef_reduce_kernel<<<r.nb, 256, 0, s>>>(nper, c->d_llc_part + (size_t)r.b0 * nper, c->d_llc_sum + r.b0);
   c->nllc = 1;
   seir_count_launch(2);
   return seir_cuda_check(cudaGetLastError(), "seir_coef_kernel");

@@ -510,22 +510,28 @@ int seir_launch_loglik(seir_chains* c, bool grad, cudaStream_t s, seir_range r) 
 // ------------------------------------------------------------------------------------------------
 // finalize: one CTA per chain (tf_finalize, theta_fin.cuh).
 // ------------------------------------------------------------------------------------------------
-__global__ void __launch_bounds__(TF_THREADS) seir_finalize_kernel(tf_model md, tf_chains ch, const double* __restrict__ theta, int parts,
-                                                                   double* __restrict__ out, double* __restrict__ grad) {
+__global__ void __launch_bounds__(TF_THREADS) seir_finalize_kernel(tf_model md, tf_chains ch, int b0, const double* __restrict__ theta,
+                                                                   int parts, double* __restrict__ out, double* __restrict__ grad) {
   extern __shared__ double dyn[];
   __shared__ tf_shared sh;
-  const int b = blockIdx.x;
+  const int b = b0 + blockIdx.x;
   const double v = tf_finalize(md, ch, b, theta + (size_t)b * md.P, parts, grad ? grad + (size_t)b * md.P : nullptr, dyn, sh);
   if (threadIdx.x == 0) out[b] = v;
 }
 
 int seir_launch_finalize(seir_chains* c, const double* d_theta, int kind, int parts, double* d_out, double* d_grad,
                          cudaStream_t s) {
+  return seir_launch_finalize_range(c, d_theta, kind, parts, d_out, d_grad, s, seir_all(c));
+}
+
+// chains [r.b0, r.b0 + r.nb); d_theta / d_out / d_grad are the arrays of ALL chains
+int seir_launch_finalize_range(seir_chains* c, const double* d_theta, int kind, int parts, double* d_out, double* d_grad, cudaStream_t s,
+                               seir_range r) {
   (void)kind;
   const seir_model* m = c->model;
   const size_t smem = seir_tf_smem(m);
   if (smem > 48 * 1024) SEIR_CUDA(cudaFuncSetAttribute(seir_finalize_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
-  seir_finalize_kernel<<<c->B, TF_THREADS, smem, s>>>(seir_tf_model(m), seir_tf_chains(c), d_theta, parts, d_out, d_grad);
+  seir_finalize_kernel<<<r.nb, TF_THREADS, smem, s>>>(seir_tf_model(m), seir_tf_chains(c), r.b0, d_theta, parts, d_out, d_grad);
   seir_count_launch(1);
   return seir_cuda_check(cudaGetLastError(), "seir_finalize_kernel");
 }

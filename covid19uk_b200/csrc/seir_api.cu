@@ -9,6 +9,8 @@
 #include <new>
 #include <vector>
 
+#include <chrono>
+
 #include "seir_internal.cuh"
 
 static thread_local char g_err[512] = "";
@@ -252,6 +254,11 @@ void seir_chains_destroy(seir_chains* c) {
   cudaFree(c->d_stage_out); cudaFree(c->d_stage_u16);
   if (c->h_stage_u16) cudaFreeHost(c->h_stage_u16);
   if (c->copy_stream) cudaStreamDestroy(c->copy_stream);
+  if (c->tail_stream) {
+    cudaStreamDestroy(c->tail_stream);
+    cudaEventDestroy(c->tail_fork);
+    cudaEventDestroy(c->tail_join);
+  }
   if (c->stage_ev) {
     for (int k = 0; k < c->stage_nchunks; ++k) cudaEventDestroy(c->stage_ev[k]);
     delete[] c->stage_ev;
@@ -323,13 +330,24 @@ int seir_log_prob(seir_chains* c, const double* d_events, const double* d_theta,
   return seir_log_prob_cached(c, d_theta, kind, parts, d_out, stream);
 }
 
+// events-wide kernels (coefficients, contraction) + the theta-dependent half for chains [r.b0, r.b0 + r.nb)
+static int host_part(seir_chains* c, int kind, int parts, cudaStream_t s, seir_range r) {
+  if (parts & SEIR_PART_SEIR) {
+    SEIR_TRY(seir_launch_coef_range(c, s, r));
+    SEIR_TRY(seir_launch_contract_range(c, s, r));
+  }
+  SEIR_TRY(seir_launch_theta_prep(c, c->d_stage_theta, kind, parts, s, r));
+  if (parts & SEIR_PART_SEIR) SEIR_TRY(seir_launch_loglik(c, false, s, r));
+  return seir_launch_finalize_range(c, c->d_stage_theta, kind, parts, c->d_stage_out, nullptr, s, r);
+}
+
 // host packer (host_pack.cpp)
 int seir_pack_begin(const double* src, unsigned short* dst, size_t chunk_elems, size_t total_elems, int nchunks);
 int seir_pack_poll(int chunk, int jobs_per_chunk);
 int seir_pack_claim_raw(int chunk);
 int seir_pack_owner(int chunk);
 
-#define SEIR_HOST_CHUNKS 16
+#define SEIR_HOST_CHUNKS 32
 
 // Host-buffer entry point.  The event tensor is the whole transfer (8 B per count, 198 MB at the UK size with 256
 // chains, vs 1.2 ms of device work), so the chains are cut into chunks that travel two ways at once:
@@ -353,22 +371,66 @@ int seir_log_prob_host(seir_chains* c, const double* h_events, const double* h_t
     SEIR_TRY(dev_alloc(&c->d_stage_u16, ne, &c->bytes));
     SEIR_CUDA(cudaHostAlloc(reinterpret_cast<void**>(&c->h_stage_u16), ne * sizeof(unsigned short), cudaHostAllocDefault));
     SEIR_CUDA(cudaStreamCreateWithFlags(&c->copy_stream, cudaStreamNonBlocking));
+    SEIR_CUDA(cudaStreamCreateWithFlags(&c->tail_stream, cudaStreamNonBlocking));
+    SEIR_CUDA(cudaEventCreateWithFlags(&c->tail_fork, cudaEventDisableTiming));
+    SEIR_CUDA(cudaEventCreateWithFlags(&c->tail_join, cudaEventDisableTiming));
     c->stage_nchunks = B < SEIR_HOST_CHUNKS ? B : SEIR_HOST_CHUNKS;
     c->stage_ev = new cudaEvent_t[c->stage_nchunks];
     for (int k = 0; k < c->stage_nchunks; ++k) SEIR_CUDA(cudaEventCreateWithFlags(&c->stage_ev[k], cudaEventDisableTiming));
+    // host->device cost of a copy from pinned memory on this link: fixed part (us) + bytes / rate (bytes per us), from
+    // a 1 MiB and a 16 MiB copy; used for the float64 / uint16 split below
+    {
+      cudaEvent_t e0, e1;
+      SEIR_CUDA(cudaEventCreate(&e0));
+      SEIR_CUDA(cudaEventCreate(&e1));
+      const size_t avail = ne * sizeof(unsigned short), big = avail < ((size_t)16 << 20) ? avail : ((size_t)16 << 20), small = big / 16;
+      float ms_small = 0.f, ms_big = 0.f;
+      for (int rep = 0; rep < 4; ++rep) {  // (second round timed)
+        const size_t bytes = (rep & 1) ? big : small;
+        SEIR_CUDA(cudaEventRecord(e0, c->copy_stream));
+        SEIR_CUDA(cudaMemcpyAsync(c->d_stage_u16, c->h_stage_u16, bytes, cudaMemcpyHostToDevice, c->copy_stream));
+        SEIR_CUDA(cudaEventRecord(e1, c->copy_stream));
+        SEIR_CUDA(cudaEventSynchronize(e1));
+        SEIR_CUDA(cudaEventElapsedTime((rep & 1) ? &ms_big : &ms_small, e0, e1));
+      }
+      c->host_link_bpus = 25e3;  // fallback: 25 GB/s, 5 us per copy
+      c->host_copy_us = 5.0;
+      if (big >= ((size_t)4 << 20) && ms_big > ms_small && ms_small > 0.f) {
+        c->host_link_bpus = (double)(big - small) / ((ms_big - ms_small) * 1e3);
+        const double fixed = ms_small * 1e3 - (double)small / c->host_link_bpus;
+        c->host_copy_us = fixed > 0.0 ? (fixed < 50.0 ? fixed : 50.0) : 0.0;
+      }
+      c->host_tp_us = 0.0;
+      cudaEventDestroy(e0);
+      cudaEventDestroy(e1);
+    }
   }
   cudaStream_t s = cudaStreamPerThread, cs = c->copy_stream;
+  const bool trace = getenv("SEIR_HOST_TRACE") != nullptr;  // timeline of one call on stderr (tools/e2e_probe.py)
+  const auto tr0 = std::chrono::steady_clock::now();
+  auto us_now = [&]() { return (int)std::chrono::duration_cast<std::chrono::microseconds>(std::chrono::steady_clock::now() - tr0).count(); };
+  int tr_ship[SEIR_HOST_CHUNKS][3], tr_n = 0, tr_begin = 0, tr_loop = 0, tr_tail = 0;
+  static cudaEvent_t tev[2 * SEIR_HOST_CHUNKS + 8];  // trace mode: start | per ship: copy landed, ingest done | coef, contract, log-prob
+  static bool tev_ready = false;
+  if (trace && !tev_ready) {
+    for (auto& e : tev) SEIR_CUDA(cudaEventCreate(&e));
+    tev_ready = true;
+  }
+  if (trace) SEIR_CUDA(cudaEventRecord(tev[0], s));
   SEIR_CUDA(cudaMemcpyAsync(c->d_stage_theta, h_theta, nt * sizeof(double), cudaMemcpyHostToDevice, s));
   c->last_h2d_bytes = (int64_t)(nt * sizeof(double));
   if (parts & SEIR_PART_SEIR) {
     const int nch = c->stage_nchunks, cb = (B + nch - 1) / nch;  // chains per chunk (the last chunk may be short)
     const int jpc = seir_pack_begin(h_events, c->h_stage_u16, (size_t)cb * per_chain, ne, nch);
+    tr_begin = us_now();
     SEIR_TRY(seir_ingest_reset(c, s));
     int front = 0, back = nch - 1;       // next chunk expected from the pool / next chunk the caller may claim
-    int raw_pending[2] = {-1, -1};       // chunks whose float64 copy is in flight
+    int raw_pending[2] = {-1, -1};       // greedy mode: chunks whose float64 copy is in flight
+    int last_shipped = -1;               // chunk whose copy was enqueued last (its event completing = the link is idle)
     auto ship = [&](int k, bool narrowed) -> int {
       const int b0 = k * cb, nb = (b0 + cb <= B ? cb : B - b0);
       if (nb <= 0) return SEIR_OK;
+      if (trace && tr_n < SEIR_HOST_CHUNKS) { tr_ship[tr_n][0] = k; tr_ship[tr_n][1] = narrowed; tr_ship[tr_n][2] = us_now(); ++tr_n; }
       const size_t off = (size_t)b0 * per_chain, n = (size_t)nb * per_chain;
       c->last_h2d_bytes += (int64_t)(n * (narrowed ? sizeof(unsigned short) : sizeof(double)));
       if (narrowed)
@@ -377,30 +439,89 @@ int seir_log_prob_host(seir_chains* c, const double* h_events, const double* h_t
         SEIR_CUDA(cudaMemcpyAsync(c->d_stage_events + off, h_events + off, n * sizeof(double), cudaMemcpyHostToDevice, cs));
       SEIR_CUDA(cudaEventRecord(c->stage_ev[k], cs));
       SEIR_CUDA(cudaStreamWaitEvent(s, c->stage_ev[k], 0));
-      return seir_launch_ingest_range(c, narrowed ? nullptr : c->d_stage_events, narrowed ? c->d_stage_u16 : nullptr, b0, nb, s);
+      if (trace) SEIR_CUDA(cudaEventRecord(tev[2 * tr_n - 1], cs));
+      const int rc_ing = seir_launch_ingest_range(c, narrowed ? nullptr : c->d_stage_events, narrowed ? c->d_stage_u16 : nullptr, b0, nb, s);
+      if (trace) SEIR_CUDA(cudaEventRecord(tev[2 * tr_n], s));
+      last_shipped = k;
+      return rc_ing;
     };
+    // How many chunks travel as float64.  With the pool's time per chunk (tp, running mean of earlier calls) and the link's
+    // time per float64 / uint16 chunk (tr, tu; fixed cost + bytes / rate, measured when the staging buffers were made) the call
+    // ends at about  max((nch - n) tp + tu,  n tr + (nch - n) tu)  when n chunks go as they are: take the best n, and ship
+    // those n from the back at once so that the link is busy from the start.  The first call has no tp yet and claims
+    // greedily (a chunk whenever fewer than two float64 copies are in flight) -- which overshoots once the link, not the
+    // pool, is what finishes last.
+    const double tr_us = c->host_copy_us + (double)cb * per_chain * sizeof(double) / c->host_link_bpus;
+    const double tu_us = c->host_copy_us + (double)cb * per_chain * sizeof(unsigned short) / c->host_link_bpus, tp_us = c->host_tp_us;
+    int plan_raw = -1;
+    if (tp_us > 0.0) {
+      double best = 1e300;
+      for (int n = 0; n <= nch; ++n) {
+        // (link times carry an 8 % margin: copies interleaved with event records land a little slower than timed alone)
+        const double pool_t = (nch - n) * tp_us + (n < nch ? tu_us : 0.0), link_t = 1.08 * (n * tr_us + (nch - n) * tu_us);
+        const double t = pool_t > link_t ? pool_t : link_t;
+        if (t < best) { best = t; plan_raw = n; }
+      }
+    }
+    int n_raw = 0, n_packed = 0, t_pack_last = tr_begin;
     bool pool_done = false, claim_done = false;
+    // Early parts.  Once the first half of the chunks (then the next quarter, then the next eighth) has been ingested,
+    // everything else those chains need -- coefficients, contraction, theta prep, log-likelihood, finalize -- runs on a
+    // second stream while the remaining chunks are still travelling; only the last part is left for after the transfer.
+    // (Results do not depend on the cut: every kernel indexes chains absolutely and sums in a fixed per-chain order.)
+    int part_b0 = 0, next_cut = nch >= 8 ? nch / 2 : nch + 1;
+    auto early_part = [&]() -> int {
+      while (front >= next_cut && next_cut < nch) {
+        const int b1 = next_cut * cb;
+        const int step = (nch - next_cut) / 2;
+        if (b1 < B && seir_contract_range_ok(c, b1)) {
+          SEIR_CUDA(cudaEventRecord(c->tail_fork, s));  // (the ingests of every chunk below the cut are on s already)
+          SEIR_CUDA(cudaStreamWaitEvent(c->tail_stream, c->tail_fork, 0));
+          SEIR_TRY(host_part(c, kind, parts, c->tail_stream, seir_range{part_b0, b1 - part_b0}));
+          part_b0 = b1;
+        }
+        next_cut = step >= 2 ? next_cut + step : nch + 1;
+      }
+      return SEIR_OK;
+    };
     while (!(pool_done && claim_done)) {
       bool progressed = false;
+      // float64 chunks from the back
+      if (plan_raw < 0) {  // greedy
+        for (int q = 0; q < 2; ++q)
+          if (raw_pending[q] >= 0 && cudaEventQuery(c->stage_ev[raw_pending[q]]) == cudaSuccess) raw_pending[q] = -1;
+      }
+      while (!claim_done) {
+        bool want;
+        if (plan_raw < 0) {
+          want = raw_pending[0] < 0 || raw_pending[1] < 0;
+        } else if (n_raw < plan_raw) {
+          want = true;
+        } else {
+          // beyond the plan only when the link has run dry while the pool still has more than a float64 copy's worth of work
+          const bool idle = last_shipped < 0 || cudaEventQuery(c->stage_ev[last_shipped]) == cudaSuccess;
+          want = idle && front <= back && seir_pack_poll(front, jpc) < 0 && (back - front + 1) * tp_us > tr_us + tu_us;
+        }
+        if (!want) break;
+        if (back < front || !seir_pack_claim_raw(back)) { claim_done = true; break; }
+        SEIR_TRY(ship(back, false));
+        if (plan_raw < 0) raw_pending[raw_pending[0] < 0 ? 0 : 1] = back;
+        --back;
+        ++n_raw;
+        progressed = true;
+      }
       // narrowed chunks, in order
       while (!pool_done) {
-        if (front > back || seir_pack_owner(front) == 2) { pool_done = true; break; }
+        if (front > back || seir_pack_owner(front) == 2) { pool_done = true; claim_done = true; break; }
         if (seir_pack_owner(front) != 1) break;  // not started yet
         const int st = seir_pack_poll(front, jpc);
         if (st < 0) break;
         SEIR_TRY(ship(front, st == 1));  // a refused chunk travels as float64; the device-side ingest flags what is wrong with it
         ++front;
+        ++n_packed;
+        t_pack_last = us_now();
         progressed = true;
-      }
-      // float64 chunks from the back, at most two copies in flight
-      for (int q = 0; q < 2; ++q)
-        if (raw_pending[q] >= 0 && cudaEventQuery(c->stage_ev[raw_pending[q]]) == cudaSuccess) raw_pending[q] = -1;
-      while (!claim_done && (raw_pending[0] < 0 || raw_pending[1] < 0)) {
-        if (back < front || !seir_pack_claim_raw(back)) { claim_done = true; break; }
-        SEIR_TRY(ship(back, false));
-        raw_pending[raw_pending[0] < 0 ? 0 : 1] = back;
-        --back;
-        progressed = true;
+        SEIR_TRY(early_part());
       }
       if (!progressed) {
 #if defined(__x86_64__)
@@ -408,12 +529,41 @@ int seir_log_prob_host(seir_chains* c, const double* h_events, const double* h_t
 #endif
       }
     }
-    SEIR_TRY(seir_launch_coef(c, s));
-    SEIR_TRY(seir_launch_contract(c, s));
+    if (n_packed >= 2) {
+      const double meas = (double)(t_pack_last - tr_begin) / n_packed;
+      c->host_tp_us = c->host_tp_us > 0.0 ? 0.5 * (c->host_tp_us + meas) : meas;
+    }
+    tr_loop = us_now();
+    SEIR_TRY(host_part(c, kind, parts, s, seir_range{part_b0, B - part_b0}));
+    if (part_b0 > 0) {
+      SEIR_CUDA(cudaEventRecord(c->tail_join, c->tail_stream));
+      SEIR_CUDA(cudaStreamWaitEvent(s, c->tail_join, 0));
+    }
+    if (trace) SEIR_CUDA(cudaEventRecord(tev[2 * SEIR_HOST_CHUNKS + 3], s));
+  } else {
+    SEIR_TRY(seir_log_prob_cached(c, c->d_stage_theta, kind, parts, c->d_stage_out, s));
   }
-  SEIR_TRY(seir_log_prob_cached(c, c->d_stage_theta, kind, parts, c->d_stage_out, s));
   SEIR_CUDA(cudaMemcpyAsync(h_out, c->d_stage_out, (size_t)B * sizeof(double), cudaMemcpyDeviceToHost, s));
+  tr_tail = us_now();
   SEIR_CUDA(cudaStreamSynchronize(s));
+  if (trace) {
+    fprintf(stderr, "seir_log_prob_host us: pack_begin %d loop_end %d enqueued %d synced %d | link %.1f GB/s + %.1f us/copy, pool %.0f us/chunk | ships (chunk:kind@us)",
+            tr_begin, tr_loop, tr_tail, us_now(), c->host_link_bpus * 1e-3, c->host_copy_us, c->host_tp_us);
+    for (int q = 0; q < tr_n; ++q) fprintf(stderr, " %d:%s@%d", tr_ship[q][0], tr_ship[q][1] ? "u16" : "f64", tr_ship[q][2]);
+    fprintf(stderr, "\n  device us after the call's first stream op (copy landed / ingest done):");
+    float ms = 0.f;
+    for (int q = 0; q < tr_n; ++q) {
+      cudaEventElapsedTime(&ms, tev[0], tev[2 * q + 1]);
+      fprintf(stderr, " %d:%d", tr_ship[q][0], (int)(ms * 1e3f));
+      cudaEventElapsedTime(&ms, tev[0], tev[2 * q + 2]);
+      fprintf(stderr, "/%d", (int)(ms * 1e3f));
+    }
+    if (parts & SEIR_PART_SEIR) {
+      cudaEventElapsedTime(&ms, tev[0], tev[2 * SEIR_HOST_CHUNKS + 3]);
+      fprintf(stderr, " log-prob %d", (int)(ms * 1e3f));
+    }
+    fprintf(stderr, "\n");
+  }
   return SEIR_OK;
 }
 

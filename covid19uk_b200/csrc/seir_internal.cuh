@@ -132,10 +132,12 @@ struct seir_chains {
   // staging for the host-buffer entry points
   double *d_stage_events, *d_stage_theta, *d_stage_out;
   unsigned short *d_stage_u16, *h_stage_u16;  // narrowed events: device copy and pinned host staging
-  cudaStream_t copy_stream;
+  cudaStream_t copy_stream, tail_stream;       // host entry point: H2D copies; early parts of the events-wide kernels
+  cudaEvent_t tail_fork, tail_join;
   cudaEvent_t* stage_ev;                       // one per chain chunk of the host entry point
   int stage_nchunks;
   int64_t last_h2d_bytes;
+  double host_link_bpus, host_copy_us, host_tp_us;  // host entry point: link rate (bytes/us), fixed cost per copy (us), pool time per chunk (us, running mean)
 };
 
 // error plumbing (seir_api.cu)
@@ -162,9 +164,16 @@ int seir_ingest_reset(seir_chains* c, cudaStream_t s);
 int seir_launch_ingest_range(seir_chains* c, const double* d_events, const unsigned short* d_events_u16, int b0, int nb,
                              cudaStream_t s);
 int seir_launch_coef(seir_chains* c, cudaStream_t s);
+int seir_launch_coef_range(seir_chains* c, cudaStream_t s, seir_range r);
 int seir_launch_contract(seir_chains* c, cudaStream_t s);
+int seir_launch_contract_range(seir_chains* c, cudaStream_t s, seir_range r);
+bool seir_contract_range_ok(const seir_chains* c, int b0);
 int seir_launch_contract_i8(seir_chains* c, cudaStream_t s);
+int seir_launch_contract_i8_range(seir_chains* c, cudaStream_t s, seir_range r);
 int seir_launch_contract_f64(seir_chains* c, cudaStream_t s);
+int seir_launch_contract_f64_range(seir_chains* c, cudaStream_t s, seir_range r);
+int seir_launch_finalize_range(seir_chains* c, const double* d_theta, int kind, int parts, double* d_out, double* d_grad, cudaStream_t s,
+                               seir_range r);
 int seir_contract_i8_setup(seir_model* m, const double* h_cs, double max_population);
 int seir_launch_theta_prep(seir_chains* c, const double* d_theta, int kind, int parts, cudaStream_t s, seir_range r);
 int seir_launch_loglik(seir_chains* c, bool grad, cudaStream_t s, seir_range r);
