@@ -76,7 +76,13 @@ int seir_launch_state(const seir_model* m, int B, const double* d_events, double
 // The FP64 work (log binomial coefficients) lives in seir_coef_kernel below: ncu on the fused version
 // showed 16/32 active lanes (table-vs-Stirling divergence) and 37 % occupancy (profiles/r01_v2_*).
 // ------------------------------------------------------------------------------------------------
-template <int TC, typename EV>
+//
+// TMA = true (float64 events, even T, 16-byte aligned tensor; the default): the CTA's 32 rows of a day chunk are fetched by
+// 32 bulk copies (cp.async.bulk, one per row, issued by warp 0) into a float64 staging tile and converted IN PLACE to the
+// int32 tile, so the whole 64.5 KB of a UK tile is in flight at once at no register cost.  ncu on the register-path
+// kernel (profiles/r01_v7_*, 57 % of the stall samples on the first use of a loaded value, 41 % DRAM throughput): one
+// 16-byte load per lane in flight per warp is too little memory-level parallelism for 6.5 TB/s.
+template <int TC, typename EV, bool TMA>
 __global__ void __launch_bounds__(256) seir_ingest_kernel(int M, int T, int Mp, int b0, const int* __restrict__ init,
                                                           const EV* __restrict__ events, int* __restrict__ yse,
                                                           int* __restrict__ yei, int* __restrict__ yir, int* __restrict__ Sx,
@@ -84,12 +90,24 @@ __global__ void __launch_bounds__(256) seir_ingest_kernel(int M, int T, int Mp, 
                                                           long long* __restrict__ Rir, long long* __restrict__ sumYei,
                                                           long long* __restrict__ sumEres, int* __restrict__ flags,
                                                           int* __restrict__ nzd) {
-  constexpr int STRIDE = TC * 3 + 1;
-  extern __shared__ int smem_i[];
-  int* ev = smem_i;                    // [32][STRIDE]
-  int* segsum = smem_i + 32 * STRIDE;  // [8][3][32]
+  extern __shared__ __align__(16) int smem_i[];
+  __shared__ uint64_t tma_bar;
+  const int tcmax = T < TC ? T : TC;
+  // TMA: the int32 tile overlays the float64 staging tile [32][tc*3] (row stride tc*3 + 1 ints, set per chunk);
+  // register path: [32][TC*3 + 1].  Either way the stride is odd: lane <-> metapopulation reads are conflict-free.
+  int STRIDE = TC * 3 + 1;
+  int* ev = smem_i;
+  int* segsum = smem_i + (TMA ? 32 * tcmax * 6 : 32 * STRIDE);  // [8][3][32]
   int* dayY = segsum + 8 * 3 * 32;     // [TC] per-day sums over the CTA's 32 metapopulations: y_ir
   int* dayR = dayY + TC;               // [TC]                                            : I - y_ir
+  unsigned tma_phase = 0;
+  if (TMA) {
+    if (threadIdx.x == 0) {
+      mbar_init(&tma_bar, 1);
+      asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+    }
+    __syncthreads();
+  }
 
   const int b = b0 + blockIdx.y, m0 = blockIdx.x * 32;
   const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
@@ -105,7 +123,46 @@ __global__ void __launch_bounds__(256) seir_ingest_kernel(int M, int T, int Mp, 
   for (int t0 = 0; t0 < T; t0 += TC) {
     const int tc = min(TC, T - t0);
     // ---- load ----
-    for (int r = warp; r < 32; r += 8) {
+    if (TMA) {
+      const int rs = tc * 3;  // doubles per staged row
+      double* stage = reinterpret_cast<double*>(smem_i);
+      STRIDE = rs + 1;
+      if (warp == 0) {
+        const int nvalid = max(0, min(32, M - m0));  // (padding blocks hold no row: the barrier phase completes with 0 bytes)
+        const unsigned rowbytes = (unsigned)rs * 8u;
+        if (t0 > 0) asm volatile("fence.proxy.async.shared::cta;" ::: "memory");  // the tile was read through the generic proxy
+        if (lane == 0) mbar_expect_tx(&tma_bar, (unsigned)nvalid * rowbytes);
+        __syncwarp();
+        if (lane < nvalid)
+          bulk_load_1d(stage + (size_t)lane * rs, reinterpret_cast<const double*>(events) + (((size_t)b * M + m0 + lane) * T + t0) * 3, rowbytes,
+                       &tma_bar);
+      }
+      mbar_wait(&tma_bar, tma_phase);
+      tma_phase ^= 1u;
+      // In-place float64 -> int32, 8 rows at a time (warp <-> row): a wave of rows is read into registers by the whole
+      // CTA, then (barrier) written.  The int32 row r starts at byte 4 r STRIDE <= 4 r (rs + 1): a wave's writes end below
+      // byte 32 (w + 1)(rs + 1), the next wave's sources start at byte 64 (w + 1) rs -- never reached -- and everything
+      // below has been consumed already.
+      constexpr int PER_LANE = (TC * 3 + 31) / 32;
+      for (int r = warp; r < 32; r += 8) {
+        const bool live = m0 + r < M;  // (warp-uniform; rows past M were not fetched)
+        double v[PER_LANE];
+#pragma unroll
+        for (int j = 0; j < PER_LANE; ++j) {
+          const int k = j * 32 + lane;
+          v[j] = (live && k < rs) ? stage[r * rs + k] : 0.0;
+        }
+        __syncthreads();
+#pragma unroll
+        for (int j = 0; j < PER_LANE; ++j) {
+          const int k = j * 32 + lane;
+          const int iv = __double2int_rn(v[j]);
+          if ((double)iv != v[j] || iv < 0) bad |= 1;
+          if (k < rs) ev[r * STRIDE + k] = iv;
+        }
+      }
+    }
+    for (int r = warp; r < 32 && !TMA; r += 8) {
       const int mm = m0 + r;
       const EV* src = events + (((size_t)b * M + mm) * T + t0) * 3;
       if (sizeof(EV) == sizeof(double) && vec2) {  // two counts per 16-byte load (row starts are 16-byte aligned: T even)
@@ -200,17 +257,18 @@ __global__ void __launch_bounds__(256) seir_ingest_kernel(int M, int T, int Mp, 
   if (lane == 0 && bad) atomicOr(flags + b, bad);
 }
 
-template <int TC, typename EV>
+template <int TC, typename EV, bool TMA>
 static int launch_ingest_tc(seir_chains* c, const EV* d_events, int b0, int nb, cudaStream_t s) {
   const seir_model* m = c->model;
-  const size_t smem = sizeof(int) * (32 * (TC * 3 + 1) + 8 * 3 * 32 + 2 * TC);
-  static bool attr_set = false;
-  if (!attr_set) {
-    SEIR_CUDA(cudaFuncSetAttribute(seir_ingest_kernel<TC, EV>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
-    attr_set = true;
+  const int tcmax = m->T < TC ? m->T : TC;
+  const size_t smem = sizeof(int) * ((TMA ? 32 * tcmax * 6 : 32 * (TC * 3 + 1)) + 8 * 3 * 32 + 2 * TC);
+  static size_t attr = 0;
+  if (attr != smem) {
+    SEIR_CUDA(cudaFuncSetAttribute(seir_ingest_kernel<TC, EV, TMA>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+    attr = smem;
   }
   dim3 grid(c->nblk32, nb);
-  seir_ingest_kernel<TC, EV><<<grid, 256, smem, s>>>(m->M, m->T, m->Mp, b0, m->d_init, d_events, c->d_yse, c->d_yei, c->d_yir, c->d_S,
+  seir_ingest_kernel<TC, EV, TMA><<<grid, 256, smem, s>>>(m->M, m->T, m->Mp, b0, m->d_init, d_events, c->d_yse, c->d_yei, c->d_yir, c->d_S,
                                                      c->d_E, c->d_I, c->d_Yir, c->d_Rir, c->d_sumYei, c->d_sumEres, c->d_flags, c->d_nzd);
   seir_count_launch(1);
   return seir_cuda_check(cudaGetLastError(), "seir_ingest_kernel");
@@ -230,9 +288,17 @@ int seir_launch_ingest_range(seir_chains* c, const double* d_events, const unsig
                              cudaStream_t s) {
   const int T = c->model->T;
   if (d_events_u16)
-    return (T <= 96) ? launch_ingest_tc<96, unsigned short>(c, d_events_u16, b0, nb, s)
-                     : launch_ingest_tc<128, unsigned short>(c, d_events_u16, b0, nb, s);
-  return (T <= 96) ? launch_ingest_tc<96, double>(c, d_events, b0, nb, s) : launch_ingest_tc<128, double>(c, d_events, b0, nb, s);
+    return (T <= 96) ? launch_ingest_tc<96, unsigned short, false>(c, d_events_u16, b0, nb, s)
+                     : launch_ingest_tc<128, unsigned short, false>(c, d_events_u16, b0, nb, s);
+  static int use_tma = -1;
+  if (use_tma < 0) {
+    const char* e = getenv("SEIR_INGEST_TMA");  // 0: register-path loads (also taken for odd T / unaligned tensors)
+    use_tma = e ? atoi(e) : 1;
+  }
+  if (use_tma && T % 2 == 0 && (reinterpret_cast<uintptr_t>(d_events) & 15) == 0)
+    return (T <= 96) ? launch_ingest_tc<96, double, true>(c, d_events, b0, nb, s) : launch_ingest_tc<128, double, true>(c, d_events, b0, nb, s);
+  return (T <= 96) ? launch_ingest_tc<96, double, false>(c, d_events, b0, nb, s)
+                   : launch_ingest_tc<128, double, false>(c, d_events, b0, nb, s);
 }
 
 int seir_launch_ingest(seir_chains* c, const double* d_events, cudaStream_t s) {
