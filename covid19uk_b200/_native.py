@@ -17,7 +17,7 @@ PART_SEIR = 1
 PART_PRIORS = 2
 PART_ILDJ = 4
 PART_JOINT = 7
-ABI_VERSION = 7
+ABI_VERSION = 8
 
 
 class SeirSpec(ctypes.Structure):
@@ -90,6 +90,7 @@ SIGNATURES = {
     "seir_hmc_draw": (c_int, [c_void_p, ctypes.c_uint64, ctypes.c_uint32, ctypes.c_uint32, c_void_p, c_void_p, c_void_p, c_void_p]),
     "seir_propose": (c_int, [c_void_p, c_void_p, ctypes.c_uint64, ctypes.c_uint32, ctypes.c_uint32, c_void_p, c_void_p, c_void_p]),
     "seir_mcmc_sweep": (c_int, [c_void_p, c_void_p, ctypes.c_uint32] + [c_void_p] * 10),
+    "seir_mcmc_burst": (c_int, [c_void_p, c_void_p, ctypes.c_uint32, ctypes.c_int32] + [c_void_p] * 11),
     "seir_export_events": (c_int, [c_void_p, c_void_p, c_void_p]),
     "seir_simulate": (c_int, [c_void_p, c_int, ctypes.c_uint64, ctypes.c_uint32, c_void_p, c_void_p, c_void_p, c_void_p, c_void_p, c_void_p]),
     "seir_reproduction_number": (c_int, [c_void_p, c_void_p, c_void_p, c_void_p]),

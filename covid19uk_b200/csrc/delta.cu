@@ -31,6 +31,7 @@
 // ------------------------------------------------------------------------------------------------
 struct upd_outputs {
   double* tlp;
+  double* tlp_trace;  // [B] or NULL: the chain's target log-prob after this update (results/<kernel>/target_log_prob)
   int* accept;
   int* last_acc;
   int* trace;
@@ -60,6 +61,7 @@ __device__ __forceinline__ void upd_commit_rows(int b, int T, int Mp, const seir
       o.tlp[b] = prop_tlp;
       llc_adj[b] += u.dllc;
     }
+    if (o.tlp_trace) o.tlp_trace[b] = acc ? prop_tlp : o.tlp[b];
     upd[b].accept = acc;
     upd[b].dll = dll;
     o.accept[b] = acc;
@@ -458,11 +460,12 @@ __global__ void __launch_bounds__(32 * SLAB_DAYS) seir_update_commit_kernel(
 }
 
 static int launch_update(seir_chains* c, const seir_update_cfg& cfg, int slot, const seir_draw_args& draw, int* d_proposal,
-                         double* d_log_u, double* d_tlp, int* d_accept, int* d_trace, double* d_dbg, cudaStream_t s, seir_range r) {
+                         double* d_log_u, double* d_tlp, double* d_tlp_trace, int* d_accept, int* d_trace, double* d_dbg, cudaStream_t s,
+                         seir_range r) {
   const seir_model* m = c->model;
   const int B = c->B, T = m->T, Mp = m->Mp;
   const int nchunk = (T + SLAB_DAYS - 1) / SLAB_DAYS;
-  const upd_outputs outs{d_tlp, d_accept, c->d_last_acc + (size_t)slot * B * 4 * SEIR_MMAX, d_trace, d_dbg};
+  const upd_outputs outs{d_tlp, d_tlp_trace, d_accept, c->d_last_acc + (size_t)slot * B * 4 * SEIR_MMAX, d_trace, d_dbg};
   const size_t smem = upd_smem_bytes(T, Mp);
   static size_t attr = 0;
   if (smem > 48 * 1024 && attr != smem) {
@@ -491,16 +494,16 @@ static int launch_update(seir_chains* c, const seir_update_cfg& cfg, int slot, c
 int seir_launch_update(seir_chains* c, const seir_update_cfg& cfg, int slot, const int* d_proposal, const double* d_log_u,
                        double* d_tlp, int* d_accept, int* d_trace, double* d_dbg, cudaStream_t s) {
   const seir_draw_args none{0, 0ull, 0u, 0u};
-  return launch_update(c, cfg, slot, none, const_cast<int*>(d_proposal), const_cast<double*>(d_log_u), d_tlp, d_accept, d_trace, d_dbg, s,
-                       seir_all(c));
+  return launch_update(c, cfg, slot, none, const_cast<int*>(d_proposal), const_cast<double*>(d_log_u), d_tlp, nullptr, d_accept, d_trace,
+                       d_dbg, s, seir_all(c));
 }
 
 // proposal and log u drawn inside the prepare kernel (fused sweep); the record is left in d_proposal / d_log_u
 int seir_launch_update_drawn(seir_chains* c, const seir_update_cfg& cfg, int slot, unsigned long long seed, unsigned chain0,
-                             unsigned ctr, int* d_proposal, double* d_log_u, double* d_tlp, int* d_accept, int* d_trace,
-                             cudaStream_t s, seir_range r) {
+                             unsigned ctr, int* d_proposal, double* d_log_u, double* d_tlp, double* d_tlp_trace, int* d_accept,
+                             int* d_trace, cudaStream_t s, seir_range r) {
   const seir_draw_args draw{1, seed, chain0, ctr};
-  return launch_update(c, cfg, slot, draw, d_proposal, d_log_u, d_tlp, d_accept, d_trace, nullptr, s, r);
+  return launch_update(c, cfg, slot, draw, d_proposal, d_log_u, d_tlp, d_tlp_trace, d_accept, d_trace, nullptr, s, r);
 }
 
 // ------------------------------------------------------------------------------------------------

@@ -66,7 +66,8 @@ __global__ void __launch_bounds__(TF_THREADS) seir_hmc_leap_kernel(tf_model md, 
                                                                   const double* __restrict__ inv_mass, const double* __restrict__ log_u,
                                                                   double* u, double* __restrict__ p, double* grad,
                                                                   double* __restrict__ u0, double* __restrict__ val0, double* __restrict__ k0,
-                                                                  double* __restrict__ tlp, int* __restrict__ accept, double* __restrict__ dbg) {
+                                                                  double* __restrict__ tlp, double* __restrict__ tlp_trace,
+                                                                  int* __restrict__ accept, double* __restrict__ dbg) {
   extern __shared__ double dyn[];
   __shared__ tf_shared sh;
   __shared__ double red[32];
@@ -108,6 +109,7 @@ __global__ void __launch_bounds__(TF_THREADS) seir_hmc_leap_kernel(tf_model md, 
         s_acc = acc;
         accept[b] = acc;
         tlp[b] = acc ? val : val0[b];
+        if (tlp_trace) tlp_trace[b] = acc ? val : val0[b];  // results/hmc/target_log_prob of this sweep
         if (dbg) {
           dbg[(size_t)b * 4 + 0] = ratio;
           dbg[(size_t)b * 4 + 1] = val;
@@ -137,6 +139,7 @@ static int hmc_alloc(seir_chains* c) {
 
 int seir_hmc_workspace(seir_chains* c) { return hmc_alloc(c); }
 
+
 int seir_launch_hmc_momentum(seir_chains* c, unsigned long long seed, unsigned chain0, unsigned sweep, const double* d_inv_mass,
                              double* d_p, cudaStream_t s, seir_range r) {
   const int P = c->model->P;
@@ -154,7 +157,8 @@ int seir_hmc_step_begin(seir_chains* c, const double* d_u, cudaStream_t s, seir_
 }
 
 int seir_hmc_step_leap(seir_chains* c, int i, int num_leapfrog, double* d_u, const double* d_log_u, const double* d_step,
-                       const double* d_inv_mass, double* d_tlp, int* d_accept, double* d_dbg, cudaStream_t s, seir_range r) {
+                       const double* d_inv_mass, double* d_tlp, double* d_tlp_trace, int* d_accept, double* d_dbg, cudaStream_t s,
+                       seir_range r) {
   const seir_model* m = c->model;
   const int B = c->B;
   double *val0 = c->d_hmc_val + B, *k0 = c->d_hmc_val + 2 * B;
@@ -172,13 +176,13 @@ int seir_hmc_step_leap(seir_chains* c, int i, int num_leapfrog, double* d_u, con
   const tf_chains ch = seir_tf_chains(c);  // (after the log-lik launch: it fixes the partial-array shapes)
   if (i == 0)
     seir_hmc_leap_kernel<HMC_BEGIN><<<r.nb, TF_THREADS, smem, s>>>(md, ch, r.b0, d_step, d_inv_mass, d_log_u, d_u, c->d_hmc_p, c->d_hmc_grad,
-                                                                   c->d_hmc_u0, val0, k0, d_tlp, d_accept, d_dbg);
+                                                                   c->d_hmc_u0, val0, k0, d_tlp, d_tlp_trace, d_accept, d_dbg);
   else if (i < num_leapfrog)
     seir_hmc_leap_kernel<HMC_MID><<<r.nb, TF_THREADS, smem, s>>>(md, ch, r.b0, d_step, d_inv_mass, d_log_u, d_u, c->d_hmc_p, c->d_hmc_grad,
-                                                                 c->d_hmc_u0, val0, k0, d_tlp, d_accept, d_dbg);
+                                                                 c->d_hmc_u0, val0, k0, d_tlp, d_tlp_trace, d_accept, d_dbg);
   else
     seir_hmc_leap_kernel<HMC_END><<<r.nb, TF_THREADS, smem, s>>>(md, ch, r.b0, d_step, d_inv_mass, d_log_u, d_u, c->d_hmc_p, c->d_hmc_grad,
-                                                                 c->d_hmc_u0, val0, k0, d_tlp, d_accept, d_dbg);
+                                                                 c->d_hmc_u0, val0, k0, d_tlp, d_tlp_trace, d_accept, d_dbg);
   seir_count_launch(1);
   return seir_cuda_check(cudaGetLastError(), "seir_hmc_leap_kernel");
 }
@@ -194,6 +198,6 @@ int seir_launch_hmc(seir_chains* c, double* d_u, const double* d_momentum, const
   const seir_range all = seir_all(c);
   if ((rc = seir_hmc_step_begin(c, d_u, s, all)) != SEIR_OK) return rc;
   for (int i = 0; i <= num_leapfrog; ++i)
-    if ((rc = seir_hmc_step_leap(c, i, num_leapfrog, d_u, d_log_u, d_step, d_inv_mass, d_tlp, d_accept, d_dbg, s, all)) != SEIR_OK) return rc;
+    if ((rc = seir_hmc_step_leap(c, i, num_leapfrog, d_u, d_log_u, d_step, d_inv_mass, d_tlp, nullptr, d_accept, d_dbg, s, all)) != SEIR_OK) return rc;
   return SEIR_OK;
 }

@@ -50,11 +50,6 @@ static int dev_upload(T** p, const std::vector<T>& h) {
   return SEIR_OK;
 }
 
-#define SEIR_TRY(expr)            \
-  do {                            \
-    int _rc = (expr);             \
-    if (_rc != SEIR_OK) return _rc; \
-  } while (0)
 
 extern "C" {
 
@@ -247,7 +242,11 @@ void seir_chains_destroy(seir_chains* c) {
   cudaFree(c->d_tlp); cudaFree(c->d_i8_planes); cudaFree(c->d_i8_flags); cudaFree(c->d_hmc_u0); cudaFree(c->d_hmc_p); cudaFree(c->d_hmc_grad);
   cudaFree(c->d_hmc_val);
   if (c->grp_ready) {
-    for (int g = 0; g < 4; ++g) { cudaStreamDestroy(c->grp_stream[g]); cudaEventDestroy(c->grp_join[g]); }
+    for (int g = 0; g < SEIR_MAX_GROUPS; ++g) {
+      cudaStreamDestroy(c->grp_stream[g]);
+      cudaEventDestroy(c->grp_join[g]);
+      cudaEventDestroy(c->grp_stagger[g]);
+    }
     cudaEventDestroy(c->grp_fork);
   }
   cudaFree(c->d_prop); cudaFree(c->d_logu); cudaFree(c->d_stage_events); cudaFree(c->d_stage_theta);
@@ -666,6 +665,22 @@ int seir_mcmc_sweep(seir_chains* c, const seir_sweep_spec* sp, uint32_t sweep_in
     return seir_set_error(SEIR_ERR_BAD_ARG, "seir_mcmc_sweep: invalid sweep spec");
   return seir_launch_sweep(c, sp, sweep_index, d_u, d_step_size, d_inv_mass, d_tlp, d_hmc_accept, d_hmc_dbg, d_upd_accept, d_upd_tlp,
                            d_upd_trace, (cudaStream_t)stream);
+}
+
+int seir_mcmc_burst(seir_chains* c, const seir_sweep_spec* sp, uint32_t sweep_index0, int32_t num_sweeps, double* d_u,
+                    const double* d_step_size, const double* d_inv_mass, double* d_tlp, int32_t* d_hmc_accept, double* d_hmc_dbg,
+                    int32_t* d_upd_accept, double* d_upd_tlp, int32_t* d_upd_trace, double* d_draws, void* stream) {
+  if (!c || !sp || !d_step_size || !d_tlp || !d_hmc_accept || !d_upd_accept)
+    return seir_set_error(SEIR_ERR_BAD_ARG, "seir_mcmc_burst: NULL argument");
+  SEIR_TRY(check_dev_ptr(d_u, "d_u"));
+  const int T = c->model->T;
+  if (num_sweeps < 0 || num_sweeps > (1 << 20)) return seir_set_error(SEIR_ERR_BAD_ARG, "seir_mcmc_burst: bad num_sweeps %d", num_sweeps);
+  if (sp->num_leapfrog_steps < 1 || sp->num_event_time_updates < 0 || sp->mmax < 1 || sp->mmax > 2 || sp->dmax < 1 || sp->nmax < 0 ||
+      sp->occult_nmax < 0 || !(0 <= sp->t0 && sp->t0 < sp->t1 && sp->t1 <= T) || sp->num_event_time_updates > 16)
+    return seir_set_error(SEIR_ERR_BAD_ARG, "seir_mcmc_burst: invalid sweep spec");
+  if (num_sweeps == 0) return SEIR_OK;
+  return seir_launch_sweep_burst(c, sp, sweep_index0, num_sweeps, d_u, d_step_size, d_inv_mass, d_tlp, d_hmc_accept, d_hmc_dbg,
+                                 d_upd_accept, d_upd_tlp, d_upd_trace, d_draws, (cudaStream_t)stream);
 }
 
 int seir_export_events(seir_chains* c, double* d_events, void* stream) {

@@ -78,6 +78,8 @@ struct seir_upd {  // per-chain scratch of one discrete update
   double dll;      // total delta (filled by the commit kernel)
 };
 
+#define SEIR_MAX_GROUPS 8  // chain groups of a sweep (internal streams)
+
 struct seir_chains {
   const seir_model* model;
   int B;
@@ -126,8 +128,8 @@ struct seir_chains {
   int* d_prop;
   double* d_logu;
   // sweep chain groups: internal streams forked from / joined to the caller's stream
-  cudaStream_t grp_stream[4];
-  cudaEvent_t grp_fork, grp_join[4];
+  cudaStream_t grp_stream[SEIR_MAX_GROUPS];
+  cudaEvent_t grp_fork, grp_join[SEIR_MAX_GROUPS], grp_stagger[SEIR_MAX_GROUPS];
   int grp_ready;
   // staging for the host-buffer entry points
   double *d_stage_events, *d_stage_theta, *d_stage_out;
@@ -144,6 +146,14 @@ struct seir_chains {
 int seir_set_error(int code, const char* fmt, ...);
 int seir_cuda_check(cudaError_t e, const char* what);
 void seir_count_launch(int n);
+
+#ifndef SEIR_TRY
+#define SEIR_TRY(expr)              \
+  do {                              \
+    int _rc = (expr);               \
+    if (_rc != SEIR_OK) return _rc; \
+  } while (0)
+#endif
 
 #define SEIR_CUDA(call)                                   \
   do {                                                    \
@@ -184,7 +194,8 @@ int seir_launch_hmc_momentum(seir_chains* c, unsigned long long seed, unsigned c
 // the steps of one HMC transition (seir_launch_hmc = all of them over every chain)
 int seir_hmc_step_begin(seir_chains* c, const double* d_u, cudaStream_t s, seir_range r);
 int seir_hmc_step_leap(seir_chains* c, int i, int num_leapfrog, double* d_u, const double* d_log_u, const double* d_step,
-                       const double* d_inv_mass, double* d_tlp, int* d_accept, double* d_dbg, cudaStream_t s, seir_range r);
+                       const double* d_inv_mass, double* d_tlp, double* d_tlp_trace, int* d_accept, double* d_dbg, cudaStream_t s,
+                       seir_range r);
 int seir_launch_hmc(seir_chains* c, double* d_u, const double* d_momentum, const double* d_log_u, const double* d_step,
                     const double* d_inv_mass, int num_leapfrog, double* d_tlp, int* d_accept, double* d_dbg, cudaStream_t s);
 int seir_hmc_workspace(seir_chains* c);
@@ -195,6 +206,9 @@ int seir_launch_propose(seir_chains* c, const seir_update_cfg& cfg, unsigned lon
 int seir_launch_sweep(seir_chains* c, const seir_sweep_spec* sp, unsigned sweep_index, double* d_u, const double* d_step,
                       const double* d_inv_mass, double* d_tlp, int* d_hmc_accept, double* d_hmc_dbg, int* d_upd_accept,
                       double* d_upd_tlp, int* d_upd_trace, cudaStream_t s);
+int seir_launch_sweep_burst(seir_chains* c, const seir_sweep_spec* sp, unsigned sweep_index0, int num_sweeps, double* d_u,
+                            const double* d_step, const double* d_inv_mass, double* d_tlp, int* d_hmc_accept, double* d_hmc_dbg,
+                            int* d_upd_accept, double* d_upd_tlp, int* d_upd_trace, double* d_draws, cudaStream_t s);
 int seir_launch_export_events(seir_chains* c, double* d_events, cudaStream_t s);
 int seir_launch_simulate(const seir_model* m, int B, unsigned long long seed, unsigned chain0, const double* d_alpha_path,
                          const double* d_scal, const double* d_spatial, const double* d_init_state, double* d_events, cudaStream_t s);
@@ -204,8 +218,8 @@ int seir_launch_update(seir_chains* c, const seir_update_cfg& cfg, int slot, con
                        double* d_tlp, int* d_accept, int* d_trace, double* d_dbg, cudaStream_t s);
 
 int seir_launch_update_drawn(seir_chains* c, const seir_update_cfg& cfg, int slot, unsigned long long seed, unsigned chain0,
-                             unsigned ctr, int* d_proposal, double* d_log_u, double* d_tlp, int* d_accept, int* d_trace,
-                             cudaStream_t s, seir_range r);
+                             unsigned ctr, int* d_proposal, double* d_log_u, double* d_tlp, double* d_tlp_trace, int* d_accept,
+                             int* d_trace, cudaStream_t s, seir_range r);
 
 // ---- device helpers ---------------------------------------------------------------------------
 #ifdef __CUDACC__

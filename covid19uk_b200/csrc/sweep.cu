@@ -35,70 +35,82 @@ static void slot_cfg(const seir_sweep_spec* sp, int slot, seir_update_cfg* cfg) 
 // mostly idle in two thirds of the launches.  The chains are therefore cut into G contiguous groups whose launch
 // sequences run on G internal streams (forked from / joined to the caller's stream with events): while one group is in
 // a latency-bound update kernel another streams its log-likelihood.  Results do not depend on G: every kernel indexes
-// chains absolutely, and the Philox streams are keyed by the global chain id.  (The gain is modest, ~5 %: the groups
-// start every sweep in phase, so mostly like kernels overlap; they drift apart only through timing noise.)
-static int sweep_groups(seir_chains* c) {
-  static int forced = -1;
-  if (forced < 0) {
-    const char* e = getenv("SEIR_SWEEP_GROUPS");
-    forced = e ? atoi(e) : 0;
+// chains absolutely, and the Philox streams are keyed by the global chain id.
+//   * seir_launch_sweep (one sweep per call): the groups start every sweep in phase, so mostly like kernels overlap; the
+//     gain is modest (~5 %: 1 group 2.38 ms, 2 groups 2.27 ms, 4 groups 2.31 ms per sweep at B = 256, UK).
+//   * seir_launch_sweep_burst (n sweeps per call, fixed step size -- tfp.mcmc.sample_chain over a burst,
+//     inference.py:107-117): the groups are joined only at the END of the burst and start STAGGERED (group g + 1 starts
+//     when group g is 1/G of the way through its first sweep), so that the latency-bound discrete updates of one group
+//     run under the log-likelihood launches of the HMC step of another for the whole burst.
+//     Measured (B = 256, UK, 20 sweeps): 1 group 2.35 ms per sweep, 2 staggered groups 2.29 ms, 4 groups 2.6-2.7 ms and
+//     8 groups enqueue-bound (616 launches per sweep at ~4.5 us of host time each).  The stagger buys little: two (four)
+//     INDEPENDENT chain sets of 128 (64) chains driven by separate host threads (tools/concurrent_sets.py) also finish
+//     256 chain-sweeps in 2.3-2.4 ms although one set alone needs 1.7 (1.3) ms -- the one-CTA-per-chain kernels hold
+//     registers while they wait (a leap launch ~16 k registers per chain for 20 us), which is what the two-CTAs-per-SM
+//     log-likelihood launches of the other group need, so the overlap is close to zero-sum.  The burst still removes the
+//     per-sweep host work (trace copies, one C call per sweep) and the per-sweep join.
+static int env_int(const char* name, int dflt) {
+  const char* e = getenv(name);
+  return e ? atoi(e) : dflt;
+}
+
+static int sweep_groups(seir_chains* c, bool burst) {
+  static int forced = -2, forced_burst = -2;
+  if (forced == -2) {
+    forced = env_int("SEIR_SWEEP_GROUPS", 0);
+    forced_burst = env_int("SEIR_BURST_GROUPS", 0);
   }
-  int g = forced > 0 ? forced : (c->B >= 64 ? 2 : 1);  // measured at B = 256 (UK): 1 group 2.38 ms, 2 groups 2.27 ms, 4 groups 2.31 ms per sweep
-  if (g > 4) g = 4;
+  int g = forced > 0 ? forced : (c->B >= 64 ? 2 : 1);
+  if (burst) g = forced_burst > 0 ? forced_burst : (forced > 0 ? forced : (c->B >= 64 ? 2 : 1));
+  if (g > SEIR_MAX_GROUPS) g = SEIR_MAX_GROUPS;
   if (g > c->B) g = c->B;
   return g;
 }
 
 static int sweep_streams(seir_chains* c) {
   if (c->grp_ready) return SEIR_OK;
-  for (int g = 0; g < 4; ++g) {
+  for (int g = 0; g < SEIR_MAX_GROUPS; ++g) {
     SEIR_CUDA(cudaStreamCreateWithFlags(&c->grp_stream[g], cudaStreamNonBlocking));
     SEIR_CUDA(cudaEventCreateWithFlags(&c->grp_join[g], cudaEventDisableTiming));
+    SEIR_CUDA(cudaEventCreateWithFlags(&c->grp_stagger[g], cudaEventDisableTiming));
   }
   SEIR_CUDA(cudaEventCreateWithFlags(&c->grp_fork, cudaEventDisableTiming));
   c->grp_ready = 1;
   return SEIR_OK;
 }
 
-int seir_launch_sweep(seir_chains* c, const seir_sweep_spec* sp, unsigned sweep_index, double* d_u, const double* d_step,
-                      const double* d_inv_mass, double* d_tlp, int* d_hmc_accept, double* d_hmc_dbg, int* d_upd_accept,
-                      double* d_upd_tlp, int* d_upd_trace, cudaStream_t s) {
-  int rc;
-  if ((rc = sweep_alloc(c)) != SEIR_OK) return rc;
-  if ((rc = seir_hmc_workspace(c)) != SEIR_OK) return rc;
-  const int B = c->B, G = sweep_groups(c), L = sp->num_leapfrog_steps;
-  seir_range rg[4];
-  cudaStream_t st[4];
-  for (int g = 0; g < G; ++g) {
-    const int b0 = (int)((long long)B * g / G), b1 = (int)((long long)B * (g + 1) / G);
-    rg[g] = seir_range{b0, b1 - b0};
-    st[g] = s;
-  }
-  if (G > 1) {
-    if ((rc = sweep_streams(c)) != SEIR_OK) return rc;
-    SEIR_CUDA(cudaEventRecord(c->grp_fork, s));
-    for (int g = 0; g < G; ++g) {
-      st[g] = c->grp_stream[g];
-      SEIR_CUDA(cudaStreamWaitEvent(st[g], c->grp_fork, 0));
-    }
-  }
-  // Launches are enqueued step by step ACROSS the groups, so that every stream has work from the start.
-#define FOR_GROUPS(call)                       \
-  for (int g = 0; g < G; ++g) {                \
-    const seir_range r = rg[g];                \
-    cudaStream_t gs = st[g];                   \
-    (void)r; (void)gs;                         \
-    if ((rc = (call)) != SEIR_OK) return rc;   \
-  }
+// where one sweep's results go (every array indexed by the absolute chain id; NULL = not wanted)
+struct sweep_out {
+  int* hmc_accept;    // [B]
+  double* hmc_dbg;    // [B][4]
+  int* upd_accept;    // [4][B]
+  double* upd_tlp;    // [5][B]: rows 0..3 the four discrete kernels (last repetition), row 4 right after the HMC step
+  int* upd_trace;     // [4][B][4][SEIR_MMAX]
+  double* draws;      // [B][P]: u after the sweep
+};
+
+// One sweep of the chains in r, enqueued on gs.  The sweep is a sequence of (L + 1) + 4 * reps steps; after step
+// `mark_step` (counted from 1) the event `mark` is recorded on gs (burst stagger), if given.
+static int enqueue_sweep(seir_chains* c, const seir_sweep_spec* sp, unsigned sweep_index, seir_range r, cudaStream_t gs, double* d_u,
+                         const double* d_step, const double* d_inv_mass, double* d_tlp, const sweep_out& o, cudaEvent_t mark, int mark_step) {
+  const int B = c->B, L = sp->num_leapfrog_steps, P = c->model->P;
+  int step = 0;
+  auto stepped = [&]() -> int {
+    if (mark && ++step == mark_step) SEIR_CUDA(cudaEventRecord(mark, gs));
+    return SEIR_OK;
+  };
   // ---- part 0: HMC on theta ----
-  FOR_GROUPS(seir_launch_hmc_momentum(c, sp->seed, sp->chain_offset, sweep_index, d_inv_mass, c->d_hmc_p, gs, r));
-  FOR_GROUPS(seir_launch_log_uniform(r, sp->seed, sp->chain_offset, sweep_index, 0x48u, c->d_logu, gs));
-  FOR_GROUPS(seir_hmc_step_begin(c, d_u, gs, r));
-  for (int i = 0; i <= L; ++i)
-    FOR_GROUPS(seir_hmc_step_leap(c, i, L, d_u, c->d_logu, d_step, d_inv_mass, d_tlp, d_hmc_accept, d_hmc_dbg, gs, r));
-  if (d_upd_tlp)  // row 4: target log-prob of the state the HMC step left behind (traced as results/hmc/target_log_prob)
-    FOR_GROUPS(seir_cuda_check(cudaMemcpyAsync(d_upd_tlp + (size_t)4 * B + r.b0, d_tlp + r.b0, sizeof(double) * (size_t)r.nb,
-                                               cudaMemcpyDeviceToDevice, gs), "trace copy"));
+  SEIR_TRY(seir_launch_hmc_momentum(c, sp->seed, sp->chain_offset, sweep_index, d_inv_mass, c->d_hmc_p, gs, r));
+  SEIR_TRY(seir_launch_log_uniform(r, sp->seed, sp->chain_offset, sweep_index, 0x48u, c->d_logu, gs));
+  SEIR_TRY(seir_hmc_step_begin(c, d_u, gs, r));
+  for (int i = 0; i <= L; ++i) {
+    // (the last leapfrog kernel also writes row 4 of upd_tlp: results/hmc/target_log_prob)
+    SEIR_TRY(seir_hmc_step_leap(c, i, L, d_u, c->d_logu, d_step, d_inv_mass, d_tlp, o.upd_tlp ? o.upd_tlp + (size_t)4 * B : nullptr,
+                                o.hmc_accept, o.hmc_dbg, gs, r));
+    SEIR_TRY(stepped());
+  }
+  if (o.draws)  // u changes in the HMC step only
+    SEIR_CUDA(cudaMemcpyAsync(o.draws + (size_t)r.b0 * P, d_u + (size_t)r.b0 * P, sizeof(double) * (size_t)r.nb * P, cudaMemcpyDeviceToDevice, gs));
   // ---- part 1: num_event_time_updates x [S->E move, E->I move, S->E occult, E->I occult] ----
   for (int rep = 0; rep < sp->num_event_time_updates; ++rep) {
     const bool last = rep + 1 == sp->num_event_time_updates;  // MultiScanKernel returns the last inner results
@@ -106,19 +118,85 @@ int seir_launch_sweep(seir_chains* c, const seir_sweep_spec* sp, unsigned sweep_
       seir_update_cfg cfg;
       slot_cfg(sp, slot, &cfg);
       const unsigned ctr = sweep_index * 64u + (unsigned)(rep * 4 + slot);
-      FOR_GROUPS(seir_launch_update_drawn(c, cfg, slot, sp->seed, sp->chain_offset, ctr, c->d_prop, c->d_logu, d_tlp,
-                                          d_upd_accept + (size_t)slot * B,
-                                          (last && d_upd_trace) ? d_upd_trace + (size_t)slot * B * 4 * SEIR_MMAX : nullptr, gs, r));
-      if (last && d_upd_tlp)
-        FOR_GROUPS(seir_cuda_check(cudaMemcpyAsync(d_upd_tlp + (size_t)slot * B + r.b0, d_tlp + r.b0, sizeof(double) * (size_t)r.nb,
-                                                   cudaMemcpyDeviceToDevice, gs), "trace copy"));
+      SEIR_TRY(seir_launch_update_drawn(c, cfg, slot, sp->seed, sp->chain_offset, ctr, c->d_prop, c->d_logu, d_tlp,
+                                        (last && o.upd_tlp) ? o.upd_tlp + (size_t)slot * B : nullptr, o.upd_accept + (size_t)slot * B,
+                                        (last && o.upd_trace) ? o.upd_trace + (size_t)slot * B * 4 * SEIR_MMAX : nullptr, gs, r));
+      SEIR_TRY(stepped());
     }
   }
-#undef FOR_GROUPS
-  if (G > 1)
+  return SEIR_OK;
+}
+
+static int sweep_prepare(seir_chains* c, int G, seir_range* rg) {
+  int rc;
+  if ((rc = sweep_alloc(c)) != SEIR_OK) return rc;
+  if ((rc = seir_hmc_workspace(c)) != SEIR_OK) return rc;
+  for (int g = 0; g < G; ++g) {
+    const int b0 = (int)((long long)c->B * g / G), b1 = (int)((long long)c->B * (g + 1) / G);
+    rg[g] = seir_range{b0, b1 - b0};
+  }
+  return G > 1 ? sweep_streams(c) : SEIR_OK;
+}
+
+int seir_launch_sweep(seir_chains* c, const seir_sweep_spec* sp, unsigned sweep_index, double* d_u, const double* d_step,
+                      const double* d_inv_mass, double* d_tlp, int* d_hmc_accept, double* d_hmc_dbg, int* d_upd_accept,
+                      double* d_upd_tlp, int* d_upd_trace, cudaStream_t s) {
+  const int G = sweep_groups(c, false);
+  seir_range rg[SEIR_MAX_GROUPS];
+  SEIR_TRY(sweep_prepare(c, G, rg));
+  const sweep_out o{d_hmc_accept, d_hmc_dbg, d_upd_accept, d_upd_tlp, d_upd_trace, nullptr};
+  if (G == 1) return enqueue_sweep(c, sp, sweep_index, rg[0], s, d_u, d_step, d_inv_mass, d_tlp, o, nullptr, 0);
+  SEIR_CUDA(cudaEventRecord(c->grp_fork, s));
+  for (int g = 0; g < G; ++g) {
+    SEIR_CUDA(cudaStreamWaitEvent(c->grp_stream[g], c->grp_fork, 0));
+    SEIR_TRY(enqueue_sweep(c, sp, sweep_index, rg[g], c->grp_stream[g], d_u, d_step, d_inv_mass, d_tlp, o, nullptr, 0));
+    SEIR_CUDA(cudaEventRecord(c->grp_join[g], c->grp_stream[g]));
+    SEIR_CUDA(cudaStreamWaitEvent(s, c->grp_join[g], 0));
+  }
+  return SEIR_OK;
+}
+
+// n sweeps with fixed step size / mass matrix; sweep k writes its results at offset k of arrays with a leading [n] axis
+// (d_hmc_accept [n][B], d_hmc_dbg [n][B][4], d_upd_accept [n][4][B], d_upd_tlp [n][5][B], d_upd_trace [n][4][B][4][MMAX],
+// d_draws [n][B][P]; the last three and d_hmc_dbg may be NULL).  Chains and traces are bit-identical to n calls of
+// seir_launch_sweep with sweep indices sweep_index0 .. sweep_index0 + n - 1.
+int seir_launch_sweep_burst(seir_chains* c, const seir_sweep_spec* sp, unsigned sweep_index0, int num_sweeps, double* d_u,
+                            const double* d_step, const double* d_inv_mass, double* d_tlp, int* d_hmc_accept, double* d_hmc_dbg,
+                            int* d_upd_accept, double* d_upd_tlp, int* d_upd_trace, double* d_draws, cudaStream_t s) {
+  const int G = sweep_groups(c, true), B = c->B, P = c->model->P;
+  seir_range rg[SEIR_MAX_GROUPS];
+  SEIR_TRY(sweep_prepare(c, G, rg));
+  static int stagger = -1;
+  if (stagger < 0) stagger = env_int("SEIR_BURST_STAGGER", 1);
+  const int steps = (sp->num_leapfrog_steps + 1) + 4 * sp->num_event_time_updates;
+  int mark_step = steps / G;
+  if (mark_step < 1) mark_step = 1;
+  auto out_of = [&](int k) {
+    return sweep_out{d_hmc_accept + (size_t)k * B,
+                     d_hmc_dbg ? d_hmc_dbg + (size_t)k * B * 4 : nullptr,
+                     d_upd_accept + (size_t)k * 4 * B,
+                     d_upd_tlp ? d_upd_tlp + (size_t)k * 5 * B : nullptr,
+                     d_upd_trace ? d_upd_trace + (size_t)k * 4 * B * 4 * SEIR_MMAX : nullptr,
+                     d_draws ? d_draws + (size_t)k * B * P : nullptr};
+  };
+  if (G == 1) {
+    for (int k = 0; k < num_sweeps; ++k)
+      SEIR_TRY(enqueue_sweep(c, sp, sweep_index0 + (unsigned)k, rg[0], s, d_u, d_step, d_inv_mass, d_tlp, out_of(k), nullptr, 0));
+    return SEIR_OK;
+  }
+  SEIR_CUDA(cudaEventRecord(c->grp_fork, s));
+  for (int g = 0; g < G; ++g) SEIR_CUDA(cudaStreamWaitEvent(c->grp_stream[g], c->grp_fork, 0));
+  // sweep by sweep ACROSS the groups, so that every stream has work queued early
+  for (int k = 0; k < num_sweeps; ++k)
     for (int g = 0; g < G; ++g) {
-      SEIR_CUDA(cudaEventRecord(c->grp_join[g], st[g]));
-      SEIR_CUDA(cudaStreamWaitEvent(s, c->grp_join[g], 0));
+      const bool mark = stagger && k == 0 && g + 1 < G;
+      if (stagger && k == 0 && g > 0) SEIR_CUDA(cudaStreamWaitEvent(c->grp_stream[g], c->grp_stagger[g - 1], 0));
+      SEIR_TRY(enqueue_sweep(c, sp, sweep_index0 + (unsigned)k, rg[g], c->grp_stream[g], d_u, d_step, d_inv_mass, d_tlp, out_of(k),
+                             mark ? c->grp_stagger[g] : nullptr, mark_step));
     }
+  for (int g = 0; g < G; ++g) {
+    SEIR_CUDA(cudaEventRecord(c->grp_join[g], c->grp_stream[g]));
+    SEIR_CUDA(cudaStreamWaitEvent(s, c->grp_join[g], 0));
+  }
   return SEIR_OK;
 }

@@ -258,6 +258,16 @@ class SeirEngine:
         nat.check(self.lib.seir_mcmc_sweep(self.chains(B), byref(spec), int(sweep_index), p(u), p(step_size), p(inv_mass), p(tlp),
                                            p(hmc_accept), p(hmc_dbg), p(upd_accept), p(upd_tlp), p(upd_trace), self._stream()))
 
+    def mcmc_burst(self, spec: "nat.SeirSweepSpec", sweep_index0, num_sweeps, u, step_size, inv_mass, tlp, hmc_accept, upd_accept,
+                   hmc_dbg=None, upd_tlp=None, upd_trace=None, draws=None):
+        """``num_sweeps`` sweeps with a fixed step size / mass matrix in one call (seir_mcmc_burst): the result tensors carry
+        a leading [num_sweeps] axis; chains and traces are bit-identical to ``num_sweeps`` calls of :meth:`mcmc_sweep`."""
+        B = u.shape[0]
+        p = lambda t: c_void_p(t.data_ptr()) if t is not None else c_void_p(0)
+        nat.check(self.lib.seir_mcmc_burst(self.chains(B), byref(spec), int(sweep_index0), int(num_sweeps), p(u), p(step_size), p(inv_mass),
+                                           p(tlp), p(hmc_accept), p(hmc_dbg), p(upd_accept), p(upd_tlp), p(upd_trace), p(draws),
+                                           self._stream()))
+
     def export_events(self, B: int) -> torch.Tensor:
         out = torch.empty((B, self.M, self.T, 3), dtype=torch.float64, device=self.device)
         nat.check(self.lib.seir_export_events(self.chains(B), c_void_p(out.data_ptr()), self._stream()))

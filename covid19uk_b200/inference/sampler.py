@@ -122,7 +122,7 @@ class ChainSet:
         return self.engine.export_events(self.B)
 
     def sample(self, num_draws, step_size, inv_mass=None, dual_averaging: DualAveraging | None = None,
-               running_variance: RunningVariance | None = None, collect_events=False, collect_draws=True):
+               running_variance: RunningVariance | None = None, collect_events=False, collect_draws=True, burst=True):
         """Run ``num_draws`` sweeps.  Returns (draws, trace): ``draws`` = [u [n,B,P], events [n,B,M,T,3] or None],
         ``trace`` = the dictionary of trace_results_fn (inference.py:245-282) with a chain axis after the draw axis."""
         B, P, dev = self.B, self.engine.P, self.engine.device
@@ -139,6 +139,27 @@ class ChainSet:
             trace[k] = {"is_accepted": torch.empty(n, B, dtype=torch.bool, device=dev),
                         "target_log_prob": torch.empty(n, B, dtype=torch.float64, device=dev),
                         "proposed_delta": torch.empty(n, B, 4, cols, dtype=torch.int32, device=dev)}
+        if n > 0 and dual_averaging is None and running_variance is None and not collect_events and burst:
+            # fixed kernel for the whole call (sample_chain over a burst, inference.py:107-117, 232-240): one C call; the
+            # chain groups stay on the library's streams for all n sweeps (sweep.cu).  Bit-identical to the loop below.
+            hmc_acc = torch.empty(n, B, dtype=torch.int32, device=dev)
+            upd_acc = torch.empty(n, 4, B, dtype=torch.int32, device=dev)
+            upd_tlp = torch.empty(n, 5, B, dtype=torch.float64, device=dev)
+            upd_trace = torch.empty(n, 4, B, 4, nat.MMAX, dtype=torch.int32, device=dev)
+            im = inv_mass.contiguous() if inv_mass is not None else None
+            self.engine.mcmc_burst(self.spec, self.sweep_index, n, self.u, step, im, self.tlp, hmc_acc, upd_acc,
+                                   upd_tlp=upd_tlp, upd_trace=upd_trace, draws=us)
+            self.sweep_index += n
+            trace["hmc"]["is_accepted"] = hmc_acc != 0
+            trace["hmc"]["target_log_prob"] = upd_tlp[:, 4]
+            trace["hmc"]["step_size"] = step.unsqueeze(0).expand(n, B).contiguous()
+            for s, k in enumerate(MOVE_KEYS):
+                cols = trace[k]["proposed_delta"].shape[-1]
+                trace[k]["is_accepted"] = upd_acc[:, s] != 0
+                trace[k]["target_log_prob"] = upd_tlp[:, s]
+                trace[k]["proposed_delta"] = upd_trace[:, s, :, :, :cols].contiguous()
+            self.last_step_size = step
+            return [us, evs], trace
         for i in range(n):
             im = running_variance.variance().contiguous() if running_variance is not None else inv_mass
             self.engine.mcmc_sweep(self.spec, self.sweep_index, self.u, step, im, self.tlp, self._hmc_acc, self._upd_acc,

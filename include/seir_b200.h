@@ -27,7 +27,7 @@
 extern "C" {
 #endif
 
-#define SEIR_B200_ABI_VERSION 7
+#define SEIR_B200_ABI_VERSION 8
 
 typedef enum seir_status {
   SEIR_OK = 0,
@@ -213,6 +213,18 @@ typedef struct seir_sweep_spec {
 int seir_mcmc_sweep(seir_chains* chains, const seir_sweep_spec* spec, uint32_t sweep_index, double* d_u,
                     const double* d_step_size, const double* d_inv_mass, double* d_tlp, int32_t* d_hmc_accept,
                     double* d_hmc_dbg, int32_t* d_upd_accept, double* d_upd_tlp, int32_t* d_upd_trace, void* stream);
+
+/* A burst of `num_sweeps` sweeps with a fixed step size and mass matrix: what tfp.mcmc.sample_chain(num_results = burst)
+ * runs between two host-side decisions (inference.py:107-117, 232-240).  Sweep k (sweep index sweep_index0 + k) writes
+ * its results at offset k of arrays with a leading [num_sweeps] axis:
+ *   d_hmc_accept [n][B];  d_hmc_dbg [n][B][4] or NULL;  d_upd_accept [n][4][B];  d_upd_tlp [n][5][B] or NULL;
+ *   d_upd_trace [n][4][B][4][4] or NULL;  d_draws [n][B][P] or NULL (u after each sweep -- the `samples` of the burst).
+ * d_u, d_tlp are in/out as in seir_mcmc_sweep.  Chains and traces are BIT-IDENTICAL to num_sweeps calls of
+ * seir_mcmc_sweep; what changes is the schedule: the chain groups run on the library's internal streams for the whole
+ * burst, staggered, so that the latency-bound discrete updates of one group overlap the HMC step of another. */
+int seir_mcmc_burst(seir_chains* chains, const seir_sweep_spec* spec, uint32_t sweep_index0, int32_t num_sweeps, double* d_u,
+                    const double* d_step_size, const double* d_inv_mass, double* d_tlp, int32_t* d_hmc_accept, double* d_hmc_dbg,
+                    int32_t* d_upd_accept, double* d_upd_tlp, int32_t* d_upd_trace, double* d_draws, void* stream);
 
 /* Current events of every chain back in the reference layout: d_events [B,M,T,3] f64. */
 int seir_export_events(seir_chains* chains, double* d_events, void* stream);

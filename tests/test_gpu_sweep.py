@@ -130,3 +130,31 @@ def test_chain_groups_on_internal_streams_match_single_stream():
     for k in acc_all:
         assert np.array_equal(trace2[k]["is_accepted"].cpu().numpy(), acc_all[k][:, 190:200])
     eng.close()
+
+
+def test_burst_equals_sweep_by_sweep_bitwise():
+    """seir_mcmc_burst (n sweeps in one call; staggered chain groups joined only at the end of the burst) against n calls of
+    seir_mcmc_sweep: same Philox positions, same per-chain arithmetic => bit-identical parameters, events, draws and traces."""
+    from covid19uk_b200.inference.sampler import ChainSet
+
+    M, T, B, n = 24, 40, 160, 4
+    pb, eng, om, u = _setup(M, T, B, seed=11)
+    cfg = dict(CFG, dmax=min(CFG["dmax"], T - 1))
+    t_range = [T - 21, T]
+    cs = ChainSet(eng, pb["events"], u, cfg, t_range, seed=17, chain_offset=0)
+    (us, _), trace = cs.sample(n, step_size=1e-3, burst=True)
+    ev, u1, tlp1 = cs.events().cpu().numpy(), cs.u.cpu().numpy().copy(), cs.tlp.cpu().numpy().copy()
+    us = us.cpu().numpy().copy()
+    tr1 = {k: {f: v.cpu().numpy().copy() for f, v in d.items()} for k, d in trace.items()}
+    assert np.array_equal(us[-1], u1)
+    cs2 = ChainSet(eng, pb["events"], u, cfg, t_range, seed=17, chain_offset=0)
+    (us2, _), trace2 = cs2.sample(n, step_size=1e-3, burst=False)
+    assert np.array_equal(cs2.u.cpu().numpy(), u1)
+    assert np.array_equal(cs2.tlp.cpu().numpy(), tlp1)
+    assert np.array_equal(cs2.events().cpu().numpy(), ev)
+    assert np.array_equal(us2.cpu().numpy(), us)
+    for k, d in trace2.items():
+        for f, v in d.items():
+            assert np.array_equal(v.cpu().numpy(), tr1[k][f]), (k, f)
+    assert tr1["hmc"]["is_accepted"].shape == (n, B) and tr1["move/S->E"]["proposed_delta"].shape[:2] == (n, B)
+    eng.close()
