@@ -254,7 +254,7 @@ def run_native(args):
     assert bool(torch.isfinite(out_d).all()), "non-finite log-prob in the benchmark workload"
 
     # ---- MCMC sweeps/s (BASELINE.json configs[2]/[3]): HMC (16 leapfrogs) + 5 x 4 discrete updates per chain,
-    #      through the public sampler (ChainSet.sample -> seir_mcmc_sweep), trace read back to the host ----
+    #      through the public sampler (ChainSet.sample -> seir_mcmc_burst), trace read back to the host ----
     from covid19uk_b200.inference.sampler import ChainSet
 
     clocks = sampler.stop() if rank == 0 else None  # (the clock sampler covers the log-prob and e2e regions; nvidia-smi is not polled below)
@@ -360,9 +360,11 @@ def run_native(args):
             "e2e": {"value": e2e_value, "unit": UNIT, "h2d_bytes_per_step": int(eng.last_h2d_bytes(B)),
                     "d2h_bytes_per_step": int(out_h.numel() * 8),
                     "host_input_bytes_per_step": int(events_h.numel() * 8 + theta_h.numel() * 8),
-                    "note": "float64 host events [B,M,T,3] in, log-prob [B] out, through seir_log_prob_host: the host pool narrows chunks "
-                            "to uint16 (exact) from the front while float64 chunks travel from the back; h2d_bytes_per_step = bytes "
-                            "actually shipped in the last timed call (the split is dynamic)"},
+                    "note": "float64 host events [B,M,T,3] in (pinned), log-prob [B] out, through seir_log_prob_host: the host pool narrows "
+                            "chunks to uint16 (exact, streaming stores) from the front while a planned number of float64 chunks travel "
+                            "from the back; early parts of the events-wide kernels run on a second stream during the transfer; "
+                            "h2d_bytes_per_step = bytes actually shipped in the last timed call (the split adapts to the measured link "
+                            "and pool rates)"},
             "gpu_launches": int(launches),
             "clocks": clocks,
             "roofline": roofline,

@@ -102,7 +102,9 @@ SIGNATURES = {
 
 
 def lib_path() -> str:
-    return _build.lib_path()
+    """In-tree ``covid19uk_b200/lib/libseir_b200.so``; ``SEIR_B200_LIB`` names another build of the same ABI (A/B timing of
+    kernel variants inside one GPU-box visit)."""
+    return os.environ.get("SEIR_B200_LIB") or _build.lib_path()
 
 
 def load():

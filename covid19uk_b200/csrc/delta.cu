@@ -20,6 +20,16 @@
 #include "delta_common.cuh"
 #include "propose.cuh"
 
+// phase timestamps of chain 7's CTA during one iteration (build with SEIR_NVCC_EXTRA=-DSEIR_UPD_DEBUG=<iteration>, read with
+// seir_debug_upd, tools/upd_phases.py)
+#ifdef SEIR_UPD_DEBUG
+__device__ long long g_upd_dbg[32];
+__device__ int g_upd_it;
+#define UTM(k) do { if (blockIdx.x == 7 && threadIdx.x == 0 && g_upd_it == SEIR_UPD_DEBUG) { long long t_; asm volatile("mov.u64 %0, %%globaltimer;" : "=l"(t_)); g_upd_dbg[k] = t_; } } while (0)
+#else
+#define UTM(k) do { } while (0)
+#endif
+
 
 // ------------------------------------------------------------------------------------------------
 // decide + commit.  accept iff log u < dll + lac  (tfp.mcmc.MetropolisHastings [recall]); on accept the point changes
@@ -129,13 +139,41 @@ struct seir_draw_args {
   uint32_t chain0, ctr;
 };
 
-__global__ void __launch_bounds__(UPD_THREADS) seir_update_prepare_kernel(
-    int M, int T, int Mp, int b0, double dt, double nu, double log_p_nu, double eps, seir_update_cfg cfg, seir_draw_args draw, int* prop,
-    double* log_u, int* nzd_all, int* yse, int* yei, const int* __restrict__ yir, int* Sx, int* Ex, int* Ix,
-    const double* __restrict__ Bc, const int* __restrict__ init, const double* __restrict__ lgtab, const double* __restrict__ pa,
-    const double* __restrict__ psiW, const double* __restrict__ pm_arr, const double* __restrict__ gam, seir_upd* upd,
-    long long* Rir, long long* sumYei, long long* sumEres, double* llc_adj, upd_outputs outs) {
-  __shared__ long long s_redl[2 * (UPD_THREADS / 32)];
+// everything an update reads or writes, for all chains (arrays that the updates themselves modify carry no __restrict__ /
+// const: inside the fused kernel below they are re-read after being written)
+struct upd_args {
+  int M, T, Mp, nchunk;
+  double dt, nu, log_p_nu, eps;
+  int* prop;       // [B][4][SEIR_MMAX] proposal records
+  double* log_u;   // [B]
+  int* nzd_all;    // [B][2][Mp]
+  int *yse, *yei;
+  const int* yir;
+  int *Sx, *Ex, *Ix;
+  double* Bc;
+  const int* init;
+  const double *lgtab, *pa, *psiW, *pm_arr, *gam, *cs;
+  const double2* logtab;  // the log-likelihood kernel's logarithm table
+  seir_upd* upd;   // [B]
+  double* part;    // [B][nchunk]
+  long long *Rir, *sumYei, *sumEres;
+  double* llc_adj;
+};
+
+// prepare: every thread of the chain's CTA calls; returns the prepared record (also left in upd[b]).
+__device__ __forceinline__ seir_upd upd_prepare(const upd_args& A, int b, const seir_update_cfg& cfg, const seir_draw_args& draw,
+                                                 bool stage_rates) {
+  const int M = A.M, T = A.T, Mp = A.Mp;
+  const double dt = A.dt, nu = A.nu, log_p_nu = A.log_p_nu, eps = A.eps;
+  int* prop = A.prop;
+  double* log_u = A.log_u;
+  int* nzd_all = A.nzd_all;
+  int *yse = A.yse, *yei = A.yei, *Sx = A.Sx, *Ex = A.Ex, *Ix = A.Ix;
+  const int* yir = A.yir;
+  const double* Bc = A.Bc;
+  const int* init = A.init;
+  const double *lgtab = A.lgtab, *pa = A.pa, *psiW = A.psiW, *pm_arr = A.pm_arr, *gam = A.gam;
+  seir_upd* upd = A.upd;
   __shared__ seir_upd s_u;
   __shared__ int s_pm[4], s_pd[4], s_pdy[4], s_npts, s_valid;
   __shared__ int s_colvalid[SEIR_MMAX], s_r3[UPD_THREADS / 32][3];
@@ -144,7 +182,7 @@ __global__ void __launch_bounds__(UPD_THREADS) seir_update_prepare_kernel(
   __shared__ int redn[UPD_THREADS / 32];
   extern __shared__ __align__(16) unsigned char dynraw[];
   __shared__ int s_sel[3];
-  const int b = b0 + blockIdx.x, tid = threadIdx.x;
+  const int tid = threadIdx.x;
   const size_t cb = (size_t)b * T * Mp;
   const chain_view g{M, T, Mp, yse + cb, yei + cb, yir + cb, Sx + cb, Ex + cb, Ix + cb, init, 0};
   const upd_smem sm = upd_smem_carve(dynraw, T, Mp);
@@ -153,12 +191,15 @@ __global__ void __launch_bounds__(UPD_THREADS) seir_update_prepare_kernel(
   const int* nzd = nzd_all + ((size_t)b * 2 + target) * Mp;
   // ---- stage: rate factors of the chain, hot-day counts, then the (at most two) metapopulation columns the proposal
   //      touches.  Everything below reads shared memory; HBM is paid in three round trips (counts, columns, lgamma table).
-  for (int t = tid; t < T; t += UPD_THREADS) {
-    sm.pa[t] = pa[(size_t)b * T + t];
-    sm.pw[t] = psiW[(size_t)b * T + t];
-    sm.gam[t] = gam[(size_t)b * T + t];
-  }
+  if (stage_rates)  // (theta does not change between the updates of one launch: staged by the first one)
+    for (int t = tid; t < T; t += UPD_THREADS) {
+      sm.pa[t] = pa[(size_t)b * T + t];
+      sm.pw[t] = psiW[(size_t)b * T + t];
+      sm.gam[t] = gam[(size_t)b * T + t];
+    }
+  UTM(1);
   const int H = sample_hot_counts(g, cfg, nzd, sm.cnt, redn);
+  UTM(2);
   if (draw.enabled) {
     if (tid < 32) sample_metapops(g, cfg, draw.seed, draw.chain0 + (uint32_t)b, draw.ctr, sm.cnt, H, pr, log_u + b, s_sel);
   } else if (tid == 0) {  // explicit record (the RNG-free path the parity tests pin)
@@ -168,6 +209,7 @@ __global__ void __launch_bounds__(UPD_THREADS) seir_update_prepare_kernel(
     s_sel[2] = 0;
   }
   __syncthreads();
+  UTM(3);
   chain_view col[2] = {g, g};
   const double* colbc[2] = {Bc + cb, Bc + cb};
   stage_columns(g, Bc + cb, s_sel, sm.col, UPD_THREADS);
@@ -178,9 +220,11 @@ __global__ void __launch_bounds__(UPD_THREADS) seir_update_prepare_kernel(
     }
   __syncthreads();
   if (draw.enabled) {
+    UTM(4);
     if (tid < 32) sample_finish(col, cfg, draw.seed, draw.chain0 + (uint32_t)b, draw.ctr, sm.cnt, s_sel, pr);
     __syncthreads();  // warp 0's global stores of the record are visible to the whole CTA
   }
+  UTM(5);
 
   if (tid == 0) {
     int valid = 1, npts = 0;
@@ -276,6 +320,7 @@ __global__ void __launch_bounds__(UPD_THREADS) seir_update_prepare_kernel(
     if (sg > 0) { qf = q_add; qr = q_del; } else { qf = q_del; qr = q_add; }
     if (!(qf > -INFINITY)) valid = 0;
   }
+  UTM(6);
   // ---- delta log-lik of the cells owned by the touched metapopulations ----
   double dll = 0.0, dllc = 0.0;
   int neg = 0;
@@ -319,6 +364,7 @@ __global__ void __launch_bounds__(UPD_THREADS) seir_update_prepare_kernel(
       }
     }
   }
+  UTM(7);
   // one combined block reduction of (dll, dllc, neg), fixed order
   dll = warp_sum(dll);
   dllc = warp_sum(dllc);
@@ -336,111 +382,26 @@ __global__ void __launch_bounds__(UPD_THREADS) seir_update_prepare_kernel(
     upd[b] = u;
     s_u = u;
   }
-  if (target == 1) return;  // E->I: the force of infection changes too -> slab kernel, then seir_update_commit_kernel
-  // S->E: everything the decision needs is here: decide and commit in place (one launch per update)
   __syncthreads();  // s_u published; every read of the caches above is complete
-  const seir_upd u = s_u;
-  double dll_tot;
-  const int acc = upd_decide(u, 0, 0, nullptr, log_u[b], &dll_tot);
-  upd_commit_rows<UPD_THREADS>(b, T, Mp, cfg, u, acc, dll_tot, log_u[b], upd, prop, yse, yei, Sx, Ex, Ix, Rir, sumYei, sumEres, llc_adj,
-                               nzd_all, outs, s_redl);
+  return s_u;
 }
 
 // ------------------------------------------------------------------------------------------------
 // slab (target = E->I only): the infectious count of the touched metapopulations changes by dI on some
 // days => Bc'[i] = Bc[i] + sum_g Cs[m_g][i] dI_g and new S->E terms for every metapopulation i.
-// grid = (chains, day chunks); warp <-> day, lanes sweep metapopulations (coalesced day slabs).
+// warp <-> day, lanes sweep metapopulations (coalesced day slabs); one value per day, then one
+// partial per chunk of SLAB_DAYS days (summed over its days in day order, then over chunks in chunk order by upd_decide: the order of
+// every floating-point sum is fixed by T alone).
 // ------------------------------------------------------------------------------------------------
-__global__ void __launch_bounds__(32 * SLAB_DAYS) seir_update_slab_kernel(
-    int M, int T, int Mp, int b0, double dt, double eps, int kind, const seir_upd* __restrict__ upd, const int* __restrict__ yse,
-    const int* __restrict__ Sx, const int* __restrict__ Ix, const double* __restrict__ Bc, const double* __restrict__ cs,
-    const double* __restrict__ pa, const double* __restrict__ psiW, const double* __restrict__ pm_arr, double* __restrict__ part) {
-  __shared__ double red[SLAB_DAYS];
-  const int b = b0 + blockIdx.x, lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
-  const seir_upd u = upd[b];
-  const int s = blockIdx.y * SLAB_DAYS + warp;
-  double acc = 0.0;
-  const bool go = u.valid && !u.neg;
-  if (go && u.npts > 0 && s < T) {
-    const int ngroups = kind == 0 ? u.npts / 2 : 1;
-    int gm[2];
-    double gd[2];
-    bool any = false;
-    for (int g = 0; g < 2; ++g) {
-      gm[g] = 0; gd[g] = 0.0;
-      if (g < ngroups) {
-        const int p0 = kind == 0 ? 2 * g : 0, np = kind == 0 ? 2 : 1;
-        int d = 0;
-        for (int p = p0; p < p0 + np; ++p)
-          if (u.pd[p] < s) d += u.pdy[p];
-        gm[g] = u.pm[p0];
-        gd[g] = (double)d;  // I is the destination compartment of E->I: +dcum
-        any |= d != 0;
-      }
-    }
-    if (any) {
-      const size_t base = ((size_t)b * T + s) * Mp;
-      const double pas = pa[(size_t)b * T + s], pws = psiW[(size_t)b * T + s];
-      for (int i = lane; i < Mp; i += 32) {
-        const double bc = Bc[base + i];
-        double bcn = bc;
-        double dIi = 0.0;
-#pragma unroll
-        for (int g = 0; g < 2; ++g) {
-          bcn = fma(cs[(size_t)gm[g] * Mp + i], gd[g], bcn);
-          if (i == gm[g]) dIi += gd[g];
-        }
-        if (i < M) {
-          const int y = yse[base + i], S = Sx[base + i];
-          const double I = (double)Ix[base + i];
-          const double e = pas * pm_arr[(size_t)b * Mp + i];
-          const double x0 = fma(e, I + pws * bc, eps) * dt;
-          const double x1 = fma(e, I + dIi + pws * bcn, eps) * dt;
-          double term = -(double)(S - y) * (x1 - x0);
-          if (y > 0) term += (double)y * (log1mexp_neg(x1) - log1mexp_neg(x0));
-          acc += term;
-        }
-      }
-    }
-  }
-  acc = warp_sum(acc);
-  if (lane == 0) red[warp] = acc;
-  __syncthreads();
-  if (threadIdx.x == 0) {
-    double r = 0.0;
-    for (int w = 0; w < SLAB_DAYS; ++w) r += red[w];
-    part[(size_t)b * gridDim.y + blockIdx.y] = r;
-  }
-}
 
-// E->I commit in ONE launch: grid (chains, 1 + day chunks), 32*SLAB_DAYS threads.  Every CTA takes the MH decision
-// itself (same inputs, same order => same answer); CTA y = 0 commits the rows, CTA y >= 1 the Bc slabs of its chunk.
-__global__ void __launch_bounds__(32 * SLAB_DAYS) seir_update_commit_kernel(
-    int M, int T, int Mp, int b0, seir_update_cfg cfg, int nchunk, seir_upd* upd, const double* __restrict__ part,
-    const double* __restrict__ log_u, const int* __restrict__ prop, int* yse, int* yei, int* Sx, int* Ex, int* Ix, double* Bc,
-    const double* __restrict__ cs, long long* Rir, long long* sumYei, long long* sumEres, double* llc_adj, int* nzd_all, upd_outputs o) {
-  __shared__ long long redl[2 * SLAB_DAYS];
-  const int b = b0 + blockIdx.x;
-  const seir_upd u = upd[b];
-  double dll;
-  const int acc = upd_decide(u, cfg.target, nchunk, part + (size_t)b * nchunk, log_u[b], &dll);
-  if (blockIdx.y == 0) {
-    upd_commit_rows<32 * SLAB_DAYS>(b, T, Mp, cfg, u, acc, dll, log_u[b], upd, prop, yse, yei, Sx, Ex, Ix, Rir, sumYei, sumEres, llc_adj,
-                                    nzd_all, o, redl);
-    return;
-  }
-  if (!acc || u.npts == 0) return;
-  const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
-  const int s = (blockIdx.y - 1) * SLAB_DAYS + warp;
-  if (s >= T) return;
-  const int ngroups = cfg.kind == 0 ? u.npts / 2 : 1;
-  int gm[2];
-  double gd[2];
+// change of I on day s for the (at most two) touched metapopulations; false when the day is untouched
+__device__ __forceinline__ bool upd_day_shift(const seir_upd& u, int kind, int s, int* gm, double* gd) {
+  const int ngroups = kind == 0 ? u.npts / 2 : 1;
   bool any = false;
   for (int g = 0; g < 2; ++g) {
     gm[g] = 0; gd[g] = 0.0;
     if (g < ngroups) {
-      const int p0 = cfg.kind == 0 ? 2 * g : 0, np = cfg.kind == 0 ? 2 : 1;
+      const int p0 = kind == 0 ? 2 * g : 0, np = kind == 0 ? 2 : 1;
       int d = 0;
       for (int p = p0; p < p0 + np; ++p)
         if (u.pd[p] < s) d += u.pdy[p];
@@ -449,45 +410,211 @@ __global__ void __launch_bounds__(32 * SLAB_DAYS) seir_update_commit_kernel(
       any |= d != 0;
     }
   }
-  if (!any) return;
-  const size_t base = ((size_t)b * T + s) * Mp;
-  for (int i = lane; i < Mp; i += 32) {
-    double bcn = Bc[base + i];
+  return any;
+}
+
+__device__ __forceinline__ void upd_slab(const upd_args& A, int b, int kind, const seir_upd& u, double* day_acc, const double2* logtab) {
+  const int M = A.M, T = A.T, Mp = A.Mp, lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+  const bool go = u.valid && !u.neg && u.npts > 0;
+  // warp <-> day, round robin: the touched days are one or two contiguous ranges, so they spread evenly over the warps;
+  // untouched days cost a few integer instructions and no memory access.  One value per day, no barrier inside.
+  for (int s = warp; s < T; s += UPD_THREADS / 32) {
+    double acc = 0.0;
+    int gm[2];
+    double gd[2];
+    if (go && upd_day_shift(u, kind, s, gm, gd)) {
+      const size_t base = ((size_t)b * T + s) * Mp;
+      const double pas = A.pa[(size_t)b * T + s], pws = A.psiW[(size_t)b * T + s];
+      // four cells per lane at a time: the 7 x 4 loads are issued before any of them is consumed (one round trip to
+      // HBM/L2 instead of four -- the loop was latency-bound at ~1.2 us per cell, tools/upd_phases.py); the terms are
+      // still added in metapopulation order
+      const double* cs0 = A.cs + (size_t)gm[0] * Mp;
+      const double* cs1 = A.cs + (size_t)gm[1] * Mp;
+      const double* pmb = A.pm_arr + (size_t)b * Mp;
+      for (int i0 = lane; i0 < Mp; i0 += 128) {
+        double bc[4], c0[4], c1[4], pmv[4];
+        int yv[4], Sv[4], Iv[4];
 #pragma unroll
-    for (int g = 0; g < 2; ++g) bcn = fma(cs[(size_t)gm[g] * Mp + i], gd[g], bcn);
-    Bc[base + i] = bcn;
+        for (int k = 0; k < 4; ++k) {
+          const int i = i0 + 32 * k;
+          const bool in = i < Mp;
+          bc[k] = in ? A.Bc[base + i] : 0.0;
+          c0[k] = in ? cs0[i] : 0.0;
+          c1[k] = in ? cs1[i] : 0.0;
+          const bool inM = i < M;
+          yv[k] = inM ? A.yse[base + i] : 0;
+          Sv[k] = inM ? A.Sx[base + i] : 0;
+          Iv[k] = inM ? A.Ix[base + i] : 0;
+          pmv[k] = inM ? pmb[i] : 0.0;
+        }
+#pragma unroll
+        for (int k = 0; k < 4; ++k) {
+          const int i = i0 + 32 * k;
+          if (i < M) {
+            double bcn = fma(c0[k], gd[0], bc[k]);
+            bcn = fma(c1[k], gd[1], bcn);
+            double dIi = 0.0;
+            if (i == gm[0]) dIi += gd[0];
+            if (i == gm[1]) dIi += gd[1];
+            const int y = yv[k], S = Sv[k];
+            const double I = (double)Iv[k];
+            const double e = pas * pmv[k];
+            const double x0 = fma(e, I + pws * bc[k], A.eps) * A.dt;
+            const double x1 = fma(e, I + dIi + pws * bcn, A.eps) * A.dt;
+            double term = -(double)(S - y) * (x1 - x0);
+            if (y > 0) term += (double)y * (log1mexp_neg_tab(x1, logtab) - log1mexp_neg_tab(x0, logtab));
+            acc += term;
+          }
+        }
+      }
+      acc = warp_sum(acc);
+    }
+    if (lane == 0) day_acc[s] = acc;
   }
+  __syncthreads();
+  for (int c = threadIdx.x; c < A.nchunk; c += UPD_THREADS) {  // chunk partials: days in day order
+    double r = 0.0;
+    for (int w = 0; w < SLAB_DAYS; ++w) {
+      const int s = c * SLAB_DAYS + w;
+      if (s < T) r += day_acc[s];
+    }
+    A.part[(size_t)b * A.nchunk + c] = r;
+  }
+  __syncthreads();
+}
+
+// accepted E->I change: Bc'[i] = Bc[i] + sum_g Cs[m_g][i] dI_g on the affected day slabs
+__device__ __forceinline__ void upd_commit_slabs(const upd_args& A, int b, int kind, const seir_upd& u) {
+  const int T = A.T, Mp = A.Mp, lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+  for (int s = warp; s < T; s += UPD_THREADS / 32) {
+    int gm[2];
+    double gd[2];
+    if (!upd_day_shift(u, kind, s, gm, gd)) continue;
+    const size_t base = ((size_t)b * T + s) * Mp;
+    const double* cs0 = A.cs + (size_t)gm[0] * Mp;
+    const double* cs1 = A.cs + (size_t)gm[1] * Mp;
+    for (int i0 = lane; i0 < Mp; i0 += 128) {  // (loads of four cells in flight together)
+      double bc[4], c0[4], c1[4];
+#pragma unroll
+      for (int k = 0; k < 4; ++k) {
+        const int i = i0 + 32 * k;
+        const bool in = i < Mp;
+        bc[k] = in ? A.Bc[base + i] : 0.0;
+        c0[k] = in ? cs0[i] : 0.0;
+        c1[k] = in ? cs1[i] : 0.0;
+      }
+#pragma unroll
+      for (int k = 0; k < 4; ++k) {
+        const int i = i0 + 32 * k;
+        if (i < Mp) A.Bc[base + i] = fma(c1[k], gd[1], fma(c0[k], gd[0], bc[k]));
+      }
+    }
+  }
+}
+
+// ------------------------------------------------------------------------------------------------
+// The update kernel: one CTA per chain runs `nit` updates back to back -- a single one (seir_update_step: explicit or
+// drawn proposal) or the whole discrete half of a sweep, num_event_time_updates x [S->E move, E->I move, S->E occult,
+// E->I occult] (mcmc_kernel_factory.py:116-168) -- each: prepare, (E->I: slab partials,) MH decision, in-place commit.
+// The 20 updates of a UK sweep were 40 launches of one-CTA-per-chain kernels, each paying its launch, a cold
+// instruction cache and its round trips to HBM on a chain of dependent loads, with the SMs idle in between
+// (profiles/r01_v7_*: 1.08 of 2.3 ms per sweep); inside one launch the chain's state stays in L1/L2 between updates.
+// Everything an update changes is written through global memory and re-read after a CTA barrier; the event-day counts
+// are bumped with atomics (L2) and therefore read with __ldcg.
+// ------------------------------------------------------------------------------------------------
+struct upd_plan {
+  int nit;          // updates to run
+  int single_slot;  // >= 0: every iteration is this slot (nit == 1); < 0: slot = it % 4, repetition = it / 4
+  int nreps, B;
+  seir_update_cfg cfg[4];
+  seir_draw_args draw;  // draw.ctr: stream position of iteration 0 (iteration it uses ctr + it)
+  double* tlp;          // [B] running target log-prob
+  int* upd_accept;      // [4][B] (single: [B])
+  double* upd_tlp;      // [4..][B] or NULL: written by the last repetition
+  int* upd_trace;       // [4][B][4][SEIR_MMAX] or NULL: written by the last repetition
+  int* last_acc;        // [4][B][4][SEIR_MMAX]
+  double* dbg;          // single updates only
+};
+
+__global__ void __launch_bounds__(UPD_THREADS, 2) seir_update_kernel(upd_args A, upd_plan P, int b0) {
+  __shared__ long long s_redl[2 * (UPD_THREADS / 32)];
+  extern __shared__ __align__(16) unsigned char dynraw[];
+  double* day_acc = reinterpret_cast<double*>(dynraw + (upd_smem_bytes(A.T, A.Mp) + 15) / 16 * 16);  // [T], after the prepare phase's carve-up
+  __shared__ double2 s_logtab[128];
+  for (int k = threadIdx.x; k < 128; k += UPD_THREADS) s_logtab[k] = A.logtab[k];
+  __syncthreads();
+  const int b = b0 + blockIdx.x, B = P.B;
+  for (int it = 0; it < P.nit; ++it) {
+    const bool single = P.single_slot >= 0;
+    const int slot = single ? P.single_slot : (it & 3);
+    const bool last = single || (it >> 2) + 1 == P.nreps;  // MultiScanKernel returns the last inner results
+    const seir_update_cfg cfg = P.cfg[slot];
+    seir_draw_args draw = P.draw;
+    draw.ctr += (uint32_t)it;
+    const size_t so = single ? 0 : (size_t)slot * B;
+    const upd_outputs o{P.tlp, (last && P.upd_tlp) ? P.upd_tlp + so : nullptr, P.upd_accept + so,
+                        P.last_acc + (size_t)slot * B * 4 * SEIR_MMAX, (last && P.upd_trace) ? P.upd_trace + so * 4 * SEIR_MMAX : nullptr, P.dbg};
+#ifdef SEIR_UPD_DEBUG
+    if (blockIdx.x == 7 && threadIdx.x == 0) g_upd_it = it;
+#endif
+    UTM(0);
+    const seir_upd u = upd_prepare(A, b, cfg, draw, it == 0);
+    UTM(8);
+    if (cfg.target == 1) upd_slab(A, b, cfg.kind, u, day_acc, s_logtab);
+    UTM(9);  // (ends with a CTA barrier: the partials are visible)
+    double dll;
+    const double lu = A.log_u[b];
+    const int acc = upd_decide(u, cfg.target, A.nchunk, A.part + (size_t)b * A.nchunk, lu, &dll);
+    upd_commit_rows<UPD_THREADS>(b, A.T, A.Mp, cfg, u, acc, dll, lu, A.upd, A.prop, A.yse, A.yei, A.Sx, A.Ex, A.Ix, A.Rir, A.sumYei, A.sumEres,
+                                 A.llc_adj, A.nzd_all, o, s_redl);
+    UTM(10);
+    if (cfg.target == 1 && acc && u.npts > 0) upd_commit_slabs(A, b, cfg.kind, u);
+    __syncthreads();  // the next update reads what this one wrote
+    UTM(11);
+#ifdef SEIR_UPD_DEBUG
+    if (blockIdx.x == 7 && threadIdx.x == 0 && it == SEIR_UPD_DEBUG) { g_upd_dbg[12] = acc; g_upd_dbg[13] = u.npts; g_upd_dbg[14] = u.valid; }
+#endif
+  }
+}
+
+#ifdef SEIR_UPD_DEBUG
+extern "C" int seir_debug_upd(long long* h) { return (int)cudaMemcpyFromSymbol(h, g_upd_dbg, sizeof(long long) * 32); }
+#endif
+
+static upd_args make_upd_args(seir_chains* c, int* d_proposal, double* d_log_u) {
+  const seir_model* m = c->model;
+  upd_args A;
+  A.M = m->M; A.T = m->T; A.Mp = m->Mp; A.nchunk = (m->T + SLAB_DAYS - 1) / SLAB_DAYS;
+  A.dt = m->dt; A.nu = m->nu; A.log_p_nu = m->log_p_nu; A.eps = m->rate_eps;
+  A.prop = d_proposal; A.log_u = d_log_u; A.nzd_all = c->d_nzd;
+  A.yse = c->d_yse; A.yei = c->d_yei; A.yir = c->d_yir; A.Sx = c->d_S; A.Ex = c->d_E; A.Ix = c->d_I; A.Bc = c->d_Bc;
+  A.init = m->d_init; A.lgtab = m->d_lgtab; A.pa = c->d_pa; A.psiW = c->d_psiW; A.pm_arr = c->d_pm; A.gam = c->d_gam; A.cs = m->d_cs; A.logtab = m->d_logtab;
+  A.upd = c->d_upd; A.part = c->d_upd_part; A.Rir = c->d_Rir; A.sumYei = c->d_sumYei; A.sumEres = c->d_sumEres; A.llc_adj = c->d_llc_adj;
+  return A;
+}
+
+static int launch_update_kernel(seir_chains* c, const upd_args& A, const upd_plan& P, cudaStream_t s, seir_range r) {
+  const size_t smem = (upd_smem_bytes(A.T, A.Mp) + 15) / 16 * 16 + sizeof(double) * A.T;
+  static size_t attr = 0;
+  if (smem > 48 * 1024 && attr != smem) {
+    SEIR_CUDA(cudaFuncSetAttribute(seir_update_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+    attr = smem;
+  }
+  seir_update_kernel<<<r.nb, UPD_THREADS, smem, s>>>(A, P, r.b0);
+  seir_count_launch(1);
+  return seir_cuda_check(cudaGetLastError(), "seir_update_kernel");
 }
 
 static int launch_update(seir_chains* c, const seir_update_cfg& cfg, int slot, const seir_draw_args& draw, int* d_proposal,
                          double* d_log_u, double* d_tlp, double* d_tlp_trace, int* d_accept, int* d_trace, double* d_dbg, cudaStream_t s,
                          seir_range r) {
-  const seir_model* m = c->model;
-  const int B = c->B, T = m->T, Mp = m->Mp;
-  const int nchunk = (T + SLAB_DAYS - 1) / SLAB_DAYS;
-  const upd_outputs outs{d_tlp, d_tlp_trace, d_accept, c->d_last_acc + (size_t)slot * B * 4 * SEIR_MMAX, d_trace, d_dbg};
-  const size_t smem = upd_smem_bytes(T, Mp);
-  static size_t attr = 0;
-  if (smem > 48 * 1024 && attr != smem) {
-    SEIR_CUDA(cudaFuncSetAttribute(seir_update_prepare_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
-    attr = smem;
-  }
-  seir_update_prepare_kernel<<<r.nb, UPD_THREADS, smem, s>>>(
-      m->M, T, Mp, r.b0, m->dt, m->nu, m->log_p_nu, m->rate_eps, cfg, draw, d_proposal, d_log_u, c->d_nzd, c->d_yse, c->d_yei, c->d_yir, c->d_S,
-      c->d_E, c->d_I, c->d_Bc, m->d_init, m->d_lgtab, c->d_pa, c->d_psiW, c->d_pm, c->d_gam, c->d_upd, c->d_Rir, c->d_sumYei,
-      c->d_sumEres, c->d_llc_adj, outs);
-  int launches = 1;
-  if (cfg.target == 1) {
-    seir_update_slab_kernel<<<dim3(r.nb, nchunk), 32 * SLAB_DAYS, 0, s>>>(m->M, T, Mp, r.b0, m->dt, m->rate_eps, cfg.kind, c->d_upd, c->d_yse, c->d_S,
-                                                                      c->d_I, c->d_Bc, m->d_cs, c->d_pa, c->d_psiW, c->d_pm, c->d_upd_part);
-    seir_update_commit_kernel<<<dim3(r.nb, 1 + nchunk), 32 * SLAB_DAYS, 0, s>>>(m->M, T, Mp, r.b0, cfg, nchunk, c->d_upd, c->d_upd_part, d_log_u,
-                                                                            d_proposal, c->d_yse, c->d_yei, c->d_S, c->d_E, c->d_I, c->d_Bc,
-                                                                            m->d_cs, c->d_Rir, c->d_sumYei, c->d_sumEres, c->d_llc_adj,
-                                                                            c->d_nzd, outs);
-    launches += 2;
-  }
-  seir_count_launch(launches);
-  return seir_cuda_check(cudaGetLastError(), "seir_update kernels");
+  const upd_args A = make_upd_args(c, d_proposal, d_log_u);
+  upd_plan P;
+  P.nit = 1; P.single_slot = slot; P.nreps = 1; P.B = c->B;
+  P.cfg[slot] = cfg;
+  P.draw = draw;
+  P.tlp = d_tlp; P.upd_accept = d_accept; P.upd_tlp = d_tlp_trace; P.upd_trace = d_trace; P.last_acc = c->d_last_acc; P.dbg = d_dbg;
+  return launch_update_kernel(c, A, P, s, r);
 }
 
 // explicit proposal + log u (the RNG-free path the parity tests pin)
@@ -498,12 +625,27 @@ int seir_launch_update(seir_chains* c, const seir_update_cfg& cfg, int slot, con
                        d_dbg, s, seir_all(c));
 }
 
-// proposal and log u drawn inside the prepare kernel (fused sweep); the record is left in d_proposal / d_log_u
+// proposal and log u drawn inside the kernel; the record is left in d_proposal / d_log_u
 int seir_launch_update_drawn(seir_chains* c, const seir_update_cfg& cfg, int slot, unsigned long long seed, unsigned chain0,
                              unsigned ctr, int* d_proposal, double* d_log_u, double* d_tlp, double* d_tlp_trace, int* d_accept,
                              int* d_trace, cudaStream_t s, seir_range r) {
   const seir_draw_args draw{1, seed, chain0, ctr};
   return launch_update(c, cfg, slot, draw, d_proposal, d_log_u, d_tlp, d_tlp_trace, d_accept, d_trace, nullptr, s, r);
+}
+
+// the discrete half of a sweep in ONE launch: nreps x [slot 0, 1, 2, 3], iteration it at stream position ctr0 + it;
+// d_upd_accept [4][B], d_upd_tlp [>= 4][B] or NULL, d_upd_trace [4][B][4][SEIR_MMAX] or NULL (last repetition)
+int seir_launch_update_rounds(seir_chains* c, const seir_update_cfg* cfg4, int nreps, unsigned long long seed, unsigned chain0,
+                              unsigned ctr0, int* d_proposal, double* d_log_u, double* d_tlp, int* d_upd_accept, double* d_upd_tlp,
+                              int* d_upd_trace, cudaStream_t s, seir_range r) {
+  if (nreps <= 0) return SEIR_OK;
+  const upd_args A = make_upd_args(c, d_proposal, d_log_u);
+  upd_plan P;
+  P.nit = 4 * nreps; P.single_slot = -1; P.nreps = nreps; P.B = c->B;
+  for (int k = 0; k < 4; ++k) P.cfg[k] = cfg4[k];
+  P.draw = seir_draw_args{1, seed, chain0, ctr0};
+  P.tlp = d_tlp; P.upd_accept = d_upd_accept; P.upd_tlp = d_upd_tlp; P.upd_trace = d_upd_trace; P.last_acc = c->d_last_acc; P.dbg = nullptr;
+  return launch_update_kernel(c, A, P, s, r);
 }
 
 // ------------------------------------------------------------------------------------------------

@@ -5,7 +5,9 @@
 
 #include "seir_internal.cuh"
 
-#define UPD_THREADS 128
+#ifndef UPD_THREADS
+#define UPD_THREADS 256  // one CTA per chain (measured: 256 threads 2.12-2.29 ms per UK sweep, 512 threads 2.26-2.30 ms)
+#endif
 #define SLAB_DAYS 8
 
 // A chain's day-slab caches, or ONE metapopulation column of them staged in shared memory: element (s, m) lives at
@@ -31,7 +33,7 @@ struct col_stage {
 // Both columns at once: thread <-> day; the 14 strided loads of a thread (2 columns x (6 integer rows + the contraction
 // row)) are issued back to back BEFORE any of them is consumed -- one round trip to HBM.  (A copy loop that stores each
 // value as it arrives keeps a single load in flight per thread: measured 9.4 us for two columns, profiles/r01_v7_*.)
-__device__ __forceinline__ void stage_columns(const chain_view& g, const double* __restrict__ Bc_chain, const int* sel, const col_stage* c,
+__device__ __forceinline__ void stage_columns(const chain_view& g, const double* Bc_chain, const int* sel, const col_stage* c,
                                               int nthr) {
   const int T = g.T, tid = threadIdx.x;
   const bool has[2] = {sel[0] >= 0, sel[1] >= 0};

@@ -27,13 +27,13 @@
 // ---- phase A: cnt[m] = days with target events (moves: whole series, cached; occults: inside the window) --------------
 // Every thread of the CTA calls; returns H = metapopulations with cnt > 0 (valid in every thread; its barriers publish
 // cnt[]).  `redw`: shared int [nthr/32].
-__device__ __forceinline__ int sample_hot_counts(const chain_view& g, const seir_update_cfg& cfg, const int* __restrict__ nzd, int* cnt,
+__device__ __forceinline__ int sample_hot_counts(const chain_view& g, const seir_update_cfg& cfg, const int* nzd, int* cnt,
                                                  int* redw) {
   const int Mp = g.Mp, tid = threadIdx.x, nthr = blockDim.x;
   int hot = 0;
   if (cfg.kind == 0) {
     for (int m = tid; m < Mp; m += nthr) {
-      const int c = m < g.M ? nzd[m] : 0;  // maintained by ingest / commit
+      const int c = m < g.M ? __ldcg(nzd + m) : 0;  // maintained by ingest / commit (atomics: read at the L2)
       cnt[m] = c;
       hot += c > 0;
     }
@@ -198,8 +198,8 @@ __device__ __forceinline__ upd_smem upd_smem_carve(unsigned char* raw, int T, in
 
 // All phases in one call (seir_propose_kernel): every thread of the CTA calls; sel: shared int[3]; the record and log u
 // are written by warp 0 -- callers that read them afterwards need a __syncthreads() of their own.
-__device__ __forceinline__ void seir_sample_proposal(const chain_view& g, const double* __restrict__ Bc_chain, const seir_update_cfg& cfg,
-                                                     uint64_t seed, uint32_t chain, uint32_t ctr, const int* __restrict__ nzd,
+__device__ __forceinline__ void seir_sample_proposal(const chain_view& g, const double* Bc_chain, const seir_update_cfg& cfg,
+                                                     uint64_t seed, uint32_t chain, uint32_t ctr, const int* nzd,
                                                      const upd_smem& sm, int* redw, int* sel, int* pr, double* log_u_out) {
   const int H = sample_hot_counts(g, cfg, nzd, sm.cnt, redw);
   if (threadIdx.x < 32) sample_metapops(g, cfg, seed, chain, ctr, sm.cnt, H, pr, log_u_out, sel);

@@ -221,6 +221,10 @@ int seir_launch_update_drawn(seir_chains* c, const seir_update_cfg& cfg, int slo
                              unsigned ctr, int* d_proposal, double* d_log_u, double* d_tlp, double* d_tlp_trace, int* d_accept,
                              int* d_trace, cudaStream_t s, seir_range r);
 
+int seir_launch_update_rounds(seir_chains* c, const seir_update_cfg* cfg4, int nreps, unsigned long long seed, unsigned chain0,
+                              unsigned ctr0, int* d_proposal, double* d_log_u, double* d_tlp, int* d_upd_accept, double* d_upd_tlp,
+                              int* d_upd_trace, cudaStream_t s, seir_range r);
+
 // ---- device helpers ---------------------------------------------------------------------------
 #ifdef __CUDACC__
 
@@ -299,6 +303,27 @@ __device__ __forceinline__ double log1mexp_neg(double x) {
     return log(x) + fma(x2, fma(x2, fma(x2, 5.511463844797178e-06, -3.472222222222222e-04), 0.041666666666666664), -0.5 * x);
   }
   return log(-expm1(-x));
+}
+
+// log(1 - exp(-x)) with the log-likelihood kernel's table-driven logarithm (loglik.cu: 128-bucket range reduction +
+// degree-7 log1p, ~25 FP64 operations instead of ~55); `tab` = the model's d_logtab (128 x {1/c rounded, -log(1/c rounded)}),
+// usually staged in shared memory.  Positive normal x < 0.05 only; everything else takes log1mexp_neg.
+__device__ __forceinline__ double log1mexp_neg_tab(double x, const double2* tab) {
+  const int hi = __double2hiint(x), lo = __double2loint(x);
+  if (!((hi >= 0x00100000) & (x < SEIR_SMALL_X))) return log1mexp_neg(x);
+  const int ex = (hi >> 20) - 1023;
+  const double m = __hiloint2double((hi & 0x000fffff) | 0x3ff00000, lo);
+  const double2 tc = tab[(hi >> 13) & 127];
+  const double r = fma(m, tc.x, -1.0), r2 = r * r;
+  double p = fma(r, 0.14285714285714285, -0.16666666666666666);
+  p = fma(r, p, 0.2);
+  p = fma(r, p, -0.25);
+  p = fma(r, p, 0.3333333333333333);
+  p = fma(r, p, -0.5);
+  const double ed = __hiloint2double(0x43300000, ex ^ 0x80000000) - 4503601774854144.0;  // exact int -> double
+  const double lg = fma(ed, 0.6931471805599453, tc.y) + fma(r2, p, r);
+  const double x2 = x * x;
+  return lg + fma(x2, fma(x2, fma(x2, 5.511463844797178e-06, -3.472222222222222e-04), 0.041666666666666664), -0.5 * x);
 }
 
 #endif  // __CUDACC__

@@ -89,7 +89,7 @@ struct sweep_out {
   double* draws;      // [B][P]: u after the sweep
 };
 
-// One sweep of the chains in r, enqueued on gs.  The sweep is a sequence of (L + 1) + 4 * reps steps; after step
+// One sweep of the chains in r, enqueued on gs.  The sweep is a sequence of (L + 1) + 1 steps (leapfrogs, updates); after step
 // `mark_step` (counted from 1) the event `mark` is recorded on gs (burst stagger), if given.
 static int enqueue_sweep(seir_chains* c, const seir_sweep_spec* sp, unsigned sweep_index, seir_range r, cudaStream_t gs, double* d_u,
                          const double* d_step, const double* d_inv_mass, double* d_tlp, const sweep_out& o, cudaEvent_t mark, int mark_step) {
@@ -111,19 +111,12 @@ static int enqueue_sweep(seir_chains* c, const seir_sweep_spec* sp, unsigned swe
   }
   if (o.draws)  // u changes in the HMC step only
     SEIR_CUDA(cudaMemcpyAsync(o.draws + (size_t)r.b0 * P, d_u + (size_t)r.b0 * P, sizeof(double) * (size_t)r.nb * P, cudaMemcpyDeviceToDevice, gs));
-  // ---- part 1: num_event_time_updates x [S->E move, E->I move, S->E occult, E->I occult] ----
-  for (int rep = 0; rep < sp->num_event_time_updates; ++rep) {
-    const bool last = rep + 1 == sp->num_event_time_updates;  // MultiScanKernel returns the last inner results
-    for (int slot = 0; slot < 4; ++slot) {
-      seir_update_cfg cfg;
-      slot_cfg(sp, slot, &cfg);
-      const unsigned ctr = sweep_index * 64u + (unsigned)(rep * 4 + slot);
-      SEIR_TRY(seir_launch_update_drawn(c, cfg, slot, sp->seed, sp->chain_offset, ctr, c->d_prop, c->d_logu, d_tlp,
-                                        (last && o.upd_tlp) ? o.upd_tlp + (size_t)slot * B : nullptr, o.upd_accept + (size_t)slot * B,
-                                        (last && o.upd_trace) ? o.upd_trace + (size_t)slot * B * 4 * SEIR_MMAX : nullptr, gs, r));
-      SEIR_TRY(stepped());
-    }
-  }
+  // ---- part 1: num_event_time_updates x [S->E move, E->I move, S->E occult, E->I occult], one launch ----
+  seir_update_cfg cfg4[4];
+  for (int slot = 0; slot < 4; ++slot) slot_cfg(sp, slot, &cfg4[slot]);
+  SEIR_TRY(seir_launch_update_rounds(c, cfg4, sp->num_event_time_updates, sp->seed, sp->chain_offset, sweep_index * 64u, c->d_prop, c->d_logu,
+                                     d_tlp, o.upd_accept, o.upd_tlp, o.upd_trace, gs, r));
+  SEIR_TRY(stepped());
   return SEIR_OK;
 }
 
@@ -168,7 +161,7 @@ int seir_launch_sweep_burst(seir_chains* c, const seir_sweep_spec* sp, unsigned 
   SEIR_TRY(sweep_prepare(c, G, rg));
   static int stagger = -1;
   if (stagger < 0) stagger = env_int("SEIR_BURST_STAGGER", 1);
-  const int steps = (sp->num_leapfrog_steps + 1) + 4 * sp->num_event_time_updates;
+  const int steps = (sp->num_leapfrog_steps + 1) + 1;
   int mark_step = steps / G;
   if (mark_step < 1) mark_step = 1;
   auto out_of = [&](int k) {
