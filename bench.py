@@ -44,11 +44,16 @@ def _traffic(kernel_name):
         return None
     with open(path) as f:
         ks = json.load(f)["kernels"]
-    base = kernel_name.split("<")[0]
-    for k, v in ks.items():
-        if k.split("<")[0] == base:
-            return v["dram_bytes_per_launch"]
-    return None
+    total, found = 0.0, False
+    for part in kernel_name.replace("(+", "+").replace(")", "").split("+"):  # "a (+ b)" = the kernels of one stage
+        base = part.strip().split("<")[0]
+        base = {"seir_coef_kernel": "seir_coef_tma_kernel", "seir_loglik_kernel": "seir_loglik_tma_kernel"}.get(base, base)
+        for k, v in ks.items():
+            if k.split("<")[0] == base:
+                total += v["dram_bytes_per_launch"]
+                found = True
+                break
+    return total if found else None
 
 
 def _peaks():

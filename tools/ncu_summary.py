@@ -1,7 +1,10 @@
 #!/usr/bin/env python
 """Summarise an .ncu-rep (read on the CPU box with `ncu -i`) into a small markdown table for profiles/.
 
-    python tools/ncu_summary.py gpurun_out/prof.ncu-rep profiles/rNN_name.md ["title"]
+    python tools/ncu_summary.py gpurun_out/prof.ncu-rep profiles/rNN_name.md ["title"] [--traffic profiles/rNN_traffic.json]
+
+--traffic also writes dram__bytes_read.sum + dram__bytes_write.sum per launch and kernel (what bench.py reports as
+roofline.traffic).
 """
 import csv
 import io
@@ -24,9 +27,18 @@ METRICS = [
 ]
 
 
+UNIT_BYTES = {"byte": 1.0, "Kbyte": 1e3, "Mbyte": 1e6, "Gbyte": 1e9}
+
+
 def main():
-    rep, out = sys.argv[1], sys.argv[2]
-    title = sys.argv[3] if len(sys.argv) > 3 else rep
+    argv = list(sys.argv)
+    traffic_out = None
+    if "--traffic" in argv:
+        k = argv.index("--traffic")
+        traffic_out = argv[k + 1]
+        del argv[k:k + 2]
+    rep, out = argv[1], argv[2]
+    title = argv[3] if len(argv) > 3 else rep
     raw = subprocess.run(["ncu", "-i", rep, "--page", "raw", "--csv"], capture_output=True, text=True, check=True).stdout
     rows = list(csv.reader(io.StringIO(raw)))
     hdr, units, data = rows[0], rows[1], rows[2:]
@@ -49,6 +61,22 @@ def main():
         lines.append(f"| {name} | " + " | ".join(cells) + " |")
     open(out, "w").write("\n".join(lines) + "\n")
     print("\n".join(lines))
+    if traffic_out:
+        import json
+
+        ks = {}
+        for r in data:
+            name = r[idx["Kernel Name"]].split("(")[0].replace("void ", "")
+            tot = 0.0
+            for m in ("dram__bytes_read.sum", "dram__bytes_write.sum"):
+                tot += float(r[idx[m]].replace(",", "")) * UNIT_BYTES.get(units[idx[m]], 1.0)
+            e = ks.setdefault(name, {"dram_bytes_per_launch": 0.0, "launches_captured": 0})
+            e["dram_bytes_per_launch"] += tot
+            e["launches_captured"] += 1
+        for e in ks.values():
+            e["dram_bytes_per_launch"] /= e["launches_captured"]
+        json.dump({"source": f"{rep} (ncu --set full --clock-control none, tools/profile_once.py, B=256 chains 382x84): "
+                             "dram__bytes_read.sum + dram__bytes_write.sum per launch", "kernels": ks}, open(traffic_out, "w"), indent=1)
 
 
 if __name__ == "__main__":
