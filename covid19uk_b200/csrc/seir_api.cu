@@ -321,12 +321,33 @@ int seir_log_prob_grad_cached(seir_chains* c, const double* d_theta, int kind, i
   return seir_launch_finalize(c, d_theta, kind, parts, d_out, d_grad, s);
 }
 
+// library-owned side stream (+ fork / join events) for work that is independent of the caller's stream order
+static int ensure_tail_stream(seir_chains* c) {
+  if (c->tail_stream) return SEIR_OK;
+  SEIR_CUDA(cudaStreamCreateWithFlags(&c->tail_stream, cudaStreamNonBlocking));
+  SEIR_CUDA(cudaEventCreateWithFlags(&c->tail_fork, cudaEventDisableTiming));
+  SEIR_CUDA(cudaEventCreateWithFlags(&c->tail_join, cudaEventDisableTiming));
+  return SEIR_OK;
+}
+
 int seir_log_prob(seir_chains* c, const double* d_events, const double* d_theta, int kind, int parts, double* d_out,
                   void* stream) {
   if (!c) return seir_set_error(SEIR_ERR_BAD_ARG, "seir_log_prob: NULL chains");
   SEIR_TRY(check_parts(kind, parts));
-  if (parts & SEIR_PART_SEIR) SEIR_TRY(seir_ingest_events(c, d_events, stream));
-  return seir_log_prob_cached(c, d_theta, kind, parts, d_out, stream);
+  if (!(parts & SEIR_PART_SEIR)) return seir_log_prob_cached(c, d_theta, kind, parts, d_out, stream);
+  SEIR_TRY(check_dev_ptr(d_theta, "d_theta"));
+  if (!d_out) return seir_set_error(SEIR_ERR_BAD_ARG, "d_out is NULL");
+  // theta prep (one latency-bound CTA per chain) depends on theta only: it runs on the side stream under the ingest
+  cudaStream_t s = (cudaStream_t)stream;
+  SEIR_TRY(ensure_tail_stream(c));
+  SEIR_CUDA(cudaEventRecord(c->tail_fork, s));  // (earlier readers of the rate factors on s are done)
+  SEIR_CUDA(cudaStreamWaitEvent(c->tail_stream, c->tail_fork, 0));
+  SEIR_TRY(seir_launch_theta_prep(c, d_theta, kind, parts, c->tail_stream, seir_all(c)));
+  SEIR_CUDA(cudaEventRecord(c->tail_join, c->tail_stream));
+  SEIR_TRY(seir_ingest_events(c, d_events, stream));
+  SEIR_CUDA(cudaStreamWaitEvent(s, c->tail_join, 0));
+  SEIR_TRY(seir_launch_loglik(c, false, s, seir_all(c)));
+  return seir_launch_finalize(c, d_theta, kind, parts, d_out, nullptr, s);
 }
 
 // events-wide kernels (coefficients, contraction) + the theta-dependent half for chains [r.b0, r.b0 + r.nb)
@@ -370,9 +391,7 @@ int seir_log_prob_host(seir_chains* c, const double* h_events, const double* h_t
     SEIR_TRY(dev_alloc(&c->d_stage_u16, ne, &c->bytes));
     SEIR_CUDA(cudaHostAlloc(reinterpret_cast<void**>(&c->h_stage_u16), ne * sizeof(unsigned short), cudaHostAllocDefault));
     SEIR_CUDA(cudaStreamCreateWithFlags(&c->copy_stream, cudaStreamNonBlocking));
-    SEIR_CUDA(cudaStreamCreateWithFlags(&c->tail_stream, cudaStreamNonBlocking));
-    SEIR_CUDA(cudaEventCreateWithFlags(&c->tail_fork, cudaEventDisableTiming));
-    SEIR_CUDA(cudaEventCreateWithFlags(&c->tail_join, cudaEventDisableTiming));
+    SEIR_TRY(ensure_tail_stream(c));
     c->stage_nchunks = B < SEIR_HOST_CHUNKS ? B : SEIR_HOST_CHUNKS;
     c->stage_ev = new cudaEvent_t[c->stage_nchunks];
     for (int k = 0; k < c->stage_nchunks; ++k) SEIR_CUDA(cudaEventCreateWithFlags(&c->stage_ev[k], cudaEventDisableTiming));

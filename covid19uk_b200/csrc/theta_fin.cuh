@@ -198,7 +198,14 @@ __device__ __forceinline__ double tf_finalize(const tf_model& md, const tf_chain
     for (int m = tid; m < M; m += TF_THREADS) {
       double r = 0.0;
       if (want_seir)
-        for (int z = 0; z < ch.nts; ++z) r += ch.rowsum[((size_t)b * ch.nts + z) * Mp + m];
+        for (int z0 = 0; z0 < ch.nts; z0 += 4) {  // four partials in flight (the loads of a `r +=` loop were issued one by one)
+          double rv[4];
+#pragma unroll
+          for (int z = 0; z < 4; ++z) rv[z] = z0 + z < ch.nts ? ch.rowsum[((size_t)b * ch.nts + z0 + z) * Mp + m] : 0.0;
+#pragma unroll
+          for (int z = 0; z < 4; ++z)
+            if (z0 + z < ch.nts) r += rv[z];  // same order of additions as before
+        }
       acc[4] += r * md.la[m];
       acc[5] += r * sp[m];
       double gm = sigma * r;
