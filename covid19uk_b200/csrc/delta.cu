@@ -17,6 +17,8 @@
 //
 // Proposal conventions restated from gemlib ([recall], see oracle/seir_oracle.py move_max_events /
 // occult_delete_max and SURVEY Appendix B.1/B.3): parity unpinned.
+#include <stdlib.h>
+
 #include "delta_common.cuh"
 #include "propose.cuh"
 
@@ -536,7 +538,11 @@ struct upd_plan {
   double* dbg;          // single updates only
 };
 
-__global__ void __launch_bounds__(UPD_THREADS, 2) seir_update_kernel(upd_args A, upd_plan P, int b0) {
+// MINB: resident CTAs per SM the register allocation is bounded for -- 2 (126 registers, no spills) when the chains fit the
+// GPU at two CTAs per SM (the UK case: 256 chains, latency-bound), 4 (64 registers) for large chain counts, where what
+// matters is how many chains are in flight at once (scale-up config: 1024 chains).  Same arithmetic either way.
+template <int MINB>
+__global__ void __launch_bounds__(UPD_THREADS, MINB) seir_update_kernel(upd_args A, upd_plan P, int b0) {
   __shared__ long long s_redl[2 * (UPD_THREADS / 32)];
   extern __shared__ __align__(16) unsigned char dynraw[];
   double* day_acc = reinterpret_cast<double*>(dynraw + (upd_smem_bytes(A.T, A.Mp) + 15) / 16 * 16);  // [T], after the prepare phase's carve-up
@@ -596,11 +602,22 @@ static upd_args make_upd_args(seir_chains* c, int* d_proposal, double* d_log_u) 
 static int launch_update_kernel(seir_chains* c, const upd_args& A, const upd_plan& P, cudaStream_t s, seir_range r) {
   const size_t smem = (upd_smem_bytes(A.T, A.Mp) + 15) / 16 * 16 + sizeof(double) * A.T;
   static size_t attr = 0;
+  static int sms = 0, forced = 0;
+  if (!sms) {
+    int dev = 0;
+    cudaGetDevice(&dev);
+    cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev);
+    const char* e = getenv("SEIR_UPD_MINB");  // 2 / 4: force a variant (tests)
+    forced = e ? atoi(e) : 0;
+  }
   if (smem > 48 * 1024 && attr != smem) {
-    SEIR_CUDA(cudaFuncSetAttribute(seir_update_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+    SEIR_CUDA(cudaFuncSetAttribute(seir_update_kernel<2>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+    SEIR_CUDA(cudaFuncSetAttribute(seir_update_kernel<4>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
     attr = smem;
   }
-  seir_update_kernel<<<r.nb, UPD_THREADS, smem, s>>>(A, P, r.b0);
+  const bool many = forced ? forced >= 4 : r.nb > 2 * sms;
+  if (many) seir_update_kernel<4><<<r.nb, UPD_THREADS, smem, s>>>(A, P, r.b0);
+  else seir_update_kernel<2><<<r.nb, UPD_THREADS, smem, s>>>(A, P, r.b0);
   seir_count_launch(1);
   return seir_cuda_check(cudaGetLastError(), "seir_update_kernel");
 }

@@ -158,3 +158,38 @@ def test_burst_equals_sweep_by_sweep_bitwise():
             assert np.array_equal(v.cpu().numpy(), tr1[k][f]), (k, f)
     assert tr1["hmc"]["is_accepted"].shape == (n, B) and tr1["move/S->E"]["proposed_delta"].shape[:2] == (n, B)
     eng.close()
+
+
+def test_update_kernel_register_variants_agree_bitwise():
+    """seir_update_kernel is compiled for two occupancy targets (SEIR_UPD_MINB: 2 = 126 registers, the default up to two
+    chains per SM; 4 = 64 registers, picked for large chain counts).  Same arithmetic: chains, events and traces must be
+    bit-identical.  (The variant is fixed per process at first use, so the forced run is a subprocess.)"""
+    import os
+    import subprocess
+    import sys
+    import tempfile
+
+    code = r'''
+import sys, numpy as np, torch
+sys.path[:0] = [%r, %r]
+from test_gpu_sweep import _setup, CFG
+from covid19uk_b200.inference.sampler import ChainSet
+M, T, B = 24, 40, 48
+pb, eng, om, u = _setup(M, T, B, seed=21)
+cfg = dict(CFG, dmax=min(CFG["dmax"], T - 1))
+cs = ChainSet(eng, pb["events"], u, cfg, [T - 21, T], seed=9, chain_offset=0)
+(us, _), trace = cs.sample(3, step_size=1e-3)
+np.savez(sys.argv[1], u=cs.u.cpu().numpy(), ev=cs.events().cpu().numpy(), tlp=cs.tlp.cpu().numpy(),
+         acc=np.stack([trace[k]["is_accepted"].cpu().numpy() for k in ("move/S->E", "move/E->I", "occult/S->E", "occult/E->I")]),
+         tl=np.stack([trace[k]["target_log_prob"].cpu().numpy() for k in ("move/S->E", "move/E->I", "occult/S->E", "occult/E->I")]))
+''' % (os.path.dirname(os.path.dirname(os.path.abspath(__file__))), os.path.dirname(os.path.abspath(__file__)))
+    outs = []
+    with tempfile.TemporaryDirectory() as td:
+        for minb in ("2", "4"):
+            path = os.path.join(td, f"v{minb}.npz")
+            env = dict(os.environ, SEIR_UPD_MINB=minb)
+            r = subprocess.run([sys.executable, "-c", code, path], env=env, capture_output=True, text=True)
+            assert r.returncode == 0, r.stderr[-2000:]
+            outs.append(dict(np.load(path)))
+    for k in outs[0]:
+        assert np.array_equal(outs[0][k], outs[1][k]), k

@@ -110,6 +110,10 @@ def run_size(M, T, B, a):
 
         ms = timed(one, a.reps * 2)
         dll[name] = {"proposals_per_s": B / (ms * 1e-3), "ms": ms, "acceptance": float(acc_sum[0]) / max(acc_sum[1], 1)}
+        if a.split:  # the draw and the update timed on their own (the update re-applies one fixed proposal record)
+            dll[name]["propose_ms"] = timed(lambda: eng.propose(spec, B, 11, 0, 7), a.reps * 2)
+            prop, lu = eng.propose(spec, B, 11, 0, 7)
+            dll[name]["update_ms"] = timed(lambda: eng.update_step(spec, slot, prop, lu, tlp), a.reps * 2)
     res["delta_loglik"] = dll
     # the incrementally maintained target log-prob still matches a from-scratch evaluation of the updated events
     fresh = eng.log_prob(eng.export_events(B), u, kind, parts)
@@ -127,6 +131,7 @@ def main():
     ap.add_argument("--reps", type=int, default=5)
     ap.add_argument("--distinct", type=int, default=8)
     ap.add_argument("--no-oracle", action="store_true")
+    ap.add_argument("--split", action="store_true", help="also time the proposal draw and the update separately")
     ap.add_argument("--hbm-peak", type=float, default=6543.1, help="GB/s (MEASURED_PEAKS.json)")
     a = ap.parse_args()
     for sz in a.sizes.split(","):
