@@ -82,6 +82,9 @@ int seir_launch_state(const seir_model* m, int B, const double* d_events, double
 // int32 tile, so the whole 64.5 KB of a UK tile is in flight at once at no register cost.  ncu on the register-path
 // kernel (profiles/r01_v7_*, 57 % of the stall samples on the first use of a loaded value, 41 % DRAM throughput): one
 // 16-byte load per lane in flight per warp is too little memory-level parallelism for 6.5 TB/s.
+// (Tried and dropped: two half-length staging tiles fetched up front, the second landing while the first is processed --
+// 82 us against 78.5 us for the single tile: twice the barriers and shorter per-warp day segments cost more than the
+// shorter wait for the first half saves.)
 template <int TC, typename EV, bool TMA>
 __global__ void __launch_bounds__(256) seir_ingest_kernel(int M, int T, int Mp, int b0, const int* __restrict__ init,
                                                           const EV* __restrict__ events, int* __restrict__ yse,
