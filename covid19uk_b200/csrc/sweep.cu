@@ -42,13 +42,16 @@ static void slot_cfg(const seir_sweep_spec* sp, int slot, seir_update_cfg* cfg) 
 //     inference.py:107-117): the groups are joined only at the END of the burst and start STAGGERED (group g + 1 starts
 //     when group g is 1/G of the way through its first sweep), so that the latency-bound discrete updates of one group
 //     run under the log-likelihood launches of the HMC step of another for the whole burst.
-//     Measured (B = 256, UK, 20 sweeps): 1 group 2.35 ms per sweep, 2 staggered groups 2.29 ms, 4 groups 2.6-2.7 ms and
-//     8 groups enqueue-bound (616 launches per sweep at ~4.5 us of host time each).  The stagger buys little: two (four)
-//     INDEPENDENT chain sets of 128 (64) chains driven by separate host threads (tools/concurrent_sets.py) also finish
-//     256 chain-sweeps in 2.3-2.4 ms although one set alone needs 1.7 (1.3) ms -- the one-CTA-per-chain kernels hold
-//     registers while they wait (a leap launch ~16 k registers per chain for 20 us), which is what the two-CTAs-per-SM
-//     log-likelihood launches of the other group need, so the overlap is close to zero-sum.  The burst still removes the
-//     per-sweep host work (trace copies, one C call per sweep) and the per-sweep join.
+//     Measured (B = 256, UK, 30 sweeps, one update kernel per sweep): 1 group 2.23 ms per sweep; 2 groups in phase 2.22 ms;
+//     2 groups with group 1 starting when group 0 has done 9 of its 17 leapfrog steps (the default) 2.14-2.17 ms; with the
+//     start moved to step 15 / 17 / 18 (group 1 in its HMC step exactly while group 0 runs its update kernel) 3.4 / 4.4 /
+//     2.6 ms: the 128 update CTAs of a group hold 32 k registers each for the whole 0.7 ms and leave room for one
+//     log-likelihood CTA per SM instead of two (with the 64-register variant of the update kernel the same schedule costs
+//     2.5 ms, not 4.4).  Two (four) INDEPENDENT chain sets of 128 (64) chains driven by separate host threads
+//     (tools/concurrent_sets.py) also finish 256 chain-sweeps in 2.3-2.4 ms although one set alone needs 1.7 (1.3) ms:
+//     the one-CTA-per-chain kernels hold registers while they wait, which is what the two-CTAs-per-SM log-likelihood
+//     launches of the other group need, so overlap is close to zero-sum.  SEIR_BURST_GROUPS / SEIR_BURST_STAGGER /
+//     SEIR_BURST_MARK select the schedule.
 static int env_int(const char* name, int dflt) {
   const char* e = getenv(name);
   return e ? atoi(e) : dflt;
@@ -162,8 +165,11 @@ int seir_launch_sweep_burst(seir_chains* c, const seir_sweep_spec* sp, unsigned 
   static int stagger = -1;
   if (stagger < 0) stagger = env_int("SEIR_BURST_STAGGER", 1);
   const int steps = (sp->num_leapfrog_steps + 1) + 1;
-  int mark_step = steps / G;
+  static int mark_env = -1;
+  if (mark_env < 0) mark_env = env_int("SEIR_BURST_MARK", 0);
+  int mark_step = mark_env > 0 ? mark_env : steps / G;
   if (mark_step < 1) mark_step = 1;
+  if (mark_step > steps) mark_step = steps;
   auto out_of = [&](int k) {
     return sweep_out{d_hmc_accept + (size_t)k * B,
                      d_hmc_dbg ? d_hmc_dbg + (size_t)k * B * 4 : nullptr,
