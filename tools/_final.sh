@@ -1,0 +1,5 @@
+python -m pytest tests -m gpu -x -q > gpurun_out/r1y_tests.log 2>&1; tail -2 gpurun_out/r1y_tests.log
+python -c "import __graft_entry__ as g; g.smoke()" 2>&1 | tail -1
+python bench.py > gpurun_out/r1y_bench.json 2> gpurun_out/r1y_bench.err; echo "bench rc=$?"
+python bench.py --impl reference --steps 5 --warmup 1 > gpurun_out/r1y_bench_ref.json 2>> gpurun_out/r1y_bench.err
+python tools/e2e_probe.py --quick > gpurun_out/r1y_probe.json 2> gpurun_out/r1y_probe.err; tail -2 gpurun_out/r1y_probe.err | cut -c1-400
