@@ -171,7 +171,8 @@ int seir_hmc_step_leap(seir_chains* c, int i, int num_leapfrog, double* d_u, con
     attr_smem = smem;
   }
   int rc;
-  if ((rc = seir_launch_loglik(c, true, s, r)) != SEIR_OK) return rc;
+  // the energies are evaluated at the two ends of the trajectory: interior steps need the gradient only
+  if ((rc = seir_launch_loglik_ex(c, true, i == 0 || i == num_leapfrog, s, r)) != SEIR_OK) return rc;
   const tf_model md = seir_tf_model(m);
   const tf_chains ch = seir_tf_chains(c);  // (after the log-lik launch: it fixes the partial-array shapes)
   if (i == 0)

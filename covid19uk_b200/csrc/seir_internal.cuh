@@ -187,6 +187,7 @@ int seir_launch_finalize_range(seir_chains* c, const double* d_theta, int kind, 
 int seir_contract_i8_setup(seir_model* m, const double* h_cs, double max_population);
 int seir_launch_theta_prep(seir_chains* c, const double* d_theta, int kind, int parts, cudaStream_t s, seir_range r);
 int seir_launch_loglik(seir_chains* c, bool grad, cudaStream_t s, seir_range r);
+int seir_launch_loglik_ex(seir_chains* c, bool grad, bool want_val, cudaStream_t s, seir_range r);
 int seir_launch_finalize(seir_chains* c, const double* d_theta, int kind, int parts, double* d_out, double* d_grad,
                          cudaStream_t s);
 int seir_launch_hmc_momentum(seir_chains* c, unsigned long long seed, unsigned chain0, unsigned sweep, const double* d_inv_mass,
