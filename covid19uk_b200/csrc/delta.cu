@@ -463,9 +463,11 @@ __device__ __forceinline__ void upd_slab(const upd_args& A, int b, int kind, con
             const double e = pas * pmv[k];
             const double x0 = fma(e, I + pws * bc[k], A.eps) * A.dt;
             const double x1 = fma(e, I + dIi + pws * bcn, A.eps) * A.dt;
-            double term = -(double)(S - y) * (x1 - x0);
-            if (y > 0) term += (double)y * (log1mexp_neg_tab(x1, logtab) - log1mexp_neg_tab(x0, logtab));
-            acc += term;
+            if (x1 != x0 || !(x0 > 0.0)) {  // (Cs is sparse: an untouched cell with a valid hazard contributes exactly 0 -- skip its two logarithms)
+              double term = -(double)(S - y) * (x1 - x0);
+              if (y > 0) term += (double)y * (log1mexp_neg_tab(x1, logtab) - log1mexp_neg_tab(x0, logtab));
+              acc += term;
+            }
           }
         }
       }
