@@ -318,6 +318,9 @@ int seir_launch_ingest(seir_chains* c, const double* d_events, cudaStream_t s) {
 //          SHARED memory (128 KB): three conflict-tolerant shared-memory gathers instead of four FP64
 //          logarithms per coefficient.  (The first version evaluated a two-log Stirling form per
 //          coefficient and ran at 0.21 ms -- FP64-pipe bound; counts beyond the table still take it.)
+// (Tried and dropped: summing the three small-count terms -lgamma(y+1) of a cell in the ingest kernel, where the counts
+// are in registers -- the coefficient kernel drops from 80 to 67 us with four gathers per cell, but the ingest's emit
+// loop is instruction-bound and grows from 79 to 97 us.)
 // Persistent kernel: one 1024-thread CTA per SM loads the table once, then warps stride over the
 // B*T day slabs; lanes sweep the metapopulations of a slab with coalesced 128-byte loads.  One partial
 // per (chain, day) is written and reduced in fixed order by seir_finalize_kernel.
