@@ -9,6 +9,8 @@
 //
 // Also here: the counter-based Philox4x32-10 generator used by the device-side samplers.
 #include "philox.cuh"
+#include <stdlib.h>
+
 #include "seir_internal.cuh"
 #include "theta_fin.cuh"
 
@@ -75,6 +77,8 @@ __global__ void __launch_bounds__(TF_THREADS) seir_hmc_leap_kernel(tf_model md, 
   const int b = b0 + blockIdx.x, P = md.P;
   double* ub = u + (size_t)b * P;
   double* gb = grad + (size_t)b * P;
+  pdl_launch_dependents();  // (the next log-likelihood grid may become resident now; it waits for this grid's writes)
+  pdl_wait();               // the log-likelihood partials this kernel reduces
   const double val = tf_finalize(md, ch, b, ub, SEIR_PART_JOINT, gb, dyn, sh);
   const double eps = step[b];
   double k = 0.0;
@@ -172,18 +176,28 @@ int seir_hmc_step_leap(seir_chains* c, int i, int num_leapfrog, double* d_u, con
   }
   int rc;
   // the energies are evaluated at the two ends of the trajectory: interior steps need the gradient only
-  if ((rc = seir_launch_loglik_ex(c, true, i == 0 || i == num_leapfrog, s, r)) != SEIR_OK) return rc;
+  static int pdl = -1;
+  if (pdl < 0) {
+    // SEIR_PDL=1: programmatic dependent launch of the log-likelihood <-> leapfrog ping-pong (seir_internal.cuh).  Measured
+    // (UK, 256 chains, ms per sweep): one chain group 2.27 -> 2.00 with PDL; two chain groups (the default schedule)
+    // 1.99 without, 2.06-3.2 with -- the early-resident grids of one group take registers from the other group's running
+    // kernels.  Off by default: it buys nothing over the two-group schedule; on, it halves the launches for the same time.
+    const char* e = getenv("SEIR_PDL");
+    pdl = e ? atoi(e) : 0;
+  }
+  // (the first evaluation follows the theta prep kernel, a plain launch: no early start there)
+  if ((rc = seir_launch_loglik_ex(c, true, i == 0 || i == num_leapfrog, s, r, pdl && i > 0)) != SEIR_OK) return rc;
   const tf_model md = seir_tf_model(m);
   const tf_chains ch = seir_tf_chains(c);  // (after the log-lik launch: it fixes the partial-array shapes)
   if (i == 0)
-    seir_hmc_leap_kernel<HMC_BEGIN><<<r.nb, TF_THREADS, smem, s>>>(md, ch, r.b0, d_step, d_inv_mass, d_log_u, d_u, c->d_hmc_p, c->d_hmc_grad,
-                                                                   c->d_hmc_u0, val0, k0, d_tlp, d_tlp_trace, d_accept, d_dbg);
+    SEIR_CUDA(seir_launch_pdl(seir_hmc_leap_kernel<HMC_BEGIN>, dim3(r.nb), dim3(TF_THREADS), smem, s, pdl != 0, md, ch, r.b0, d_step, d_inv_mass, d_log_u, d_u,
+                              c->d_hmc_p, c->d_hmc_grad, c->d_hmc_u0, val0, k0, d_tlp, d_tlp_trace, d_accept, d_dbg));
   else if (i < num_leapfrog)
-    seir_hmc_leap_kernel<HMC_MID><<<r.nb, TF_THREADS, smem, s>>>(md, ch, r.b0, d_step, d_inv_mass, d_log_u, d_u, c->d_hmc_p, c->d_hmc_grad,
-                                                                 c->d_hmc_u0, val0, k0, d_tlp, d_tlp_trace, d_accept, d_dbg);
+    SEIR_CUDA(seir_launch_pdl(seir_hmc_leap_kernel<HMC_MID>, dim3(r.nb), dim3(TF_THREADS), smem, s, pdl != 0, md, ch, r.b0, d_step, d_inv_mass, d_log_u, d_u,
+                              c->d_hmc_p, c->d_hmc_grad, c->d_hmc_u0, val0, k0, d_tlp, d_tlp_trace, d_accept, d_dbg));
   else
-    seir_hmc_leap_kernel<HMC_END><<<r.nb, TF_THREADS, smem, s>>>(md, ch, r.b0, d_step, d_inv_mass, d_log_u, d_u, c->d_hmc_p, c->d_hmc_grad,
-                                                                 c->d_hmc_u0, val0, k0, d_tlp, d_tlp_trace, d_accept, d_dbg);
+    SEIR_CUDA(seir_launch_pdl(seir_hmc_leap_kernel<HMC_END>, dim3(r.nb), dim3(TF_THREADS), smem, s, pdl != 0, md, ch, r.b0, d_step, d_inv_mass, d_log_u, d_u,
+                              c->d_hmc_p, c->d_hmc_grad, c->d_hmc_u0, val0, k0, d_tlp, d_tlp_trace, d_accept, d_dbg));
   seir_count_launch(1);
   return seir_cuda_check(cudaGetLastError(), "seir_hmc_leap_kernel");
 }

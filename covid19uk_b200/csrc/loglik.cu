@@ -311,6 +311,7 @@ __global__ void __launch_bounds__(NTHR + 32, NTHR >= 384 ? (GRAD ? 2 : 3) : 1) s
     asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
   }
   if (tid < 128) tab[tid] = logtab[tid];
+  pdl_wait();  // (PDL launches: everything below reads what the previous kernel on the stream wrote)
   for (int t = tid; t < nt; t += NTHR + 32) {
     pa_s[t] = pa[(size_t)b * T + tb + t];
     pw_s[t] = psiW[(size_t)b * T + tb + t];
@@ -379,6 +380,7 @@ __global__ void __launch_bounds__(NTHR + 32, NTHR >= 384 ? (GRAD ? 2 : 3) : 1) s
       }
     }
   }
+  pdl_launch_dependents();  // (the next kernel may be scheduled onto the SMs this grid's last wave is leaving)
   const int slot = blockIdx.z * gridDim.x + blockIdx.x, nslot = gridDim.x * gridDim.z;
   const double v = block_sum(val, red);
   if (tid == 0) val_part[(size_t)b * nslot + slot] = v;
@@ -493,10 +495,10 @@ static int choose_dps(const seir_chains* c, bool grad, const loglik_cfg& k, logl
   return dps;
 }
 
-int seir_launch_loglik(seir_chains* c, bool grad, cudaStream_t s, seir_range r) { return seir_launch_loglik_ex(c, grad, true, s, r); }
+int seir_launch_loglik(seir_chains* c, bool grad, cudaStream_t s, seir_range r) { return seir_launch_loglik_ex(c, grad, true, s, r, false); }
 
 // want_val = false (grad only): the value partials are written as zeros -- for callers that use the gradient alone
-int seir_launch_loglik_ex(seir_chains* c, bool grad, bool want_val, cudaStream_t s, seir_range r) {
+int seir_launch_loglik_ex(seir_chains* c, bool grad, bool want_val, cudaStream_t s, seir_range r, bool pdl) {
   const seir_model* m = c->model;
   const loglik_cfg k = loglik_config(c);
   loglik_fn fn = grad ? loglik_kernel_for<true>(k) : loglik_kernel_for<false>(k);
@@ -511,9 +513,10 @@ int seir_launch_loglik_ex(seir_chains* c, bool grad, bool want_val, cudaStream_t
     SEIR_CUDA(cudaFuncSetAttribute(fn, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
     c->ll_attr_smem[grad] = smem;
   }
-  fn<<<grid, k.tma ? k.threads + 32 : k.threads, smem, s>>>(m->T, m->Mp, dps, r.b0, m->dt, m->rate_eps, c->d_yse, c->d_S, c->d_I, c->d_Bc, c->d_pa, c->d_psiW,
-                                   m->d_W, c->d_pm, m->d_logtab, c->d_val_part, c->d_psi_part, c->d_col_part, c->d_rowsum, LL_COEFS,
-                                   (want_val || !grad) ? 1 : 0);
+  // (PDL only for the TMA kernel: it is the one that calls pdl_wait)
+  SEIR_CUDA(seir_launch_pdl(fn, grid, dim3(k.tma ? k.threads + 32 : k.threads), smem, s, pdl && k.tma, m->T, m->Mp, dps, r.b0, m->dt, m->rate_eps,
+                            c->d_yse, c->d_S, c->d_I, c->d_Bc, c->d_pa, c->d_psiW, m->d_W, c->d_pm, m->d_logtab, c->d_val_part, c->d_psi_part,
+                            c->d_col_part, c->d_rowsum, LL_COEFS, (want_val || !grad) ? 1 : 0));
   seir_count_launch(1);
   return seir_cuda_check(cudaGetLastError(), "seir_loglik_kernel");
 }

@@ -187,7 +187,7 @@ int seir_launch_finalize_range(seir_chains* c, const double* d_theta, int kind, 
 int seir_contract_i8_setup(seir_model* m, const double* h_cs, double max_population);
 int seir_launch_theta_prep(seir_chains* c, const double* d_theta, int kind, int parts, cudaStream_t s, seir_range r);
 int seir_launch_loglik(seir_chains* c, bool grad, cudaStream_t s, seir_range r);
-int seir_launch_loglik_ex(seir_chains* c, bool grad, bool want_val, cudaStream_t s, seir_range r);
+int seir_launch_loglik_ex(seir_chains* c, bool grad, bool want_val, cudaStream_t s, seir_range r, bool pdl);
 int seir_launch_finalize(seir_chains* c, const double* d_theta, int kind, int parts, double* d_out, double* d_grad,
                          cudaStream_t s);
 int seir_launch_hmc_momentum(seir_chains* c, unsigned long long seed, unsigned chain0, unsigned sweep, const double* d_inv_mass,
@@ -228,6 +228,30 @@ int seir_launch_update_rounds(seir_chains* c, const seir_update_cfg* cfg4, int n
 
 // ---- device helpers ---------------------------------------------------------------------------
 #ifdef __CUDACC__
+
+// Programmatic dependent launch (PDL): a kernel launched with seir_launch_pdl(..., pdl = true) may be scheduled while
+// its predecessor on the stream is still draining (after every CTA of the predecessor has called
+// pdl_launch_dependents() or exited); it calls pdl_wait() before it touches anything the predecessor wrote (the wait
+// returns when the predecessor has completed and its writes are visible).  Used for the log-likelihood <-> leapfrog
+// ping-pong of an HMC trajectory (34 kernel boundaries per sweep).  Both instructions are no-ops in a normal launch.
+__device__ __forceinline__ void pdl_wait() { asm volatile("griddepcontrol.wait;" ::: "memory"); }
+__device__ __forceinline__ void pdl_launch_dependents() { asm volatile("griddepcontrol.launch_dependents;" ::: "memory"); }
+
+template <typename... KArgs, typename... Args>
+static inline cudaError_t seir_launch_pdl(void (*kernel)(KArgs...), dim3 grid, dim3 block, size_t smem, cudaStream_t s, bool pdl,
+                                          Args... args) {
+  cudaLaunchConfig_t cfg = {};
+  cfg.gridDim = grid;
+  cfg.blockDim = block;
+  cfg.dynamicSmemBytes = smem;
+  cfg.stream = s;
+  cudaLaunchAttribute at[1];
+  at[0].id = cudaLaunchAttributeProgrammaticStreamSerialization;
+  at[0].val.programmaticStreamSerializationAllowed = 1;
+  cfg.attrs = at;
+  cfg.numAttrs = pdl ? 1 : 0;
+  return cudaLaunchKernelEx(&cfg, kernel, static_cast<KArgs>(args)...);
+}
 
 __device__ __forceinline__ double warp_sum(double v) {
 #pragma unroll
