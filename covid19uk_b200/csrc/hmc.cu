@@ -186,7 +186,7 @@ int seir_hmc_step_leap(seir_chains* c, int i, int num_leapfrog, double* d_u, con
     pdl = e ? atoi(e) : 0;
   }
   // (the first evaluation follows the theta prep kernel, a plain launch: no early start there)
-  if ((rc = seir_launch_loglik_ex(c, true, i == 0 || i == num_leapfrog, s, r, pdl && i > 0)) != SEIR_OK) return rc;
+  if ((rc = seir_launch_loglik_ex(c, true, i == 0 || i == num_leapfrog, s, r, pdl == 1 && i > 0)) != SEIR_OK) return rc;  // (SEIR_PDL=2: leap kernels only)
   const tf_model md = seir_tf_model(m);
   const tf_chains ch = seir_tf_chains(c);  // (after the log-lik launch: it fixes the partial-array shapes)
   if (i == 0)
