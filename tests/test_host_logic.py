@@ -17,3 +17,55 @@ def test_dual_averaging_and_running_variance_host_logic():
         rv.update(x[i])
     ref = torch.cat([x[50:100], x[100:]]).var(dim=0, unbiased=False)
     assert torch.allclose(rv.variance(), ref, rtol=1e-10)
+
+
+def test_host_packer_is_exact_or_refuses():
+    """host_pack.cpp (the host half of seir_log_prob_host): float64 counts are narrowed to uint16 EXACTLY, chunk by chunk and
+    in order, or the chunk is refused (a count beyond uint16, a negative one, a non-integer, NaN); a chunk the caller has
+    claimed for itself is left alone, and so is everything behind it.  Pure host code: no GPU involved."""
+    import ctypes
+
+    import numpy as np
+
+    from covid19uk_b200 import _native as nat
+
+    lib = ctypes.CDLL(nat.lib_path())
+    lib.seir_pack_begin.restype = ctypes.c_int
+    lib.seir_pack_begin.argtypes = [ctypes.c_void_p, ctypes.c_void_p, ctypes.c_size_t, ctypes.c_size_t, ctypes.c_int]
+    for f in (lib.seir_pack_wait, lib.seir_pack_poll):
+        f.restype = ctypes.c_int
+        f.argtypes = [ctypes.c_int, ctypes.c_int]
+    lib.seir_pack_claim_raw.restype = ctypes.c_int
+    lib.seir_pack_claim_raw.argtypes = [ctypes.c_int]
+    rng = np.random.default_rng(0)
+    nchunks, chunk = 12, 50_003  # (odd chunk length: unaligned destinations take the plain-store path; the last chunk is short)
+    n = nchunks * chunk - 1234
+    src = rng.integers(0, 65536, size=n).astype(np.float64)
+    bad_at = {2: 70000.0, 4: -1.0, 6: 12.5, 8: np.nan}
+    for ch, v in bad_at.items():
+        src[ch * chunk + 17 * ch] = v
+    for rep in range(3):  # the pool is reused across batches
+        dst = np.zeros(n, dtype=np.uint16)
+        jpc = lib.seir_pack_begin(src.ctypes.data, dst.ctypes.data, chunk, n, nchunks)
+        assert jpc >= 1
+        status = [lib.seir_pack_wait(k, jpc) for k in range(nchunks)]
+        for k in range(nchunks):
+            lo, hi = k * chunk, min(n, (k + 1) * chunk)
+            if k in bad_at:
+                assert status[k] == 0, k
+            else:
+                assert status[k] == 1, k
+                assert np.array_equal(dst[lo:hi], src[lo:hi].astype(np.uint16)), k
+    # a claimed chunk: the pool narrows everything in front of it and nothing from it on
+    good = rng.integers(0, 300, size=n).astype(np.float64)
+    dst = np.full(n, 7, dtype=np.uint16)
+    # (claim before the pool can get there: chunks are taken in order and the last one is far behind the front)
+    jpc = lib.seir_pack_begin(good.ctypes.data, dst.ctypes.data, chunk, n, nchunks)
+    claimed = lib.seir_pack_claim_raw(nchunks - 1)
+    for k in range(nchunks - 1):
+        assert lib.seir_pack_wait(k, jpc) == 1
+        assert np.array_equal(dst[k * chunk:(k + 1) * chunk], good[k * chunk:(k + 1) * chunk].astype(np.uint16))
+    if claimed:
+        assert np.all(dst[(nchunks - 1) * chunk:] == 7)
+    else:  # the pool was faster than this thread: then it narrowed the chunk itself
+        assert lib.seir_pack_wait(nchunks - 1, jpc) == 1
