@@ -238,6 +238,15 @@ int seir_pack_claim_raw(int chunk) {
   return (*g_owner)[chunk].compare_exchange_strong(expect, 2, std::memory_order_acq_rel) ? 1 : 0;
 }
 
+// Abandon the current batch (error path of the caller): no further job is handed out, and the call returns once no
+// worker is reading the source buffer any more.
+void seir_pack_cancel(void) {
+  if (!g_pool) return;
+  Pool& p = *g_pool;
+  p.next.store(p.njobs, std::memory_order_release);
+  while (p.active.load(std::memory_order_acquire) != 0) std::this_thread::yield();
+}
+
 int seir_pack_owner(int chunk) { return (*g_owner)[chunk].load(std::memory_order_acquire); }
 
 int seir_pack_wait(int chunk, int jobs_per_chunk) {

@@ -366,18 +366,31 @@ int seir_pack_begin(const double* src, unsigned short* dst, size_t chunk_elems, 
 int seir_pack_poll(int chunk, int jobs_per_chunk);
 int seir_pack_claim_raw(int chunk);
 int seir_pack_owner(int chunk);
+void seir_pack_cancel(void);
 
 #define SEIR_HOST_CHUNKS 32
 
 // Host-buffer entry point.  The event tensor is the whole transfer (8 B per count, 198 MB at the UK size with 256
-// chains, vs 1.2 ms of device work), so the chains are cut into chunks that travel two ways at once:
+// chains, vs 0.3 ms of device work), so the chains are cut into chunks that travel two ways at once:
 //   * from the FRONT the host thread pool narrows chunks to uint16 (exact, or the chunk is refused) into pinned staging;
 //     a narrowed chunk is a quarter of the bytes on the link;
-//   * from the BACK the calling thread ships chunks as they are (float64), at most two in flight, so the link is busy
-//     while the cores narrow.
+//   * from the BACK the calling thread ships a planned number of chunks as they are (float64), so that the link is busy
+//     while the cores narrow (the plan: see below).
 // Each chunk's ingest kernel runs as soon as its copy lands (event-ordered on the compute stream); the events-wide
-// kernels (coefficients, contraction) and the theta-dependent half follow once every chunk is in.
+// kernels (coefficients, contraction) and the theta-dependent half run in parts: on a second stream for the chains
+// already in, after the transfer for the last part.
+static int log_prob_host_impl(seir_chains* c, const double* h_events, const double* h_theta, int kind, int parts, double* h_out);
+
 int seir_log_prob_host(seir_chains* c, const double* h_events, const double* h_theta, int kind, int parts, double* h_out) {
+  const int rc = log_prob_host_impl(c, h_events, h_theta, kind, parts, h_out);
+  if (rc != SEIR_OK) {  // leave nothing behind that still reads the caller's buffers: pool jobs, copies in flight
+    seir_pack_cancel();
+    cudaDeviceSynchronize();
+  }
+  return rc;
+}
+
+static int log_prob_host_impl(seir_chains* c, const double* h_events, const double* h_theta, int kind, int parts, double* h_out) {
   if (!c || !h_events || !h_theta || !h_out) return seir_set_error(SEIR_ERR_BAD_ARG, "seir_log_prob_host: NULL argument");
   SEIR_TRY(check_parts(kind, parts));
   const seir_model* m = c->model;
