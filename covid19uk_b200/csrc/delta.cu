@@ -214,7 +214,7 @@ __device__ __forceinline__ seir_upd upd_prepare(const upd_args& A, int b, const 
   UTM(3);
   chain_view col[2] = {g, g};
   const double* colbc[2] = {Bc + cb, Bc + cb};
-  stage_columns(g, Bc + cb, s_sel, sm.col, UPD_THREADS);
+  stage_columns(g, Bc + cb, s_sel, sm.col, UPD_THREADS, cfg.kind == 1 ? max(0, min(cfg.t0, T)) : 0);
   for (int k = 0; k < 2; ++k)
     if (s_sel[k] >= 0) {
       col[k] = column_view(g, sm.col[k], s_sel[k]);

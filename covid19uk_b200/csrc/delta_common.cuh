@@ -33,11 +33,14 @@ struct col_stage {
 // Both columns at once: thread <-> day; the 14 strided loads of a thread (2 columns x (6 integer rows + the contraction
 // row)) are issued back to back BEFORE any of them is consumed -- one round trip to HBM.  (A copy loop that stores each
 // value as it arrives keeps a single load in flight per thread: measured 9.4 us for two columns, profiles/r01_v7_*.)
+// Days [s_lo, T) only: an occult update never looks before its window (the day is drawn inside it, the bounds and the
+// delta log-lik run from that day to T), so the days before it are not fetched -- at T = 365 that is 17 x fewer scattered
+// sectors per column.  Event-time moves pass s_lo = 0.
 __device__ __forceinline__ void stage_columns(const chain_view& g, const double* Bc_chain, const int* sel, const col_stage* c,
-                                              int nthr) {
+                                              int nthr, int s_lo) {
   const int T = g.T, tid = threadIdx.x;
   const bool has[2] = {sel[0] >= 0, sel[1] >= 0};
-  for (int s0 = 0; s0 < T; s0 += nthr) {
+  for (int s0 = s_lo; s0 < T; s0 += nthr) {
     const int s = s0 + tid;
     int vi[2][6];
     double vb[2];

@@ -205,7 +205,7 @@ __device__ __forceinline__ void seir_sample_proposal(const chain_view& g, const 
   if (threadIdx.x < 32) sample_metapops(g, cfg, seed, chain, ctr, sm.cnt, H, pr, log_u_out, sel);
   __syncthreads();
   chain_view col[2] = {g, g};
-  stage_columns(g, Bc_chain, sel, sm.col, blockDim.x);
+  stage_columns(g, Bc_chain, sel, sm.col, blockDim.x, cfg.kind == 1 ? max(0, min(cfg.t0, g.T)) : 0);
   for (int k = 0; k < 2; ++k)
     if (sel[k] >= 0) col[k] = column_view(g, sm.col[k], sel[k]);
   __syncthreads();
