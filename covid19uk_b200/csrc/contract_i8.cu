@@ -393,7 +393,9 @@ int seir_launch_contract_i8_range(seir_chains* c, cudaStream_t s, seir_range r) 
   if (row0 % I8_BM != 0) return seir_set_error(SEIR_ERR_BAD_ARG, "seir_launch_contract_i8_range: chain range does not start a row tile");
   const int ntiles = (int)((R + I8_BM - 1) / I8_BM) * (m->Mp / I8_BN);
   size_t a_region = (size_t)m->i8_na * I8_BM * m->Mp;
+#if I8_STAGE_OUT > 0
   if (a_region < (size_t)I8_STAGE_OUT) a_region = I8_STAGE_OUT;
+#endif
   const size_t smem = a_region + (size_t)I8_STAGES * I8_KBLOCK + 1024;  // (+ slack to align the dynamic base to 1024 bytes)
   static int sms = 0;
   static size_t attr = 0;
