@@ -397,13 +397,9 @@ int seir_launch_contract_i8_range(seir_chains* c, cudaStream_t s, seir_range r) 
   if (a_region < (size_t)I8_STAGE_OUT) a_region = I8_STAGE_OUT;
 #endif
   const size_t smem = a_region + (size_t)I8_STAGES * I8_KBLOCK + 1024;  // (+ slack to align the dynamic base to 1024 bytes)
-  static int sms = 0;
-  static size_t attr = 0;
-  if (!sms) {
-    int dev = 0;
-    cudaGetDevice(&dev);
-    cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev);
-  }
+  const int sms = m->sms;
+  static size_t attr_dev[SEIR_MAX_DEVICES] = {0};  // (the opt-in is per device)
+  size_t& attr = attr_dev[c->model->device % SEIR_MAX_DEVICES];
   if (attr != smem) {
     SEIR_CUDA(cudaFuncSetAttribute(seir_contract_i8_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
     attr = smem;

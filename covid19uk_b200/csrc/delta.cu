@@ -603,12 +603,11 @@ static upd_args make_upd_args(seir_chains* c, int* d_proposal, double* d_log_u) 
 
 static int launch_update_kernel(seir_chains* c, const upd_args& A, const upd_plan& P, cudaStream_t s, seir_range r) {
   const size_t smem = (upd_smem_bytes(A.T, A.Mp) + 15) / 16 * 16 + sizeof(double) * A.T;
-  static size_t attr = 0;
-  static int sms = 0, forced = 0;
-  if (!sms) {
-    int dev = 0;
-    cudaGetDevice(&dev);
-    cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev);
+  static size_t attr_dev[SEIR_MAX_DEVICES] = {0};  // (the opt-in is per device)
+  size_t& attr = attr_dev[c->model->device % SEIR_MAX_DEVICES];
+  const int sms = c->model->sms;
+  static int forced = -1;
+  if (forced < 0) {
     const char* e = getenv("SEIR_UPD_MINB");  // 2 / 4: force a variant (tests)
     forced = e ? atoi(e) : 0;
   }

@@ -167,7 +167,8 @@ int seir_hmc_step_leap(seir_chains* c, int i, int num_leapfrog, double* d_u, con
   const int B = c->B;
   double *val0 = c->d_hmc_val + B, *k0 = c->d_hmc_val + 2 * B;
   const size_t smem = seir_tf_smem(m);
-  static size_t attr_smem = 0;
+  static size_t attr_dev[SEIR_MAX_DEVICES] = {0};  // (the opt-in is per device)
+  size_t& attr_smem = attr_dev[m->device % SEIR_MAX_DEVICES];
   if (smem > 48 * 1024 && attr_smem != smem) {
     SEIR_CUDA(cudaFuncSetAttribute(seir_hmc_leap_kernel<HMC_BEGIN>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
     SEIR_CUDA(cudaFuncSetAttribute(seir_hmc_leap_kernel<HMC_MID>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));

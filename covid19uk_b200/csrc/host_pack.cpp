@@ -25,8 +25,9 @@ bool pack_block_scalar(const double* __restrict__ src, uint16_t* __restrict__ ds
   int bad = 0;
   for (size_t i = 0; i < n; ++i) {
     const double v = src[i];
-    const int32_t k = (int32_t)v;  // out-of-range / NaN give INT_MIN => caught below
-    bad |= (k < 0) | (k > 65535) | ((double)k != v);
+    const bool in_range = v >= 0.0 && v <= 65535.0;  // (false for NaN; the conversion below is defined only inside the range)
+    const int32_t k = in_range ? (int32_t)v : 0;
+    bad |= !in_range | ((double)k != v);
     dst[i] = (uint16_t)k;
   }
   return bad == 0;
@@ -184,6 +185,15 @@ int seir_pack_threads(void) {
 // One batch at a time (the chain-set handle is not thread-safe anyway).
 int seir_pack_begin(const double* src, uint16_t* dst, size_t chunk_elems, size_t total_elems, int nchunks) {
   if (!g_pool) g_pool = new Pool(seir_pack_threads());
+  Pool& p = *g_pool;
+  // Workers enter run_jobs() only while holding `mu` (they raise `active` under it), so with the lock held and
+  // active == 0 no worker reads the batch descriptor and none can start: everything below is rewritten under the lock.
+  std::unique_lock<std::mutex> lk(p.mu);
+  while (p.active.load(std::memory_order_acquire) != 0) {  // stragglers of the previous batch
+    lk.unlock();
+    std::this_thread::yield();
+    lk.lock();
+  }
   if (!g_done || (int)g_done->size() < nchunks) {
     delete g_done;
     delete g_bad;
@@ -192,8 +202,6 @@ int seir_pack_begin(const double* src, uint16_t* dst, size_t chunk_elems, size_t
     g_bad = new std::vector<std::atomic<int>>(nchunks);
     g_owner = new std::vector<std::atomic<int>>(nchunks);
   }
-  Pool& p = *g_pool;
-  while (p.active.load(std::memory_order_acquire) != 0) std::this_thread::yield();  // stragglers of the previous batch
   const int nthreads = (int)p.workers.size();
   // Every thread works on the EARLIEST unfinished chunk: one job per thread per chunk (jobs of at least 8192 counts), so
   // that chunks complete one after the other at the pool's full rate and the link never waits for a burst of them.
@@ -210,7 +218,6 @@ int seir_pack_begin(const double* src, uint16_t* dst, size_t chunk_elems, size_t
     (*g_owner)[c].store(0, std::memory_order_relaxed);
   }
   {
-    std::lock_guard<std::mutex> lk(p.mu);
     p.src = src;
     p.dst = dst;
     p.chunk_elems = chunk_elems;
@@ -224,6 +231,7 @@ int seir_pack_begin(const double* src, uint16_t* dst, size_t chunk_elems, size_t
     p.next.store(0, std::memory_order_relaxed);
     ++p.generation;
   }
+  lk.unlock();
   p.cv.notify_all();
   return jpc;
 }

@@ -265,7 +265,8 @@ static int launch_ingest_tc(seir_chains* c, const EV* d_events, int b0, int nb, 
   const seir_model* m = c->model;
   const int tcmax = m->T < TC ? m->T : TC;
   const size_t smem = sizeof(int) * ((TMA ? 32 * tcmax * 6 : 32 * (TC * 3 + 1)) + 8 * 3 * 32 + 2 * TC);
-  static size_t attr = 0;
+  static size_t attr_dev[SEIR_MAX_DEVICES] = {0};  // (the opt-in is per device)
+  size_t& attr = attr_dev[c->model->device % SEIR_MAX_DEVICES];
   if (attr != smem) {
     SEIR_CUDA(cudaFuncSetAttribute(seir_ingest_kernel<TC, EV, TMA>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
     attr = smem;
@@ -494,7 +495,8 @@ static int launch_coef_tma(seir_chains* c, int tabn, cudaStream_t s, int sms, se
   if (NB < 1) return 1;  // does not fit: caller falls back
   if (NB > 4) NB = 4;
   const size_t smem = table + (size_t)nst * NB * m->Mp * 20;
-  static size_t attr = 0;
+  static size_t attr_dev[SEIR_MAX_DEVICES] = {0};  // (the opt-in is per device)
+  size_t& attr = attr_dev[c->model->device % SEIR_MAX_DEVICES];
   if (attr != smem) {
     SEIR_CUDA(cudaFuncSetAttribute(seir_coef_tma_kernel<CT, MINB>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
     attr = smem;
@@ -510,12 +512,14 @@ int seir_launch_coef(seir_chains* c, cudaStream_t s) { return seir_launch_coef_r
 
 int seir_launch_coef_range(seir_chains* c, cudaStream_t s, seir_range r) {
   const seir_model* m = c->model;
-  static int sms = 0, variant = -1;
-  if (!sms) {
-    int dev = 0;
-    cudaGetDevice(&dev);
-    cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev);
+  const int sms = m->sms;
+  static int variant = -1;
+  static bool coef_attr_dev[SEIR_MAX_DEVICES] = {false};
+  if (!coef_attr_dev[m->device % SEIR_MAX_DEVICES]) {
     SEIR_CUDA(cudaFuncSetAttribute(seir_coef_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)(sizeof(double) * SEIR_LGTAB_BIG)));
+    coef_attr_dev[m->device % SEIR_MAX_DEVICES] = true;
+  }
+  if (variant < 0) {
     // experiments: 0 direct loads; 1 TMA ring, one 800-thread CTA per SM, 16384-entry table; 2 TMA ring, one 1024-thread CTA;
     // 3 TMA ring, two 640-thread CTAs per SM with an 8192-entry table each (counts beyond the table take the Stirling path)
     // Measured at the UK size, B = 256 (CUDA events): 0: 88 us, 1: 87 us, 2: 80 us, 3: 81 us -- the kernel is bound by the

@@ -24,7 +24,8 @@ int seir_launch_propose(seir_chains* c, const seir_update_cfg& cfg, unsigned lon
                         int* d_proposal, double* d_log_u, cudaStream_t s) {
   const seir_model* m = c->model;
   const size_t smem = upd_smem_bytes(m->T, m->Mp);
-  static size_t attr = 0;
+  static size_t attr_dev[SEIR_MAX_DEVICES] = {0};  // (the opt-in is per device)
+  size_t& attr = attr_dev[c->model->device % SEIR_MAX_DEVICES];
   if (smem > 48 * 1024 && attr != smem) {
     SEIR_CUDA(cudaFuncSetAttribute(seir_propose_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
     attr = smem;

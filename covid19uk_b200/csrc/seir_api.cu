@@ -31,6 +31,21 @@ int seir_cuda_check(cudaError_t e, const char* what) {
 
 void seir_count_launch(int n) { g_launches.fetch_add(n, std::memory_order_relaxed); }
 
+// Every public entry point runs with the model's device current and leaves the caller's current device as it found it
+// (the ABI takes an explicit device at seir_model_create; torch's current device may be another one).
+struct seir_device_guard {
+  int prev = -1;
+  bool changed = false;
+  explicit seir_device_guard(int dev) {
+    if (cudaGetDevice(&prev) == cudaSuccess && prev != dev) changed = cudaSetDevice(dev) == cudaSuccess;
+  }
+  ~seir_device_guard() {
+    if (changed) cudaSetDevice(prev);
+  }
+  seir_device_guard(const seir_device_guard&) = delete;
+  seir_device_guard& operator=(const seir_device_guard&) = delete;
+};
+
 static inline int round_up(int x, int m) { return (x + m - 1) / m * m; }
 
 template <typename T>
@@ -68,12 +83,17 @@ int seir_model_create(const seir_spec* spec, int device, seir_model** out) {
     return seir_set_error(SEIR_ERR_BAD_ARG, "seir_model_create: NULL array in spec");
   if (spec->n_commute_volume < 1 || spec->n_weekday < 1)
     return seir_set_error(SEIR_ERR_SHAPE, "seir_model_create: empty commute_volume / weekday");
-  SEIR_CUDA(cudaSetDevice(device));
+  seir_device_guard guard_(device);
+  {
+    int cur = -1;
+    if (cudaGetDevice(&cur) != cudaSuccess || cur != device) return seir_set_error(SEIR_ERR_CUDA, "seir_model_create: cannot select device %d", device);
+  }
 
   seir_model* m = new (std::nothrow) seir_model();
   if (!m) return seir_set_error(SEIR_ERR_BAD_ARG, "out of host memory");
   memset(m, 0, sizeof(*m));
   m->device = device;
+  if (cudaDeviceGetAttribute(&m->sms, cudaDevAttrMultiProcessorCount, device) != cudaSuccess || m->sms < 1) m->sms = 148;
   m->M = M;
   m->T = T;
   m->Mp = round_up(M, SEIR_PAD);
@@ -163,7 +183,7 @@ int seir_model_create(const seir_spec* spec, int device, seir_model** out) {
 
 void seir_model_destroy(seir_model* m) {
   if (!m) return;
-  cudaSetDevice(m->device);
+  seir_device_guard guard_(m->device);
   cudaFree(m->d_cs); cudaFree(m->d_cst); cudaFree(m->d_cs_i8); cudaFree(m->d_cs_scale); cudaFree(m->d_rN); cudaFree(m->d_W); cudaFree(m->d_wk); cudaFree(m->d_aidx); cudaFree(m->d_tfirst); cudaFree(m->d_la);
   cudaFree(m->d_init); cudaFree(m->d_car_indptr); cudaFree(m->d_car_indices); cudaFree(m->d_car_values); cudaFree(m->d_lgtab); cudaFree(m->d_logtab);
   delete m;
@@ -180,9 +200,9 @@ int seir_model_dims(const seir_model* m, int32_t* M, int32_t* T, int32_t* P, int
 
 int seir_chains_create(const seir_model* m, int B, seir_chains** out) {
   if (!m || !out) return seir_set_error(SEIR_ERR_BAD_ARG, "seir_chains_create: NULL argument");
+  seir_device_guard guard_(m->device);
   *out = nullptr;
   if (B < 1 || B > 65535) return seir_set_error(SEIR_ERR_SHAPE, "seir_chains_create: need 1 <= num_chains <= 65535 (got %d)", B);
-  SEIR_CUDA(cudaSetDevice(m->device));
   seir_chains* c = new (std::nothrow) seir_chains();
   if (!c) return seir_set_error(SEIR_ERR_BAD_ARG, "out of host memory");
   memset(c, 0, sizeof(*c));
@@ -234,7 +254,7 @@ int seir_chains_create(const seir_model* m, int B, seir_chains** out) {
 
 void seir_chains_destroy(seir_chains* c) {
   if (!c) return;
-  cudaSetDevice(c->model->device);
+  seir_device_guard guard_(c->model->device);
   cudaFree(c->d_yse); cudaFree(c->d_yei); cudaFree(c->d_yir); cudaFree(c->d_S); cudaFree(c->d_E); cudaFree(c->d_I);
   cudaFree(c->d_Bc); cudaFree(c->d_llc_part); cudaFree(c->d_llc_sum); cudaFree(c->d_Yir); cudaFree(c->d_pa); cudaFree(c->d_psiW); cudaFree(c->d_gam);
   cudaFree(c->d_logpir); cudaFree(c->d_pm); cudaFree(c->d_scal); cudaFree(c->d_carq); cudaFree(c->d_val_part); cudaFree(c->d_psi_part);
@@ -284,6 +304,7 @@ static int check_parts(int kind, int parts) {
 
 int seir_compute_state(const seir_model* m, int B, const double* d_events, double* d_state, void* stream) {
   if (!m) return seir_set_error(SEIR_ERR_BAD_ARG, "seir_compute_state: NULL model");
+  seir_device_guard guard_(m->device);
   if (B < 1) return seir_set_error(SEIR_ERR_SHAPE, "seir_compute_state: num_chains < 1");
   SEIR_TRY(check_dev_ptr(d_events, "d_events"));
   SEIR_TRY(check_dev_ptr(d_state, "d_state"));
@@ -292,6 +313,7 @@ int seir_compute_state(const seir_model* m, int B, const double* d_events, doubl
 
 int seir_ingest_events(seir_chains* c, const double* d_events, void* stream) {
   if (!c) return seir_set_error(SEIR_ERR_BAD_ARG, "seir_ingest_events: NULL chains");
+  seir_device_guard guard_(c->model->device);
   SEIR_TRY(check_dev_ptr(d_events, "d_events"));
   SEIR_TRY(seir_launch_ingest(c, d_events, (cudaStream_t)stream));
   SEIR_TRY(seir_launch_coef(c, (cudaStream_t)stream));
@@ -300,6 +322,7 @@ int seir_ingest_events(seir_chains* c, const double* d_events, void* stream) {
 
 int seir_log_prob_cached(seir_chains* c, const double* d_theta, int kind, int parts, double* d_out, void* stream) {
   if (!c) return seir_set_error(SEIR_ERR_BAD_ARG, "seir_log_prob_cached: NULL chains");
+  seir_device_guard guard_(c->model->device);
   SEIR_TRY(check_parts(kind, parts));
   SEIR_TRY(check_dev_ptr(d_theta, "d_theta"));
   if (!d_out) return seir_set_error(SEIR_ERR_BAD_ARG, "d_out is NULL");
@@ -312,6 +335,7 @@ int seir_log_prob_cached(seir_chains* c, const double* d_theta, int kind, int pa
 int seir_log_prob_grad_cached(seir_chains* c, const double* d_theta, int kind, int parts, double* d_out, double* d_grad,
                               void* stream) {
   if (!c) return seir_set_error(SEIR_ERR_BAD_ARG, "seir_log_prob_grad_cached: NULL chains");
+  seir_device_guard guard_(c->model->device);
   SEIR_TRY(check_parts(kind, parts));
   SEIR_TRY(check_dev_ptr(d_theta, "d_theta"));
   if (!d_out || !d_grad) return seir_set_error(SEIR_ERR_BAD_ARG, "d_out / d_grad is NULL");
@@ -333,6 +357,7 @@ static int ensure_tail_stream(seir_chains* c) {
 int seir_log_prob(seir_chains* c, const double* d_events, const double* d_theta, int kind, int parts, double* d_out,
                   void* stream) {
   if (!c) return seir_set_error(SEIR_ERR_BAD_ARG, "seir_log_prob: NULL chains");
+  seir_device_guard guard_(c->model->device);
   SEIR_TRY(check_parts(kind, parts));
   if (!(parts & SEIR_PART_SEIR)) return seir_log_prob_cached(c, d_theta, kind, parts, d_out, stream);
   SEIR_TRY(check_dev_ptr(d_theta, "d_theta"));
@@ -383,7 +408,8 @@ static int log_prob_host_impl(seir_chains* c, const double* h_events, const doub
 
 int seir_log_prob_host(seir_chains* c, const double* h_events, const double* h_theta, int kind, int parts, double* h_out) {
   const int rc = log_prob_host_impl(c, h_events, h_theta, kind, parts, h_out);
-  if (rc != SEIR_OK) {  // leave nothing behind that still reads the caller's buffers: pool jobs, copies in flight
+  if (rc != SEIR_OK && c) {
+    seir_device_guard guard_(c->model->device);  // leave nothing behind that still reads the caller's buffers: pool jobs, copies in flight
     seir_pack_cancel();
     cudaDeviceSynchronize();
   }
@@ -394,7 +420,7 @@ static int log_prob_host_impl(seir_chains* c, const double* h_events, const doub
   if (!c || !h_events || !h_theta || !h_out) return seir_set_error(SEIR_ERR_BAD_ARG, "seir_log_prob_host: NULL argument");
   SEIR_TRY(check_parts(kind, parts));
   const seir_model* m = c->model;
-  SEIR_CUDA(cudaSetDevice(m->device));
+  seir_device_guard guard_(m->device);
   const int B = c->B;
   const size_t per_chain = (size_t)m->M * m->T * 3, ne = (size_t)B * per_chain, nt = (size_t)B * m->P;
   if (!c->d_stage_events) {
@@ -603,6 +629,7 @@ int64_t seir_last_h2d_bytes(const seir_chains* c) { return c ? c->last_h2d_bytes
 int seir_run_stage(seir_chains* c, int stage, const double* d_events, const double* d_theta, int kind, int parts, double* d_out,
                    double* d_grad, void* stream) {
   if (!c) return seir_set_error(SEIR_ERR_BAD_ARG, "seir_run_stage: NULL chains");
+  seir_device_guard guard_(c->model->device);
   cudaStream_t s = (cudaStream_t)stream;
   switch (stage) {
     case 0: SEIR_TRY(check_dev_ptr(d_events, "d_events")); return seir_launch_ingest(c, d_events, s);
@@ -626,6 +653,7 @@ int seir_run_stage(seir_chains* c, int stage, const double* d_events, const doub
 
 int seir_prepare_theta(seir_chains* c, const double* d_theta, int kind, void* stream) {
   if (!c) return seir_set_error(SEIR_ERR_BAD_ARG, "seir_prepare_theta: NULL chains");
+  seir_device_guard guard_(c->model->device);
   SEIR_TRY(check_dev_ptr(d_theta, "d_theta"));
   if (kind != SEIR_THETA_CONSTRAINED && kind != SEIR_THETA_UNCONSTRAINED)
     return seir_set_error(SEIR_ERR_BAD_ARG, "seir_prepare_theta: bad theta_kind");
@@ -636,6 +664,7 @@ int seir_update_step(seir_chains* c, const seir_update_spec* spec, int slot, con
                      double* d_tlp, int32_t* d_accept, int32_t* d_trace, double* d_dbg, void* stream) {
   if (!c || !spec || !d_proposal || !d_log_u || !d_tlp || !d_accept)
     return seir_set_error(SEIR_ERR_BAD_ARG, "seir_update_step: NULL argument");
+  seir_device_guard guard_(c->model->device);
   const seir_model* m = c->model;
   if (slot < 0 || slot > 3) return seir_set_error(SEIR_ERR_BAD_ARG, "seir_update_step: slot must be 0..3");
   if (spec->kind != 0 && spec->kind != 1) return seir_set_error(SEIR_ERR_BAD_ARG, "seir_update_step: kind must be 0 (move) or 1 (occult)");
@@ -657,6 +686,7 @@ int seir_hmc_step(seir_chains* c, double* d_u, const double* d_momentum, const d
                   const double* d_inv_mass, int num_leapfrog_steps, double* d_tlp, int32_t* d_accept, double* d_dbg, void* stream) {
   if (!c || !d_momentum || !d_log_u || !d_step_size || !d_tlp || !d_accept)
     return seir_set_error(SEIR_ERR_BAD_ARG, "seir_hmc_step: NULL argument");
+  seir_device_guard guard_(c->model->device);
   SEIR_TRY(check_dev_ptr(d_u, "d_u"));
   if (num_leapfrog_steps < 1 || num_leapfrog_steps > 4096)
     return seir_set_error(SEIR_ERR_BAD_ARG, "seir_hmc_step: num_leapfrog_steps out of range");
@@ -667,6 +697,7 @@ int seir_hmc_step(seir_chains* c, double* d_u, const double* d_momentum, const d
 int seir_hmc_draw(seir_chains* c, uint64_t seed, uint32_t chain_offset, uint32_t sweep_index, const double* d_inv_mass,
                   double* d_momentum, double* d_log_u, void* stream) {
   if (!c || !d_momentum || !d_log_u) return seir_set_error(SEIR_ERR_BAD_ARG, "seir_hmc_draw: NULL argument");
+  seir_device_guard guard_(c->model->device);
   SEIR_TRY(seir_launch_hmc_momentum(c, seed, chain_offset, sweep_index, d_inv_mass, d_momentum, (cudaStream_t)stream, seir_all(c)));
   return seir_launch_log_uniform(seir_all(c), seed, chain_offset, sweep_index, 0x48u, d_log_u, (cudaStream_t)stream);
 }
@@ -674,6 +705,7 @@ int seir_hmc_draw(seir_chains* c, uint64_t seed, uint32_t chain_offset, uint32_t
 int seir_propose(seir_chains* c, const seir_update_spec* spec, uint64_t seed, uint32_t chain_offset, uint32_t counter,
                  int32_t* d_proposal, double* d_log_u, void* stream) {
   if (!c || !spec || !d_proposal || !d_log_u) return seir_set_error(SEIR_ERR_BAD_ARG, "seir_propose: NULL argument");
+  seir_device_guard guard_(c->model->device);
   if ((spec->kind != 0 && spec->kind != 1) || (spec->target != 0 && spec->target != 1))
     return seir_set_error(SEIR_ERR_BAD_ARG, "seir_propose: bad kind/target");
   if (spec->kind == 0 && (spec->mmax < 1 || spec->mmax > 2 || spec->dmax < 1))
@@ -690,6 +722,7 @@ int seir_mcmc_sweep(seir_chains* c, const seir_sweep_spec* sp, uint32_t sweep_in
                     double* d_upd_tlp, int32_t* d_upd_trace, void* stream) {
   if (!c || !sp || !d_step_size || !d_tlp || !d_hmc_accept || !d_upd_accept)
     return seir_set_error(SEIR_ERR_BAD_ARG, "seir_mcmc_sweep: NULL argument");
+  seir_device_guard guard_(c->model->device);
   SEIR_TRY(check_dev_ptr(d_u, "d_u"));
   const int T = c->model->T;
   if (sp->num_leapfrog_steps < 1 || sp->num_event_time_updates < 0 || sp->mmax < 1 || sp->mmax > 2 || sp->dmax < 1 || sp->nmax < 0 ||
@@ -704,6 +737,7 @@ int seir_mcmc_burst(seir_chains* c, const seir_sweep_spec* sp, uint32_t sweep_in
                     int32_t* d_upd_accept, double* d_upd_tlp, int32_t* d_upd_trace, double* d_draws, void* stream) {
   if (!c || !sp || !d_step_size || !d_tlp || !d_hmc_accept || !d_upd_accept)
     return seir_set_error(SEIR_ERR_BAD_ARG, "seir_mcmc_burst: NULL argument");
+  seir_device_guard guard_(c->model->device);
   SEIR_TRY(check_dev_ptr(d_u, "d_u"));
   const int T = c->model->T;
   if (num_sweeps < 0 || num_sweeps > (1 << 20)) return seir_set_error(SEIR_ERR_BAD_ARG, "seir_mcmc_burst: bad num_sweeps %d", num_sweeps);
@@ -717,6 +751,7 @@ int seir_mcmc_burst(seir_chains* c, const seir_sweep_spec* sp, uint32_t sweep_in
 
 int seir_export_events(seir_chains* c, double* d_events, void* stream) {
   if (!c) return seir_set_error(SEIR_ERR_BAD_ARG, "seir_export_events: NULL chains");
+  seir_device_guard guard_(c->model->device);
   SEIR_TRY(check_dev_ptr(d_events, "d_events"));
   return seir_launch_export_events(c, d_events, (cudaStream_t)stream);
 }
@@ -725,6 +760,7 @@ int seir_simulate(const seir_model* m, int B, uint64_t seed, uint32_t chain_offs
                   const double* d_spatial_effect, const double* d_initial_state, double* d_events, void* stream) {
   if (!m || !d_alpha_path || !d_scalars || !d_spatial_effect || !d_initial_state)
     return seir_set_error(SEIR_ERR_BAD_ARG, "seir_simulate: NULL argument");
+  seir_device_guard guard_(m->device);
   if (B < 1 || B > 65535) return seir_set_error(SEIR_ERR_SHAPE, "seir_simulate: need 1 <= num_samples <= 65535");
   SEIR_TRY(check_dev_ptr(d_events, "d_events"));
   return seir_launch_simulate(m, B, seed, chain_offset, d_alpha_path, d_scalars, d_spatial_effect, d_initial_state, d_events,
@@ -733,6 +769,7 @@ int seir_simulate(const seir_model* m, int B, uint64_t seed, uint32_t chain_offs
 
 int seir_reproduction_number(seir_chains* c, const double* d_theta, double* d_rit, void* stream) {
   if (!c || !d_rit) return seir_set_error(SEIR_ERR_BAD_ARG, "seir_reproduction_number: NULL argument");
+  seir_device_guard guard_(c->model->device);
   SEIR_TRY(check_dev_ptr(d_theta, "d_theta"));
   if (c->model->initial_step != 0)
     return seir_set_error(SEIR_ERR_UNSUPPORTED, "seir_reproduction_number: the reference evaluates the NGM at t = 0..T-1 of the inference window (initial_step 0)");
@@ -741,12 +778,14 @@ int seir_reproduction_number(seir_chains* c, const double* d_theta, double* d_ri
 
 int seir_pressure_components(seir_chains* c, const double* d_theta, double* d_within, double* d_between, void* stream) {
   if (!c || !d_within || !d_between) return seir_set_error(SEIR_ERR_BAD_ARG, "seir_pressure_components: NULL argument");
+  seir_device_guard guard_(c->model->device);
   SEIR_TRY(check_dev_ptr(d_theta, "d_theta"));
   return seir_launch_pressure(c, d_theta, d_within, d_between, (cudaStream_t)stream);
 }
 
 int seir_export_contraction(seir_chains* c, double* d_bc, void* stream) {
   if (!c) return seir_set_error(SEIR_ERR_BAD_ARG, "seir_export_contraction: NULL chains");
+  seir_device_guard guard_(c->model->device);
   SEIR_TRY(check_dev_ptr(d_bc, "d_bc"));
   const seir_model* m = c->model;
   SEIR_CUDA(cudaMemcpy2DAsync(d_bc, sizeof(double) * m->M, c->d_Bc, sizeof(double) * m->Mp, sizeof(double) * m->M, (size_t)c->B * m->T,
@@ -756,6 +795,7 @@ int seir_export_contraction(seir_chains* c, double* d_bc, void* stream) {
 
 int seir_chain_flags(const seir_chains* c, int32_t* d_flags_out, void* stream) {
   if (!c || !d_flags_out) return seir_set_error(SEIR_ERR_BAD_ARG, "seir_chain_flags: NULL argument");
+  seir_device_guard guard_(c->model->device);
   SEIR_CUDA(cudaMemcpyAsync(d_flags_out, c->d_flags, sizeof(int) * (size_t)c->B, cudaMemcpyDeviceToDevice, (cudaStream_t)stream));
   return SEIR_OK;
 }

@@ -15,6 +15,7 @@
 #define SEIR_LL_THREADS 128  // metapopulations per CTA in the log-likelihood kernel
 #define SEIR_NSCAL 16        // per-chain scalar slots
 #define SEIR_MAX_SPLITS 16    // max day splits of the log-likelihood grid
+#define SEIR_MAX_DEVICES 64    // per-device memos of kernel attributes (cudaFuncSetAttribute applies to the current device)
 
 // per-chain scalar slots (d_scal[b*SEIR_NSCAL + k])
 enum {
@@ -28,6 +29,7 @@ enum {
 
 struct seir_model {
   int device;
+  int sms;  // multiprocessors of `device`
   int M, T, Mp, P;
   int initial_step;
   double dt, nu, rate_eps, car_log_det_scale;

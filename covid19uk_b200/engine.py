@@ -90,6 +90,10 @@ class SeirEngine:
         nat.check(self.lib.seir_model_create(byref(spec), self.device.index, byref(handle)))
         self._model = handle
         self._chains: dict[int, c_void_p] = {}
+        # generation of the events held by each chain set: 0 = nothing ingested yet, +1 per ingest.  The samplers' event
+        # handles (gemlib.mcmc.DeviceEvents, inference.sampler.ChainSet) remember the generation they were made at, so a
+        # later explicit-events evaluation with the same number of chains cannot silently replace their in-place state.
+        self._generation: dict[int, int] = {}
         self.initial_state = init
         self.chain_offset = 0  # global id of this rank's first chain (multi-GPU: set by the launcher)
 
@@ -115,6 +119,21 @@ class SeirEngine:
             nat.check(self.lib.seir_chains_create(self._model, int(B), byref(h)))
             self._chains[B] = h
         return h
+
+    def generation(self, B: int) -> int:
+        return self._generation.get(int(B), 0)
+
+    def _ingested(self, B: int):
+        self._generation[int(B)] = self._generation.get(int(B), 0) + 1
+
+    def require_events(self, B: int, what: str, generation=None):
+        """The *_cached / sampler / analytics entry points read the caches of the last ingested event tensor."""
+        g = self._generation.get(int(B), 0)
+        if g == 0:
+            raise RuntimeError(f"{what}: no events have been ingested for a set of {B} chains (call ingest() / log_prob(events, ...) first)")
+        if generation is not None and generation != g:
+            raise RuntimeError(f"{what}: the {B}-chain caches were re-ingested (generation {g}) after this handle was made "
+                               f"(generation {generation}); its in-place sampler state is gone")
 
     def chains_bytes(self, B: int) -> int:
         return int(self.lib.seir_chains_bytes(self.chains(B)))
@@ -144,10 +163,13 @@ class SeirEngine:
     def ingest(self, events: torch.Tensor):
         ev = self.to_device(events, (self.M, self.T, 3))
         nat.check(self.lib.seir_ingest_events(self.chains(ev.shape[0]), c_void_p(ev.data_ptr()), self._stream()))
+        self._ingested(ev.shape[0])
         return ev.shape[0]
 
     def log_prob_cached(self, theta, kind=nat.THETA_CONSTRAINED, parts=nat.PART_SEIR):
         th = self.to_device(theta, (self.P,))
+        if parts & nat.PART_SEIR:
+            self.require_events(th.shape[0], "log_prob_cached")
         out = torch.empty((th.shape[0],), dtype=torch.float64, device=self.device)
         nat.check(self.lib.seir_log_prob_cached(self.chains(th.shape[0]), c_void_p(th.data_ptr()), kind, parts, c_void_p(out.data_ptr()), self._stream()))
         return out
@@ -160,10 +182,14 @@ class SeirEngine:
         if out is None:
             out = torch.empty((th.shape[0],), dtype=torch.float64, device=self.device)
         nat.check(self.lib.seir_log_prob(self.chains(ev.shape[0]), c_void_p(ev.data_ptr()), c_void_p(th.data_ptr()), kind, parts, c_void_p(out.data_ptr()), self._stream()))
+        if parts & nat.PART_SEIR:
+            self._ingested(ev.shape[0])
         return out
 
     def value_and_grad_cached(self, theta, kind=nat.THETA_UNCONSTRAINED, parts=nat.PART_JOINT):
         th = self.to_device(theta, (self.P,))
+        if parts & nat.PART_SEIR:
+            self.require_events(th.shape[0], "value_and_grad_cached")
         out = torch.empty((th.shape[0],), dtype=torch.float64, device=self.device)
         grad = torch.empty_like(th)
         nat.check(self.lib.seir_log_prob_grad_cached(self.chains(th.shape[0]), c_void_p(th.data_ptr()), kind, parts, c_void_p(out.data_ptr()), c_void_p(grad.data_ptr()), self._stream()))
@@ -174,6 +200,8 @@ class SeirEngine:
         B = h_events.shape[0]
         assert h_events.dtype == torch.float64 and h_events.is_contiguous() and not h_events.is_cuda
         nat.check(self.lib.seir_log_prob_host(self.chains(B), c_void_p(h_events.data_ptr()), c_void_p(h_theta.data_ptr()), kind, parts, c_void_p(h_out.data_ptr())))
+        if parts & nat.PART_SEIR:
+            self._ingested(B)
         return h_out
 
     def last_h2d_bytes(self, B: int) -> int:
@@ -183,12 +211,15 @@ class SeirEngine:
     def run_stage(self, B, stage, events=None, theta=None, kind=nat.THETA_CONSTRAINED, parts=nat.PART_SEIR, out=None, grad=None):
         """Enqueue one kernel of the pipeline (measurement hook, see seir_run_stage)."""
         ptr = lambda t: c_void_p(t.data_ptr()) if t is not None else c_void_p(0)
+        if stage == 0:
+            self._ingested(B)
         nat.check(self.lib.seir_run_stage(self.chains(B), stage, ptr(events), ptr(theta), kind, parts, ptr(out), ptr(grad), self._stream()))
 
     # ---- a6 / a7: discrete updates ----
     def prepare_theta(self, theta, kind=nat.THETA_UNCONSTRAINED):
         """Load the rate factors of `theta` [B,P] for the discrete updates (after any change of theta)."""
         th = self.to_device(theta, (self.P,))
+        self.require_events(th.shape[0], "prepare_theta")
         nat.check(self.lib.seir_prepare_theta(self.chains(th.shape[0]), c_void_p(th.data_ptr()), kind, self._stream()))
         return th
 
@@ -198,6 +229,7 @@ class SeirEngine:
         proposal int32 [B,4,MMAX] (rows m, t, delta_t, x_star), log_u [B], tlp [B] (updated in place).
         Returns (is_accepted [B] int32, trace [B,4,MMAX] int32, debug [B,4] or None)."""
         B = tlp.shape[0]
+        self.require_events(B, "update_step")
         prop = torch.as_tensor(proposal, dtype=torch.int32, device=self.device).contiguous()
         lu = torch.as_tensor(log_u, dtype=torch.float64, device=self.device).contiguous()
         assert tuple(prop.shape) == (B, 4, nat.MMAX) and tlp.is_cuda and tlp.dtype == torch.float64
@@ -216,6 +248,7 @@ class SeirEngine:
         float64 tensor updated in place.  Returns (tlp [B], is_accepted [B] int32, debug [B,4] or None)."""
         assert u.is_cuda and u.dtype == torch.float64 and u.is_contiguous() and u.dim() == 2 and u.shape[1] == self.P
         B = u.shape[0]
+        self.require_events(B, "hmc_step")
         dev = lambda a: torch.as_tensor(a, dtype=torch.float64, device=self.device).contiguous()
         mom, lu = dev(momentum), dev(log_u)
         st = dev(step_size).expand(B).contiguous() if dev(step_size).dim() == 0 else dev(step_size)
@@ -244,6 +277,7 @@ class SeirEngine:
     # ---- device-side proposals and the fused sweep (a8) ----
     def propose(self, spec: "nat.SeirUpdateSpec", B, seed, chain_offset, counter):
         """Draw one proposal per chain on the device -> (proposal int32 [B,4,MMAX], log_u [B])."""
+        self.require_events(B, "propose")
         prop = torch.empty((B, 4, nat.MMAX), dtype=torch.int32, device=self.device)
         lu = torch.empty((B,), dtype=torch.float64, device=self.device)
         nat.check(self.lib.seir_propose(self.chains(B), byref(spec), int(seed), int(chain_offset), int(counter),
@@ -254,6 +288,7 @@ class SeirEngine:
                    hmc_dbg=None, upd_tlp=None, upd_trace=None):
         """One Metropolis-within-Gibbs sweep for every chain; all tensors are caller-owned CUDA tensors."""
         B = u.shape[0]
+        self.require_events(B, "mcmc_sweep")
         p = lambda t: c_void_p(t.data_ptr()) if t is not None else c_void_p(0)
         nat.check(self.lib.seir_mcmc_sweep(self.chains(B), byref(spec), int(sweep_index), p(u), p(step_size), p(inv_mass), p(tlp),
                                            p(hmc_accept), p(hmc_dbg), p(upd_accept), p(upd_tlp), p(upd_trace), self._stream()))
@@ -263,12 +298,14 @@ class SeirEngine:
         """``num_sweeps`` sweeps with a fixed step size / mass matrix in one call (seir_mcmc_burst): the result tensors carry
         a leading [num_sweeps] axis; chains and traces are bit-identical to ``num_sweeps`` calls of :meth:`mcmc_sweep`."""
         B = u.shape[0]
+        self.require_events(B, "mcmc_burst")
         p = lambda t: c_void_p(t.data_ptr()) if t is not None else c_void_p(0)
         nat.check(self.lib.seir_mcmc_burst(self.chains(B), byref(spec), int(sweep_index0), int(num_sweeps), p(u), p(step_size), p(inv_mass),
                                            p(tlp), p(hmc_accept), p(hmc_dbg), p(upd_accept), p(upd_tlp), p(upd_trace), p(draws),
                                            self._stream()))
 
     def export_events(self, B: int) -> torch.Tensor:
+        self.require_events(B, "export_events")
         out = torch.empty((B, self.M, self.T, 3), dtype=torch.float64, device=self.device)
         nat.check(self.lib.seir_export_events(self.chains(B), c_void_p(out.data_ptr()), self._stream()))
         return out
@@ -294,6 +331,7 @@ class SeirEngine:
         """R_it [B,T,M] (posterior/reproduction_number.py:13-45); `theta` [B,P] CONSTRAINED; events ingested before."""
         th = self.to_device(theta, (self.P,))
         B = th.shape[0]
+        self.require_events(B, "reproduction_number")
         out = torch.empty((B, self.T, self.M), dtype=torch.float64, device=self.device)
         nat.check(self.lib.seir_reproduction_number(self.chains(B), c_void_p(th.data_ptr()), c_void_p(out.data_ptr()), self._stream()))
         return out
@@ -302,6 +340,7 @@ class SeirEngine:
         """(within, between) [B,M] infection pressure at the final state (posterior/within_between.py:13-56)."""
         th = self.to_device(theta, (self.P,))
         B = th.shape[0]
+        self.require_events(B, "pressure_components")
         within = torch.empty((B, self.M), dtype=torch.float64, device=self.device)
         between = torch.empty_like(within)
         nat.check(self.lib.seir_pressure_components(self.chains(B), c_void_p(th.data_ptr()), c_void_p(within.data_ptr()),
@@ -310,6 +349,7 @@ class SeirEngine:
 
     def export_contraction(self, B: int) -> torch.Tensor:
         """The cached contraction Cstar (I/N) of the ingested events, [B,T,M]."""
+        self.require_events(B, "export_contraction")
         out = torch.empty((B, self.T, self.M), dtype=torch.float64, device=self.device)
         nat.check(self.lib.seir_export_contraction(self.chains(B), c_void_p(out.data_ptr()), self._stream()))
         return out

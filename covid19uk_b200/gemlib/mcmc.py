@@ -36,12 +36,19 @@ class DeviceEvents:
     def __init__(self, engine, num_chains):
         self.engine = engine
         self.num_chains = int(num_chains)
+        self.generation = engine.generation(self.num_chains)  # of the ingest these events came from
+
+    def check(self, what="DeviceEvents"):
+        """Raise if the chain set was re-ingested since (e.g. by ``model.log_prob(explicit events)`` with as many chains):
+        the in-place sampler state this handle stands for would be gone."""
+        self.engine.require_events(self.num_chains, what, self.generation)
 
     @property
     def shape(self):
         return (self.num_chains, self.engine.M, self.engine.T, 3)
 
     def to_tensor(self) -> torch.Tensor:
+        self.check("DeviceEvents.to_tensor")
         return self.engine.export_events(self.num_chains)
 
     def numpy(self):
@@ -50,6 +57,7 @@ class DeviceEvents:
 
 def _as_device_events(engine, events):
     if isinstance(events, DeviceEvents):
+        events.check()
         return events
     B = engine.ingest(events)
     return DeviceEvents(engine, B)

@@ -188,7 +188,7 @@ def run_mcmc(joint_log_prob_fn, current_state, param_bijector, initial_condition
 
     print("Sampling...", file=sys.stderr, flush=True)
     # per chain: mean step size over the last half of the final adaptation window (inference.py:437-439)
-    hmc_kernel_kwargs["step_size"] = trace["hmc"]["step_size"][-(last_window_size // 2):].mean(dim=0)
+    hmc_kernel_kwargs["step_size"] = trace["hmc"]["step_size"][(-last_window_size) // 2:].mean(dim=0)
     fixed_sample, kernel = make_fixed_window_sampler(
         config["num_burst_samples"], joint_log_prob_fn, hmc_kernel_kwargs, event_kernel_kwargs, trace_fn=trace_results_fn,
         seed=tm.SeedPath(seed_base, 1 + offset), jit_compile=True)

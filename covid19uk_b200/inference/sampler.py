@@ -74,7 +74,7 @@ class RunningVariance:
     @classmethod
     def from_draws(cls, draws: torch.Tensor):
         """draws [n, B, P] (unconstrained)."""
-        half = draws[-(draws.shape[0] // 2):]
+        half = draws[(-draws.shape[0]) // 2:]  # inference.py:38: `-n // 2` is (-n)//2, the last ceil(n/2) draws
         return cls(draws.shape[0] / 2, half.mean(dim=0), half.var(dim=0, unbiased=False))
 
     def update(self, x: torch.Tensor):
@@ -99,6 +99,7 @@ class ChainSet:
         if self.u.shape[0] == 1 and self.B > 1:
             self.u = self.u.expand(self.B, -1).contiguous()
         engine.ingest(ev)
+        self.generation = engine.generation(self.B)
         self.tlp = engine.log_prob_cached(self.u, nat.THETA_UNCONSTRAINED, nat.PART_JOINT)
         self.spec = nat.SeirSweepSpec(
             num_leapfrog_steps=int(num_leapfrog_steps), num_event_time_updates=int(config["num_event_time_updates"]),
@@ -114,11 +115,14 @@ class ChainSet:
 
     def refresh(self):
         """Rebuild every cache from the current events (bounds floating-point drift of the incremental updates)."""
+        self.engine.require_events(self.B, "ChainSet.refresh", self.generation)
         ev = self.engine.export_events(self.B)
         self.engine.ingest(ev)
+        self.generation = self.engine.generation(self.B)
         self.tlp = self.engine.log_prob_cached(self.u, nat.THETA_UNCONSTRAINED, nat.PART_JOINT)
 
     def events(self) -> torch.Tensor:
+        self.engine.require_events(self.B, "ChainSet.events", self.generation)
         return self.engine.export_events(self.B)
 
     def sample(self, num_draws, step_size, inv_mass=None, dual_averaging: DualAveraging | None = None,
@@ -126,6 +130,7 @@ class ChainSet:
         """Run ``num_draws`` sweeps.  Returns (draws, trace): ``draws`` = [u [n,B,P], events [n,B,M,T,3] or None],
         ``trace`` = the dictionary of trace_results_fn (inference.py:245-282) with a chain axis after the draw axis."""
         B, P, dev = self.B, self.engine.P, self.engine.device
+        self.engine.require_events(B, "ChainSet.sample", self.generation)
         mm = self.spec.mmax
         step = torch.as_tensor(step_size, dtype=torch.float64, device=dev).expand(B).contiguous().clone()
         n = int(num_draws)

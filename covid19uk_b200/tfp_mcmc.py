@@ -115,7 +115,7 @@ def get_weighted_running_variance(draws):
     """inference.py:36-47: mean / variance of the last half of a window, weighted as n/2 samples.
     ``draws`` [n, B, P] (unconstrained)."""
     n = draws.shape[0]
-    half = draws[-(n // 2):] if n >= 2 else draws
+    half = draws[(-n) // 2:]  # `draws[-n // 2:]` parses as (-n)//2: the last ceil(n/2) draws (13 of 25)
     return RunningVariance.from_stats(n / 2, half.mean(dim=0), half.var(dim=0, unbiased=False))
 
 

@@ -24,6 +24,7 @@ def load():
             build()
         _LIB = ctypes.CDLL(path)
         _LIB.seir_oracle_log_prob.restype = ctypes.c_int
+        _LIB.seir_oracle_joint_log_prob.restype = ctypes.c_int
         _LIB.seir_oracle_max_threads.restype = ctypes.c_int
     return _LIB
 
@@ -46,6 +47,31 @@ def log_prob(consts, initial_state, events, theta, num_threads=0):
     if rc != 0:
         raise MemoryError("seir_oracle_log_prob")
     return out
+
+
+def joint_log_prob(consts, car, initial_state, events, u, want_grad=False, num_threads=0):
+    """joint_log_prob(unconstrained u [B,P], events [B,M,T,3]) of inference.py:537-557 -> [B] (and its gradient [B,P]);
+    consts from seir_oracle.rate_constants, car from seir_oracle.car_constants."""
+    lib = load()
+    ev = np.ascontiguousarray(events, np.float64)
+    uu = np.ascontiguousarray(u, np.float64)
+    B, M, T, _ = ev.shape
+    assert uu.shape == (B, 6 + (T - 1) + M)
+    times = np.arange(T)
+    W = np.ascontiguousarray(consts["W"][np.clip(times, 0, len(consts["W"]) - 1)])
+    wk = np.ascontiguousarray(consts["weekday_c"][np.clip(times, 0, len(consts["weekday_c"]) - 1)])
+    L = np.ascontiguousarray(car["scale_tril"], np.float64)
+    out = np.empty(B, np.float64)
+    grad = np.empty_like(uu) if want_grad else None
+    p = lambda a: a.ctypes.data_as(ctypes.c_void_p) if a is not None else ctypes.c_void_p(0)
+    keep = [np.ascontiguousarray(consts["Cstar"]), np.ascontiguousarray(consts["N"]), W, wk,
+            np.ascontiguousarray(consts["log_area_c"]), np.ascontiguousarray(initial_state, np.float64)]
+    rc = lib.seir_oracle_joint_log_prob(ctypes.c_int(B), ctypes.c_int(M), ctypes.c_int(T), *[p(a) for a in keep], p(L),
+                                        ctypes.c_double(float(car["log_det_scale"])), p(ev), p(uu), ctypes.c_double(0.28),
+                                        ctypes.c_double(1e-9), p(out), p(grad), ctypes.c_int(num_threads))
+    if rc != 0:
+        raise MemoryError("seir_oracle_joint_log_prob")
+    return (out, grad) if want_grad else out
 
 
 def max_threads():

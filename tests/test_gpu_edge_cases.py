@@ -76,3 +76,36 @@ def test_epidemic_without_events():
         ref = om.joint_log_prob(cs.u[b].cpu().numpy(), ev[b])
         assert abs(fresh[b] - ref) <= 1e-10 * abs(ref)
     eng.close()
+
+
+def test_cached_entry_points_refuse_chain_sets_without_events_and_stale_handles():
+    """chain sets are keyed by the number of chains.  A *_cached / analytics call on a set that never ingested
+    events must raise (not return a finite number computed on all-zero caches), and a sampler handle must notice that a later
+    explicit-events evaluation with as many chains re-ingested its caches."""
+    from covid19uk_b200 import _native as nat
+    from covid19uk_b200 import synthetic as syn
+    from covid19uk_b200.engine import SeirEngine
+    from covid19uk_b200.gemlib.mcmc import DeviceEvents
+    from covid19uk_b200.inference.sampler import ChainSet
+    from oracle import seir_oracle as so
+
+    M, T, B = 16, 30, 3
+    pb = syn.make_problem(M, T, chains=B, seed=9)
+    eng = SeirEngine(pb["covariates"], pb["initial_state"], 0, T)
+    u = so.unconstrain(pb["theta"])
+    with pytest.raises(RuntimeError, match="no events have been ingested"):
+        eng.log_prob_cached(u, nat.THETA_UNCONSTRAINED, nat.PART_JOINT)
+    with pytest.raises(RuntimeError, match="no events have been ingested"):
+        eng.reproduction_number(pb["theta"])
+    # priors only do not read the caches
+    assert bool(np.isfinite(eng.log_prob_cached(u, nat.THETA_UNCONSTRAINED, nat.PART_PRIORS | nat.PART_ILDJ).cpu().numpy()).all())
+    cfg = dict(dmax=T - 1, nmax=25, m=2, occult_nmax=15, num_event_time_updates=1)
+    cs = ChainSet(eng, pb["events"], u, cfg, [T - 21, T], seed=1, num_leapfrog_steps=2)
+    handle = DeviceEvents(eng, B)
+    cs.sample(1, step_size=1e-4, collect_draws=False)
+    eng.log_prob(pb["events"], pb["theta"])  # explicit events, same B: re-ingests the caches
+    with pytest.raises(RuntimeError, match="re-ingested"):
+        cs.sample(1, step_size=1e-4, collect_draws=False)
+    with pytest.raises(RuntimeError, match="re-ingested"):
+        handle.to_tensor()
+    eng.close()

@@ -193,3 +193,34 @@ np.savez(sys.argv[1], u=cs.u.cpu().numpy(), ev=cs.events().cpu().numpy(), tlp=cs
             outs.append(dict(np.load(path)))
     for k in outs[0]:
         assert np.array_equal(outs[0][k], outs[1][k]), k
+
+
+def test_uk_256_chains_two_fused_sweeps_vs_oracle():
+    """BASELINE.json configs[2] at full size (382 x 84, 256 chains): two fused sweeps; chains 0, 127, 255 are
+    re-evaluated from scratch by the oracle -- the incrementally maintained target log-prob is the oracle's joint
+    log-prob of the chain's new parameters and events (1e-10), events stay non-negative integers, states valid."""
+    from covid19uk_b200 import synthetic as syn
+    from covid19uk_b200.engine import SeirEngine
+    from covid19uk_b200.inference.sampler import ChainSet
+    from oracle import seir_oracle as so
+
+    M, T, B = 382, 84, 256
+    pb = syn.make_problem(M, T, chains=B, seed=0, distinct=8)
+    eng = SeirEngine(pb["covariates"], pb["initial_state"], 0, T)
+    om = so.OracleModel(pb["covariates"], pb["initial_state"], 0, T)
+    u = so.unconstrain(pb["theta"])
+    cs = ChainSet(eng, pb["events"], u, CFG, [T - 21, T], seed=11)
+    _, trace = cs.sample(2, step_size=2e-5, collect_draws=False)
+    ev, un, tlp = cs.events().cpu().numpy(), cs.u.cpu().numpy(), cs.tlp.cpu().numpy()
+    assert np.all(ev >= 0) and np.array_equal(ev, np.floor(ev))
+    assert int(eng.chain_flags(B).abs().sum()) == 0
+    moved = 0
+    for b in (0, 127, 255):
+        ref = om.joint_log_prob(un[b], ev[b])
+        assert abs(tlp[b] - ref) <= 1e-10 * abs(ref), (b, tlp[b], ref)
+        assert np.all(so.compute_state(pb["initial_state"], ev[b]) >= 0)
+        moved += int(np.any(ev[b] != pb["events"][b]))
+    # the trace rows agree with the final target log-prob (last kernel of the last sweep)
+    assert np.array_equal(trace["occult/E->I"]["target_log_prob"][-1].cpu().numpy(), tlp)
+    assert any(float(v["is_accepted"].double().mean()) > 0 for v in trace.values())
+    eng.close()

@@ -69,3 +69,22 @@ def test_host_packer_is_exact_or_refuses():
         assert np.all(dst[(nchunks - 1) * chunk:] == 7)
     else:  # the pool was faster than this thread: then it narrowed the chunk itself
         assert lib.seir_pack_wait(nchunks - 1, jpc) == 1
+
+
+def test_window_slices_follow_the_reference_precedence():
+    """inference.py:38 slices ``draws[-n // 2:]`` = ``draws[(-n) // 2:]``: the last ceil(n/2) draws (13 of 25), with weight
+    n/2; inference.py:437-439 does the same with the step sizes of the last window."""
+    import torch
+    from covid19uk_b200 import tfp_mcmc as tm
+    from covid19uk_b200.inference.sampler import RunningVariance
+
+    for n in (25, 50, 7, 1):
+        draws = torch.arange(n, dtype=torch.float64).reshape(n, 1, 1) ** 2
+        half = draws[(-n) // 2:]
+        assert half.shape[0] == (n + 1) // 2
+        rv = tm.get_weighted_running_variance(draws)
+        assert rv.num_samples == n / 2
+        assert torch.equal(rv.mean, half.mean(dim=0))
+        assert torch.allclose(rv.variance(), half.var(dim=0, unbiased=False))
+        rv2 = RunningVariance.from_draws(draws)
+        assert torch.equal(rv2.mean, half.mean(dim=0)) and rv2.n == n / 2
