@@ -18,7 +18,7 @@ HERE = os.path.dirname(os.path.abspath(__file__))
 CSRC = os.path.join(HERE, "csrc")
 LIBDIR = os.path.join(HERE, "lib")
 LIBNAME = "libseir_b200.so"
-SOURCES = ["seir_api.cu", "ingest.cu", "contract.cu", "contract_i8.cu", "loglik.cu", "delta.cu", "hmc.cu", "propose.cu", "sweep.cu", "analytics.cu", "simulate.cu", "host_pack.cpp"]
+SOURCES = ["seir_api.cu", "ingest.cu", "contract.cu", "contract_i8.cu", "loglik.cu", "delta.cu", "hmc.cu", "hmc_traj.cu", "propose.cu", "sweep.cu", "analytics.cu", "simulate.cu", "host_pack.cpp"]
 CXX_FLAGS = ["-O3", "-std=c++17", "-fPIC", "-pthread"]
 NVCC_FLAGS = [
     "-O3",

@@ -212,6 +212,8 @@ int seir_launch_hmc(seir_chains* c, double* d_u, const double* d_momentum, const
   if (d_momentum)
     SEIR_CUDA(cudaMemcpyAsync(c->d_hmc_p, d_momentum, sizeof(double) * (size_t)B * P, cudaMemcpyDeviceToDevice, s));
   const seir_range all = seir_all(c);
+  if (seir_hmc_traj_applies(c))  // the whole transition in one persistent kernel (hmc_traj.cu)
+    return seir_launch_hmc_traj(c, d_u, d_log_u, d_step, d_inv_mass, num_leapfrog, d_tlp, nullptr, d_accept, d_dbg, s, all, 0);
   if ((rc = seir_hmc_step_begin(c, d_u, s, all)) != SEIR_OK) return rc;
   for (int i = 0; i <= num_leapfrog; ++i)
     if ((rc = seir_hmc_step_leap(c, i, num_leapfrog, d_u, d_log_u, d_step, d_inv_mass, d_tlp, nullptr, d_accept, d_dbg, s, all)) != SEIR_OK) return rc;

@@ -1,0 +1,964 @@
+// a9, persistent form: ONE CTA runs a chain's WHOLE HMC transition -- the 1 + L value-and-gradient evaluations of the joint
+// log-density, the leapfrog kicks and drifts, the parameter-derived rate factors and the Metropolis decision -- without
+// leaving the SM (tfp.experimental.mcmc.PreconditionedHamiltonianMonteCarlo [recall]; call site
+// mcmc_kernel_factory.py:14-29, kwargs inference.py:324-329).
+//
+// Why: the round-1 path launched [log-likelihood kernel, leapfrog kernel] x 17 per sweep.  Every log-likelihood launch
+// re-streamed the parameter-free caches of all chains (yse, S, I, Bc: 20 B per cell, 166 MB at 256 UK chains, more than
+// the 126 MB L2) from HBM, and every leapfrog kernel was a latency-bound O(P) pass over global partials: 17 x (58 + 21) us.
+// Here a chain's working set is read from HBM ONCE per transition:
+//   * evaluation 0 streams the four cache arrays through a shared-memory ring (1-D bulk copies, cp.async.bulk + mbarrier),
+//     and, while it computes, re-packs every cell into 16 bytes -- {y:16 | I:24 | S-y:24 bits, W_t Bc f64} -- in a
+//     per-CTA scratch region (516 KB at the UK size);
+//   * evaluations 1..L stream the packed scratch, which stays in L2: 148 CTAs x 516 KB = 76 MB (measured,
+//     tools/ubench/l2_stream.cu: per-CTA regions adding up to 92 MB re-stream at 14 TB/s, 111 MB fall back to the HBM rate);
+//   * a producer warp keeps the ring full across evaluations (the data does not depend on the parameters), so the copy of
+//     the next evaluation's first stages overlaps the O(P) leapfrog arithmetic, which runs on shared memory with
+//     CTA-level barriers instead of kernel boundaries.
+// Results do not depend on the launch shape: one CTA <-> one chain, fixed thread <-> metapopulation mapping, fixed
+// reduction trees.
+#include <stdlib.h>
+
+#include "cell.cuh"
+#include "philox.cuh"
+#include "seir_internal.cuh"
+#include "tma.cuh"
+
+#define TJ_DAYS 4    // days per ring stage = one column-sum butterfly group
+#define TJ_NACC 8
+#define HALF_LOG_2PI 0.9189385332046727
+
+struct traj_args {
+  // model
+  int M, T, Mp, P, car_prior;
+  double dt, eps, nu, log_p_nu, car_log_det_scale;
+  const double *W, *wk, *la, *rN, *car_values;
+  const int *aidx, *tfirst, *car_indptr, *car_indices;
+  const double2* logtab;
+  // events-only caches of the chain set
+  const int *yse, *S, *I;
+  const double* Bc;
+  const long long *Yir, *Rir, *sumYei, *sumEres;
+  const int* flags;
+  const double *llc_sum, *llc_adj;
+  int nllc;
+  // parameter-derived arrays left behind for the discrete updates (what tf_theta_prep writes)
+  double *pa, *psiW, *gam, *logpir, *pm, *scal;
+  // the transition
+  double* u;                // [B][P] in / out
+  const double* momentum;   // [B][P]
+  const double *log_u, *step, *inv_mass;
+  double *tlp, *tlp_trace;
+  int* accept;
+  double* dbg;
+  unsigned char* scratch;   // [gridDim.x][T][Mp] x 16 bytes
+  int b0, nb, L;
+  int sd, pd;               // days per source / packed ring stage (multiples of TJ_DAYS)
+  unsigned stage_bytes;     // bytes of one ring stage
+};
+
+// phase timestamps (SM clock) of CTA 0's first chain: build with SEIR_NVCC_EXTRA=-DSEIR_TRAJ_DEBUG, read with seir_debug_traj
+#ifdef SEIR_TRAJ_DEBUG
+__device__ long long g_tj_dbg[1024];
+#define TJT(k) do { if (blockIdx.x == 0 && threadIdx.x == 0 && kchain == 0 && (k) < 1024) g_tj_dbg[(k)] = clock64(); } while (0)
+extern "C" int seir_debug_traj(long long* h) { return (int)cudaMemcpyFromSymbol(h, g_tj_dbg, sizeof(long long) * 1024); }
+#else
+#define TJT(k) do { } while (0)
+#endif
+
+__device__ __forceinline__ void tj_bar(int nthr) { asm volatile("bar.sync 1, %0;" ::"r"(nthr) : "memory"); }
+
+__device__ __forceinline__ double tj_softplus(double x) { return fmax(x, 0.0) + log1p(exp(-fabs(x))); }
+__device__ __forceinline__ double tj_sigmoid(double x) { return 1.0 / (1.0 + exp(-x)); }
+__device__ __forceinline__ double tj_normal_lp(double x, double s) {
+  const double z = x / s;
+  return -0.5 * z * z - (HALF_LOG_2PI + log(s));
+}
+
+// transposing butterfly: lanes hold a[0..3] (4 days); afterwards lane 8*j holds the warp total of a[j]
+__device__ __forceinline__ double tj_warp_sum4_transposed(const double (&a)[4]) {
+  const int lane = threadIdx.x & 31;
+  const bool up16 = lane & 16, up8 = lane & 8;
+  double k0 = up16 ? a[2] : a[0], k1 = up16 ? a[3] : a[1];
+  const double s0 = up16 ? a[0] : a[2], s1 = up16 ? a[1] : a[3];
+  k0 += __shfl_xor_sync(0xffffffffu, s0, 16);
+  k1 += __shfl_xor_sync(0xffffffffu, s1, 16);
+  double c = up8 ? k1 : k0;
+  c += __shfl_xor_sync(0xffffffffu, up8 ? k0 : k1, 8);
+  c += __shfl_xor_sync(0xffffffffu, c, 4);
+  c += __shfl_xor_sync(0xffffffffu, c, 2);
+  c += __shfl_xor_sync(0xffffffffu, c, 1);
+  return c;  // day index of this lane's total: ((lane >> 4) & 1) * 2 + ((lane >> 3) & 1)
+}
+
+// TJ_NACC accumulators reduced over the NTHR threads: inside a warp through its shared-memory tile (tj_col_reduce, 4
+// accumulators per round: 8-wide shuffle butterflies cost 80 SHFL per warp), then an ordered pass over the warp partials.
+// Bitwise reproducible; every thread returns with the totals.
+template <int NTHR>
+__device__ __forceinline__ void tj_block_sum(double (&v)[TJ_NACC], double* tile, double (*red)[TJ_NACC]);
+
+struct tj_smem {  // carved from dynamic shared memory after the ring
+  double *u, *p, *g, *im;                    // [P]
+  double *pa, *gam, *yir, *rir, *col, *cs;   // [Tp]
+  double* colw;                              // [NCW][Tp + 4]
+  double* tile;                              // [NCW][TJ_DAYS][32] column-sum tiles of the warps
+  double (*red)[TJ_NACC];                    // [NCW]
+  double* sc;                                // [16]
+};
+
+static size_t tj_state_bytes(int nthr, int T, int P) {  // everything after the ring
+  const int Tp = (T + 3) / 4 * 4;
+  size_t b = sizeof(double) * (4 * (size_t)((P + 1) / 2 * 2));  // u p g im
+  b += sizeof(double) * (6 * (size_t)Tp);                       // pa gam yir rir col cs
+  b += sizeof(double) * (size_t)(nthr / 32) * (Tp + 4);         // colw
+  b += sizeof(double) * (size_t)(nthr / 32) * TJ_DAYS * 32;     // tile
+  b += sizeof(double) * (size_t)(nthr / 32) * TJ_NACC;          // red
+  b += sizeof(double) * 16;                                     // sc
+  return b + 128;
+}
+
+enum { TSC_PSI = 0, TSC_SIGMA, TSC_DPSI, TSC_DSIG, TSC_G0, TSC_G1, TSC_PRIOR, TSC_BETA, TSC_GAMMA0, TSC_GAMMA1, TSC_ALPHA0 };
+
+struct tj_cell_ctx {
+  int T, Mp;
+  double psi, epsdt;
+  unsigned long long magic;  // 0x4330000000000000 in a register pair (uint_to_double_wide)
+  const double2* tab;
+  const double* W;
+  const double* pa;        // shared: dt exp(alpha path) per day
+  unsigned char* scratch;  // this CTA's packed cells
+  int* ovf;                // shared flag: a cell does not fit the packed format
+  int src_stride;          // source stages: ints between the yse / S / I blocks (= days per source stage * Mp)
+};
+
+// Where a 4-day group lives inside a ring stage.  Packed stage: [days][Mp] x 16 B.  Source stage: four blocks
+// yse | S | I (int32) | Bc (f64), each [days per source stage][Mp].
+struct tj_gptr {
+  const unsigned char* pk;  // packed: first cell of the group's first day
+  const int* sy;            // source: yse of the group's first day (S, I at + src_stride, + 2 src_stride)
+  const double* sb;         // source: Bc of the group's first day
+};
+
+// One ring stage = TJ_DAYS days of the thread's metapopulations.  All loads first, then the cells' fast paths with no
+// branch in between (the compiler interleaves their dependent chains), one branch for the rare out-of-range cells, then the
+// accumulations in a fixed order.  PACKED: the stage holds 16-byte packed cells; otherwise the four cache arrays
+// (WRITE: evaluation 0 also re-packs every cell into the scratch).  FULL: all TJ_DAYS days exist and every metapopulation
+// slot of the thread is real (Mp == NTHR * MPT): no predicates.
+template <int NTHR, int MPT, bool PACKED, bool VAL, bool WRITE, bool FULL>
+__device__ __forceinline__ bool tj_group(const tj_cell_ctx& cx, const ll_coefs& K, const tj_gptr gp, int grp, int days,
+                                         const bool (&act)[MPT], const double (&pm_m)[MPT], double& val, double& psig,
+                                         double (&row)[MPT], double (&colv)[TJ_DAYS]) {
+  const int tid = threadIdx.x, Mp = cx.Mp;
+  double yd[TJ_DAYS][MPT], rd[TJ_DAYS][MPT], X[TJ_DAYS][MPT], bw[TJ_DAYS][MPT], ee[TJ_DAYS][MPT];
+  const int t0 = grp * TJ_DAYS;
+#pragma unroll
+  for (int j = 0; j < TJ_DAYS; ++j) {
+    const bool on = FULL || j < days;
+    const int t = t0 + (on ? j : 0);
+    const double pat = cx.pa[t];
+#pragma unroll
+    for (int q = 0; q < MPT; ++q) {
+      const int m = tid + q * NTHR;
+      const bool a = FULL || (on && act[q]);
+      double Id;
+      if (PACKED) {
+        uint4 w;
+        if (FULL) {
+          w = *reinterpret_cast<const uint4*>(gp.pk + ((size_t)j * Mp + m) * 16);
+        } else {
+          w = make_uint4(0u, 0u, 0u, 0u);
+          if (a) w = *reinterpret_cast<const uint4*>(gp.pk + ((size_t)j * Mp + m) * 16);
+        }
+        Id = uint_to_double_wide(w.x & 0x00ffffffu, cx.magic);
+        rd[j][q] = uint_to_double_wide(w.y & 0x00ffffffu, cx.magic);
+        yd[j][q] = uint_to_double_wide(__byte_perm(__byte_perm(w.x, 0u, 0x4443), w.y, 0x3270), cx.magic);
+        bw[j][q] = __hiloint2double((int)w.w, (int)w.z);
+      } else {
+        const int* sy = gp.sy + j * Mp;
+        int y = 0, S = 0, I = 0;
+        double bc = 0.0;
+        if (a) {
+          y = sy[m];
+          S = sy[cx.src_stride + m];
+          I = sy[2 * cx.src_stride + m];
+          bc = gp.sb[j * Mp + m];
+        }
+        const int r = S - y;
+        yd[j][q] = int_to_double_magic(y);
+        rd[j][q] = int_to_double_magic(r);
+        Id = int_to_double_magic(I);
+        bw[j][q] = cx.W[t] * bc;
+        if (WRITE && a) {  // re-pack the cell for evaluations 1..L
+          if (((unsigned)y > 0xffffu) | ((unsigned)I > 0x00ffffffu) | ((unsigned)r > 0x00ffffffu)) *cx.ovf = 1;
+          uint4 w;
+          w.x = ((unsigned)I & 0x00ffffffu) | ((unsigned)y << 24);
+          w.y = ((unsigned)r & 0x00ffffffu) | (((unsigned)y >> 8) << 24);
+          w.z = (unsigned)__double2loint(bw[j][q]);
+          w.w = (unsigned)__double2hiint(bw[j][q]);
+          *reinterpret_cast<uint4*>(cx.scratch + ((size_t)t * Mp + m) * 16) = w;
+        }
+      }
+      X[j][q] = fma(cx.psi, bw[j][q], Id);
+      ee[j][q] = a ? pat * pm_m[q] : 0.0;  // (inactive cells: x = eps dt, y = r = 0 => term 0, gradient 0)
+    }
+  }
+  double term[TJ_DAYS][MPT], gge[TJ_DAYS][MPT];
+  bool all_fast = true;
+#pragma unroll
+  for (int j = 0; j < TJ_DAYS; ++j)
+#pragma unroll
+    for (int q = 0; q < MPT; ++q) {
+      term[j][q] = 0.0;
+      gge[j][q] = 0.0;
+      all_fast &= cell_fast<true, VAL>(yd[j][q], rd[j][q], X[j][q], ee[j][q], cx.epsdt, cx.tab, K, term[j][q], gge[j][q]);
+    }
+  if (__builtin_expect(!all_fast, 0)) return false;  // (rare: the caller re-does the group on the generic path)
+#pragma unroll
+  for (int j = 0; j < TJ_DAYS; ++j) {
+    colv[j] = 0.0;
+#pragma unroll
+    for (int q = 0; q < MPT; ++q) {
+      if (VAL) val += term[j][q];
+      const double h = gge[j][q] * X[j][q];
+      row[q] += h;
+      psig = fma(gge[j][q], bw[j][q], psig);
+      colv[j] += h;
+    }
+  }
+  return true;
+}
+
+// Everything off the main path -- partial groups, padded metapopulation slots, chains that do not fit the packed format, groups
+// holding a cell outside the fast range -- goes through ONE out-of-line function built on cell_eval (branch per cell).  It
+// takes and returns plain values (a by-reference interface would force the hot loop's accumulators into local memory).
+template <int MPT>
+struct tj_out {
+  double val, psig, row[MPT], colv[TJ_DAYS];
+};
+template <int MPT>
+struct tj_pm {
+  double v[MPT];
+  int act;  // bit q: metapopulation slot q of the thread is real
+};
+
+template <int NTHR, int MPT>
+__device__ __noinline__ tj_out<MPT> tj_group_generic(const tj_cell_ctx cx, const ll_coefs K, const tj_gptr gp, int grp, int days,
+                                                     const tj_pm<MPT> pm, int packed, int want_val, int write) {
+  const int tid = threadIdx.x, Mp = cx.Mp;
+  tj_out<MPT> o;
+  o.val = 0.0;
+  o.psig = 0.0;
+  for (int q = 0; q < MPT; ++q) o.row[q] = 0.0;
+  for (int j = 0; j < TJ_DAYS; ++j) {
+    o.colv[j] = 0.0;
+    if (j >= days) continue;
+    const int t = grp * TJ_DAYS + j;
+    const double pat = cx.pa[t];
+    for (int q = 0; q < MPT; ++q) {
+      if (!((pm.act >> q) & 1)) continue;
+      const int m = tid + q * NTHR;
+      double yd, rd, Id, bw;
+      if (packed) {
+        const uint4 w = *reinterpret_cast<const uint4*>(gp.pk + ((size_t)j * Mp + m) * 16);
+        Id = uint_to_double_magic(w.x & 0x00ffffffu);
+        rd = uint_to_double_magic(w.y & 0x00ffffffu);
+        yd = uint_to_double_magic(__byte_perm(__byte_perm(w.x, 0u, 0x4443), w.y, 0x3270));
+        bw = __hiloint2double((int)w.w, (int)w.z);
+      } else {
+        const int* sy = gp.sy + j * Mp;
+        const int y = sy[m], S = sy[cx.src_stride + m], I = sy[2 * cx.src_stride + m];
+        const double bc = gp.sb[j * Mp + m];
+        const int r = S - y;
+        yd = int_to_double_magic(y);
+        rd = int_to_double_magic(r);
+        Id = int_to_double_magic(I);
+        bw = cx.W[t] * bc;
+        if (write) {
+          if (((unsigned)y > 0xffffu) | ((unsigned)I > 0x00ffffffu) | ((unsigned)r > 0x00ffffffu)) *cx.ovf = 1;
+          uint4 w;
+          w.x = ((unsigned)I & 0x00ffffffu) | ((unsigned)y << 24);
+          w.y = ((unsigned)r & 0x00ffffffu) | (((unsigned)y >> 8) << 24);
+          w.z = (unsigned)__double2loint(bw);
+          w.w = (unsigned)__double2hiint(bw);
+          *reinterpret_cast<uint4*>(cx.scratch + ((size_t)t * Mp + m) * 16) = w;
+        }
+      }
+      const double X = fma(cx.psi, bw, Id);
+      double gg_e = 0.0;
+      if (want_val) cell_eval<true, true>(yd, rd, X, pat * pm.v[q], cx.epsdt, cx.tab, K, o.val, gg_e);
+      else cell_eval<true, false>(yd, rd, X, pat * pm.v[q], cx.epsdt, cx.tab, K, o.val, gg_e);
+      const double h = gg_e * X;
+      o.row[q] += h;
+      o.psig = fma(gg_e, bw, o.psig);
+      o.colv[j] += h;
+    }
+  }
+  return o;
+}
+
+// Per-day column sums of a group over the 32 metapopulations of a warp, through a per-warp shared-memory tile instead of
+// shuffle butterflies (the kernel is instruction-issue bound): 4 conflict-free stores, each lane adds 4 values of one day
+// (two 16-byte loads), three shuffle steps over the 8 lanes of a day.  Fixed order.  The lane with (lane & 7) == 0 returns
+// the total of day lane >> 3.
+__device__ __forceinline__ double tj_col_reduce(const double (&colv)[TJ_DAYS], double* tile /* [TJ_DAYS][32] of this warp */) {
+  const int lane = threadIdx.x & 31;
+#pragma unroll
+  for (int j = 0; j < TJ_DAYS; ++j) tile[j * 32 + lane] = colv[j];
+  __syncwarp();
+  const double2 a = *reinterpret_cast<const double2*>(tile + lane * 4), b = *reinterpret_cast<const double2*>(tile + lane * 4 + 2);
+  double c = (a.x + a.y) + (b.x + b.y);
+  c += __shfl_xor_sync(0xffffffffu, c, 1);
+  c += __shfl_xor_sync(0xffffffffu, c, 2);
+  c += __shfl_xor_sync(0xffffffffu, c, 4);
+  return c;  // (the shuffles also order this group's tile reads before the next group's stores)
+}
+
+// The ring: TWO stages, each one large bulk copy (measured, tools/ubench/tma_feed.cu: a 1-D bulk copy costs ~700 cycles plus
+// its bytes whatever the ring depth -- 24 KB stages feed an SM at 32 B/clk, 72 KB stages at ~95 B/clk).  A packed stage holds
+// pd days (3 groups at the UK size: 73.7 KB), a source stage sd days in four blocks (yse | S | I | Bc, four copies).  There is
+// no producer warp (it would push the CTA to 416 threads and the register cap to 128): the warp that releases a stage LAST
+// issues the next copy into it.  s_seq orders everything: stage n of the CTA's life lives in buffer n & 1.
+struct tj_ring {
+  uint64_t full[2];
+  int cnt[2];        // warps that have released the stage in the buffer
+  int consumed;      // stages fully released
+  int next;          // next stage to load (global index over the CTA's life)
+  // the chain whose stages are being loaded, and where its stages start
+  int ld_k, ld_base, ld_packed, ld_eval0_done;
+};
+
+struct tj_sched {
+  int T, Mp, L, sd, pd, ns0, nsp;  // days per source / packed stage, stages per evaluation in each mode
+};
+
+// stage n (chain-local) -> evaluation, first day, days, mode
+__device__ __forceinline__ void tj_stage_of(const tj_sched& s, int n, int packed, int& eval, int& d0, int& nd, int& src) {
+  if (n < s.ns0 || !packed) {
+    eval = n / s.ns0;
+    const int k = n - eval * s.ns0;
+    d0 = k * s.sd;
+    nd = min(s.sd, s.T - d0);
+    src = 1;
+  } else {
+    const int r = n - s.ns0;
+    eval = 1 + r / s.nsp;
+    const int k = r - (eval - 1) * s.nsp;
+    d0 = k * s.pd;
+    nd = min(s.pd, s.T - d0);
+    src = 0;
+  }
+}
+
+template <int NTHR>
+__device__ __forceinline__ void tj_block_sum(double (&v)[TJ_NACC], double* tile, double (*red)[TJ_NACC]) {
+  const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+  static_assert(TJ_NACC == 2 * TJ_DAYS, "two rounds of the 4-wide tile reduce");
+  double* mytile = tile + warp * (TJ_DAYS * 32);
+#pragma unroll
+  for (int r = 0; r < 2; ++r) {
+    const double c4[TJ_DAYS] = {v[4 * r], v[4 * r + 1], v[4 * r + 2], v[4 * r + 3]};
+    const double tot = tj_col_reduce(c4, mytile);
+    if ((lane & 7) == 0) red[warp][4 * r + (lane >> 3)] = tot;
+  }
+  tj_bar(NTHR);
+#pragma unroll
+  for (int i = 0; i < TJ_NACC; ++i) {
+    double s = 0.0;
+#pragma unroll
+    for (int w = 0; w < NTHR / 32; ++w) s += red[w][i];
+    v[i] = s;
+  }
+  tj_bar(NTHR);  // (red[] may be rewritten)
+}
+
+template <int NTHR, int MPT>
+__global__ void __launch_bounds__(NTHR, 1) seir_hmc_traj_kernel(const traj_args A, const ll_coefs K) {
+  constexpr int NCW = NTHR / 32;
+  extern __shared__ __align__(128) unsigned char smraw[];
+  __shared__ tj_ring ring;
+  __shared__ double2 tab[128];
+  __shared__ int s_ovf;
+  const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
+  const int M = A.M, T = A.T, Mp = A.Mp, P = A.P, L = A.L;
+  const int Tp = (T + 3) / 4 * 4, P2 = (P + 1) / 2 * 2;
+  tj_sched sc;
+  sc.T = T; sc.Mp = Mp; sc.L = L; sc.sd = A.sd; sc.pd = A.pd;
+  sc.ns0 = (T + sc.sd - 1) / sc.sd;
+  sc.nsp = (T + sc.pd - 1) / sc.pd;
+  const size_t stage_bytes = A.stage_bytes;
+  tj_smem sm;
+  {
+    double* q = reinterpret_cast<double*>(smraw + 2 * stage_bytes);
+    sm.u = q; q += P2; sm.p = q; q += P2; sm.g = q; q += P2; sm.im = q; q += P2;
+    sm.pa = q; q += Tp; sm.gam = q; q += Tp; sm.yir = q; q += Tp; sm.rir = q; q += Tp; sm.col = q; q += Tp; sm.cs = q; q += Tp;
+    sm.colw = q; q += (size_t)NCW * (Tp + 4);
+    sm.tile = q; q += (size_t)NCW * TJ_DAYS * 32;
+    sm.red = reinterpret_cast<double (*)[TJ_NACC]>(q); q += (size_t)NCW * TJ_NACC;
+    sm.sc = q;
+  }
+  unsigned char* scratch = A.scratch + (size_t)blockIdx.x * T * Mp * 16;
+  const int nmine = (A.nb - (int)blockIdx.x + (int)gridDim.x - 1) / (int)gridDim.x;  // chains of this CTA: b0 + blockIdx.x + k gridDim.x
+
+  // Issue every load that may go now: its buffer is free (stage n - 2 released) and its data exists (the packed scratch of a
+  // chain is complete only after the chain's evaluation 0).  Called by ONE thread at a time: the lane that released a stage
+  // last, or thread 0 behind a CTA barrier.
+  auto pump = [&]() {
+    for (;;) {
+      const int n = ring.next;
+      if (n >= ring.consumed + 2 || ring.ld_k >= nmine) return;
+      const int nl = n - ring.ld_base;
+      const int nchain = ring.ld_packed ? sc.ns0 + L * sc.nsp : (L + 1) * sc.ns0;
+      if (nl >= sc.ns0 && !ring.ld_eval0_done) return;  // (evaluations >= 1 of this chain: wait for its scratch / its mode)
+      if (nl >= nchain) {  // on to the next chain of this CTA: its evaluation 0 reads the caches
+        ring.ld_k += 1;
+        ring.ld_base = n;
+        ring.ld_packed = 1;
+        ring.ld_eval0_done = 0;
+        continue;
+      }
+      int eval, d0, nd, src;
+      tj_stage_of(sc, nl, ring.ld_packed, eval, d0, nd, src);
+      unsigned char* dst = smraw + (size_t)(n & 1) * stage_bytes;
+      uint64_t* bar = &ring.full[n & 1];
+      if (!src) {
+        const unsigned bytes = (unsigned)(nd * Mp * 16);
+        mbar_expect_tx(bar, bytes);
+        bulk_load_1d(dst, scratch + (size_t)d0 * Mp * 16, bytes, bar);
+      } else {
+        const int bb = A.b0 + (int)blockIdx.x + ring.ld_k * (int)gridDim.x;
+        const size_t o = ((size_t)bb * T + d0) * Mp;
+        const unsigned n4 = (unsigned)(nd * Mp * 4);
+        mbar_expect_tx(bar, 5u * n4);
+        const size_t blk = (size_t)sc.sd * Mp * 4;  // (block stride of a FULL source stage, also for the short last one)
+        bulk_load_1d(dst, A.yse + o, n4, bar);
+        bulk_load_1d(dst + blk, A.S + o, n4, bar);
+        bulk_load_1d(dst + 2 * blk, A.I + o, n4, bar);
+        bulk_load_1d(dst + 3 * blk, A.Bc + o, 2u * n4, bar);
+      }
+      ring.next = n + 1;
+    }
+  };
+
+  if (tid == 0) {
+    mbar_init(&ring.full[0], 1);
+    mbar_init(&ring.full[1], 1);
+    asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+    ring.cnt[0] = ring.cnt[1] = 0;
+    ring.consumed = 0;
+    ring.next = 0;
+    ring.ld_k = 0;
+    ring.ld_base = 0;
+    ring.ld_packed = 1;
+    ring.ld_eval0_done = 0;
+    pump();  // the first two stages of the first chain
+  }
+  if (tid < 128) tab[tid] = A.logtab[tid];
+  __syncthreads();
+
+  // ------------------------------------------------------------------------------------------------------------------
+  // consumers: NTHR threads, thread <-> metapopulations m = tid + q NTHR
+  // ------------------------------------------------------------------------------------------------------------------
+  bool act[MPT];
+  double la_m[MPT], rN_m[MPT];
+#pragma unroll
+  for (int q = 0; q < MPT; ++q) {
+    const int m = tid + q * NTHR;
+    act[q] = m < Mp;
+    la_m[q] = act[q] ? A.la[m] : 0.0;
+    rN_m[q] = act[q] ? A.rN[m] : 0.0;  // (0 in the padding)
+  }
+  const double epsdt = A.eps * A.dt;
+  const bool full_m = Mp == NTHR * MPT;
+  const unsigned long long magic = (unsigned long long)__double_as_longlong(K.k[13]);  // 2^52: bit pattern 0x4330000000000000
+  unsigned nglob = 0;  // stages consumed over the CTA's life
+  for (int k = 0; k < nmine; ++k) {
+    const int kchain = k;
+    (void)kchain;
+    TJT(0);
+    const int b = A.b0 + (int)blockIdx.x + k * (int)gridDim.x;
+    double* ub = A.u + (size_t)b * P;
+    // ---- per chain: state of the transition into shared memory ----
+    for (int j = tid; j < P; j += NTHR) {
+      sm.u[j] = ub[j];
+      sm.p[j] = A.momentum[(size_t)b * P + j];
+      sm.im[j] = A.inv_mass ? A.inv_mass[(size_t)b * P + j] : 1.0;
+    }
+    for (int t = tid; t < T; t += NTHR) {
+      sm.yir[t] = (double)A.Yir[(size_t)b * T + t];
+      sm.rir[t] = (double)A.Rir[(size_t)b * T + t];
+    }
+    if (tid == 0) s_ovf = 0;
+    const double step = A.step[b];
+    double llc = A.llc_adj[b];
+    for (int q = 0; q < A.nllc; ++q) llc += A.llc_sum[(size_t)b * A.nllc + q];
+    double ei_term;
+    {
+      const double yei = (double)A.sumYei[b], eres = (double)A.sumEres[b];
+      ei_term = -eres * A.nu * A.dt;
+      if (yei > 0.0) ei_term += yei * A.log_p_nu;
+    }
+    const int flag = A.flags[b];
+    double val0 = 0.0, k0 = 0.0;
+    int packed = 0;
+    tj_bar(NTHR);
+    TJT(1);
+
+    for (int i = 0; i <= L + 1; ++i) {
+      // i <= L: evaluation i of the trajectory at the current sm.u.  i == L + 1: rate factors of the state the chain is
+      // LEFT in (accepted: the proposal; rejected: the start), exported for the discrete updates that follow.
+      const bool last = i == L + 1;
+      const bool want_val = i == 0 || i == L;
+      TJT(8 + i * 8 + 0);
+      // ---------------- A: parameter-derived factors ----------------
+      const double* alpha_t = sm.u + 6;
+      const double* sp = sm.u + 6 + (T - 1);
+      if (warp == 0) {  // inclusive scan of alpha_t: lanes own consecutive chunks, shuffle scan over the chunk totals
+        const int n = T - 1, chunk = (n + 31) / 32;
+        const int c0 = min(n, lane * chunk), c1 = min(n, c0 + chunk);
+        double tot = 0.0;
+        for (int j = c0; j < c1; ++j) tot += alpha_t[j];
+        double incl = tot;
+#pragma unroll
+        for (int o = 1; o < 32; o <<= 1) {
+          const double up = __shfl_up_sync(0xffffffffu, incl, o);
+          if (lane >= o) incl += up;
+        }
+        double run = incl - tot;
+        for (int j = c0; j < c1; ++j) {
+          run += alpha_t[j];
+          sm.cs[j] = run;
+        }
+      } else if (warp == 1) {  // scalars: bijector (inference.py:525-535), scalar priors (model_spec.py:140-198), ILDJ -- one per lane
+        const double eps_m = 2.220446049250313e-16;
+        const double u0 = sm.u[0], u1 = sm.u[1];
+        double r = 0.0;
+        if (lane == 0) r = tj_softplus(u0) + eps_m;                    // psi
+        else if (lane == 1) r = tj_softplus(u1) + eps_m;               // sigma_space
+        else if (lane == 2) r = tj_sigmoid(u0);                        // d psi / d u0
+        else if (lane == 3) r = tj_sigmoid(u1);
+        else if (want_val) {
+          if (lane == 4) r = -tj_softplus(-u0) - tj_softplus(-u1);     // ILDJ
+          else if (lane == 5) r = tj_normal_lp(sm.u[5], 10.0) + tj_normal_lp(sm.u[2], 1.0);
+          else if (lane == 6) r = tj_normal_lp(sm.u[3], 100.0) + tj_normal_lp(sm.u[4], 100.0);
+        }
+        const double psi = __shfl_sync(0xffffffffu, r, 0), sigma = __shfl_sync(0xffffffffu, r, 1);
+        if (want_val) {
+          if (lane == 7) r = 2.0 * log(psi) - 10.0 * psi - (0.6931471805599453 - 3.0 * 2.302585092994046);  // Gamma(3, 10)
+          else if (lane == 8)
+            r = (sigma < 0.0) ? -INFINITY : (0.5 * log(2.0 / 3.141592653589793) - log(0.1) - 0.5 * (sigma / 0.1) * (sigma / 0.1));
+        }
+        double prior = 0.0;  // same order of additions as tf_theta_prep: ILDJ, alpha_0, beta, psi, sigma, gamma0 + gamma1
+        if (want_val) {
+          const double a4 = __shfl_sync(0xffffffffu, r, 4), a5 = __shfl_sync(0xffffffffu, r, 5), a6 = __shfl_sync(0xffffffffu, r, 6);
+          const double a7 = __shfl_sync(0xffffffffu, r, 7), a8 = __shfl_sync(0xffffffffu, r, 8);
+          prior = (((a4 + a5) + a7) + a8) + a6;
+        }
+        const double dpsi = __shfl_sync(0xffffffffu, r, 2), dsig = __shfl_sync(0xffffffffu, r, 3);
+        if (lane == 0) {
+          sm.sc[TSC_PSI] = psi; sm.sc[TSC_SIGMA] = sigma; sm.sc[TSC_DPSI] = dpsi; sm.sc[TSC_DSIG] = dsig;
+          sm.sc[TSC_G0] = 1.0 - dpsi; sm.sc[TSC_G1] = 1.0 - dsig; sm.sc[TSC_PRIOR] = prior;
+          sm.sc[TSC_BETA] = sm.u[2]; sm.sc[TSC_GAMMA0] = sm.u[3]; sm.sc[TSC_GAMMA1] = sm.u[4]; sm.sc[TSC_ALPHA0] = sm.u[5];
+        }
+      }
+      // CAR prior: (Q sp)_m and the quadratic form (model_spec.py:171-181); parameter-only, independent of the scalars
+      double carq[MPT];
+      double acc[TJ_NACC];
+#pragma unroll
+      for (int a = 0; a < TJ_NACC; ++a) acc[a] = 0.0;
+#pragma unroll
+      for (int q = 0; q < MPT; ++q) {
+        const int m = tid + q * NTHR;
+        carq[q] = 0.0;
+        if (m < M) {
+          double r = 0.0;
+          for (int e = A.car_indptr[m]; e < A.car_indptr[m + 1]; ++e) r += A.car_values[e] * sp[A.car_indices[e]];
+          carq[q] = r;
+          acc[7] -= 0.5 * sp[m] * r;
+        }
+      }
+      if (want_val)
+        for (int j = tid; j < T - 1; j += NTHR) acc[7] += tj_normal_lp(alpha_t[j], 0.005);
+      tj_bar(NTHR);  // cs[], sc[] published
+      TJT(8 + i * 8 + 1);
+      const double psi = sm.sc[TSC_PSI], sigma = sm.sc[TSC_SIGMA], beta = sm.sc[TSC_BETA];
+      double pm_m[MPT];
+#pragma unroll
+      for (int q = 0; q < MPT; ++q) {
+        const int m = tid + q * NTHR;
+        pm_m[q] = (m < M) ? exp(beta * la_m[q] + sigma * sp[m]) * rN_m[q] : 0.0;
+      }
+      // per day, two tasks on separate threads (tail warps first: every thread also has its pm factors to do):
+      //   task 0  exp(alpha path) dt
+      //   task 1  the I->R rate and the I->R sufficient-statistic terms (value: acc[4]; gradient: acc[5], acc[6])
+      for (int tt = NTHR - 1 - tid; tt < 2 * T; tt += NTHR) {
+        const int task = tt >= T, t = task ? tt - T : tt;
+        if (task == 0) {
+          const int kk = A.aidx[t];
+          const double a = (kk < 0) ? sm.sc[TSC_ALPHA0] : sm.sc[TSC_ALPHA0] + sm.cs[kk];
+          const double ea = exp(a);
+          sm.pa[t] = ea * A.dt;
+          if (last) {
+            A.pa[(size_t)b * T + t] = ea;
+            A.psiW[(size_t)b * T + t] = psi * A.W[t];
+          }
+        } else {
+          const double gt = exp(sm.sc[TSC_GAMMA0] + sm.sc[TSC_GAMMA1] * A.wk[t]);
+          sm.gam[t] = gt;
+          if (last) {
+            A.gam[(size_t)b * T + t] = gt;
+            A.logpir[(size_t)b * T + t] = log(-expm1(-gt * A.dt));
+          } else {
+            const double yv = sm.yir[t], rv = sm.rir[t];
+            if (want_val) {
+              double term = -rv * gt * A.dt;
+              if (yv > 0.0) term += yv * log(-expm1(-gt * A.dt));
+              acc[4] += term;
+            }
+            double d = -rv;
+            if (yv > 0.0) d += yv / expm1(gt * A.dt);
+            d *= A.dt * gt;
+            acc[5] += d;
+            acc[6] += d * A.wk[t];
+          }
+        }
+      }
+      if (last) {
+#pragma unroll
+        for (int q = 0; q < MPT; ++q)
+          if (act[q]) A.pm[(size_t)b * Mp + tid + q * NTHR] = pm_m[q];
+        if (tid < SEIR_NSCAL) {
+          double v = 0.0;
+          if (tid == SC_PSI) v = psi;
+          if (tid == SC_SIGMA) v = sigma;
+          if (tid == SC_BETA) v = beta;
+          if (tid == SC_GAMMA0) v = sm.sc[TSC_GAMMA0];
+          if (tid == SC_GAMMA1) v = sm.sc[TSC_GAMMA1];
+          if (tid == SC_ALPHA0) v = sm.sc[TSC_ALPHA0];
+          if (tid == SC_DPSI_DU) v = sm.sc[TSC_DPSI];
+          if (tid == SC_DSIGMA_DU) v = sm.sc[TSC_DSIG];
+          A.scal[(size_t)b * SEIR_NSCAL + tid] = v;
+        }
+        tj_bar(NTHR);
+        break;
+      }
+      tj_bar(NTHR);  // pa[] published
+      TJT(8 + i * 8 + 2);
+
+      // ---------------- B: the cells ----------------
+      double val = 0.0, psig = 0.0, row[MPT];
+#pragma unroll
+      for (int q = 0; q < MPT; ++q) row[q] = 0.0;
+      const int cstride = Tp + 4;
+      tj_cell_ctx cx;
+      tj_pm<MPT> pmv;
+      pmv.act = 0;
+#pragma unroll
+      for (int q = 0; q < MPT; ++q) {
+        pmv.v[q] = pm_m[q];
+        pmv.act |= act[q] ? (1 << q) : 0;
+      }
+      cx.T = T; cx.Mp = Mp; cx.psi = psi; cx.epsdt = epsdt; cx.tab = tab; cx.W = A.W; cx.pa = sm.pa; cx.scratch = scratch;
+      cx.ovf = &s_ovf;
+      cx.magic = magic;
+      cx.src_stride = sc.sd * Mp;
+      const bool src_eval = i == 0 || !packed;
+      const int nstages = src_eval ? sc.ns0 : sc.nsp, sdays = src_eval ? sc.sd : sc.pd;
+      for (int s = 0; s < nstages; ++s, ++nglob) {
+        const int buf = (int)(nglob & 1u);
+        mbar_wait(&ring.full[buf], (nglob >> 1) & 1u);
+        const unsigned char* stage = smraw + (size_t)buf * stage_bytes;
+        const int d0 = s * sdays, nd = min(sdays, T - d0);
+        for (int gd = 0; gd < nd; gd += TJ_DAYS) {  // the 4-day groups of the stage
+          const int grp = (d0 + gd) / TJ_DAYS;  // (stage days are multiples of TJ_DAYS: groups never straddle stages)
+          tj_gptr gp;
+          gp.pk = stage + (size_t)gd * Mp * 16;
+          gp.sy = reinterpret_cast<const int*>(stage) + (size_t)gd * Mp;
+          gp.sb = reinterpret_cast<const double*>(stage + (size_t)3 * sc.sd * Mp * 4) + (size_t)gd * Mp;
+          double colv[TJ_DAYS];
+          const int days = min(TJ_DAYS, nd - gd);
+          const bool full = full_m && days == TJ_DAYS;
+          bool done = false;
+          double v1 = val, p1 = psig, r1[MPT];
+#pragma unroll
+          for (int q = 0; q < MPT; ++q) r1[q] = row[q];
+          if (full) {  // the main path: whole groups, every slot real
+            if (!src_eval) {
+              if (want_val) done = tj_group<NTHR, MPT, true, true, false, true>(cx, K, gp, grp, days, act, pm_m, v1, p1, r1, colv);
+              else done = tj_group<NTHR, MPT, true, false, false, true>(cx, K, gp, grp, days, act, pm_m, v1, p1, r1, colv);
+            } else if (i == 0) {
+              done = tj_group<NTHR, MPT, false, true, true, true>(cx, K, gp, grp, days, act, pm_m, v1, p1, r1, colv);
+            }
+          }
+          if (done) {
+            val = v1;
+            psig = p1;
+#pragma unroll
+            for (int q = 0; q < MPT; ++q) row[q] = r1[q];
+          } else {  // (accumulators untouched by a group that bailed out: the generic function adds its own sums, same order)
+            const tj_out<MPT> o = tj_group_generic<NTHR, MPT>(cx, K, gp, grp, days, pmv, src_eval ? 0 : 1, want_val ? 1 : 0, i == 0 ? 1 : 0);
+            val += o.val;
+            psig += o.psig;
+#pragma unroll
+            for (int q = 0; q < MPT; ++q) row[q] += o.row[q];
+#pragma unroll
+            for (int j = 0; j < TJ_DAYS; ++j) colv[j] = o.colv[j];
+          }
+          const double tot = tj_col_reduce(colv, sm.tile + warp * (TJ_DAYS * 32));
+          if ((lane & 7) == 0 && (lane >> 3) < days) sm.colw[warp * cstride + grp * TJ_DAYS + (lane >> 3)] = tot;
+        }
+        // release the stage; the warp that does so last refills the ring
+        if (i == 0) {  // (this warp's scratch writes: visible to the async proxy before any later bulk copy can be issued)
+          __threadfence();
+          asm volatile("fence.proxy.async;" ::: "memory");
+        }
+        __syncwarp();
+        if (lane == 0) {
+          __threadfence_block();
+          if (atomicAdd(&ring.cnt[buf], 1) == NCW - 1) {
+            ring.cnt[buf] = 0;
+            __threadfence_block();
+            *reinterpret_cast<volatile int*>(&ring.consumed) = ring.consumed + 1;
+            pump();
+            __threadfence_block();
+          }
+        }
+      }
+
+      TJT(8 + i * 8 + 3);
+      // ---------------- C: reductions, gradient ----------------
+      acc[0] = val;
+      acc[1] = psig;
+#pragma unroll
+      for (int q = 0; q < MPT; ++q) {
+        const int m = tid + q * NTHR;
+        if (m < M) {
+          acc[2] += row[q] * la_m[q];
+          acc[3] += row[q] * sp[m];
+          sm.g[6 + (T - 1) + m] = sigma * row[q] - carq[q];
+        }
+      }
+      tj_block_sum<NTHR>(acc, sm.tile, sm.red);  // (its barriers also publish colw[]; s_ovf is settled)
+      TJT(8 + i * 8 + 4);
+      if (i == 0) {
+        packed = !s_ovf;
+        if (tid == 0) {  // every warp has released evaluation 0's stages (and fenced its scratch writes): the chain's later loads may go
+          ring.ld_packed = packed;
+          ring.ld_eval0_done = 1;
+          pump();
+        }
+      }
+      for (int tt = tid; tt < ((Tp * 4 + 31) & ~31); tt += NTHR) {  // 4 threads per day (whole warps): a quarter of the warp partials each
+        const int t = tt >> 2, part = tt & 3;
+        double s = 0.0;
+        if (t < T)
+          for (int w = part; w < NCW; w += 4) s += sm.colw[w * cstride + t];
+        s += __shfl_xor_sync(0xffffffffu, s, 1);
+        s += __shfl_xor_sync(0xffffffffu, s, 2);
+        if (part == 0 && t < Tp) sm.col[t] = s;
+      }
+      tj_bar(NTHR);
+      if (warp == 0) {  // suffix sums of the per-day column sums (lanes own consecutive chunks of days; lane 31 first)
+        const int chunk = (T + 31) / 32;
+        const int c0 = min(T, lane * chunk), c1 = min(T, c0 + chunk);
+        double cs = 0.0;
+        for (int t = c1 - 1; t >= c0; --t) cs += sm.col[t];
+        double incl = cs;
+#pragma unroll
+        for (int o = 1; o < 32; o <<= 1) {
+          const double up = __shfl_down_sync(0xffffffffu, incl, o);
+          if (lane + o < 32) incl += up;
+        }
+        double tail = incl - cs;
+        for (int t = c1 - 1; t >= c0; --t) {
+          tail += sm.col[t];
+          sm.col[t] = tail;
+        }
+        __syncwarp();
+        for (int j = lane; j < T - 1; j += 32) {
+          const int tf = A.tfirst[j];
+          sm.g[6 + j] = (tf < T ? sm.col[tf] : 0.0) - alpha_t[j] * 40000.0;  // d/dx of Normal(0, 0.005)
+        }
+        if (lane == 0) {
+          const double u2 = sm.u[2], u3 = sm.u[3], u4 = sm.u[4], u5 = sm.u[5];
+          const double gpsi = acc[1] + 2.0 / psi - 10.0;
+          const double gsg = acc[3] - sigma * 100.0;
+          sm.g[0] = gpsi * sm.sc[TSC_DPSI] + sm.sc[TSC_G0];
+          sm.g[1] = gsg * sm.sc[TSC_DSIG] + sm.sc[TSC_G1];
+          sm.g[2] = acc[2] - u2;
+          sm.g[3] = acc[5] - u3 * 1.0e-4;
+          sm.g[4] = acc[6] - u4 * 1.0e-4;
+          sm.g[5] = sm.col[0] - u5 * 0.01;
+        }
+      }
+      double v = 0.0;
+      if (want_val) {
+        v = sm.sc[TSC_PRIOR] + acc[7] - (double)M * HALF_LOG_2PI - A.car_log_det_scale;
+        v += acc[0] + llc + ei_term + acc[4];
+        if (flag != 0) v = -INFINITY;
+      }
+      tj_bar(NTHR);  // g[] complete
+      TJT(8 + i * 8 + 5);
+
+      // ---------------- D: leapfrog ----------------
+      // i == 0: K0, half kick, drift.  0 < i < L: kick, drift.  i == L: half kick, K1, Metropolis decision.
+      const double kick = (i == 0 || i == L) ? 0.5 * step : step;
+      double ke = 0.0;
+      for (int j = tid; j < P; j += NTHR) {
+        const double im = sm.im[j];
+        double pj = sm.p[j];
+        if (i == 0) ke += im * pj * pj;
+        pj = fma(kick, sm.g[j], pj);
+        if (i == L) ke += im * pj * pj;
+        sm.p[j] = pj;
+        if (i < L) sm.u[j] = fma(step, im * pj, sm.u[j]);
+      }
+      if (i == 0 || i == L) {
+        double e8[TJ_NACC];
+#pragma unroll
+        for (int a = 0; a < TJ_NACC; ++a) e8[a] = 0.0;
+        e8[0] = ke;
+        tj_block_sum<NTHR>(e8, sm.tile, sm.red);
+        if (i == 0) {
+          k0 = 0.5 * e8[0];
+          val0 = v;
+        } else {
+          const double k1 = 0.5 * e8[0];
+          const double ratio = (v - k1) - (val0 - k0);
+          const bool fin = isfinite(v) && isfinite(k1);
+          const int accd = (fin && A.log_u[b] < ratio) ? 1 : 0;  // non-finite proposed energy rejects; NaN compares false
+          if (tid == 0) {
+            A.accept[b] = accd;
+            A.tlp[b] = accd ? v : val0;
+            if (A.tlp_trace) A.tlp_trace[b] = accd ? v : val0;
+            if (A.dbg) {
+              A.dbg[(size_t)b * 4 + 0] = ratio;
+              A.dbg[(size_t)b * 4 + 1] = v;
+              A.dbg[(size_t)b * 4 + 2] = k0;
+              A.dbg[(size_t)b * 4 + 3] = k1;
+            }
+          }
+          // the state the chain is left in: the proposal (already in sm.u) or the start (still in global memory)
+          if (accd) {
+            for (int j = tid; j < P; j += NTHR) ub[j] = sm.u[j];
+          } else {
+            for (int j = tid; j < P; j += NTHR) sm.u[j] = ub[j];
+          }
+        }
+      }
+      tj_bar(NTHR);  // u[] / p[] settled for the next evaluation
+      TJT(8 + i * 8 + 6);
+    }
+  }
+}
+
+// ---- host side ---------------------------------------------------------------------------------------------------------
+typedef void (*traj_fn)(const traj_args, const ll_coefs);
+
+struct traj_cfg {
+  traj_fn fn;
+  int nthr, mpt;
+};
+
+static bool traj_pick(int Mp, traj_cfg* k) {
+  if (Mp <= 128) *k = traj_cfg{seir_hmc_traj_kernel<128, 1>, 128, 1};
+  else if (Mp <= 256) *k = traj_cfg{seir_hmc_traj_kernel<256, 1>, 256, 1};
+  else if (Mp <= 384) *k = traj_cfg{seir_hmc_traj_kernel<384, 1>, 384, 1};
+  else if (Mp <= 512) *k = traj_cfg{seir_hmc_traj_kernel<512, 1>, 512, 1};
+  else if (Mp <= 1024) *k = traj_cfg{seir_hmc_traj_kernel<512, 2>, 512, 2};
+  else return false;
+  return true;
+}
+
+// Whether the persistent trajectory kernel applies to this chain set (shared memory for two ring stages of at least one
+// 4-day group + the O(P) state); if so, the launch shape.  SEIR_HMC_TRAJ=0 forces the round-1 launch sequence (hmc.cu).
+struct traj_shape {
+  int sd, pd;
+  unsigned stage_bytes;
+  size_t smem;
+};
+
+static bool traj_plan(const seir_chains* c, traj_cfg* k, traj_shape* sh) {
+  static int enabled = -1;
+  if (enabled < 0) {
+    const char* e = getenv("SEIR_HMC_TRAJ");
+    enabled = e ? atoi(e) : 1;
+  }
+  if (!enabled) return false;
+  const seir_model* m = c->model;
+  if (!traj_pick(m->Mp, k)) return false;
+  int dev_smem = 0;
+  if (cudaDeviceGetAttribute(&dev_smem, cudaDevAttrMaxSharedMemoryPerBlockOptin, m->device) != cudaSuccess) return false;
+  const size_t state = tj_state_bytes(k->nthr, m->T, m->P);
+  const size_t budget = (size_t)dev_smem - 4096;  // (static shared memory of the kernel: ring bookkeeping, log table)
+  if (state + 2 * (size_t)TJ_DAYS * m->Mp * 20 > budget) return false;
+  const size_t per_stage = (budget - state) / 2;
+  const int Tp = (m->T + TJ_DAYS - 1) / TJ_DAYS * TJ_DAYS;
+  int pd = (int)(per_stage / ((size_t)m->Mp * 16)) / TJ_DAYS * TJ_DAYS, sd = (int)(per_stage / ((size_t)m->Mp * 20)) / TJ_DAYS * TJ_DAYS;
+  if (pd > Tp) pd = Tp;
+  if (sd > Tp) sd = Tp;
+  static int cap = -1;
+  if (cap < 0) {
+    const char* e = getenv("SEIR_TRAJ_STAGE_DAYS");  // experiments: cap the days per stage
+    cap = e ? atoi(e) : 0;
+  }
+  if (cap >= TJ_DAYS) {
+    if (pd > cap) pd = cap / TJ_DAYS * TJ_DAYS;
+    if (sd > cap) sd = cap / TJ_DAYS * TJ_DAYS;
+  }
+  if (pd < TJ_DAYS || sd < TJ_DAYS) return false;
+  const size_t pb = (size_t)pd * m->Mp * 16, sb = (size_t)sd * m->Mp * 20;
+  sh->sd = sd;
+  sh->pd = pd;
+  sh->stage_bytes = (unsigned)(((pb > sb ? pb : sb) + 127) / 128 * 128);
+  sh->smem = 2 * (size_t)sh->stage_bytes + state;
+  return sh->smem <= budget;
+}
+
+bool seir_hmc_traj_applies(const seir_chains* c) {
+  traj_cfg k;
+  traj_shape sh;
+  return traj_plan(c, &k, &sh);
+}
+
+// One HMC transition of chains [r.b0, r.b0 + r.nb) with the momentum in c->d_hmc_p.  Leaves the rate factors of the
+// resulting state in the chain set (what seir_hmc_step_leap's END step does in the round-1 sequence).
+int seir_launch_hmc_traj(seir_chains* c, double* d_u, const double* d_log_u, const double* d_step, const double* d_inv_mass,
+                         int num_leapfrog, double* d_tlp, double* d_tlp_trace, int* d_accept, double* d_dbg, cudaStream_t s,
+                         seir_range r, int slot) {
+  const seir_model* m = c->model;
+  traj_cfg k;
+  traj_shape sh;
+  if (!traj_plan(c, &k, &sh)) return seir_set_error(SEIR_ERR_UNSUPPORTED, "seir_launch_hmc_traj: shape not supported");
+  const int grid = r.nb < m->sms ? r.nb : m->sms;
+  const size_t per_cta = (size_t)m->T * m->Mp * 16;
+  if (slot < 0 || slot >= SEIR_MAX_GROUPS) return seir_set_error(SEIR_ERR_BAD_ARG, "seir_launch_hmc_traj: bad scratch slot %d", slot);
+  if (!c->d_traj_scratch[slot]) {  // (chain groups run concurrently on separate streams: one scratch per group)
+    SEIR_CUDA(cudaMalloc(reinterpret_cast<void**>(&c->d_traj_scratch[slot]), per_cta * (size_t)m->sms));
+    c->bytes += (int64_t)(per_cta * (size_t)m->sms);
+  }
+  static size_t attr_dev[SEIR_MAX_DEVICES][8] = {{0}};
+  size_t& attr = attr_dev[m->device % SEIR_MAX_DEVICES][(k.nthr / 128 - 1) * 2 + (k.mpt - 1)];
+  const size_t smem = sh.smem;
+  if (attr != smem) {
+    SEIR_CUDA(cudaFuncSetAttribute(k.fn, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+    attr = smem;
+  }
+  traj_args A;
+  A.M = m->M; A.T = m->T; A.Mp = m->Mp; A.P = m->P; A.car_prior = 1;
+  A.dt = m->dt; A.eps = m->rate_eps; A.nu = m->nu; A.log_p_nu = m->log_p_nu; A.car_log_det_scale = m->car_log_det_scale;
+  A.W = m->d_W; A.wk = m->d_wk; A.la = m->d_la; A.rN = m->d_rN; A.car_values = m->d_car_values;
+  A.aidx = m->d_aidx; A.tfirst = m->d_tfirst; A.car_indptr = m->d_car_indptr; A.car_indices = m->d_car_indices;
+  A.logtab = m->d_logtab;
+  A.yse = c->d_yse; A.S = c->d_S; A.I = c->d_I; A.Bc = c->d_Bc;
+  A.Yir = c->d_Yir; A.Rir = c->d_Rir; A.sumYei = c->d_sumYei; A.sumEres = c->d_sumEres; A.flags = c->d_flags;
+  A.llc_sum = c->d_llc_sum; A.llc_adj = c->d_llc_adj; A.nllc = c->nllc;
+  A.pa = c->d_pa; A.psiW = c->d_psiW; A.gam = c->d_gam; A.logpir = c->d_logpir; A.pm = c->d_pm; A.scal = c->d_scal;
+  A.u = d_u; A.momentum = c->d_hmc_p; A.log_u = d_log_u; A.step = d_step; A.inv_mass = d_inv_mass;
+  A.tlp = d_tlp; A.tlp_trace = d_tlp_trace; A.accept = d_accept; A.dbg = d_dbg;
+  A.scratch = c->d_traj_scratch[slot];
+  A.b0 = r.b0; A.nb = r.nb; A.L = num_leapfrog;
+  A.sd = sh.sd; A.pd = sh.pd; A.stage_bytes = sh.stage_bytes;
+  k.fn<<<grid, k.nthr, smem, s>>>(A, LL_COEFS);
+  seir_count_launch(1);
+  return seir_cuda_check(cudaGetLastError(), "seir_hmc_traj_kernel");
+}

@@ -11,6 +11,7 @@
 #include <stdlib.h>
 
 #include "seir_internal.cuh"
+#include "cell.cuh"
 #include "theta_fin.cuh"
 #include "tma.cuh"
 
@@ -74,86 +75,22 @@ int seir_launch_theta_prep(seir_chains* c, const double* d_theta, int kind, int 
 //   * the per-day column sums of 4 consecutive days are reduced across the warp together by a transposing
 //     butterfly (6 shuffles for 4 days instead of 20).
 // ------------------------------------------------------------------------------------------------
-#define LL_SMALL_X 0.05
 #define LL_UNROLL 4
 
-__device__ __forceinline__ double int_to_double_magic(int k) {  // exact int32 -> double with one FP64 add
-  return __hiloint2double(0x43300000, k ^ 0x80000000) - 4503601774854144.0;  // 2^52 + 2^31
-}
-
-// Polynomial / series coefficients travel as a by-value kernel parameter: they sit in constant bank 0 and FP64
-// instructions take them directly as c[0x0][offset] operands.  (As literals the compiler rebuilt each 64-bit immediate
-// with two UMOVs per use -- 14 % of the instructions of the v5 kernel, profiles/r01_v5_ncu_full_summary.md; a
-// __constant__ array costs an LDC per use.)
-struct ll_coefs {
-  double k[13];
-};
-static const ll_coefs LL_COEFS = {{
-    0.14285714285714285, -0.16666666666666666, 0.2, -0.25, 0.3333333333333333, -0.5,  // log1p(r) = r + r^2 (c5 + r (c4 + ...))
-    0.6931471805599453,                                                                // ln 2
-    5.511463844797178e-06, -3.472222222222222e-04, 0.041666666666666664,             // log(1-e^-x) - log x + x/2, even powers
-    3.306878306878307e-05, -1.388888888888889e-03, 0.08333333333333333}};            // 1/expm1(x) - 1/x + 1/2, odd powers
-
-// One (day, metapopulation) cell of the S->E term.  Fast path for a positive normal x = lam*dt < 0.05 (always, for
-// realistic infection hazards), evaluated branch-free:
-//   log x   table-driven range reduction: x = 2^e m, c_i = centre of the mantissa bucket (128 buckets in shared memory),
-//           r = m/c_i - 1 (|r| <= 2^-8, exact through an FMA with the rounded 1/c_i whose own log is tabulated),
-//           log x = e ln2 - log(1/c_i) + log1p(r) [degree 7]
-//   1/x     (gradient only; tolerance 1e-8) FP32 reciprocal + one FP64 Newton step: relative error 2^-46
-//   log(1-e^-x) = log x - x/2 + x^2/24 - x^4/2880 + x^6/181440        (truncation < 1e-17)
-//   1/expm1(x)  = 1/x - 1/2 + x/12 - x^3/720 + x^5/30240
-// Anything else (x >= 0.05, x <= 0, subnormal, NaN) takes the library path: NaN log for x < 0 like the reference.
-// Outputs: val += term;  GRAD: ge = d term / d lam * e  (so that h = ge * X is the cell's d/d log-rate).
-// want_val = false (gradient kernels only; CTA-uniform): the term itself is not needed -- the interior steps of a leapfrog
-// trajectory use the gradient alone (energies are evaluated at its two ends) -- and the logarithm (table lookup,
-// degree-7 polynomial, exponent conversion: ~15 % of the instructions of a cell) is skipped.
+// One cell: cell.cuh (integer -> double by the 2^52 trick, reciprocal seeded through integer operations: nothing on the
+// conversion unit).  want_val = false (gradient kernels only; CTA-uniform): the term itself is not needed -- the interior
+// steps of a leapfrog trajectory use the gradient alone (energies are evaluated at its two ends) -- and the logarithm is skipped.
 template <bool GRAD>
-__device__ __forceinline__ void ll_cell(int y, int S, int I, double bc, double e, double pwt, double dt, double eps,
-                                        const double2* __restrict__ tab, const ll_coefs& LLK_, bool want_val, double& val, double& h,
-                                        double& gebc) {
-  const double* LLK = LLK_.k;
-  const double X = (double)I + pwt * bc;
-  const double eX = e * X;
-  const double x = (eX + eps) * dt;
-  const double yd = (double)y, rd = (double)(S - y);
-  const int hi = __double2hiint(x), lo = __double2loint(x);
-  const double x2 = x * x;
-  double term = 0.0;
-  if (!GRAD || want_val) {
-    const int ex = (hi >> 20) - 1023;
-    const double m = __hiloint2double((hi & 0x000fffff) | 0x3ff00000, lo);
-    const double2 tc = tab[(hi >> 13) & 127];  // {1/c rounded, -log(1/c rounded)}
-    const double r = fma(m, tc.x, -1.0);
-    const double r2 = r * r;
-    double p = fma(r, LLK[0], LLK[1]);
-    p = fma(r, p, LLK[2]);
-    p = fma(r, p, LLK[3]);
-    p = fma(r, p, LLK[4]);
-    p = fma(r, p, LLK[5]);
-    const double lg = fma(int_to_double_magic(ex), LLK[6], tc.y) + fma(r2, p, r);
-    term = fma(yd, lg + fma(x2, fma(x2, fma(x2, LLK[7], LLK[8]), LLK[9]), -0.5 * x), -rd * x);
-  }
-  double gg = 0.0;
+__device__ __forceinline__ void ll_cell(int y, int S, int I, double bc, double e, double pwt, double epsdt, const double2* __restrict__ tab,
+                                        const ll_coefs& K, bool want_val, double& val, double& h, double& gebc) {
+  const double yd = int_to_double_magic(y), rd = int_to_double_magic(S - y);
+  const double X = fma(pwt, bc, int_to_double_magic(I));
+  double gg_e = 0.0;
+  if (!GRAD || want_val) cell_eval<GRAD, true>(yd, rd, X, e, epsdt, tab, K, val, gg_e);
+  else cell_eval<GRAD, false>(yd, rd, X, e, epsdt, tab, K, val, gg_e);
   if (GRAD) {
-    double rc = (double)__frcp_rn((float)x);
-    rc = fma(rc, fma(-x, rc, 1.0), rc);
-    gg = fma(yd, (rc - 0.5) + x * fma(x2, fma(x2, LLK[10], LLK[11]), LLK[12]), -rd);
-  }
-  const bool fast = (hi >= 0x00100000) & (x < LL_SMALL_X);
-  if (__builtin_expect(!fast, 0)) {
-    const double em = expm1(-x);  // -(1-exp(-x)) = -p
-    term = -rd * x;
-    gg = -rd;
-    if (y > 0) {
-      if (!GRAD || want_val) term += yd * log(-em);
-      if (GRAD) gg += yd * (1.0 + em) / (-em);
-    }
-  }
-  val += term;
-  if (GRAD) {
-    const double ge = (gg * dt) * e;
-    h = ge * X;
-    gebc = ge * bc;
+    h = gg_e * X;
+    gebc = gg_e * bc;
   }
 }
 
@@ -190,9 +127,10 @@ __global__ void __launch_bounds__(SEIR_LL_THREADS, GRAD ? 6 : 10) seir_loglik_ke
   const int m0 = blockIdx.x * (SEIR_LL_THREADS * MPT) + tid;
   const int tb = blockIdx.z * dps, nt = min(dps, T - tb);
   const int cstride = dps + LL_UNROLL;
+  const double epsdt = eps * dt;
   tab[tid] = logtab[tid];  // SEIR_LL_THREADS == 128 entries
   for (int t = tid; t < nt; t += SEIR_LL_THREADS) {
-    pa_s[t] = pa[(size_t)b * T + tb + t];
+    pa_s[t] = pa[(size_t)b * T + tb + t] * dt;  // (dt folded into the day factor: x = e X + eps dt)
     pw_s[t] = psiW[(size_t)b * T + tb + t];
     if (GRAD) w_s[t] = W[tb + t];
   }
@@ -228,7 +166,7 @@ __global__ void __launch_bounds__(SEIR_LL_THREADS, GRAD ? 6 : 10) seir_loglik_ke
             bc = __ldg(Bc + o);
           }
           double h = 0.0, gebc = 0.0;
-          ll_cell<GRAD>(y, S, I, bc, pat * pm_m[q], pwt, dt, eps, tab, K, want_val != 0, val, h, gebc);
+          ll_cell<GRAD>(y, S, I, bc, pat * pm_m[q], pwt, epsdt, tab, K, want_val != 0, val, h, gebc);
           if (GRAD) {
             row[q] += h;
             psig = fma(w_s[t], gebc, psig);
@@ -301,6 +239,7 @@ __global__ void __launch_bounds__(NTHR + 32, NTHR >= 384 ? (GRAD ? 2 : 3) : 1) s
   const int tb = blockIdx.z * dps, nt = min(dps, T - tb);
   const int ngroups = (nt + LL_STAGE_DAYS - 1) / LL_STAGE_DAYS;
   const int cstride = dps + LL_UNROLL;
+  const double epsdt = eps * dt;
   const bool producer = warp == NCW;
 
   if (tid == 0) {
@@ -313,7 +252,7 @@ __global__ void __launch_bounds__(NTHR + 32, NTHR >= 384 ? (GRAD ? 2 : 3) : 1) s
   if (tid < 128) tab[tid] = logtab[tid];
   pdl_wait();  // (PDL launches: everything below reads what the previous kernel on the stream wrote)
   for (int t = tid; t < nt; t += NTHR + 32) {
-    pa_s[t] = pa[(size_t)b * T + tb + t];
+    pa_s[t] = pa[(size_t)b * T + tb + t] * dt;  // (dt folded into the day factor: x = e X + eps dt)
     pw_s[t] = psiW[(size_t)b * T + tb + t];
     if (GRAD) w_s[t] = W[tb + t];
   }
@@ -363,7 +302,7 @@ __global__ void __launch_bounds__(NTHR + 32, NTHR >= 384 ? (GRAD ? 2 : 3) : 1) s
           for (int q = 0; q < MPT; ++q) {
             const int k = tid + q * NTHR;
             double h = 0.0, gebc = 0.0;
-            ll_cell<GRAD>(sy[k], sS[k], sI[k], sB[k], pat * pm_m[q], pwt, dt, eps, tab, K, want_val != 0, val, h, gebc);
+            ll_cell<GRAD>(sy[k], sS[k], sI[k], sB[k], pat * pm_m[q], pwt, epsdt, tab, K, want_val != 0, val, h, gebc);
             if (GRAD) {
               row[q] += h;
               psig = fma(w_s[t], gebc, psig);

@@ -261,6 +261,7 @@ void seir_chains_destroy(seir_chains* c) {
   cudaFree(c->d_col_part); cudaFree(c->d_rowsum); cudaFree(c->d_upd); cudaFree(c->d_upd_part);
   cudaFree(c->d_tlp); cudaFree(c->d_i8_planes); cudaFree(c->d_i8_flags); cudaFree(c->d_hmc_u0); cudaFree(c->d_hmc_p); cudaFree(c->d_hmc_grad);
   cudaFree(c->d_hmc_val);
+  for (int g = 0; g < SEIR_MAX_GROUPS; ++g) cudaFree(c->d_traj_scratch[g]);
   if (c->grp_ready) {
     for (int g = 0; g < SEIR_MAX_GROUPS; ++g) {
       cudaStreamDestroy(c->grp_stream[g]);

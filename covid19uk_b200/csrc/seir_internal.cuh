@@ -126,6 +126,7 @@ struct seir_chains {
   int* d_last_acc;        // [4 kinds][B][4][SEIR_MMAX] last accepted proposal (MetropolisHastings accepted_results)
   // HMC workspace (allocated on first use)
   double *d_hmc_u0, *d_hmc_p, *d_hmc_grad, *d_hmc_val;
+  unsigned char* d_traj_scratch[SEIR_MAX_GROUPS];  // packed cells of the chains in flight of the trajectory kernel (hmc_traj.cu), per chain group
   // sweep scratch: sampled proposals and log-uniforms
   int* d_prop;
   double* d_logu;
@@ -202,6 +203,10 @@ int seir_hmc_step_leap(seir_chains* c, int i, int num_leapfrog, double* d_u, con
 int seir_launch_hmc(seir_chains* c, double* d_u, const double* d_momentum, const double* d_log_u, const double* d_step,
                     const double* d_inv_mass, int num_leapfrog, double* d_tlp, int* d_accept, double* d_dbg, cudaStream_t s);
 int seir_hmc_workspace(seir_chains* c);
+bool seir_hmc_traj_applies(const seir_chains* c);
+int seir_launch_hmc_traj(seir_chains* c, double* d_u, const double* d_log_u, const double* d_step, const double* d_inv_mass,
+                         int num_leapfrog, double* d_tlp, double* d_tlp_trace, int* d_accept, double* d_dbg, cudaStream_t s,
+                         seir_range r, int slot);
 int seir_launch_log_uniform(seir_range r, unsigned long long seed, unsigned chain0, unsigned sweep, unsigned purpose, double* d_out,
                             cudaStream_t s);
 int seir_launch_propose(seir_chains* c, const seir_update_cfg& cfg, unsigned long long seed, unsigned chain0, unsigned ctr,

@@ -95,7 +95,8 @@ struct sweep_out {
 // One sweep of the chains in r, enqueued on gs.  The sweep is a sequence of (L + 1) + 1 steps (leapfrogs, updates); after step
 // `mark_step` (counted from 1) the event `mark` is recorded on gs (burst stagger), if given.
 static int enqueue_sweep(seir_chains* c, const seir_sweep_spec* sp, unsigned sweep_index, seir_range r, cudaStream_t gs, double* d_u,
-                         const double* d_step, const double* d_inv_mass, double* d_tlp, const sweep_out& o, cudaEvent_t mark, int mark_step) {
+                         const double* d_step, const double* d_inv_mass, double* d_tlp, const sweep_out& o, cudaEvent_t mark, int mark_step,
+                         int group) {
   const int B = c->B, L = sp->num_leapfrog_steps, P = c->model->P;
   int step = 0;
   auto stepped = [&]() -> int {
@@ -105,12 +106,17 @@ static int enqueue_sweep(seir_chains* c, const seir_sweep_spec* sp, unsigned swe
   // ---- part 0: HMC on theta ----
   SEIR_TRY(seir_launch_hmc_momentum(c, sp->seed, sp->chain_offset, sweep_index, d_inv_mass, c->d_hmc_p, gs, r));
   SEIR_TRY(seir_launch_log_uniform(r, sp->seed, sp->chain_offset, sweep_index, 0x48u, c->d_logu, gs));
-  SEIR_TRY(seir_hmc_step_begin(c, d_u, gs, r));
-  for (int i = 0; i <= L; ++i) {
-    // (the last leapfrog kernel also writes row 4 of upd_tlp: results/hmc/target_log_prob)
-    SEIR_TRY(seir_hmc_step_leap(c, i, L, d_u, c->d_logu, d_step, d_inv_mass, d_tlp, o.upd_tlp ? o.upd_tlp + (size_t)4 * B : nullptr,
-                                o.hmc_accept, o.hmc_dbg, gs, r));
+  double* tlp_row4 = o.upd_tlp ? o.upd_tlp + (size_t)4 * B : nullptr;  // results/hmc/target_log_prob
+  if (seir_hmc_traj_applies(c)) {  // the whole transition in one persistent kernel (hmc_traj.cu)
+    SEIR_TRY(seir_launch_hmc_traj(c, d_u, c->d_logu, d_step, d_inv_mass, L, d_tlp, tlp_row4, o.hmc_accept, o.hmc_dbg, gs, r, group));
+    step += L;  // (counts as the L + 1 steps of the launch sequence below for the burst stagger)
     SEIR_TRY(stepped());
+  } else {
+    SEIR_TRY(seir_hmc_step_begin(c, d_u, gs, r));
+    for (int i = 0; i <= L; ++i) {
+      SEIR_TRY(seir_hmc_step_leap(c, i, L, d_u, c->d_logu, d_step, d_inv_mass, d_tlp, tlp_row4, o.hmc_accept, o.hmc_dbg, gs, r));
+      SEIR_TRY(stepped());
+    }
   }
   if (o.draws)  // u changes in the HMC step only
     SEIR_CUDA(cudaMemcpyAsync(o.draws + (size_t)r.b0 * P, d_u + (size_t)r.b0 * P, sizeof(double) * (size_t)r.nb * P, cudaMemcpyDeviceToDevice, gs));
@@ -141,11 +147,11 @@ int seir_launch_sweep(seir_chains* c, const seir_sweep_spec* sp, unsigned sweep_
   seir_range rg[SEIR_MAX_GROUPS];
   SEIR_TRY(sweep_prepare(c, G, rg));
   const sweep_out o{d_hmc_accept, d_hmc_dbg, d_upd_accept, d_upd_tlp, d_upd_trace, nullptr};
-  if (G == 1) return enqueue_sweep(c, sp, sweep_index, rg[0], s, d_u, d_step, d_inv_mass, d_tlp, o, nullptr, 0);
+  if (G == 1) return enqueue_sweep(c, sp, sweep_index, rg[0], s, d_u, d_step, d_inv_mass, d_tlp, o, nullptr, 0, 0);
   SEIR_CUDA(cudaEventRecord(c->grp_fork, s));
   for (int g = 0; g < G; ++g) {
     SEIR_CUDA(cudaStreamWaitEvent(c->grp_stream[g], c->grp_fork, 0));
-    SEIR_TRY(enqueue_sweep(c, sp, sweep_index, rg[g], c->grp_stream[g], d_u, d_step, d_inv_mass, d_tlp, o, nullptr, 0));
+    SEIR_TRY(enqueue_sweep(c, sp, sweep_index, rg[g], c->grp_stream[g], d_u, d_step, d_inv_mass, d_tlp, o, nullptr, 0, g));
     SEIR_CUDA(cudaEventRecord(c->grp_join[g], c->grp_stream[g]));
     SEIR_CUDA(cudaStreamWaitEvent(s, c->grp_join[g], 0));
   }
@@ -180,7 +186,7 @@ int seir_launch_sweep_burst(seir_chains* c, const seir_sweep_spec* sp, unsigned 
   };
   if (G == 1) {
     for (int k = 0; k < num_sweeps; ++k)
-      SEIR_TRY(enqueue_sweep(c, sp, sweep_index0 + (unsigned)k, rg[0], s, d_u, d_step, d_inv_mass, d_tlp, out_of(k), nullptr, 0));
+      SEIR_TRY(enqueue_sweep(c, sp, sweep_index0 + (unsigned)k, rg[0], s, d_u, d_step, d_inv_mass, d_tlp, out_of(k), nullptr, 0, 0));
     return SEIR_OK;
   }
   SEIR_CUDA(cudaEventRecord(c->grp_fork, s));
@@ -191,7 +197,7 @@ int seir_launch_sweep_burst(seir_chains* c, const seir_sweep_spec* sp, unsigned 
       const bool mark = stagger && k == 0 && g + 1 < G;
       if (stagger && k == 0 && g > 0) SEIR_CUDA(cudaStreamWaitEvent(c->grp_stream[g], c->grp_stagger[g - 1], 0));
       SEIR_TRY(enqueue_sweep(c, sp, sweep_index0 + (unsigned)k, rg[g], c->grp_stream[g], d_u, d_step, d_inv_mass, d_tlp, out_of(k),
-                             mark ? c->grp_stagger[g] : nullptr, mark_step));
+                             mark ? c->grp_stagger[g] : nullptr, mark_step, g));
     }
   for (int g = 0; g < G; ++g) {
     SEIR_CUDA(cudaEventRecord(c->grp_join[g], c->grp_stream[g]));

@@ -101,10 +101,27 @@ __device__ __forceinline__ void tf_theta_prep(const tf_model& md, const tf_chain
 #pragma unroll
   for (int i = 0; i < TF_NACC; ++i) acc[i] = 0.0;
   if (warp == 0) {
-    // warp 0: the sequential cumulative sum (same order as a cumsum) on shared memory, lane 0 only, plus the scalar priors
+    // warp 0: inclusive scan of alpha_t on shared memory -- lanes own consecutive chunks, shuffle scan over the chunk totals
+    // (the SAME order of additions as the trajectory kernel, hmc_traj.cu: the rate factors either of them leaves behind are
+    // bitwise equal); lane 0 then evaluates the scalar priors
+    {
+      const int n = T - 1, chunk = (n + 31) / 32;
+      const int c0 = min(n, lane * chunk), c1 = min(n, c0 + chunk);
+      double tot = 0.0;
+      for (int j = c0; j < c1; ++j) tot += alpha_t[j];
+      double incl = tot;
+#pragma unroll
+      for (int o = 1; o < 32; o <<= 1) {
+        const double up = __shfl_up_sync(0xffffffffu, incl, o);
+        if (lane >= o) incl += up;
+      }
+      double run = incl - tot;
+      for (int j = c0; j < c1; ++j) {
+        run += alpha_t[j];
+        cs[j] = run;
+      }
+    }
     if (lane == 0) {
-      double run = 0.0;
-      for (int k = 0; k < T - 1; ++k) { run += alpha_t[k]; cs[k] = run; }
       double prior = ildj;
       if (parts & SEIR_PART_PRIORS) {
         prior += normal_lp(alpha0, 10.0);                                                          // alpha_0  model_spec.py:140
