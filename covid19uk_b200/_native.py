@@ -17,7 +17,7 @@ PART_SEIR = 1
 PART_PRIORS = 2
 PART_ILDJ = 4
 PART_JOINT = 7
-ABI_VERSION = 8
+ABI_VERSION = 9
 
 
 class SeirSpec(ctypes.Structure):
@@ -81,6 +81,7 @@ SIGNATURES = {
     "seir_log_prob_cached": (c_int, [c_void_p, c_void_p, c_int, c_int, c_void_p, c_void_p]),
     "seir_log_prob": (c_int, [c_void_p, c_void_p, c_void_p, c_int, c_int, c_void_p, c_void_p]),
     "seir_log_prob_host": (c_int, [c_void_p, c_void_p, c_void_p, c_int, c_int, c_void_p]),
+    "seir_log_prob_host_u16": (c_int, [c_void_p, c_void_p, c_void_p, c_int, c_int, c_void_p]),
     "seir_last_h2d_bytes": (c_int64, [c_void_p]),
     "seir_log_prob_grad_cached": (c_int, [c_void_p, c_void_p, c_int, c_int, c_void_p, c_void_p, c_void_p]),
     "seir_run_stage": (c_int, [c_void_p, c_int, c_void_p, c_void_p, c_int, c_int, c_void_p, c_void_p, c_void_p]),
@@ -90,8 +91,9 @@ SIGNATURES = {
     "seir_hmc_draw": (c_int, [c_void_p, ctypes.c_uint64, ctypes.c_uint32, ctypes.c_uint32, c_void_p, c_void_p, c_void_p, c_void_p]),
     "seir_propose": (c_int, [c_void_p, c_void_p, ctypes.c_uint64, ctypes.c_uint32, ctypes.c_uint32, c_void_p, c_void_p, c_void_p]),
     "seir_mcmc_sweep": (c_int, [c_void_p, c_void_p, ctypes.c_uint32] + [c_void_p] * 10),
-    "seir_mcmc_burst": (c_int, [c_void_p, c_void_p, ctypes.c_uint32, ctypes.c_int32] + [c_void_p] * 11),
+    "seir_mcmc_burst": (c_int, [c_void_p, c_void_p, ctypes.c_uint32, ctypes.c_int32] + [c_void_p] * 10 + [ctypes.c_int32, c_void_p, c_void_p, c_void_p]),
     "seir_export_events": (c_int, [c_void_p, c_void_p, c_void_p]),
+    "seir_export_events_u16": (c_int, [c_void_p, c_void_p, c_void_p, c_void_p]),
     "seir_simulate": (c_int, [c_void_p, c_int, ctypes.c_uint64, ctypes.c_uint32, c_void_p, c_void_p, c_void_p, c_void_p, c_void_p, c_void_p]),
     "seir_reproduction_number": (c_int, [c_void_p, c_void_p, c_void_p, c_void_p]),
     "seir_pressure_components": (c_int, [c_void_p, c_void_p, c_void_p, c_void_p, c_void_p]),

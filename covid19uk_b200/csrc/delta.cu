@@ -669,11 +669,14 @@ int seir_launch_update_rounds(seir_chains* c, const seir_update_cfg* cfg4, int n
 // ------------------------------------------------------------------------------------------------
 // caches -> reference layout: events f64 [B, M, T, 3]  (the `seir` sample written to the posterior)
 // ------------------------------------------------------------------------------------------------
-__global__ void __launch_bounds__(256) seir_export_events_kernel(int M, int T, int Mp, const int* __restrict__ yse,
+// OUT = double (the reference's dtype) or unsigned short (compact posterior storage: counts are small integers; a count
+// beyond 65535 saturates and raises *overflow, which the caller checks)
+template <typename OUT>
+__global__ void __launch_bounds__(256) seir_export_events_kernel(int M, int T, int Mp, int b0, const int* __restrict__ yse,
                                                                  const int* __restrict__ yei, const int* __restrict__ yir,
-                                                                 double* __restrict__ events) {
+                                                                 OUT* __restrict__ events, int* __restrict__ overflow) {
   __shared__ int tile[3][32][33];
-  const int b = blockIdx.z, m0 = blockIdx.x * 32, t0 = blockIdx.y * 32;
+  const int b = b0 + blockIdx.z, m0 = blockIdx.x * 32, t0 = blockIdx.y * 32;
   const int tx = threadIdx.x & 31, ty = threadIdx.x >> 5;  // 8 warps
   for (int r = ty; r < 32; r += 8) {                        // r: day, tx: metapopulation (coalesced slab reads)
     const int t = t0 + r, m = m0 + tx;
@@ -688,10 +691,18 @@ __global__ void __launch_bounds__(256) seir_export_events_kernel(int M, int T, i
   for (int r = ty; r < 32; r += 8) {                        // r: metapopulation, lanes cover 32 days x 3 transitions
     const int m = m0 + r;
     if (m >= M) continue;
-    double* dst = events + (((size_t)b * M + m) * T + t0) * 3;
+    OUT* dst = events + (((size_t)b * M + m) * T + t0) * 3;
     for (int k = tx; k < 96; k += 32) {
       const int t = k / 3, x = k - 3 * t;
-      if (t0 + t < T) dst[k] = (double)tile[x][t][r];
+      if (t0 + t < T) {
+        const int v = tile[x][t][r];
+        if (sizeof(OUT) == 2) {
+          if ((unsigned)v > 65535u) *overflow = 1;
+          dst[k] = (OUT)(v < 0 ? 0 : (v > 65535 ? 65535 : v));
+        } else {
+          dst[k] = (OUT)v;
+        }
+      }
     }
   }
 }
@@ -699,7 +710,20 @@ __global__ void __launch_bounds__(256) seir_export_events_kernel(int M, int T, i
 int seir_launch_export_events(seir_chains* c, double* d_events, cudaStream_t s) {
   const seir_model* m = c->model;
   dim3 grid((m->M + 31) / 32, (m->T + 31) / 32, c->B);
-  seir_export_events_kernel<<<grid, 256, 0, s>>>(m->M, m->T, m->Mp, c->d_yse, c->d_yei, c->d_yir, d_events);
+  seir_export_events_kernel<double><<<grid, 256, 0, s>>>(m->M, m->T, m->Mp, 0, c->d_yse, c->d_yei, c->d_yir, d_events, nullptr);
   seir_count_launch(1);
   return seir_cuda_check(cudaGetLastError(), "seir_export_events_kernel");
+}
+
+int seir_launch_export_events_u16(seir_chains* c, unsigned short* d_events, int* d_overflow, cudaStream_t s) {
+  return seir_launch_export_events_u16_range(c, d_events, d_overflow, s, seir_all(c));
+}
+
+// chains [r.b0, r.b0 + r.nb); d_events is the array of ALL chains
+int seir_launch_export_events_u16_range(seir_chains* c, unsigned short* d_events, int* d_overflow, cudaStream_t s, seir_range r) {
+  const seir_model* m = c->model;
+  dim3 grid((m->M + 31) / 32, (m->T + 31) / 32, r.nb);
+  seir_export_events_kernel<unsigned short><<<grid, 256, 0, s>>>(m->M, m->T, m->Mp, r.b0, c->d_yse, c->d_yei, c->d_yir, d_events, d_overflow);
+  seir_count_launch(1);
+  return seir_cuda_check(cudaGetLastError(), "seir_export_events_kernel<u16>");
 }

@@ -405,10 +405,11 @@ void seir_pack_cancel(void);
 // Each chunk's ingest kernel runs as soon as its copy lands (event-ordered on the compute stream); the events-wide
 // kernels (coefficients, contraction) and the theta-dependent half run in parts: on a second stream for the chains
 // already in, after the transfer for the last part.
-static int log_prob_host_impl(seir_chains* c, const double* h_events, const double* h_theta, int kind, int parts, double* h_out);
+static int log_prob_host_impl(seir_chains* c, const double* h_events, const unsigned short* h_events_u16, const double* h_theta, int kind,
+                              int parts, double* h_out);
 
 int seir_log_prob_host(seir_chains* c, const double* h_events, const double* h_theta, int kind, int parts, double* h_out) {
-  const int rc = log_prob_host_impl(c, h_events, h_theta, kind, parts, h_out);
+  const int rc = log_prob_host_impl(c, h_events, nullptr, h_theta, kind, parts, h_out);
   if (rc != SEIR_OK && c) {
     seir_device_guard guard_(c->model->device);  // leave nothing behind that still reads the caller's buffers: pool jobs, copies in flight
     seir_pack_cancel();
@@ -417,8 +418,22 @@ int seir_log_prob_host(seir_chains* c, const double* h_events, const double* h_t
   return rc;
 }
 
-static int log_prob_host_impl(seir_chains* c, const double* h_events, const double* h_theta, int kind, int parts, double* h_out) {
-  if (!c || !h_events || !h_theta || !h_out) return seir_set_error(SEIR_ERR_BAD_ARG, "seir_log_prob_host: NULL argument");
+// Integer host contract: the events arrive as uint16 counts [B,M,T,3] (what they are: model_spec.py:118-126 stores counts in
+// float64 because TensorFlow wants one dtype).  Nothing is narrowed on the host; the chunks travel as they are, a quarter of
+// the float64 bytes, and everything else is the pipeline of seir_log_prob_host.
+int seir_log_prob_host_u16(seir_chains* c, const uint16_t* h_events, const double* h_theta, int kind, int parts, double* h_out) {
+  if (!h_events) return seir_set_error(SEIR_ERR_BAD_ARG, "seir_log_prob_host_u16: NULL argument");
+  const int rc = log_prob_host_impl(c, nullptr, h_events, h_theta, kind, parts, h_out);
+  if (rc != SEIR_OK && c) {
+    seir_device_guard guard_(c->model->device);
+    cudaDeviceSynchronize();
+  }
+  return rc;
+}
+
+static int log_prob_host_impl(seir_chains* c, const double* h_events, const unsigned short* h_events_u16, const double* h_theta, int kind,
+                              int parts, double* h_out) {
+  if (!c || (!h_events && !h_events_u16) || !h_theta || !h_out) return seir_set_error(SEIR_ERR_BAD_ARG, "seir_log_prob_host: NULL argument");
   SEIR_TRY(check_parts(kind, parts));
   const seir_model* m = c->model;
   seir_device_guard guard_(m->device);
@@ -479,7 +494,8 @@ static int log_prob_host_impl(seir_chains* c, const double* h_events, const doub
   c->last_h2d_bytes = (int64_t)(nt * sizeof(double));
   if (parts & SEIR_PART_SEIR) {
     const int nch = c->stage_nchunks, cb = (B + nch - 1) / nch;  // chains per chunk (the last chunk may be short)
-    const int jpc = seir_pack_begin(h_events, c->h_stage_u16, (size_t)cb * per_chain, ne, nch);
+    const unsigned short* src_u16 = h_events_u16 ? h_events_u16 : c->h_stage_u16;
+    const int jpc = h_events_u16 ? 1 : seir_pack_begin(h_events, c->h_stage_u16, (size_t)cb * per_chain, ne, nch);
     tr_begin = us_now();
     SEIR_TRY(seir_ingest_reset(c, s));
     int front = 0, back = nch - 1;       // next chunk expected from the pool / next chunk the caller may claim
@@ -492,7 +508,7 @@ static int log_prob_host_impl(seir_chains* c, const double* h_events, const doub
       const size_t off = (size_t)b0 * per_chain, n = (size_t)nb * per_chain;
       c->last_h2d_bytes += (int64_t)(n * (narrowed ? sizeof(unsigned short) : sizeof(double)));
       if (narrowed)
-        SEIR_CUDA(cudaMemcpyAsync(c->d_stage_u16 + off, c->h_stage_u16 + off, n * sizeof(unsigned short), cudaMemcpyHostToDevice, cs));
+        SEIR_CUDA(cudaMemcpyAsync(c->d_stage_u16 + off, src_u16 + off, n * sizeof(unsigned short), cudaMemcpyHostToDevice, cs));
       else
         SEIR_CUDA(cudaMemcpyAsync(c->d_stage_events + off, h_events + off, n * sizeof(double), cudaMemcpyHostToDevice, cs));
       SEIR_CUDA(cudaEventRecord(c->stage_ev[k], cs));
@@ -542,6 +558,14 @@ static int log_prob_host_impl(seir_chains* c, const double* h_events, const doub
       }
       return SEIR_OK;
     };
+    if (h_events_u16) {  // integer contract: every chunk as it is, in order
+      for (front = 0; front < nch;) {
+        SEIR_TRY(ship(front, true));
+        ++front;
+        SEIR_TRY(early_part());
+      }
+      pool_done = claim_done = true;
+    }
     while (!(pool_done && claim_done)) {
       bool progressed = false;
       // float64 chunks from the back
@@ -735,9 +759,12 @@ int seir_mcmc_sweep(seir_chains* c, const seir_sweep_spec* sp, uint32_t sweep_in
 
 int seir_mcmc_burst(seir_chains* c, const seir_sweep_spec* sp, uint32_t sweep_index0, int32_t num_sweeps, double* d_u,
                     const double* d_step_size, const double* d_inv_mass, double* d_tlp, int32_t* d_hmc_accept, double* d_hmc_dbg,
-                    int32_t* d_upd_accept, double* d_upd_tlp, int32_t* d_upd_trace, double* d_draws, void* stream) {
+                    int32_t* d_upd_accept, double* d_upd_tlp, int32_t* d_upd_trace, double* d_draws, int32_t keep_every,
+                    uint16_t* d_events_u16, int32_t* d_overflow, void* stream) {
   if (!c || !sp || !d_step_size || !d_tlp || !d_hmc_accept || !d_upd_accept)
     return seir_set_error(SEIR_ERR_BAD_ARG, "seir_mcmc_burst: NULL argument");
+  if (keep_every < 1 || (d_events_u16 && !d_overflow))
+    return seir_set_error(SEIR_ERR_BAD_ARG, "seir_mcmc_burst: keep_every must be >= 1 and d_events_u16 needs d_overflow");
   seir_device_guard guard_(c->model->device);
   SEIR_TRY(check_dev_ptr(d_u, "d_u"));
   const int T = c->model->T;
@@ -747,7 +774,7 @@ int seir_mcmc_burst(seir_chains* c, const seir_sweep_spec* sp, uint32_t sweep_in
     return seir_set_error(SEIR_ERR_BAD_ARG, "seir_mcmc_burst: invalid sweep spec");
   if (num_sweeps == 0) return SEIR_OK;
   return seir_launch_sweep_burst(c, sp, sweep_index0, num_sweeps, d_u, d_step_size, d_inv_mass, d_tlp, d_hmc_accept, d_hmc_dbg,
-                                 d_upd_accept, d_upd_tlp, d_upd_trace, d_draws, (cudaStream_t)stream);
+                                 d_upd_accept, d_upd_tlp, d_upd_trace, d_draws, keep_every, d_events_u16, d_overflow, (cudaStream_t)stream);
 }
 
 int seir_export_events(seir_chains* c, double* d_events, void* stream) {
@@ -755,6 +782,13 @@ int seir_export_events(seir_chains* c, double* d_events, void* stream) {
   seir_device_guard guard_(c->model->device);
   SEIR_TRY(check_dev_ptr(d_events, "d_events"));
   return seir_launch_export_events(c, d_events, (cudaStream_t)stream);
+}
+
+int seir_export_events_u16(seir_chains* c, uint16_t* d_events, int32_t* d_overflow, void* stream) {
+  if (!c || !d_overflow) return seir_set_error(SEIR_ERR_BAD_ARG, "seir_export_events_u16: NULL argument");
+  seir_device_guard guard_(c->model->device);
+  SEIR_TRY(check_dev_ptr(d_events, "d_events"));
+  return seir_launch_export_events_u16(c, d_events, d_overflow, (cudaStream_t)stream);
 }
 
 int seir_simulate(const seir_model* m, int B, uint64_t seed, uint32_t chain_offset, const double* d_alpha_path, const double* d_scalars,

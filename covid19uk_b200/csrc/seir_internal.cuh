@@ -216,8 +216,11 @@ int seir_launch_sweep(seir_chains* c, const seir_sweep_spec* sp, unsigned sweep_
                       double* d_upd_tlp, int* d_upd_trace, cudaStream_t s);
 int seir_launch_sweep_burst(seir_chains* c, const seir_sweep_spec* sp, unsigned sweep_index0, int num_sweeps, double* d_u,
                             const double* d_step, const double* d_inv_mass, double* d_tlp, int* d_hmc_accept, double* d_hmc_dbg,
-                            int* d_upd_accept, double* d_upd_tlp, int* d_upd_trace, double* d_draws, cudaStream_t s);
+                            int* d_upd_accept, double* d_upd_tlp, int* d_upd_trace, double* d_draws, int keep_every,
+                            unsigned short* d_events_u16, int* d_overflow, cudaStream_t s);
 int seir_launch_export_events(seir_chains* c, double* d_events, cudaStream_t s);
+int seir_launch_export_events_u16(seir_chains* c, unsigned short* d_events, int* d_overflow, cudaStream_t s);
+int seir_launch_export_events_u16_range(seir_chains* c, unsigned short* d_events, int* d_overflow, cudaStream_t s, seir_range r);
 int seir_launch_simulate(const seir_model* m, int B, unsigned long long seed, unsigned chain0, const double* d_alpha_path,
                          const double* d_scal, const double* d_spatial, const double* d_init_state, double* d_events, cudaStream_t s);
 int seir_launch_rit(seir_chains* c, const double* d_theta, double* d_out, cudaStream_t s);

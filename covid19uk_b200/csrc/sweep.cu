@@ -90,6 +90,8 @@ struct sweep_out {
   double* upd_tlp;    // [5][B]: rows 0..3 the four discrete kernels (last repetition), row 4 right after the HMC step
   int* upd_trace;     // [4][B][4][SEIR_MMAX]
   double* draws;      // [B][P]: u after the sweep
+  unsigned short* events_u16;  // [B][M][T][3]: the events after the sweep, compact
+  int* overflow;               // set when a count does not fit 16 bits
 };
 
 // One sweep of the chains in r, enqueued on gs.  The sweep is a sequence of (L + 1) + 1 steps (leapfrogs, updates); after step
@@ -126,6 +128,7 @@ static int enqueue_sweep(seir_chains* c, const seir_sweep_spec* sp, unsigned swe
   SEIR_TRY(seir_launch_update_rounds(c, cfg4, sp->num_event_time_updates, sp->seed, sp->chain_offset, sweep_index * 64u, c->d_prop, c->d_logu,
                                      d_tlp, o.upd_accept, o.upd_tlp, o.upd_trace, gs, r));
   SEIR_TRY(stepped());
+  if (o.events_u16) SEIR_TRY(seir_launch_export_events_u16_range(c, o.events_u16, o.overflow, gs, r));
   return SEIR_OK;
 }
 
@@ -146,7 +149,7 @@ int seir_launch_sweep(seir_chains* c, const seir_sweep_spec* sp, unsigned sweep_
   const int G = sweep_groups(c, false);
   seir_range rg[SEIR_MAX_GROUPS];
   SEIR_TRY(sweep_prepare(c, G, rg));
-  const sweep_out o{d_hmc_accept, d_hmc_dbg, d_upd_accept, d_upd_tlp, d_upd_trace, nullptr};
+  const sweep_out o{d_hmc_accept, d_hmc_dbg, d_upd_accept, d_upd_tlp, d_upd_trace, nullptr, nullptr, nullptr};
   if (G == 1) return enqueue_sweep(c, sp, sweep_index, rg[0], s, d_u, d_step, d_inv_mass, d_tlp, o, nullptr, 0, 0);
   SEIR_CUDA(cudaEventRecord(c->grp_fork, s));
   for (int g = 0; g < G; ++g) {
@@ -158,14 +161,20 @@ int seir_launch_sweep(seir_chains* c, const seir_sweep_spec* sp, unsigned sweep_
   return SEIR_OK;
 }
 
-// n sweeps with fixed step size / mass matrix; sweep k writes its results at offset k of arrays with a leading [n] axis
-// (d_hmc_accept [n][B], d_hmc_dbg [n][B][4], d_upd_accept [n][4][B], d_upd_tlp [n][5][B], d_upd_trace [n][4][B][4][MMAX],
-// d_draws [n][B][P]; the last three and d_hmc_dbg may be NULL).  Chains and traces are bit-identical to n calls of
-// seir_launch_sweep with sweep indices sweep_index0 .. sweep_index0 + n - 1.
+// n sweeps with fixed step size / mass matrix.  keep_every = 1: sweep k writes its results at offset k of arrays with a
+// leading [n] axis (d_hmc_accept [n][B], d_hmc_dbg [n][B][4], d_upd_accept [n][4][B], d_upd_tlp [n][5][B], d_upd_trace
+// [n][4][B][4][MMAX], d_draws [n][B][P], d_events_u16 [n][B][M][T][3]; the last four and d_hmc_dbg may be NULL).
+// keep_every = e > 1 (tfp.mcmc.sample_chain's num_steps_between_results = e - 1): only sweeps e - 1, 2e - 1, ... are kept, at
+// offsets 0, 1, ...; the arrays have a leading [n / e + 1] axis whose LAST slot is scratch for the sweeps in between.
+// Chains and traces are bit-identical to n calls of seir_launch_sweep with sweep indices sweep_index0 .. sweep_index0 + n - 1.
 int seir_launch_sweep_burst(seir_chains* c, const seir_sweep_spec* sp, unsigned sweep_index0, int num_sweeps, double* d_u,
                             const double* d_step, const double* d_inv_mass, double* d_tlp, int* d_hmc_accept, double* d_hmc_dbg,
-                            int* d_upd_accept, double* d_upd_tlp, int* d_upd_trace, double* d_draws, cudaStream_t s) {
+                            int* d_upd_accept, double* d_upd_tlp, int* d_upd_trace, double* d_draws, int keep_every,
+                            unsigned short* d_events_u16, int* d_overflow, cudaStream_t s) {
   const int G = sweep_groups(c, true), B = c->B, P = c->model->P;
+  if (keep_every < 1) keep_every = 1;
+  const int spare = num_sweeps / keep_every;  // slot of the sweeps that are not kept
+  const size_t ev_per = (size_t)B * c->model->M * c->model->T * 3;
   seir_range rg[SEIR_MAX_GROUPS];
   SEIR_TRY(sweep_prepare(c, G, rg));
   static int stagger = -1;
@@ -176,13 +185,17 @@ int seir_launch_sweep_burst(seir_chains* c, const seir_sweep_spec* sp, unsigned 
   int mark_step = mark_env > 0 ? mark_env : steps / G;
   if (mark_step < 1) mark_step = 1;
   if (mark_step > steps) mark_step = steps;
-  auto out_of = [&](int k) {
+  auto out_of = [&](int sweep) {
+    const bool kept = (sweep + 1) % keep_every == 0;
+    const int k = kept ? sweep / keep_every : spare;
     return sweep_out{d_hmc_accept + (size_t)k * B,
                      d_hmc_dbg ? d_hmc_dbg + (size_t)k * B * 4 : nullptr,
                      d_upd_accept + (size_t)k * 4 * B,
                      d_upd_tlp ? d_upd_tlp + (size_t)k * 5 * B : nullptr,
                      d_upd_trace ? d_upd_trace + (size_t)k * 4 * B * 4 * SEIR_MMAX : nullptr,
-                     d_draws ? d_draws + (size_t)k * B * P : nullptr};
+                     (d_draws && kept) ? d_draws + (size_t)k * B * P : nullptr,
+                     (d_events_u16 && kept) ? d_events_u16 + (size_t)k * ev_per : nullptr,
+                     d_overflow};
   };
   if (G == 1) {
     for (int k = 0; k < num_sweeps; ++k)

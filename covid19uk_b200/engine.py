@@ -294,15 +294,37 @@ class SeirEngine:
                                            p(hmc_accept), p(hmc_dbg), p(upd_accept), p(upd_tlp), p(upd_trace), self._stream()))
 
     def mcmc_burst(self, spec: "nat.SeirSweepSpec", sweep_index0, num_sweeps, u, step_size, inv_mass, tlp, hmc_accept, upd_accept,
-                   hmc_dbg=None, upd_tlp=None, upd_trace=None, draws=None):
+                   hmc_dbg=None, upd_tlp=None, upd_trace=None, draws=None, keep_every=1, events_u16=None, overflow=None):
         """``num_sweeps`` sweeps with a fixed step size / mass matrix in one call (seir_mcmc_burst): the result tensors carry
-        a leading [num_sweeps] axis; chains and traces are bit-identical to ``num_sweeps`` calls of :meth:`mcmc_sweep`."""
+        a leading [num_sweeps] axis; chains and traces are bit-identical to ``num_sweeps`` calls of :meth:`mcmc_sweep`.
+        ``keep_every = e`` keeps every e-th sweep only (result tensors: ``num_sweeps // e`` kept slots + one scratch slot);
+        ``events_u16`` [slots,B,M,T,3] (torch.uint16) receives the compact events of every kept sweep."""
         B = u.shape[0]
         self.require_events(B, "mcmc_burst")
         p = lambda t: c_void_p(t.data_ptr()) if t is not None else c_void_p(0)
         nat.check(self.lib.seir_mcmc_burst(self.chains(B), byref(spec), int(sweep_index0), int(num_sweeps), p(u), p(step_size), p(inv_mass),
                                            p(tlp), p(hmc_accept), p(hmc_dbg), p(upd_accept), p(upd_tlp), p(upd_trace), p(draws),
-                                           self._stream()))
+                                           int(keep_every), p(events_u16), p(overflow), self._stream()))
+
+    def export_events_u16(self, B: int, out=None) -> torch.Tensor:
+        """The current events as uint16 counts [B,M,T,3] (compact posterior storage); raises if a count exceeds 65535."""
+        self.require_events(B, "export_events_u16")
+        if out is None:
+            out = torch.empty((B, self.M, self.T, 3), dtype=torch.uint16, device=self.device)
+        ovf = torch.zeros(1, dtype=torch.int32, device=self.device)
+        nat.check(self.lib.seir_export_events_u16(self.chains(B), c_void_p(out.data_ptr()), c_void_p(ovf.data_ptr()), self._stream()))
+        if int(ovf.item()) != 0:
+            raise OverflowError("an event count exceeds 65535: store the events as float64 (events_dtype=torch.float64)")
+        return out
+
+    def log_prob_host_u16(self, h_events: torch.Tensor, h_theta: torch.Tensor, h_out: torch.Tensor, kind=nat.THETA_CONSTRAINED, parts=nat.PART_SEIR):
+        """Integer host contract: (pinned) uint16 events [B,M,T,3] in, log-prob [B] out, synchronous."""
+        B = h_events.shape[0]
+        assert h_events.dtype in (torch.uint16, torch.int16) and h_events.is_contiguous() and not h_events.is_cuda
+        nat.check(self.lib.seir_log_prob_host_u16(self.chains(B), c_void_p(h_events.data_ptr()), c_void_p(h_theta.data_ptr()), kind, parts, c_void_p(h_out.data_ptr())))
+        if parts & nat.PART_SEIR:
+            self._ingested(B)
+        return h_out
 
     def export_events(self, B: int) -> torch.Tensor:
         self.require_events(B, "export_events")

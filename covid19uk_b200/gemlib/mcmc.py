@@ -47,9 +47,12 @@ class DeviceEvents:
     def shape(self):
         return (self.num_chains, self.engine.M, self.engine.T, 3)
 
-    def to_tensor(self) -> torch.Tensor:
+    def to_tensor(self, dtype=torch.float64) -> torch.Tensor:
+        """The events in the reference layout [B,M,T,3]: float64 (the reference's dtype) or torch.uint16 (compact)."""
         self.check("DeviceEvents.to_tensor")
-        return self.engine.export_events(self.num_chains)
+        if dtype == torch.uint16:
+            return self.engine.export_events_u16(self.num_chains)
+        return self.engine.export_events(self.num_chains).to(dtype)
 
     def numpy(self):
         return self.to_tensor().cpu().numpy()
@@ -295,6 +298,82 @@ class GibbsKernel:
             inner.append(tm.MetropolisHastingsResults(acc_res, upd_acc[s] != 0, None, None))
         res1 = GibbsKernelResults(upd_tlp[3], inner)
         return [new_u, ev], GibbsKernelResults(tlp, [res0, res1])
+
+    # -- a whole window of the FIXED standard kernel in one seir_mcmc_burst call --
+    def burst_plan(self, state):
+        """(parts, tree, moves, base) when this kernel is the reference's standard tree with a plain (non-adapting) HMC kernel on
+        the parameter block -- what make_fixed_window_sampler builds (inference.py:199-242) -- else None."""
+        if not self.fused:
+            return None
+        parts = self.normalise_state(state)
+        if not isinstance(parts, list):
+            return None
+        tree = self._standard_tree(self._kernels(parts))
+        if tree is None or tree[1]:  # adaptation wrappers need the host between sweeps
+            return None
+        base, _, scan = tree
+        moves = scan.inner_kernel._kernels([parts[1]])
+        if len(moves) != 4 or not all(isinstance(k, tm.MetropolisHastings) for _, k in moves) or scan.num_updates > 16:
+            return None
+        return parts, tree, moves, base
+
+    def burst(self, plan, previous_kernel_results, num_results, keep_every, sp, events_dtype=None):
+        """``num_results * keep_every`` sweeps on the device in ONE C call (tfp.mcmc.sample_chain over a burst,
+        inference.py:107-117, 232-240), every ``keep_every``-th kept.  Returns (u draws [n,B,P], events draws [n,B,M,T,3] or
+        None, results with a leading [n] axis on every field, final state, final results); bit-identical to ``one_step`` in a
+        loop (tests/test_gpu_kernel_tree.py)."""
+        parts, tree, moves, base = plan
+        _, _, scan = tree
+        u, ev = parts
+        spec = self._sweep_spec(base, scan, moves, self.chain_offset, sp.base)
+        if spec is None:
+            return None
+        eng, B, dev = self.engine, ev.num_chains, self.engine.device
+        n, e = int(num_results), int(keep_every)
+        slots = n + (1 if e > 1 else 0)
+        hmc_prev = previous_kernel_results.inner_results[0]
+        step = tm.unnest.get_innermost(hmc_prev, "step_size").contiguous()
+        md = tm.unnest.get_innermost(hmc_prev, "momentum_distribution", default=False)
+        inv_mass = md.inv_mass.contiguous() if md not in (None, False) else None
+        new_u = u.clone()
+        tlp = previous_kernel_results.target_log_prob.clone()
+        hmc_acc = torch.empty(slots, B, dtype=torch.int32, device=dev)
+        hmc_dbg = torch.empty(slots, B, 4, dtype=torch.float64, device=dev)
+        upd_acc = torch.empty(slots, 4, B, dtype=torch.int32, device=dev)
+        upd_tlp = torch.empty(slots, 5, B, dtype=torch.float64, device=dev)
+        upd_trace = torch.empty(slots, 4, B, 4, nat.MMAX, dtype=torch.int32, device=dev)
+        draws = torch.empty(slots, B, eng.P, dtype=torch.float64, device=dev)
+        ev16 = ovf = None
+        if events_dtype is not None:
+            ev16 = torch.empty(slots, B, eng.M, eng.T, 3, dtype=torch.uint16, device=dev)
+            ovf = torch.zeros(1, dtype=torch.int32, device=dev)
+        eng.mcmc_burst(spec, sp.sweep, n * e, new_u, step, inv_mass, tlp, hmc_acc, upd_acc, hmc_dbg=hmc_dbg, upd_tlp=upd_tlp,
+                       upd_trace=upd_trace, draws=draws, keep_every=e, events_u16=ev16, overflow=ovf)
+        events = None
+        if ev16 is not None:
+            if int(ovf.item()) != 0:
+                raise OverflowError("an event count exceeds 65535: set Mcmc.store_events_as: float64")
+            events = ev16[:n] if events_dtype == torch.uint16 else ev16[:n].to(events_dtype)
+        md_out = md if md is not False else None
+        stepn = step.unsqueeze(0).expand(n, B)
+        hmc_res = tm.HMCResults(hmc_acc[:n] != 0, upd_tlp[:n, 4], hmc_dbg[:n, :, 0], stepn, md_out, hmc_dbg[:n, :, 1])
+        inner = []
+        for s_, (_, k) in enumerate(moves):
+            cols = k.inner_kernel.update_spec.mmax if k.inner_kernel.kind == 0 else 1
+            tr = upd_trace[:n, s_]
+            acc_res = EventTimesResults(None, upd_tlp[:n, s_], tr[:, :, 0, :cols], tr[:, :, 1, :cols], tr[:, :, 2, :cols], tr[:, :, 3, :cols])
+            inner.append(tm.MetropolisHastingsResults(acc_res, upd_acc[:n, s_] != 0, None, None))
+        stacked = GibbsKernelResults(upd_tlp[:n, 3], [hmc_res, GibbsKernelResults(upd_tlp[:n, 3], inner)])
+
+        def last(x):  # the final kernel results: slot n - 1
+            return None if x is None else x[n - 1]
+
+        hmc_last = tm.HMCResults(last(hmc_res.is_accepted), last(hmc_res.target_log_prob), last(hmc_res.log_accept_ratio), step, md_out,
+                                 last(hmc_res.proposed_target_log_prob))
+        inner_last = [tm.MetropolisHastingsResults(EventTimesResults(None, *[last(f) for f in r.accepted_results[1:]]), last(r.is_accepted), None, None)
+                      for r in inner]
+        final = GibbsKernelResults(tlp, [hmc_last, GibbsKernelResults(upd_tlp[n - 1, 3], inner_last)])
+        return draws[:n], events, stacked, [new_u, ev], final
 
     def one_step(self, state, previous_kernel_results, seed=None, chain_offset=None):
         parts = self.normalise_state(state)

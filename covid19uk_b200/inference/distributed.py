@@ -56,3 +56,89 @@ def gather_chains(tree, num_chains: int, chain_dim: int = 1, group=None):
         return _gather_tensor(node, chain_dim, counts, group)
 
     return rec(tree)
+
+
+# ---- the product path: per-burst gather to the rank that writes the posterior file -----------------------------------------
+def world():
+    """(rank, world_size) of the default process group, (0, 1) outside torch.distributed."""
+    if dist.is_available() and dist.is_initialized():
+        return dist.get_rank(), dist.get_world_size()
+    return 0, 1
+
+
+def init_from_env(device_index=None):
+    """One process per GPU under ``torchrun``: initialise NCCL (or gloo without CUDA) from RANK / WORLD_SIZE / LOCAL_RANK.
+    Returns (rank, world_size, local_rank); a no-op (0, 1, 0) when WORLD_SIZE is unset or 1."""
+    import os
+
+    ws = int(os.environ.get("WORLD_SIZE", "1"))
+    if ws <= 1:
+        return 0, 1, 0
+    local = int(os.environ.get("LOCAL_RANK", "0")) if device_index is None else int(device_index)
+    if not dist.is_initialized():
+        if torch.cuda.is_available():
+            torch.cuda.set_device(local)
+            dist.init_process_group("nccl", device_id=torch.device("cuda", local))
+        else:
+            dist.init_process_group("gloo")
+    return dist.get_rank(), dist.get_world_size(), local
+
+
+_RAW = {torch.uint16: torch.uint8, torch.int16: torch.uint8}  # dtypes NCCL / gloo do not take: moved as raw bytes (last axis x 2)
+
+
+def _gather_to(t: torch.Tensor, chain_dim: int, counts, dst: int, group=None, max_bytes=1 << 30):
+    """Gather ``t`` (chain axis ``chain_dim``, ``counts[r]`` chains on rank r) to rank ``dst`` in global chain order; other
+    ranks get None.  Large tensors (the compact event draws) travel in slices of the leading axis of at most ``max_bytes``
+    per rank, so that the receive buffers stay bounded."""
+    rank, ws = dist.get_rank(group), dist.get_world_size(group)
+    cmax = max(counts)
+    raw = _RAW.get(t.dtype)
+    x = t.contiguous().view(raw) if raw is not None else (t.to(torch.uint8) if t.dtype == torch.bool else t)
+    x = x.movedim(chain_dim, 0).contiguous()  # [B_local, ...]
+    if x.shape[0] < cmax:
+        x = torch.cat([x, torch.zeros((cmax - x.shape[0],) + tuple(x.shape[1:]), dtype=x.dtype, device=x.device)], dim=0)
+    rest = tuple(x.shape[1:])
+    lead = rest[0] if rest else 1
+    per_lead = x[0].numel() * x.element_size() * cmax // max(lead, 1)
+    step = max(1, min(lead, max_bytes // max(per_lead, 1))) if rest else 1
+    pieces = []
+    for a in range(0, lead, step):
+        part = x[:, a:a + step].contiguous() if rest else x
+        bufs = [torch.empty_like(part) for _ in range(ws)] if rank == dst else None
+        dist.gather(part, bufs, dst=dst, group=group)
+        if rank == dst:
+            pieces.append(torch.cat([bufs[r][:counts[r]] for r in range(ws)], dim=0))
+        if not rest:
+            break
+    if rank != dst:
+        return None
+    full = torch.cat(pieces, dim=1) if rest else pieces[0]
+    full = full.movedim(0, chain_dim)
+    if t.dtype == torch.bool:
+        return full.to(torch.bool)
+    return full.contiguous().view(t.dtype) if raw is not None else full
+
+
+def gather_to_rank0(tree, num_chains: int, chain_dim: int = 1, group=None, dst: int = 0):
+    """The per-burst exchange of the product path: every rank's slice of a (nested dict / list of) tensors with
+    a chain axis -> rank ``dst`` in global chain order (NCCL gather over NVLink on the GPU box, gloo in the CPU tests).
+    Returns the gathered tree on ``dst`` and None elsewhere; the identity outside torch.distributed.  ``None`` leaves pass."""
+    if not (dist.is_available() and dist.is_initialized()) or dist.get_world_size(group) == 1:
+        return tree
+    ws = dist.get_world_size(group)
+    counts = [shard_chains(num_chains, ws, r)[1] for r in range(ws)]
+    me = dist.get_rank(group)
+
+    def rec(node):
+        if node is None:
+            return None
+        if isinstance(node, dict):
+            out = {k: rec(v) for k, v in node.items()}
+            return out if me == dst else None
+        if isinstance(node, (list, tuple)):
+            out = [rec(v) for v in node]
+            return type(node)(out) if me == dst else None
+        return _gather_to(node, chain_dim, counts, dst, group)
+
+    return rec(tree)

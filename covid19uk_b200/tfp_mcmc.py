@@ -323,27 +323,44 @@ def _stack_tree(items):
 
 
 def sample_chain(num_results, current_state, kernel, previous_kernel_results=None, return_final_kernel_results=True,
-                 trace_fn=None, seed=None, first_sweep_index=None):
-    """``num_results`` transitions of ``kernel`` from ``current_state`` = [u, events].  Returns
-    ``(draws, trace, final_kernel_results)``: draws = [u [n,B,P], events [n,B,M,T,3]] (float64 CUDA tensors, like the
-    reference's draws), trace = the stacked outputs of ``trace_fn(state, results)``."""
+                 trace_fn=None, seed=None, first_sweep_index=None, num_steps_between_results=0, events_dtype=torch.float64,
+                 return_final_state=False):
+    """``num_results`` kept transitions of ``kernel`` from ``current_state`` = [u, events]
+    (``num_steps_between_results`` unrecorded transitions before each, as in tfp.mcmc.sample_chain).  Returns
+    ``(draws, trace, final_kernel_results)``: draws = [u [n,B,P] float64, events [n,B,M,T,3]] (CUDA tensors; ``events_dtype``
+    float64 like the reference's draws, ``torch.uint16`` for compact storage, ``None`` to skip the event draws), trace = the
+    stacked outputs of ``trace_fn(state, results)``.  ``return_final_state=True`` appends the final state, whose event part is
+    the device-resident handle (no re-ingest between windows).
+
+    A fixed (non-adapting) standard kernel runs as ONE ``seir_mcmc_burst`` call when ``trace_fn`` is marked ``batched_ok``
+    (it is then called once on results whose fields carry a leading draw axis)."""
     from .gemlib.mcmc import DeviceEvents
 
     state = kernel.normalise_state(current_state)
     results = previous_kernel_results if previous_kernel_results is not None else kernel.bootstrap_results(state)
     base = as_seed_path(seed)
+    n, every = int(num_results), int(num_steps_between_results) + 1
     # position in the RNG streams: the seed's sweep index is the offset of this window, the kernel counts on from it
     sweep0 = (base.sweep + getattr(kernel, "sweep_counter", 0)) if first_sweep_index is None else int(first_sweep_index)
-    us, evs, traces = [], [], []
-    for i in range(int(num_results)):
-        state, results = kernel.one_step(state, results, seed=SeedPath(base.base, sweep0 + i))
-        us.append(state[0].clone())
-        evs.append(state[1].to_tensor() if isinstance(state[1], DeviceEvents) else state[1])
-        if trace_fn is not None:
-            traces.append(trace_fn(state, results))
-    kernel.sweep_counter = getattr(kernel, "sweep_counter", 0) + int(num_results)
-    draws = [torch.stack(us, dim=0), torch.stack(evs, dim=0)]
-    trace = _stack_tree(traces) if traces else None
-    if return_final_kernel_results:
-        return draws, trace, results
-    return draws, trace
+    plan = kernel.burst_plan(state) if (n > 0 and hasattr(kernel, "burst_plan") and (trace_fn is None or getattr(trace_fn, "batched_ok", False))) else None
+    out = kernel.burst(plan, results, n, every, SeedPath(base.base, sweep0), events_dtype) if plan is not None else None
+    if out is not None:
+        u_draws, ev_draws, stacked, state, results = out
+        draws = [u_draws, ev_draws]
+        trace = trace_fn(state, stacked) if trace_fn is not None else None
+    else:
+        us, evs, traces = [], [], []
+        for i in range(n * every):
+            state, results = kernel.one_step(state, results, seed=SeedPath(base.base, sweep0 + i))
+            if (i + 1) % every:
+                continue
+            us.append(state[0].clone())
+            if events_dtype is not None:
+                evs.append(state[1].to_tensor(events_dtype) if isinstance(state[1], DeviceEvents) else state[1])
+            if trace_fn is not None:
+                traces.append(trace_fn(state, results))
+        draws = [torch.stack(us, dim=0), torch.stack(evs, dim=0) if evs else None]
+        trace = _stack_tree(traces) if traces else None
+    kernel.sweep_counter = getattr(kernel, "sweep_counter", 0) + n * every
+    ret = (draws, trace) + ((results,) if return_final_kernel_results else ())
+    return ret + ((state,) if return_final_state else ())

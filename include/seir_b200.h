@@ -27,7 +27,7 @@
 extern "C" {
 #endif
 
-#define SEIR_B200_ABI_VERSION 8
+#define SEIR_B200_ABI_VERSION 9
 
 typedef enum seir_status {
   SEIR_OK = 0,
@@ -123,6 +123,12 @@ int seir_log_prob(seir_chains* chains, const double* d_events, const double* d_t
  * bit-identical to seir_log_prob on the same data. */
 int seir_log_prob_host(seir_chains* chains, const double* h_events, const double* h_theta, int theta_kind,
                        int parts, double* h_out);
+
+/* The same with the events as uint16 counts, h_events [B,M,T,3] u16 (the integer host contract): the reference keeps the
+ * integer-valued event tensor in float64 (model_spec.py:118-126, DTYPE :22) only because its graph has one dtype; a caller
+ * that holds counts ships a quarter of the bytes and nothing is narrowed on the host. */
+int seir_log_prob_host_u16(seir_chains* chains, const uint16_t* h_events, const double* h_theta, int theta_kind, int parts,
+                           double* h_out);
 
 /* Bytes the last seir_log_prob_host call moved host->device (events as shipped -- uint16 where the host pool
  * narrowed a chunk exactly, float64 otherwise -- plus theta).  Measurement accessor for bench.py's e2e figure. */
@@ -221,13 +227,23 @@ int seir_mcmc_sweep(seir_chains* chains, const seir_sweep_spec* spec, uint32_t s
  *   d_upd_trace [n][4][B][4][4] or NULL;  d_draws [n][B][P] or NULL (u after each sweep -- the `samples` of the burst).
  * d_u, d_tlp are in/out as in seir_mcmc_sweep.  Chains and traces are BIT-IDENTICAL to num_sweeps calls of
  * seir_mcmc_sweep; what changes is the schedule: the chain groups run on the library's internal streams for the whole
- * burst, staggered, so that the latency-bound discrete updates of one group overlap the HMC step of another. */
+ * burst, staggered, so that the latency-bound discrete updates of one group overlap the HMC step of another.  keep_every = e >= 1 keeps every e-th sweep only
+ * (tfp.mcmc.sample_chain's num_steps_between_results = e - 1; the Mcmc `thin` key of example_config.yaml:33, dead in the
+ * reference's run_mcmc, inference.py:455): result arrays then carry num_sweeps / e kept slots PLUS ONE scratch slot.
+ * d_events_u16 [slots][B][M][T][3] (or NULL) receives the events after every kept sweep as uint16 counts; a count beyond 65535
+ * saturates and sets *d_overflow. */
 int seir_mcmc_burst(seir_chains* chains, const seir_sweep_spec* spec, uint32_t sweep_index0, int32_t num_sweeps, double* d_u,
                     const double* d_step_size, const double* d_inv_mass, double* d_tlp, int32_t* d_hmc_accept, double* d_hmc_dbg,
-                    int32_t* d_upd_accept, double* d_upd_tlp, int32_t* d_upd_trace, double* d_draws, void* stream);
+                    int32_t* d_upd_accept, double* d_upd_tlp, int32_t* d_upd_trace, double* d_draws, int32_t keep_every,
+                    uint16_t* d_events_u16, int32_t* d_overflow, void* stream);
 
 /* Current events of every chain back in the reference layout: d_events [B,M,T,3] f64. */
 int seir_export_events(seir_chains* chains, double* d_events, void* stream);
+
+/* The same as uint16 counts, d_events [B,M,T,3] u16: compact storage of the `samples/seir` draws (inference.py:285-300 keeps
+ * every draw's event tensor as float64: 770 KB per chain and draw at the UK size; counts are small integers, so 2 bytes are
+ * exact).  A count beyond 65535 saturates and sets *d_overflow (int32 on the device, zeroed by the caller) to 1. */
+int seir_export_events_u16(seir_chains* chains, uint16_t* d_events, int32_t* d_overflow, void* stream);
 
 /* f4: CovidUK(...).sample(**par)["seir"] as used by predicted_incidence (posterior/predict.py:14-72; pinned to the CPU in
  * the reference, predict.py:112): chain-binomial forward simulation of `B` posterior samples over the model's num_steps

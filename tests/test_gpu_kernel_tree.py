@@ -25,7 +25,7 @@ def _problem(M=24, T=40, B=3, seed=2):
     return pb, model, so.unconstrain(pb["theta"])
 
 
-def _run(model, pb, u, kind, fused, n=6):
+def _run(model, pb, u, kind, fused, n=6, **kw):
     import torch
     from covid19uk_b200 import tfp_mcmc as tm
     from covid19uk_b200.gemlib.mcmc import GibbsKernel
@@ -45,7 +45,7 @@ def _run(model, pb, u, kind, fused, n=6):
                                            torch.full(u.shape, 0.5, dtype=torch.float64, device="cuda"))
         part0 = kf.make_hmc_slow_adapt_kernel(rv, hmc_kwargs, da_kwargs)
     kernel = GibbsKernel(model.joint_log_prob, [(0, part0), (1, kf.make_event_multiscan_gibbs_step(**ev_kwargs))], fused=fused)
-    draws, trace, fkr = tm.sample_chain(n, [u, pb["events"]], kernel, trace_fn=inf.trace_results_fn, seed=tm.SeedPath(11, 5))
+    draws, trace, fkr = tm.sample_chain(n, [u, pb["events"]], kernel, trace_fn=inf.trace_results_fn, seed=tm.SeedPath(11, 5), **kw)
     return draws, trace, fkr
 
 
@@ -70,6 +70,28 @@ def test_composed_tree_equals_fused_sweep_bitwise(kind):
     model.engine.close()
 
 
+def test_thinned_compact_burst_equals_the_sweep_by_sweep_loop():
+    """tfp.mcmc.sample_chain(num_steps_between_results = 2) with uint16 event draws: the fixed standard kernel runs as ONE
+    seir_mcmc_burst call (9 sweeps, 3 kept); the composed tree walks the same 9 sweeps one kernel at a time.  Draws, traces and
+    the final target log-prob agree bitwise; the kept draws are sweeps 3, 6, 9 of the unthinned run."""
+    import torch
+
+    pb, model, u = _problem()
+    kw = dict(num_steps_between_results=2, events_dtype=torch.uint16)
+    d_b, t_b, r_b = _run(model, pb, u, "fixed", fused=True, n=3, **kw)
+    d_l, t_l, r_l = _run(model, pb, u, "fixed", fused=False, n=3, **kw)
+    d_all, t_all, _ = _run(model, pb, u, "fixed", fused=True, n=9)
+    assert d_b[1].dtype == torch.uint16 and tuple(d_b[1].shape) == (3, 3, pb["M"], pb["T"], 3)
+    assert torch.equal(d_b[0], d_l[0]) and torch.equal(d_b[1].to(torch.int32), d_l[1].to(torch.int32))
+    assert torch.equal(d_b[0], d_all[0][2::3]) and torch.equal(d_b[1].to(torch.float64), d_all[1][2::3])
+    for key in t_b:
+        for name in t_b[key]:
+            assert torch.equal(t_b[key][name], t_l[key][name]), (key, name)
+            assert torch.equal(t_b[key][name], t_all[key][name][2::3]), (key, name)
+    assert torch.equal(r_b.target_log_prob, r_l.target_log_prob)
+    model.engine.close()
+
+
 def test_run_mcmc_streams_the_posterior_file(tmp_path):
     import torch
     from covid19uk_b200 import hdf5_min
@@ -91,6 +113,7 @@ def test_run_mcmc_streams_the_posterior_file(tmp_path):
     psi = f["samples/psi"][:]
     assert psi.shape == (n, 2) and np.all(psi > 0)  # constrained samples are written (param_bijector.inverse)
     ev = f["samples/seir"][:]
+    assert ev.dtype == np.uint16  # compact by default (Mcmc.store_events_as: uint16); float64 restores the reference's dtype
     assert ev.min() >= 0 and np.array_equal(ev, np.round(ev))
     # the last sample's log-prob recomputed from scratch equals the traced running value
     u_last = inf.ParamBijector.forward(torch.cat([torch.as_tensor(f[f"samples/{k}"][-1]).reshape(2, -1) for k in

@@ -94,8 +94,8 @@ def test_mirror_api_surface():
     assert list(inspect.signature(gm.UncalibratedOccultUpdate.__init__).parameters)[1:6] == [
         "target_log_prob_fn", "topology", "cumulative_event_offset", "nmax", "t_range"]
     assert gm.TransitionTopology(None, 0, 1).target == 0
-    assert list(inspect.signature(inf.run_mcmc).parameters) == ["joint_log_prob_fn", "current_state", "param_bijector",
-                                                                 "initial_conditions", "config", "output_file"]
+    assert list(inspect.signature(inf.run_mcmc).parameters)[:6] == ["joint_log_prob_fn", "current_state", "param_bijector",
+                                                                     "initial_conditions", "config", "output_file"]
     assert list(inspect.signature(gm.Posterior.__init__).parameters)[1:] == ["filename", "sample_dict", "results_dict", "num_samples"]
     with pytest.raises(TypeError):
         tm.engine_of(lambda u, e: 0.0)
@@ -163,3 +163,67 @@ def test_chain_partition_and_gloo_gather(tmp_path):
     assert got["out"]["move/S->E"]["proposed_delta"].shape == (4, total, 4, 2)
     assert torch.equal(got["out"]["move/S->E"]["proposed_delta"][0, :, 0, 0], ids.to(torch.int32))
     assert torch.equal(got["flat"]["u"][:, 0], ids)
+
+
+def _gloo_rank0_worker(rank, world, port, total, tmp):
+    """The per-burst exchange of the product path on CPU: every rank holds its contiguous share of `total` chains; rank 0 gathers
+    (uint16 event draws in bounded slices of the draw axis) and streams the ONE posterior file."""
+    import torch
+    import torch.distributed as dist
+
+    from covid19uk_b200.inference.distributed import gather_to_rank0, shard_chains
+    from covid19uk_b200.posterior import Posterior
+
+    dist.init_process_group("gloo", init_method=f"tcp://127.0.0.1:{port}", rank=rank, world_size=world)
+    off, cnt = shard_chains(total, world, rank)
+    ids = torch.arange(off, off + cnt)
+    n, M, T = 6, 3, 5
+
+    def window(w):
+        ev = (ids[None, :, None, None, None] * 100 + torch.arange(n)[:, None, None, None, None] + w * 1000 +
+              torch.arange(M * T * 3).reshape(1, 1, M, T, 3) % 7).to(torch.uint16)
+        return {"samples": {"psi": (ids[None, :] + 0.5 * w + torch.arange(n)[:, None]).to(torch.float64), "seir": ev},
+                "results": {"hmc": {"is_accepted": ((ids[None, :] + torch.arange(n)[:, None] + w) % 2 == 0)}}}
+
+    post = None
+    for w in range(2):
+        tree = gather_to_rank0(window(w), total, chain_dim=1) if w else gather_to_rank0(window(w), total, chain_dim=1)
+        if rank == 0:
+            if post is None:
+                post = Posterior(os.path.join(tmp, "post.h5"), tree["samples"], tree["results"], 2 * n)
+            post.write_samples(tree["samples"], first_dim_offset=w * n)
+            post.write_results(tree["results"], first_dim_offset=w * n)
+        else:
+            assert tree is None
+    # bounded slices: the same gather with a tiny budget per message
+    from covid19uk_b200.inference import distributed as dd
+    counts = [shard_chains(total, world, r)[1] for r in range(world)]
+    sl = dd._gather_to(window(1)["samples"]["seir"], 1, counts, 0, max_bytes=64)
+    if rank == 0:
+        post.close()
+        torch.save(sl, os.path.join(tmp, "sliced.pt"))
+    dist.barrier()
+    dist.destroy_process_group()
+
+
+def test_rank0_gather_streams_one_posterior_file(tmp_path):
+    import torch
+    import torch.multiprocessing as mp
+
+    from covid19uk_b200 import hdf5_min
+
+    total, world, port = 5, 2, 31000 + os.getpid() % 2000
+    mp.spawn(_gloo_rank0_worker, args=(world, port, total, str(tmp_path)), nprocs=world, join=True)
+    f = hdf5_min.File(os.path.join(tmp_path, "post.h5"), "r")
+    ids = np.arange(total)
+    n, M, T = 6, 3, 5
+    ev = f["samples/seir"][:]
+    assert ev.shape == (2 * n, total, M, T, 3) and ev.dtype == np.uint16
+    for w in range(2):
+        want = (ids[None, :, None, None, None] * 100 + np.arange(n)[:, None, None, None, None] + w * 1000 +
+                np.arange(M * T * 3).reshape(1, 1, M, T, 3) % 7).astype(np.uint16)
+        assert np.array_equal(ev[w * n:(w + 1) * n], want)
+        assert np.array_equal(f["samples/psi"][w * n:(w + 1) * n], ids[None, :] + 0.5 * w + np.arange(n)[:, None])
+        assert np.array_equal(f["results/hmc/is_accepted"][w * n:(w + 1) * n], (ids[None, :] + np.arange(n)[:, None] + w) % 2 == 0)
+    sl = torch.load(os.path.join(tmp_path, "sliced.pt"))
+    assert np.array_equal(sl.numpy(), ev[n:2 * n])
