@@ -139,7 +139,7 @@ __device__ __forceinline__ bool cell_fast(double yd, double rd, double X, double
 }
 
 template <bool GRAD, bool VAL>
-__device__ __noinline__ void cell_slow(double yd, double rd, double X, double e, double epsdt, double& term, double& gg_e) {
+__device__ __forceinline__ void cell_slow(double yd, double rd, double X, double e, double epsdt, double& term, double& gg_e) {
   const double x = fma(e, X, epsdt);
   const double em = expm1(-x);  // -(1-exp(-x)) = -p
   double t = -rd * x, gg = -rd;
@@ -149,4 +149,12 @@ __device__ __noinline__ void cell_slow(double yd, double rd, double X, double e,
   }
   if (VAL) term = t;
   if (GRAD) gg_e = gg * e;
+}
+
+// by-value form of the library path (a by-reference interface forces the caller's result arrays into local memory)
+template <bool VAL>
+__device__ __noinline__ double2 cell_slow_v(double yd, double rd, double X, double e, double epsdt) {
+  double t = 0.0, g = 0.0;
+  cell_slow<true, VAL>(yd, rd, X, e, epsdt, t, g);
+  return make_double2(t, g);
 }

@@ -26,6 +26,7 @@
 
 #define TJ_DAYS 4    // days per ring stage = one column-sum butterfly group
 #define TJ_NACC 8
+#define TJ_NTHR 384  // 12 warps: the days of a 12-day packed stage, one each
 #define HALF_LOG_2PI 0.9189385332046727
 
 struct traj_args {
@@ -100,17 +101,19 @@ __device__ __forceinline__ void tj_block_sum(double (&v)[TJ_NACC], double* tile,
 struct tj_smem {  // carved from dynamic shared memory after the ring
   double *u, *p, *g, *im;                    // [P]
   double *pa, *gam, *yir, *rir, *col, *cs;   // [Tp]
-  double* colw;                              // [NCW][Tp + 4]
+  double* rowp;                              // [NCW][Mp] row-sum partials of the warps (one evaluation)
+  double* pm;                                // [Mp] per-metapopulation rate factors of the evaluation
   double* tile;                              // [NCW][TJ_DAYS][32] column-sum tiles of the warps
   double (*red)[TJ_NACC];                    // [NCW]
   double* sc;                                // [16]
 };
 
-static size_t tj_state_bytes(int nthr, int T, int P) {  // everything after the ring
+static size_t tj_state_bytes(int nthr, int T, int Mp, int P) {  // everything after the ring
   const int Tp = (T + 3) / 4 * 4;
   size_t b = sizeof(double) * (4 * (size_t)((P + 1) / 2 * 2));  // u p g im
   b += sizeof(double) * (6 * (size_t)Tp);                       // pa gam yir rir col cs
-  b += sizeof(double) * (size_t)(nthr / 32) * (Tp + 4);         // colw
+  b += sizeof(double) * (size_t)(nthr / 32) * Mp;               // rowp
+  b += sizeof(double) * (size_t)Mp;                             // pm
   b += sizeof(double) * (size_t)(nthr / 32) * TJ_DAYS * 32;     // tile
   b += sizeof(double) * (size_t)(nthr / 32) * TJ_NACC;          // red
   b += sizeof(double) * 16;                                     // sc
@@ -125,175 +128,82 @@ struct tj_cell_ctx {
   unsigned long long magic;  // 0x4330000000000000 in a register pair (uint_to_double_wide)
   const double2* tab;
   const double* W;
-  const double* pa;        // shared: dt exp(alpha path) per day
   unsigned char* scratch;  // this CTA's packed cells
   int* ovf;                // shared flag: a cell does not fit the packed format
   int src_stride;          // source stages: ints between the yse / S / I blocks (= days per source stage * Mp)
 };
 
-// Where a 4-day group lives inside a ring stage.  Packed stage: [days][Mp] x 16 B.  Source stage: four blocks
+// Where one day lives inside a ring stage.  Packed stage: [days][Mp] x 16 B.  Source stage: four blocks
 // yse | S | I (int32) | Bc (f64), each [days per source stage][Mp].
-struct tj_gptr {
-  const unsigned char* pk;  // packed: first cell of the group's first day
-  const int* sy;            // source: yse of the group's first day (S, I at + src_stride, + 2 src_stride)
-  const double* sb;         // source: Bc of the group's first day
+struct tj_dptr {
+  const unsigned char* pk;  // packed: first cell of the day
+  const int* sy;            // source: yse of the day (S, I at + src_stride, + 2 src_stride)
+  const double* sb;         // source: Bc of the day
 };
 
-// One ring stage = TJ_DAYS days of the thread's metapopulations.  All loads first, then the cells' fast paths with no
-// branch in between (the compiler interleaves their dependent chains), one branch for the rare out-of-range cells, then the
-// accumulations in a fixed order.  PACKED: the stage holds 16-byte packed cells; otherwise the four cache arrays
-// (WRITE: evaluation 0 also re-packs every cell into the scratch).  FULL: all TJ_DAYS days exist and every metapopulation
-// slot of the thread is real (Mp == NTHR * MPT): no predicates.
-template <int NTHR, int MPT, bool PACKED, bool VAL, bool WRITE, bool FULL>
-__device__ __forceinline__ bool tj_group(const tj_cell_ctx& cx, const ll_coefs& K, const tj_gptr gp, int grp, int days,
-                                         const bool (&act)[MPT], const double (&pm_m)[MPT], double& val, double& psig,
-                                         double (&row)[MPT], double (&colv)[TJ_DAYS]) {
-  const int tid = threadIdx.x, Mp = cx.Mp;
-  double yd[TJ_DAYS][MPT], rd[TJ_DAYS][MPT], X[TJ_DAYS][MPT], bw[TJ_DAYS][MPT], ee[TJ_DAYS][MPT];
-  const int t0 = grp * TJ_DAYS;
+// Thread <-> cell mapping of the cell phase: a WARP owns a day of the stage, its lanes own the metapopulations
+// m = lane + 32 k (k < KM = Mp / 32).  The per-day column sum is then ONE warp reduction per day (it was a cross-warp
+// reduction per 4-day group when threads owned metapopulations), the row sums are per-thread registers reduced across the
+// warps once per evaluation, and a lane has KM independent cells in flight.
+//
+// CNT cells of one day (k = k0 .. k0 + CNT - 1).  All loads first, then the fast paths with no branch in between (the compiler
+// interleaves the dependent chains), and the caller takes ONE branch for the rare cells outside the fast range.
+// PACKED: the stage holds 16-byte packed cells; otherwise the four cache arrays (WRITE: evaluation 0 also re-packs every cell
+// into the scratch).
+template <int CNT, bool PACKED, bool VAL, bool WRITE>
+__device__ __forceinline__ bool tj_cells(const tj_cell_ctx& cx, const ll_coefs& K, const tj_dptr dp, int t, int m0, double pat, double wt,
+                                         const double* pm, double (&term)[CNT], double (&gge)[CNT], double (&X)[CNT], double (&bw)[CNT]) {
+  double yd[CNT], rd[CNT];
 #pragma unroll
-  for (int j = 0; j < TJ_DAYS; ++j) {
-    const bool on = FULL || j < days;
-    const int t = t0 + (on ? j : 0);
-    const double pat = cx.pa[t];
-#pragma unroll
-    for (int q = 0; q < MPT; ++q) {
-      const int m = tid + q * NTHR;
-      const bool a = FULL || (on && act[q]);
-      double Id;
-      if (PACKED) {
+  for (int j = 0; j < CNT; ++j) {
+    const int m = m0 + 32 * j;
+    double Id;
+    if (PACKED) {
+      const uint4 w = *reinterpret_cast<const uint4*>(dp.pk + (size_t)m * 16);
+      Id = uint_to_double_wide(w.x & 0x00ffffffu, cx.magic);
+      rd[j] = uint_to_double_wide(w.y & 0x00ffffffu, cx.magic);
+      yd[j] = uint_to_double_wide(__byte_perm(__byte_perm(w.x, 0u, 0x4443), w.y, 0x3270), cx.magic);
+      bw[j] = __hiloint2double((int)w.w, (int)w.z);
+    } else {
+      const int y = dp.sy[m], S = dp.sy[cx.src_stride + m], I = dp.sy[2 * cx.src_stride + m];
+      const double bc = dp.sb[m];
+      const int r = S - y;
+      yd[j] = int_to_double_magic(y);
+      rd[j] = int_to_double_magic(r);
+      Id = int_to_double_magic(I);
+      bw[j] = wt * bc;
+      if (WRITE) {  // re-pack the cell for evaluations 1..L
+        if (((unsigned)y > 0xffffu) | ((unsigned)I > 0x00ffffffu) | ((unsigned)r > 0x00ffffffu)) *cx.ovf = 1;
         uint4 w;
-        if (FULL) {
-          w = *reinterpret_cast<const uint4*>(gp.pk + ((size_t)j * Mp + m) * 16);
-        } else {
-          w = make_uint4(0u, 0u, 0u, 0u);
-          if (a) w = *reinterpret_cast<const uint4*>(gp.pk + ((size_t)j * Mp + m) * 16);
-        }
-        Id = uint_to_double_wide(w.x & 0x00ffffffu, cx.magic);
-        rd[j][q] = uint_to_double_wide(w.y & 0x00ffffffu, cx.magic);
-        yd[j][q] = uint_to_double_wide(__byte_perm(__byte_perm(w.x, 0u, 0x4443), w.y, 0x3270), cx.magic);
-        bw[j][q] = __hiloint2double((int)w.w, (int)w.z);
-      } else {
-        const int* sy = gp.sy + j * Mp;
-        int y = 0, S = 0, I = 0;
-        double bc = 0.0;
-        if (a) {
-          y = sy[m];
-          S = sy[cx.src_stride + m];
-          I = sy[2 * cx.src_stride + m];
-          bc = gp.sb[j * Mp + m];
-        }
-        const int r = S - y;
-        yd[j][q] = int_to_double_magic(y);
-        rd[j][q] = int_to_double_magic(r);
-        Id = int_to_double_magic(I);
-        bw[j][q] = cx.W[t] * bc;
-        if (WRITE && a) {  // re-pack the cell for evaluations 1..L
-          if (((unsigned)y > 0xffffu) | ((unsigned)I > 0x00ffffffu) | ((unsigned)r > 0x00ffffffu)) *cx.ovf = 1;
-          uint4 w;
-          w.x = ((unsigned)I & 0x00ffffffu) | ((unsigned)y << 24);
-          w.y = ((unsigned)r & 0x00ffffffu) | (((unsigned)y >> 8) << 24);
-          w.z = (unsigned)__double2loint(bw[j][q]);
-          w.w = (unsigned)__double2hiint(bw[j][q]);
-          *reinterpret_cast<uint4*>(cx.scratch + ((size_t)t * Mp + m) * 16) = w;
-        }
+        w.x = ((unsigned)I & 0x00ffffffu) | ((unsigned)y << 24);
+        w.y = ((unsigned)r & 0x00ffffffu) | (((unsigned)y >> 8) << 24);
+        w.z = (unsigned)__double2loint(bw[j]);
+        w.w = (unsigned)__double2hiint(bw[j]);
+        *reinterpret_cast<uint4*>(cx.scratch + ((size_t)t * cx.Mp + m) * 16) = w;
       }
-      X[j][q] = fma(cx.psi, bw[j][q], Id);
-      ee[j][q] = a ? pat * pm_m[q] : 0.0;  // (inactive cells: x = eps dt, y = r = 0 => term 0, gradient 0)
     }
+    X[j] = fma(cx.psi, bw[j], Id);
   }
-  double term[TJ_DAYS][MPT], gge[TJ_DAYS][MPT];
   bool all_fast = true;
 #pragma unroll
-  for (int j = 0; j < TJ_DAYS; ++j)
-#pragma unroll
-    for (int q = 0; q < MPT; ++q) {
-      term[j][q] = 0.0;
-      gge[j][q] = 0.0;
-      all_fast &= cell_fast<true, VAL>(yd[j][q], rd[j][q], X[j][q], ee[j][q], cx.epsdt, cx.tab, K, term[j][q], gge[j][q]);
-    }
-  if (__builtin_expect(!all_fast, 0)) return false;  // (rare: the caller re-does the group on the generic path)
-#pragma unroll
-  for (int j = 0; j < TJ_DAYS; ++j) {
-    colv[j] = 0.0;
-#pragma unroll
-    for (int q = 0; q < MPT; ++q) {
-      if (VAL) val += term[j][q];
-      const double h = gge[j][q] * X[j][q];
-      row[q] += h;
-      psig = fma(gge[j][q], bw[j][q], psig);
-      colv[j] += h;
-    }
+  for (int j = 0; j < CNT; ++j) {
+    term[j] = 0.0;
+    gge[j] = 0.0;
+    all_fast &= cell_fast<true, VAL>(yd[j], rd[j], X[j], pat * pm[j], cx.epsdt, cx.tab, K, term[j], gge[j]);
   }
-  return true;
-}
-
-// Everything off the main path -- partial groups, padded metapopulation slots, chains that do not fit the packed format, groups
-// holding a cell outside the fast range -- goes through ONE out-of-line function built on cell_eval (branch per cell).  It
-// takes and returns plain values (a by-reference interface would force the hot loop's accumulators into local memory).
-template <int MPT>
-struct tj_out {
-  double val, psig, row[MPT], colv[TJ_DAYS];
-};
-template <int MPT>
-struct tj_pm {
-  double v[MPT];
-  int act;  // bit q: metapopulation slot q of the thread is real
-};
-
-template <int NTHR, int MPT>
-__device__ __noinline__ tj_out<MPT> tj_group_generic(const tj_cell_ctx cx, const ll_coefs K, const tj_gptr gp, int grp, int days,
-                                                     const tj_pm<MPT> pm, int packed, int want_val, int write) {
-  const int tid = threadIdx.x, Mp = cx.Mp;
-  tj_out<MPT> o;
-  o.val = 0.0;
-  o.psig = 0.0;
-  for (int q = 0; q < MPT; ++q) o.row[q] = 0.0;
-  for (int j = 0; j < TJ_DAYS; ++j) {
-    o.colv[j] = 0.0;
-    if (j >= days) continue;
-    const int t = grp * TJ_DAYS + j;
-    const double pat = cx.pa[t];
-    for (int q = 0; q < MPT; ++q) {
-      if (!((pm.act >> q) & 1)) continue;
-      const int m = tid + q * NTHR;
-      double yd, rd, Id, bw;
-      if (packed) {
-        const uint4 w = *reinterpret_cast<const uint4*>(gp.pk + ((size_t)j * Mp + m) * 16);
-        Id = uint_to_double_magic(w.x & 0x00ffffffu);
-        rd = uint_to_double_magic(w.y & 0x00ffffffu);
-        yd = uint_to_double_magic(__byte_perm(__byte_perm(w.x, 0u, 0x4443), w.y, 0x3270));
-        bw = __hiloint2double((int)w.w, (int)w.z);
-      } else {
-        const int* sy = gp.sy + j * Mp;
-        const int y = sy[m], S = sy[cx.src_stride + m], I = sy[2 * cx.src_stride + m];
-        const double bc = gp.sb[j * Mp + m];
-        const int r = S - y;
-        yd = int_to_double_magic(y);
-        rd = int_to_double_magic(r);
-        Id = int_to_double_magic(I);
-        bw = cx.W[t] * bc;
-        if (write) {
-          if (((unsigned)y > 0xffffu) | ((unsigned)I > 0x00ffffffu) | ((unsigned)r > 0x00ffffffu)) *cx.ovf = 1;
-          uint4 w;
-          w.x = ((unsigned)I & 0x00ffffffu) | ((unsigned)y << 24);
-          w.y = ((unsigned)r & 0x00ffffffu) | (((unsigned)y >> 8) << 24);
-          w.z = (unsigned)__double2loint(bw);
-          w.w = (unsigned)__double2hiint(bw);
-          *reinterpret_cast<uint4*>(cx.scratch + ((size_t)t * Mp + m) * 16) = w;
-        }
+  if (__builtin_expect(!all_fast, 0)) {  // (rare) repair the cells outside the fast range on the library path
+#pragma unroll
+    for (int j = 0; j < CNT; ++j) {
+      const double e = pat * pm[j], x = fma(e, X[j], cx.epsdt);
+      const int hi = __double2hiint(x);
+      if (!((unsigned)(hi - CELL_HI_LO) < (unsigned)(CELL_HI_UP - CELL_HI_LO))) {
+        const double2 r = cell_slow_v<VAL>(yd[j], rd[j], X[j], e, cx.epsdt);
+        term[j] = r.x;
+        gge[j] = r.y;
       }
-      const double X = fma(cx.psi, bw, Id);
-      double gg_e = 0.0;
-      if (want_val) cell_eval<true, true>(yd, rd, X, pat * pm.v[q], cx.epsdt, cx.tab, K, o.val, gg_e);
-      else cell_eval<true, false>(yd, rd, X, pat * pm.v[q], cx.epsdt, cx.tab, K, o.val, gg_e);
-      const double h = gg_e * X;
-      o.row[q] += h;
-      o.psig = fma(gg_e, bw, o.psig);
-      o.colv[j] += h;
     }
   }
-  return o;
+  return all_fast;
 }
 
 // Per-day column sums of a group over the 32 metapopulations of a warp, through a per-warp shared-memory tile instead of
@@ -371,9 +281,10 @@ __device__ __forceinline__ void tj_block_sum(double (&v)[TJ_NACC], double* tile,
   tj_bar(NTHR);  // (red[] may be rewritten)
 }
 
-template <int NTHR, int MPT>
-__global__ void __launch_bounds__(NTHR, 1) seir_hmc_traj_kernel(const traj_args A, const ll_coefs K) {
-  constexpr int NCW = NTHR / 32;
+template <int KM>
+__global__ void __launch_bounds__(TJ_NTHR, 1) seir_hmc_traj_kernel(const traj_args A, const ll_coefs K) {
+  constexpr int NTHR = TJ_NTHR, NCW = NTHR / 32;
+  constexpr int MPT = (32 * KM + NTHR - 1) / NTHR;  // metapopulations per thread in the O(P) phases (thread <-> m = tid + q NTHR)
   extern __shared__ __align__(128) unsigned char smraw[];
   __shared__ tj_ring ring;
   __shared__ double2 tab[128];
@@ -391,7 +302,8 @@ __global__ void __launch_bounds__(NTHR, 1) seir_hmc_traj_kernel(const traj_args 
     double* q = reinterpret_cast<double*>(smraw + 2 * stage_bytes);
     sm.u = q; q += P2; sm.p = q; q += P2; sm.g = q; q += P2; sm.im = q; q += P2;
     sm.pa = q; q += Tp; sm.gam = q; q += Tp; sm.yir = q; q += Tp; sm.rir = q; q += Tp; sm.col = q; q += Tp; sm.cs = q; q += Tp;
-    sm.colw = q; q += (size_t)NCW * (Tp + 4);
+    sm.rowp = q; q += (size_t)NCW * Mp;
+    sm.pm = q; q += Mp;
     sm.tile = q; q += (size_t)NCW * TJ_DAYS * 32;
     sm.red = reinterpret_cast<double (*)[TJ_NACC]>(q); q += (size_t)NCW * TJ_NACC;
     sm.sc = q;
@@ -468,9 +380,11 @@ __global__ void __launch_bounds__(NTHR, 1) seir_hmc_traj_kernel(const traj_args 
     rN_m[q] = act[q] ? A.rN[m] : 0.0;  // (0 in the padding)
   }
   const double epsdt = A.eps * A.dt;
-  const bool full_m = Mp == NTHR * MPT;
   const unsigned long long magic = (unsigned long long)__double_as_longlong(K.k[13]);  // 2^52: bit pattern 0x4330000000000000
   unsigned nglob = 0;  // stages consumed over the CTA's life
+#ifdef SEIR_TRAJ_DEBUG
+  long long twait = 0;
+#endif
   for (int k = 0; k < nmine; ++k) {
     const int kchain = k;
     (void)kchain;
@@ -586,6 +500,7 @@ __global__ void __launch_bounds__(NTHR, 1) seir_hmc_traj_kernel(const traj_args 
       for (int q = 0; q < MPT; ++q) {
         const int m = tid + q * NTHR;
         pm_m[q] = (m < M) ? exp(beta * la_m[q] + sigma * sp[m]) * rN_m[q] : 0.0;
+        if (act[q]) sm.pm[m] = pm_m[q];  // for the cell phase, where lanes own metapopulations lane + 32 k
       }
       // per day, two tasks on separate threads (tail warps first: every thread also has its pm factors to do):
       //   task 0  exp(alpha path) dt
@@ -645,19 +560,16 @@ __global__ void __launch_bounds__(NTHR, 1) seir_hmc_traj_kernel(const traj_args 
       TJT(8 + i * 8 + 2);
 
       // ---------------- B: the cells ----------------
-      double val = 0.0, psig = 0.0, row[MPT];
+      // warp <-> day of the stage, lane <-> metapopulations m = lane + 32 k: KM cells of a day per lane
+      double val = 0.0, psig = 0.0;
+      double pmr[KM], rowr[KM];  // this lane's rate factors and row-sum partials (over the days its warp owns)
 #pragma unroll
-      for (int q = 0; q < MPT; ++q) row[q] = 0.0;
-      const int cstride = Tp + 4;
-      tj_cell_ctx cx;
-      tj_pm<MPT> pmv;
-      pmv.act = 0;
-#pragma unroll
-      for (int q = 0; q < MPT; ++q) {
-        pmv.v[q] = pm_m[q];
-        pmv.act |= act[q] ? (1 << q) : 0;
+      for (int kk = 0; kk < KM; ++kk) {
+        pmr[kk] = sm.pm[lane + 32 * kk];  // (staged in phase A, published by its last barrier)
+        rowr[kk] = 0.0;
       }
-      cx.T = T; cx.Mp = Mp; cx.psi = psi; cx.epsdt = epsdt; cx.tab = tab; cx.W = A.W; cx.pa = sm.pa; cx.scratch = scratch;
+      tj_cell_ctx cx;
+      cx.T = T; cx.Mp = Mp; cx.psi = psi; cx.epsdt = epsdt; cx.tab = tab; cx.W = A.W; cx.scratch = scratch;
       cx.ovf = &s_ovf;
       cx.magic = magic;
       cx.src_stride = sc.sd * Mp;
@@ -665,46 +577,73 @@ __global__ void __launch_bounds__(NTHR, 1) seir_hmc_traj_kernel(const traj_args 
       const int nstages = src_eval ? sc.ns0 : sc.nsp, sdays = src_eval ? sc.sd : sc.pd;
       for (int s = 0; s < nstages; ++s, ++nglob) {
         const int buf = (int)(nglob & 1u);
+#ifdef SEIR_TRAJ_DEBUG
+        const long long tw0 = clock64();
+#endif
         mbar_wait(&ring.full[buf], (nglob >> 1) & 1u);
+#ifdef SEIR_TRAJ_DEBUG
+        if (s == 0) twait = 0;
+        twait += clock64() - tw0;
+        if (blockIdx.x == 0 && tid == 0 && kchain == 0 && s == nstages - 1) g_tj_dbg[8 + i * 8 + 7] = twait;
+#endif
         const unsigned char* stage = smraw + (size_t)buf * stage_bytes;
         const int d0 = s * sdays, nd = min(sdays, T - d0);
-        for (int gd = 0; gd < nd; gd += TJ_DAYS) {  // the 4-day groups of the stage
-          const int grp = (d0 + gd) / TJ_DAYS;  // (stage days are multiples of TJ_DAYS: groups never straddle stages)
-          tj_gptr gp;
-          gp.pk = stage + (size_t)gd * Mp * 16;
-          gp.sy = reinterpret_cast<const int*>(stage) + (size_t)gd * Mp;
-          gp.sb = reinterpret_cast<const double*>(stage + (size_t)3 * sc.sd * Mp * 4) + (size_t)gd * Mp;
-          double colv[TJ_DAYS];
-          const int days = min(TJ_DAYS, nd - gd);
-          const bool full = full_m && days == TJ_DAYS;
-          bool done = false;
-          double v1 = val, p1 = psig, r1[MPT];
+        for (int d = warp; d < nd; d += NCW) {  // the days of the stage this warp owns
+          const int t = d0 + d;
+          const double pat = sm.pa[t], wt = A.W[t];
+          tj_dptr dp;
+          dp.pk = stage + (size_t)d * Mp * 16;
+          dp.sy = reinterpret_cast<const int*>(stage) + (size_t)d * Mp;
+          dp.sb = reinterpret_cast<const double*>(stage + (size_t)3 * sc.sd * Mp * 4) + (size_t)d * Mp;
+          double colacc = 0.0;
 #pragma unroll
-          for (int q = 0; q < MPT; ++q) r1[q] = row[q];
-          if (full) {  // the main path: whole groups, every slot real
-            if (!src_eval) {
-              if (want_val) done = tj_group<NTHR, MPT, true, true, false, true>(cx, K, gp, grp, days, act, pm_m, v1, p1, r1, colv);
-              else done = tj_group<NTHR, MPT, true, false, false, true>(cx, K, gp, grp, days, act, pm_m, v1, p1, r1, colv);
-            } else if (i == 0) {
-              done = tj_group<NTHR, MPT, false, true, true, true>(cx, K, gp, grp, days, act, pm_m, v1, p1, r1, colv);
+          for (int k0 = 0; k0 < KM; k0 += 4) {
+            constexpr int dummy = 0;
+            (void)dummy;
+            if (k0 + 4 <= KM) {
+              double term[4], gge[4], X[4], bw[4];
+              const double pm4[4] = {pmr[k0], pmr[k0 + 1 < KM ? k0 + 1 : k0], pmr[k0 + 2 < KM ? k0 + 2 : k0], pmr[k0 + 3 < KM ? k0 + 3 : k0]};
+              if (!src_eval) {
+                if (want_val) tj_cells<4, true, true, false>(cx, K, dp, t, lane + 32 * k0, pat, wt, pm4, term, gge, X, bw);
+                else tj_cells<4, true, false, false>(cx, K, dp, t, lane + 32 * k0, pat, wt, pm4, term, gge, X, bw);
+              } else if (i == 0) {
+                tj_cells<4, false, true, true>(cx, K, dp, t, lane + 32 * k0, pat, wt, pm4, term, gge, X, bw);
+              } else {
+                if (want_val) tj_cells<4, false, true, false>(cx, K, dp, t, lane + 32 * k0, pat, wt, pm4, term, gge, X, bw);
+                else tj_cells<4, false, false, false>(cx, K, dp, t, lane + 32 * k0, pat, wt, pm4, term, gge, X, bw);
+              }
+#pragma unroll
+              for (int j = 0; j < 4; ++j) {
+                val += term[j];
+                const double h = gge[j] * X[j];
+                if (k0 + j < KM) rowr[k0 + j] += h;
+                psig = fma(gge[j], bw[j], psig);
+                colacc += h;
+              }
+            } else {  // KM is even: a tail of 2 cells
+              double term[2], gge[2], X[2], bw[2];
+              const double pm2[2] = {pmr[k0], pmr[k0 + 1 < KM ? k0 + 1 : k0]};
+              if (!src_eval) {
+                if (want_val) tj_cells<2, true, true, false>(cx, K, dp, t, lane + 32 * k0, pat, wt, pm2, term, gge, X, bw);
+                else tj_cells<2, true, false, false>(cx, K, dp, t, lane + 32 * k0, pat, wt, pm2, term, gge, X, bw);
+              } else if (i == 0) {
+                tj_cells<2, false, true, true>(cx, K, dp, t, lane + 32 * k0, pat, wt, pm2, term, gge, X, bw);
+              } else {
+                if (want_val) tj_cells<2, false, true, false>(cx, K, dp, t, lane + 32 * k0, pat, wt, pm2, term, gge, X, bw);
+                else tj_cells<2, false, false, false>(cx, K, dp, t, lane + 32 * k0, pat, wt, pm2, term, gge, X, bw);
+              }
+#pragma unroll
+              for (int j = 0; j < 2; ++j) {
+                val += term[j];
+                const double h = gge[j] * X[j];
+                if (k0 + j < KM) rowr[k0 + j] += h;
+                psig = fma(gge[j], bw[j], psig);
+                colacc += h;
+              }
             }
           }
-          if (done) {
-            val = v1;
-            psig = p1;
-#pragma unroll
-            for (int q = 0; q < MPT; ++q) row[q] = r1[q];
-          } else {  // (accumulators untouched by a group that bailed out: the generic function adds its own sums, same order)
-            const tj_out<MPT> o = tj_group_generic<NTHR, MPT>(cx, K, gp, grp, days, pmv, src_eval ? 0 : 1, want_val ? 1 : 0, i == 0 ? 1 : 0);
-            val += o.val;
-            psig += o.psig;
-#pragma unroll
-            for (int q = 0; q < MPT; ++q) row[q] += o.row[q];
-#pragma unroll
-            for (int j = 0; j < TJ_DAYS; ++j) colv[j] = o.colv[j];
-          }
-          const double tot = tj_col_reduce(colv, sm.tile + warp * (TJ_DAYS * 32));
-          if ((lane & 7) == 0 && (lane >> 3) < days) sm.colw[warp * cstride + grp * TJ_DAYS + (lane >> 3)] = tot;
+          colacc = warp_sum(colacc);  // the day's column sum: this warp owns the whole day
+          if (lane == 0) sm.col[t] = colacc;
         }
         // release the stage; the warp that does so last refills the ring
         if (i == 0) {  // (this warp's scratch writes: visible to the async proxy before any later bulk copy can be issued)
@@ -715,13 +654,24 @@ __global__ void __launch_bounds__(NTHR, 1) seir_hmc_traj_kernel(const traj_args 
         if (lane == 0) {
           __threadfence_block();
           if (atomicAdd(&ring.cnt[buf], 1) == NCW - 1) {
-            ring.cnt[buf] = 0;
+            atomicExch(&ring.cnt[buf], 0);
             __threadfence_block();
             *reinterpret_cast<volatile int*>(&ring.consumed) = ring.consumed + 1;
             pump();
             __threadfence_block();
           }
         }
+      }
+      // row sums: every warp's partials -> shared memory -> thread <-> metapopulation adds the warps in order
+#pragma unroll
+      for (int kk = 0; kk < KM; ++kk) sm.rowp[warp * Mp + lane + 32 * kk] = rowr[kk];
+      tj_bar(NTHR);
+      double row[MPT];
+#pragma unroll
+      for (int q = 0; q < MPT; ++q) {
+        row[q] = 0.0;
+        if (act[q])
+          for (int w = 0; w < NCW; ++w) row[q] += sm.rowp[w * Mp + tid + q * NTHR];
       }
 
       TJT(8 + i * 8 + 3);
@@ -737,7 +687,7 @@ __global__ void __launch_bounds__(NTHR, 1) seir_hmc_traj_kernel(const traj_args 
           sm.g[6 + (T - 1) + m] = sigma * row[q] - carq[q];
         }
       }
-      tj_block_sum<NTHR>(acc, sm.tile, sm.red);  // (its barriers also publish colw[]; s_ovf is settled)
+      tj_block_sum<NTHR>(acc, sm.tile, sm.red);  // (its barriers also publish col[]; s_ovf is settled)
       TJT(8 + i * 8 + 4);
       if (i == 0) {
         packed = !s_ovf;
@@ -747,16 +697,6 @@ __global__ void __launch_bounds__(NTHR, 1) seir_hmc_traj_kernel(const traj_args 
           pump();
         }
       }
-      for (int tt = tid; tt < ((Tp * 4 + 31) & ~31); tt += NTHR) {  // 4 threads per day (whole warps): a quarter of the warp partials each
-        const int t = tt >> 2, part = tt & 3;
-        double s = 0.0;
-        if (t < T)
-          for (int w = part; w < NCW; w += 4) s += sm.colw[w * cstride + t];
-        s += __shfl_xor_sync(0xffffffffu, s, 1);
-        s += __shfl_xor_sync(0xffffffffu, s, 2);
-        if (part == 0 && t < Tp) sm.col[t] = s;
-      }
-      tj_bar(NTHR);
       if (warp == 0) {  // suffix sums of the per-day column sums (lanes own consecutive chunks of days; lane 31 first)
         const int chunk = (T + 31) / 32;
         const int c0 = min(T, lane * chunk), c1 = min(T, c0 + chunk);
@@ -856,17 +796,20 @@ typedef void (*traj_fn)(const traj_args, const ll_coefs);
 
 struct traj_cfg {
   traj_fn fn;
-  int nthr, mpt;
+  int nthr, km;
 };
 
 static bool traj_pick(int Mp, traj_cfg* k) {
-  if (Mp <= 128) *k = traj_cfg{seir_hmc_traj_kernel<128, 1>, 128, 1};
-  else if (Mp <= 256) *k = traj_cfg{seir_hmc_traj_kernel<256, 1>, 256, 1};
-  else if (Mp <= 384) *k = traj_cfg{seir_hmc_traj_kernel<384, 1>, 384, 1};
-  else if (Mp <= 512) *k = traj_cfg{seir_hmc_traj_kernel<512, 1>, 512, 1};
-  else if (Mp <= 1024) *k = traj_cfg{seir_hmc_traj_kernel<512, 2>, 512, 2};
-  else return false;
-  return true;
+  if (Mp % 32) return false;
+  switch (Mp / 32) {  // KM: metapopulations per lane in the cell phase
+    case 2: *k = traj_cfg{seir_hmc_traj_kernel<2>, TJ_NTHR, 2}; return true;
+    case 4: *k = traj_cfg{seir_hmc_traj_kernel<4>, TJ_NTHR, 4}; return true;
+    case 6: *k = traj_cfg{seir_hmc_traj_kernel<6>, TJ_NTHR, 6}; return true;
+    case 8: *k = traj_cfg{seir_hmc_traj_kernel<8>, TJ_NTHR, 8}; return true;
+    case 12: *k = traj_cfg{seir_hmc_traj_kernel<12>, TJ_NTHR, 12}; return true;
+    case 16: *k = traj_cfg{seir_hmc_traj_kernel<16>, TJ_NTHR, 16}; return true;
+    default: return false;
+  }
 }
 
 // Whether the persistent trajectory kernel applies to this chain set (shared memory for two ring stages of at least one
@@ -888,7 +831,7 @@ static bool traj_plan(const seir_chains* c, traj_cfg* k, traj_shape* sh) {
   if (!traj_pick(m->Mp, k)) return false;
   int dev_smem = 0;
   if (cudaDeviceGetAttribute(&dev_smem, cudaDevAttrMaxSharedMemoryPerBlockOptin, m->device) != cudaSuccess) return false;
-  const size_t state = tj_state_bytes(k->nthr, m->T, m->P);
+  const size_t state = tj_state_bytes(k->nthr, m->T, m->Mp, m->P);
   const size_t budget = (size_t)dev_smem - 4096;  // (static shared memory of the kernel: ring bookkeeping, log table)
   if (state + 2 * (size_t)TJ_DAYS * m->Mp * 20 > budget) return false;
   const size_t per_stage = (budget - state) / 2;
@@ -937,7 +880,7 @@ int seir_launch_hmc_traj(seir_chains* c, double* d_u, const double* d_log_u, con
     c->bytes += (int64_t)(per_cta * (size_t)m->sms);
   }
   static size_t attr_dev[SEIR_MAX_DEVICES][8] = {{0}};
-  size_t& attr = attr_dev[m->device % SEIR_MAX_DEVICES][(k.nthr / 128 - 1) * 2 + (k.mpt - 1)];
+  size_t& attr = attr_dev[m->device % SEIR_MAX_DEVICES][k.km / 2 - 1];
   const size_t smem = sh.smem;
   if (attr != smem) {
     SEIR_CUDA(cudaFuncSetAttribute(k.fn, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));

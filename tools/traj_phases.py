@@ -21,4 +21,5 @@ names = ["A1 scan/scalars/CAR", "A2 per-day/pm", "B cells", "C block sum", "C co
 for i in range(L + 2):
     s = h[8 + i * 8: 8 + i * 8 + 7]
     d = np.diff(s)
+    print(f"[feed wait of warp 0: {int(h[8 + i * 8 + 7])}] ", end="")
     print(f"eval {i:2d}: start {s[0]-t0:8d}  " + "  ".join(f"{n} {int(x)}" for n, x in zip(names, d) if x > 0 and x < 10**9))
