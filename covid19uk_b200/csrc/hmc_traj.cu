@@ -27,6 +27,11 @@
 #define TJ_DAYS 4    // days per ring stage = one column-sum butterfly group
 #define TJ_NACC 8
 #define TJ_NTHR 384  // 12 warps: the days of a 12-day packed stage, one each
+#ifdef TJ_REGS  // experiments: cap the registers so that a discrete-update CTA of another chain group fits beside this kernel's CTA
+#define TJ_BOUNDS __maxnreg__(TJ_REGS)
+#else
+#define TJ_BOUNDS __launch_bounds__(TJ_NTHR, 1)
+#endif
 #define HALF_LOG_2PI 0.9189385332046727
 
 struct traj_args {
@@ -101,7 +106,7 @@ __device__ __forceinline__ void tj_block_sum(double (&v)[TJ_NACC], double* tile,
 struct tj_smem {  // carved from dynamic shared memory after the ring
   double *u, *p, *g, *im;                    // [P]
   double *pa, *gam, *yir, *rir, *col, *cs;   // [Tp]
-  double* rowp;                              // [NCW][Mp] row-sum partials of the warps (one evaluation)
+  double* rowp;                              // [NCW / 2][Mp] row-sum partials of half of the warps (one evaluation)
   double* pm;                                // [Mp] per-metapopulation rate factors of the evaluation
   double* tile;                              // [NCW][TJ_DAYS][32] column-sum tiles of the warps
   double (*red)[TJ_NACC];                    // [NCW]
@@ -112,7 +117,7 @@ static size_t tj_state_bytes(int nthr, int T, int Mp, int P) {  // everything af
   const int Tp = (T + 3) / 4 * 4;
   size_t b = sizeof(double) * (4 * (size_t)((P + 1) / 2 * 2));  // u p g im
   b += sizeof(double) * (6 * (size_t)Tp);                       // pa gam yir rir col cs
-  b += sizeof(double) * (size_t)(nthr / 32) * Mp;               // rowp
+  b += sizeof(double) * (size_t)(nthr / 64) * Mp;               // rowp (half of the warps at a time)
   b += sizeof(double) * (size_t)Mp;                             // pm
   b += sizeof(double) * (size_t)(nthr / 32) * TJ_DAYS * 32;     // tile
   b += sizeof(double) * (size_t)(nthr / 32) * TJ_NACC;          // red
@@ -282,7 +287,7 @@ __device__ __forceinline__ void tj_block_sum(double (&v)[TJ_NACC], double* tile,
 }
 
 template <int KM>
-__global__ void __launch_bounds__(TJ_NTHR, 1) seir_hmc_traj_kernel(const traj_args A, const ll_coefs K) {
+__global__ void TJ_BOUNDS seir_hmc_traj_kernel(const traj_args A, const ll_coefs K) {
   constexpr int NTHR = TJ_NTHR, NCW = NTHR / 32;
   constexpr int MPT = (32 * KM + NTHR - 1) / NTHR;  // metapopulations per thread in the O(P) phases (thread <-> m = tid + q NTHR)
   extern __shared__ __align__(128) unsigned char smraw[];
@@ -302,7 +307,7 @@ __global__ void __launch_bounds__(TJ_NTHR, 1) seir_hmc_traj_kernel(const traj_ar
     double* q = reinterpret_cast<double*>(smraw + 2 * stage_bytes);
     sm.u = q; q += P2; sm.p = q; q += P2; sm.g = q; q += P2; sm.im = q; q += P2;
     sm.pa = q; q += Tp; sm.gam = q; q += Tp; sm.yir = q; q += Tp; sm.rir = q; q += Tp; sm.col = q; q += Tp; sm.cs = q; q += Tp;
-    sm.rowp = q; q += (size_t)NCW * Mp;
+    sm.rowp = q; q += (size_t)(NCW / 2) * Mp;
     sm.pm = q; q += Mp;
     sm.tile = q; q += (size_t)NCW * TJ_DAYS * 32;
     sm.red = reinterpret_cast<double (*)[TJ_NACC]>(q); q += (size_t)NCW * TJ_NACC;
@@ -662,16 +667,22 @@ __global__ void __launch_bounds__(TJ_NTHR, 1) seir_hmc_traj_kernel(const traj_ar
           }
         }
       }
-      // row sums: every warp's partials -> shared memory -> thread <-> metapopulation adds the warps in order
-#pragma unroll
-      for (int kk = 0; kk < KM; ++kk) sm.rowp[warp * Mp + lane + 32 * kk] = rowr[kk];
-      tj_bar(NTHR);
+      // row sums: every warp's partials -> shared memory (half of the warps at a time: the buffer holds NCW / 2 rows) -> thread
+      // <-> metapopulation adds the warps in order
       double row[MPT];
 #pragma unroll
-      for (int q = 0; q < MPT; ++q) {
-        row[q] = 0.0;
-        if (act[q])
-          for (int w = 0; w < NCW; ++w) row[q] += sm.rowp[w * Mp + tid + q * NTHR];
+      for (int q = 0; q < MPT; ++q) row[q] = 0.0;
+#pragma unroll
+      for (int half = 0; half < 2; ++half) {
+        if (half) tj_bar(NTHR);  // (the first half has been read)
+        if (warp / (NCW / 2) == half)
+#pragma unroll
+          for (int kk = 0; kk < KM; ++kk) sm.rowp[(warp - half * (NCW / 2)) * Mp + lane + 32 * kk] = rowr[kk];
+        tj_bar(NTHR);
+#pragma unroll
+        for (int q = 0; q < MPT; ++q)
+          if (act[q])
+            for (int w = 0; w < NCW / 2; ++w) row[q] += sm.rowp[w * Mp + tid + q * NTHR];
       }
 
       TJT(8 + i * 8 + 3);

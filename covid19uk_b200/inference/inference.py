@@ -57,6 +57,22 @@ class ParamBijector:
 EVENTS_DTYPE = {"uint16": torch.uint16, "float64": torch.float64}  # Mcmc.store_events_as
 
 
+class _nvtx:
+    """NVTX range around a window / burst / gather (visible in nsys / ncu timelines); a no-op without CUDA."""
+
+    def __init__(self, name):
+        self.name = name
+
+    def __enter__(self):
+        if torch.cuda.is_available():
+            torch.cuda.nvtx.range_push(self.name)
+
+    def __exit__(self, *exc):
+        if torch.cuda.is_available():
+            torch.cuda.nvtx.range_pop()
+        return False
+
+
 def _window(kernel_list, name, num_draws, joint_log_prob_fn, initial_position, trace_fn, seed, events_dtype=torch.float64):
     """One adaptation window.  Returns sample_chain's (draws, trace, final kernel results) with ``draws[1][-1]`` replaced by
     nothing: the final state travels as the fourth element (its event part is the device-resident handle, so the next
@@ -75,7 +91,8 @@ def _fast_adapt_window(num_draws, joint_log_prob_fn, initial_position, hmc_kerne
     Returns draws, trace, the adapted step size, the variance accumulator of the window and the final state."""
     kernel_list = [(0, make_hmc_fast_adapt_kernel(hmc_kernel_kwargs=hmc_kernel_kwargs, dual_averaging_kwargs=dual_averaging_kwargs)),
                    (1, make_event_multiscan_gibbs_step(**event_kernel_kwargs))]
-    draws, trace, fkr, final = _window(kernel_list, "fast_adapt", num_draws, joint_log_prob_fn, initial_position, trace_fn, seed, events_dtype)
+    with _nvtx(f"seir/fast_adapt_window_{num_draws}"):
+        draws, trace, fkr, final = _window(kernel_list, "fast_adapt", num_draws, joint_log_prob_fn, initial_position, trace_fn, seed, events_dtype)
     step_size = tm.unnest.get_outermost(fkr.inner_results[0], "step_size")
     return draws, trace, step_size, get_weighted_running_variance(draws[0]), final
 
@@ -85,7 +102,8 @@ def _slow_adapt_window(num_draws, joint_log_prob_fn, initial_position, initial_r
     """inference.py:124-196: step size and diagonal mass matrix adapted together."""
     kernel_list = [(0, make_hmc_slow_adapt_kernel(initial_running_variance, hmc_kernel_kwargs, dual_averaging_kwargs)),
                    (1, make_event_multiscan_gibbs_step(**event_kernel_kwargs))]
-    draws, trace, fkr, final = _window(kernel_list, "slow_adapt", num_draws, joint_log_prob_fn, initial_position, trace_fn, seed, events_dtype)
+    with _nvtx(f"seir/slow_adapt_window_{num_draws}"):
+        draws, trace, fkr, final = _window(kernel_list, "slow_adapt", num_draws, joint_log_prob_fn, initial_position, trace_fn, seed, events_dtype)
     step_size = tm.unnest.get_outermost(fkr.inner_results[0], "step_size")
     momentum_distribution = tm.unnest.get_outermost(fkr.inner_results[0], "momentum_distribution")
     return draws, trace, step_size, get_weighted_running_variance(draws[0]), momentum_distribution, final
@@ -176,7 +194,8 @@ def run_mcmc(joint_log_prob_fn, current_state, param_bijector, initial_condition
 
         tree = {"samples": draws_to_dict([param_bijector.inverse(draws[0]), draws[1]]), "results": trace}
         t0 = time.perf_counter()
-        out = dd.gather_to_rank0(tree, B_total, chain_dim=1)
+        with _nvtx("seir/gather_to_rank0"):
+            out = dd.gather_to_rank0(tree, B_total, chain_dim=1)
         if torch.cuda.is_available():
             torch.cuda.synchronize()
         gather_ms.append(1e3 * (time.perf_counter() - t0))
@@ -185,8 +204,9 @@ def run_mcmc(joint_log_prob_fn, current_state, param_bijector, initial_condition
     def write(posterior, draws, trace, offset):
         tree = collect(draws, trace)
         if rank == 0:
-            posterior.write_samples(tree["samples"], first_dim_offset=offset)
-            posterior.write_results(tree["results"], first_dim_offset=offset)
+            with _nvtx("seir/posterior_write"):
+                posterior.write_samples(tree["samples"], first_dim_offset=offset)
+                posterior.write_results(tree["results"], first_dim_offset=offset)
 
     print("Initialising output...", end="", flush=True, file=sys.stderr)
     probe, _ = make_fixed_window_sampler(1, joint_log_prob_fn, hmc_kernel_kwargs, event_kernel_kwargs, trace_fn=trace_results_fn,
@@ -239,7 +259,8 @@ def run_mcmc(joint_log_prob_fn, current_state, param_bijector, initial_condition
         seed=tm.SeedPath(seed_base, sweep_pos), jit_compile=True, num_steps_between_results=thin - 1, events_dtype=events_dtype)
     pkr = kernel.bootstrap_results(kernel.normalise_state(current_state))
     for _ in range(config["num_bursts"]):
-        draws, trace, pkr, current_state = fixed_sample(current_state, pkr)
+        with _nvtx("seir/burst"):
+            draws, trace, pkr, current_state = fixed_sample(current_state, pkr)
         write(posterior, draws, trace, offset)
         offset += config["num_burst_samples"]
     run_mcmc.last_gather_ms = gather_ms

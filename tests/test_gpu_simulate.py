@@ -137,3 +137,36 @@ def test_predicted_incidence_mirror():
         assert sim.min() >= 0 and np.array_equal(sim, np.round(sim))
         for b in range(B):
             assert so.compute_state(init[b], sim[b], closed=True).min() >= 0
+
+
+def test_model_sample_surface():
+    """CovidUK(...).sample(**pars) (model_spec.py:287-299, posterior/predict.py:57-64): pinned parameter nodes are returned as
+    given, the others come from their priors, `seir` is a valid epidemic whose log-prob under the same parameters is finite,
+    and equals what seir_simulate gives for the same streams."""
+    import torch
+    from covid19uk_b200 import model_spec
+    from covid19uk_b200 import synthetic as syn
+    from oracle import seir_oracle as so
+
+    M, T, B = 20, 30, 5
+    pb = syn.make_problem(M, T, chains=B, seed=2)
+    model = model_spec.CovidUK(pb["covariates"], pb["initial_state"], 0, T)
+    pars = {k: np.stack([so.unpack_params(pb["theta"][b], M, T)[k] for b in range(B)]) for k in model_spec.PARAM_ORDER}
+    s = model.sample(seed=7, **pars)
+    assert set(s) == set(model_spec.PARAM_ORDER) | {"seir"}
+    ev = s["seir"].cpu().numpy()
+    assert ev.shape == (B, M, T, 3) and ev.min() >= 0 and np.array_equal(ev, np.round(ev))
+    assert np.all(so.compute_state(pb["initial_state"], ev) >= 0)
+    for k in model_spec.PARAM_ORDER:
+        np.testing.assert_array_equal(s[k].cpu().numpy().reshape(pars[k].shape), pars[k])
+    lp = model.log_prob({**{k: s[k] for k in model_spec.PARAM_ORDER}, "seir": s["seir"]}).cpu().numpy()
+    assert np.all(np.isfinite(lp))
+    s2 = model.sample(seed=7, **pars)
+    assert torch.equal(s["seir"], s2["seir"])  # counter-based streams: reproducible
+    # unpinned nodes are drawn from the priors; a single unbatched draw has the reference's shapes
+    one = model.sample(seed=3, alpha_0=-1.7, gamma0=-1.5, gamma1=0.1, psi=0.5, beta_area=0.1, sigma_space=0.05)
+    assert tuple(one["seir"].shape) == (M, T, 3) and tuple(one["alpha_t"].shape) == (T - 1,) and tuple(one["spatial_effect"].shape) == (M,)
+    many = model.sample(sample_shape=(64,), seed=4)
+    assert tuple(many["psi"].shape) == (64,) and float(many["psi"].min()) > 0 and float(many["sigma_space"].min()) >= 0
+    assert abs(float(many["alpha_t"].std()) - 0.005) < 0.001
+    model.engine.close()
