@@ -20,6 +20,7 @@ def main():
     ap.add_argument("--chains", type=int, default=256)
     ap.add_argument("--M", type=int, default=382)
     ap.add_argument("--T", type=int, default=84)
+    ap.add_argument("--leapfrog", type=int, default=16)
     a = ap.parse_args()
     import torch
 
@@ -34,11 +35,11 @@ def main():
     u = unconstrain(torch.from_numpy(pb["theta"])).cuda()
     out = torch.empty(a.chains, dtype=torch.float64, device="cuda")
     cfg = dict(dmax=84, nmax=25, m=2, occult_nmax=15, num_event_time_updates=1)
-    cs = ChainSet(eng, ev, u, cfg, [a.T - 21, a.T], seed=1, num_leapfrog_steps=1)
-
     def once():
         eng.log_prob(ev, u, nat.THETA_UNCONSTRAINED, nat.PART_JOINT, out=out)
         eng.value_and_grad_cached(u, nat.THETA_UNCONSTRAINED, nat.PART_JOINT)
+        # (a sampler handle refuses caches that an explicit-events evaluation re-ingested: the chain set is made afterwards)
+        cs = ChainSet(eng, ev, u, cfg, [a.T - 21, a.T], seed=1, num_leapfrog_steps=a.leapfrog)
         cs.sample(1, step_size=2e-5, collect_draws=False)
 
     once()
