@@ -560,8 +560,8 @@ def main():
     ap.add_argument("--chains", type=int, default=256, help="chains per GPU")
     ap.add_argument("--sweeps", type=int, default=10, help="MCMC sweeps per timed burst")
     ap.add_argument("--sweep-step-size", type=float, default=2e-5)
-    ap.add_argument("--tuned-dmax", type=int, default=2, help="event-time proposals of the second sweeps/s figure")
-    ap.add_argument("--tuned-nmax", type=int, default=2)
+    ap.add_argument("--tuned-dmax", type=int, default=16, help="event-time proposals of the second sweeps/s figure")
+    ap.add_argument("--tuned-nmax", type=int, default=16)
     ap.add_argument("--no-cpu-baseline", action="store_true", help="skip the CPU oracle leg (profiling runs)")
     args = ap.parse_args()
     if args.impl == "reference":

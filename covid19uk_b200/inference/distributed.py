@@ -120,25 +120,80 @@ def _gather_to(t: torch.Tensor, chain_dim: int, counts, dst: int, group=None, ma
     return full.contiguous().view(t.dtype) if raw is not None else full
 
 
-def gather_to_rank0(tree, num_chains: int, chain_dim: int = 1, group=None, dst: int = 0):
+def gather_to_rank0(tree, num_chains: int, chain_dim: int = 1, group=None, dst: int = 0, max_bytes=1 << 30):
     """The per-burst exchange of the product path: every rank's slice of a (nested dict / list of) tensors with
     a chain axis -> rank ``dst`` in global chain order (NCCL gather over NVLink on the GPU box, gloo in the CPU tests).
-    Returns the gathered tree on ``dst`` and None elsewhere; the identity outside torch.distributed.  ``None`` leaves pass."""
+    Returns the gathered tree on ``dst`` and None elsewhere; the identity outside torch.distributed.  ``None`` leaves pass.
+
+    All leaves travel in ONE message per rank -- each leaf's chains as rows of raw bytes, the leaves side by side (a burst's
+    trace is ~20 small tensors: one collective of latency instead of twenty) -- except leaves above ``max_bytes`` per rank
+    (the compact event draws), which go on their own in bounded slices of the draw axis."""
     if not (dist.is_available() and dist.is_initialized()) or dist.get_world_size(group) == 1:
         return tree
     ws = dist.get_world_size(group)
     counts = [shard_chains(num_chains, ws, r)[1] for r in range(ws)]
     me = dist.get_rank(group)
+    cmax = max(counts)
+    leaves = []
 
-    def rec(node):
+    def collect(node):
+        if node is None:
+            return
+        if isinstance(node, dict):
+            for v in node.values():
+                collect(v)
+        elif isinstance(node, (list, tuple)):
+            for v in node:
+                collect(v)
+        else:
+            leaves.append(node)
+
+    collect(tree)
+    small, packed_rows = [], []
+    for t in leaves:
+        x = t.movedim(chain_dim, 0).contiguous()  # [B_local, ...]
+        nbytes = (x[0].numel() if x.shape[0] else 0) * x.element_size()
+        if nbytes * cmax > max_bytes or x.shape[0] == 0:
+            small.append(None)
+            continue
+        rows = (x.to(torch.uint8) if x.dtype == torch.bool else x).reshape(x.shape[0], -1).view(torch.uint8)  # [B_local, nbytes]
+        small.append((tuple(x.shape[1:]), t.dtype, rows.shape[1]))
+        packed_rows.append(rows)
+    gathered = None
+    if packed_rows:
+        buf = torch.cat(packed_rows, dim=1)
+        if buf.shape[0] < cmax:
+            buf = torch.cat([buf, torch.zeros((cmax - buf.shape[0], buf.shape[1]), dtype=torch.uint8, device=buf.device)], dim=0)
+        bufs = [torch.empty_like(buf) for _ in range(ws)] if me == dst else None
+        dist.gather(buf.contiguous(), bufs, dst=dst, group=group)
+        if me == dst:
+            gathered = torch.cat([bufs[r][:counts[r]] for r in range(ws)], dim=0)  # [B_total, total bytes]
+    out_leaves, col = [], 0
+    for t, meta in zip(leaves, small):
+        if meta is None:
+            out_leaves.append(_gather_to(t, chain_dim, counts, dst, group, max_bytes))
+            continue
+        rest, dtype, nb = meta
+        if me == dst:
+            raw = gathered[:, col:col + nb].contiguous()
+            x = raw.view(torch.uint8 if dtype == torch.bool else dtype).reshape((raw.shape[0],) + rest)
+            if dtype == torch.bool:
+                x = x.to(torch.bool)
+            out_leaves.append(x.movedim(0, chain_dim))
+        else:
+            out_leaves.append(None)
+        col += nb
+    if me != dst:
+        return None
+    it = iter(out_leaves)
+
+    def rebuild(node):
         if node is None:
             return None
         if isinstance(node, dict):
-            out = {k: rec(v) for k, v in node.items()}
-            return out if me == dst else None
+            return {k: rebuild(v) for k, v in node.items()}
         if isinstance(node, (list, tuple)):
-            out = [rec(v) for v in node]
-            return type(node)(out) if me == dst else None
-        return _gather_to(node, chain_dim, counts, dst, group)
+            return type(node)(rebuild(v) for v in node)
+        return next(it)
 
-    return rec(tree)
+    return rebuild(tree)

@@ -28,6 +28,8 @@ def main():
     ap.add_argument("--step-size", type=float, default=2e-5)
     ap.add_argument("--updates", type=int, default=5, help="num_event_time_updates (0 = HMC only)")
     ap.add_argument("--leapfrog", type=int, default=16)
+    ap.add_argument("--dmax", type=int, default=84)
+    ap.add_argument("--nmax", type=int, default=25)
     a = ap.parse_args()
     import torch
 
@@ -39,7 +41,7 @@ def main():
     pb = syn.make_problem(a.M, a.T, chains=a.chains, seed=0, distinct=min(a.chains, 16))
     eng = SeirEngine(pb["covariates"], pb["initial_state"], 0, a.T)
     u0 = unconstrain(torch.from_numpy(pb["theta"]))
-    cs = ChainSet(eng, pb["events"], u0, dict(CFG, num_event_time_updates=a.updates), [a.T - 21, a.T], seed=1, num_leapfrog_steps=a.leapfrog)
+    cs = ChainSet(eng, pb["events"], u0, dict(CFG, num_event_time_updates=a.updates, dmax=a.dmax, nmax=a.nmax), [a.T - 21, a.T], seed=1, num_leapfrog_steps=a.leapfrog)
     cs.sample(a.warmup, step_size=a.step_size, collect_draws=False)
     torch.cuda.synchronize()
     l0 = nat.launch_count()
