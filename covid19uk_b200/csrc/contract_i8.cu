@@ -56,6 +56,10 @@ __device__ long long g_i8dbg[64];
 #define TM(k) do { } while (0)
 #endif
 
+__device__ __forceinline__ double i8_int_to_double(int k) {  // exact int32 -> double with one FP64 add
+  return __hiloint2double(0x43300000, k ^ 0x80000000) - 4503601774854144.0;  // 2^52 + 2^31
+}
+
 // ---- tcgen05 wrappers -------------------------------------------------------------------------------------------------
 __device__ __forceinline__ void tc_fence_before() { asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory"); }
 __device__ __forceinline__ void tc_fence_after() { asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory"); }
@@ -174,7 +178,7 @@ __global__ void __launch_bounds__(I8_THREADS, 1) seir_contract_i8_kernel(long lo
   if (tid == 0) {
     for (int s = 0; s < I8_STAGES; ++s) { mbar_init(&full_b[s], 1); mbar_init(&empty_b[s], 1); }
     mbar_init(&a_ready, 1);
-    mbar_init(&a_region_free, I8_EPI_THREADS / 32);
+    mbar_init(&a_region_free, 1);  // one arrival per tile: the commit behind the tile's last MMA (the MMA issuer)
     for (int s = 0; s < 4; ++s) { mbar_init(&t_full[s], 1); mbar_init(&t_empty[s], I8_EPI_THREADS / 32); }
     asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
   }
@@ -221,15 +225,15 @@ __global__ void __launch_bounds__(I8_THREADS, 1) seir_contract_i8_kernel(long lo
         if (lane == 0) mbar_arrive(&t_empty[slot]);  // the slot may be overwritten
 #pragma unroll
         for (int j = 0; j < 32; ++j) {
-          out[j] = fma((double)(int)v0[j], w, out[j]);
-          out[32 + j] = fma((double)(int)v1[j], w, out[32 + j]);
+          // int32 -> double by the 2^52 + 2^31 trick (one DADD on the FP64 pipe, exact): the conversion unit (I2F.F64) runs
+          // at a quarter of the FP64 rate and this loop is 448 conversions per thread and tile (tools/ubench/fp64_rates.cu)
+          out[j] = fma(i8_int_to_double((int)v0[j]), w, out[j]);
+          out[32 + j] = fma(i8_int_to_double((int)v1[j]), w, out[32 + j]);
         }
       }
       if (tid == 0 && it == 1) TM(3);
-      // every MMA of the tile has completed (its last group was just drained): the A planes are dead, the producer may
-      // refill them while this tile is being stored
-      __syncwarp();
-      if (lane == 0) mbar_arrive(&a_region_free);
+      // (the A planes were released by the commit behind the tile's last MMA: the producer refills them and the next tile's
+      //  first groups run while this tile is still being drained and stored)
       // ---- store: thread <-> row, 64 consecutive columns as sixteen 32-byte stores (st.global.v4.f64: every store fills
       //      a whole 32-byte sector; a 16-byte store pattern took 8.4 us per tile, a shared-memory transposition 3.5 us but
       //      held the A region until the end)
@@ -332,6 +336,7 @@ __global__ void __launch_bounds__(I8_THREADS, 1) seir_contract_i8_kernel(long lo
         // plane c done: group na-1-c has all its pairs; after the last plane every remaining group has
         const int s_hi = na_t - 1 - c, s_lo = (c == I8_NB - 1) ? -(I8_NB - 1) : s_hi;
         for (int s = s_hi; s >= s_lo; --s) tc_commit(&t_full[s & 3]);
+        if (c == I8_NB - 1) tc_commit(&a_region_free);  // every MMA of the tile has read its A planes once this commit arrives
         if (itm == 1) TM(40 + c);
       }
     }
