@@ -59,8 +59,6 @@ struct traj_args {
   double* dbg;
   unsigned char* scratch;   // [gridDim.x][T][Mp] x 16 bytes
   int b0, nb, L;
-  int sd, pd;               // days per source / packed ring stage (multiples of TJ_DAYS)
-  unsigned stage_bytes;     // bytes of one ring stage
 };
 
 // phase timestamps (SM clock) of CTA 0's first chain: build with SEIR_NVCC_EXTRA=-DSEIR_TRAJ_DEBUG, read with seir_debug_traj
@@ -117,9 +115,7 @@ static size_t tj_state_bytes(int nthr, int T, int Mp, int P) {  // everything af
   const int Tp = (T + 3) / 4 * 4;
   size_t b = sizeof(double) * (4 * (size_t)((P + 1) / 2 * 2));  // u p g im
   b += sizeof(double) * (6 * (size_t)Tp);                       // pa gam yir rir col cs
-  b += sizeof(double) * (size_t)(nthr / 64) * Mp;               // rowp (half of the warps at a time)
   b += sizeof(double) * (size_t)Mp;                             // pm
-  b += sizeof(double) * (size_t)(nthr / 32) * TJ_DAYS * 32;     // tile
   b += sizeof(double) * (size_t)(nthr / 32) * TJ_NACC;          // red
   b += sizeof(double) * 16;                                     // sc
   return b + 128;
@@ -228,41 +224,19 @@ __device__ __forceinline__ double tj_col_reduce(const double (&colv)[TJ_DAYS], d
   return c;  // (the shuffles also order this group's tile reads before the next group's stores)
 }
 
-// The ring: TWO stages, each one large bulk copy (measured, tools/ubench/tma_feed.cu: a 1-D bulk copy costs ~700 cycles plus
-// its bytes whatever the ring depth -- 24 KB stages feed an SM at 32 B/clk, 72 KB stages at ~95 B/clk).  A packed stage holds
-// pd days (3 groups at the UK size: 73.7 KB), a source stage sd days in four blocks (yse | S | I | Bc, four copies).  There is
-// no producer warp (it would push the CTA to 416 threads and the register cap to 128): the warp that releases a stage LAST
-// issues the next copy into it.  s_seq orders everything: stage n of the CTA's life lives in buffer n & 1.
-struct tj_ring {
-  uint64_t full[2];
-  int cnt[2];        // warps that have released the stage in the buffer
-  int consumed;      // stages fully released
-  int next;          // next stage to load (global index over the CTA's life)
-  // the chain whose stages are being loaded, and where its stages start
-  int ld_k, ld_base, ld_packed, ld_eval0_done;
-};
-
-struct tj_sched {
-  int T, Mp, L, sd, pd, ns0, nsp;  // days per source / packed stage, stages per evaluation in each mode
-};
-
-// stage n (chain-local) -> evaluation, first day, days, mode
-__device__ __forceinline__ void tj_stage_of(const tj_sched& s, int n, int packed, int& eval, int& d0, int& nd, int& src) {
-  if (n < s.ns0 || !packed) {
-    eval = n / s.ns0;
-    const int k = n - eval * s.ns0;
-    d0 = k * s.sd;
-    nd = min(s.sd, s.T - d0);
-    src = 1;
-  } else {
-    const int r = n - s.ns0;
-    eval = 1 + r / s.nsp;
-    const int k = r - (eval - 1) * s.nsp;
-    d0 = k * s.pd;
-    nd = min(s.pd, s.T - d0);
-    src = 0;
-  }
+// Data movement of the cell phase: every WARP streams its own days (day t belongs to warp t % NCW) through a private
+// double-buffered shared-memory slot with per-thread 16-byte asynchronous copies (cp.async.cg: LDGSTS, L2 -> shared memory),
+// the copy of its next day in flight while it computes the current one.  No warp ever waits for another: no ring, no
+// mbarriers, no producer.  (The earlier versions fed a CTA-wide ring with 1-D bulk copies: tools/ubench/tma_feed.cu measures
+// ~700 cycles + bytes per bulk copy WHATEVER the ring depth -- successive copies of an SM do not overlap -- so every stage
+// boundary exposed a copy's latency to all 12 warps: 2 x 74 KB stages 4.3 k cycles per stage for 2.9 k of arithmetic, 3 x 49 KB
+// and 4 x 25 KB stages slower still.)
+__device__ __forceinline__ void tj_cp16(void* smem_dst, const void* gsrc) {
+  asm volatile("cp.async.cg.shared.global [%0], [%1], 16;" ::"r"(smem_u32(smem_dst)), "l"(gsrc) : "memory");
 }
+__device__ __forceinline__ void tj_cp_commit() { asm volatile("cp.async.commit_group;" ::: "memory"); }
+template <int N>
+__device__ __forceinline__ void tj_cp_wait() { asm volatile("cp.async.wait_group %0;" ::"n"(N) : "memory"); }
 
 template <int NTHR>
 __device__ __forceinline__ void tj_block_sum(double (&v)[TJ_NACC], double* tile, double (*red)[TJ_NACC]) {
@@ -291,84 +265,26 @@ __global__ void TJ_BOUNDS seir_hmc_traj_kernel(const traj_args A, const ll_coefs
   constexpr int NTHR = TJ_NTHR, NCW = NTHR / 32;
   constexpr int MPT = (32 * KM + NTHR - 1) / NTHR;  // metapopulations per thread in the O(P) phases (thread <-> m = tid + q NTHR)
   extern __shared__ __align__(128) unsigned char smraw[];
-  __shared__ tj_ring ring;
   __shared__ double2 tab[128];
   __shared__ int s_ovf;
   const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
   const int M = A.M, T = A.T, Mp = A.Mp, P = A.P, L = A.L;
   const int Tp = (T + 3) / 4 * 4, P2 = (P + 1) / 2 * 2;
-  tj_sched sc;
-  sc.T = T; sc.Mp = Mp; sc.L = L; sc.sd = A.sd; sc.pd = A.pd;
-  sc.ns0 = (T + sc.sd - 1) / sc.sd;
-  sc.nsp = (T + sc.pd - 1) / sc.pd;
-  const size_t stage_bytes = A.stage_bytes;
+  const size_t slot_bytes = (size_t)Mp * 20;  // one day: packed 16 B per cell, or yse | S | I (int32) | Bc (f64)
   tj_smem sm;
   {
-    double* q = reinterpret_cast<double*>(smraw + 2 * stage_bytes);
+    double* q = reinterpret_cast<double*>(smraw + (size_t)NCW * 2 * slot_bytes);
     sm.u = q; q += P2; sm.p = q; q += P2; sm.g = q; q += P2; sm.im = q; q += P2;
     sm.pa = q; q += Tp; sm.gam = q; q += Tp; sm.yir = q; q += Tp; sm.rir = q; q += Tp; sm.col = q; q += Tp; sm.cs = q; q += Tp;
-    sm.rowp = q; q += (size_t)(NCW / 2) * Mp;
     sm.pm = q; q += Mp;
-    sm.tile = q; q += (size_t)NCW * TJ_DAYS * 32;
     sm.red = reinterpret_cast<double (*)[TJ_NACC]>(q); q += (size_t)NCW * TJ_NACC;
     sm.sc = q;
+    // the reductions between the cell phases reuse the day slots (no copy is in flight then)
+    sm.rowp = reinterpret_cast<double*>(smraw);
+    sm.tile = sm.rowp + (size_t)(NCW / 2) * Mp;
   }
   unsigned char* scratch = A.scratch + (size_t)blockIdx.x * T * Mp * 16;
   const int nmine = (A.nb - (int)blockIdx.x + (int)gridDim.x - 1) / (int)gridDim.x;  // chains of this CTA: b0 + blockIdx.x + k gridDim.x
-
-  // Issue every load that may go now: its buffer is free (stage n - 2 released) and its data exists (the packed scratch of a
-  // chain is complete only after the chain's evaluation 0).  Called by ONE thread at a time: the lane that released a stage
-  // last, or thread 0 behind a CTA barrier.
-  auto pump = [&]() {
-    for (;;) {
-      const int n = ring.next;
-      if (n >= ring.consumed + 2 || ring.ld_k >= nmine) return;
-      const int nl = n - ring.ld_base;
-      const int nchain = ring.ld_packed ? sc.ns0 + L * sc.nsp : (L + 1) * sc.ns0;
-      if (nl >= sc.ns0 && !ring.ld_eval0_done) return;  // (evaluations >= 1 of this chain: wait for its scratch / its mode)
-      if (nl >= nchain) {  // on to the next chain of this CTA: its evaluation 0 reads the caches
-        ring.ld_k += 1;
-        ring.ld_base = n;
-        ring.ld_packed = 1;
-        ring.ld_eval0_done = 0;
-        continue;
-      }
-      int eval, d0, nd, src;
-      tj_stage_of(sc, nl, ring.ld_packed, eval, d0, nd, src);
-      unsigned char* dst = smraw + (size_t)(n & 1) * stage_bytes;
-      uint64_t* bar = &ring.full[n & 1];
-      if (!src) {
-        const unsigned bytes = (unsigned)(nd * Mp * 16);
-        mbar_expect_tx(bar, bytes);
-        bulk_load_1d(dst, scratch + (size_t)d0 * Mp * 16, bytes, bar);
-      } else {
-        const int bb = A.b0 + (int)blockIdx.x + ring.ld_k * (int)gridDim.x;
-        const size_t o = ((size_t)bb * T + d0) * Mp;
-        const unsigned n4 = (unsigned)(nd * Mp * 4);
-        mbar_expect_tx(bar, 5u * n4);
-        const size_t blk = (size_t)sc.sd * Mp * 4;  // (block stride of a FULL source stage, also for the short last one)
-        bulk_load_1d(dst, A.yse + o, n4, bar);
-        bulk_load_1d(dst + blk, A.S + o, n4, bar);
-        bulk_load_1d(dst + 2 * blk, A.I + o, n4, bar);
-        bulk_load_1d(dst + 3 * blk, A.Bc + o, 2u * n4, bar);
-      }
-      ring.next = n + 1;
-    }
-  };
-
-  if (tid == 0) {
-    mbar_init(&ring.full[0], 1);
-    mbar_init(&ring.full[1], 1);
-    asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
-    ring.cnt[0] = ring.cnt[1] = 0;
-    ring.consumed = 0;
-    ring.next = 0;
-    ring.ld_k = 0;
-    ring.ld_base = 0;
-    ring.ld_packed = 1;
-    ring.ld_eval0_done = 0;
-    pump();  // the first two stages of the first chain
-  }
   if (tid < 128) tab[tid] = A.logtab[tid];
   __syncthreads();
 
@@ -386,7 +302,6 @@ __global__ void TJ_BOUNDS seir_hmc_traj_kernel(const traj_args A, const ll_coefs
   }
   const double epsdt = A.eps * A.dt;
   const unsigned long long magic = (unsigned long long)__double_as_longlong(K.k[13]);  // 2^52: bit pattern 0x4330000000000000
-  unsigned nglob = 0;  // stages consumed over the CTA's life
 #ifdef SEIR_TRAJ_DEBUG
   long long twait = 0;
 #endif
@@ -577,34 +492,48 @@ __global__ void TJ_BOUNDS seir_hmc_traj_kernel(const traj_args A, const ll_coefs
       cx.T = T; cx.Mp = Mp; cx.psi = psi; cx.epsdt = epsdt; cx.tab = tab; cx.W = A.W; cx.scratch = scratch;
       cx.ovf = &s_ovf;
       cx.magic = magic;
-      cx.src_stride = sc.sd * Mp;
+      cx.src_stride = Mp;
       const bool src_eval = i == 0 || !packed;
-      const int nstages = src_eval ? sc.ns0 : sc.nsp, sdays = src_eval ? sc.sd : sc.pd;
-      for (int s = 0; s < nstages; ++s, ++nglob) {
-        const int buf = (int)(nglob & 1u);
-#ifdef SEIR_TRAJ_DEBUG
-        const long long tw0 = clock64();
-#endif
-        mbar_wait(&ring.full[buf], (nglob >> 1) & 1u);
-#ifdef SEIR_TRAJ_DEBUG
-        if (s == 0) twait = 0;
-        twait += clock64() - tw0;
-        if (blockIdx.x == 0 && tid == 0 && kchain == 0 && s == nstages - 1) g_tj_dbg[8 + i * 8 + 7] = twait;
-#endif
-        const unsigned char* stage = smraw + (size_t)buf * stage_bytes;
-        const int d0 = s * sdays, nd = min(sdays, T - d0);
-        for (int d = warp; d < nd; d += NCW) {  // the days of the stage this warp owns
-          const int t = d0 + d;
+      unsigned char* slot0 = smraw + (size_t)warp * 2 * slot_bytes;  // this warp's two day slots
+      const size_t cb = (size_t)b * T * Mp;
+      auto issue = [&](int t, int which) {  // this warp's copies of day t into slot `which` (every lane its 16-byte pieces)
+        unsigned char* dst = slot0 + (size_t)which * slot_bytes;
+        if (!src_eval) {
+          const unsigned char* src = scratch + (size_t)t * Mp * 16;
+#pragma unroll
+          for (int kk = 0; kk < KM; ++kk) tj_cp16(dst + (size_t)(lane + 32 * kk) * 16, src + (size_t)(lane + 32 * kk) * 16);
+        } else {
+          const size_t o = cb + (size_t)t * Mp;
+          for (int c = lane; c < Mp / 4; c += 32) {  // four int32 counts per piece
+            tj_cp16(dst + (size_t)c * 16, A.yse + o + 4 * c);
+            tj_cp16(dst + (size_t)Mp * 4 + (size_t)c * 16, A.S + o + 4 * c);
+            tj_cp16(dst + (size_t)Mp * 8 + (size_t)c * 16, A.I + o + 4 * c);
+          }
+          for (int c = lane; c < Mp / 2; c += 32) tj_cp16(dst + (size_t)Mp * 12 + (size_t)c * 16, A.Bc + o + 2 * c);
+        }
+        tj_cp_commit();
+      };
+      int which = 0;
+      if (warp < T) issue(warp, 0);
+      for (int t = warp; t < T; t += NCW) {  // day t belongs to warp t % NCW
+        const int tn = t + NCW;
+        if (tn < T) {  // (the other slot was consumed in the previous iteration: the __syncwarp at its end orders the reads)
+          issue(tn, which ^ 1);
+          tj_cp_wait<1>();
+        } else {
+          tj_cp_wait<0>();
+        }
+        __syncwarp();  // every lane's pieces of day t have landed
+        {
+          const unsigned char* day = slot0 + (size_t)which * slot_bytes;
           const double pat = sm.pa[t], wt = A.W[t];
           tj_dptr dp;
-          dp.pk = stage + (size_t)d * Mp * 16;
-          dp.sy = reinterpret_cast<const int*>(stage) + (size_t)d * Mp;
-          dp.sb = reinterpret_cast<const double*>(stage + (size_t)3 * sc.sd * Mp * 4) + (size_t)d * Mp;
+          dp.pk = day;
+          dp.sy = reinterpret_cast<const int*>(day);
+          dp.sb = reinterpret_cast<const double*>(day + (size_t)Mp * 12);
           double colacc = 0.0;
 #pragma unroll
           for (int k0 = 0; k0 < KM; k0 += 4) {
-            constexpr int dummy = 0;
-            (void)dummy;
             if (k0 + 4 <= KM) {
               double term[4], gge[4], X[4], bw[4];
               const double pm4[4] = {pmr[k0], pmr[k0 + 1 < KM ? k0 + 1 : k0], pmr[k0 + 2 < KM ? k0 + 2 : k0], pmr[k0 + 3 < KM ? k0 + 3 : k0]};
@@ -650,23 +579,12 @@ __global__ void TJ_BOUNDS seir_hmc_traj_kernel(const traj_args A, const ll_coefs
           colacc = warp_sum(colacc);  // the day's column sum: this warp owns the whole day
           if (lane == 0) sm.col[t] = colacc;
         }
-        // release the stage; the warp that does so last refills the ring
-        if (i == 0) {  // (this warp's scratch writes: visible to the async proxy before any later bulk copy can be issued)
-          __threadfence();
-          asm volatile("fence.proxy.async;" ::: "memory");
-        }
-        __syncwarp();
-        if (lane == 0) {
-          __threadfence_block();
-          if (atomicAdd(&ring.cnt[buf], 1) == NCW - 1) {
-            atomicExch(&ring.cnt[buf], 0);
-            __threadfence_block();
-            *reinterpret_cast<volatile int*>(&ring.consumed) = ring.consumed + 1;
-            pump();
-            __threadfence_block();
-          }
-        }
+        __syncwarp();  // the slot may be refilled
+        which ^= 1;
       }
+      if (i == 0) __threadfence();  // (this thread's scratch writes of evaluation 0, read back by its own copies from evaluation 1 on)
+      tj_bar(NTHR);  // every warp is done with its slots: the reductions below reuse that memory
+
       // row sums: every warp's partials -> shared memory (half of the warps at a time: the buffer holds NCW / 2 rows) -> thread
       // <-> metapopulation adds the warps in order
       double row[MPT];
@@ -700,14 +618,7 @@ __global__ void TJ_BOUNDS seir_hmc_traj_kernel(const traj_args A, const ll_coefs
       }
       tj_block_sum<NTHR>(acc, sm.tile, sm.red);  // (its barriers also publish col[]; s_ovf is settled)
       TJT(8 + i * 8 + 4);
-      if (i == 0) {
-        packed = !s_ovf;
-        if (tid == 0) {  // every warp has released evaluation 0's stages (and fenced its scratch writes): the chain's later loads may go
-          ring.ld_packed = packed;
-          ring.ld_eval0_done = 1;
-          pump();
-        }
-      }
+      if (i == 0) packed = !s_ovf;
       if (warp == 0) {  // suffix sums of the per-day column sums (lanes own consecutive chunks of days; lane 31 first)
         const int chunk = (T + 31) / 32;
         const int c0 = min(T, lane * chunk), c1 = min(T, c0 + chunk);
@@ -826,8 +737,6 @@ static bool traj_pick(int Mp, traj_cfg* k) {
 // Whether the persistent trajectory kernel applies to this chain set (shared memory for two ring stages of at least one
 // 4-day group + the O(P) state); if so, the launch shape.  SEIR_HMC_TRAJ=0 forces the round-1 launch sequence (hmc.cu).
 struct traj_shape {
-  int sd, pd;
-  unsigned stage_bytes;
   size_t smem;
 };
 
@@ -842,29 +751,11 @@ static bool traj_plan(const seir_chains* c, traj_cfg* k, traj_shape* sh) {
   if (!traj_pick(m->Mp, k)) return false;
   int dev_smem = 0;
   if (cudaDeviceGetAttribute(&dev_smem, cudaDevAttrMaxSharedMemoryPerBlockOptin, m->device) != cudaSuccess) return false;
-  const size_t state = tj_state_bytes(k->nthr, m->T, m->Mp, m->P);
-  const size_t budget = (size_t)dev_smem - 4096;  // (static shared memory of the kernel: ring bookkeeping, log table)
-  if (state + 2 * (size_t)TJ_DAYS * m->Mp * 20 > budget) return false;
-  const size_t per_stage = (budget - state) / 2;
-  const int Tp = (m->T + TJ_DAYS - 1) / TJ_DAYS * TJ_DAYS;
-  int pd = (int)(per_stage / ((size_t)m->Mp * 16)) / TJ_DAYS * TJ_DAYS, sd = (int)(per_stage / ((size_t)m->Mp * 20)) / TJ_DAYS * TJ_DAYS;
-  if (pd > Tp) pd = Tp;
-  if (sd > Tp) sd = Tp;
-  static int cap = -1;
-  if (cap < 0) {
-    const char* e = getenv("SEIR_TRAJ_STAGE_DAYS");  // experiments: cap the days per stage
-    cap = e ? atoi(e) : 0;
-  }
-  if (cap >= TJ_DAYS) {
-    if (pd > cap) pd = cap / TJ_DAYS * TJ_DAYS;
-    if (sd > cap) sd = cap / TJ_DAYS * TJ_DAYS;
-  }
-  if (pd < TJ_DAYS || sd < TJ_DAYS) return false;
-  const size_t pb = (size_t)pd * m->Mp * 16, sb = (size_t)sd * m->Mp * 20;
-  sh->sd = sd;
-  sh->pd = pd;
-  sh->stage_bytes = (unsigned)(((pb > sb ? pb : sb) + 127) / 128 * 128);
-  sh->smem = 2 * (size_t)sh->stage_bytes + state;
+  const size_t budget = (size_t)dev_smem - 4096;  // (static shared memory of the kernel: the log table)
+  const size_t slots = (size_t)(k->nthr / 32) * 2 * m->Mp * 20;  // two day slots per warp
+  // the reductions between the cell phases live inside the slot memory
+  if ((size_t)(k->nthr / 64) * m->Mp * 8 + (size_t)(k->nthr / 32) * TJ_DAYS * 32 * 8 > slots) return false;
+  sh->smem = slots + tj_state_bytes(k->nthr, m->T, m->Mp, m->P);
   return sh->smem <= budget;
 }
 
@@ -911,7 +802,6 @@ int seir_launch_hmc_traj(seir_chains* c, double* d_u, const double* d_log_u, con
   A.tlp = d_tlp; A.tlp_trace = d_tlp_trace; A.accept = d_accept; A.dbg = d_dbg;
   A.scratch = c->d_traj_scratch[slot];
   A.b0 = r.b0; A.nb = r.nb; A.L = num_leapfrog;
-  A.sd = sh.sd; A.pd = sh.pd; A.stage_bytes = sh.stage_bytes;
   k.fn<<<grid, k.nthr, smem, s>>>(A, LL_COEFS);
   seir_count_launch(1);
   return seir_cuda_check(cudaGetLastError(), "seir_hmc_traj_kernel");
