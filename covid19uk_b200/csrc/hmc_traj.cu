@@ -7,14 +7,17 @@
 // re-streamed the parameter-free caches of all chains (yse, S, I, Bc: 20 B per cell, 166 MB at 256 UK chains, more than
 // the 126 MB L2) from HBM, and every leapfrog kernel was a latency-bound O(P) pass over global partials: 17 x (58 + 21) us.
 // Here a chain's working set is read from HBM ONCE per transition:
-//   * evaluation 0 streams the four cache arrays through a shared-memory ring (1-D bulk copies, cp.async.bulk + mbarrier),
-//     and, while it computes, re-packs every cell into 16 bytes -- {y:16 | I:24 | S-y:24 bits, W_t Bc f64} -- in a
-//     per-CTA scratch region (516 KB at the UK size);
+//   * evaluation 0 streams the four cache arrays and, while it computes, re-packs every cell into 16 bytes --
+//     {I:24 | y low 8, S-y:24 | y high 8, W_t Bc f64} -- in a per-CTA scratch region (516 KB at the UK size);
 //   * evaluations 1..L stream the packed scratch, which stays in L2: 148 CTAs x 516 KB = 76 MB (measured,
 //     tools/ubench/l2_stream.cu: per-CTA regions adding up to 92 MB re-stream at 14 TB/s, 111 MB fall back to the HBM rate);
-//   * a producer warp keeps the ring full across evaluations (the data does not depend on the parameters), so the copy of
-//     the next evaluation's first stages overlaps the O(P) leapfrog arithmetic, which runs on shared memory with
-//     CTA-level barriers instead of kernel boundaries.
+//   * the stream: day t belongs to warp t % 12; every warp fetches ITS OWN days into a private double-buffered
+//     shared-memory slot with per-thread 16-byte cp.async.cg copies (L2 -> shared memory, no registers), one day ahead of
+//     the day it computes -- no ring, no mbarriers, no CTA-wide synchronisation inside the cell phase.  (The first versions
+//     used a TMA ring: measured, tools/ubench/tma_feed.cu, a 1-D bulk copy costs ~700 cycles plus its bytes whatever the
+//     ring depth, so that successive stages of an SM do not overlap: 24 KB stages fed 32 B/clk, 72 KB stages ~95 B/clk, and
+//     every stage hand-over was a CTA-wide rendezvous.)
+//   * the O(P) leapfrog arithmetic runs on shared memory with CTA-level barriers instead of kernel boundaries.
 // Results do not depend on the launch shape: one CTA <-> one chain, fixed thread <-> metapopulation mapping, fixed
 // reduction trees.
 #include <stdlib.h>
@@ -24,9 +27,9 @@
 #include "seir_internal.cuh"
 #include "tma.cuh"
 
-#define TJ_DAYS 4    // days per ring stage = one column-sum butterfly group
+#define TJ_DAYS 4    // width of the shared-memory tile reduce (tj_col_reduce)
 #define TJ_NACC 8
-#define TJ_NTHR 384  // 12 warps: the days of a 12-day packed stage, one each
+#define TJ_NTHR 384  // 12 warps; day t is streamed and evaluated by warp t % 12
 #ifdef TJ_REGS  // experiments: cap the registers so that a discrete-update CTA of another chain group fits beside this kernel's CTA
 #define TJ_BOUNDS __maxnreg__(TJ_REGS)
 #else
