@@ -64,8 +64,11 @@ template <int NT>
 __device__ __forceinline__ void upd_commit_rows(int b, int T, int Mp, const seir_update_cfg& cfg, const seir_upd& u, int acc, double dll,
                                                 double log_u, seir_upd* upd, const int* prop, int* yse, int* yei, int* Sx, int* Ex,
                                                 int* Ix, long long* Rir, long long* sumYei, long long* sumEres, double* llc_adj,
-                                                int* nzd_all, const upd_outputs& o, long long* redl) {
+                                                int* nzd_all, const upd_outputs& o, long long* redl, const win_cache wc) {
   const int tid = threadIdx.x;
+  // window counts kept by this CTA for the target (NULL: none kept yet): bumped like the event-day counts
+  int* wkeep = (wc.wcnt && wc.wmeta[cfg.target]) ? wc.wcnt + (size_t)cfg.target * Mp : nullptr;
+  const int kw0 = wkeep ? wc.wmeta[2 + cfg.target] : 0, kw1 = wkeep ? wc.wmeta[4 + cfg.target] : 0;
   if (tid == 0) {
     double prop_tlp = o.tlp[b] + dll;
     if (!u.valid || u.neg) prop_tlp = -INFINITY;
@@ -106,7 +109,10 @@ __device__ __forceinline__ void upd_commit_rows(int b, int T, int Mp, const seir
       if (dy) {  // the point changes of a proposal are distinct cells: one thread owns each
         const int y_old = yt[o2], y_new = y_old + dy;
         yt[o2] = y_new;
-        if ((y_old > 0) != (y_new > 0)) atomicAdd(nzd_all + ((size_t)b * 2 + cfg.target) * Mp + m, y_new > 0 ? 1 : -1);
+        if ((y_old > 0) != (y_new > 0)) {
+          atomicAdd(nzd_all + ((size_t)b * 2 + cfg.target) * Mp + m, y_new > 0 ? 1 : -1);
+          if (wkeep && s >= kw0 && s < kw1) atomicAdd(wkeep + m, y_new > 0 ? 1 : -1);
+        }
       }
       if (dc) {
         src[o2] -= dc;
@@ -164,7 +170,7 @@ struct upd_args {
 
 // prepare: every thread of the chain's CTA calls; returns the prepared record (also left in upd[b]).
 __device__ __forceinline__ seir_upd upd_prepare(const upd_args& A, int b, const seir_update_cfg& cfg, const seir_draw_args& draw,
-                                                 bool stage_rates) {
+                                                 bool stage_rates, const win_cache wc) {
   const int M = A.M, T = A.T, Mp = A.Mp;
   const double dt = A.dt, nu = A.nu, log_p_nu = A.log_p_nu, eps = A.eps;
   int* prop = A.prop;
@@ -200,7 +206,7 @@ __device__ __forceinline__ seir_upd upd_prepare(const upd_args& A, int b, const 
       sm.gam[t] = gam[(size_t)b * T + t];
     }
   UTM(1);
-  const int H = sample_hot_counts(g, cfg, nzd, sm.cnt, redn);
+  const int H = sample_hot_counts(g, cfg, nzd, sm.cnt, redn, wc);
   UTM(2);
   if (draw.enabled) {
     if (tid < 32) sample_metapops(g, cfg, draw.seed, draw.chain0 + (uint32_t)b, draw.ctr, sm.cnt, H, pr, log_u + b, s_sel);
@@ -526,10 +532,16 @@ __device__ __forceinline__ void upd_commit_slabs(const upd_args& A, int b, int k
 // Everything an update changes is written through global memory and re-read after a CTA barrier; the event-day counts
 // are bumped with atomics (L2) and therefore read with __ldcg.
 // ------------------------------------------------------------------------------------------------
+// dynamic shared memory of the update kernel: [prepare carve-up | day_acc [T] | kept window counts [2][Mp]]
+__host__ __device__ __forceinline__ size_t upd_wcnt_offset(int T, int Mp) {
+  return ((upd_smem_bytes(T, Mp) + 15) / 16 * 16 + sizeof(double) * (size_t)T + 15) / 16 * 16;
+}
+
 struct upd_plan {
   int nit;          // updates to run
   int single_slot;  // >= 0: every iteration is this slot (nit == 1); < 0: slot = it % 4, repetition = it / 4
   int nreps, B;
+  int keep_window;  // keep the occult-window counts in shared memory across the updates (set by launch_update_kernel)
   seir_update_cfg cfg[4];
   seir_draw_args draw;  // draw.ctr: stream position of iteration 0 (iteration it uses ctr + it)
   double* tlp;          // [B] running target log-prob
@@ -549,6 +561,12 @@ __global__ void __launch_bounds__(UPD_THREADS, MINB) seir_update_kernel(upd_args
   extern __shared__ __align__(16) unsigned char dynraw[];
   double* day_acc = reinterpret_cast<double*>(dynraw + (upd_smem_bytes(A.T, A.Mp) + 15) / 16 * 16);  // [T], after the prepare phase's carve-up
   __shared__ double2 s_logtab[128];
+  __shared__ int s_wmeta[6];
+  // the occult-window counts stay in shared memory across the updates of the launch (a 7 us scan of the window per occult
+  // update otherwise); a single update has nothing to keep
+  win_cache wc{nullptr, s_wmeta};
+  if (P.keep_window) wc.wcnt = reinterpret_cast<int*>(dynraw + upd_wcnt_offset(A.T, A.Mp));
+  if (threadIdx.x < 6) s_wmeta[threadIdx.x] = 0;
   for (int k = threadIdx.x; k < 128; k += UPD_THREADS) s_logtab[k] = A.logtab[k];
   __syncthreads();
   const int b = b0 + blockIdx.x, B = P.B;
@@ -566,7 +584,7 @@ __global__ void __launch_bounds__(UPD_THREADS, MINB) seir_update_kernel(upd_args
     if (blockIdx.x == 7 && threadIdx.x == 0) g_upd_it = it;
 #endif
     UTM(0);
-    const seir_upd u = upd_prepare(A, b, cfg, draw, it == 0);
+    const seir_upd u = upd_prepare(A, b, cfg, draw, it == 0, wc);
     UTM(8);
     if (cfg.target == 1) upd_slab(A, b, cfg.kind, u, day_acc, s_logtab);
     UTM(9);  // (ends with a CTA barrier: the partials are visible)
@@ -574,7 +592,7 @@ __global__ void __launch_bounds__(UPD_THREADS, MINB) seir_update_kernel(upd_args
     const double lu = A.log_u[b];
     const int acc = upd_decide(u, cfg.target, A.nchunk, A.part + (size_t)b * A.nchunk, lu, &dll);
     upd_commit_rows<UPD_THREADS>(b, A.T, A.Mp, cfg, u, acc, dll, lu, A.upd, A.prop, A.yse, A.yei, A.Sx, A.Ex, A.Ix, A.Rir, A.sumYei, A.sumEres,
-                                 A.llc_adj, A.nzd_all, o, s_redl);
+                                 A.llc_adj, A.nzd_all, o, s_redl, wc);
     UTM(10);
     if (cfg.target == 1 && acc && u.npts > 0) upd_commit_slabs(A, b, cfg.kind, u);
     __syncthreads();  // the next update reads what this one wrote
@@ -601,8 +619,14 @@ static upd_args make_upd_args(seir_chains* c, int* d_proposal, double* d_log_u) 
   return A;
 }
 
-static int launch_update_kernel(seir_chains* c, const upd_args& A, const upd_plan& P, cudaStream_t s, seir_range r) {
-  const size_t smem = (upd_smem_bytes(A.T, A.Mp) + 15) / 16 * 16 + sizeof(double) * A.T;
+static int launch_update_kernel(seir_chains* c, const upd_args& A, upd_plan P, cudaStream_t s, seir_range r) {
+  static int keepwin = -1;
+  if (keepwin < 0) {
+    const char* e = getenv("SEIR_UPD_KEEPWIN");  // 0: rescan the window in every occult update (A/B measurements)
+    keepwin = e ? atoi(e) : 1;
+  }
+  P.keep_window = (P.nit > 1 && keepwin) ? 1 : 0;
+  const size_t smem = upd_wcnt_offset(A.T, A.Mp) + (P.keep_window ? sizeof(int) * 2 * (size_t)A.Mp : 0);
   static size_t attr_dev[SEIR_MAX_DEVICES] = {0};  // (the opt-in is per device)
   size_t& attr = attr_dev[c->model->device % SEIR_MAX_DEVICES];
   const int sms = c->model->sms;

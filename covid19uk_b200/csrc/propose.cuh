@@ -27,10 +27,19 @@
 // ---- phase A: cnt[m] = days with target events (moves: whole series, cached; occults: inside the window) --------------
 // Every thread of the CTA calls; returns H = metapopulations with cnt > 0 (valid in every thread; its barriers publish
 // cnt[]).  `redw`: shared int [nthr/32].
+// Window counts a CTA keeps across the updates of one launch (update kernel, delta.cu): cnt[target][Mp] in shared memory,
+// filled by the first occult update of a target, bumped by every commit of that target; meta = {valid[2], t0[2], t1[2]}.
+struct win_cache {
+  int* wcnt;   // [2][Mp] or NULL (nothing kept: single-update launches, the proposal kernel)
+  int* wmeta;  // [6]
+};
+
 __device__ __forceinline__ int sample_hot_counts(const chain_view& g, const seir_update_cfg& cfg, const int* nzd, int* cnt,
-                                                 int* redw) {
+                                                 int* redw, const win_cache wc = win_cache{nullptr, nullptr}) {
   const int Mp = g.Mp, tid = threadIdx.x, nthr = blockDim.x;
   int hot = 0;
+  bool fill_keep = false;
+  const int w0 = cfg.t0, w1 = min(cfg.t1, g.T);
   if (cfg.kind == 0) {
     for (int m = tid; m < Mp; m += nthr) {
       const int c = m < g.M ? __ldcg(nzd + m) : 0;  // maintained by ingest / commit (atomics: read at the L2)
@@ -38,25 +47,34 @@ __device__ __forceinline__ int sample_hot_counts(const chain_view& g, const seir
       hot += c > 0;
     }
   } else {
+    int* keep = wc.wcnt ? wc.wcnt + (size_t)cfg.target * Mp : nullptr;
+    const bool have = keep && wc.wmeta[cfg.target] && wc.wmeta[2 + cfg.target] == w0 && wc.wmeta[4 + cfg.target] == w1;  // (CTA-uniform)
+    fill_keep = keep && !have;
     const int* yt = yarr(g, cfg.target);
-    const int w0 = cfg.t0, w1 = min(cfg.t1, g.T);
     for (int q = tid; q < Mp / 4; q += nthr) {  // 4 consecutive metapopulations per thread (the padding holds zeros)
       int c0 = 0, c1 = 0, c2 = 0, c3 = 0;
-      for (int s0 = w0; s0 < w1; s0 += SEIR_WIN_BATCH) {
-        int4 y[SEIR_WIN_BATCH];
+      if (have) {
+        const int4 c = *reinterpret_cast<const int4*>(keep + 4 * q);
+        c0 = c.x; c1 = c.y; c2 = c.z; c3 = c.w;
+      } else {
+        for (int s0 = w0; s0 < w1; s0 += SEIR_WIN_BATCH) {
+          int4 y[SEIR_WIN_BATCH];
 #pragma unroll
-        for (int j = 0; j < SEIR_WIN_BATCH; ++j)  // independent 16-byte loads: one round trip per batch of days
-          y[j] = (s0 + j < w1) ? *reinterpret_cast<const int4*>(yt + (size_t)(s0 + j) * Mp + 4 * q) : make_int4(0, 0, 0, 0);
+          for (int j = 0; j < SEIR_WIN_BATCH; ++j)  // independent 16-byte loads: one round trip per batch of days
+            y[j] = (s0 + j < w1) ? *reinterpret_cast<const int4*>(yt + (size_t)(s0 + j) * Mp + 4 * q) : make_int4(0, 0, 0, 0);
 #pragma unroll
-        for (int j = 0; j < SEIR_WIN_BATCH; ++j) { c0 += y[j].x > 0; c1 += y[j].y > 0; c2 += y[j].z > 0; c3 += y[j].w > 0; }
+          for (int j = 0; j < SEIR_WIN_BATCH; ++j) { c0 += y[j].x > 0; c1 += y[j].y > 0; c2 += y[j].z > 0; c3 += y[j].w > 0; }
+        }
+        if (keep) *reinterpret_cast<int4*>(keep + 4 * q) = make_int4(c0, c1, c2, c3);
       }
       *reinterpret_cast<int4*>(cnt + 4 * q) = make_int4(c0, c1, c2, c3);
       hot += (c0 > 0) + (c1 > 0) + (c2 > 0) + (c3 > 0);
     }
   }
   hot = __reduce_add_sync(0xffffffffu, hot);
-  __syncthreads();
+  __syncthreads();  // (every thread has read the window record)
   if ((tid & 31) == 0) redw[tid >> 5] = hot;
+  if (fill_keep && tid == 0) { wc.wmeta[cfg.target] = 1; wc.wmeta[2 + cfg.target] = w0; wc.wmeta[4 + cfg.target] = w1; }
   __syncthreads();  // (also publishes cnt[])
   int H = 0;
   for (int w = 0; w < (nthr >> 5); ++w) H += redw[w];
