@@ -22,12 +22,12 @@
 #include "delta_common.cuh"
 #include "propose.cuh"
 
-// phase timestamps of chain 7's CTA during one iteration (build with SEIR_NVCC_EXTRA=-DSEIR_UPD_DEBUG=<iteration>, read with
-// seir_debug_upd, tools/upd_phases.py)
+// phase timestamps of chain 7's CTA during every update of a launch (build with SEIR_NVCC_EXTRA=-DSEIR_UPD_DEBUG, read with
+// seir_debug_upd -> [32 iterations][16], tools/upd_phases.py)
 #ifdef SEIR_UPD_DEBUG
-__device__ long long g_upd_dbg[32];
+__device__ long long g_upd_dbg[32 * 16];
 __device__ int g_upd_it;
-#define UTM(k) do { if (blockIdx.x == 7 && threadIdx.x == 0 && g_upd_it == SEIR_UPD_DEBUG) { long long t_; asm volatile("mov.u64 %0, %%globaltimer;" : "=l"(t_)); g_upd_dbg[k] = t_; } } while (0)
+#define UTM(k) do { if (blockIdx.x == 7 && threadIdx.x == 0) { long long t_; asm volatile("mov.u64 %0, %%globaltimer;" : "=l"(t_)); g_upd_dbg[(g_upd_it & 31) * 16 + (k)] = t_; } } while (0)
 #else
 #define UTM(k) do { } while (0)
 #endif
@@ -598,13 +598,13 @@ __global__ void __launch_bounds__(UPD_THREADS, MINB) seir_update_kernel(upd_args
     __syncthreads();  // the next update reads what this one wrote
     UTM(11);
 #ifdef SEIR_UPD_DEBUG
-    if (blockIdx.x == 7 && threadIdx.x == 0 && it == SEIR_UPD_DEBUG) { g_upd_dbg[12] = acc; g_upd_dbg[13] = u.npts; g_upd_dbg[14] = u.valid; }
+    if (blockIdx.x == 7 && threadIdx.x == 0) { long long* d_ = g_upd_dbg + (it & 31) * 16; d_[12] = acc; d_[13] = u.npts; d_[14] = u.valid; }
 #endif
   }
 }
 
 #ifdef SEIR_UPD_DEBUG
-extern "C" int seir_debug_upd(long long* h) { return (int)cudaMemcpyFromSymbol(h, g_upd_dbg, sizeof(long long) * 32); }
+extern "C" int seir_debug_upd(long long* h) { return (int)cudaMemcpyFromSymbol(h, g_upd_dbg, sizeof(long long) * 32 * 16); }
 #endif
 
 static upd_args make_upd_args(seir_chains* c, int* d_proposal, double* d_log_u) {

@@ -102,14 +102,14 @@ __device__ __forceinline__ double tj_warp_sum4_transposed(const double (&a)[4]) 
 // accumulators per round: 8-wide shuffle butterflies cost 80 SHFL per warp), then an ordered pass over the warp partials.
 // Bitwise reproducible; every thread returns with the totals.
 template <int NTHR>
-__device__ __forceinline__ void tj_block_sum(double (&v)[TJ_NACC], double* tile, double (*red)[TJ_NACC]);
+__device__ __forceinline__ void tj_block_sum(double (&v)[TJ_NACC], double* mytile, double (*red)[TJ_NACC]);
 
 struct tj_smem {  // carved from dynamic shared memory after the ring
   double *u, *p, *g, *im;                    // [P]
   double *pa, *gam, *yir, *rir, *col, *cs;   // [Tp]
-  double* rowp;                              // [NCW / 2][Mp] row-sum partials of half of the warps (one evaluation)
+  double* rowp;                              // [Mp] this warp's row-sum partials (one evaluation), inside its day slots
   double* pm;                                // [Mp] per-metapopulation rate factors of the evaluation
-  double* tile;                              // [NCW][TJ_DAYS][32] column-sum tiles of the warps
+  double* tile;                              // [TJ_DAYS][32] this warp's reduce tile, inside its day slots
   double (*red)[TJ_NACC];                    // [NCW]
   double* sc;                                // [16]
 };
@@ -124,7 +124,7 @@ static size_t tj_state_bytes(int nthr, int T, int Mp, int P) {  // everything af
   return b + 128;
 }
 
-enum { TSC_PSI = 0, TSC_SIGMA, TSC_DPSI, TSC_DSIG, TSC_G0, TSC_G1, TSC_PRIOR, TSC_BETA, TSC_GAMMA0, TSC_GAMMA1, TSC_ALPHA0 };
+enum { TSC_PSI = 0, TSC_SIGMA, TSC_DPSI, TSC_DSIG, TSC_G0, TSC_G1, TSC_PRIOR, TSC_BETA, TSC_GAMMA0, TSC_GAMMA1, TSC_ALPHA0, TSC_VAL };
 
 struct tj_cell_ctx {
   int T, Mp;
@@ -241,17 +241,21 @@ __device__ __forceinline__ void tj_cp_commit() { asm volatile("cp.async.commit_g
 template <int N>
 __device__ __forceinline__ void tj_cp_wait() { asm volatile("cp.async.wait_group %0;" ::"n"(N) : "memory"); }
 
-template <int NTHR>
-__device__ __forceinline__ void tj_block_sum(double (&v)[TJ_NACC], double* tile, double (*red)[TJ_NACC]) {
+// this warp's totals of the TJ_NACC accumulators -> red[warp][]
+__device__ __forceinline__ void tj_warp_sums(const double (&v)[TJ_NACC], double* mytile, double (*red)[TJ_NACC]) {
   const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
   static_assert(TJ_NACC == 2 * TJ_DAYS, "two rounds of the 4-wide tile reduce");
-  double* mytile = tile + warp * (TJ_DAYS * 32);
 #pragma unroll
   for (int r = 0; r < 2; ++r) {
     const double c4[TJ_DAYS] = {v[4 * r], v[4 * r + 1], v[4 * r + 2], v[4 * r + 3]};
     const double tot = tj_col_reduce(c4, mytile);
     if ((lane & 7) == 0) red[warp][4 * r + (lane >> 3)] = tot;
   }
+}
+
+template <int NTHR>
+__device__ __forceinline__ void tj_block_sum(double (&v)[TJ_NACC], double* mytile, double (*red)[TJ_NACC]) {
+  tj_warp_sums(v, mytile, red);
   tj_bar(NTHR);
 #pragma unroll
   for (int i = 0; i < TJ_NACC; ++i) {
@@ -282,9 +286,10 @@ __global__ void TJ_BOUNDS seir_hmc_traj_kernel(const traj_args A, const ll_coefs
     sm.pm = q; q += Mp;
     sm.red = reinterpret_cast<double (*)[TJ_NACC]>(q); q += (size_t)NCW * TJ_NACC;
     sm.sc = q;
-    // the reductions between the cell phases reuse the day slots (no copy is in flight then)
-    sm.rowp = reinterpret_cast<double*>(smraw);
-    sm.tile = sm.rowp + (size_t)(NCW / 2) * Mp;
+    // the reductions between the cell phases reuse the day slots (no copy of the warp is in flight then): every warp keeps
+    // its row-sum partials [Mp] and its reduce tile [TJ_DAYS][32] at the start of ITS OWN two slots
+    sm.rowp = reinterpret_cast<double*>(smraw + (size_t)warp * 2 * slot_bytes);
+    sm.tile = sm.rowp + Mp;
   }
   unsigned char* scratch = A.scratch + (size_t)blockIdx.x * T * Mp * 16;
   const int nmine = (A.nb - (int)blockIdx.x + (int)gridDim.x - 1) / (int)gridDim.x;  // chains of this CTA: b0 + blockIdx.x + k gridDim.x
@@ -302,6 +307,13 @@ __global__ void TJ_BOUNDS seir_hmc_traj_kernel(const traj_args A, const ll_coefs
     act[q] = m < Mp;
     la_m[q] = act[q] ? A.la[m] : 0.0;
     rN_m[q] = act[q] ? A.rN[m] : 0.0;  // (0 in the padding)
+  }
+  int car_e0[MPT], car_e1[MPT];  // CSR row extents of this thread's metapopulations (CAR precision matrix)
+#pragma unroll
+  for (int q = 0; q < MPT; ++q) {
+    const int m = tid + q * NTHR;
+    car_e0[q] = m < M ? A.car_indptr[m] : 0;
+    car_e1[q] = m < M ? A.car_indptr[m + 1] : 0;
   }
   const double epsdt = A.eps * A.dt;
   const unsigned long long magic = (unsigned long long)__double_as_longlong(K.k[13]);  // 2^52: bit pattern 0x4330000000000000
@@ -346,10 +358,19 @@ __global__ void TJ_BOUNDS seir_hmc_traj_kernel(const traj_args A, const ll_coefs
       const bool last = i == L + 1;
       const bool want_val = i == 0 || i == L;
       TJT(8 + i * 8 + 0);
-      // ---------------- A: parameter-derived factors ----------------
+      // ---------------- A: parameter-derived factors (ONE barrier) ----------------
+      // Independent pieces on separate warps, nothing waits for another warp inside the phase:
+      //   warp 0          inclusive scan of alpha_t, then (same warp) exp(alpha path) dt of every day
+      //   warp 1          bijector, scalar priors, ILDJ
+      //   last T threads  the I->R rate and the I->R sufficient-statistic terms (they depend on the raw u[3], u[4] only)
+      //   every thread    its metapopulation's rate factor (sigma recomputed per thread: the same function of u[1]) and CAR row
       const double* alpha_t = sm.u + 6;
       const double* sp = sm.u + 6 + (T - 1);
-      if (warp == 0) {  // inclusive scan of alpha_t: lanes own consecutive chunks, shuffle scan over the chunk totals
+      const double eps_m = 2.220446049250313e-16;
+      double acc[TJ_NACC];
+#pragma unroll
+      for (int a = 0; a < TJ_NACC; ++a) acc[a] = 0.0;
+      if (warp == 0) {  // lanes own consecutive chunks, shuffle scan over the chunk totals
         const int n = T - 1, chunk = (n + 31) / 32;
         const int c0 = min(n, lane * chunk), c1 = min(n, c0 + chunk);
         double tot = 0.0;
@@ -365,8 +386,16 @@ __global__ void TJ_BOUNDS seir_hmc_traj_kernel(const traj_args A, const ll_coefs
           run += alpha_t[j];
           sm.cs[j] = run;
         }
+        __syncwarp();
+        const double alpha0 = sm.u[5];
+        for (int t = lane; t < T; t += 32) {
+          const int kk = A.aidx[t];
+          const double a = (kk < 0) ? alpha0 : alpha0 + sm.cs[kk];
+          const double ea = exp(a);
+          sm.pa[t] = ea * A.dt;
+          if (last) A.pa[(size_t)b * T + t] = ea;
+        }
       } else if (warp == 1) {  // scalars: bijector (inference.py:525-535), scalar priors (model_spec.py:140-198), ILDJ -- one per lane
-        const double eps_m = 2.220446049250313e-16;
         const double u0 = sm.u[0], u1 = sm.u[1];
         double r = 0.0;
         if (lane == 0) r = tj_softplus(u0) + eps_m;                    // psi
@@ -396,90 +425,68 @@ __global__ void TJ_BOUNDS seir_hmc_traj_kernel(const traj_args A, const ll_coefs
           sm.sc[TSC_G0] = 1.0 - dpsi; sm.sc[TSC_G1] = 1.0 - dsig; sm.sc[TSC_PRIOR] = prior;
           sm.sc[TSC_BETA] = sm.u[2]; sm.sc[TSC_GAMMA0] = sm.u[3]; sm.sc[TSC_GAMMA1] = sm.u[4]; sm.sc[TSC_ALPHA0] = sm.u[5];
         }
+        if (last) {
+          if (lane < SEIR_NSCAL) {
+            double v = 0.0;
+            if (lane == SC_PSI) v = psi;
+            if (lane == SC_SIGMA) v = sigma;
+            if (lane == SC_BETA) v = sm.u[2];
+            if (lane == SC_GAMMA0) v = sm.u[3];
+            if (lane == SC_GAMMA1) v = sm.u[4];
+            if (lane == SC_ALPHA0) v = sm.u[5];
+            if (lane == SC_DPSI_DU) v = dpsi;
+            if (lane == SC_DSIGMA_DU) v = dsig;
+            A.scal[(size_t)b * SEIR_NSCAL + lane] = v;
+          }
+          for (int t = lane; t < T; t += 32) A.psiW[(size_t)b * T + t] = psi * A.W[t];
+        }
       }
-      // CAR prior: (Q sp)_m and the quadratic form (model_spec.py:171-181); parameter-only, independent of the scalars
+      for (int t = NTHR - 1 - tid; t < T; t += NTHR) {  // (tail threads first: warps 0 and 1 have their own work)
+        const double gt = exp(sm.u[3] + sm.u[4] * A.wk[t]);
+        sm.gam[t] = gt;
+        if (last) {
+          A.gam[(size_t)b * T + t] = gt;
+          A.logpir[(size_t)b * T + t] = log(-expm1(-gt * A.dt));
+        } else {
+          const double yv = sm.yir[t], rv = sm.rir[t];
+          if (want_val) {
+            double term = -rv * gt * A.dt;
+            if (yv > 0.0) term += yv * log(-expm1(-gt * A.dt));
+            acc[4] += term;
+          }
+          double d = -rv;
+          if (yv > 0.0) d += yv / expm1(gt * A.dt);
+          d *= A.dt * gt;
+          acc[5] += d;
+          acc[6] += d * A.wk[t];
+        }
+      }
+      // per metapopulation: rate factor; CAR prior (Q sp)_m and the quadratic form (model_spec.py:171-181)
+      const double beta = sm.u[2], sigma = tj_softplus(sm.u[1]) + eps_m;
       double carq[MPT];
-      double acc[TJ_NACC];
-#pragma unroll
-      for (int a = 0; a < TJ_NACC; ++a) acc[a] = 0.0;
 #pragma unroll
       for (int q = 0; q < MPT; ++q) {
         const int m = tid + q * NTHR;
         carq[q] = 0.0;
+        double pmq = 0.0;
         if (m < M) {
           double r = 0.0;
-          for (int e = A.car_indptr[m]; e < A.car_indptr[m + 1]; ++e) r += A.car_values[e] * sp[A.car_indices[e]];
+          for (int e = car_e0[q]; e < car_e1[q]; ++e) r += __ldg(A.car_values + e) * sp[__ldg(A.car_indices + e)];
           carq[q] = r;
           acc[7] -= 0.5 * sp[m] * r;
+          pmq = exp(beta * la_m[q] + sigma * sp[m]) * rN_m[q];
+        }
+        if (act[q]) {
+          sm.pm[m] = pmq;  // for the cell phase, where lanes own metapopulations lane + 32 k
+          if (last) A.pm[(size_t)b * Mp + m] = pmq;
         }
       }
       if (want_val)
         for (int j = tid; j < T - 1; j += NTHR) acc[7] += tj_normal_lp(alpha_t[j], 0.005);
-      tj_bar(NTHR);  // cs[], sc[] published
+      tj_bar(NTHR);  // cs[], sc[], pa[], gam[], pm[] published
       TJT(8 + i * 8 + 1);
-      const double psi = sm.sc[TSC_PSI], sigma = sm.sc[TSC_SIGMA], beta = sm.sc[TSC_BETA];
-      double pm_m[MPT];
-#pragma unroll
-      for (int q = 0; q < MPT; ++q) {
-        const int m = tid + q * NTHR;
-        pm_m[q] = (m < M) ? exp(beta * la_m[q] + sigma * sp[m]) * rN_m[q] : 0.0;
-        if (act[q]) sm.pm[m] = pm_m[q];  // for the cell phase, where lanes own metapopulations lane + 32 k
-      }
-      // per day, two tasks on separate threads (tail warps first: every thread also has its pm factors to do):
-      //   task 0  exp(alpha path) dt
-      //   task 1  the I->R rate and the I->R sufficient-statistic terms (value: acc[4]; gradient: acc[5], acc[6])
-      for (int tt = NTHR - 1 - tid; tt < 2 * T; tt += NTHR) {
-        const int task = tt >= T, t = task ? tt - T : tt;
-        if (task == 0) {
-          const int kk = A.aidx[t];
-          const double a = (kk < 0) ? sm.sc[TSC_ALPHA0] : sm.sc[TSC_ALPHA0] + sm.cs[kk];
-          const double ea = exp(a);
-          sm.pa[t] = ea * A.dt;
-          if (last) {
-            A.pa[(size_t)b * T + t] = ea;
-            A.psiW[(size_t)b * T + t] = psi * A.W[t];
-          }
-        } else {
-          const double gt = exp(sm.sc[TSC_GAMMA0] + sm.sc[TSC_GAMMA1] * A.wk[t]);
-          sm.gam[t] = gt;
-          if (last) {
-            A.gam[(size_t)b * T + t] = gt;
-            A.logpir[(size_t)b * T + t] = log(-expm1(-gt * A.dt));
-          } else {
-            const double yv = sm.yir[t], rv = sm.rir[t];
-            if (want_val) {
-              double term = -rv * gt * A.dt;
-              if (yv > 0.0) term += yv * log(-expm1(-gt * A.dt));
-              acc[4] += term;
-            }
-            double d = -rv;
-            if (yv > 0.0) d += yv / expm1(gt * A.dt);
-            d *= A.dt * gt;
-            acc[5] += d;
-            acc[6] += d * A.wk[t];
-          }
-        }
-      }
-      if (last) {
-#pragma unroll
-        for (int q = 0; q < MPT; ++q)
-          if (act[q]) A.pm[(size_t)b * Mp + tid + q * NTHR] = pm_m[q];
-        if (tid < SEIR_NSCAL) {
-          double v = 0.0;
-          if (tid == SC_PSI) v = psi;
-          if (tid == SC_SIGMA) v = sigma;
-          if (tid == SC_BETA) v = beta;
-          if (tid == SC_GAMMA0) v = sm.sc[TSC_GAMMA0];
-          if (tid == SC_GAMMA1) v = sm.sc[TSC_GAMMA1];
-          if (tid == SC_ALPHA0) v = sm.sc[TSC_ALPHA0];
-          if (tid == SC_DPSI_DU) v = sm.sc[TSC_DPSI];
-          if (tid == SC_DSIGMA_DU) v = sm.sc[TSC_DSIG];
-          A.scal[(size_t)b * SEIR_NSCAL + tid] = v;
-        }
-        tj_bar(NTHR);
-        break;
-      }
-      tj_bar(NTHR);  // pa[] published
+      if (last) break;
+      const double psi = sm.sc[TSC_PSI];
       TJT(8 + i * 8 + 2);
 
       // ---------------- B: the cells ----------------
@@ -586,43 +593,35 @@ __global__ void TJ_BOUNDS seir_hmc_traj_kernel(const traj_args A, const ll_coefs
         which ^= 1;
       }
       if (i == 0) __threadfence();  // (this thread's scratch writes of evaluation 0, read back by its own copies from evaluation 1 on)
-      tj_bar(NTHR);  // every warp is done with its slots: the reductions below reuse that memory
-
-      // row sums: every warp's partials -> shared memory (half of the warps at a time: the buffer holds NCW / 2 rows) -> thread
-      // <-> metapopulation adds the warps in order
-      double row[MPT];
+      // row sums: every warp leaves its partials at the start of its OWN slots (its copies have all landed), one barrier,
+      // then thread <-> metapopulation adds the warps in order
 #pragma unroll
-      for (int q = 0; q < MPT; ++q) row[q] = 0.0;
-#pragma unroll
-      for (int half = 0; half < 2; ++half) {
-        if (half) tj_bar(NTHR);  // (the first half has been read)
-        if (warp / (NCW / 2) == half)
-#pragma unroll
-          for (int kk = 0; kk < KM; ++kk) sm.rowp[(warp - half * (NCW / 2)) * Mp + lane + 32 * kk] = rowr[kk];
-        tj_bar(NTHR);
-#pragma unroll
-        for (int q = 0; q < MPT; ++q)
-          if (act[q])
-            for (int w = 0; w < NCW / 2; ++w) row[q] += sm.rowp[w * Mp + tid + q * NTHR];
-      }
-
+      for (int kk = 0; kk < KM; ++kk) sm.rowp[lane + 32 * kk] = rowr[kk];
+      tj_bar(NTHR);  // every warp is done with its slots; partials and col[] published; s_ovf settled
       TJT(8 + i * 8 + 3);
       // ---------------- C: reductions, gradient ----------------
+      if (i == 0) packed = !s_ovf;
       acc[0] = val;
       acc[1] = psig;
 #pragma unroll
       for (int q = 0; q < MPT; ++q) {
         const int m = tid + q * NTHR;
-        if (m < M) {
-          acc[2] += row[q] * la_m[q];
-          acc[3] += row[q] * sp[m];
-          sm.g[6 + (T - 1) + m] = sigma * row[q] - carq[q];
+        if (act[q]) {
+          const double* rp = reinterpret_cast<const double*>(smraw) + m;
+          double r = 0.0;
+#pragma unroll
+          for (int w = 0; w < NCW; ++w) r += rp[(size_t)w * (2 * slot_bytes / 8)];
+          if (m < M) {
+            acc[2] += r * la_m[q];
+            acc[3] += r * sp[m];
+            sm.g[6 + (T - 1) + m] = sigma * r - carq[q];
+          }
         }
       }
-      tj_block_sum<NTHR>(acc, sm.tile, sm.red);  // (its barriers also publish col[]; s_ovf is settled)
+      tj_warp_sums(acc, sm.tile, sm.red);
+      tj_bar(NTHR);  // red[] published
       TJT(8 + i * 8 + 4);
-      if (i == 0) packed = !s_ovf;
-      if (warp == 0) {  // suffix sums of the per-day column sums (lanes own consecutive chunks of days; lane 31 first)
+      if (warp == 1) {  // meanwhile: suffix sums of the per-day column sums (lanes own consecutive chunks of days; lane 31 first)
         const int chunk = (T + 31) / 32;
         const int c0 = min(T, lane * chunk), c1 = min(T, c0 + chunk);
         double cs = 0.0;
@@ -643,25 +642,35 @@ __global__ void TJ_BOUNDS seir_hmc_traj_kernel(const traj_args A, const ll_coefs
           const int tf = A.tfirst[j];
           sm.g[6 + j] = (tf < T ? sm.col[tf] : 0.0) - alpha_t[j] * 40000.0;  // d/dx of Normal(0, 0.005)
         }
+        if (lane == 0) sm.g[5] = sm.col[0] - sm.u[5] * 0.01;
+      }
+      if (warp == 0) {  // totals in warp order (lane a <-> accumulator a), then the six scalar gradient entries and the value
+        double tot = 0.0;
+        if (lane < TJ_NACC)
+#pragma unroll
+          for (int w = 0; w < NCW; ++w) tot += sm.red[w][lane];
+        const double t0 = __shfl_sync(0xffffffffu, tot, 0), t1 = __shfl_sync(0xffffffffu, tot, 1), t2 = __shfl_sync(0xffffffffu, tot, 2);
+        const double t3 = __shfl_sync(0xffffffffu, tot, 3), t4 = __shfl_sync(0xffffffffu, tot, 4), t5 = __shfl_sync(0xffffffffu, tot, 5);
+        const double t6 = __shfl_sync(0xffffffffu, tot, 6), t7 = __shfl_sync(0xffffffffu, tot, 7);
         if (lane == 0) {
-          const double u2 = sm.u[2], u3 = sm.u[3], u4 = sm.u[4], u5 = sm.u[5];
-          const double gpsi = acc[1] + 2.0 / psi - 10.0;
-          const double gsg = acc[3] - sigma * 100.0;
+          const double u2 = sm.u[2], u3 = sm.u[3], u4 = sm.u[4];
+          const double gpsi = t1 + 2.0 / psi - 10.0;
+          const double gsg = t3 - sigma * 100.0;
           sm.g[0] = gpsi * sm.sc[TSC_DPSI] + sm.sc[TSC_G0];
           sm.g[1] = gsg * sm.sc[TSC_DSIG] + sm.sc[TSC_G1];
-          sm.g[2] = acc[2] - u2;
-          sm.g[3] = acc[5] - u3 * 1.0e-4;
-          sm.g[4] = acc[6] - u4 * 1.0e-4;
-          sm.g[5] = sm.col[0] - u5 * 0.01;
+          sm.g[2] = t2 - u2;
+          sm.g[3] = t5 - u3 * 1.0e-4;
+          sm.g[4] = t6 - u4 * 1.0e-4;
+          if (want_val) {
+            double v = sm.sc[TSC_PRIOR] + t7 - (double)M * HALF_LOG_2PI - A.car_log_det_scale;
+            v += t0 + llc + ei_term + t4;
+            if (flag != 0) v = -INFINITY;
+            sm.sc[TSC_VAL] = v;
+          }
         }
       }
-      double v = 0.0;
-      if (want_val) {
-        v = sm.sc[TSC_PRIOR] + acc[7] - (double)M * HALF_LOG_2PI - A.car_log_det_scale;
-        v += acc[0] + llc + ei_term + acc[4];
-        if (flag != 0) v = -INFINITY;
-      }
-      tj_bar(NTHR);  // g[] complete
+      tj_bar(NTHR);  // g[] (and the value) complete
+      const double v = want_val ? sm.sc[TSC_VAL] : 0.0;
       TJT(8 + i * 8 + 5);
 
       // ---------------- D: leapfrog ----------------
