@@ -68,9 +68,11 @@ struct traj_args {
 #ifdef SEIR_TRAJ_DEBUG
 __device__ long long g_tj_dbg[1024];
 #define TJT(k) do { if (blockIdx.x == 0 && threadIdx.x == 0 && kchain == 0 && (k) < 1024) g_tj_dbg[(k)] = clock64(); } while (0)
+#define TJW(k) do { if (blockIdx.x == 0 && (threadIdx.x & 31) == 0 && kchain == 0 && i == 5) g_tj_dbg[512 + (k) * 16 + (threadIdx.x >> 5)] = clock64(); } while (0)
 extern "C" int seir_debug_traj(long long* h) { return (int)cudaMemcpyFromSymbol(h, g_tj_dbg, sizeof(long long) * 1024); }
 #else
 #define TJT(k) do { } while (0)
+#define TJW(k) do { } while (0)
 #endif
 
 __device__ __forceinline__ void tj_bar(int nthr) { asm volatile("bar.sync 1, %0;" ::"r"(nthr) : "memory"); }
@@ -112,6 +114,7 @@ struct tj_smem {  // carved from dynamic shared memory after the ring
   double* tile;                              // [TJ_DAYS][32] this warp's reduce tile, inside its day slots
   double (*red)[TJ_NACC];                    // [NCW]
   double* sc;                                // [16]
+  int *aidx, *tfirst;                        // [Tp] day -> alpha_t segment, alpha_t segment -> first day (model constants)
 };
 
 static size_t tj_state_bytes(int nthr, int T, int Mp, int P) {  // everything after the ring
@@ -121,10 +124,11 @@ static size_t tj_state_bytes(int nthr, int T, int Mp, int P) {  // everything af
   b += sizeof(double) * (size_t)Mp;                             // pm
   b += sizeof(double) * (size_t)(nthr / 32) * TJ_NACC;          // red
   b += sizeof(double) * 16;                                     // sc
+  b += sizeof(int) * 2 * (size_t)Tp;                            // aidx tfirst
   return b + 128;
 }
 
-enum { TSC_PSI = 0, TSC_SIGMA, TSC_DPSI, TSC_DSIG, TSC_G0, TSC_G1, TSC_PRIOR, TSC_BETA, TSC_GAMMA0, TSC_GAMMA1, TSC_ALPHA0, TSC_VAL };
+enum { TSC_PSI = 0, TSC_SIGMA, TSC_DPSI, TSC_DSIG, TSC_G0, TSC_G1, TSC_PRIOR, TSC_BETA, TSC_GAMMA0, TSC_GAMMA1, TSC_ALPHA0, TSC_VAL, TSC_2_OVER_PSI };
 
 struct tj_cell_ctx {
   int T, Mp;
@@ -285,7 +289,8 @@ __global__ void TJ_BOUNDS seir_hmc_traj_kernel(const traj_args A, const ll_coefs
     sm.pa = q; q += Tp; sm.gam = q; q += Tp; sm.yir = q; q += Tp; sm.rir = q; q += Tp; sm.col = q; q += Tp; sm.cs = q; q += Tp;
     sm.pm = q; q += Mp;
     sm.red = reinterpret_cast<double (*)[TJ_NACC]>(q); q += (size_t)NCW * TJ_NACC;
-    sm.sc = q;
+    sm.sc = q; q += 16;
+    sm.aidx = reinterpret_cast<int*>(q); sm.tfirst = sm.aidx + Tp;
     // the reductions between the cell phases reuse the day slots (no copy of the warp is in flight then): every warp keeps
     // its row-sum partials [Mp] and its reduce tile [TJ_DAYS][32] at the start of ITS OWN two slots
     sm.rowp = reinterpret_cast<double*>(smraw + (size_t)warp * 2 * slot_bytes);
@@ -294,6 +299,10 @@ __global__ void TJ_BOUNDS seir_hmc_traj_kernel(const traj_args A, const ll_coefs
   unsigned char* scratch = A.scratch + (size_t)blockIdx.x * T * Mp * 16;
   const int nmine = (A.nb - (int)blockIdx.x + (int)gridDim.x - 1) / (int)gridDim.x;  // chains of this CTA: b0 + blockIdx.x + k gridDim.x
   if (tid < 128) tab[tid] = A.logtab[tid];
+  for (int t = tid; t < T; t += NTHR) {
+    sm.aidx[t] = A.aidx[t];
+    if (t < T - 1) sm.tfirst[t] = A.tfirst[t];
+  }
   __syncthreads();
 
   // ------------------------------------------------------------------------------------------------------------------
@@ -358,18 +367,20 @@ __global__ void TJ_BOUNDS seir_hmc_traj_kernel(const traj_args A, const ll_coefs
       const bool last = i == L + 1;
       const bool want_val = i == 0 || i == L;
       TJT(8 + i * 8 + 0);
-      // ---------------- A: parameter-derived factors (ONE barrier) ----------------
-      // Independent pieces on separate warps, nothing waits for another warp inside the phase:
-      //   warp 0          inclusive scan of alpha_t, then (same warp) exp(alpha path) dt of every day
+      // ---------------- A: parameter-derived factors ----------------
+      // First part, independent pieces on separate warps (nothing waits for another warp):
+      //   warp 0          inclusive scan of alpha_t
       //   warp 1          bijector, scalar priors, ILDJ
       //   last T threads  the I->R rate and the I->R sufficient-statistic terms (they depend on the raw u[3], u[4] only)
-      //   every thread    its metapopulation's rate factor (sigma recomputed per thread: the same function of u[1]) and CAR row
+      //   every thread    the CAR row of its metapopulation
+      // Second part (needs the scan and the scalars): exp(alpha path) per day, rate factor per metapopulation.
       const double* alpha_t = sm.u + 6;
       const double* sp = sm.u + 6 + (T - 1);
       const double eps_m = 2.220446049250313e-16;
       double acc[TJ_NACC];
 #pragma unroll
       for (int a = 0; a < TJ_NACC; ++a) acc[a] = 0.0;
+      TJW(0);
       if (warp == 0) {  // lanes own consecutive chunks, shuffle scan over the chunk totals
         const int n = T - 1, chunk = (n + 31) / 32;
         const int c0 = min(n, lane * chunk), c1 = min(n, c0 + chunk);
@@ -386,23 +397,14 @@ __global__ void TJ_BOUNDS seir_hmc_traj_kernel(const traj_args A, const ll_coefs
           run += alpha_t[j];
           sm.cs[j] = run;
         }
-        __syncwarp();
-        const double alpha0 = sm.u[5];
-        for (int t = lane; t < T; t += 32) {
-          const int kk = A.aidx[t];
-          const double a = (kk < 0) ? alpha0 : alpha0 + sm.cs[kk];
-          const double ea = exp(a);
-          sm.pa[t] = ea * A.dt;
-          if (last) A.pa[(size_t)b * T + t] = ea;
-        }
       } else if (warp == 1) {  // scalars: bijector (inference.py:525-535), scalar priors (model_spec.py:140-198), ILDJ -- one per lane
         const double u0 = sm.u[0], u1 = sm.u[1];
         double r = 0.0;
-        if (lane == 0) r = tj_softplus(u0) + eps_m;                    // psi
-        else if (lane == 1) r = tj_softplus(u1) + eps_m;               // sigma_space
-        else if (lane == 2) r = tj_sigmoid(u0);                        // d psi / d u0
-        else if (lane == 3) r = tj_sigmoid(u1);
-        else if (want_val) {
+        if (lane < 4) {  // psi, sigma_space, d psi / d u0, d sigma / d u1: the same instructions on every lane (no divergence)
+          const double x = (lane & 1) ? u1 : u0;
+          const double spx = tj_softplus(x) + eps_m, sgx = tj_sigmoid(x);
+          r = lane < 2 ? spx : sgx;
+        } else if (want_val) {
           if (lane == 4) r = -tj_softplus(-u0) - tj_softplus(-u1);     // ILDJ
           else if (lane == 5) r = tj_normal_lp(sm.u[5], 10.0) + tj_normal_lp(sm.u[2], 1.0);
           else if (lane == 6) r = tj_normal_lp(sm.u[3], 100.0) + tj_normal_lp(sm.u[4], 100.0);
@@ -424,6 +426,7 @@ __global__ void TJ_BOUNDS seir_hmc_traj_kernel(const traj_args A, const ll_coefs
           sm.sc[TSC_PSI] = psi; sm.sc[TSC_SIGMA] = sigma; sm.sc[TSC_DPSI] = dpsi; sm.sc[TSC_DSIG] = dsig;
           sm.sc[TSC_G0] = 1.0 - dpsi; sm.sc[TSC_G1] = 1.0 - dsig; sm.sc[TSC_PRIOR] = prior;
           sm.sc[TSC_BETA] = sm.u[2]; sm.sc[TSC_GAMMA0] = sm.u[3]; sm.sc[TSC_GAMMA1] = sm.u[4]; sm.sc[TSC_ALPHA0] = sm.u[5];
+          sm.sc[TSC_2_OVER_PSI] = 2.0 / psi;
         }
         if (last) {
           if (lane < SEIR_NSCAL) {
@@ -441,6 +444,7 @@ __global__ void TJ_BOUNDS seir_hmc_traj_kernel(const traj_args A, const ll_coefs
           for (int t = lane; t < T; t += 32) A.psiW[(size_t)b * T + t] = psi * A.W[t];
         }
       }
+      TJW(1);
       for (int t = NTHR - 1 - tid; t < T; t += NTHR) {  // (tail threads first: warps 0 and 1 have their own work)
         const double gt = exp(sm.u[3] + sm.u[4] * A.wk[t]);
         sm.gam[t] = gt;
@@ -461,30 +465,59 @@ __global__ void TJ_BOUNDS seir_hmc_traj_kernel(const traj_args A, const ll_coefs
           acc[6] += d * A.wk[t];
         }
       }
-      // per metapopulation: rate factor; CAR prior (Q sp)_m and the quadratic form (model_spec.py:171-181)
-      const double beta = sm.u[2], sigma = tj_softplus(sm.u[1]) + eps_m;
+      TJW(2);
+      // CAR prior: (Q sp)_m and the quadratic form (model_spec.py:171-181); parameter-only, independent of the scalars
       double carq[MPT];
 #pragma unroll
       for (int q = 0; q < MPT; ++q) {
         const int m = tid + q * NTHR;
         carq[q] = 0.0;
-        double pmq = 0.0;
         if (m < M) {
           double r = 0.0;
-          for (int e = car_e0[q]; e < car_e1[q]; ++e) r += __ldg(A.car_values + e) * sp[__ldg(A.car_indices + e)];
+          for (int e = car_e0[q]; e < car_e1[q]; e += 4) {  // four entries of the row per round trip; same order of additions
+            double cv[4];
+            int ci[4];
+#pragma unroll
+            for (int j = 0; j < 4; ++j) {
+              const int ee = min(e + j, car_e1[q] - 1);
+              cv[j] = __ldg(A.car_values + ee);
+              ci[j] = __ldg(A.car_indices + ee);
+            }
+#pragma unroll
+            for (int j = 0; j < 4; ++j)
+              if (e + j < car_e1[q]) r += cv[j] * sp[ci[j]];
+          }
           carq[q] = r;
           acc[7] -= 0.5 * sp[m] * r;
-          pmq = exp(beta * la_m[q] + sigma * sp[m]) * rN_m[q];
-        }
-        if (act[q]) {
-          sm.pm[m] = pmq;  // for the cell phase, where lanes own metapopulations lane + 32 k
-          if (last) A.pm[(size_t)b * Mp + m] = pmq;
         }
       }
       if (want_val)
         for (int j = tid; j < T - 1; j += NTHR) acc[7] += tj_normal_lp(alpha_t[j], 0.005);
-      tj_bar(NTHR);  // cs[], sc[], pa[], gam[], pm[] published
+      TJW(3);
+      tj_bar(NTHR);  // cs[], sc[], gam[] published
+      TJW(4);
       TJT(8 + i * 8 + 1);
+      // per day: exp(alpha path) dt (tail threads first); per metapopulation: rate factor -- two independent exponentials
+      const double beta = sm.sc[TSC_BETA], sigma = sm.sc[TSC_SIGMA];
+      for (int t = NTHR - 1 - tid; t < T; t += NTHR) {
+        const int kk = sm.aidx[t];
+        const double alpha0 = sm.sc[TSC_ALPHA0];
+        const double ea = exp((kk < 0) ? alpha0 : alpha0 + sm.cs[kk]);
+        sm.pa[t] = ea * A.dt;
+        if (last) A.pa[(size_t)b * T + t] = ea;
+      }
+#pragma unroll
+      for (int q = 0; q < MPT; ++q) {
+        const int m = tid + q * NTHR;
+        if (act[q]) {
+          const double pmq = (m < M) ? exp(beta * la_m[q] + sigma * sp[m]) * rN_m[q] : 0.0;
+          sm.pm[m] = pmq;  // for the cell phase, where lanes own metapopulations lane + 32 k
+          if (last) A.pm[(size_t)b * Mp + m] = pmq;
+        }
+      }
+      TJW(5);
+      tj_bar(NTHR);  // pm[], pa[] published
+      TJW(6);
       if (last) break;
       const double psi = sm.sc[TSC_PSI];
       TJT(8 + i * 8 + 2);
@@ -639,7 +672,7 @@ __global__ void TJ_BOUNDS seir_hmc_traj_kernel(const traj_args A, const ll_coefs
         }
         __syncwarp();
         for (int j = lane; j < T - 1; j += 32) {
-          const int tf = A.tfirst[j];
+          const int tf = sm.tfirst[j];
           sm.g[6 + j] = (tf < T ? sm.col[tf] : 0.0) - alpha_t[j] * 40000.0;  // d/dx of Normal(0, 0.005)
         }
         if (lane == 0) sm.g[5] = sm.col[0] - sm.u[5] * 0.01;
@@ -654,7 +687,7 @@ __global__ void TJ_BOUNDS seir_hmc_traj_kernel(const traj_args A, const ll_coefs
         const double t6 = __shfl_sync(0xffffffffu, tot, 6), t7 = __shfl_sync(0xffffffffu, tot, 7);
         if (lane == 0) {
           const double u2 = sm.u[2], u3 = sm.u[3], u4 = sm.u[4];
-          const double gpsi = t1 + 2.0 / psi - 10.0;
+          const double gpsi = t1 + sm.sc[TSC_2_OVER_PSI] - 10.0;
           const double gsg = t3 - sigma * 100.0;
           sm.g[0] = gpsi * sm.sc[TSC_DPSI] + sm.sc[TSC_G0];
           sm.g[1] = gsg * sm.sc[TSC_DSIG] + sm.sc[TSC_G1];

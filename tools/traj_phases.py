@@ -23,3 +23,9 @@ for i in range(L + 2):
     d = np.diff(s)
     print(f"[feed wait of warp 0: {int(h[8 + i * 8 + 7])}] ", end="")
     print(f"eval {i:2d}: start {s[0]-t0:8d}  " + "  ".join(f"{n} {int(x)}" for n, x in zip(names, d) if x > 0 and x < 10**9))
+
+w = h[512:512 + 7 * 16].reshape(7, 16)[:, :12]
+if w[0, 0] > 0:
+    print("per-warp stamps of evaluation 5, phase A (cycles since warp 0 entered): rows = enter, role part done, I->R done, CAR done (barrier arrival), barrier left, pm done, barrier left")
+    for k in range(7):
+        print("  ", k, " ".join("%6d" % (x - w[0, 0]) for x in w[k]))
