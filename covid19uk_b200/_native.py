@@ -17,7 +17,7 @@ PART_SEIR = 1
 PART_PRIORS = 2
 PART_ILDJ = 4
 PART_JOINT = 7
-ABI_VERSION = 9
+ABI_VERSION = 10
 
 
 class SeirSpec(ctypes.Structure):
@@ -100,6 +100,7 @@ SIGNATURES = {
     "seir_export_contraction": (c_int, [c_void_p, c_void_p, c_void_p]),
     "seir_chain_flags": (c_int, [c_void_p, c_void_p, c_void_p]),
     "seir_launch_count": (c_int64, []),
+    "seir_sm_partition_info": (c_int, [c_int, c_void_p, c_void_p]),
 }
 
 

@@ -640,7 +640,7 @@ static int launch_update_kernel(seir_chains* c, const upd_args& A, upd_plan P, c
     SEIR_CUDA(cudaFuncSetAttribute(seir_update_kernel<4>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
     attr = smem;
   }
-  const bool many = forced ? forced >= 4 : r.nb > 2 * sms;
+  const bool many = forced ? forced >= 4 : (c->upd_minb_hint >= 4 || r.nb > 2 * sms);
   if (many) seir_update_kernel<4><<<r.nb, UPD_THREADS, smem, s>>>(A, P, r.b0);
   else seir_update_kernel<2><<<r.nb, UPD_THREADS, smem, s>>>(A, P, r.b0);
   seir_count_launch(1);

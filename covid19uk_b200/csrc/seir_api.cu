@@ -270,6 +270,14 @@ void seir_chains_destroy(seir_chains* c) {
     }
     cudaEventDestroy(c->grp_fork);
   }
+  if (c->part_ready) {
+    for (int g = 0; g < SEIR_MAX_GROUPS; ++g) {
+      cudaStreamDestroy(c->part_hs[g]);
+      cudaStreamDestroy(c->part_us[g]);
+      cudaEventDestroy(c->part_hdone[g]);
+      cudaEventDestroy(c->part_udone[g]);
+    }
+  }
   cudaFree(c->d_prop); cudaFree(c->d_logu); cudaFree(c->d_stage_events); cudaFree(c->d_stage_theta);
   cudaFree(c->d_stage_out); cudaFree(c->d_stage_u16);
   if (c->h_stage_u16) cudaFreeHost(c->h_stage_u16);

@@ -134,6 +134,11 @@ struct seir_chains {
   cudaStream_t grp_stream[SEIR_MAX_GROUPS];
   cudaEvent_t grp_fork, grp_join[SEIR_MAX_GROUPS], grp_stagger[SEIR_MAX_GROUPS];
   int grp_ready;
+  // SM-partitioned burst (sweep.cu): per chain group one stream in the trajectory partition and one in the update partition
+  cudaStream_t part_hs[SEIR_MAX_GROUPS], part_us[SEIR_MAX_GROUPS];
+  cudaEvent_t part_hdone[SEIR_MAX_GROUPS], part_udone[SEIR_MAX_GROUPS];
+  int part_ready;
+  int upd_minb_hint;  // 4: the update kernel is launched in its four-CTAs-per-SM variant whatever the group size (partitioned burst)
   // staging for the host-buffer entry points
   double *d_stage_events, *d_stage_theta, *d_stage_out;
   unsigned short *d_stage_u16, *h_stage_u16;  // narrowed events: device copy and pinned host staging

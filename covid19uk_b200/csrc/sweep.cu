@@ -4,6 +4,7 @@
 //                        GibbsKernel([S->E move, E->I move, S->E occult, E->I occult]))) ])
 // (inference.py:219-228, mcmc_kernel_factory.py:116-168).  Everything is enqueued on one stream with no host
 // synchronisation; random numbers come from Philox streams keyed by the global chain id.
+#include <cuda.h>  // types of the green-context driver API (entry points are resolved at run time: no link dependency)
 #include <stdlib.h>
 
 #include "seir_internal.cuh"
@@ -56,6 +57,8 @@ static int env_int(const char* name, int dflt) {
   const char* e = getenv(name);
   return e ? atoi(e) : dflt;
 }
+
+static int forced_groups_env() { return env_int("SEIR_SWEEP_GROUPS", 0) > 0 || env_int("SEIR_BURST_GROUPS", 0) > 0; }
 
 static int sweep_groups(seir_chains* c, bool burst) {
   static int forced = -2, forced_burst = -2;
@@ -133,6 +136,126 @@ static int enqueue_sweep(seir_chains* c, const seir_sweep_spec* sp, unsigned swe
   return SEIR_OK;
 }
 
+// ---- SM partitions --------------------------------------------------------------------------------------------------------
+// At 256 UK chains the two halves of a sweep want different things from an SM: a trajectory CTA fills it (384 x 168 registers,
+// 200 KB of shared memory; 0.42 ms per chain), the 20 dependent discrete updates of a chain are one small latency-bound CTA
+// (0.7 ms, two per SM).  Chain groups on plain streams overlap them badly: the update CTAs of a group spread over all SMs (the
+// block scheduler fills breadth-first) and every SM that holds even one of them cannot take a trajectory CTA.  Green contexts
+// (driver API, CUDA 12.4+) fix WHERE the two kinds run: the device's SMs are split into a trajectory partition and an update
+// partition; each chain group gets one stream in either, linked by events, and the groups drift apart by themselves.  Memory,
+// modules and events are those of the primary context.  Results do not depend on any of this (absolute chain indices, Philox
+// keyed by chain): tests/test_gpu_sweep.py.
+// The schedule is then bound by SM x time: (256 x 0.42 + 256 x 0.68 / 2) / 148 = 1.30 ms per sweep, which is what it
+// measures (1.31 ms; plain chain groups 1.40-1.45 ms).  Measured at 256 UK chains, ms per sweep (U = SMs of the update
+// partition, G = chain groups, n = update CTAs per SM the kernel variant is bounded for):
+//   U 64 G 8 n 2: 1.31 (default)   U 60 G 8 n 2: 1.31   U 72 G 8 n 2: 1.39   U 48 G 8 n 2: 1.43   U 64 G 6 n 2: 1.37   U 64 G 4 n 2: 1.38
+//   U 40 G 5 n 4: 1.52   U 48 G 8 n 4: 1.43   U 56 G 8 n 4: 1.43   U 32 G 5 n 4: 1.66   (85-register variant, n 3: 1.31-1.35)
+//   SEIR_SM_PARTITION=0 disables; SEIR_PART_U, SEIR_PART_GROUPS, SEIR_PART_MINB select U, G, n.
+struct sm_partition {
+  int state;  // 0: not tried, 1: ready, -1: unavailable
+  CUgreenCtx h, u;
+  int h_sms, u_sms;
+};
+static sm_partition g_part[SEIR_MAX_DEVICES];
+
+typedef CUresult (*pfn_cuDeviceGet)(CUdevice*, int);
+typedef CUresult (*pfn_cuDeviceGetDevResource)(CUdevice, CUdevResource*, CUdevResourceType);
+typedef CUresult (*pfn_cuDevSmResourceSplitByCount)(CUdevResource*, unsigned int*, const CUdevResource*, CUdevResource*, unsigned int, unsigned int);
+typedef CUresult (*pfn_cuDevResourceGenerateDesc)(CUdevResourceDesc*, CUdevResource*, unsigned int);
+typedef CUresult (*pfn_cuGreenCtxCreate)(CUgreenCtx*, CUdevResourceDesc, CUdevice, unsigned int);
+typedef CUresult (*pfn_cuGreenCtxStreamCreate)(CUstream*, CUgreenCtx, unsigned int, int);
+
+template <typename F>
+static bool driver_fn(const char* name, F* fn) {
+  void* p = nullptr;
+  cudaDriverEntryPointQueryResult q;
+  if (cudaGetDriverEntryPoint(name, &p, cudaEnableDefault, &q) != cudaSuccess || q != cudaDriverEntryPointSuccess || !p) {
+    cudaGetLastError();
+    return false;
+  }
+  *fn = reinterpret_cast<F>(p);
+  return true;
+}
+
+static sm_partition* partition_of(const seir_model* m) {
+  sm_partition* pt = &g_part[m->device % SEIR_MAX_DEVICES];
+  if (pt->state != 0) return pt->state > 0 ? pt : nullptr;
+  pt->state = -1;
+  if (!env_int("SEIR_SM_PARTITION", 1)) return nullptr;
+  pfn_cuDeviceGet dget;
+  pfn_cuDeviceGetDevResource dres;
+  pfn_cuDevSmResourceSplitByCount dsplit;
+  pfn_cuDevResourceGenerateDesc ddesc;
+  pfn_cuGreenCtxCreate dctx;
+  if (!driver_fn("cuDeviceGet", &dget) || !driver_fn("cuDeviceGetDevResource", &dres) || !driver_fn("cuDevSmResourceSplitByCount", &dsplit) ||
+      !driver_fn("cuDevResourceGenerateDesc", &ddesc) || !driver_fn("cuGreenCtxCreate", &dctx))
+    return nullptr;
+  CUdevice dev;
+  CUdevResource all, upart, rest;
+  if (dget(&dev, m->device) != CUDA_SUCCESS || dres(dev, &all, CU_DEV_RESOURCE_TYPE_SM) != CUDA_SUCCESS) return nullptr;
+  const int want_u = env_int("SEIR_PART_U", 64);
+  if (want_u < 8 || (int)all.sm.smCount < want_u + 32) return nullptr;
+  unsigned n = 1;
+  if (dsplit(&upart, &n, &all, &rest, 0, (unsigned)want_u) != CUDA_SUCCESS || n != 1 || rest.sm.smCount == 0) return nullptr;
+  CUdevResourceDesc du, dh;
+  if (ddesc(&du, &upart, 1) != CUDA_SUCCESS || ddesc(&dh, &rest, 1) != CUDA_SUCCESS) return nullptr;
+  if (dctx(&pt->u, du, dev, CU_GREEN_CTX_DEFAULT_STREAM) != CUDA_SUCCESS) return nullptr;
+  if (dctx(&pt->h, dh, dev, CU_GREEN_CTX_DEFAULT_STREAM) != CUDA_SUCCESS) return nullptr;
+  pt->u_sms = (int)upart.sm.smCount;
+  pt->h_sms = (int)rest.sm.smCount;
+  pt->state = 1;
+  return pt;
+}
+
+extern "C" int seir_sm_partition_info(int device, int* trajectory_sms, int* update_sms) {
+  if (device < 0) return 0;
+  const sm_partition* pt = &g_part[device % SEIR_MAX_DEVICES];
+  if (pt->state <= 0) return 0;
+  if (trajectory_sms) *trajectory_sms = pt->h_sms;
+  if (update_sms) *update_sms = pt->u_sms;
+  return 1;
+}
+
+static int partition_streams(seir_chains* c, sm_partition* pt) {
+  if (c->part_ready) return SEIR_OK;
+  pfn_cuGreenCtxStreamCreate dstream;
+  if (!driver_fn("cuGreenCtxStreamCreate", &dstream)) return seir_set_error(SEIR_ERR_CUDA, "cuGreenCtxStreamCreate is not available");
+  for (int g = 0; g < SEIR_MAX_GROUPS; ++g) {
+    CUstream hs, us;
+    if (dstream(&hs, pt->h, CU_STREAM_NON_BLOCKING, 0) != CUDA_SUCCESS || dstream(&us, pt->u, CU_STREAM_NON_BLOCKING, 0) != CUDA_SUCCESS)
+      return seir_set_error(SEIR_ERR_CUDA, "cuGreenCtxStreamCreate failed");
+    c->part_hs[g] = reinterpret_cast<cudaStream_t>(hs);
+    c->part_us[g] = reinterpret_cast<cudaStream_t>(us);
+    SEIR_CUDA(cudaEventCreateWithFlags(&c->part_hdone[g], cudaEventDisableTiming));
+    SEIR_CUDA(cudaEventCreateWithFlags(&c->part_udone[g], cudaEventDisableTiming));
+  }
+  c->part_ready = 1;
+  return SEIR_OK;
+}
+
+// the two halves of a sweep on their own streams (the partitioned burst)
+static int enqueue_sweep_hmc(seir_chains* c, const seir_sweep_spec* sp, unsigned sweep_index, seir_range r, cudaStream_t hs, double* d_u,
+                             const double* d_step, const double* d_inv_mass, double* d_tlp, const sweep_out& o, int group) {
+  const int B = c->B, P = c->model->P;
+  SEIR_TRY(seir_launch_hmc_momentum(c, sp->seed, sp->chain_offset, sweep_index, d_inv_mass, c->d_hmc_p, hs, r));
+  SEIR_TRY(seir_launch_log_uniform(r, sp->seed, sp->chain_offset, sweep_index, 0x48u, c->d_logu, hs));
+  double* tlp_row4 = o.upd_tlp ? o.upd_tlp + (size_t)4 * B : nullptr;
+  SEIR_TRY(seir_launch_hmc_traj(c, d_u, c->d_logu, d_step, d_inv_mass, sp->num_leapfrog_steps, d_tlp, tlp_row4, o.hmc_accept, o.hmc_dbg, hs, r, group));
+  if (o.draws)
+    SEIR_CUDA(cudaMemcpyAsync(o.draws + (size_t)r.b0 * P, d_u + (size_t)r.b0 * P, sizeof(double) * (size_t)r.nb * P, cudaMemcpyDeviceToDevice, hs));
+  return SEIR_OK;
+}
+
+static int enqueue_sweep_updates(seir_chains* c, const seir_sweep_spec* sp, unsigned sweep_index, seir_range r, cudaStream_t us, double* d_tlp,
+                                 const sweep_out& o) {
+  seir_update_cfg cfg4[4];
+  for (int slot = 0; slot < 4; ++slot) slot_cfg(sp, slot, &cfg4[slot]);
+  SEIR_TRY(seir_launch_update_rounds(c, cfg4, sp->num_event_time_updates, sp->seed, sp->chain_offset, sweep_index * 64u, c->d_prop, c->d_logu,
+                                     d_tlp, o.upd_accept, o.upd_tlp, o.upd_trace, us, r));
+  if (o.events_u16) SEIR_TRY(seir_launch_export_events_u16_range(c, o.events_u16, o.overflow, us, r));
+  return SEIR_OK;
+}
+
 static int sweep_prepare(seir_chains* c, int G, seir_range* rg) {
   int rc;
   if ((rc = sweep_alloc(c)) != SEIR_OK) return rc;
@@ -198,6 +321,41 @@ int seir_launch_sweep_burst(seir_chains* c, const seir_sweep_spec* sp, unsigned 
                      (d_events_u16 && kept) ? d_events_u16 + (size_t)k * ev_per : nullptr,
                      d_overflow};
   };
+  // SM-partitioned schedule: the trajectory kernel applies, there are discrete updates to hide, and enough chains for the groups
+  sm_partition* pt = nullptr;
+  if (forced_groups_env() == 0 && B >= 192 && num_sweeps >= 2 && sp->num_event_time_updates > 0 && seir_hmc_traj_applies(c)) pt = partition_of(c->model);
+  if (pt) {
+    int PG = env_int("SEIR_PART_GROUPS", 8);
+    if (PG < 2) PG = 2;
+    if (PG > SEIR_MAX_GROUPS) PG = SEIR_MAX_GROUPS;
+    SEIR_TRY(partition_streams(c, pt));
+    seir_range pg[SEIR_MAX_GROUPS];
+    for (int g = 0; g < PG; ++g) {
+      const int b0 = (int)((long long)B * g / PG), b1 = (int)((long long)B * (g + 1) / PG);
+      pg[g] = seir_range{b0, b1 - b0};
+    }
+    SEIR_TRY(sweep_streams(c));  // (grp_fork)
+    SEIR_CUDA(cudaEventRecord(c->grp_fork, s));
+    for (int g = 0; g < PG; ++g) SEIR_CUDA(cudaStreamWaitEvent(c->part_hs[g], c->grp_fork, 0));
+    auto one = [&](int k, int g) -> int {
+      const sweep_out o = out_of(k);
+      if (k > 0) SEIR_CUDA(cudaStreamWaitEvent(c->part_hs[g], c->part_udone[g], 0));  // the group's previous sweep
+      SEIR_TRY(enqueue_sweep_hmc(c, sp, sweep_index0 + (unsigned)k, pg[g], c->part_hs[g], d_u, d_step, d_inv_mass, d_tlp, o, g));
+      SEIR_CUDA(cudaEventRecord(c->part_hdone[g], c->part_hs[g]));
+      SEIR_CUDA(cudaStreamWaitEvent(c->part_us[g], c->part_hdone[g], 0));
+      SEIR_TRY(enqueue_sweep_updates(c, sp, sweep_index0 + (unsigned)k, pg[g], c->part_us[g], d_tlp, o));
+      SEIR_CUDA(cudaEventRecord(c->part_udone[g], c->part_us[g]));
+      return SEIR_OK;
+    };
+    c->upd_minb_hint = env_int("SEIR_PART_MINB", 2);  // update CTAs per SM of their partition the kernel variant is bounded for (2 or 4)
+    int rc = SEIR_OK;
+    for (int k = 0; k < num_sweeps && rc == SEIR_OK; ++k)  // sweep by sweep ACROSS the groups: every stream has work queued early
+      for (int g = 0; g < PG && rc == SEIR_OK; ++g) rc = one(k, g);
+    c->upd_minb_hint = 0;
+    if (rc != SEIR_OK) return rc;
+    for (int g = 0; g < PG; ++g) SEIR_CUDA(cudaStreamWaitEvent(s, c->part_udone[g], 0));
+    return rc;
+  }
   if (G == 1) {
     for (int k = 0; k < num_sweeps; ++k)
       SEIR_TRY(enqueue_sweep(c, sp, sweep_index0 + (unsigned)k, rg[0], s, d_u, d_step, d_inv_mass, d_tlp, out_of(k), nullptr, 0, 0));

@@ -27,7 +27,7 @@
 extern "C" {
 #endif
 
-#define SEIR_B200_ABI_VERSION 9
+#define SEIR_B200_ABI_VERSION 10
 
 typedef enum seir_status {
   SEIR_OK = 0,
@@ -284,6 +284,11 @@ int seir_run_stage(seir_chains* chains, int stage, const double* d_events, const
 
 /* number of kernels launched by this library since load (bench.py's gpu_launches) */
 int64_t seir_launch_count(void);
+
+/* SM partitions of seir_mcmc_burst on `device` (green contexts: a trajectory partition and a discrete-update partition,
+ * DESIGN.md 3.1): returns 1 and the two SM counts when a burst has set them up, 0 when the plain chain-group schedule is in
+ * use (small chain counts, SEIR_SM_PARTITION=0, a driver without green contexts).  No reference counterpart. */
+int seir_sm_partition_info(int device, int* trajectory_sms, int* update_sms);
 
 #ifdef __cplusplus
 }

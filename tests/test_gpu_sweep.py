@@ -160,6 +160,44 @@ def test_burst_equals_sweep_by_sweep_bitwise():
     eng.close()
 
 
+def test_sm_partitioned_burst_equals_sweep_by_sweep_bitwise():
+    """From 192 chains on, seir_mcmc_burst runs the trajectory kernels and the discrete-update kernels of 5 chain groups in two
+    SM partitions (green contexts), the groups drifting apart over the burst.  Against n single sweeps (one
+    stream, no partitions): bit-identical parameters, target log-probs, events, draws and traces -- and the partitions must
+    really have been set up (a silent fall-back to the plain schedule would make this test vacuous)."""
+    import ctypes
+
+    from covid19uk_b200 import _native as nat
+    from covid19uk_b200.inference.sampler import ChainSet
+
+    M, T, B, n = 40, 40, 200, 5  # (Mp = 64: the persistent trajectory kernel applies)
+    pb, eng, om, u = _setup(M, T, B, seed=13)
+    cfg = dict(CFG, dmax=min(CFG["dmax"], T - 1))
+    t_range = [T - 21, T]
+    cs = ChainSet(eng, pb["events"], u, cfg, t_range, seed=23, chain_offset=0)
+    (us, _), trace = cs.sample(n, step_size=1e-3, burst=True)
+    h, usm = ctypes.c_int(0), ctypes.c_int(0)
+    import torch
+    assert nat.load().seir_sm_partition_info(torch.cuda.current_device(), ctypes.byref(h), ctypes.byref(usm)) == 1
+    assert h.value >= 32 and usm.value >= 8 and h.value + usm.value == torch.cuda.get_device_properties(0).multi_processor_count
+    ev, u1, tlp1 = cs.events().cpu().numpy(), cs.u.cpu().numpy().copy(), cs.tlp.cpu().numpy().copy()
+    us = us.cpu().numpy().copy()
+    tr1 = {k: {f: v.cpu().numpy().copy() for f, v in d.items()} for k, d in trace.items()}
+    cs2 = ChainSet(eng, pb["events"], u, cfg, t_range, seed=23, chain_offset=0)
+    (us2, _), trace2 = cs2.sample(n, step_size=1e-3, burst=False)
+    assert np.array_equal(cs2.u.cpu().numpy(), u1)
+    assert np.array_equal(cs2.tlp.cpu().numpy(), tlp1)
+    assert np.array_equal(cs2.events().cpu().numpy(), ev)
+    assert np.array_equal(us2.cpu().numpy(), us)
+    for k, d in trace2.items():
+        for f, v in d.items():
+            assert np.array_equal(v.cpu().numpy(), tr1[k][f]), (k, f)
+    # the incrementally maintained target log-prob against a from-scratch evaluation of the final state
+    fresh = eng.log_prob(ev, cs.u, nat.THETA_UNCONSTRAINED, nat.PART_JOINT).cpu().numpy()
+    np.testing.assert_allclose(tlp1, fresh, rtol=1e-10)
+    eng.close()
+
+
 def test_update_kernel_register_variants_agree_bitwise():
     """seir_update_kernel is compiled for two occupancy targets (SEIR_UPD_MINB: 2 = 126 registers, the default up to two
     chains per SM; 4 = 64 registers, picked for large chain counts).  Same arithmetic: chains, events and traces must be
