@@ -411,7 +411,7 @@ def run_native(args):
 
     tmpdir = tempfile.mkdtemp(prefix="seir_bench_")
     post = {"p": None, "off": 0}
-    e2e_thin, e2e_keep, e2e_bursts = 2 * max(1, args.sweeps), 2, 2
+    e2e_thin, e2e_keep, e2e_bursts = 20, 2, 2  # thin 20: the operational setting (lancs_space_model_concept.tex:325-329)
 
     def sink(tree):
         t_w0 = time.perf_counter()
@@ -558,7 +558,7 @@ def main():
     ap.add_argument("--warmup", type=int, default=3)
     ap.add_argument("--impl", default="native", choices=["native", "reference"])
     ap.add_argument("--chains", type=int, default=256, help="chains per GPU")
-    ap.add_argument("--sweeps", type=int, default=10, help="MCMC sweeps per timed burst")
+    ap.add_argument("--sweeps", type=int, default=50, help="MCMC sweeps per timed burst (the reference's num_burst_samples is 100, example_config.yaml:32)")
     ap.add_argument("--sweep-step-size", type=float, default=2e-5)
     ap.add_argument("--tuned-dmax", type=int, default=16, help="event-time proposals of the second sweeps/s figure")
     ap.add_argument("--tuned-nmax", type=int, default=16)

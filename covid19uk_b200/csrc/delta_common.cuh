@@ -6,7 +6,8 @@
 #include "seir_internal.cuh"
 
 #ifndef UPD_THREADS
-#define UPD_THREADS 256  // one CTA per chain (measured: 256 threads 2.12-2.29 ms per UK sweep, 512 threads 2.26-2.30 ms)
+#define UPD_THREADS 256  // one CTA per chain (measured, ms per UK sweep: round 1 256 threads 2.12-2.29, 512 threads 2.26-2.30; round 2 with SM
+                         // partitions 256 threads 1.31, 128 threads at four CTAs per SM 1.43-1.46: a chain's update latency grows from 0.68 to ~1.0 ms)
 #endif
 #define SLAB_DAYS 8
 
