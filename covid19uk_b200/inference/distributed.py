@@ -156,7 +156,10 @@ def gather_to_rank0(tree, num_chains: int, chain_dim: int = 1, group=None, dst: 
         if nbytes * cmax > max_bytes or x.shape[0] == 0:
             small.append(None)
             continue
-        rows = (x.to(torch.uint8) if x.dtype == torch.bool else x).reshape(x.shape[0], -1).view(torch.uint8)  # [B_local, nbytes]
+        flat = (x.to(torch.uint8) if x.dtype == torch.bool else x).reshape(x.shape[0], -1)
+        if flat.stride() != (flat.shape[1], 1):  # (a size-1 axis keeps whatever stride it had: "contiguous", but not viewable as bytes)
+            flat = torch.empty(flat.shape, dtype=flat.dtype, device=flat.device).copy_(flat)
+        rows = flat.view(torch.uint8)  # [B_local, nbytes]
         small.append((tuple(x.shape[1:]), t.dtype, rows.shape[1]))
         packed_rows.append(rows)
     gathered = None

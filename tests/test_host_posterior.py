@@ -195,6 +195,12 @@ def _gloo_rank0_worker(rank, world, port, total, tmp):
             post.write_results(tree["results"], first_dim_offset=w * n)
         else:
             assert tree is None
+    # a single-draw leaf cut out of a larger array: [1, B_local] whose chain axis, moved to the front, is "contiguous" only
+    # because the size-1 axis hides its stride (a real trace of a one-sweep window looks like this)
+    one = (torch.arange(4 * cnt, dtype=torch.float64).reshape(4, cnt) + 1000.0 * off)[2:3]
+    g1 = gather_to_rank0({"x": one + ids[None, :].to(torch.float64)}, total, chain_dim=1)
+    if rank == 0:
+        torch.save(g1["x"], os.path.join(tmp, "single.pt"))
     # bounded slices: the same gather with a tiny budget per message
     from covid19uk_b200.inference import distributed as dd
     counts = [shard_chains(total, world, r)[1] for r in range(world)]
@@ -225,5 +231,9 @@ def test_rank0_gather_streams_one_posterior_file(tmp_path):
         assert np.array_equal(ev[w * n:(w + 1) * n], want)
         assert np.array_equal(f["samples/psi"][w * n:(w + 1) * n], ids[None, :] + 0.5 * w + np.arange(n)[:, None])
         assert np.array_equal(f["results/hmc/is_accepted"][w * n:(w + 1) * n], (ids[None, :] + np.arange(n)[:, None] + w) % 2 == 0)
+    one = torch.load(os.path.join(tmp_path, "single.pt")).numpy()
+    from covid19uk_b200.inference.distributed import shard_chains
+    want_one = np.concatenate([np.arange(2 * c, 3 * c) + 1000.0 * o + np.arange(o, o + c) for o, c in (shard_chains(total, world, r) for r in range(world))])
+    assert one.shape == (1, total) and np.array_equal(one[0], want_one)
     sl = torch.load(os.path.join(tmp_path, "sliced.pt"))
     assert np.array_equal(sl.numpy(), ev[n:2 * n])
