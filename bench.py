@@ -449,7 +449,7 @@ def run_native(args):
         hbm_peak, peak_src = _peaks()
         grad_d = torch.empty_like(theta_d)
         kw = dict(events=events_d, theta=theta_d, kind=kind, parts=parts, out=out_d, grad=grad_d)
-        names = {0: "seir_ingest_kernel", 7: "seir_coef_kernel", 1: "seir_contract_i8_kernel (+ seir_i8_split_kernel)", 2: "seir_theta_prep_kernel",
+        names = {0: "seir_ingest_kernel", 7: "seir_coef_kernel", 1: "seir_contract_i8_longk_kernel (+ seir_i8_split_kernel)", 2: "seir_theta_prep_kernel",
                  3: "seir_loglik_kernel<false>", 5: "seir_finalize_kernel", 4: "seir_loglik_kernel<true>"}
         cold_stages = (0, 7, 1, 2, 3, 5)
         stage_ms = {s: time_stage(eng, B, s, max(K, 10), **kw) for s in cold_stages + (4, 9)}  # 9: the FP64 DMMA contraction, for comparison

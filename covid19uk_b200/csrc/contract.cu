@@ -108,7 +108,7 @@ static bool contract_uses_i8(const seir_model* m) {
   static int use_i8 = -1;
   if (use_i8 < 0) {
     const char* e = getenv("SEIR_CONTRACT_I8");  // 0: always the FP64 DMMA kernel below; default: the exact int8 tcgen05 kernel
-    use_i8 = e ? atoi(e) : 1;                    // (contract_i8.cu) wherever it applies (Mp a multiple of 128, <= 384)
+    use_i8 = e ? atoi(e) : 1;                    // (contract_i8.cu) wherever it applies (Mp a multiple of 128, <= 4096)
   }
   return use_i8 && m->i8_na > 0;
 }

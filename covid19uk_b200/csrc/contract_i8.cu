@@ -346,13 +346,157 @@ __global__ void __launch_bounds__(I8_THREADS, 1) seir_contract_i8_kernel(long lo
   if (warp == 9) asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, %1;" ::"r"(tmem_base), "r"(512u) : "memory");
 }
 
+// ---- the same contraction for long K (Mp > 384: BASELINE.json configs[4], 2000 regions) ------------------------------
+// The digit planes of a 128-row tile no longer fit shared memory (3 x 128 x 2048 B), so the loop order turns around: K blocks
+// outermost, and inside a K block EVERY digit pair (a, c).  All groups s = a - c in [-5, 2] are then live for the whole
+// tile: 8 groups x 64 int32 columns = the 512 TMEM columns, hence 128 x 64 output tiles.  One ring stage = K block h of the
+// tile's na_t planes of I (16 KB each) + of the 6 digit planes of the tile's 64 columns of Cs (8 KB each: the first or
+// second half of the [128 columns x 128 B] block the host laid out); two stages of 96 KB.  Every operand byte is fetched
+// once per tile.  Same exact integers, same epilogue order of additions as seir_contract_i8_kernel.
+#define I8L_BN 64
+#define I8L_STAGES 2
+#define I8L_A_BYTES (3 * I8_KBLOCK)               // up to three planes of I per stage
+#define I8L_B_BYTES (I8_NB * I8L_BN * I8_KB)     // six half blocks of Cs per stage
+#define I8L_STAGE_BYTES (I8L_A_BYTES + I8L_B_BYTES)
+#define I8L_IDESC ((2u << 4) | (0u << 7) | (1u << 10) | ((uint32_t)(I8L_BN >> 3) << 17) | ((uint32_t)(I8_BM >> 4) << 24))
+
+__global__ void __launch_bounds__(I8_THREADS, 1) seir_contract_i8_longk_kernel(long long R, int Mp, int na, int ntiles,
+                                                                               const unsigned char* __restrict__ planes,
+                                                                               const int* __restrict__ flags,
+                                                                               const signed char* __restrict__ Bd,
+                                                                               const double* __restrict__ colscale, double* __restrict__ Bc) {
+  extern __shared__ __align__(1024) unsigned char smem[];
+  __shared__ uint64_t full_b[I8L_STAGES], empty_b[I8L_STAGES], acc_full, acc_free;
+  __shared__ uint32_t tmem_base_s;
+  const int nkb = Mp / I8_KB;
+  const size_t plane_a = (size_t)I8_BM * Mp;  // bytes of one digit plane of a row tile
+  const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
+  const int ncol_tiles = Mp / I8L_BN, nct128 = Mp / I8_BN;
+  if (tid == 0) {
+    for (int s = 0; s < I8L_STAGES; ++s) { mbar_init(&full_b[s], 1); mbar_init(&empty_b[s], 1); }
+    mbar_init(&acc_full, 1);                      // the commit behind the tile's last MMA
+    mbar_init(&acc_free, I8_EPI_THREADS / 32);   // every epilogue warp has read the accumulators
+    asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+  }
+  if (warp == 9) {
+    asm volatile("tcgen05.alloc.cta_group::1.sync.aligned.shared::cta.b32 [%0], %1;" ::"r"(smem_u32(&tmem_base_s)), "r"(512u) : "memory");
+    asm volatile("tcgen05.relinquish_alloc_permit.cta_group::1.sync.aligned;" ::: "memory");
+  }
+  tc_fence_before();
+  __syncthreads();
+  tc_fence_after();
+  const uint32_t tmem_base = tmem_base_s;
+
+  if (warp < 8) {
+    // ================= epilogue =================
+    const int half = warp >> 2;             // which 32 of the tile's 64 columns this warp drains
+    const int lane_base = (warp & 3) * 32;  // TMEM lanes (= tile rows) this warp may access
+    int it = 0;
+    for (int tile = blockIdx.x; tile < ntiles; tile += gridDim.x, ++it) {
+      const int rb = tile / ncol_tiles, ct = tile - rb * ncol_tiles;
+      const long long r0 = (long long)rb * I8_BM;
+      int na_t = 1;
+      for (int a = 1; a < na; ++a)
+        if (__ldg(flags + rb * 4 + a)) na_t = a + 1;
+      mbar_wait(&acc_full, (uint32_t)it & 1u);
+      tc_fence_after();
+      double out[32];
+#pragma unroll
+      for (int j = 0; j < 32; ++j) out[j] = 0.0;
+      for (int s = na_t - 1; s >= -(I8_NB - 1); --s) {
+        const double w = ldexp(1.0, 8 * (s - 1));  // 256^(s-1), exact
+        const uint32_t taddr = tmem_base + ((uint32_t)lane_base << 16) + (uint32_t)((s + I8_NB - 1) * I8L_BN + half * 32);
+        uint32_t v[32];
+        tc_ld32(taddr, v);
+        tc_wait_ld();
+#pragma unroll
+        for (int j = 0; j < 32; ++j) out[j] = fma(i8_int_to_double((int)v[j]), w, out[j]);
+      }
+      tc_fence_before();
+      __syncwarp();
+      if (lane == 0) mbar_arrive(&acc_free);  // the next tile's MMAs may overwrite the accumulators
+      const int c0 = ct * I8L_BN + half * 32;
+      const long long row = r0 + lane_base + lane;
+      if (row < R) {
+        double* dst = Bc + row * Mp + c0;
+#pragma unroll
+        for (int j = 0; j < 32; j += 4) {
+          const double x0 = out[j] * colscale[c0 + j], x1 = out[j + 1] * colscale[c0 + j + 1], x2 = out[j + 2] * colscale[c0 + j + 2],
+                       x3 = out[j + 3] * colscale[c0 + j + 3];
+          asm volatile("st.global.v4.f64 [%0], {%1, %2, %3, %4};" ::"l"(dst + j), "d"(x0), "d"(x1), "d"(x2), "d"(x3) : "memory");
+        }
+      }
+    }
+  } else if (warp == 8) {
+    // ================= producer =================
+    if (lane == 0) {
+      uint32_t n = 0;
+      for (int tile = blockIdx.x; tile < ntiles; tile += gridDim.x) {
+        const int rb = tile / ncol_tiles, ct = tile - rb * ncol_tiles;
+        int na_t = 1;
+        for (int a = 1; a < na; ++a)
+          if (__ldg(flags + rb * 4 + a)) na_t = a + 1;
+        const unsigned char* a_src = planes + (size_t)rb * na * plane_a;
+        for (int h = 0; h < nkb; ++h, ++n) {
+          const int st = n % I8L_STAGES;
+          if (n >= I8L_STAGES) mbar_wait(&empty_b[st], ((n / I8L_STAGES) - 1) & 1u);
+          unsigned char* sa = smem + (size_t)st * I8L_STAGE_BYTES;
+          unsigned char* sb = sa + I8L_A_BYTES;
+          mbar_expect_tx(&full_b[st], (unsigned)(na_t * I8_KBLOCK + I8_NB * I8L_BN * I8_KB));
+          for (int a = 0; a < na_t; ++a)
+            bulk_load_1d(sa + (size_t)a * I8_KBLOCK, a_src + (size_t)a * plane_a + (size_t)h * I8_KBLOCK, (unsigned)I8_KBLOCK, &full_b[st]);
+          for (int c = 0; c < I8_NB; ++c)
+            bulk_load_1d(sb + (size_t)c * (I8L_BN * I8_KB),
+                         Bd + (((size_t)c * nct128 + (ct >> 1)) * nkb + h) * I8_KBLOCK + (size_t)(ct & 1) * (I8L_BN * I8_KB),
+                         (unsigned)(I8L_BN * I8_KB), &full_b[st]);
+        }
+      }
+    }
+  } else if (lane == 0) {
+    // ================= MMA issuer (warp 9, one thread) =================
+    uint32_t n = 0;
+    int itm = 0;
+    for (int tile = blockIdx.x; tile < ntiles; tile += gridDim.x, ++itm) {
+      int na_t = 1;
+      for (int a = 1; a < na; ++a)
+        if (__ldg(flags + (tile / ncol_tiles) * 4 + a)) na_t = a + 1;
+      if (itm > 0) {  // the epilogue has drained the previous tile
+        mbar_wait(&acc_free, (uint32_t)(itm - 1) & 1u);
+        tc_fence_after();
+      }
+      for (int h = 0; h < nkb; ++h, ++n) {
+        const int st = n % I8L_STAGES;
+        mbar_wait(&full_b[st], (n / I8L_STAGES) & 1u);
+        tc_fence_after();
+        const uint32_t sa = smem_u32(smem + (size_t)st * I8L_STAGE_BYTES), sb = sa + I8L_A_BYTES;
+        for (int c = 0; c < I8_NB; ++c) {
+          const uint64_t b_desc0 = umma_desc(sb + (uint32_t)c * (I8L_BN * I8_KB));
+          for (int a = 0; a < na_t; ++a) {
+            const uint64_t a_desc0 = umma_desc(sa + (uint32_t)a * I8_KBLOCK);
+            const uint32_t d_addr = tmem_base + (uint32_t)((a - c + I8_NB - 1) * I8L_BN);
+            const bool first = h == 0 && (c == 0 || a == 0);  // group a - c receives its first digit pair
+            tc_mma_i8(d_addr, a_desc0, b_desc0, I8L_IDESC, first ? 0u : 1u);
+#pragma unroll
+            for (int kk = 1; kk < I8_KB / 32; ++kk) tc_mma_i8(d_addr, a_desc0 + (uint64_t)kk * 2u, b_desc0 + (uint64_t)kk * 2u, I8L_IDESC, 1u);
+          }
+        }
+        tc_commit(&empty_b[st]);  // the stage is free once these MMAs have read it
+      }
+      tc_commit(&acc_full);
+    }
+  }
+  tc_fence_before();
+  __syncthreads();
+  if (warp == 9) asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, %1;" ::"r"(tmem_base), "r"(512u) : "memory");
+}
+
 // ---- host: split Cs into digit planes, once per model --------------------------------------------------------------
-// Returns 0 and fills the device arrays when the integer path applies (Mp a multiple of 128, at most 384, populations
-// below 2^21), 1 when it does not (the FP64 DMMA kernel of contract.cu is used), < 0 on a CUDA error.
+// Returns 0 and fills the device arrays when the integer path applies (Mp a multiple of 128, at most 4096, populations
+// below 2^24), 1 when it does not (the FP64 DMMA kernel of contract.cu is used), < 0 on a CUDA error.
 int seir_contract_i8_setup(seir_model* m, const double* h_cs /*[Mp][Mp], Cs[j][i]*/, double max_population) {
   m->i8_na = 0;
   const int Mp = m->Mp;
-  if (Mp % I8_BN != 0 || Mp > 384) return 1;
+  if (Mp % I8_BN != 0 || Mp > 4096) return 1;  // (Mp <= 384: seir_contract_i8_kernel; longer K: seir_contract_i8_longk_kernel)
   int na = 1;
   while (na < 6 && ldexp(1.0, 8 * na) <= max_population) ++na;  // infectious counts never exceed the population
   if (na > 3) return 1;
@@ -396,17 +540,27 @@ int seir_launch_contract_i8_range(seir_chains* c, cudaStream_t s, seir_range r) 
   const seir_model* m = c->model;
   const long long Rall = (long long)c->B * m->T, R = (long long)r.nb * m->T, row0 = (long long)r.b0 * m->T;
   if (row0 % I8_BM != 0) return seir_set_error(SEIR_ERR_BAD_ARG, "seir_launch_contract_i8_range: chain range does not start a row tile");
-  const int ntiles = (int)((R + I8_BM - 1) / I8_BM) * (m->Mp / I8_BN);
+  static int force_longk = -1;
+  if (force_longk < 0) {
+    const char* e = getenv("SEIR_I8_LONGK");  // 0: the plane-major 128 x 128 kernel where it applies (Mp <= 384; A/B timing)
+    force_longk = e ? atoi(e) : 1;
+  }
+  // the K-outermost kernel is the default for every shape: UK, 256 chains 62 us against 86 us (every operand byte fetched once,
+  // 7 rounds of 1008 half-width tiles instead of 4 rounds of 504)
+  const bool longk = m->Mp > 384 || force_longk > 0;
+  const int ntiles = (int)((R + I8_BM - 1) / I8_BM) * (m->Mp / (longk ? I8L_BN : I8_BN));
   size_t a_region = (size_t)m->i8_na * I8_BM * m->Mp;
 #if I8_STAGE_OUT > 0
   if (a_region < (size_t)I8_STAGE_OUT) a_region = I8_STAGE_OUT;
 #endif
-  const size_t smem = a_region + (size_t)I8_STAGES * I8_KBLOCK + 1024;  // (+ slack to align the dynamic base to 1024 bytes)
+  const size_t smem = longk ? (size_t)I8L_STAGES * I8L_STAGE_BYTES + 1024
+                            : a_region + (size_t)I8_STAGES * I8_KBLOCK + 1024;  // (+ slack to align the dynamic base to 1024 bytes)
   const int sms = m->sms;
-  static size_t attr_dev[SEIR_MAX_DEVICES] = {0};  // (the opt-in is per device)
-  size_t& attr = attr_dev[c->model->device % SEIR_MAX_DEVICES];
+  static size_t attr_dev[SEIR_MAX_DEVICES][2] = {{0}};  // (the opt-in is per device)
+  size_t& attr = attr_dev[c->model->device % SEIR_MAX_DEVICES][longk ? 1 : 0];
   if (attr != smem) {
-    SEIR_CUDA(cudaFuncSetAttribute(seir_contract_i8_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+    if (longk) SEIR_CUDA(cudaFuncSetAttribute(seir_contract_i8_longk_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+    else SEIR_CUDA(cudaFuncSetAttribute(seir_contract_i8_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
     attr = smem;
   }
   const int nrt_all = (int)((Rall + I8_BM - 1) / I8_BM), nrt = (int)((R + I8_BM - 1) / I8_BM), rt0 = (int)(row0 / I8_BM);
@@ -420,8 +574,12 @@ int seir_launch_contract_i8_range(seir_chains* c, cudaStream_t s, seir_range r) 
   const size_t cell0 = (size_t)row0 * m->Mp;
   SEIR_CUDA(cudaMemsetAsync(flags, 0, sizeof(int) * 4 * (size_t)nrt, s));
   seir_i8_split_kernel<<<dim3(nrt, 4), I8_EPI_THREADS, 0, s>>>(R, m->Mp, m->i8_na, c->d_I + cell0, planes, flags);
-  seir_contract_i8_kernel<<<ntiles < sms ? ntiles : sms, I8_THREADS, smem, s>>>(R, m->Mp, m->i8_na, ntiles, planes, flags, m->d_cs_i8,
-                                                                                m->d_cs_scale, c->d_Bc + cell0);
+  if (longk)
+    seir_contract_i8_longk_kernel<<<ntiles < sms ? ntiles : sms, I8_THREADS, smem, s>>>(R, m->Mp, m->i8_na, ntiles, planes, flags, m->d_cs_i8,
+                                                                                        m->d_cs_scale, c->d_Bc + cell0);
+  else
+    seir_contract_i8_kernel<<<ntiles < sms ? ntiles : sms, I8_THREADS, smem, s>>>(R, m->Mp, m->i8_na, ntiles, planes, flags, m->d_cs_i8,
+                                                                                  m->d_cs_scale, c->d_Bc + cell0);
   seir_count_launch(2);
   return seir_cuda_check(cudaGetLastError(), "seir_contract_i8_kernel");
 }
