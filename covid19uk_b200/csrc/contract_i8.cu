@@ -32,6 +32,7 @@
 // 148 SMs = 4 rounds.
 #include <math.h>
 #include <stdlib.h>
+#include <string.h>
 
 #include <vector>
 
@@ -86,6 +87,14 @@ __device__ __forceinline__ void tc_ld32(uint32_t taddr, uint32_t (&v)[32]) {
         "=r"(v[30]), "=r"(v[31])
       : "r"(taddr));
 }
+// One lane of a fully active warp.  The MMA issuer and the copy producer must be chosen THIS way: behind `if (lane == 0)` the
+// compiler treats the branch as divergent and wraps every tcgen05.mma / bulk copy (uniform-datapath instructions) in an
+// ELECT / BRA.U.ANY loop over the active lanes -- eight extra instructions and a backward branch per MMA.
+__device__ __forceinline__ bool i8_elect_one() {
+  uint32_t p;
+  asm volatile("{\n\t.reg .pred P;\n\telect.sync _|P, 0xffffffff;\n\tselp.u32 %0, 1, 0, P;\n\t}" : "=r"(p));
+  return p != 0;
+}
 __device__ __forceinline__ void tc_wait_ld() { asm volatile("tcgen05.wait::ld.sync.aligned;" ::: "memory"); }
 
 // K-major, 128-byte swizzle (cute::UMMA::SmemDescriptor bit layout; layout type SWIZZLE_128B = 2): an operand block is
@@ -108,8 +117,10 @@ __host__ __device__ __forceinline__ size_t sw128_offset(int r, int k, int nrows)
 // grid (row tiles, 4): a CTA splits a quarter of a 128-row tile; unit = (row r, 16-byte K chunk kc); a lane group of 8 consecutive rows x 4 chunks writes 512
 // bytes per plane.  Planes are stored per row tile in the 128-byte-swizzled K-major UMMA layout, so the contraction kernel
 // brings a plane into shared memory with ONE bulk copy; flags[rt][a] says whether plane a of the tile holds anything.
+// kmajor = 0: [a][K block][16 KB] (a plane is contiguous: seir_contract_i8_kernel brings it in with one copy);
+// kmajor = 1: [K block][a][16 KB] (the planes of a K block are contiguous: one copy per ring stage of the K-outermost kernel).
 __global__ void __launch_bounds__(I8_EPI_THREADS) seir_i8_split_kernel(long long R, int Mp, int na, const int* __restrict__ Ix,
-                                                                       unsigned char* __restrict__ planes, int* __restrict__ flags) {
+                                                                       unsigned char* __restrict__ planes, int* __restrict__ flags, int kmajor) {
   __shared__ int s_nz[4];
   const int tid = threadIdx.x, lane = tid & 31, rt = blockIdx.x, K = Mp;
   const long long r0 = (long long)rt * I8_BM;
@@ -124,6 +135,7 @@ __global__ void __launch_bounds__(I8_EPI_THREADS) seir_i8_split_kernel(long long
   for (int u0 = ulo + tid; u0 < uhi; u0 += 4 * I8_EPI_THREADS) {  // 4 units = 16 independent 16-byte loads in flight per thread
     int4 v[4][4];
     uint32_t off[4];
+    int kblk[4];
 #pragma unroll
     for (int b4 = 0; b4 < 4; ++b4) {
       const int u = u0 + b4 * I8_EPI_THREADS;
@@ -135,7 +147,9 @@ __global__ void __launch_bounds__(I8_EPI_THREADS) seir_i8_split_kernel(long long
 #pragma unroll
       for (int q = 0; q < 4; ++q)
         v[b4][q] = in ? __ldg(reinterpret_cast<const int4*>(Ix + gr * Mp + kc * 16 + q * 4)) : make_int4(0, 0, 0, 0);
-      off[b4] = (uint32_t)sw128_offset(r, kc * 16, I8_BM);
+      // (block-local offset; the K block index kc / 8 is applied per plane below)
+      off[b4] = (uint32_t)sw128_offset(r, (kc * 16) & 127, I8_BM);
+      kblk[b4] = (kc * 16) >> 7;
     }
 #pragma unroll
     for (int b4 = 0; b4 < 4; ++b4) {
@@ -147,7 +161,8 @@ __global__ void __launch_bounds__(I8_EPI_THREADS) seir_i8_split_kernel(long long
         o.y = ((v[b4][1].x >> sh) & 255) | (((v[b4][1].y >> sh) & 255) << 8) | (((v[b4][1].z >> sh) & 255) << 16) | (((v[b4][1].w >> sh) & 255) << 24);
         o.z = ((v[b4][2].x >> sh) & 255) | (((v[b4][2].y >> sh) & 255) << 8) | (((v[b4][2].z >> sh) & 255) << 16) | (((v[b4][2].w >> sh) & 255) << 24);
         o.w = ((v[b4][3].x >> sh) & 255) | (((v[b4][3].y >> sh) & 255) << 8) | (((v[b4][3].z >> sh) & 255) << 16) | (((v[b4][3].w >> sh) & 255) << 24);
-        *reinterpret_cast<uint4*>(dst + (size_t)a * plane_a + off[b4]) = o;
+        const size_t blk = kmajor ? ((size_t)kblk[b4] * na + a) * I8_KBLOCK : (size_t)a * plane_a + (size_t)kblk[b4] * I8_KBLOCK;
+        *reinterpret_cast<uint4*>(dst + blk + off[b4]) = o;
         nz[a] |= o.x | o.y | o.z | o.w;
       }
     }
@@ -254,7 +269,7 @@ __global__ void __launch_bounds__(I8_THREADS, 1) seir_contract_i8_kernel(long lo
     }
   } else if (warp == 8) {
     // ================= producer: planes of Cs =================
-    if (lane == 0) {
+    if (i8_elect_one()) {
       uint32_t n = 0, itp = 0;
       for (int tile = blockIdx.x; tile < ntiles; tile += gridDim.x, ++itp) {
         const int rb = tile / ncol_tiles, ct = tile - rb * ncol_tiles;
@@ -284,8 +299,8 @@ __global__ void __launch_bounds__(I8_THREADS, 1) seir_contract_i8_kernel(long lo
           }
       }
     }
-  } else if (lane == 0) {
-    // ================= MMA issuer (warp 9, one thread) =================
+  } else if (i8_elect_one()) {
+    // ================= MMA issuer (warp 9, one elected thread) =================
     uint32_t n = 0, ph_aready = 0;
     uint32_t hosted[4] = {0, 0, 0, 0};  // groups started in each accumulator slot so far (over all tiles)
     uint64_t a_desc_plane[3];
@@ -371,7 +386,7 @@ __global__ void __launch_bounds__(I8_THREADS, 1) seir_contract_i8_longk_kernel(l
   const int nkb = Mp / I8_KB;
   const size_t plane_a = (size_t)I8_BM * Mp;  // bytes of one digit plane of a row tile
   const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
-  const int ncol_tiles = Mp / I8L_BN, nct128 = Mp / I8_BN;
+  const int ncol_tiles = Mp / I8L_BN;
   if (tid == 0) {
     for (int s = 0; s < I8L_STAGES; ++s) { mbar_init(&full_b[s], 1); mbar_init(&empty_b[s], 1); }
     mbar_init(&acc_full, 1);                      // the commit behind the tile's last MMA
@@ -429,31 +444,30 @@ __global__ void __launch_bounds__(I8_THREADS, 1) seir_contract_i8_longk_kernel(l
     }
   } else if (warp == 8) {
     // ================= producer =================
-    if (lane == 0) {
+    if (i8_elect_one()) {
       uint32_t n = 0;
       for (int tile = blockIdx.x; tile < ntiles; tile += gridDim.x) {
         const int rb = tile / ncol_tiles, ct = tile - rb * ncol_tiles;
         int na_t = 1;
         for (int a = 1; a < na; ++a)
           if (__ldg(flags + rb * 4 + a)) na_t = a + 1;
-        const unsigned char* a_src = planes + (size_t)rb * na * plane_a;
+        const unsigned char* a_src = planes + (size_t)rb * na * plane_a;  // [K block][plane][16 KB] (seir_i8_split_kernel, kmajor)
+        const signed char* b_src = Bd + (size_t)ct * nkb * I8L_B_BYTES;   // [K block][digit plane][8 KB]
         for (int h = 0; h < nkb; ++h, ++n) {
           const int st = n % I8L_STAGES;
           if (n >= I8L_STAGES) mbar_wait(&empty_b[st], ((n / I8L_STAGES) - 1) & 1u);
           unsigned char* sa = smem + (size_t)st * I8L_STAGE_BYTES;
           unsigned char* sb = sa + I8L_A_BYTES;
-          mbar_expect_tx(&full_b[st], (unsigned)(na_t * I8_KBLOCK + I8_NB * I8L_BN * I8_KB));
-          for (int a = 0; a < na_t; ++a)
-            bulk_load_1d(sa + (size_t)a * I8_KBLOCK, a_src + (size_t)a * plane_a + (size_t)h * I8_KBLOCK, (unsigned)I8_KBLOCK, &full_b[st]);
-          for (int c = 0; c < I8_NB; ++c)
-            bulk_load_1d(sb + (size_t)c * (I8L_BN * I8_KB),
-                         Bd + (((size_t)c * nct128 + (ct >> 1)) * nkb + h) * I8_KBLOCK + (size_t)(ct & 1) * (I8L_BN * I8_KB),
-                         (unsigned)(I8L_BN * I8_KB), &full_b[st]);
+          // TWO copies per stage: a 1-D bulk copy costs ~700 cycles + its bytes and the copies of an SM do not overlap
+          // (tools/ubench/tma_feed.cu) -- with one copy per plane (8 per stage) the kernel was bound by their number
+          mbar_expect_tx(&full_b[st], (unsigned)(na_t * I8_KBLOCK + I8L_B_BYTES));
+          bulk_load_1d(sa, a_src + (size_t)h * na * I8_KBLOCK, (unsigned)(na_t * I8_KBLOCK), &full_b[st]);
+          bulk_load_1d(sb, b_src + (size_t)h * I8L_B_BYTES, (unsigned)I8L_B_BYTES, &full_b[st]);
         }
       }
     }
-  } else if (lane == 0) {
-    // ================= MMA issuer (warp 9, one thread) =================
+  } else if (i8_elect_one()) {
+    // ================= MMA issuer (warp 9, one elected thread) =================
     uint32_t n = 0;
     int itm = 0;
     for (int tile = blockIdx.x; tile < ntiles; tile += gridDim.x, ++itm) {
@@ -527,6 +541,17 @@ int seir_contract_i8_setup(seir_model* m, const double* h_cs /*[Mp][Mp], Cs[j][i
   }
   SEIR_CUDA(cudaMalloc(reinterpret_cast<void**>(&m->d_cs_i8), bd.size()));
   SEIR_CUDA(cudaMemcpy(m->d_cs_i8, bd.data(), bd.size(), cudaMemcpyHostToDevice));
+  {  // the same digits regrouped for the K-outermost kernel: [Mp/64 column tiles][K blocks][6 planes][8 KB half block]
+    const int nkb = Mp / I8_KB, half = I8L_BN * I8_KB;
+    std::vector<signed char> bl(bd.size());
+    for (int c = 0; c < I8_NB; ++c)
+      for (int ct = 0; ct < 2 * nct; ++ct)
+        for (int h = 0; h < nkb; ++h)
+          memcpy(&bl[(((size_t)ct * nkb + h) * I8_NB + c) * half],
+                 &bd[(((size_t)c * nct + (ct >> 1)) * nkb + h) * I8_KBLOCK + (size_t)(ct & 1) * half], (size_t)half);
+    SEIR_CUDA(cudaMalloc(reinterpret_cast<void**>(&m->d_cs_i8l), bl.size()));
+    SEIR_CUDA(cudaMemcpy(m->d_cs_i8l, bl.data(), bl.size(), cudaMemcpyHostToDevice));
+  }
   SEIR_CUDA(cudaMalloc(reinterpret_cast<void**>(&m->d_cs_scale), sizeof(double) * Mp));
   SEIR_CUDA(cudaMemcpy(m->d_cs_scale, scale.data(), sizeof(double) * Mp, cudaMemcpyHostToDevice));
   m->i8_na = na;
@@ -573,9 +598,9 @@ int seir_launch_contract_i8_range(seir_chains* c, cudaStream_t s, seir_range r) 
   int* flags = c->d_i8_flags + 4 * (size_t)rt0;
   const size_t cell0 = (size_t)row0 * m->Mp;
   SEIR_CUDA(cudaMemsetAsync(flags, 0, sizeof(int) * 4 * (size_t)nrt, s));
-  seir_i8_split_kernel<<<dim3(nrt, 4), I8_EPI_THREADS, 0, s>>>(R, m->Mp, m->i8_na, c->d_I + cell0, planes, flags);
+  seir_i8_split_kernel<<<dim3(nrt, 4), I8_EPI_THREADS, 0, s>>>(R, m->Mp, m->i8_na, c->d_I + cell0, planes, flags, longk ? 1 : 0);
   if (longk)
-    seir_contract_i8_longk_kernel<<<ntiles < sms ? ntiles : sms, I8_THREADS, smem, s>>>(R, m->Mp, m->i8_na, ntiles, planes, flags, m->d_cs_i8,
+    seir_contract_i8_longk_kernel<<<ntiles < sms ? ntiles : sms, I8_THREADS, smem, s>>>(R, m->Mp, m->i8_na, ntiles, planes, flags, m->d_cs_i8l,
                                                                                         m->d_cs_scale, c->d_Bc + cell0);
   else
     seir_contract_i8_kernel<<<ntiles < sms ? ntiles : sms, I8_THREADS, smem, s>>>(R, m->Mp, m->i8_na, ntiles, planes, flags, m->d_cs_i8,

@@ -184,7 +184,7 @@ int seir_model_create(const seir_spec* spec, int device, seir_model** out) {
 void seir_model_destroy(seir_model* m) {
   if (!m) return;
   seir_device_guard guard_(m->device);
-  cudaFree(m->d_cs); cudaFree(m->d_cst); cudaFree(m->d_cs_i8); cudaFree(m->d_cs_scale); cudaFree(m->d_rN); cudaFree(m->d_W); cudaFree(m->d_wk); cudaFree(m->d_aidx); cudaFree(m->d_tfirst); cudaFree(m->d_la);
+  cudaFree(m->d_cs); cudaFree(m->d_cst); cudaFree(m->d_cs_i8); cudaFree(m->d_cs_i8l); cudaFree(m->d_cs_scale); cudaFree(m->d_rN); cudaFree(m->d_W); cudaFree(m->d_wk); cudaFree(m->d_aidx); cudaFree(m->d_tfirst); cudaFree(m->d_la);
   cudaFree(m->d_init); cudaFree(m->d_car_indptr); cudaFree(m->d_car_indices); cudaFree(m->d_car_values); cudaFree(m->d_lgtab); cudaFree(m->d_logtab);
   delete m;
 }

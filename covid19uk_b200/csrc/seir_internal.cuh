@@ -39,7 +39,8 @@ struct seir_model {
   double* d_cs;        // [Mp*Mp] zero padded: Cs[j][i] = Cstar[j][i] / N[j]  (Cstar symmetric, model_spec.py:216-219)
   double* d_cst;       // [Mp*Mp] its transpose: Cst[i][j] = Cstar[i][j] / N[j]  (next-generation matrix, analytics.cu)
   double w_last;       // last entry of the commute-volume series (within_between.py evaluates its rates at t = len(W))
-  signed char* d_cs_i8;  // [7][Mp/128][2][128 x Mp/2] int8 digit planes of Cs in UMMA core-matrix layout (contract_i8.cu), or NULL
+  signed char* d_cs_i8;  // [6 planes][Mp/128 column tiles][Mp/128 K blocks][128 columns x 128 B, 128-byte swizzle] int8 digits of Cs (contract_i8.cu), or NULL
+  signed char* d_cs_i8l; // the same digits for the K-outermost kernel: [Mp/64 column tiles][K blocks][6 planes][64 columns x 128 B] (one copy per ring stage)
   double* d_cs_scale;    // [Mp] per-column power-of-two scale of those digits
   int i8_na;             // int8 digit planes of the infectious counts (0: integer path not applicable)
   double* d_rN;        // [Mp] 1/N, 0 in the padding
