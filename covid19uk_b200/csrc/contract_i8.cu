@@ -87,14 +87,6 @@ __device__ __forceinline__ void tc_ld32(uint32_t taddr, uint32_t (&v)[32]) {
         "=r"(v[30]), "=r"(v[31])
       : "r"(taddr));
 }
-// One lane of a fully active warp.  The MMA issuer and the copy producer must be chosen THIS way: behind `if (lane == 0)` the
-// compiler treats the branch as divergent and wraps every tcgen05.mma / bulk copy (uniform-datapath instructions) in an
-// ELECT / BRA.U.ANY loop over the active lanes -- eight extra instructions and a backward branch per MMA.
-__device__ __forceinline__ bool i8_elect_one() {
-  uint32_t p;
-  asm volatile("{\n\t.reg .pred P;\n\telect.sync _|P, 0xffffffff;\n\tselp.u32 %0, 1, 0, P;\n\t}" : "=r"(p));
-  return p != 0;
-}
 __device__ __forceinline__ void tc_wait_ld() { asm volatile("tcgen05.wait::ld.sync.aligned;" ::: "memory"); }
 
 // K-major, 128-byte swizzle (cute::UMMA::SmemDescriptor bit layout; layout type SWIZZLE_128B = 2): an operand block is
@@ -269,7 +261,7 @@ __global__ void __launch_bounds__(I8_THREADS, 1) seir_contract_i8_kernel(long lo
     }
   } else if (warp == 8) {
     // ================= producer: planes of Cs =================
-    if (i8_elect_one()) {
+    if (seir_elect_one()) {
       uint32_t n = 0, itp = 0;
       for (int tile = blockIdx.x; tile < ntiles; tile += gridDim.x, ++itp) {
         const int rb = tile / ncol_tiles, ct = tile - rb * ncol_tiles;
@@ -299,7 +291,7 @@ __global__ void __launch_bounds__(I8_THREADS, 1) seir_contract_i8_kernel(long lo
           }
       }
     }
-  } else if (i8_elect_one()) {
+  } else if (seir_elect_one()) {
     // ================= MMA issuer (warp 9, one elected thread) =================
     uint32_t n = 0, ph_aready = 0;
     uint32_t hosted[4] = {0, 0, 0, 0};  // groups started in each accumulator slot so far (over all tiles)
@@ -444,7 +436,7 @@ __global__ void __launch_bounds__(I8_THREADS, 1) seir_contract_i8_longk_kernel(l
     }
   } else if (warp == 8) {
     // ================= producer =================
-    if (i8_elect_one()) {
+    if (seir_elect_one()) {
       uint32_t n = 0;
       for (int tile = blockIdx.x; tile < ntiles; tile += gridDim.x) {
         const int rb = tile / ncol_tiles, ct = tile - rb * ncol_tiles;
@@ -466,7 +458,7 @@ __global__ void __launch_bounds__(I8_THREADS, 1) seir_contract_i8_longk_kernel(l
         }
       }
     }
-  } else if (i8_elect_one()) {
+  } else if (seir_elect_one()) {
     // ================= MMA issuer (warp 9, one elected thread) =================
     uint32_t n = 0;
     int itm = 0;

@@ -263,7 +263,7 @@ __global__ void __launch_bounds__(NTHR + 32, NTHR >= 384 ? (GRAD ? 2 : 3) : 1) s
 #pragma unroll
   for (int q = 0; q < MPT; ++q) row[q] = 0.0;
   if (producer) {
-    if (lane == 0) {
+    if (seir_elect_one()) {  // (not `lane == 0`: tma.cuh)
       for (int g = 0; g < ngroups; ++g) {
         const int st = g % NSTAGE;
         if (g >= NSTAGE) mbar_wait(&empty[st], (unsigned)((g / NSTAGE - 1) & 1));

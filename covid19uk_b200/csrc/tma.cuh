@@ -31,3 +31,13 @@ __device__ __forceinline__ void mbar_arrive(uint64_t* bar) {
   asm volatile("mbarrier.arrive.shared::cta.b64 _, [%0];" ::"r"(smem_u32(bar)) : "memory");
 }
 
+
+// One lane of a fully active warp (elect.sync).  Producers of bulk copies and issuers of tcgen05.mma must be chosen THIS way:
+// behind `if (lane == 0)` the compiler treats the branch as divergent and wraps every uniform-datapath instruction
+// (UBLKCP, UTCIMMA, ...) in an ELECT / BRA.U.ANY loop over the active lanes -- several extra instructions and a backward
+// branch per copy / MMA (cuobjdump -sass; contract_i8.cu: 116 -> 100 cycles per MMA step).
+__device__ __forceinline__ bool seir_elect_one() {
+  unsigned p;
+  asm volatile("{\n\t.reg .pred P;\n\telect.sync _|P, 0xffffffff;\n\tselp.u32 %0, 1, 0, P;\n\t}" : "=r"(p));
+  return p != 0;
+}
