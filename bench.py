@@ -513,6 +513,10 @@ def run_native(args):
                     "unit": dom["unit"], "frac": dom["frac"], "traffic": tr,
                     "traffic_unit": f"dram bytes per launch (ncu --set full, profiles/{src})", "share_of_step": dom["ms"] / cold_sum,
                     "peak_source": (peak_src if dom["bound"] == "hbm" else dom.get("peak_source", ""))}
+        if dom["bound"] == "hbm" and tr:
+            # `achieved` = ALGORITHMIC bytes / time; `frac` prices the kernel's ACTUAL dram traffic against the peak
+            roofline.update(frac_algorithmic=dom.get("frac_algorithmic"), achieved_actual=tr / (dom["ms"] * 1e-3) / 1e9,
+                            note="frac = actual dram bytes (ncu) / time / peak; frac_algorithmic = achieved / peak")
         warm_grad = hbm_entry(names[4], stage_ms[4], alg_bytes[4])
         warm_ms = stage_ms[2] + stage_ms[3] + stage_ms[5]
         line = {
