@@ -562,7 +562,7 @@ def main():
     ap.add_argument("--warmup", type=int, default=3)
     ap.add_argument("--impl", default="native", choices=["native", "reference"])
     ap.add_argument("--chains", type=int, default=256, help="chains per GPU")
-    ap.add_argument("--sweeps", type=int, default=50, help="MCMC sweeps per timed burst (the reference's num_burst_samples is 100, example_config.yaml:32)")
+    ap.add_argument("--sweeps", type=int, default=100, help="MCMC sweeps per timed burst (= the reference's num_burst_samples, example_config.yaml:32)")
     ap.add_argument("--sweep-step-size", type=float, default=2e-5)
     ap.add_argument("--tuned-dmax", type=int, default=16, help="event-time proposals of the second sweeps/s figure")
     ap.add_argument("--tuned-nmax", type=int, default=16)
