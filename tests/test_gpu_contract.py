@@ -11,7 +11,7 @@ pytestmark = pytest.mark.gpu
 
 
 # (M > 384: the long-K kernel -- K blocks outermost, 128 x 64 tiles, eight accumulator groups live in TMEM)
-@pytest.mark.parametrize("M,T,B", [(382, 84, 5), (382, 84, 64), (250, 33, 7), (128, 20, 3), (500, 40, 6), (640, 21, 13), (1000, 12, 3)])
+@pytest.mark.parametrize("M,T,B", [(382, 84, 5), (382, 84, 64), (250, 33, 7), (128, 20, 3), (500, 40, 6), (640, 21, 13), (1000, 12, 3), (2000, 9, 2)])
 def test_int8_contraction_matches_fp64(M, T, B):
     import torch
     from covid19uk_b200 import synthetic as syn
