@@ -496,6 +496,173 @@ __global__ void __launch_bounds__(I8_THREADS, 1) seir_contract_i8_longk_kernel(l
   if (warp == 9) asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, %1;" ::"r"(tmem_base), "r"(512u) : "memory");
 }
 
+// ---- long K, 128 x 128 tiles in TWO passes over K ---------------------------------------------------------------------
+// The K-outermost kernel above delivers operands at ~55 B/clk: an N = 64 instruction reads 4 KB of I for 2 KB of Cs.  With
+// N = 128 the same bytes of I serve twice the columns, but eight live groups of 128 columns do not fit the 512 TMEM columns --
+// so the groups are split: pass 0 accumulates the four most significant groups s in [s_top - 3, s_top] (digit planes 0..3 of
+// Cs), pass 1 the rest (planes 4 - s_top .. 5), each pass a full sweep over the K blocks with four 128-column accumulators.
+// The planes of I are fetched twice (L2), every digit pair is still multiplied once: -25 % operand bytes per MAC.  Used where
+// the tile count does not quantise (Mp > 384: thousands of tiles per SM); at the UK size 504 tiles are 3.4 rounds that cost 4.
+#define I8T_A_BYTES (3 * I8_KBLOCK)
+#define I8T_B_BYTES (4 * I8_KBLOCK)
+#define I8T_STAGE_BYTES (I8T_A_BYTES + I8T_B_BYTES)
+#define I8T_STAGES 2
+
+__global__ void __launch_bounds__(I8_THREADS, 1) seir_contract_i8_twopass_kernel(long long R, int Mp, int na, int ntiles,
+                                                                                 const unsigned char* __restrict__ planes,
+                                                                                 const int* __restrict__ flags,
+                                                                                 const signed char* __restrict__ Bd,
+                                                                                 const double* __restrict__ colscale, double* __restrict__ Bc) {
+  extern __shared__ __align__(1024) unsigned char smem[];
+  __shared__ uint64_t full_b[I8T_STAGES], empty_b[I8T_STAGES], acc_full, acc_free;
+  __shared__ uint32_t tmem_base_s;
+  const int nkb = Mp / I8_KB;
+  const size_t plane_a = (size_t)I8_BM * Mp;
+  const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
+  const int ncol_tiles = Mp / I8_BN;
+  if (tid == 0) {
+    for (int s = 0; s < I8T_STAGES; ++s) { mbar_init(&full_b[s], 1); mbar_init(&empty_b[s], 1); }
+    mbar_init(&acc_full, 1);                      // the commit behind a pass's last MMA
+    mbar_init(&acc_free, I8_EPI_THREADS / 32);   // every epilogue warp has read the pass's accumulators
+    asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+  }
+  if (warp == 9) {
+    asm volatile("tcgen05.alloc.cta_group::1.sync.aligned.shared::cta.b32 [%0], %1;" ::"r"(smem_u32(&tmem_base_s)), "r"(512u) : "memory");
+    asm volatile("tcgen05.relinquish_alloc_permit.cta_group::1.sync.aligned;" ::: "memory");
+  }
+  tc_fence_before();
+  __syncthreads();
+  tc_fence_after();
+  const uint32_t tmem_base = tmem_base_s;
+  // pass p of a tile with na_t planes: groups s in [s_lo, s_hi], digit planes of Cs c in [c_lo, c_hi]
+  auto pass_range = [](int na_t, int p, int& s_lo, int& s_hi, int& c_lo, int& c_hi) {
+    const int s_top = na_t - 1;
+    if (p == 0) { s_hi = s_top; s_lo = s_top - 3; c_lo = 0; c_hi = 3; }
+    else { s_hi = s_top - 4; s_lo = -(I8_NB - 1); c_lo = 4 - s_top; c_hi = I8_NB - 1; }
+  };
+
+  if (warp < 8) {
+    // ================= epilogue =================
+    const int half = warp >> 2;             // which 64 of the tile's 128 columns this warp drains
+    const int lane_base = (warp & 3) * 32;  // TMEM lanes (= tile rows) this warp may access
+    uint32_t npass = 0;
+    for (int tile = blockIdx.x; tile < ntiles; tile += gridDim.x) {
+      const int rb = tile / ncol_tiles, ct = tile - rb * ncol_tiles;
+      const long long r0 = (long long)rb * I8_BM;
+      int na_t = 1;
+      for (int a = 1; a < na; ++a)
+        if (__ldg(flags + rb * 4 + a)) na_t = a + 1;
+      double out[64];
+#pragma unroll
+      for (int j = 0; j < 64; ++j) out[j] = 0.0;
+      for (int p = 0; p < 2; ++p, ++npass) {
+        int s_lo, s_hi, c_lo, c_hi;
+        pass_range(na_t, p, s_lo, s_hi, c_lo, c_hi);
+        mbar_wait(&acc_full, npass & 1u);
+        tc_fence_after();
+        for (int s = s_hi; s >= s_lo; --s) {  // (most significant group first over both passes: the order of the other kernels)
+          const double w = ldexp(1.0, 8 * (s - 1));  // 256^(s-1), exact
+          const uint32_t taddr = tmem_base + ((uint32_t)lane_base << 16) + (uint32_t)((s_hi - s) * I8_BN + half * 64);
+          uint32_t v0[32], v1[32];
+          tc_ld32(taddr, v0);
+          tc_ld32(taddr + 32u, v1);
+          tc_wait_ld();
+#pragma unroll
+          for (int j = 0; j < 32; ++j) {
+            out[j] = fma(i8_int_to_double((int)v0[j]), w, out[j]);
+            out[32 + j] = fma(i8_int_to_double((int)v1[j]), w, out[32 + j]);
+          }
+        }
+        tc_fence_before();
+        __syncwarp();
+        if (lane == 0) mbar_arrive(&acc_free);  // the next pass may overwrite the accumulators
+      }
+      const int c0 = ct * I8_BN + half * 64;
+      const long long row = r0 + lane_base + lane;
+      if (row < R) {
+        double* dst = Bc + row * Mp + c0;
+#pragma unroll
+        for (int j = 0; j < 64; j += 4) {
+          const double x0 = out[j] * colscale[c0 + j], x1 = out[j + 1] * colscale[c0 + j + 1], x2 = out[j + 2] * colscale[c0 + j + 2],
+                       x3 = out[j + 3] * colscale[c0 + j + 3];
+          asm volatile("st.global.v4.f64 [%0], {%1, %2, %3, %4};" ::"l"(dst + j), "d"(x0), "d"(x1), "d"(x2), "d"(x3) : "memory");
+        }
+      }
+    }
+  } else if (warp == 8) {
+    // ================= producer =================
+    if (seir_elect_one()) {
+      uint32_t n = 0;
+      const int nct = Mp / I8_BN;
+      for (int tile = blockIdx.x; tile < ntiles; tile += gridDim.x) {
+        const int rb = tile / ncol_tiles, ct = tile - rb * ncol_tiles;
+        int na_t = 1;
+        for (int a = 1; a < na; ++a)
+          if (__ldg(flags + rb * 4 + a)) na_t = a + 1;
+        const unsigned char* a_src = planes + (size_t)rb * na * plane_a;  // [K block][plane][16 KB] (seir_i8_split_kernel, kmajor)
+        for (int p = 0; p < 2; ++p) {
+          int s_lo, s_hi, c_lo, c_hi;
+          pass_range(na_t, p, s_lo, s_hi, c_lo, c_hi);
+          const int nc = c_hi - c_lo + 1;
+          for (int h = 0; h < nkb; ++h, ++n) {
+            const int st = n % I8T_STAGES;
+            if (n >= I8T_STAGES) mbar_wait(&empty_b[st], ((n / I8T_STAGES) - 1) & 1u);
+            unsigned char* sa = smem + (size_t)st * I8T_STAGE_BYTES;
+            unsigned char* sb = sa + I8T_A_BYTES;
+            mbar_expect_tx(&full_b[st], (unsigned)((na_t + nc) * I8_KBLOCK));
+            bulk_load_1d(sa, a_src + (size_t)h * na * I8_KBLOCK, (unsigned)(na_t * I8_KBLOCK), &full_b[st]);
+            for (int c = 0; c < nc; ++c)  // plane-major host layout [plane][column tile][K block][16 KB]
+              bulk_load_1d(sb + (size_t)c * I8_KBLOCK, Bd + (((size_t)(c_lo + c) * nct + ct) * nkb + h) * I8_KBLOCK, (unsigned)I8_KBLOCK, &full_b[st]);
+          }
+        }
+      }
+    }
+  } else if (seir_elect_one()) {
+    // ================= MMA issuer (warp 9, one elected thread) =================
+    uint32_t n = 0, npass = 0;
+    for (int tile = blockIdx.x; tile < ntiles; tile += gridDim.x) {
+      int na_t = 1;
+      for (int a = 1; a < na; ++a)
+        if (__ldg(flags + (tile / ncol_tiles) * 4 + a)) na_t = a + 1;
+      for (int p = 0; p < 2; ++p, ++npass) {
+        int s_lo, s_hi, c_lo, c_hi;
+        pass_range(na_t, p, s_lo, s_hi, c_lo, c_hi);
+        if (npass > 0) {  // the epilogue has drained the previous pass
+          mbar_wait(&acc_free, (npass - 1) & 1u);
+          tc_fence_after();
+        }
+        uint32_t started = 0;  // groups of this pass that have received their first digit pair
+        for (int h = 0; h < nkb; ++h, ++n) {
+          const int st = n % I8T_STAGES;
+          mbar_wait(&full_b[st], (n / I8T_STAGES) & 1u);
+          tc_fence_after();
+          const uint32_t sa = smem_u32(smem + (size_t)st * I8T_STAGE_BYTES), sb = sa + I8T_A_BYTES;
+          for (int c = c_lo; c <= c_hi; ++c) {
+            const uint64_t b_desc0 = umma_desc(sb + (uint32_t)(c - c_lo) * I8_KBLOCK);
+            for (int a = 0; a < na_t; ++a) {
+              const int s = a - c;
+              if (s < s_lo || s > s_hi) continue;  // the other pass's group
+              const uint32_t slot = (uint32_t)(s_hi - s);
+              const uint64_t a_desc0 = umma_desc(sa + (uint32_t)a * I8_KBLOCK);
+              const uint32_t d_addr = tmem_base + slot * I8_BN;
+              const bool first = !((started >> slot) & 1u);
+              started |= 1u << slot;
+              tc_mma_i8(d_addr, a_desc0, b_desc0, I8_IDESC, first ? 0u : 1u);
+#pragma unroll
+              for (int kk = 1; kk < I8_KB / 32; ++kk) tc_mma_i8(d_addr, a_desc0 + (uint64_t)kk * 2u, b_desc0 + (uint64_t)kk * 2u, I8_IDESC, 1u);
+            }
+          }
+          tc_commit(&empty_b[st]);  // the stage is free once these MMAs have read it
+        }
+        tc_commit(&acc_full);
+      }
+    }
+  }
+  tc_fence_before();
+  __syncthreads();
+  if (warp == 9) asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, %1;" ::"r"(tmem_base), "r"(512u) : "memory");
+}
+
 // ---- host: split Cs into digit planes, once per model --------------------------------------------------------------
 // Returns 0 and fills the device arrays when the integer path applies (Mp a multiple of 128, at most 4096, populations
 // below 2^24), 1 when it does not (the FP64 DMMA kernel of contract.cu is used), < 0 on a CUDA error.
@@ -565,18 +732,26 @@ int seir_launch_contract_i8_range(seir_chains* c, cudaStream_t s, seir_range r) 
   // the K-outermost kernel is the default for every shape: UK, 256 chains 62 us against 86 us (every operand byte fetched once,
   // 7 rounds of 1008 half-width tiles instead of 4 rounds of 504)
   const bool longk = m->Mp > 384 || force_longk > 0;
-  const int ntiles = (int)((R + I8_BM - 1) / I8_BM) * (m->Mp / (longk ? I8L_BN : I8_BN));
+  static int use_twopass = -1;
+  if (use_twopass < 0) {
+    const char* e = getenv("SEIR_I8_TWOPASS");  // 0: the single-pass 128 x 64 kernel also for long K (A/B timing; same results)
+    use_twopass = e ? atoi(e) : 1;
+  }
+  const bool twopass = m->Mp > 384 && use_twopass > 0;
+  const int ntiles = (int)((R + I8_BM - 1) / I8_BM) * (m->Mp / ((longk && !twopass) ? I8L_BN : I8_BN));
   size_t a_region = (size_t)m->i8_na * I8_BM * m->Mp;
 #if I8_STAGE_OUT > 0
   if (a_region < (size_t)I8_STAGE_OUT) a_region = I8_STAGE_OUT;
 #endif
-  const size_t smem = longk ? (size_t)I8L_STAGES * I8L_STAGE_BYTES + 1024
-                            : a_region + (size_t)I8_STAGES * I8_KBLOCK + 1024;  // (+ slack to align the dynamic base to 1024 bytes)
+  const size_t smem = twopass ? (size_t)I8T_STAGES * I8T_STAGE_BYTES + 1024
+                     : longk  ? (size_t)I8L_STAGES * I8L_STAGE_BYTES + 1024
+                              : a_region + (size_t)I8_STAGES * I8_KBLOCK + 1024;  // (+ slack to align the dynamic base to 1024 bytes)
   const int sms = m->sms;
-  static size_t attr_dev[SEIR_MAX_DEVICES][2] = {{0}};  // (the opt-in is per device)
-  size_t& attr = attr_dev[c->model->device % SEIR_MAX_DEVICES][longk ? 1 : 0];
+  static size_t attr_dev[SEIR_MAX_DEVICES][3] = {{0}};  // (the opt-in is per device)
+  size_t& attr = attr_dev[c->model->device % SEIR_MAX_DEVICES][twopass ? 2 : (longk ? 1 : 0)];
   if (attr != smem) {
-    if (longk) SEIR_CUDA(cudaFuncSetAttribute(seir_contract_i8_longk_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+    if (twopass) SEIR_CUDA(cudaFuncSetAttribute(seir_contract_i8_twopass_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+    else if (longk) SEIR_CUDA(cudaFuncSetAttribute(seir_contract_i8_longk_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
     else SEIR_CUDA(cudaFuncSetAttribute(seir_contract_i8_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
     attr = smem;
   }
@@ -591,7 +766,10 @@ int seir_launch_contract_i8_range(seir_chains* c, cudaStream_t s, seir_range r) 
   const size_t cell0 = (size_t)row0 * m->Mp;
   SEIR_CUDA(cudaMemsetAsync(flags, 0, sizeof(int) * 4 * (size_t)nrt, s));
   seir_i8_split_kernel<<<dim3(nrt, 4), I8_EPI_THREADS, 0, s>>>(R, m->Mp, m->i8_na, c->d_I + cell0, planes, flags, longk ? 1 : 0);
-  if (longk)
+  if (twopass)
+    seir_contract_i8_twopass_kernel<<<ntiles < sms ? ntiles : sms, I8_THREADS, smem, s>>>(R, m->Mp, m->i8_na, ntiles, planes, flags, m->d_cs_i8,
+                                                                                          m->d_cs_scale, c->d_Bc + cell0);
+  else if (longk)
     seir_contract_i8_longk_kernel<<<ntiles < sms ? ntiles : sms, I8_THREADS, smem, s>>>(R, m->Mp, m->i8_na, ntiles, planes, flags, m->d_cs_i8l,
                                                                                         m->d_cs_scale, c->d_Bc + cell0);
   else
