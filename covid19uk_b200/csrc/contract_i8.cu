@@ -481,6 +481,8 @@ __global__ void __launch_bounds__(I8_THREADS, 1) seir_contract_i8_longk_kernel(l
             const uint64_t a_desc0 = umma_desc(sa + (uint32_t)a * I8_KBLOCK);
             const uint32_t d_addr = tmem_base + (uint32_t)((a - c + I8_NB - 1) * I8L_BN);
             const bool first = h == 0 && (c == 0 || a == 0);  // group a - c receives its first digit pair
+            // (instruction order, measured at the UK size: these runs of 4 K steps per digit pair 71.6 us; all pairs of a group back to
+            //  back, runs of up to 12, 72.5 us; K step outermost, a different accumulator group with every instruction, 87.8 us)
             tc_mma_i8(d_addr, a_desc0, b_desc0, I8L_IDESC, first ? 0u : 1u);
 #pragma unroll
             for (int kk = 1; kk < I8_KB / 32; ++kk) tc_mma_i8(d_addr, a_desc0 + (uint64_t)kk * 2u, b_desc0 + (uint64_t)kk * 2u, I8L_IDESC, 1u);
